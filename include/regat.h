@@ -1,0 +1,272 @@
+/* regat.h -- C ABI of libregat.so: the B200 (sm_100a) implementation of ReGAT's
+ * implicit-relation graph-attention + BUTD-fusion hot path.
+ *
+ * The reference (jhss/TF_VQA_ReGAT) has no FFI; its boundary for this path is the tf.keras
+ * layer API.  Each entry point below names the reference code it stands in for
+ * (file:line under the reference tree).  INTEGRATION.md shows the ctypes / TF-DLPack
+ * binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; row-major, contiguous;
+ *   - `dtype` is the storage type of activations: REGAT_F32 or REGAT_BF16 (fp32 accumulate);
+ *     parameters, optimizer state, weight gradients, logits and the loss are always fp32;
+ *   - tensors are BORROWED for the duration of the call; the library never allocates or
+ *     frees caller memory and keeps no reference to it (engine_bind excepted: it keeps
+ *     the pointers until the next bind/destroy);
+ *   - every call is asynchronous on `stream` (a cudaStream_t) and performs no hidden sync;
+ *   - return value: 0 = ok, negative = regat_status; message via regat_last_error()
+ *     (thread-local).  No exception or abort crosses this boundary;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry returns
+ *     REGAT_ERR_CUDA.
+ */
+#ifndef REGAT_H_
+#define REGAT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REGAT_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define REGAT_API __attribute__((visibility("default")))
+#else
+#define REGAT_API
+#endif
+
+typedef void* regat_stream_t; /* cudaStream_t */
+
+typedef enum regat_status {
+  REGAT_OK = 0,
+  REGAT_ERR_ARG = -1,         /* null pointer / bad enum */
+  REGAT_ERR_SHAPE = -2,       /* unsupported or inconsistent shape */
+  REGAT_ERR_DTYPE = -3,
+  REGAT_ERR_DEVICE = -4,      /* DLPack tensor not on the current CUDA device */
+  REGAT_ERR_ALIGN = -5,       /* pointer / leading dimension not 16-byte aligned */
+  REGAT_ERR_CUDA = -6,        /* CUDA runtime / driver error (incl. no device) */
+  REGAT_ERR_UNSUPPORTED = -7,
+  REGAT_ERR_WORKSPACE = -8    /* caller-provided buffer too small */
+} regat_status;
+
+typedef enum regat_dtype { REGAT_F32 = 0, REGAT_BF16 = 1 } regat_dtype;
+
+/* Hyper-parameters of the path.  Defaults = reference config/butd_vqa.json:1-29. */
+typedef struct regat_config {
+  int32_t v_dim;        /* 2048  region feature dim                                   */
+  int32_t q_dim;        /* 768   num_hid: question dim = BUTD hidden                  */
+  int32_t rel_dim;      /* 1024  relation_dim                                         */
+  int32_t num_heads;    /* 16    (head dim rel_dim/num_heads must be 64)              */
+  int32_t pos_emb_dim;  /* 64    imp_pos_emb_dim                                      */
+  int32_t nongt_dim;    /* 20                                                        */
+  int32_t dir_num;      /* 2                                                         */
+  int32_t num_answers;  /* 3129                                                      */
+  int32_t label_bias;   /* 0     graph_att_net.py:25 use_bias of the label FC         */
+  int32_t residual;     /* 1     relation_encoder.py:88-91                            */
+  float grad_clip;      /* 0.25  per-tensor clip_by_norm, train.py:112 / main.py:24   */
+  float beta1, beta2, eps; /* Adamax 0.9, 0.999, 1e-8, train.py:48                    */
+} regat_config;
+
+REGAT_API int regat_abi_version(void);
+/* Copies the calling thread's last error message (NUL-terminated) into buf; returns its length. */
+REGAT_API int regat_last_error(char* buf, size_t n);
+/* Fills cfg with the reference defaults above. */
+REGAT_API int regat_default_config(regat_config* cfg);
+/* Number of CUDA devices visible (0 on a CPU-only box); never fails. */
+REGAT_API int regat_device_count(void);
+
+/* ------------------------------------------------------------------ stage 1 ----------
+ * Materialised position embedding, the drop-in for
+ * position_emb.py:153-160 prepare_graph_variables (-> :117-151, :96-115):
+ *   boxes [B,N,4] fp32 abs-pixel (x1,y1,x2,y2)  ->  pos_emb [B,M,N,feat_dim] fp32,
+ *   M = min(nongt_dim, N).  wave_div_host: feat_dim/8 fp32 divisors 1000^(8k/feat_dim)
+ *   computed by the HOST binding in fp32 exactly as position_emb.py:98-100 does.
+ * The fused attention kernel never needs this tensor; it exists for callers that want the
+ * reference's array (compat path) and for parity tests of the geometry code.            */
+REGAT_API int regat_position_embedding(const float* boxes, int B, int N, int nongt_dim, int feat_dim,
+                             const float* wave_div_host, float* pos_emb, regat_stream_t stream);
+
+/* ------------------------------------------------------------------ weight norm -------
+ * weight_norm.py:35-41: W = g * v / sqrt(max(sum v^2, 1e-12)), scalar g, whole-tensor norm.
+ * Because the norm is a scalar, W = alpha*v; GEMMs read v and scale by alpha in their epilogue.
+ *   sumsq[l] += sum(v_l^2) for each of n_layers tensors (caller zeroes sumsq);
+ *   v_lowp (optional, bf16): a bf16 copy of each v with leading dimension ld_lowp[l]
+ *   (>= cols, multiple of 8) at element offset off_lowp[l].
+ * descriptors are HOST arrays of length n_layers.                                       */
+REGAT_API int regat_wn_prepare(const float* params, const int64_t* v_off_host, const int64_t* v_numel_host,
+                     const int32_t* v_cols_host, int n_layers, float* sumsq,
+                     void* v_lowp, const int64_t* off_lowp_host, const int32_t* ld_lowp_host,
+                     regat_stream_t stream);
+/* alpha[l] = g_l * rsqrt(max(sumsq[l], 1e-12)); inv_norm[l] = rsqrt(max(sumsq[l],1e-12)). */
+REGAT_API int regat_wn_alpha(const float* params, const int64_t* g_off_host, int n_layers, const float* sumsq,
+                   float* alpha, float* inv_norm, regat_stream_t stream);
+
+/* ------------------------------------------------------------------ dense (fc.py:11-50) --
+ * C[M,N] = epilogue( op(A)[M,K] . op(B)[K,N] ), fp32 accumulate.
+ *   transA = 0: A stored [M,K] (lda >= K);  1: A stored [K,M] (lda >= M)
+ *   transB = 0: B stored [K,N] (ldb >= N);  1: B stored [N,K] (ldb >= K)
+ * REGAT_F32 runs an exact-fp32 SIMT kernel (parity mode); REGAT_BF16 runs the TMA + tcgen05
+ * kernel (A, B bf16).  Epilogue, applied per element x = acc in this order:
+ *   x += row_scale[r] * addend[(r / addend_rows) * addend_ld + c]   (if addend)
+ *   x *= alpha[c / alpha_cols]    (alpha_cols == 0: alpha[0]; alpha == NULL: 1)
+ *   x += bias[c]                  (if bias)
+ *   x  = max(x, 0)                (if relu)
+ *   x += C_old[r,c]               (if accumulate)
+ *   x  = gate[r,c] > 0 ? x : 0    (if gate; same dtype/ld as given)
+ *   C[r,c] = x                    (dtype c_dtype: REGAT_F32 or the activation dtype)
+ *   C2[(r / c2_rows_in) * c2_rows_keep + r % c2_rows_in, c] = x  if r % c2_rows_in < c2_rows_keep
+ * split_k > 1 (bf16 path, c_dtype F32, no epilogue but alpha): partial sums are atomically
+ * added into C, which the caller has zeroed or wants accumulated into.                   */
+typedef struct regat_epilogue {
+  const float* alpha; int32_t alpha_cols;
+  const float* bias;
+  const float* addend; int32_t addend_ld; int32_t addend_rows; const float* row_scale;
+  int32_t relu;
+  int32_t accumulate;
+  const void* gate; int32_t gate_ld;
+  void* c2; int32_t c2_ld; int32_t c2_rows_in; int32_t c2_rows_keep;
+  int32_t split_k;
+} regat_epilogue;
+
+REGAT_API int regat_gemm(int dtype, int transA, int transB, int M, int N, int K,
+               const void* A, int lda, const void* B, int ldb,
+               void* C, int ldc, int c_dtype, const regat_epilogue* epi, regat_stream_t stream);
+
+/* ------------------------------------------------------------------ kernel (a) ---------
+ * Fused geometry-bias graph attention, forward.  Replaces, for all dir_num directions and all
+ * heads of one GraphAttentionNetwork call: position_emb.py:96-151 (geometry + sinusoid),
+ * graph_att_layer.py:63-111 (logits, pair_pos_fc bias, relu/max/log, adjacency where (a no-op
+ * for the implicit relation, relation_encoder.py:76), label bias, softmax over the first
+ * M = min(nongt_dim, N) objects, aggregation), the grouped 1x1 conv graph_att_layer.py:112-117
+ * (re-associated into V' = s[:, :M] . Kc + bc, computed by regat_gemm beforehand), the sum
+ * over directions + ReLU graph_att_net.py:64-81, and the residual relation_encoder.py:88-91.
+ *
+ *   q     [B*N, dirs*D]   : Q_d at column d*D                         (activation dtype)
+ *   kv    [B*M, 2*dirs*D] : K_d at column d*D, V'_d at (dirs+d)*D
+ *   boxes [B,N,4] fp32, or pos_emb [B,M,N,E] fp32 (exactly one non-NULL)
+ *   wg    : dirs pointers' worth of pair_pos_fc: v [dirs][E,H] fp32 raw kernels (contiguous per
+ *           dir at wg + d*wg_stride), alpha_g [dirs], bg [dirs][H] (at bg + d*bg_stride)
+ *   label_c : device scalar c = WN(label FC)(1) (+bias)  (graph_att_net.py:71)
+ *   s, v0 [B*N, D] ; out v1 [B*N, D] = (residual ? v0 : 0) + relu(s + sum_d O_d)
+ *   save_p, save_gbias [B,dirs,H,N,M] fp32 and gate [B*N, H] uint64 (bit e of word (row,h) set
+ *   iff relu input > 0) are written when non-NULL (training).
+ * Head dim must be 64; N <= 128; 16*M*dirs*H*4 bytes must fit in shared memory.          */
+REGAT_API int regat_geoattn_fwd(int dtype, int B, int N, int nongt_dim, int D, int H, int dirs, int E,
+                      const void* q, const void* kv, const float* boxes, const float* pos_emb,
+                      const float* wave_div_host,
+                      const float* wg, int64_t wg_stride, const float* alpha_g,
+                      const float* bg, int64_t bg_stride, const float* label_c,
+                      const void* s, const void* v0, int residual, void* v1,
+                      float* save_p, float* save_gbias, uint64_t* gate, regat_stream_t stream);
+
+/* Backward of the attention part.  Consumes dv1 [B*N,D] (gradient w.r.t. the encoder output),
+ * the saved P / gbias / gate, Q and KV; produces
+ *   dq [B*N, dirs*D], dkv [B*M, 2*dirs*D]  (activation dtype),
+ *   dout [B*N, D] = dv1 * gate  (the gradient of relu's input: the direct `s` term),
+ *   and overwrites save_p in place with dL (gradient w.r.t. the logits), which
+ *   regat_geo_bwd then reduces.                                                           */
+REGAT_API int regat_attn_bwd(int dtype, int B, int N, int nongt_dim, int D, int H, int dirs,
+                   const void* q, const void* kv, const void* dv1, const uint64_t* gate,
+                   float* p_inout_dl, void* dq, void* dkv, void* dout, regat_stream_t stream);
+
+/* Backward of the geometry bias: recomputes Emb(i',j') from the boxes (never stored) and reduces
+ *   dWg[d][e][h] += sum Emb * dz,  dbg[d][h] += sum dz,  dc += sum dL
+ * with dz = dL / z where z = exp(gbias) >= 1e-6 (graph_att_layer.py:79-88), else 0.
+ * dwg receives the gradient w.r.t. the EFFECTIVE kernel W = alpha*v (same layout as wg).  */
+REGAT_API int regat_geo_bwd(int B, int N, int nongt_dim, int H, int dirs, int E,
+                  const float* boxes, const float* pos_emb, const float* wave_div_host,
+                  const float* dl, const float* gbias,
+                  float* dwg, int64_t dwg_stride, float* dbg, int64_t dbg_stride, float* dc,
+                  regat_stream_t stream);
+
+/* ------------------------------------------------------------------ BUTD pooling --------
+ * fusion.py:43-54 + :34 with the (linear) v2attention FC re-associated:
+ *   logit[b,n] = <v1[b,n,:], weff[b,:]> + cb[b];  att = softmax_n;  pooled[b,:] = sum_n att*v1.
+ * weff [B,D] and cb [B] are produced by regat_gemm / regat_rowdot from q2attention and linear. */
+REGAT_API int regat_butd_pool_fwd(int dtype, int B, int N, int D, const void* v1, const void* weff,
+                        const float* cb, float* att, void* pooled, regat_stream_t stream);
+/* dv1[b,n,:] = att*dpooled + dlogit*weff ; dweff[b,:] = sum_n dlogit*v1 ; dcb[b] = sum_n dlogit */
+REGAT_API int regat_butd_pool_bwd(int dtype, int B, int N, int D, const void* v1, const void* weff,
+                        const float* att, const void* dpooled, void* dv1, void* dweff, float* dcb,
+                        regat_stream_t stream);
+
+/* ------------------------------------------------------------------ loss (train.py:20-26,107-108)
+ * loss = A * mean_{b,a} BCEwithlogits(logits, target) (added into *loss, caller zeroes);
+ * dlogits = (sigmoid(x) - z) / B, written with leading dim ld_d in dtype d_dtype (padding
+ * columns zeroed).  score (optional) += sum_b target[b, argmax_a logits[b,:]]  (train.py:28-39). */
+REGAT_API int regat_bce_fwd_bwd(int B, int A, const float* logits, int ld_logits, const float* target,
+                      float* loss, float* score, void* dlogits, int ld_d, int d_dtype,
+                      regat_stream_t stream);
+
+/* ------------------------------------------------------------------ engine --------------
+ * The whole hot path of rel_graph_net.py:53-62 (+ train.py:103-113) as one call sequence on
+ * one stream with static buffers (CUDA-graph capturable).                                 */
+typedef struct regat_engine regat_engine;
+
+REGAT_API int regat_engine_create(const regat_config* cfg, int dtype, int max_batch, int max_rois,
+                        regat_engine** out);
+REGAT_API int regat_engine_destroy(regat_engine* e);
+/* Element counts of the flat fp32 parameter buffer (same for grads and each Adamax slot) and
+ * byte size of the workspace.  Layout = Keras variable order, see tf_vqa_regat_b200/config.py. */
+REGAT_API int regat_engine_sizes(const regat_engine* e, int64_t* param_elems, int64_t* workspace_bytes);
+/* Offset (elements) and size of parameter tensor idx in layout order; returns REGAT_ERR_ARG past the end. */
+REGAT_API int regat_engine_param(const regat_engine* e, int idx, int64_t* offset, int64_t* numel,
+                       int32_t* layer, int32_t* kind /*0=v,1=g,2=bias*/);
+REGAT_API int regat_engine_bind(regat_engine* e, float* params, float* grads, float* adamax_m,
+                      float* adamax_u, void* workspace, int64_t workspace_bytes);
+/* Forward only (eval, train.py:136-177): logits [B, num_answers] fp32, optional att [B,N].
+ * features [B,N,v_dim] fp32, boxes [B,N,4] fp32, q_att/q_last [B,q_dim] fp32.             */
+REGAT_API int regat_engine_forward(regat_engine* e, int B, int N, const float* features, const float* boxes,
+                         const float* q_att, const float* q_last, float* logits, float* att,
+                         regat_stream_t stream);
+/* Forward + backward: fills grads with dL/dW_eff for every kernel (W_eff = g*v/||v||) and dL/db for every
+ * bias -- linear in the batch, hence the quantity to all-reduce (see regat_engine_finalize_grads);
+ * loss_out[0] = loss, loss_out[1] = batch score; dq_att/dq_last [B,q_dim] fp32 (optional) for the
+ * upstream language model.  grad_scale multiplies the loss gradient (1/world for data parallel). */
+REGAT_API int regat_engine_fwd_bwd(regat_engine* e, int B, int N, const float* features, const float* boxes,
+                         const float* q_att, const float* q_last, const float* target,
+                         float grad_scale, float* loss_out, float* logits, float* dq_att,
+                         float* dq_last, regat_stream_t stream);
+/* Per-tensor clip_by_norm + Adamax (train.py:112-113) on the bound grads; step is 1-based. */
+REGAT_API int regat_engine_update(regat_engine* e, float lr, int step, regat_stream_t stream);
+/* fwd_bwd + update (single GPU). */
+REGAT_API int regat_engine_train_step(regat_engine* e, int B, int N, const float* features,
+                            const float* boxes, const float* q_att, const float* q_last,
+                            const float* target, float lr, int step, float* loss_out,
+                            regat_stream_t stream);
+/* Number of kernel launches the last engine call issued (for bench.py's gpu_launches). */
+REGAT_API int regat_engine_last_launches(const regat_engine* e);
+/* Copies the configuration the engine was created with. */
+REGAT_API int regat_engine_config(const regat_engine* e, regat_config* cfg);
+/* Overrides the 8 sinusoid divisors 1000^(k/8) (default: powf in C).  The Python binding passes the
+ * values NumPy computes in fp32 so that stage 1 tracks position_emb.py:98-100 bit for bit.          */
+REGAT_API int regat_engine_set_wave_div(regat_engine* e, const float* wave_div_host);
+/* Converts the bound grads buffer IN PLACE from dL/dW_eff (what fwd_bwd leaves; the quantity that is
+ * all-reduced in data parallel) to the reference's tape.gradient values (dv, dg) of weight_norm.py:41
+ * (train.py:111).  Optional -- regat_engine_update accepts either state.                            */
+REGAT_API int regat_engine_finalize_grads(regat_engine* e, regat_stream_t stream);
+/* Device pointer of a named internal activation (tests and the Python layer mirror): v0, mask, s, Qb,
+ * KVb, v1, P, GB, att, pooled, joint, hid, logits, alpha, scal, dv1, ds, dQb, dKVb.                   */
+REGAT_API int regat_engine_buffer(const regat_engine* e, const char* name, void** ptr);
+
+/* ------------------------------------------------------------------ DLPack front door ----
+ * Same as the two engine calls above, taking DLManagedTensor* (from
+ * tf.experimental.dlpack.to_dlpack / torch.utils.dlpack.to_dlpack; capsule "dltensor").
+ * Tensors must be kDLCUDA on the current device, fp32, compact row-major.  The capsule stays
+ * owned by the caller: the deleter is never called.                                        */
+struct DLManagedTensor;
+REGAT_API int regat_engine_forward_dl(regat_engine* e, struct DLManagedTensor* features,
+                            struct DLManagedTensor* boxes, struct DLManagedTensor* q_att,
+                            struct DLManagedTensor* q_last, struct DLManagedTensor* logits_out,
+                            regat_stream_t stream);
+REGAT_API int regat_engine_train_step_dl(regat_engine* e, struct DLManagedTensor* features,
+                               struct DLManagedTensor* boxes, struct DLManagedTensor* q_att,
+                               struct DLManagedTensor* q_last, struct DLManagedTensor* target,
+                               float lr, int step, float* loss_out, regat_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REGAT_H_ */

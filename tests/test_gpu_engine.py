@@ -1,0 +1,161 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+fp32 mode: 1e-4 relative (north_star); bf16 mode: 1e-2 relative on logits + same argmax."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import regat_fused as ofu
+from oracle import regat_numpy as onp
+from oracle import regat_torch as ot
+from tf_vqa_regat_b200 import synthetic as syn
+from tf_vqa_regat_b200.config import HotPathConfig
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(v_dim=192, q_dim=96, rel_dim=256, num_heads=4, nongt_dim=20, num_answers=301)
+
+
+def _rel(a, b):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def _setup(kw, B, N, adaptive, tl, dtype, seed=1000):
+    from tf_vqa_regat_b200.engine import HotPathEngine
+    cfg = HotPathConfig(**kw)
+    inp = syn.make_inputs(cfg, B, N, seed=seed, adaptive=adaptive)
+    flat = syn.make_params(cfg, seed=7, trained_like=tl)
+    eng = HotPathEngine(cfg, B, N, dtype=dtype)
+    eng.load_params(flat)
+    dev = {k: torch.tensor(v).cuda() for k, v in inp.items() if k != "n_obj"}
+    named64 = syn.unflatten(cfg, flat.astype(np.float64))
+    args64 = [inp[k].astype(np.float64) if k != "boxes" else inp[k] for k in ("features", "boxes", "q_att", "q_last", "target")]
+    return cfg, inp, flat, eng, dev, named64, args64
+
+
+CASES = [  # kw, B, N, adaptive, trained_like
+    (SMALL, 3, 36, False, False),
+    (SMALL, 5, 36, True, True),
+    (SMALL, 2, 12, False, True),           # N < nongt_dim: M clamps to N (graph_att_layer.py:42)
+    (dict(SMALL, nongt_dim=36), 2, 36, False, True),   # full K x K
+    (dict(SMALL, nongt_dim=20), 2, 100, True, True),   # adaptive up to 100 boxes
+    (dict(SMALL, v_dim=256), 2, 20, False, True),      # v_dim == rel_dim: no v2out (relation_encoder.py:52-55)
+    (dict(SMALL, dir_num=1, num_heads=8, rel_dim=512, residual=False, label_bias=True), 2, 24, False, True),
+]
+
+
+@pytest.mark.parametrize("kw,B,N,adaptive,tl", CASES)
+def test_forward_fp32_parity(kw, B, N, adaptive, tl):
+    cfg, inp, flat, eng, dev, named64, args64 = _setup(kw, B, N, adaptive, tl, "fp32")
+    logits, att = eng.forward(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"], return_att=True)
+    ref = onp.forward(named64, cfg, *args64)
+    M = cfg.m_keys(N)
+    # masking is bit-exact
+    np.testing.assert_array_equal(eng.buffer("mask", (B, N), torch.float32).cpu().numpy(), ref["mask"])
+    assert _rel(eng.buffer("v1", (B, N, cfg.rel_dim)).cpu().numpy(), ref["v1"]) < 1e-4
+    assert _rel(att.cpu().numpy(), ref["att_weights"]) < 1e-4
+    assert _rel(logits.cpu().numpy(), ref["logits"]) < 1e-4
+    assert np.array_equal(logits.argmax(1).cpu().numpy(), ref["logits"].argmax(1))
+
+
+@pytest.mark.parametrize("kw,B,N,adaptive,tl", CASES[:5])
+def test_forward_bf16_parity(kw, B, N, adaptive, tl):
+    cfg, inp, flat, eng, dev, named64, args64 = _setup(kw, B, N, adaptive, tl, "bf16")
+    logits = eng.forward(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"])
+    ref = onp.forward(named64, cfg, *args64)
+    assert _rel(logits.cpu().numpy(), ref["logits"]) < 1e-2
+    # same answer wherever the oracle's top-2 margin is above bf16 resolution
+    top2 = np.sort(ref["logits"], axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 2e-2 * np.abs(ref["logits"]).max()
+    assert np.array_equal(logits.argmax(1).cpu().numpy()[clear], ref["logits"].argmax(1)[clear])
+
+
+def test_attention_intermediates_fp32():
+    """Kernel (a) alone: saved P / geometry bias / Q / K / V' against the fused-formulation oracle."""
+    kw, B, N = SMALL, 3, 36
+    cfg, inp, flat, eng, dev, named64, args64 = _setup(kw, B, N, False, True, "fp32")
+    eng.fwd_bwd(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"], dev["target"])
+    it = ofu.forward(named64, cfg, *args64)
+    M, D, H, dirs = cfg.m_keys(N), cfg.rel_dim, cfg.num_heads, cfg.dir_num
+    Q = eng.buffer("Qb", (B, N, dirs, D)).cpu().numpy()
+    KV = eng.buffer("KVb", (B, M, 2 * dirs, D)).cpu().numpy()
+    GB = eng.buffer("GB", (B, dirs, H, N, M), torch.float32).cpu().numpy()
+    for d in range(dirs):
+        assert _rel(Q[:, :, d], it["dirs"][d]["Q"]) < 1e-4
+        assert _rel(KV[:, :, d], it["dirs"][d]["K"]) < 1e-4
+        assert _rel(KV[:, :, dirs + d], it["dirs"][d]["Vp"]) < 1e-4
+        z = it["dirs"][d]["z"]
+        gb_ref = np.log(np.maximum(np.maximum(z, 0), 1e-6))
+        # log amplifies the 1-ulp sin/cos argument noise where z ~ 0: compare where z is not tiny
+        ok = z > 1e-2
+        assert np.abs(GB[:, d] - gb_ref)[ok].max() < 2e-3
+        assert np.array_equal(GB[:, d] == np.float32(np.log(np.float32(1e-6))), z <= 1e-6) or \
+            (np.abs((GB[:, d] == np.float32(np.log(np.float32(1e-6)))).astype(int) - (z <= 1e-6).astype(int)).mean() < 1e-3)
+
+
+@pytest.mark.parametrize("kw,B,N,adaptive,tl", [CASES[1], CASES[2], CASES[6]])
+def test_gradients_fp32_parity(kw, B, N, adaptive, tl):
+    cfg, inp, flat, eng, dev, named64, args64 = _setup(kw, B, N, adaptive, tl, "fp32")
+    out = eng.fwd_bwd(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"], dev["target"], want_dq=True, want_logits=True)
+    eng.finalize_grads()
+    torch.cuda.synchronize()
+    loss, grads, dq_att, dq_last, ref = ot.loss_and_grads(named64, cfg, inp)
+    assert abs(float(out["loss"]) - loss) < 1e-4 * abs(loss)
+    ref_score = float(np.take_along_axis(inp["target"], ref["logits"].argmax(1)[:, None], 1).sum())
+    assert abs(float(out["score"]) - ref_score) < 1e-5
+    assert _rel(out["dq_att"].cpu().numpy(), dq_att) < 2e-4
+    assert _rel(out["dq_last"].cpu().numpy(), dq_last) < 2e-4
+    got = {k: v.cpu().numpy() for k, v in eng.named(eng.grads).items()}
+    worst = {}
+    for name, g in grads.items():
+        if name.endswith("implicit_relation.bias/v") or name.endswith("implicit_relation.bias/g") or \
+                name.endswith("implicit_relation.bias/bias") or name in ("joint_emb.linear/bias", "joint_emb.v2attention/bias"):
+            # softmax-shift directions: mathematically zero, rounding noise on both sides
+            scale = max(np.abs(grads["joint_emb.linear/v"]).max(), 1e-12)
+            assert np.abs(got[name]).max() < 1e-3 * scale + 1e-6, name
+            continue
+        worst[name] = _rel(got[name], g)
+    bad = {k: v for k, v in worst.items() if v > 5e-4}
+    assert not bad, bad
+
+
+def test_train_steps_fp32_track_oracle():
+    """Three optimizer steps: parameters after clip_by_norm + Adamax follow the oracle's."""
+    kw, B, N = SMALL, 4, 36
+    cfg, inp, flat, eng, dev, named64, args64 = _setup(kw, B, N, True, True, "fp32")
+    lr = 1e-3
+    p = {k: v.copy() for k, v in named64.items()}
+    m = {k: np.zeros_like(v) for k, v in p.items()}
+    u = {k: np.zeros_like(v) for k, v in p.items()}
+    losses_ref, losses = [], []
+    for step in range(1, 4):
+        loss, grads, _, _, _ = ot.loss_and_grads(p, cfg, inp)
+        losses_ref.append(loss)
+        for k in p:
+            g = ot.clip_by_norm(grads[k], cfg.grad_clip)
+            p[k], m[k], u[k] = ot.adamax_step(p[k], g, m[k], u[k], step, lr, cfg.beta1, cfg.beta2, cfg.eps)
+        l = eng.train_step(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"], dev["target"], lr, step)
+        losses.append(float(l[0]))
+    np.testing.assert_allclose(losses, losses_ref, rtol=2e-4)
+    got = {k: v.cpu().numpy() for k, v in eng.named().items()}
+    for k in p:
+        if "implicit_relation.bias" in k or k in ("joint_emb.linear/bias", "joint_emb.v2attention/bias"):
+            continue     # Adamax normalises pure rounding noise to +-lr there (documented in DESIGN.md)
+        # an Adamax step is at most lr per element; demand agreement to a small fraction of the total movement
+        assert np.abs(got[k] - p[k]).max() < 0.05 * 3 * lr + 1e-6, k
+
+
+def test_gradients_bf16_close():
+    kw, B, N = SMALL, 4, 36
+    cfg, inp, flat, eng, dev, named64, args64 = _setup(kw, B, N, False, True, "bf16")
+    out = eng.fwd_bwd(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"], dev["target"])
+    eng.finalize_grads()
+    loss, grads, _, _, _ = ot.loss_and_grads(named64, cfg, inp)
+    assert abs(float(out["loss"]) - loss) < 1e-2 * abs(loss)
+    got = {k: v.cpu().numpy() for k, v in eng.named(eng.grads).items()}
+    for name in ["v_relation.v2out/v", "v_relation.implicit_relation.self_weights/v",
+                 "v_relation.implicit_relation.neighbor_net.0.query/v", "v_relation.implicit_relation.neighbor_net.1.linear_out_/v",
+                 "joint_emb.visual_embed/v", "classifier.layers.3/v", "classifier.layers.0/bias"]:
+        g, r = got[name].ravel().astype(np.float64), grads[name].ravel()
+        cos = float(g @ r / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30))
+        assert cos > 0.995, (name, cos)

@@ -1,0 +1,595 @@
+// The hot path as one launch sequence on one stream with static buffers:
+//   rel_graph_net.py:53-62 (v_relation -> joint_emb -> classifier), train.py:103-113 (loss, gradients,
+//   per-tensor clip, Adamax).  No allocation, no host sync, no host-side data dependence, so the
+//   whole step can be captured in a CUDA graph by the caller.
+//
+// Re-associations relative to the reference formulation (all exact in real arithmetic; proven against the
+// reference-formulation oracle in tests/):
+//   W = g v/||v||_F = alpha*v            -> GEMMs read v (or its bf16 copy), alpha applied in the epilogue
+//   [v0 || mask*q] Ws                   -> v0 Ws[:D] + mask (q Ws[D:])          (relation_encoder.py:31-35)
+//   grouped conv of (p . s[:M])         -> p . (s[:M] Kc + bc)                  (graph_att_layer.py:110-117)
+//   linear((v1 Wva + b) * (q Wqa + b))  -> <v1, Wva ((q Wqa + b) * wl)> + const (fusion.py:47-52, all-linear FCs)
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace regat {
+
+struct Layer {
+  long long v_off = -1, g_off = -1, b_off = -1;
+  int rows = 0, cols = 0;       // kernel viewed as [rows, cols]
+  long long lowp_off = -1;      // element offset of the bf16 copy in the workspace
+  int lowp_ld = 0;
+};
+
+struct Entry { long long off, numel; int layer, kind; };
+
+}  // namespace regat
+
+using namespace regat;
+
+struct regat_engine {
+  regat_config cfg;
+  int dtype;
+  int max_b, max_n;
+  int use_tc;                      // bf16 dense kernels: 1 = tcgen05 (default), 0 = SIMT cross-check (REGAT_GEMM=simt)
+  std::vector<Layer> layers;
+  std::vector<Entry> entries;      // flat layout order: v, g, [bias] per layer
+  long long param_elems = 0;
+  int l_v2out = -1, l_self = -1, l_label = -1, l_pos[2], l_q[2], l_k[2], l_out[2];
+  int l_va = -1, l_qa = -1, l_lin = -1, l_ve = -1, l_qe = -1, l_c0 = -1, l_c3 = -1;
+  TensorList tl_v;  int chunks_v = 0;     // all weight-normed kernels (weight prep)
+  TensorList tl_opt; int chunks_opt = 0;  // kernels + biases (optimizer)
+  float wave_div[8];
+  // bound buffers
+  float* params = nullptr; float* grads = nullptr; float* am = nullptr; float* au = nullptr;
+  unsigned char* ws = nullptr; long long ws_bytes = 0;
+  long long ws_need = 0;
+  // workspace carve (byte offsets)
+  struct Buf { long long off = -1; };
+  Buf lowp, sumsq, alpha, invn, scal, stats, featT, qattT, qlastT, v0, mask, qs, s, strunc, Qb, KVb, v1, P, GB, gate, uqe,
+      uw, cb, weff, att, pooled, pv, joint, hid, logits, dlogits, dhid, djoint, dpv, duqe, dpooled, dv1, dweff, dcb, duw,
+      dQb, dKVb, ds, dstrunc, dsq;
+  int a_pad = 0;
+  int last_launches = 0;
+  int grads_final = 0;
+  template <typename T> T* at(const Buf& b) const { return reinterpret_cast<T*>(ws + b.off); }
+  void* atv(const Buf& b) const { return ws + b.off; }
+};
+
+namespace regat {
+namespace {
+
+constexpr long long ALIGN_ELEMS = 64;   // 256-byte alignment of every tensor in the flat fp32 buffers
+
+long long rup(long long x, long long a) { return (x + a - 1) / a * a; }
+
+// numpy-compatible fp32 1000^(k/8): position_emb.py:98-100 computes np.power in float32.
+void fill_wave_div(float* d, int feat_dim) {
+  for (int k = 0; k < 8; ++k) d[k] = powf(1000.0f, (8.0f / (float)feat_dim) * (float)k);
+}
+
+int add_layer(regat_engine* e, int rows, int cols, bool bias) {
+  Layer L;
+  L.rows = rows; L.cols = cols;
+  long long off = e->param_elems;
+  const int li = (int)e->layers.size();
+  L.v_off = off; e->entries.push_back({off, (long long)rows * cols, li, 0}); off = rup(off + (long long)rows * cols, ALIGN_ELEMS);
+  L.g_off = off; e->entries.push_back({off, 1, li, 1}); off = rup(off + 1, ALIGN_ELEMS);
+  if (bias) { L.b_off = off; e->entries.push_back({off, cols, li, 2}); off = rup(off + cols, ALIGN_ELEMS); }
+  e->param_elems = off;
+  e->layers.push_back(L);
+  return li;
+}
+
+// Keras-2 variable order of the reference layers; mirrored by tf_vqa_regat_b200/config.py.
+void build_layout(regat_engine* e) {
+  const regat_config& c = e->cfg;
+  const int V = c.v_dim, Q = c.q_dim, D = c.rel_dim, H = c.num_heads, E = c.pos_emb_dim, A = c.num_answers, Hd = c.q_dim;
+  if (V != D) e->l_v2out = add_layer(e, V, D, true);                   // relation_encoder.py:52-53
+  e->l_self = add_layer(e, D + Q, D, true);                            // graph_att_net.py:24
+  e->l_label = add_layer(e, 1, 1, c.label_bias != 0);                  // graph_att_net.py:25
+  for (int d = 0; d < c.dir_num; ++d) {                                // graph_att_layer.py:25-37
+    e->l_pos[d] = add_layer(e, E, H, true);
+    e->l_q[d] = add_layer(e, D, D, true);
+    e->l_k[d] = add_layer(e, D, D, true);
+    e->l_out[d] = add_layer(e, D, D, true);                            // Conv2D kernel [1,1,D,D]
+  }
+  e->l_va = add_layer(e, D, Hd, true);                                 // fusion.py:15-20
+  e->l_qa = add_layer(e, Q, Hd, true);
+  e->l_lin = add_layer(e, Hd, 1, true);
+  e->l_ve = add_layer(e, D, Hd, true);
+  e->l_qe = add_layer(e, Q, Hd, true);
+  e->l_c0 = add_layer(e, Hd, 2 * Hd, true);                            // classifier.py:14-19
+  e->l_c3 = add_layer(e, 2 * Hd, A, true);
+}
+
+long long carve(regat_engine* e) {
+  const regat_config& c = e->cfg;
+  const long long B = e->max_b, N = e->max_n, M = std::min<long long>(c.nongt_dim, N);
+  const long long R = B * N, Rm = B * M;
+  const long long V = c.v_dim, Q = c.q_dim, D = c.rel_dim, H = c.num_heads, A = c.num_answers, Hd = c.q_dim, dirs = c.dir_num;
+  const long long es = dtype_size(e->dtype);
+  long long off = 0;
+  auto take = [&](regat_engine::Buf& b, long long bytes) { b.off = off; off = rup(off + bytes, 256); };
+  e->a_pad = (int)rup(A, 64);
+  // bf16 copies of the kernels (bf16 mode only); leading dimension padded to a multiple of 8 elements
+  long long lowp_elems = 0;
+  for (auto& L : e->layers) {
+    L.lowp_ld = (int)rup(L.cols, 8);
+    L.lowp_off = lowp_elems;
+    lowp_elems = rup(lowp_elems + (long long)L.rows * L.lowp_ld, 128);
+  }
+  take(e->lowp, e->dtype == REGAT_BF16 ? lowp_elems * 2 : 0);
+  const long long nl = (long long)e->layers.size();
+  take(e->sumsq, nl * 4); take(e->alpha, nl * 4); take(e->invn, nl * 4);
+  take(e->scal, 64 * 4);                       // [0]=label const c, [1]=dc, [2]=loss, [3]=score
+  take(e->stats, 2 * MAX_TENSORS * 4);
+  take(e->featT, e->dtype == REGAT_BF16 ? R * V * 2 : 0);
+  take(e->qattT, e->dtype == REGAT_BF16 ? B * Q * 2 : 0);
+  take(e->qlastT, e->dtype == REGAT_BF16 ? B * Q * 2 : 0);
+  take(e->v0, e->l_v2out >= 0 ? R * D * es : 0);
+  take(e->mask, R * 4);
+  take(e->qs, B * D * 4);
+  take(e->s, R * D * es); take(e->strunc, Rm * D * es);
+  take(e->Qb, R * dirs * D * es); take(e->KVb, Rm * 2 * dirs * D * es);
+  take(e->v1, R * D * es);
+  take(e->P, B * dirs * H * N * M * 4); take(e->GB, B * dirs * H * N * M * 4);
+  take(e->gate, R * H * 8);
+  take(e->uqe, B * 2 * Hd * es); take(e->uw, B * Hd * es); take(e->cb, B * 4);
+  take(e->weff, B * D * es); take(e->att, B * N * 4); take(e->pooled, B * D * es);
+  take(e->pv, B * Hd * es); take(e->joint, B * Hd * es); take(e->hid, B * 2 * Hd * es);
+  take(e->logits, B * A * 4);
+  take(e->dlogits, B * e->a_pad * es);
+  take(e->dhid, B * 2 * Hd * es); take(e->djoint, B * Hd * es); take(e->dpv, B * Hd * es); take(e->duqe, B * 2 * Hd * es);
+  take(e->dpooled, B * D * es); take(e->dv1, R * D * es); take(e->dweff, B * D * es); take(e->dcb, B * 4);
+  take(e->duw, B * Hd * es);
+  take(e->dQb, R * dirs * D * es); take(e->dKVb, Rm * 2 * dirs * D * es);
+  take(e->ds, R * D * es); take(e->dstrunc, Rm * D * es); take(e->dsq, B * D * es);
+  return off;
+}
+
+void build_lists(regat_engine* e) {
+  TensorList& tv = e->tl_v;
+  memset(&tv, 0, sizeof(tv));
+  TensorList& to = e->tl_opt;
+  memset(&to, 0, sizeof(to));
+  for (size_t l = 0; l < e->layers.size(); ++l) {
+    const Layer& L = e->layers[l];
+    int i = tv.n++;
+    tv.off[i] = L.v_off; tv.numel[i] = (long long)L.rows * L.cols; tv.g_off[i] = L.g_off; tv.cols[i] = L.cols;
+    tv.off_lowp[i] = L.lowp_off; tv.ld_lowp[i] = L.lowp_ld; tv.kind[i] = 0; tv.layer[i] = (int)l;
+    int j = to.n++;
+    to.off[j] = L.v_off; to.numel[j] = (long long)L.rows * L.cols; to.g_off[j] = L.g_off; to.cols[j] = L.cols; to.kind[j] = 0;
+    to.layer[j] = (int)l;
+    if (L.b_off >= 0) {
+      j = to.n++;
+      to.off[j] = L.b_off; to.numel[j] = L.cols; to.g_off[j] = -1; to.cols[j] = L.cols; to.kind[j] = 1; to.layer[j] = (int)l;
+    }
+  }
+  e->chunks_v = build_tensor_list(tv);
+  e->chunks_opt = build_tensor_list(to);
+}
+
+__global__ void zero_list_kernel(float* buf, TensorList tl) {
+  for (int l = blockIdx.x; l < tl.n; l += gridDim.x)
+    for (long long i = threadIdx.x; i < tl.numel[l]; i += blockDim.x) buf[tl.off[l] + i] = 0.f;
+}
+
+struct Ctx {
+  regat_engine* e;
+  cudaStream_t st;
+  int B, N, M, R, Rm;
+  const float* features; const float* boxes; const float* q_att; const float* q_last;
+};
+
+EpiArgs epi0() { EpiArgs x; memset(&x, 0, sizeof(x)); return x; }
+
+int dense(regat_engine* e, cudaStream_t st, bool tA, bool tB, int M, int N, int K, const void* A, int lda, const void* Bm,
+          int ldb, void* C, int ldc, int c_dtype, const EpiArgs& ep, int split_k = 1) {
+  if (e->dtype == REGAT_F32) return gemm_simt(REGAT_F32, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, REGAT_F32, ep, st);
+  if (e->use_tc && gemm_tc_supported(tA, tB, M, N, K, A, lda, Bm, ldb))
+    return gemm_tc(tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, c_dtype, ep, split_k, st);
+  return gemm_simt(REGAT_BF16, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, c_dtype, ep, st);
+}
+
+// kernel operand of layer l: fp32 master weights in parity mode, bf16 copy otherwise
+const void* W(const regat_engine* e, int l, long long row = 0) {
+  const Layer& L = e->layers[l];
+  if (e->dtype == REGAT_F32) return e->params + L.v_off + row * L.cols;
+  return reinterpret_cast<const bf16*>(e->ws + e->lowp.off) + L.lowp_off + row * L.lowp_ld;
+}
+int ldW(const regat_engine* e, int l) { return e->dtype == REGAT_F32 ? e->layers[l].cols : e->layers[l].lowp_ld; }
+const float* biasp(const regat_engine* e, int l) { return e->layers[l].b_off >= 0 ? e->params + e->layers[l].b_off : nullptr; }
+float* gradW(const regat_engine* e, int l, long long row = 0) { return e->grads + e->layers[l].v_off + row * e->layers[l].cols; }
+float* gradB(const regat_engine* e, int l) { return e->layers[l].b_off >= 0 ? e->grads + e->layers[l].b_off : nullptr; }
+const float* alphap(const regat_engine* e, int l) { return e->at<float>(e->alpha) + l; }
+
+// y = act(alpha*(x W) + b)
+int fc_fwd(regat_engine* e, cudaStream_t st, int l, long long w_row0, int rows, int K, const void* x, int ldx, void* y, int ldy,
+           int y_dtype, bool relu, bool with_bias = true) {
+  EpiArgs ep = epi0();
+  ep.alpha = alphap(e, l);
+  ep.bias = with_bias ? biasp(e, l) : nullptr;
+  ep.relu = relu;
+  return dense(e, st, false, false, rows, e->layers[l].cols, K, x, ldx, W(e, l, w_row0), ldW(e, l), y, ldy, y_dtype, ep);
+}
+// dx (+)= alpha * (dy W^T)   [optionally gated]
+int fc_dgrad(regat_engine* e, cudaStream_t st, int l, long long w_row0, int rows, int K_in, const void* dy, int lddy, void* dx,
+             int lddx, int dx_dtype, bool accumulate, const void* gate = nullptr, int gate_ld = 0) {
+  EpiArgs ep = epi0();
+  ep.alpha = alphap(e, l);
+  ep.accumulate = accumulate;
+  ep.gate = gate; ep.gate_ld = gate_ld;
+  return dense(e, st, false, true, rows, K_in, e->layers[l].cols, dy, lddy, W(e, l, w_row0), ldW(e, l), dx, lddx, dx_dtype, ep);
+}
+// dW_eff[w_row0 : w_row0+K_in, :] = x^T dy  (fp32, into the grads buffer);  db += colsum(dy)
+int fc_wgrad(regat_engine* e, cudaStream_t st, int l, long long w_row0, int rows, int K_in, const void* x, int ldx, const void* dy,
+             int lddy, bool with_bias) {
+  EpiArgs ep = epi0();
+  REGAT_TRY(dense(e, st, true, false, K_in, e->layers[l].cols, rows, x, ldx, dy, lddy, gradW(e, l, w_row0), e->layers[l].cols,
+                  REGAT_F32, ep));
+  if (with_bias && gradB(e, l)) REGAT_TRY(k_colsum(e->dtype, dy, lddy, rows, e->layers[l].cols, gradB(e, l), st));
+  return REGAT_OK;
+}
+
+int prepare_weights(regat_engine* e, cudaStream_t st) {
+  float* sumsq = e->at<float>(e->sumsq);
+  REGAT_CUDA(cudaMemsetAsync(sumsq, 0, e->layers.size() * sizeof(float), st));
+  REGAT_TRY(k_wn_prepare(e->params, e->tl_v, e->chunks_v, sumsq, e->dtype == REGAT_BF16 ? e->atv(e->lowp) : nullptr, st));
+  REGAT_TRY(k_wn_alpha(e->params, e->tl_v, sumsq, e->at<float>(e->alpha), e->at<float>(e->invn), st));
+  const Layer& LL = e->layers[e->l_label];
+  REGAT_TRY(k_label_const(e->params, LL.v_off, LL.b_off, alphap(e, e->l_label), e->at<float>(e->scal), st));
+  return REGAT_OK;
+}
+
+int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
+  regat_engine* e = c.e;
+  cudaStream_t st = c.st;
+  const regat_config& cf = e->cfg;
+  const int dt = e->dtype, B = c.B, N = c.N, M = c.M, R = c.R, Rm = c.Rm;
+  const int V = cf.v_dim, Q = cf.q_dim, D = cf.rel_dim, H = cf.num_heads, A = cf.num_answers, Hd = cf.q_dim, dirs = cf.dir_num;
+
+  REGAT_TRY(prepare_weights(e, st));
+  // activations in the compute dtype
+  const void* feat = c.features; const void* qatt = c.q_att; const void* qlast = c.q_last;
+  if (dt == REGAT_BF16) {
+    REGAT_TRY(k_cast(REGAT_BF16, c.features, e->atv(e->featT), (long long)R * V, st));
+    REGAT_TRY(k_cast(REGAT_BF16, c.q_att, e->atv(e->qattT), (long long)B * Q, st));
+    REGAT_TRY(k_cast(REGAT_BF16, c.q_last, e->atv(e->qlastT), (long long)B * Q, st));
+    feat = e->atv(e->featT); qatt = e->atv(e->qattT); qlast = e->atv(e->qlastT);
+  }
+  // v0 = relu(v2out(visual))                                            relation_encoder.py:78-79
+  const void* v0 = feat;
+  if (e->l_v2out >= 0) {
+    REGAT_TRY(fc_fwd(e, st, e->l_v2out, 0, R, V, feat, V, e->atv(e->v0), D, dt, true));
+    v0 = e->atv(e->v0);
+  }
+  // mask = (sum_d v0 != 0);  s = self_weights([v0 || mask*q])            relation_encoder.py:13-37, graph_att_net.py:58
+  REGAT_TRY(k_rowmask(dt, v0, R, D, e->at<float>(e->mask), st));
+  {
+    EpiArgs ep = epi0();
+    REGAT_TRY(dense(e, st, false, false, B, D, Q, qatt, Q, W(e, e->l_self, D), ldW(e, e->l_self), e->atv(e->qs), D, REGAT_F32, ep));
+    ep.alpha = alphap(e, e->l_self); ep.bias = biasp(e, e->l_self);
+    ep.addend = e->at<float>(e->qs); ep.addend_ld = D; ep.addend_rows = N; ep.row_scale = e->at<float>(e->mask);
+    ep.c2 = e->atv(e->strunc); ep.c2_ld = D; ep.c2_rows_in = N; ep.c2_rows_keep = M;
+    REGAT_TRY(dense(e, st, false, false, R, D, D, v0, D, W(e, e->l_self, 0), ldW(e, e->l_self), e->atv(e->s), D, dt, ep));
+  }
+  // per direction: Q = query(s), K = key(s[:, :M]), V' = s[:, :M] Kc + bc   graph_att_layer.py:47,55,112-117
+  const size_t es = dtype_size(dt);
+  for (int d = 0; d < dirs; ++d) {
+    REGAT_TRY(fc_fwd(e, st, e->l_q[d], 0, R, D, e->atv(e->s), D, e->at<unsigned char>(e->Qb) + (size_t)d * D * es, dirs * D, dt, false));
+    REGAT_TRY(fc_fwd(e, st, e->l_k[d], 0, Rm, D, e->atv(e->strunc), D, e->at<unsigned char>(e->KVb) + (size_t)d * D * es, 2 * dirs * D, dt, false));
+    REGAT_TRY(fc_fwd(e, st, e->l_out[d], 0, Rm, D, e->atv(e->strunc), D, e->at<unsigned char>(e->KVb) + (size_t)(dirs + d) * D * es, 2 * dirs * D, dt, false));
+  }
+  // fused geometry-bias attention + relu + residual -> v1
+  {
+    const Layer& P0 = e->layers[e->l_pos[0]];
+    const long long wstride = dirs > 1 ? e->layers[e->l_pos[1]].v_off - P0.v_off : 0;
+    const long long bstride = dirs > 1 ? e->layers[e->l_pos[1]].b_off - P0.b_off : 0;
+    // alpha of the pair_pos_fc layers must be contiguous per direction: gather them
+    float* ag = e->at<float>(e->scal) + 8;
+    for (int d = 0; d < dirs; ++d)
+      REGAT_CUDA(cudaMemcpyAsync(ag + d, alphap(e, e->l_pos[d]), sizeof(float), cudaMemcpyDeviceToDevice, st));
+    REGAT_TRY(regat_geoattn_fwd(dt, B, N, cf.nongt_dim, D, H, dirs, cf.pos_emb_dim, e->atv(e->Qb), e->atv(e->KVb), c.boxes, nullptr,
+                                e->wave_div, e->params + P0.v_off, wstride, ag, e->params + P0.b_off, bstride,
+                                e->at<float>(e->scal), e->atv(e->s), v0, cf.residual, e->atv(e->v1),
+                                training ? e->at<float>(e->P) : nullptr, training ? e->at<float>(e->GB) : nullptr,
+                                training ? e->at<uint64_t>(e->gate) : nullptr, st));
+  }
+  // BUTD: u = q2attention(q), qe = question_embed(q)                     fusion.py:37,48
+  REGAT_TRY(fc_fwd(e, st, e->l_qa, 0, B, Q, qlast, Q, e->atv(e->uqe), 2 * Hd, dt, false));
+  REGAT_TRY(fc_fwd(e, st, e->l_qe, 0, B, Q, qlast, Q, e->at<unsigned char>(e->uqe) + (size_t)Hd * es, 2 * Hd, dt, false));
+  REGAT_TRY(k_butd_prep(dt, e->atv(e->uqe), 2 * Hd, e->params + e->layers[e->l_lin].v_off, alphap(e, e->l_lin), biasp(e, e->l_va),
+                        biasp(e, e->l_lin), e->atv(e->uw), e->at<float>(e->cb), B, Hd, st));
+  {  // weff = alpha_va * (uw Wva^T)
+    EpiArgs ep = epi0();
+    ep.alpha = alphap(e, e->l_va);
+    REGAT_TRY(dense(e, st, false, true, B, D, Hd, e->atv(e->uw), Hd, W(e, e->l_va), ldW(e, e->l_va), e->atv(e->weff), D, dt, ep));
+  }
+  REGAT_TRY(regat_butd_pool_fwd(dt, B, N, D, e->atv(e->v1), e->atv(e->weff), e->at<float>(e->cb), e->at<float>(e->att),
+                                e->atv(e->pooled), st));
+  if (att_out) REGAT_CUDA(cudaMemcpyAsync(att_out, e->atv(e->att), (size_t)B * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  REGAT_TRY(fc_fwd(e, st, e->l_ve, 0, B, D, e->atv(e->pooled), D, e->atv(e->pv), Hd, dt, false));
+  REGAT_TRY(k_mul(dt, e->atv(e->pv), Hd, e->at<unsigned char>(e->uqe) + (size_t)Hd * es, 2 * Hd, e->atv(e->joint), Hd, B, Hd, st));
+  // classifier                                                          classifier.py:14-25
+  REGAT_TRY(fc_fwd(e, st, e->l_c0, 0, B, Hd, e->atv(e->joint), Hd, e->atv(e->hid), 2 * Hd, dt, true));
+  REGAT_TRY(fc_fwd(e, st, e->l_c3, 0, B, 2 * Hd, e->atv(e->hid), 2 * Hd, e->atv(e->logits), A, REGAT_F32, false));
+  if (logits_out)
+    REGAT_CUDA(cudaMemcpyAsync(logits_out, e->atv(e->logits), (size_t)B * A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return REGAT_OK;
+}
+
+int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float* dq_last) {
+  regat_engine* e = c.e;
+  cudaStream_t st = c.st;
+  const regat_config& cf = e->cfg;
+  const int dt = e->dtype, B = c.B, N = c.N, M = c.M, R = c.R, Rm = c.Rm;
+  const int V = cf.v_dim, Q = cf.q_dim, D = cf.rel_dim, H = cf.num_heads, A = cf.num_answers, Hd = cf.q_dim, dirs = cf.dir_num;
+  const size_t es = dtype_size(dt);
+  const void* feat = dt == REGAT_BF16 ? e->atv(e->featT) : (const void*)c.features;
+  const void* qatt = dt == REGAT_BF16 ? e->atv(e->qattT) : (const void*)c.q_att;
+  const void* qlast = dt == REGAT_BF16 ? e->atv(e->qlastT) : (const void*)c.q_last;
+  const void* v0 = e->l_v2out >= 0 ? e->atv(e->v0) : feat;
+  float* scal = e->at<float>(e->scal);
+
+  // bias / pair_pos_fc / label gradients are accumulated with atomics: zero those slots (kernels' gradients are overwritten)
+  {
+    TensorList z;
+    memset(&z, 0, sizeof(z));
+    for (size_t l = 0; l < e->layers.size(); ++l) {
+      const Layer& L = e->layers[l];
+      if (L.b_off >= 0) { z.off[z.n] = L.b_off; z.numel[z.n] = L.cols; ++z.n; }
+      z.off[z.n] = L.g_off; z.numel[z.n] = 1; ++z.n;
+    }
+    zero_list_kernel<<<z.n, 128, 0, st>>>(e->grads, z);
+    REGAT_POST_LAUNCH();
+    for (int d = 0; d < dirs; ++d) {
+      const Layer& L = e->layers[e->l_pos[d]];
+      REGAT_CUDA(cudaMemsetAsync(e->grads + L.v_off, 0, (size_t)L.rows * L.cols * sizeof(float), st));
+    }
+    REGAT_CUDA(cudaMemsetAsync(scal + 1, 0, 3 * sizeof(float), st));   // dc, loss, score
+  }
+  // loss + dlogits                                                     train.py:107-108
+  REGAT_TRY(k_bce(B, A, e->at<float>(e->logits), A, target, grad_scale, scal + 2, scal + 3, e->atv(e->dlogits), e->a_pad, dt, st));
+  // classifier
+  REGAT_TRY(fc_wgrad(e, st, e->l_c3, 0, B, 2 * Hd, e->atv(e->hid), 2 * Hd, e->atv(e->dlogits), e->a_pad, true));
+  REGAT_TRY(fc_dgrad(e, st, e->l_c3, 0, B, 2 * Hd, e->atv(e->dlogits), e->a_pad, e->atv(e->dhid), 2 * Hd, dt, false, e->atv(e->hid), 2 * Hd));
+  REGAT_TRY(fc_wgrad(e, st, e->l_c0, 0, B, Hd, e->atv(e->joint), Hd, e->atv(e->dhid), 2 * Hd, true));
+  REGAT_TRY(fc_dgrad(e, st, e->l_c0, 0, B, Hd, e->atv(e->dhid), 2 * Hd, e->atv(e->djoint), Hd, dt, false));
+  // joint = pv * qe
+  unsigned char* dqe = e->at<unsigned char>(e->duqe) + (size_t)Hd * es;
+  REGAT_TRY(k_mul_bwd(dt, e->atv(e->djoint), Hd, e->atv(e->pv), Hd, e->at<unsigned char>(e->uqe) + (size_t)Hd * es, 2 * Hd,
+                      e->atv(e->dpv), Hd, dqe, 2 * Hd, B, Hd, st));
+  REGAT_TRY(fc_wgrad(e, st, e->l_ve, 0, B, D, e->atv(e->pooled), D, e->atv(e->dpv), Hd, true));
+  REGAT_TRY(fc_dgrad(e, st, e->l_ve, 0, B, D, e->atv(e->dpv), Hd, e->atv(e->dpooled), D, dt, false));
+  // attention pooling
+  REGAT_TRY(regat_butd_pool_bwd(dt, B, N, D, e->atv(e->v1), e->atv(e->weff), e->at<float>(e->att), e->atv(e->dpooled),
+                                e->atv(e->dv1), e->atv(e->dweff), e->at<float>(e->dcb), st));
+  {  // weff = alpha_va (uw Wva^T):  dWva_eff = dweff^T uw ;  duw = alpha_va (dweff Wva)
+    EpiArgs ep = epi0();
+    REGAT_TRY(dense(e, st, true, false, D, Hd, B, e->atv(e->dweff), D, e->atv(e->uw), Hd, gradW(e, e->l_va), Hd, REGAT_F32, ep));
+    ep.alpha = alphap(e, e->l_va);
+    REGAT_TRY(dense(e, st, false, false, B, Hd, D, e->atv(e->dweff), D, W(e, e->l_va), ldW(e, e->l_va), e->atv(e->duw), Hd, dt, ep));
+  }
+  REGAT_TRY(k_butd_prep_bwd(dt, e->atv(e->duw), e->at<float>(e->dcb), e->atv(e->uqe), 2 * Hd, e->atv(e->uw),
+                            e->params + e->layers[e->l_lin].v_off, alphap(e, e->l_lin), biasp(e, e->l_va), e->atv(e->duqe), 2 * Hd,
+                            gradW(e, e->l_lin), gradB(e, e->l_va), gradB(e, e->l_lin), B, Hd, st));
+  REGAT_TRY(fc_wgrad(e, st, e->l_qa, 0, B, Q, qlast, Q, e->atv(e->duqe), 2 * Hd, true));
+  REGAT_TRY(fc_wgrad(e, st, e->l_qe, 0, B, Q, qlast, Q, dqe, 2 * Hd, true));
+  if (dq_last) {
+    REGAT_TRY(fc_dgrad(e, st, e->l_qa, 0, B, Q, e->atv(e->duqe), 2 * Hd, dq_last, Q, REGAT_F32, false));
+    REGAT_TRY(fc_dgrad(e, st, e->l_qe, 0, B, Q, dqe, 2 * Hd, dq_last, Q, REGAT_F32, true));
+  }
+  // attention backward: dQ, dK, dV', dout (-> ds), dL (in place of P); then the geometry reduction
+  REGAT_TRY(regat_attn_bwd(dt, B, N, cf.nongt_dim, D, H, dirs, e->atv(e->Qb), e->atv(e->KVb), e->atv(e->dv1),
+                           e->at<uint64_t>(e->gate), e->at<float>(e->P), e->atv(e->dQb), e->atv(e->dKVb), e->atv(e->ds), st));
+  {
+    const Layer& P0 = e->layers[e->l_pos[0]];
+    const long long wstride = dirs > 1 ? e->layers[e->l_pos[1]].v_off - P0.v_off : 0;
+    const long long bstride = dirs > 1 ? e->layers[e->l_pos[1]].b_off - P0.b_off : 0;
+    REGAT_TRY(regat_geo_bwd(B, N, cf.nongt_dim, H, dirs, cf.pos_emb_dim, c.boxes, nullptr, e->wave_div, e->at<float>(e->P),
+                            e->at<float>(e->GB), e->grads + P0.v_off, wstride, e->grads + P0.b_off, bstride, scal + 1, st));
+    const Layer& LL = e->layers[e->l_label];
+    REGAT_TRY(k_label_grad(scal + 1, e->grads, LL.v_off, LL.b_off, st));
+  }
+  for (int d = 0; d < dirs; ++d) {
+    unsigned char* dQd = e->at<unsigned char>(e->dQb) + (size_t)d * D * es;
+    unsigned char* dKd = e->at<unsigned char>(e->dKVb) + (size_t)d * D * es;
+    unsigned char* dVd = e->at<unsigned char>(e->dKVb) + (size_t)(dirs + d) * D * es;
+    REGAT_TRY(fc_wgrad(e, st, e->l_q[d], 0, R, D, e->atv(e->s), D, dQd, dirs * D, true));
+    REGAT_TRY(fc_dgrad(e, st, e->l_q[d], 0, R, D, dQd, dirs * D, e->atv(e->ds), D, dt, true));
+    REGAT_TRY(fc_wgrad(e, st, e->l_k[d], 0, Rm, D, e->atv(e->strunc), D, dKd, 2 * dirs * D, true));
+    REGAT_TRY(fc_dgrad(e, st, e->l_k[d], 0, Rm, D, dKd, 2 * dirs * D, e->atv(e->dstrunc), D, dt, d > 0));
+    REGAT_TRY(fc_wgrad(e, st, e->l_out[d], 0, Rm, D, e->atv(e->strunc), D, dVd, 2 * dirs * D, true));
+    REGAT_TRY(fc_dgrad(e, st, e->l_out[d], 0, Rm, D, dVd, 2 * dirs * D, e->atv(e->dstrunc), D, dt, true));
+  }
+  REGAT_TRY(k_addrows(dt, e->atv(e->ds), e->atv(e->dstrunc), B, N, M, D, st));
+  // self_weights: s = alpha (v0 Ws[:D] + mask (q Ws[D:])) + b
+  REGAT_TRY(fc_wgrad(e, st, e->l_self, 0, R, D, v0, D, e->atv(e->ds), D, true));
+  REGAT_TRY(k_segsum(dt, e->atv(e->ds), e->at<float>(e->mask), B, N, D, e->atv(e->dsq), st));
+  REGAT_TRY(fc_wgrad(e, st, e->l_self, D, B, Q, qatt, Q, e->atv(e->dsq), D, false));
+  if (dq_att) REGAT_TRY(fc_dgrad(e, st, e->l_self, D, B, Q, e->atv(e->dsq), D, dq_att, Q, REGAT_F32, false));
+  if (e->l_v2out >= 0) {
+    // dv0 = (dv1 [residual] + alpha ds Ws[:D]^T) o (v0 > 0), in place in the dv1 buffer; then v2out's gradients
+    REGAT_TRY(fc_dgrad(e, st, e->l_self, 0, R, D, e->atv(e->ds), D, e->atv(e->dv1), D, dt, cf.residual != 0, v0, D));
+    REGAT_TRY(fc_wgrad(e, st, e->l_v2out, 0, R, V, feat, V, e->atv(e->dv1), D, true));
+  }
+  e->grads_final = 0;
+  return REGAT_OK;
+}
+
+int opt_stats(regat_engine* e, cudaStream_t st) {
+  float* stats = e->at<float>(e->stats);
+  REGAT_CUDA(cudaMemsetAsync(stats, 0, 2 * MAX_TENSORS * sizeof(float), st));
+  return k_opt_reduce(e->params, e->grads, e->tl_opt, e->chunks_opt, stats, st);
+}
+
+int check_call(regat_engine* e, int B, int N, bool need_opt) {
+  REGAT_REQUIRE(e, REGAT_ERR_ARG, "engine is null");
+  REGAT_REQUIRE(e->params && e->ws, REGAT_ERR_ARG, "engine: call regat_engine_bind first");
+  REGAT_REQUIRE(!need_opt || (e->grads && e->am && e->au), REGAT_ERR_ARG, "engine: grads / Adamax buffers not bound");
+  REGAT_REQUIRE(B > 0 && N > 0, REGAT_ERR_SHAPE, "engine: empty batch (B=%d, N=%d)", B, N);
+  REGAT_REQUIRE(B <= e->max_b && N <= e->max_n, REGAT_ERR_SHAPE, "engine: batch %dx%d exceeds the capacity %dx%d given at create", B, N,
+                e->max_b, e->max_n);
+  return REGAT_OK;
+}
+
+}  // namespace
+}  // namespace regat
+
+extern "C" int regat_default_config(regat_config* cfg) {
+  REGAT_REQUIRE(cfg, REGAT_ERR_ARG, "default_config: null pointer");
+  cfg->v_dim = 2048; cfg->q_dim = 768; cfg->rel_dim = 1024; cfg->num_heads = 16; cfg->pos_emb_dim = 64; cfg->nongt_dim = 20;
+  cfg->dir_num = 2; cfg->num_answers = 3129; cfg->label_bias = 0; cfg->residual = 1;
+  cfg->grad_clip = 0.25f; cfg->beta1 = 0.9f; cfg->beta2 = 0.999f; cfg->eps = 1e-8f;
+  return REGAT_OK;
+}
+
+extern "C" int regat_engine_create(const regat_config* cfg, int dtype, int max_batch, int max_rois, regat_engine** out) {
+  REGAT_REQUIRE(cfg && out, REGAT_ERR_ARG, "engine_create: null pointer");
+  REGAT_REQUIRE(dtype == REGAT_F32 || dtype == REGAT_BF16, REGAT_ERR_DTYPE, "engine_create: bad dtype %d", dtype);
+  REGAT_REQUIRE(max_batch > 0 && max_rois > 0 && max_rois <= 128, REGAT_ERR_SHAPE, "engine_create: need 0 < max_rois <= 128, max_batch > 0");
+  REGAT_REQUIRE(cfg->rel_dim == cfg->num_heads * 64, REGAT_ERR_UNSUPPORTED, "engine_create: head dim must be 64");
+  REGAT_REQUIRE(cfg->pos_emb_dim == 64, REGAT_ERR_UNSUPPORTED, "engine_create: pos_emb_dim must be 64");
+  REGAT_REQUIRE(cfg->dir_num >= 1 && cfg->dir_num <= 2, REGAT_ERR_SHAPE, "engine_create: dir_num must be 1 or 2 (graph_att_net.py:18)");
+  REGAT_REQUIRE(cfg->v_dim % 8 == 0 && cfg->q_dim % 8 == 0 && cfg->nongt_dim > 0 && cfg->num_answers > 0, REGAT_ERR_SHAPE,
+                "engine_create: v_dim and q_dim must be multiples of 8");
+  regat_engine* e = new regat_engine();
+  e->cfg = *cfg; e->dtype = dtype; e->max_b = max_batch; e->max_n = max_rois;
+  const char* g = getenv("REGAT_GEMM");
+  e->use_tc = !(g && strcmp(g, "simt") == 0);
+  build_layout(e);
+  e->ws_need = carve(e);
+  build_lists(e);
+  fill_wave_div(e->wave_div, cfg->pos_emb_dim);
+  *out = e;
+  return REGAT_OK;
+}
+extern "C" int regat_engine_destroy(regat_engine* e) { delete e; return REGAT_OK; }
+
+extern "C" int regat_engine_sizes(const regat_engine* e, int64_t* param_elems, int64_t* workspace_bytes) {
+  REGAT_REQUIRE(e, REGAT_ERR_ARG, "engine is null");
+  if (param_elems) *param_elems = e->param_elems;
+  if (workspace_bytes) *workspace_bytes = e->ws_need;
+  return REGAT_OK;
+}
+extern "C" int regat_engine_param(const regat_engine* e, int idx, int64_t* offset, int64_t* numel, int32_t* layer, int32_t* kind) {
+  REGAT_REQUIRE(e, REGAT_ERR_ARG, "engine is null");
+  if (idx < 0 || idx >= (int)e->entries.size()) return REGAT_ERR_ARG;
+  const Entry& x = e->entries[idx];
+  if (offset) *offset = x.off;
+  if (numel) *numel = x.numel;
+  if (layer) *layer = x.layer;
+  if (kind) *kind = x.kind;
+  return REGAT_OK;
+}
+extern "C" int regat_engine_bind(regat_engine* e, float* params, float* grads, float* adamax_m, float* adamax_u, void* workspace,
+                                 int64_t workspace_bytes) {
+  REGAT_REQUIRE(e && params && workspace, REGAT_ERR_ARG, "engine_bind: null pointer");
+  REGAT_REQUIRE(workspace_bytes >= e->ws_need, REGAT_ERR_WORKSPACE, "engine_bind: workspace %lld B < required %lld B",
+                (long long)workspace_bytes, e->ws_need);
+  REGAT_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)params & 255) == 0 && (!grads || ((uintptr_t)grads & 255) == 0),
+                REGAT_ERR_ALIGN, "engine_bind: buffers must be 256-byte aligned");
+  e->params = params; e->grads = grads; e->am = adamax_m; e->au = adamax_u;
+  e->ws = static_cast<unsigned char*>(workspace); e->ws_bytes = workspace_bytes;
+  return REGAT_OK;
+}
+
+extern "C" int regat_engine_forward(regat_engine* e, int B, int N, const float* features, const float* boxes, const float* q_att,
+                                    const float* q_last, float* logits, float* att, regat_stream_t stream) {
+  REGAT_TRY(check_call(e, B, N, false));
+  REGAT_REQUIRE(features && boxes && q_att && q_last, REGAT_ERR_ARG, "engine_forward: null input");
+  const int l0 = launch_counter();
+  Ctx c{e, (cudaStream_t)stream, B, N, std::min(e->cfg.nongt_dim, N), B * N, B * std::min(e->cfg.nongt_dim, N), features, boxes, q_att, q_last};
+  REGAT_TRY(forward(c, false, logits, att));
+  e->last_launches = launch_counter() - l0;
+  return REGAT_OK;
+}
+
+extern "C" int regat_engine_fwd_bwd(regat_engine* e, int B, int N, const float* features, const float* boxes, const float* q_att,
+                                    const float* q_last, const float* target, float grad_scale, float* loss_out, float* logits,
+                                    float* dq_att, float* dq_last, regat_stream_t stream) {
+  REGAT_TRY(check_call(e, B, N, false));
+  REGAT_REQUIRE(e->grads, REGAT_ERR_ARG, "engine_fwd_bwd: grads buffer not bound");
+  REGAT_REQUIRE(features && boxes && q_att && q_last && target, REGAT_ERR_ARG, "engine_fwd_bwd: null input");
+  const int l0 = launch_counter();
+  cudaStream_t st = (cudaStream_t)stream;
+  Ctx c{e, st, B, N, std::min(e->cfg.nongt_dim, N), B * N, B * std::min(e->cfg.nongt_dim, N), features, boxes, q_att, q_last};
+  REGAT_TRY(forward(c, true, logits, nullptr));
+  REGAT_TRY(backward(c, target, grad_scale, dq_att, dq_last));
+  if (loss_out) REGAT_CUDA(cudaMemcpyAsync(loss_out, e->at<float>(e->scal) + 2, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  e->last_launches = launch_counter() - l0;
+  return REGAT_OK;
+}
+
+// Converts the grads buffer in place from dL/dW_eff to the reference's (dv, dg) -- what tape.gradient returns
+// (train.py:111).  Optional: regat_engine_update accepts either state.
+extern "C" int regat_engine_finalize_grads(regat_engine* e, regat_stream_t stream) {
+  REGAT_REQUIRE(e && e->grads && e->ws, REGAT_ERR_ARG, "engine_finalize_grads: not bound");
+  if (e->grads_final) return REGAT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  REGAT_TRY(opt_stats(e, st));
+  REGAT_TRY(k_opt_finalize(e->params, e->grads, e->tl_opt, e->chunks_opt, e->at<float>(e->stats), e->at<float>(e->alpha),
+                           e->at<float>(e->invn), st));
+  e->grads_final = 1;
+  return REGAT_OK;
+}
+
+extern "C" int regat_engine_update(regat_engine* e, float lr, int step, regat_stream_t stream) {
+  REGAT_REQUIRE(e && e->params && e->grads && e->am && e->au && e->ws, REGAT_ERR_ARG, "engine_update: buffers not bound");
+  REGAT_REQUIRE(step >= 1, REGAT_ERR_ARG, "engine_update: step is 1-based");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int l0 = launch_counter();
+  REGAT_TRY(opt_stats(e, st));
+  OptHyper hp;
+  hp.lr_t = (float)((double)lr / (1.0 - pow((double)e->cfg.beta1, (double)step)));
+  hp.beta1 = e->cfg.beta1; hp.beta2 = e->cfg.beta2; hp.eps = e->cfg.eps; hp.clip = e->cfg.grad_clip;
+  hp.grads_are_final = e->grads_final;
+  REGAT_TRY(k_opt_update(e->params, e->grads, e->am, e->au, e->tl_opt, e->chunks_opt, e->at<float>(e->stats), e->at<float>(e->alpha),
+                         e->at<float>(e->invn), hp, st));
+  e->last_launches = launch_counter() - l0;
+  return REGAT_OK;
+}
+
+extern "C" int regat_engine_train_step(regat_engine* e, int B, int N, const float* features, const float* boxes, const float* q_att,
+                                       const float* q_last, const float* target, float lr, int step, float* loss_out,
+                                       regat_stream_t stream) {
+  REGAT_TRY(check_call(e, B, N, true));
+  const int l0 = launch_counter();
+  REGAT_TRY(regat_engine_fwd_bwd(e, B, N, features, boxes, q_att, q_last, target, 1.0f, loss_out, nullptr, nullptr, nullptr, stream));
+  REGAT_TRY(regat_engine_update(e, lr, step, stream));
+  e->last_launches = launch_counter() - l0;
+  return REGAT_OK;
+}
+
+extern "C" int regat_engine_last_launches(const regat_engine* e) { return e ? e->last_launches : 0; }
+
+extern "C" int regat_engine_set_wave_div(regat_engine* e, const float* wave_div_host) {
+  REGAT_REQUIRE(e && wave_div_host, REGAT_ERR_ARG, "engine_set_wave_div: null pointer");
+  for (int k = 0; k < 8; ++k) e->wave_div[k] = wave_div_host[k];
+  return REGAT_OK;
+}
+
+extern "C" int regat_engine_config(const regat_engine* e, regat_config* cfg) {
+  REGAT_REQUIRE(e && cfg, REGAT_ERR_ARG, "engine_config: null pointer");
+  *cfg = e->cfg;
+  return REGAT_OK;
+}
+
+// raw views of internal activations for tests / the Python layer mirror (name lookup keeps the ABI small)
+extern "C" int regat_engine_buffer(const regat_engine* e, const char* name, void** ptr) {
+  REGAT_REQUIRE(e && name && ptr && e->ws, REGAT_ERR_ARG, "engine_buffer: null / unbound");
+#define REGAT_BUF(n) if (strcmp(name, #n) == 0) { *ptr = e->ws + e->n.off; return REGAT_OK; }
+  REGAT_BUF(v0) REGAT_BUF(mask) REGAT_BUF(s) REGAT_BUF(Qb) REGAT_BUF(KVb) REGAT_BUF(v1) REGAT_BUF(P) REGAT_BUF(GB) REGAT_BUF(att)
+  REGAT_BUF(pooled) REGAT_BUF(joint) REGAT_BUF(hid) REGAT_BUF(logits) REGAT_BUF(alpha) REGAT_BUF(scal) REGAT_BUF(dv1) REGAT_BUF(ds)
+  REGAT_BUF(dQb) REGAT_BUF(dKVb)
+#undef REGAT_BUF
+  REGAT_REQUIRE(false, REGAT_ERR_ARG, "engine_buffer: unknown buffer '%s'", name);
+}

@@ -1,0 +1,884 @@
+// Kernel (a): fused box-geometry bias + multi-head graph attention, forward and backward.
+//
+// What it replaces in the reference (file:line under the reference tree):
+//   position_emb.py:117-151  pairwise log-geometry            \  recomputed on chip per pair,
+//   position_emb.py:96-115   sinusoidal embedding (64-d)      /  never written to HBM
+//   graph_att_layer.py:74-88 pair_pos_fc 64->H, relu, max(.,1e-6), log, raw reshape scramble
+//   graph_att_layer.py:63-68 QK^T/sqrt(dh);  :90-102 adjacency where (no-op, adj==1) + label const
+//   graph_att_layer.py:104-117 softmax over the first M objects, aggregation, grouped 1x1 conv
+//                            (re-associated: V' = s[:, :M].Kc + bc is an input here)
+//   graph_att_net.py:64-81   sum over directions, ReLU;  relation_encoder.py:88-91 residual
+//
+// Design (B200): the path is HBM-bound (~3 FLOP/B), so everything is sized for bytes:
+//   * forward: one CTA per (graph, 16-row tile).  Phase 1: 256 threads compute the 16 x M pair
+//     embeddings (32 accurate sincosf each) and the 64 x (dirs*H) projection once for ALL heads and
+//     both directions, leaving log-bias in shared memory.  Phase 2: warp w owns heads w, w+8,...;
+//     Q/K/V' fragments are loaded straight from global with 128-bit loads (k- and n-index
+//     permutations make every mma fragment a contiguous load, so there is no smem staging and
+//     no bank conflict), logits/softmax live in mma C fragments, P feeds the PV mma with no
+//     shuffle, and the epilogue fuses  v1 = v0 + relu(s + O_0 + O_1).
+//   * the tiny matmuls run on mma.sync.m16n8k8 tf32.  bf16 inputs are exact in tf32; in fp32 parity
+//     mode every product is done as 3xTF32 (hi*hi + hi*lo + lo*hi), which is fp32-accurate.
+//   * backward: one CTA per (graph, dir, head): phase A (row tiles over warps) dP, dL, dQ; phase B
+//     (head-dim slices over warps) dK, dV' from shared-memory copies; dL overwrites P in place and a
+//     separate pair-tiled kernel reduces dW_g/db_g with recomputed embeddings.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace regat {
+namespace {
+
+constexpr int EMB = 64;        // imp_pos_emb_dim (butd_vqa.json:11); 8 wavelengths x {sin,cos} x 4 terms
+constexpr int HD = 64;         // head dim (graph_att_layer.py:23 with 1024/16)
+constexpr int ROWS = 16;       // query rows per forward CTA = one mma m-tile
+constexpr int MAX_ROIS = 128;
+constexpr int MAX_DH = 32;      // dir_num * num_heads handled by one CTA
+
+struct WaveDiv { float d[8]; };
+
+// ------------------------------------------------------------------------------------------
+// geometry (same fp32 operation order as position_emb.py:122-142 and :104-108)
+__device__ __forceinline__ float4 box_terms(const float* bx) {
+  float x1 = bx[0], y1 = bx[1], x2 = bx[2], y2 = bx[3];
+  return make_float4(x2 - x1 + 1.f, y2 - y1 + 1.f, 0.5f * (x1 + x2), 0.5f * (y1 + y2));  // w,h,cx,cy
+}
+
+__device__ __forceinline__ void pair_log_geometry(const float4& oi, const float4& oj, float (&P)[4]) {
+  float dx = fabsf(__fdiv_rn(oi.z - oj.z, oi.x));
+  float dy = fabsf(__fdiv_rn(oi.w - oj.w, oi.y));
+  P[0] = logf(dx < 1e-3f ? 1e-3f : dx);
+  P[1] = logf(dy < 1e-3f ? 1e-3f : dy);
+  P[2] = logf(__fdiv_rn(oi.x, oj.x));
+  P[3] = logf(__fdiv_rn(oi.y, oj.y));
+}
+
+// the 16 features of one geometry term: [k] = sin(100*P/div_k), [8+k] = cos(...)  (position_emb.py:104-113)
+__device__ __forceinline__ void embedding_group(float Pc, const WaveDiv& wd, float (&emb)[16]) {
+  const float x = 100.0f * Pc;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sincosf(__fdiv_rn(x, wd.d[k]), &emb[k], &emb[8 + k]);
+}
+
+// feature c*16+k = sin(100*P_c/div_k), c*16+8+k = cos(...)   (position_emb.py:104-113)
+__device__ __forceinline__ void pair_embedding(const float4& oi, const float4& oj, const WaveDiv& wd,
+                                               float (&emb)[EMB]) {
+  float P[4];
+  pair_log_geometry(oi, oj, P);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float x = 100.0f * P[c];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float sn, cs;
+      sincosf(__fdiv_rn(x, wd.d[k]), &sn, &cs);
+      emb[c * 16 + k] = sn;
+      emb[c * 16 + 8 + k] = cs;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// mma.sync m16n8k8 tf32 helpers
+__device__ __forceinline__ uint32_t tf32_of(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// operand prepared once, used for 1 (bf16 mode) or 3 (fp32 mode, 3xTF32) mma
+template <bool S3, int NR> struct Opnd {
+  uint32_t hi[NR];
+  uint32_t lo[S3 ? NR : 1];
+  __device__ __forceinline__ void set(int i, float x) {
+    hi[i] = tf32_of(x);
+    if constexpr (S3) lo[i] = tf32_of(x - __uint_as_float(hi[i]));
+  }
+};
+template <bool S3>
+__device__ __forceinline__ void mma_acc(float (&c)[4], const Opnd<S3, 4>& a, const Opnd<S3, 2>& b) {
+  if constexpr (S3) {
+    mma_tf32(c, a.lo, b.hi);
+    mma_tf32(c, a.hi, b.lo);
+  }
+  mma_tf32(c, a.hi, b.hi);
+}
+
+// ------------------------------------------------------------------------------------------
+// fragment loads.  A 64-wide head slice of one row is split over the 4 lanes of a quad (t = lane%4) so
+// that every lane issues only 128-bit loads; k-step s (0..7) of the mma takes (v[2s], v[2s+1]) as its
+// (k=t, k=t+4) pair.  A and B rows use the same map, so the dot product is unchanged.
+template <typename T> __device__ __forceinline__ void load_row16(const T* row, int t, float (&v)[16]);
+template <> __device__ __forceinline__ void load_row16<float>(const float* row, int t, float (&v)[16]) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    float4 x = __ldg(reinterpret_cast<const float4*>(row + 16 * kk + 4 * t));
+    v[4 * kk] = x.x; v[4 * kk + 1] = x.y; v[4 * kk + 2] = x.z; v[4 * kk + 3] = x.w;
+  }
+}
+template <> __device__ __forceinline__ void load_row16<bf16>(const bf16* row, int t, float (&v)[16]) {
+#pragma unroll
+  for (int kk = 0; kk < 2; ++kk) {
+    uint4 x = __ldg(reinterpret_cast<const uint4*>(row + 32 * kk + 8 * t));
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      v[8 * kk + 2 * i] = __uint_as_float(w[i] << 16);
+      v[8 * kk + 2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+}
+// which element (0..63) of the head slice v[idx] is
+template <typename T> __device__ __forceinline__ int row16_elem(int idx, int t) {
+  if constexpr (sizeof(T) == 4) return 16 * (idx >> 2) + 4 * t + (idx & 3);
+  else return 32 * (idx >> 3) + 8 * t + (idx & 7);
+}
+// 8 contiguous elements
+template <typename T> __device__ __forceinline__ void load8c(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void load8c<float>(const float* p, float (&v)[8]) {
+  float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8c<bf16>(const bf16* p, float (&v)[8]) {
+  uint4 x = __ldg(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[2 * i] = __uint_as_float(w[i] << 16);
+    v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+template <typename T> __device__ __forceinline__ void store_n(T* p, const float* v, int n);  // n multiple of 4 (fp32) / 8 (bf16)
+template <> __device__ __forceinline__ void store_n<float>(float* p, const float* v, int n) {
+  for (int i = 0; i < n; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+}
+template <> __device__ __forceinline__ void store_n<bf16>(bf16* p, const float* v, int n) {
+  for (int i = 0; i < n; i += 8) {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(v[i + 2 * k], v[i + 2 * k + 1]);
+      w[k] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p + i) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+template <typename T> __device__ __forceinline__ void store4(T* p, float a, float b, float c, float d) {
+  if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+  } else {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+}
+
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v;
+}
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return v;
+}
+
+// padded key stride of the per-CTA bias tile: multiple of 8 and == 8 (mod 16) so that the 64-bit
+// C-fragment reads of a half-warp hit 16 distinct bank pairs.
+__host__ __device__ inline int bias_stride(int M) {
+  int mp = (M + 7) / 8 * 8;
+  return (mp % 16 == 0) ? mp + 8 : mp;
+}
+
+// ==========================================================================================
+// forward
+struct FwdParams {
+  int B, N, M, D, H, dirs, MP, residual;
+  const void* q; const void* kv;
+  const float* boxes; const float* pos_emb; WaveDiv wd;
+  const float* wg; long long wg_stride; const float* alpha_g; const float* bg; long long bg_stride;
+  const float* label_c;
+  const void* s; const void* v0; void* v1;
+  float* save_p; float* save_gb; unsigned long long* gate;
+};
+
+template <typename T, bool S3, int NTS>
+__global__ void __launch_bounds__(256, 2) geoattn_fwd_kernel(const FwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int DH = p.dirs * p.H;
+  float4* obj = reinterpret_cast<float4*>(smem_raw);                 // [MAX_ROIS]
+  float* wgs = reinterpret_cast<float*>(obj + MAX_ROIS);             // [EMB][DH]
+  float* bgs = wgs + EMB * DH;                                       // [DH]
+  float* ags = bgs + DH;                                             // [DH] alpha per (d,h)
+  float* tile = ags + DH;                                            // [DH][ROWS][MP]
+  const int tid = threadIdx.x, b = blockIdx.y, i0 = blockIdx.x * ROWS;
+  const int N = p.N, M = p.M, MP = p.MP, D = p.D, H = p.H;
+
+  // ---- phase 0: per-object terms and the pair_pos_fc weights into shared memory
+  for (int n = tid; n < N; n += 256) obj[n] = p.boxes ? box_terms(p.boxes + ((size_t)b * N + n) * 4) : make_float4(1, 1, 0, 0);
+  for (int x = tid; x < EMB * DH; x += 256) {
+    int e = x / DH, dh = x - e * DH, d = dh / H, h = dh - d * H;
+    wgs[x] = p.wg[(size_t)d * p.wg_stride + e * H + h];
+  }
+  for (int dh = tid; dh < DH; dh += 256) {
+    int d = dh / H, h = dh - d * H;
+    bgs[dh] = p.bg ? p.bg[(size_t)d * p.bg_stride + h] : 0.f;
+    ags[dh] = p.alpha_g[d];
+  }
+  __syncthreads();
+
+  // ---- phase 1: geometry bias for the 16 x M pairs of this row tile, all heads and directions.
+  // bias[i,j] belongs to box pair (f / N, f % N), f = i*M + j  (graph_att_layer.py:74,81 raw reshape of
+  // the row-sliced [M,N] tensor from position_emb.py:146).
+  for (int pi = tid; pi < ROWS * M; pi += 256) {
+    const int il = pi / M, j = pi - il * M, i = i0 + il;
+    if (i < N) {
+      const int f = i * M + j;
+      float P[4] = {0.f, 0.f, 0.f, 0.f};
+      const float4* src = nullptr;
+      if (p.pos_emb) {
+        src = reinterpret_cast<const float4*>(p.pos_emb + ((size_t)b * M * N + f) * EMB);
+      } else {
+        const int ip = f / N, jp = f - ip * N;
+        pair_log_geometry(obj[ip], obj[jp], P);
+      }
+      // z[dh] accumulated over the four 16-feature groups (sin x8, cos x8 of one geometry term), so only
+      // 16 embedding values are live at a time.
+      float zacc[MAX_DH];
+#pragma unroll
+      for (int u = 0; u < MAX_DH; ++u) zacc[u] = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        float emb[16];
+        if (src) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            float4 x = __ldg(src + 4 * c + k);
+            emb[4 * k] = x.x; emb[4 * k + 1] = x.y; emb[4 * k + 2] = x.z; emb[4 * k + 3] = x.w;
+          }
+        } else {
+          embedding_group(P[c], p.wd, emb);
+        }
+#pragma unroll
+        for (int dh0 = 0; dh0 < MAX_DH; dh0 += 4) {
+          if (dh0 < DH) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+              const float4 w = *reinterpret_cast<const float4*>(wgs + (c * 16 + e) * DH + dh0);
+              zacc[dh0] = fmaf(emb[e], w.x, zacc[dh0]); zacc[dh0 + 1] = fmaf(emb[e], w.y, zacc[dh0 + 1]);
+              zacc[dh0 + 2] = fmaf(emb[e], w.z, zacc[dh0 + 2]); zacc[dh0 + 3] = fmaf(emb[e], w.w, zacc[dh0 + 3]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int dh = 0; dh < MAX_DH; ++dh) {
+        if (dh < DH) {
+          const float z = fmaf(ags[dh], zacc[dh], bgs[dh]);
+          const float gb = logf(fmaxf(fmaxf(z, 0.f), 1e-6f));           // graph_att_layer.py:79,86,88
+          tile[(dh * ROWS + il) * MP + j] = gb;
+          if (p.save_gb) p.save_gb[(((size_t)b * DH + dh) * N + i) * M + j] = gb;
+        }
+      }
+    } else {
+      for (int dh = 0; dh < DH; ++dh) tile[(dh * ROWS + il) * MP + j] = 0.f;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: attention.  warp <-> head; lane (g = lane/4, t = lane%4) in mma fragment terms.
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const T* Q = static_cast<const T*>(p.q);
+  const T* KV = static_cast<const T*>(p.kv);
+  const int ldq = p.dirs * D, ldkv = 2 * p.dirs * D;
+  const float c_label = p.label_c ? __ldg(p.label_c) : 0.f;
+  const int r0 = i0 + g, r1 = i0 + g + 8;                      // the two query rows this lane touches
+  const int r0c = min(r0, N - 1), r1c = min(r1, N - 1);
+
+  for (int h = warp; h < H; h += 8) {
+    float oacc[8][4];
+#pragma unroll
+    for (int ot = 0; ot < 8; ++ot) { oacc[ot][0] = oacc[ot][1] = oacc[ot][2] = oacc[ot][3] = 0.f; }
+
+    for (int d = 0; d < p.dirs; ++d) {
+      const int dh = d * H + h;
+      // S = Q K^T
+      float qa[16], qb[16];
+      load_row16<T>(Q + ((size_t)b * N + r0c) * ldq + d * D + h * HD, t, qa);
+      load_row16<T>(Q + ((size_t)b * N + r1c) * ldq + d * D + h * HD, t, qb);
+      float sacc[NTS][4];
+#pragma unroll
+      for (int nt = 0; nt < NTS; ++nt) { sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f; }
+#pragma unroll
+      for (int nt = 0; nt < NTS; ++nt) {
+        if (nt * 8 < M) {
+          float kr[16];
+          load_row16<T>(KV + ((size_t)b * M + min(nt * 8 + g, M - 1)) * ldkv + d * D + h * HD, t, kr);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            Opnd<S3, 4> a; Opnd<S3, 2> bb;
+            a.set(0, qa[2 * ks]); a.set(1, qb[2 * ks]); a.set(2, qa[2 * ks + 1]); a.set(3, qb[2 * ks + 1]);
+            bb.set(0, kr[2 * ks]); bb.set(1, kr[2 * ks + 1]);
+            mma_acc<S3>(sacc[nt], a, bb);
+          }
+        }
+      }
+      // logits = S/sqrt(dh) + geometry bias + label const; mask padded key columns; softmax over keys
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < NTS; ++nt) {
+        const int c0 = nt * 8 + 2 * t;
+        const float2 b0 = *reinterpret_cast<const float2*>(tile + (dh * ROWS + g) * MP + min(c0, MP - 2));
+        const float2 b1 = *reinterpret_cast<const float2*>(tile + (dh * ROWS + g + 8) * MP + min(c0, MP - 2));
+        sacc[nt][0] = c0 < M ? fmaf(sacc[nt][0], 0.125f, b0.x + c_label) : -INFINITY;
+        sacc[nt][1] = c0 + 1 < M ? fmaf(sacc[nt][1], 0.125f, b0.y + c_label) : -INFINITY;
+        sacc[nt][2] = c0 < M ? fmaf(sacc[nt][2], 0.125f, b1.x + c_label) : -INFINITY;
+        sacc[nt][3] = c0 + 1 < M ? fmaf(sacc[nt][3], 0.125f, b1.y + c_label) : -INFINITY;
+        mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
+      }
+      mx0 = quad_max(mx0); mx1 = quad_max(mx1);
+      float sm0 = 0.f, sm1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NTS; ++nt) {
+        sacc[nt][0] = expf(sacc[nt][0] - mx0); sacc[nt][1] = expf(sacc[nt][1] - mx0);
+        sacc[nt][2] = expf(sacc[nt][2] - mx1); sacc[nt][3] = expf(sacc[nt][3] - mx1);
+        sm0 += sacc[nt][0] + sacc[nt][1]; sm1 += sacc[nt][2] + sacc[nt][3];
+      }
+      const float inv0 = 1.f / quad_sum(sm0), inv1 = 1.f / quad_sum(sm1);
+#pragma unroll
+      for (int nt = 0; nt < NTS; ++nt) {
+        sacc[nt][0] *= inv0; sacc[nt][1] *= inv0; sacc[nt][2] *= inv1; sacc[nt][3] *= inv1;
+        if (p.save_p) {
+          const int c0 = nt * 8 + 2 * t;
+          float* pr0 = p.save_p + (((size_t)b * DH + dh) * N + r0) * M;
+          float* pr1 = p.save_p + (((size_t)b * DH + dh) * N + r1) * M;
+          if (r0 < N) { if (c0 < M) pr0[c0] = sacc[nt][0]; if (c0 + 1 < M) pr0[c0 + 1] = sacc[nt][1]; }
+          if (r1 < N) { if (c0 < M) pr1[c0] = sacc[nt][2]; if (c0 + 1 < M) pr1[c0 + 1] = sacc[nt][3]; }
+        }
+      }
+      // O += P V'.  k-step nt uses keys (8nt+2t, 8nt+2t+1) as (k=t, k=t+4): the C fragment of P is already
+      // the A fragment.  Output n-tile ot, column g stands for head-dim element 8g+ot, so a lane loads 8
+      // contiguous V' elements per key and ends up owning 16 contiguous output elements per row.
+#pragma unroll
+      for (int nt = 0; nt < NTS; ++nt) {
+        if (nt * 8 < M) {
+          float va[8], vb[8];
+          const int j0 = min(nt * 8 + 2 * t, M - 1), j1 = min(nt * 8 + 2 * t + 1, M - 1);
+          load8c<T>(KV + ((size_t)b * M + j0) * ldkv + (p.dirs + d) * D + h * HD + 8 * g, va);
+          load8c<T>(KV + ((size_t)b * M + j1) * ldkv + (p.dirs + d) * D + h * HD + 8 * g, vb);
+          Opnd<S3, 4> a;
+          a.set(0, sacc[nt][0]); a.set(1, sacc[nt][2]); a.set(2, sacc[nt][1]); a.set(3, sacc[nt][3]);
+#pragma unroll
+          for (int ot = 0; ot < 8; ++ot) {
+            Opnd<S3, 2> bb;
+            bb.set(0, va[ot]); bb.set(1, vb[ot]);
+            mma_acc<S3>(oacc[ot], a, bb);
+          }
+        }
+      }
+    }  // dirs
+
+    // epilogue: lane owns head-dim elements [16t, 16t+16) of rows r0 and r1
+    const T* S = static_cast<const T*>(p.s);
+    const T* V0 = static_cast<const T*>(p.v0);
+    T* V1 = static_cast<T*>(p.v1);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int r = half ? r1 : r0;
+      unsigned long long bits = 0ull;
+      if (r < N) {
+        const size_t off = ((size_t)b * N + r) * D + h * HD + 16 * t;
+        float sv[16], vv[16], out[16];
+        load8c<T>(S + off, *reinterpret_cast<float(*)[8]>(&sv[0]));
+        load8c<T>(S + off + 8, *reinterpret_cast<float(*)[8]>(&sv[8]));
+        if (p.residual) {
+          load8c<T>(V0 + off, *reinterpret_cast<float(*)[8]>(&vv[0]));
+          load8c<T>(V0 + off + 8, *reinterpret_cast<float(*)[8]>(&vv[8]));
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const float o = oacc[u & 7][(u >> 3) + 2 * half];      // element 16t+u <- tile (u%8), col 2t + u/8
+          const float x = sv[u] + o;
+          if (x > 0.f) bits |= 1ull << (16 * t + u);
+          out[u] = (p.residual ? vv[u] : 0.f) + fmaxf(x, 0.f);
+        }
+        store_n<T>(V1 + off, out, 16);
+      }
+      if (p.gate) {
+        bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+        bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+        if (t == 0 && r < N) p.gate[((size_t)b * N + r) * H + h] = bits;
+      }
+    }
+  }
+}
+
+// ==========================================================================================
+// attention backward: one CTA (4 warps) per (graph, dir, head)
+struct BwdParams {
+  int B, N, M, D, H, dirs, NP;       // NP = N rounded up to 16
+  const void* q; const void* kv; const void* dv1; const unsigned long long* gate;
+  float* p_dl; void* dq; void* dkv; void* dout;
+};
+constexpr int LDX = HD + 8;          // smem row stride of the Q / dO tiles (== 8 mod 32: conflict-free float2 reads)
+
+template <int NTS> __host__ __device__ constexpr int tile_ld() { return (NTS * 8 % 32 == 8) ? NTS * 8 : (NTS * 8 / 32) * 32 + 40; }
+
+template <typename T, bool S3, int NTS>
+__global__ void __launch_bounds__(128) attn_bwd_kernel(const BwdParams p) {
+  constexpr int LDT = tile_ld<NTS>();        // stride of the dL / P tiles, == 8 (mod 32)
+  constexpr int MJ = (NTS + 1) / 2;          // 16-row tiles over keys
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* Qs = reinterpret_cast<float*>(smem_raw);   // [NP][LDX]
+  float* dOs = Qs + p.NP * LDX;                     // [NP][LDX]   gated dO
+  float* Ls = dOs + p.NP * LDX;                     // [NP][LDT]   dL
+  float* Ps = Ls + p.NP * LDT;                      // [NP][LDT]   P
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int N = p.N, M = p.M, D = p.D, H = p.H, NP = p.NP;
+  const int h = blockIdx.x % H, d = (blockIdx.x / H) % p.dirs, b = blockIdx.x / (H * p.dirs);
+  const int dh = d * H + h;
+  const int ldq = p.dirs * D, ldkv = 2 * p.dirs * D;
+  const T* Q = static_cast<const T*>(p.q);
+  const T* KV = static_cast<const T*>(p.kv);
+  const T* dV1 = static_cast<const T*>(p.dv1);
+
+  // ---- fill Qs, dOs (gated by the saved relu mask) with coalesced loads; direction 0 also emits dout
+  for (int x = tid; x < NP * (HD / 8); x += 128) {
+    const int i = x / (HD / 8), e0 = (x % (HD / 8)) * 8;
+    float qv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (i < N) {
+      load8c<T>(Q + ((size_t)b * N + i) * ldq + d * D + h * HD + e0, qv);
+      load8c<T>(dV1 + ((size_t)b * N + i) * D + h * HD + e0, dv);
+      const unsigned long long bits = __ldg(p.gate + ((size_t)b * N + i) * H + h);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) dv[u] = ((bits >> (e0 + u)) & 1ull) ? dv[u] : 0.f;
+      if (d == 0) store_n<T>(static_cast<T*>(p.dout) + ((size_t)b * N + i) * D + h * HD + e0, dv, 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { Qs[i * LDX + e0 + u] = qv[u]; dOs[i * LDX + e0 + u] = dv[u]; }
+  }
+  // zero the key padding of the dL / P tiles (columns >= M are never written below)
+  for (int x = tid; x < NP * LDT; x += 128) { Ls[x] = 0.f; Ps[x] = 0.f; }
+  __syncthreads();
+
+  // ---- phase A: per 16-row tile: dP = dO V'^T, dL = P o (dP - rowsum(P o dP)), dQ = dL K / 8
+  float* P_g = p.p_dl + ((size_t)b * p.dirs * H + dh) * N * M;
+  for (int mt = warp; mt * 16 < N; mt += 4) {
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    // gated dO rows as A fragments, same per-lane element map as the V' rows below
+    float da[16], db[16];
+    {
+      const int r0c = min(r0, N - 1), r1c = min(r1, N - 1);
+      load_row16<T>(dV1 + ((size_t)b * N + r0c) * D + h * HD, t, da);
+      load_row16<T>(dV1 + ((size_t)b * N + r1c) * D + h * HD, t, db);
+      const unsigned long long g0 = r0 < N ? __ldg(p.gate + ((size_t)b * N + r0c) * H + h) : 0ull;
+      const unsigned long long g1 = r1 < N ? __ldg(p.gate + ((size_t)b * N + r1c) * H + h) : 0ull;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        const int e = row16_elem<T>(u, t);
+        da[u] = ((g0 >> e) & 1ull) ? da[u] : 0.f;
+        db[u] = ((g1 >> e) & 1ull) ? db[u] : 0.f;
+      }
+    }
+    float sacc[NTS][4];
+#pragma unroll
+    for (int nt = 0; nt < NTS; ++nt) {
+      sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
+      if (nt * 8 < M) {
+        float vr[16];
+        load_row16<T>(KV + ((size_t)b * M + min(nt * 8 + g, M - 1)) * ldkv + (p.dirs + d) * D + h * HD, t, vr);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          Opnd<S3, 4> a; Opnd<S3, 2> bb;
+          a.set(0, da[2 * ks]); a.set(1, db[2 * ks]); a.set(2, da[2 * ks + 1]); a.set(3, db[2 * ks + 1]);
+          bb.set(0, vr[2 * ks]); bb.set(1, vr[2 * ks + 1]);
+          mma_acc<S3>(sacc[nt], a, bb);
+        }
+      }
+    }
+    float pr[NTS][4];
+    float dl0 = 0.f, dl1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NTS; ++nt) {
+      const int c0 = nt * 8 + 2 * t;
+      pr[nt][0] = (r0 < N && c0 < M) ? P_g[(size_t)r0 * M + c0] : 0.f;
+      pr[nt][1] = (r0 < N && c0 + 1 < M) ? P_g[(size_t)r0 * M + c0 + 1] : 0.f;
+      pr[nt][2] = (r1 < N && c0 < M) ? P_g[(size_t)r1 * M + c0] : 0.f;
+      pr[nt][3] = (r1 < N && c0 + 1 < M) ? P_g[(size_t)r1 * M + c0 + 1] : 0.f;
+      dl0 += pr[nt][0] * sacc[nt][0] + pr[nt][1] * sacc[nt][1];
+      dl1 += pr[nt][2] * sacc[nt][2] + pr[nt][3] * sacc[nt][3];
+    }
+    dl0 = quad_sum(dl0); dl1 = quad_sum(dl1);
+    float dqacc[8][4];
+#pragma unroll
+    for (int ot = 0; ot < 8; ++ot) { dqacc[ot][0] = dqacc[ot][1] = dqacc[ot][2] = dqacc[ot][3] = 0.f; }
+#pragma unroll
+    for (int nt = 0; nt < NTS; ++nt) {
+      const int c0 = nt * 8 + 2 * t;
+      float dl[4];
+      dl[0] = pr[nt][0] * (sacc[nt][0] - dl0); dl[1] = pr[nt][1] * (sacc[nt][1] - dl0);
+      dl[2] = pr[nt][2] * (sacc[nt][2] - dl1); dl[3] = pr[nt][3] * (sacc[nt][3] - dl1);
+      if (r0 < N) { if (c0 < M) P_g[(size_t)r0 * M + c0] = dl[0]; if (c0 + 1 < M) P_g[(size_t)r0 * M + c0 + 1] = dl[1]; }
+      if (r1 < N) { if (c0 < M) P_g[(size_t)r1 * M + c0] = dl[2]; if (c0 + 1 < M) P_g[(size_t)r1 * M + c0 + 1] = dl[3]; }
+      if (c0 < NTS * 8) {
+        *reinterpret_cast<float2*>(Ls + r0 * LDT + c0) = make_float2(dl[0], dl[1]);
+        *reinterpret_cast<float2*>(Ls + r1 * LDT + c0) = make_float2(dl[2], dl[3]);
+        *reinterpret_cast<float2*>(Ps + r0 * LDT + c0) = make_float2(pr[nt][0], pr[nt][1]);
+        *reinterpret_cast<float2*>(Ps + r1 * LDT + c0) = make_float2(pr[nt][2], pr[nt][3]);
+      }
+      if (nt * 8 < M) {
+        float ka[8], kb[8];
+        const int j0 = min(nt * 8 + 2 * t, M - 1), j1 = min(nt * 8 + 2 * t + 1, M - 1);
+        load8c<T>(KV + ((size_t)b * M + j0) * ldkv + d * D + h * HD + 8 * g, ka);
+        load8c<T>(KV + ((size_t)b * M + j1) * ldkv + d * D + h * HD + 8 * g, kb);
+        Opnd<S3, 4> a;
+        a.set(0, dl[0]); a.set(1, dl[2]); a.set(2, dl[1]); a.set(3, dl[3]);
+#pragma unroll
+        for (int ot = 0; ot < 8; ++ot) {
+          Opnd<S3, 2> bb;
+          bb.set(0, ka[ot]); bb.set(1, kb[ot]);
+          mma_acc<S3>(dqacc[ot], a, bb);
+        }
+      }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int r = half ? r1 : r0;
+      if (r < N) {
+        float out[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) out[u] = 0.125f * dqacc[u & 7][(u >> 3) + 2 * half];
+        store_n<T>(static_cast<T*>(p.dq) + ((size_t)b * N + r) * ldq + d * D + h * HD + 16 * t, out, 16);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B: dK = dL^T Q / 8, dV' = P^T dO.  warp w owns head-dim elements [16w, 16w+16);
+  // n-tile ot in {0,1}, column g <-> element 16w + 2g + ot;  k index = query row.
+  float dk[MJ][2][4], dv[MJ][2][4];
+#pragma unroll
+  for (int jm = 0; jm < MJ; ++jm)
+#pragma unroll
+    for (int ot = 0; ot < 2; ++ot)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { dk[jm][ot][u] = 0.f; dv[jm][ot][u] = 0.f; }
+  for (int ks = 0; ks * 8 < NP; ++ks) {
+    const int i0 = ks * 8 + t, i1 = i0 + 4;
+    const float2 q0 = *reinterpret_cast<const float2*>(Qs + i0 * LDX + 16 * warp + 2 * g);
+    const float2 q1 = *reinterpret_cast<const float2*>(Qs + i1 * LDX + 16 * warp + 2 * g);
+    const float2 o0 = *reinterpret_cast<const float2*>(dOs + i0 * LDX + 16 * warp + 2 * g);
+    const float2 o1 = *reinterpret_cast<const float2*>(dOs + i1 * LDX + 16 * warp + 2 * g);
+    Opnd<S3, 2> bq[2], bo[2];
+    bq[0].set(0, q0.x); bq[0].set(1, q1.x); bq[1].set(0, q0.y); bq[1].set(1, q1.y);
+    bo[0].set(0, o0.x); bo[0].set(1, o1.x); bo[1].set(0, o0.y); bo[1].set(1, o1.y);
+#pragma unroll
+    for (int jm = 0; jm < MJ; ++jm) {
+      if (jm * 16 < M) {
+        Opnd<S3, 4> al, ap;
+        const int ja = jm * 16 + g, jb = min(ja + 8, LDT - 1);
+        al.set(0, Ls[i0 * LDT + ja]); al.set(1, Ls[i0 * LDT + jb]); al.set(2, Ls[i1 * LDT + ja]); al.set(3, Ls[i1 * LDT + jb]);
+        ap.set(0, Ps[i0 * LDT + ja]); ap.set(1, Ps[i0 * LDT + jb]); ap.set(2, Ps[i1 * LDT + ja]); ap.set(3, Ps[i1 * LDT + jb]);
+#pragma unroll
+        for (int ot = 0; ot < 2; ++ot) {
+          mma_acc<S3>(dk[jm][ot], al, bq[ot]);
+          mma_acc<S3>(dv[jm][ot], ap, bo[ot]);
+        }
+      }
+    }
+  }
+  T* dKV = static_cast<T*>(p.dkv);
+#pragma unroll
+  for (int jm = 0; jm < MJ; ++jm) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int j = jm * 16 + g + 8 * half;
+      if (j < M) {
+        // C fragment (row, cols 2t, 2t+1) of tile ot <-> elements 16w + 4t + {ot, 2 + ot}
+        T* rowp = dKV + ((size_t)b * M + j) * ldkv + h * HD + 16 * warp + 4 * t;
+        store4<T>(rowp + d * D, 0.125f * dk[jm][0][2 * half], 0.125f * dk[jm][1][2 * half],
+                  0.125f * dk[jm][0][2 * half + 1], 0.125f * dk[jm][1][2 * half + 1]);
+        store4<T>(rowp + (p.dirs + d) * D, dv[jm][0][2 * half], dv[jm][1][2 * half], dv[jm][0][2 * half + 1],
+                  dv[jm][1][2 * half + 1]);
+      }
+    }
+  }
+}
+
+// ==========================================================================================
+// geometry backward: dWg[d][e][h] += sum_pairs Emb[e] * dz[d,h],  dbg += sum dz,  dc += sum dL
+struct GeoBwdParams {
+  int B, N, M, H, dirs;
+  const float* boxes; const float* pos_emb; WaveDiv wd;
+  const float* dl; const float* gbias;
+  float* dwg; long long dwg_stride; float* dbg; long long dbg_stride; float* dc;
+};
+constexpr int GB_PAIRS = 256, GB_LDE = EMB + 1;
+
+template <int DH>   // DH = dirs*H, multiple of 8, <= 32
+__global__ void __launch_bounds__(256) geo_bwd_kernel(const GeoBwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* embS = reinterpret_cast<float*>(smem_raw);        // [GB_PAIRS][GB_LDE]
+  float* dzS = embS + GB_PAIRS * GB_LDE;                   // [GB_PAIRS][DH]
+  __shared__ float red[8];
+  const int tid = threadIdx.x;
+  const int N = p.N, M = p.M, NM = p.N * p.M;
+  const long long total = (long long)p.B * NM;
+  const float LOGMIN = logf(1e-6f);
+  constexpr int G = DH / 8;              // dh groups of 8
+  constexpr int EPT = EMB * G / 256 > 0 ? EMB * G / 256 : 1;   // e's per thread (1 for DH=32)
+  // thread -> (e, dh group): for DH=32: e = tid/4, grp = tid%4
+  const int grp = tid % G, e_base = (tid / G) * EPT;
+  const bool active = (tid / G) * EPT < EMB;
+  float acc[EPT][8];
+  float bsum[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) { bsum[u] = 0.f;
+#pragma unroll
+    for (int q = 0; q < EPT; ++q) acc[q][u] = 0.f; }
+  float csum = 0.f;
+
+  for (long long base = (long long)blockIdx.x * GB_PAIRS; base < total; base += (long long)gridDim.x * GB_PAIRS) {
+    const long long pi = base + tid;
+    float emb[EMB];
+    if (pi < total) {
+      const int b = (int)(pi / NM), f = (int)(pi - (long long)b * NM);
+      if (p.pos_emb) {
+        const float4* src = reinterpret_cast<const float4*>(p.pos_emb + ((size_t)b * NM + f) * EMB);
+#pragma unroll
+        for (int k = 0; k < EMB / 4; ++k) {
+          float4 x = __ldg(src + k);
+          emb[4 * k] = x.x; emb[4 * k + 1] = x.y; emb[4 * k + 2] = x.z; emb[4 * k + 3] = x.w;
+        }
+      } else {
+        const int ip = f / N, jp = f - ip * N;
+        pair_embedding(box_terms(p.boxes + ((size_t)b * N + ip) * 4), box_terms(p.boxes + ((size_t)b * N + jp) * 4), p.wd, emb);
+      }
+#pragma unroll
+      for (int dh = 0; dh < DH; ++dh) {
+        const size_t idx = ((size_t)b * DH + dh) * NM + f;
+        const float dl = __ldg(p.dl + idx), gb = __ldg(p.gbias + idx);
+        csum += dl;
+        dzS[tid * DH + dh] = gb > LOGMIN ? dl * expf(-gb) : 0.f;     // d log(max(relu(z),1e-6)) / dz
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < EMB; ++e) emb[e] = 0.f;
+#pragma unroll
+      for (int dh = 0; dh < DH; ++dh) dzS[tid * DH + dh] = 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < EMB; ++e) embS[tid * GB_LDE + e] = emb[e];
+    __syncthreads();
+    if (active) {
+      for (int q = 0; q < GB_PAIRS; ++q) {
+        const float4 z0 = *reinterpret_cast<const float4*>(dzS + q * DH + 8 * grp);
+        const float4 z1 = *reinterpret_cast<const float4*>(dzS + q * DH + 8 * grp + 4);
+        const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+#pragma unroll
+        for (int qq = 0; qq < EPT; ++qq) {
+          const float ev = embS[q * GB_LDE + e_base + qq];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc[qq][u] = fmaf(ev, zz[u], acc[qq][u]);
+        }
+        if (e_base == 0) {
+#pragma unroll
+          for (int u = 0; u < 8; ++u) bsum[u] += zz[u];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (active) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int dh = 8 * grp + u, d = dh / p.H, h = dh - d * p.H;
+#pragma unroll
+      for (int qq = 0; qq < EPT; ++qq) atomicAdd(p.dwg + (size_t)d * p.dwg_stride + (e_base + qq) * p.H + h, acc[qq][u]);
+      if (e_base == 0 && p.dbg) atomicAdd(p.dbg + (size_t)d * p.dbg_stride + h, bsum[u]);
+    }
+  }
+  csum = warp_sum(csum);
+  if ((tid & 31) == 0) red[tid >> 5] = csum;
+  __syncthreads();
+  if (tid == 0 && p.dc) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    atomicAdd(p.dc, s);
+  }
+}
+
+// ==========================================================================================
+// stage 1 standalone: materialised pos_emb [B,M,N,64] (compat path for prepare_graph_variables)
+__global__ void __launch_bounds__(256) pos_emb_kernel(const float* __restrict__ boxes, int B, int N, int M, WaveDiv wd,
+                                                      float* __restrict__ out) {
+  const long long total = (long long)B * M * N;
+  for (long long x = (long long)blockIdx.x * blockDim.x + threadIdx.x; x < total; x += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(x % N), i = (int)((x / N) % M), b = (int)(x / ((long long)N * M));
+    float emb[EMB];
+    pair_embedding(box_terms(boxes + ((size_t)b * N + i) * 4), box_terms(boxes + ((size_t)b * N + j) * 4), wd, emb);
+    float4* dst = reinterpret_cast<float4*>(out + x * EMB);
+#pragma unroll
+    for (int k = 0; k < EMB / 4; ++k) dst[k] = make_float4(emb[4 * k], emb[4 * k + 1], emb[4 * k + 2], emb[4 * k + 3]);
+  }
+}
+
+template <typename K> int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) REGAT_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return REGAT_OK;
+}
+
+template <typename T, bool S3>
+int launch_fwd(const FwdParams& p, cudaStream_t st) {
+  const int DH = p.dirs * p.H;
+  const size_t smem = sizeof(float4) * MAX_ROIS + sizeof(float) * ((size_t)EMB * DH + 2 * DH + (size_t)DH * ROWS * p.MP);
+  REGAT_REQUIRE(smem <= 227 * 1024, REGAT_ERR_UNSUPPORTED, "geoattn_fwd: bias tile needs %zu B of shared memory (nongt_dim too large)", smem);
+  dim3 grid(ceil_div(p.N, ROWS), p.B);
+  const int nts = ceil_div(p.M, 8);
+#define REGAT_FWD_CASE(NTS)                                                     \
+  {                                                                             \
+    REGAT_TRY(set_smem(geoattn_fwd_kernel<T, S3, NTS>, smem));                  \
+    geoattn_fwd_kernel<T, S3, NTS><<<grid, 256, smem, st>>>(p);                 \
+  }
+  if (nts <= 3) REGAT_FWD_CASE(3)
+  else if (nts <= 5) REGAT_FWD_CASE(5)
+  else if (nts <= 13) REGAT_FWD_CASE(13)
+  else REGAT_REQUIRE(false, REGAT_ERR_UNSUPPORTED, "geoattn_fwd: min(nongt_dim, N) = %d > 104 keys unsupported", p.M);
+#undef REGAT_FWD_CASE
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+
+template <typename T, bool S3, int NTS>
+int launch_bwd_nts(const BwdParams& p, cudaStream_t st) {
+  const size_t smem = sizeof(float) * (size_t)p.NP * (2 * LDX + 2 * tile_ld<NTS>());
+  REGAT_REQUIRE(smem <= 227 * 1024, REGAT_ERR_UNSUPPORTED, "attn_bwd: needs %zu B of shared memory", smem);
+  REGAT_TRY(set_smem(attn_bwd_kernel<T, S3, NTS>, smem));
+  attn_bwd_kernel<T, S3, NTS><<<p.B * p.dirs * p.H, 128, smem, st>>>(p);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+template <typename T, bool S3>
+int launch_bwd(const BwdParams& p, cudaStream_t st) {
+  const int nts = ceil_div(p.M, 8);
+  if (nts <= 3) return launch_bwd_nts<T, S3, 3>(p, st);
+  if (nts <= 5) return launch_bwd_nts<T, S3, 5>(p, st);
+  if (nts <= 13) return launch_bwd_nts<T, S3, 13>(p, st);
+  REGAT_REQUIRE(false, REGAT_ERR_UNSUPPORTED, "attn_bwd: min(nongt_dim, N) = %d > 104 keys unsupported", p.M);
+}
+
+int check_common(int B, int N, int D, int H, int dirs, int E) {
+  REGAT_REQUIRE(B > 0 && N > 0, REGAT_ERR_SHAPE, "geoattn: empty batch (B=%d, N=%d)", B, N);
+  REGAT_REQUIRE(N <= MAX_ROIS, REGAT_ERR_UNSUPPORTED, "geoattn: N=%d > %d objects unsupported", N, MAX_ROIS);
+  REGAT_REQUIRE(H > 0 && D == H * HD, REGAT_ERR_UNSUPPORTED, "geoattn: head dim must be 64 (rel_dim=%d, heads=%d)", D, H);
+  REGAT_REQUIRE(dirs >= 1 && dirs <= 2, REGAT_ERR_SHAPE, "geoattn: dir_num must be 1 or 2 (graph_att_net.py:18)");
+  REGAT_REQUIRE(E == EMB, REGAT_ERR_UNSUPPORTED, "geoattn: pos_emb_dim must be 64");
+  REGAT_REQUIRE((dirs * H) % 4 == 0 && dirs * H <= MAX_DH, REGAT_ERR_UNSUPPORTED,
+                "geoattn: dir_num*num_heads must be a multiple of 4 and <= 32");
+  return REGAT_OK;
+}
+
+}  // namespace
+}  // namespace regat
+
+using namespace regat;
+
+extern "C" int regat_position_embedding(const float* boxes, int B, int N, int nongt_dim, int feat_dim,
+                                        const float* wave_div_host, float* pos_emb, regat_stream_t stream) {
+  REGAT_REQUIRE(boxes && pos_emb && wave_div_host, REGAT_ERR_ARG, "position_embedding: null pointer");
+  REGAT_REQUIRE(feat_dim == EMB, REGAT_ERR_UNSUPPORTED, "position_embedding: feat_dim must be 64");
+  REGAT_REQUIRE(aligned16(pos_emb), REGAT_ERR_ALIGN, "position_embedding: output not 16-byte aligned");
+  if (B <= 0 || N <= 0) return REGAT_OK;
+  const int M = nongt_dim < N ? nongt_dim : N;
+  WaveDiv wd;
+  for (int k = 0; k < 8; ++k) wd.d[k] = wave_div_host[k];
+  const long long total = (long long)B * M * N;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 8);
+  pos_emb_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(boxes, B, N, M, wd, pos_emb);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+
+extern "C" int regat_geoattn_fwd(int dtype, int B, int N, int nongt_dim, int D, int H, int dirs, int E,
+                                 const void* q, const void* kv, const float* boxes, const float* pos_emb,
+                                 const float* wave_div_host, const float* wg, int64_t wg_stride,
+                                 const float* alpha_g, const float* bg, int64_t bg_stride, const float* label_c,
+                                 const void* s, const void* v0, int residual, void* v1, float* save_p,
+                                 float* save_gbias, uint64_t* gate, regat_stream_t stream) {
+  REGAT_TRY(check_common(B, N, D, H, dirs, E));
+  REGAT_REQUIRE(q && kv && wg && alpha_g && s && v1, REGAT_ERR_ARG, "geoattn_fwd: null pointer");
+  REGAT_REQUIRE((boxes != nullptr) != (pos_emb != nullptr), REGAT_ERR_ARG,
+                "geoattn_fwd: pass exactly one of boxes / pos_emb (graph_att_net.py:42-51)");
+  REGAT_REQUIRE(!boxes || wave_div_host, REGAT_ERR_ARG, "geoattn_fwd: wave_div_host missing");
+  REGAT_REQUIRE(!residual || v0, REGAT_ERR_ARG, "geoattn_fwd: residual needs v0");
+  REGAT_REQUIRE(aligned16(q) && aligned16(kv) && aligned16(s) && aligned16(v1) && (!v0 || aligned16(v0)) &&
+                    (!pos_emb || aligned16(pos_emb)),
+                REGAT_ERR_ALIGN, "geoattn_fwd: tensors must be 16-byte aligned");
+  REGAT_REQUIRE(dtype == REGAT_F32 || dtype == REGAT_BF16, REGAT_ERR_DTYPE, "geoattn_fwd: bad dtype %d", dtype);
+  FwdParams p;
+  p.B = B; p.N = N; p.M = nongt_dim < N ? nongt_dim : N; p.D = D; p.H = H; p.dirs = dirs;
+  p.MP = bias_stride(p.M); p.residual = residual;
+  p.q = q; p.kv = kv; p.boxes = boxes; p.pos_emb = pos_emb;
+  for (int k = 0; k < 8; ++k) p.wd.d[k] = wave_div_host ? wave_div_host[k] : 1.f;
+  p.wg = wg; p.wg_stride = wg_stride; p.alpha_g = alpha_g; p.bg = bg; p.bg_stride = bg_stride; p.label_c = label_c;
+  p.s = s; p.v0 = v0; p.v1 = v1; p.save_p = save_p; p.save_gb = save_gbias;
+  p.gate = reinterpret_cast<unsigned long long*>(gate);
+  if (dtype == REGAT_F32) return launch_fwd<float, true>(p, (cudaStream_t)stream);
+  return launch_fwd<bf16, false>(p, (cudaStream_t)stream);
+}
+
+extern "C" int regat_attn_bwd(int dtype, int B, int N, int nongt_dim, int D, int H, int dirs, const void* q,
+                              const void* kv, const void* dv1, const uint64_t* gate, float* p_inout_dl, void* dq,
+                              void* dkv, void* dout, regat_stream_t stream) {
+  REGAT_TRY(check_common(B, N, D, H, dirs, EMB));
+  REGAT_REQUIRE(q && kv && dv1 && gate && p_inout_dl && dq && dkv && dout, REGAT_ERR_ARG, "attn_bwd: null pointer");
+  REGAT_REQUIRE(aligned16(q) && aligned16(kv) && aligned16(dv1) && aligned16(dq) && aligned16(dkv) && aligned16(dout),
+                REGAT_ERR_ALIGN, "attn_bwd: tensors must be 16-byte aligned");
+  REGAT_REQUIRE(dtype == REGAT_F32 || dtype == REGAT_BF16, REGAT_ERR_DTYPE, "attn_bwd: bad dtype %d", dtype);
+  BwdParams p;
+  p.B = B; p.N = N; p.M = nongt_dim < N ? nongt_dim : N; p.D = D; p.H = H; p.dirs = dirs;
+  p.NP = (N + 15) / 16 * 16;
+  p.q = q; p.kv = kv; p.dv1 = dv1; p.gate = reinterpret_cast<const unsigned long long*>(gate);
+  p.p_dl = p_inout_dl; p.dq = dq; p.dkv = dkv; p.dout = dout;
+  if (dtype == REGAT_F32) return launch_bwd<float, true>(p, (cudaStream_t)stream);
+  return launch_bwd<bf16, false>(p, (cudaStream_t)stream);
+}
+
+extern "C" int regat_geo_bwd(int B, int N, int nongt_dim, int H, int dirs, int E, const float* boxes,
+                             const float* pos_emb, const float* wave_div_host, const float* dl, const float* gbias,
+                             float* dwg, int64_t dwg_stride, float* dbg, int64_t dbg_stride, float* dc,
+                             regat_stream_t stream) {
+  REGAT_REQUIRE(E == EMB, REGAT_ERR_UNSUPPORTED, "geo_bwd: pos_emb_dim must be 64");
+  REGAT_REQUIRE(dl && gbias && dwg, REGAT_ERR_ARG, "geo_bwd: null pointer");
+  REGAT_REQUIRE((boxes != nullptr) != (pos_emb != nullptr), REGAT_ERR_ARG, "geo_bwd: pass exactly one of boxes / pos_emb");
+  REGAT_REQUIRE(!boxes || wave_div_host, REGAT_ERR_ARG, "geo_bwd: wave_div_host missing");
+  if (B <= 0 || N <= 0) return REGAT_OK;
+  GeoBwdParams p;
+  p.B = B; p.N = N; p.M = nongt_dim < N ? nongt_dim : N; p.H = H; p.dirs = dirs;
+  p.boxes = boxes; p.pos_emb = pos_emb;
+  for (int k = 0; k < 8; ++k) p.wd.d[k] = wave_div_host ? wave_div_host[k] : 1.f;
+  p.dl = dl; p.gbias = gbias; p.dwg = dwg; p.dwg_stride = dwg_stride; p.dbg = dbg; p.dbg_stride = dbg_stride; p.dc = dc;
+  const int DH = dirs * H;
+  const size_t smem = sizeof(float) * (size_t)GB_PAIRS * (GB_LDE + DH);
+  const long long tiles = ((long long)B * p.N * p.M + GB_PAIRS - 1) / GB_PAIRS;
+  const int blocks = (int)std::min<long long>(tiles, (long long)num_sms() * 2);
+  cudaStream_t st = (cudaStream_t)stream;
+#define REGAT_GB_CASE(X)                                                   \
+  {                                                                        \
+    REGAT_TRY(set_smem(geo_bwd_kernel<X>, smem));                          \
+    geo_bwd_kernel<X><<<blocks, 256, smem, st>>>(p);                       \
+  }
+  if (DH == 32) REGAT_GB_CASE(32)
+  else if (DH == 16) REGAT_GB_CASE(16)
+  else if (DH == 8) REGAT_GB_CASE(8)
+  else REGAT_REQUIRE(false, REGAT_ERR_UNSUPPORTED, "geo_bwd: dir_num*num_heads must be 8, 16 or 32 (got %d)", DH);
+#undef REGAT_GB_CASE
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}

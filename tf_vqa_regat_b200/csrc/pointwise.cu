@@ -1,0 +1,621 @@
+// Bandwidth-bound helper kernels of the hot path: weight-norm statistics, padded-object mask,
+// BUTD pooling, BCE loss, bias gradients, per-tensor clip + Adamax.  All HBM-bound: coalesced
+// 128-bit accesses, grid sized in multiples of the SM count, warp-shuffle reductions.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace regat {
+namespace {
+
+template <typename T> struct Vec8;   // 8 elements = 16 B (bf16) or 32 B (fp32)
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float (&v)[8]) {
+  if constexpr (sizeof(T) == 4) {
+    float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  } else {
+    uint4 x = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+  }
+}
+template <typename T> __device__ __forceinline__ void st8(T* p, const float (&v)[8]) {
+  if constexpr (sizeof(T) == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]); w[k] = *reinterpret_cast<uint32_t*>(&h); }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {   // blockDim.x == 256
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+  }
+  __syncthreads();
+  return s;   // valid in warp 0
+}
+
+// ---------------------------------------------------------------- weight norm (weight_norm.py:35-41)
+constexpr int WN_CHUNK = 4096;   // elements per block
+__global__ void __launch_bounds__(256) wn_prepare_kernel(const float* __restrict__ params, TensorList tl, float* sumsq,
+                                                         bf16* lowp) {
+  __shared__ float red[8];
+  int l = 0;
+  while (l + 1 < tl.n && (int)blockIdx.x >= tl.chunk_start[l + 1]) ++l;
+  const long long base = (long long)(blockIdx.x - tl.chunk_start[l]) * WN_CHUNK;
+  const float* v = params + tl.off[l];
+  const long long n = tl.numel[l];
+  float ss = 0.f;
+  for (long long i = base + threadIdx.x; i < min(base + (long long)WN_CHUNK, n); i += 256) {
+    const float x = v[i];
+    ss = fmaf(x, x, ss);
+    if (lowp) {
+      const int cols = tl.cols[l];
+      const long long r = i / cols, c = i - r * cols;
+      lowp[tl.off_lowp[l] + r * tl.ld_lowp[l] + c] = __float2bfloat16_rn(x);
+    }
+  }
+  ss = block_sum_256(ss, red);
+  if (threadIdx.x == 0) atomicAdd(sumsq + l, ss);
+}
+
+__global__ void wn_alpha_kernel(const float* __restrict__ params, TensorList tl, const float* __restrict__ sumsq,
+                                float* alpha, float* inv_norm) {
+  const int l = threadIdx.x;
+  if (l < tl.n) {
+    const float inv = rsqrtf(fmaxf(sumsq[l], 1e-12f));     // tf.nn.l2_normalize epsilon
+    inv_norm[l] = inv;
+    alpha[l] = params[tl.g_off[l]] * inv;
+  }
+}
+
+// ---------------------------------------------------------------- casts / elementwise
+template <typename TO>
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in, TO* __restrict__ out, long long n8) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n8; i += (long long)gridDim.x * 256) {
+    float v[8];
+    ld8<float>(in + i * 8, v);
+    st8<TO>(out + i * 8, v);
+  }
+}
+
+// mask[r] = (sum_d v[r,d] != 0)  -- relation_encoder.py:20-21.  One warp per row.
+template <typename T>
+__global__ void __launch_bounds__(256) rowmask_kernel(const T* __restrict__ v, int rows, int D, float* __restrict__ mask) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int c = lane * 8; c < D; c += 256) {
+    float x[8];
+    ld8<T>(v + (size_t)r * D + c, x);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += x[u];
+  }
+  s = warp_sum(s);
+  if (lane == 0) mask[r] = s != 0.f ? 1.f : 0.f;
+}
+
+// out[r,c] = a[r,c]*b[r,c]   (joint = visual_embed * question_embed, fusion.py:39)
+template <typename T>
+__global__ void __launch_bounds__(256) mul_kernel(const T* __restrict__ a, int lda, const T* __restrict__ b, int ldb,
+                                                  T* __restrict__ out, int ldo, int rows, int cols) {
+  const long long n = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+    out[(size_t)r * ldo + c] = from_f<T>(to_f(a[(size_t)r * lda + c]) * to_f(b[(size_t)r * ldb + c]));
+  }
+}
+// da = dz*b, db = dz*a
+template <typename T>
+__global__ void __launch_bounds__(256) mul_bwd_kernel(const T* __restrict__ dz, int ldz, const T* __restrict__ a, int lda,
+                                                      const T* __restrict__ b, int ldb, T* __restrict__ da, int ldda,
+                                                      T* __restrict__ db, int lddb, int rows, int cols) {
+  const long long n = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const int r = (int)(i / cols), c = (int)(i - (long long)r * cols);
+    const float g = to_f(dz[(size_t)r * ldz + c]);
+    da[(size_t)r * ldda + c] = from_f<T>(g * to_f(b[(size_t)r * ldb + c]));
+    db[(size_t)r * lddb + c] = from_f<T>(g * to_f(a[(size_t)r * lda + c]));
+  }
+}
+
+// ---------------------------------------------------------------- BUTD (fusion.py:43-54, :34)
+// uw[b,c] = u[b,c] * (alpha_l * vl[c]);  cb[b] = sum_c bva[c]*uw[b,c] + bl
+template <typename T>
+__global__ void __launch_bounds__(256) butd_prep_kernel(const T* __restrict__ u, int ldu, const float* __restrict__ vl,
+                                                        const float* __restrict__ alpha_l, const float* __restrict__ bva,
+                                                        const float* __restrict__ bl, T* __restrict__ uw, float* __restrict__ cb,
+                                                        int Hd) {
+  __shared__ float red[8];
+  const int b = blockIdx.x;
+  const float al = *alpha_l;
+  float s = 0.f;
+  for (int c = threadIdx.x; c < Hd; c += 256) {
+    const float x = to_f(u[(size_t)b * ldu + c]) * (al * vl[c]);
+    const T xr = from_f<T>(x);
+    uw[(size_t)b * Hd + c] = xr;
+    s = fmaf(bva ? bva[c] : 0.f, to_f(xr), s);
+  }
+  s = block_sum_256(s, red);
+  if (threadIdx.x == 0) cb[b] = s + (bl ? *bl : 0.f);
+}
+// duw_tot = duw + dcb[b]*bva;  du = duw_tot * wl';  dwl[c] += sum_b duw_tot*u;  dbva[c] += sum_b dcb[b]*uw[b,c];  dbl += sum_b dcb
+template <typename T>
+__global__ void __launch_bounds__(256) butd_prep_bwd_kernel(const T* __restrict__ duw, const float* __restrict__ dcb,
+                                                            const T* __restrict__ u, int ldu, const T* __restrict__ uw,
+                                                            const float* __restrict__ vl, const float* __restrict__ alpha_l,
+                                                            const float* __restrict__ bva, T* __restrict__ du, int lddu,
+                                                            float* dwl, float* dbva, float* dbl, int B, int Hd) {
+  // one thread per column c, loops over b (B is a few hundred): coalesced across c
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < Hd) {
+    const float wl = *alpha_l * vl[c], bv = bva ? bva[c] : 0.f;
+    float sw = 0.f, sb = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const float g = to_f(duw[(size_t)b * Hd + c]) + dcb[b] * bv;
+      du[(size_t)b * lddu + c] = from_f<T>(g * wl);
+      sw = fmaf(g, to_f(u[(size_t)b * ldu + c]), sw);
+      sb = fmaf(dcb[b], to_f(uw[(size_t)b * Hd + c]), sb);
+    }
+    dwl[c] = sw;                 // gradient w.r.t. the effective [Hd,1] kernel of joint_emb.linear
+    if (dbva) dbva[c] = sb;
+  }
+  if (dbl && blockIdx.x == 0 && threadIdx.x == 0) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += dcb[b];
+    *dbl = s;
+  }
+}
+
+// One CTA per graph: logits over objects, softmax over N (padded rows included, fusion.py:54), weighted sum.
+template <typename T>
+__global__ void __launch_bounds__(256) butd_pool_fwd_kernel(const T* __restrict__ v1, const T* __restrict__ weff,
+                                                            const float* __restrict__ cb, float* __restrict__ att,
+                                                            T* __restrict__ pooled, int N, int D) {
+  extern __shared__ float sm[];      // [N] logits/att
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const T* vb = v1 + (size_t)b * N * D;
+  const T* wb = weff + (size_t)b * D;
+  for (int n = warp; n < N; n += 8) {
+    float s = 0.f;
+    for (int c = lane * 8; c < D; c += 256) {
+      float x[8], w[8];
+      ld8<T>(vb + (size_t)n * D + c, x);
+      ld8<T>(wb + c, w);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s = fmaf(x[u], w[u], s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) sm[n] = s + cb[b];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int n = lane; n < N; n += 32) mx = fmaxf(mx, sm[n]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int n = lane; n < N; n += 32) { const float e = expf(sm[n] - mx); sm[n] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int n = lane; n < N; n += 32) { const float a = sm[n] * inv; sm[n] = a; att[(size_t)b * N + n] = a; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x * 8; c < D; c += 256 * 8) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int n = 0; n < N; ++n) {
+      float x[8];
+      ld8<T>(vb + (size_t)n * D + c, x);
+      const float a = sm[n];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] = fmaf(a, x[u], acc[u]);
+    }
+    st8<T>(pooled + (size_t)b * D + c, acc);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) butd_pool_bwd_kernel(const T* __restrict__ v1, const T* __restrict__ weff,
+                                                            const float* __restrict__ att, const T* __restrict__ dpooled,
+                                                            T* __restrict__ dv1, T* __restrict__ dweff, float* __restrict__ dcb,
+                                                            int N, int D) {
+  extern __shared__ float sm[];      // [2N]: att, dlogit
+  float* a_s = sm; float* dl_s = sm + N;
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const T* vb = v1 + (size_t)b * N * D;
+  const T* dp = dpooled + (size_t)b * D;
+  for (int n = threadIdx.x; n < N; n += 256) a_s[n] = att[(size_t)b * N + n];
+  // da[n] = <dpooled, v1[n]>
+  for (int n = warp; n < N; n += 8) {
+    float s = 0.f;
+    for (int c = lane * 8; c < D; c += 256) {
+      float x[8], g[8];
+      ld8<T>(vb + (size_t)n * D + c, x);
+      ld8<T>(dp + c, g);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s = fmaf(x[u], g[u], s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) dl_s[n] = s;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float dot = 0.f;
+    for (int n = lane; n < N; n += 32) dot = fmaf(a_s[n], dl_s[n], dot);
+    dot = warp_sum(dot);
+    float tot = 0.f;
+    for (int n = lane; n < N; n += 32) { const float d = a_s[n] * (dl_s[n] - dot); dl_s[n] = d; tot += d; }
+    tot = warp_sum(tot);
+    if (lane == 0) dcb[b] = tot;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x * 8; c < D; c += 256 * 8) {
+    float g[8], w[8], acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    ld8<T>(dp + c, g);
+    ld8<T>(weff + (size_t)b * D + c, w);
+    for (int n = 0; n < N; ++n) {
+      float x[8], o[8];
+      ld8<T>(vb + (size_t)n * D + c, x);
+      const float a = a_s[n], d = dl_s[n];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { o[u] = fmaf(a, g[u], d * w[u]); acc[u] = fmaf(d, x[u], acc[u]); }
+      st8<T>(dv1 + ((size_t)b * N + n) * D + c, o);
+    }
+    st8<T>(dweff + (size_t)b * D + c, acc);
+  }
+}
+
+// ---------------------------------------------------------------- loss (train.py:20-26, 107-108; score :28-39)
+template <typename TD>
+__global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ logits, int ldl, const float* __restrict__ target,
+                                                  int A, float inv_B, float gscale, float* loss, float* score,
+                                                  TD* __restrict__ dlog, int ldd) {
+  __shared__ float red[8];
+  __shared__ float bestv[8];
+  __shared__ int besti[8];
+  const int b = blockIdx.x;
+  const float* x = logits + (size_t)b * ldl;
+  const float* z = target + (size_t)b * A;
+  float ls = 0.f, bv = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int a = threadIdx.x; a < ldd; a += 256) {
+    float g = 0.f;
+    if (a < A) {
+      const float xv = x[a], zv = z[a];
+      ls += fmaxf(xv, 0.f) - xv * zv + log1pf(expf(-fabsf(xv)));   // tf.nn.sigmoid_cross_entropy_with_logits
+      g = (1.f / (1.f + expf(-xv)) - zv) * inv_B * gscale;
+      if (xv > bv) { bv = xv; bi = a; }
+    }
+    if (dlog) dlog[(size_t)b * ldd + a] = from_f<TD>(g);
+  }
+  // argmax with first-index tie-break (np.argmax)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { bestv[threadIdx.x >> 5] = bv; besti[threadIdx.x >> 5] = bi; }
+  ls = block_sum_256(ls, red);      // contains __syncthreads
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (bestv[w] > bestv[0] || (bestv[w] == bestv[0] && besti[w] < besti[0])) { bestv[0] = bestv[w]; besti[0] = besti[w]; }
+    atomicAdd(loss, ls * inv_B);                 // mean over B*A, times A
+    if (score) atomicAdd(score, z[besti[0]]);
+  }
+}
+
+// ---------------------------------------------------------------- reductions for the backward
+// out[c] (+)= sum_r x[r,c]   (bias gradients).  grid.x over column blocks of 256, grid.y over row slabs; atomics.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int ld, int rows, int cols, float* out) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= cols) return;
+  const int rpb = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rpb, r1 = min(rows, r0 + rpb);
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s += to_f(x[(size_t)r * ld + c]);
+  if (r0 < r1) atomicAdd(out + c, s);
+}
+// out[b,c] = sum_n w[b*N+n] * x[(b*N+n), c]   (dsq: gradient reaching q through the mask, relation_encoder.py:31)
+template <typename T>
+__global__ void __launch_bounds__(256) segsum_kernel(const T* __restrict__ x, const float* __restrict__ w, int N, int D,
+                                                     T* __restrict__ out) {
+  const int b = blockIdx.y, c = (blockIdx.x * 256 + threadIdx.x) * 8;
+  if (c >= D) return;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int n = 0; n < N; ++n) {
+    const float wv = w[(size_t)b * N + n];
+    if (wv != 0.f) {
+      float v[8];
+      ld8<T>(x + ((size_t)b * N + n) * D + c, v);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] = fmaf(wv, v[u], acc[u]);
+    }
+  }
+  st8<T>(out + (size_t)b * D + c, acc);
+}
+// dst[b, n, :] += src[b*M + n, :] for n < M   (keys/values are the first M objects, graph_att_layer.py:43)
+template <typename T>
+__global__ void __launch_bounds__(256) addrows_kernel(T* __restrict__ dst, const T* __restrict__ src, int N, int M, int D,
+                                                      long long n8) {
+  const int d8 = D / 8;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n8; i += (long long)gridDim.x * 256) {
+    const long long row = i / d8;
+    const int c = (int)(i - row * d8) * 8;
+    const long long b = row / M, n = row - b * M;
+    float a[8], s[8];
+    T* dp = dst + ((size_t)b * N + n) * D + c;
+    ld8<T>(dp, a);
+    ld8<T>(src + (size_t)row * D + c, s);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) a[u] += s[u];
+    st8<T>(dp, a);
+  }
+}
+
+// ---------------------------------------------------------------- optimizer (train.py:112-113, weight_norm.py:41 backward)
+// pass 1: per tensor: dot = sum G*v, gg = sum G^2 (v tensors);  gg = sum g^2 (bias tensors)
+__global__ void __launch_bounds__(256) opt_reduce_kernel(const float* __restrict__ params, const float* __restrict__ grads,
+                                                         TensorList tl, float* stats /* [n][2] */) {
+  __shared__ float red[8];
+  int l = 0;
+  while (l + 1 < tl.n && (int)blockIdx.x >= tl.chunk_start[l + 1]) ++l;
+  const long long base = (long long)(blockIdx.x - tl.chunk_start[l]) * WN_CHUNK;
+  const long long n = tl.numel[l], end = min(base + (long long)WN_CHUNK, n);
+  const float* g = grads + tl.off[l];
+  const float* v = params + tl.off[l];
+  float dot = 0.f, gg = 0.f;
+  for (long long i = base + threadIdx.x; i < end; i += 256) {
+    const float gv = g[i];
+    dot = fmaf(gv, v[i], dot);
+    gg = fmaf(gv, gv, gg);
+  }
+  dot = block_sum_256(dot, red);
+  gg = block_sum_256(gg, red);
+  if (threadIdx.x == 0) { atomicAdd(stats + 2 * l, dot); atomicAdd(stats + 2 * l + 1, gg); }
+}
+
+// pass 2: tensors are listed as kind 0 (v of a weight-normed layer, grads hold dL/dW_eff), 1 (bias, plain).
+// v:   dv = alpha*(G - dot*inv^2 * v),  ||dv||^2 = alpha^2 * max(gg - dot^2*inv^2, 0)
+// g:   dg = dot*inv   (scalar; handled by the thread that owns element 0 of the v tensor)
+// then clip_by_norm per tensor and Keras Adamax.
+__global__ void __launch_bounds__(256) opt_update_kernel(float* __restrict__ params, const float* __restrict__ grads,
+                                                         float* __restrict__ am, float* __restrict__ au, TensorList tl,
+                                                         const float* __restrict__ stats, const float* __restrict__ alpha,
+                                                         const float* __restrict__ inv_norm, OptHyper hp) {
+  int l = 0;
+  while (l + 1 < tl.n && (int)blockIdx.x >= tl.chunk_start[l + 1]) ++l;
+  const long long base = (long long)(blockIdx.x - tl.chunk_start[l]) * WN_CHUNK;
+  const long long n = tl.numel[l], end = min(base + (long long)WN_CHUNK, n);
+  const long long off = tl.off[l];
+  const float dot = stats[2 * l], gg = stats[2 * l + 1];
+  float a = 1.f, proj = 0.f, nrm;
+  if (tl.kind[l] == 0 && !hp.grads_are_final) {
+    const int wl = tl.layer[l];
+    const float inv = inv_norm[wl];
+    a = alpha[wl];
+    proj = dot * inv * inv;
+    nrm = fabsf(a) * sqrtf(fmaxf(gg - dot * dot * inv * inv, 0.f));
+  } else {
+    nrm = sqrtf(gg);
+  }
+  const float cs = hp.clip / fmaxf(nrm, hp.clip);           // tf.clip_by_norm
+  for (long long i = base + threadIdx.x; i < end; i += 256) {
+    const float w = params[off + i];
+    const float g = cs * a * (grads[off + i] - proj * w);
+    const float m = hp.beta1 * am[off + i] + (1.f - hp.beta1) * g;
+    const float u = fmaxf(hp.beta2 * au[off + i], fabsf(g));
+    am[off + i] = m; au[off + i] = u;
+    params[off + i] = w - hp.lr_t * m / (u + hp.eps);
+  }
+  if (tl.kind[l] == 0 && base == 0 && threadIdx.x == 0) {    // the scalar g of this layer
+    const long long go = tl.g_off[l];
+    float dg = hp.grads_are_final ? grads[go] : dot * inv_norm[tl.layer[l]];
+    dg *= hp.clip / fmaxf(fabsf(dg), hp.clip);
+    const float m = hp.beta1 * am[go] + (1.f - hp.beta1) * dg;
+    const float u = fmaxf(hp.beta2 * au[go], fabsf(dg));
+    am[go] = m; au[go] = u;
+    params[go] -= hp.lr_t * m / (u + hp.eps);
+  }
+}
+
+// in-place conversion of effective-weight gradients to the reference's (dv, dg)  [for inspection / parity tests]
+__global__ void __launch_bounds__(256) opt_finalize_kernel(const float* __restrict__ params, float* __restrict__ grads,
+                                                           TensorList tl, const float* __restrict__ stats,
+                                                           const float* __restrict__ alpha, const float* __restrict__ inv_norm) {
+  int l = 0;
+  while (l + 1 < tl.n && (int)blockIdx.x >= tl.chunk_start[l + 1]) ++l;
+  if (tl.kind[l] != 0) return;
+  const long long base = (long long)(blockIdx.x - tl.chunk_start[l]) * WN_CHUNK;
+  const long long n = tl.numel[l], end = min(base + (long long)WN_CHUNK, n);
+  const long long off = tl.off[l];
+  const int wl = tl.layer[l];
+  const float dot = stats[2 * l], inv = inv_norm[wl], a = alpha[wl];
+  for (long long i = base + threadIdx.x; i < end; i += 256)
+    grads[off + i] = a * (grads[off + i] - dot * inv * inv * params[off + i]);
+  if (base == 0 && threadIdx.x == 0) grads[tl.g_off[l]] = dot * inv;
+}
+
+__global__ void label_const_kernel(const float* __restrict__ params, long long v_off, long long b_off, const float* alpha_l,
+                                   float* c) {
+  *c = *alpha_l * params[v_off] + (b_off >= 0 ? params[b_off] : 0.f);   // graph_att_net.py:71 on an all-ones adjacency
+}
+__global__ void label_grad_kernel(const float* dc, float* grads, long long v_off, long long b_off) {
+  grads[v_off] = *dc;
+  if (b_off >= 0) grads[b_off] = *dc;
+}
+
+inline int grid_for(long long n, int per_block = 256) {
+  return (int)std::max<long long>(1, std::min<long long>((n + per_block - 1) / per_block, (long long)num_sms() * 8));
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- host launchers (declared in kernels.h)
+int build_tensor_list(TensorList& tl) {
+  int c = 0;
+  for (int l = 0; l < tl.n; ++l) {
+    tl.chunk_start[l] = c;
+    c += (int)((tl.numel[l] + WN_CHUNK - 1) / WN_CHUNK);
+  }
+  tl.chunk_start[tl.n] = c;
+  return c;
+}
+
+int k_wn_prepare(const float* params, const TensorList& tl, int chunks, float* sumsq, void* lowp, cudaStream_t st) {
+  wn_prepare_kernel<<<chunks, 256, 0, st>>>(params, tl, sumsq, static_cast<bf16*>(lowp));
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+int k_wn_alpha(const float* params, const TensorList& tl, const float* sumsq, float* alpha, float* inv_norm, cudaStream_t st) {
+  wn_alpha_kernel<<<1, 32, 0, st>>>(params, tl, sumsq, alpha, inv_norm);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+int k_cast(int to_dtype, const float* in, void* out, long long n, cudaStream_t st) {
+  REGAT_REQUIRE(n % 8 == 0, REGAT_ERR_SHAPE, "cast: element count must be a multiple of 8");
+  if (to_dtype == REGAT_BF16) cast_kernel<bf16><<<grid_for(n / 8), 256, 0, st>>>(in, static_cast<bf16*>(out), n / 8);
+  else cast_kernel<float><<<grid_for(n / 8), 256, 0, st>>>(in, static_cast<float*>(out), n / 8);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+#define DISPATCH_T(dt, ...)                          \
+  if ((dt) == REGAT_BF16) { typedef bf16 T; __VA_ARGS__; } else { typedef float T; __VA_ARGS__; }
+
+int k_rowmask(int dt, const void* v, int rows, int D, float* mask, cudaStream_t st) {
+  REGAT_REQUIRE(D % 8 == 0, REGAT_ERR_SHAPE, "rowmask: D must be a multiple of 8");
+  DISPATCH_T(dt, (rowmask_kernel<T><<<ceil_div(rows, 8), 256, 0, st>>>(static_cast<const T*>(v), rows, D, mask)));
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+int k_mul(int dt, const void* a, int lda, const void* b, int ldb, void* out, int ldo, int rows, int cols, cudaStream_t st) {
+  DISPATCH_T(dt, (mul_kernel<T><<<grid_for((long long)rows * cols), 256, 0, st>>>(static_cast<const T*>(a), lda, static_cast<const T*>(b), ldb,
+                                                                                 static_cast<T*>(out), ldo, rows, cols)));
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+int k_mul_bwd(int dt, const void* dz, int ldz, const void* a, int lda, const void* b, int ldb, void* da, int ldda, void* db,
+              int lddb, int rows, int cols, cudaStream_t st) {
+  DISPATCH_T(dt, (mul_bwd_kernel<T><<<grid_for((long long)rows * cols), 256, 0, st>>>(
+                     static_cast<const T*>(dz), ldz, static_cast<const T*>(a), lda, static_cast<const T*>(b), ldb,
+                     static_cast<T*>(da), ldda, static_cast<T*>(db), lddb, rows, cols)));
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+int k_butd_prep(int dt, const void* u, int ldu, const float* vl, const float* alpha_l, const float* bva, const float* bl,
+                void* uw, float* cb, int B, int Hd, cudaStream_t st) {
+  DISPATCH_T(dt, (butd_prep_kernel<T><<<B, 256, 0, st>>>(static_cast<const T*>(u), ldu, vl, alpha_l, bva, bl, static_cast<T*>(uw), cb, Hd)));
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+int k_butd_prep_bwd(int dt, const void* duw, const float* dcb, const void* u, int ldu, const void* uw, const float* vl,
+                    const float* alpha_l, const float* bva, void* du, int lddu, float* dwl, float* dbva, float* dbl, int B,
+                    int Hd, cudaStream_t st) {
+  DISPATCH_T(dt, (butd_prep_bwd_kernel<T><<<ceil_div(Hd, 256), 256, 0, st>>>(
+                     static_cast<const T*>(duw), dcb, static_cast<const T*>(u), ldu, static_cast<const T*>(uw), vl, alpha_l, bva,
+                     static_cast<T*>(du), lddu, dwl, dbva, dbl, B, Hd)));
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+int k_bce(int B, int A, const float* logits, int ldl, const float* target, float gscale, float* loss, float* score,
+          void* dlog, int ldd, int d_dtype, cudaStream_t st) {
+  if (d_dtype == REGAT_BF16) bce_kernel<bf16><<<B, 256, 0, st>>>(logits, ldl, target, A, 1.f / B, gscale, loss, score, static_cast<bf16*>(dlog), dlog ? ldd : A);
+  else bce_kernel<float><<<B, 256, 0, st>>>(logits, ldl, target, A, 1.f / B, gscale, loss, score, static_cast<float*>(dlog), dlog ? ldd : A);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+int k_colsum(int dt, const void* x, int ld, int rows, int cols, float* out, cudaStream_t st) {
+  const int slabs = std::max(1, std::min(rows / 64, 64));
+  dim3 grid(ceil_div(cols, 256), slabs);
+  DISPATCH_T(dt, (colsum_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x), ld, rows, cols, out)));
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+int k_segsum(int dt, const void* x, const float* w, int B, int N, int D, void* out, cudaStream_t st) {
+  REGAT_REQUIRE(D % 8 == 0, REGAT_ERR_SHAPE, "segsum: D must be a multiple of 8");
+  dim3 grid(ceil_div(D / 8, 256), B);
+  DISPATCH_T(dt, (segsum_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x), w, N, D, static_cast<T*>(out))));
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+int k_addrows(int dt, void* dst, const void* src, int B, int N, int M, int D, cudaStream_t st) {
+  REGAT_REQUIRE(D % 8 == 0, REGAT_ERR_SHAPE, "addrows: D must be a multiple of 8");
+  const long long n8 = (long long)B * M * (D / 8);
+  DISPATCH_T(dt, (addrows_kernel<T><<<grid_for(n8), 256, 0, st>>>(static_cast<T*>(dst), static_cast<const T*>(src), N, M, D, n8)));
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+int k_opt_reduce(const float* params, const float* grads, const TensorList& tl, int chunks, float* stats, cudaStream_t st) {
+  opt_reduce_kernel<<<chunks, 256, 0, st>>>(params, grads, tl, stats);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+int k_opt_update(float* params, const float* grads, float* m, float* u, const TensorList& tl, int chunks, const float* stats,
+                 const float* alpha, const float* inv_norm, const OptHyper& hp, cudaStream_t st) {
+  opt_update_kernel<<<chunks, 256, 0, st>>>(params, grads, m, u, tl, stats, alpha, inv_norm, hp);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+int k_opt_finalize(const float* params, float* grads, const TensorList& tl, int chunks, const float* stats, const float* alpha,
+                   const float* inv_norm, cudaStream_t st) {
+  opt_finalize_kernel<<<chunks, 256, 0, st>>>(params, grads, tl, stats, alpha, inv_norm);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+int k_label_const(const float* params, long long v_off, long long b_off, const float* alpha_l, float* c, cudaStream_t st) {
+  label_const_kernel<<<1, 1, 0, st>>>(params, v_off, b_off, alpha_l, c);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+int k_label_grad(const float* dc, float* grads, long long v_off, long long b_off, cudaStream_t st) {
+  label_grad_kernel<<<1, 1, 0, st>>>(dc, grads, v_off, b_off);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+
+}  // namespace regat
+
+using namespace regat;
+
+extern "C" int regat_butd_pool_fwd(int dtype, int B, int N, int D, const void* v1, const void* weff, const float* cb,
+                                   float* att, void* pooled, regat_stream_t stream) {
+  REGAT_REQUIRE(v1 && weff && cb && att && pooled, REGAT_ERR_ARG, "butd_pool_fwd: null pointer");
+  REGAT_REQUIRE(D % 8 == 0, REGAT_ERR_SHAPE, "butd_pool_fwd: D must be a multiple of 8");
+  REGAT_REQUIRE(aligned16(v1) && aligned16(weff) && aligned16(pooled), REGAT_ERR_ALIGN, "butd_pool_fwd: unaligned tensor");
+  if (B <= 0 || N <= 0) return REGAT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_T(dtype, (butd_pool_fwd_kernel<T><<<B, 256, N * sizeof(float), st>>>(static_cast<const T*>(v1), static_cast<const T*>(weff), cb, att,
+                                                                               static_cast<T*>(pooled), N, D)));
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+extern "C" int regat_butd_pool_bwd(int dtype, int B, int N, int D, const void* v1, const void* weff, const float* att,
+                                   const void* dpooled, void* dv1, void* dweff, float* dcb, regat_stream_t stream) {
+  REGAT_REQUIRE(v1 && weff && att && dpooled && dv1 && dweff && dcb, REGAT_ERR_ARG, "butd_pool_bwd: null pointer");
+  REGAT_REQUIRE(D % 8 == 0, REGAT_ERR_SHAPE, "butd_pool_bwd: D must be a multiple of 8");
+  if (B <= 0 || N <= 0) return REGAT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_T(dtype, (butd_pool_bwd_kernel<T><<<B, 256, 2 * N * sizeof(float), st>>>(
+                        static_cast<const T*>(v1), static_cast<const T*>(weff), att, static_cast<const T*>(dpooled),
+                        static_cast<T*>(dv1), static_cast<T*>(dweff), dcb, N, D)));
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+extern "C" int regat_bce_fwd_bwd(int B, int A, const float* logits, int ld_logits, const float* target, float* loss,
+                                 float* score, void* dlogits, int ld_d, int d_dtype, regat_stream_t stream) {
+  REGAT_REQUIRE(logits && target && loss, REGAT_ERR_ARG, "bce: null pointer");
+  REGAT_REQUIRE(ld_logits >= A && (!dlogits || ld_d >= A), REGAT_ERR_SHAPE, "bce: leading dimension smaller than A");
+  if (B <= 0) return REGAT_OK;
+  return k_bce(B, A, logits, ld_logits, target, 1.f, loss, score, dlogits, ld_d, d_dtype, (cudaStream_t)stream);
+}

@@ -1,0 +1,143 @@
+"""Python face of the C engine (include/regat.h: regat_engine_*): the hot path of
+rel_graph_net.py:53-62 and train.py:103-113 as single calls.  torch is used for device memory and streams
+only; every number is produced by libregat.so kernels."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import HotPathConfig, param_layout
+
+_DT = {"fp32": _lib.F32, "float32": _lib.F32, "bf16": _lib.BF16, "bfloat16": _lib.BF16}
+
+
+def _c_config(cfg: HotPathConfig) -> _lib.Config:
+    return _lib.Config(cfg.v_dim, cfg.q_dim, cfg.rel_dim, cfg.num_heads, cfg.pos_emb_dim, cfg.nongt_dim, cfg.dir_num,
+                       cfg.num_answers, int(cfg.label_bias), int(cfg.residual), cfg.grad_clip, cfg.beta1, cfg.beta2, cfg.eps)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class HotPathEngine:
+    """Owns the flat parameter / gradient / Adamax buffers and the workspace of one GPU.
+
+    dtype "fp32": exact-fp32 kernels (parity mode, 1e-4);  "bf16": bf16 activations and tcgen05 GEMMs with fp32
+    accumulation, fp32 master weights (1e-2 on logits, same argmax).
+    """
+
+    def __init__(self, cfg: HotPathConfig, max_batch: int, max_rois: int, dtype: str = "bf16", device="cuda:0",
+                 training: bool = True):
+        if not torch.cuda.is_available():
+            raise _lib.RegatError(-6, "HotPathEngine needs a CUDA device; there is no CPU fallback")
+        self.cfg, self.dtype_name, self.dtype = cfg, dtype, _DT[dtype]
+        self.device = torch.device(device)
+        self.max_batch, self.max_rois = max_batch, max_rois
+        self.lib = _lib.lib()
+        torch.cuda.set_device(self.device)
+        self._h = C.c_void_p()
+        cc = _c_config(cfg)
+        _lib.check(self.lib.regat_engine_create(C.byref(cc), self.dtype, max_batch, max_rois, C.byref(self._h)))
+        pe, wb = C.c_int64(), C.c_int64()
+        _lib.check(self.lib.regat_engine_sizes(self._h, C.byref(pe), C.byref(wb)))
+        self.entries, total = param_layout(cfg)
+        assert total == pe.value, "Python and C parameter layouts disagree"
+        self.param_elems, self.workspace_bytes = pe.value, wb.value
+        z = lambda: torch.zeros(pe.value, dtype=torch.float32, device=self.device)
+        self.params = z()
+        self.grads = z() if training else None
+        self.adamax_m = z() if training else None
+        self.adamax_u = z() if training else None
+        self.workspace = torch.zeros(wb.value, dtype=torch.uint8, device=self.device)
+        _lib.check(self.lib.regat_engine_bind(self._h, self.params.data_ptr(), _lib.ptr(self.grads), _lib.ptr(self.adamax_m),
+                                              _lib.ptr(self.adamax_u), self.workspace.data_ptr(), wb.value))
+        self._wd = _lib.wave_divisors(cfg.pos_emb_dim)
+        _lib.check(self.lib.regat_engine_set_wave_div(self._h, self._wd.ctypes.data))
+        self._loss = torch.zeros(2, dtype=torch.float32, device=self.device)
+        self.step_count = 0
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self.lib.regat_engine_destroy(h)
+            self._h = None
+
+    # ---- parameters
+    def load_params(self, flat):
+        """flat fp32 buffer in config.param_layout order (np.ndarray or tensor)."""
+        t = torch.as_tensor(np.asarray(flat, dtype=np.float32)) if not isinstance(flat, torch.Tensor) else flat
+        assert t.numel() == self.param_elems
+        self.params.copy_(t.to(self.device, torch.float32))
+
+    def named(self, buf=None):
+        """name -> view into a flat buffer (default: params)."""
+        buf = self.params if buf is None else buf
+        return {e.name: buf[e.offset:e.offset + e.numel].view(e.shape) for e in self.entries}
+
+    # ---- calls
+    @staticmethod
+    def _chk(t, shape):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == tuple(shape), \
+            f"expected contiguous fp32 CUDA tensor of shape {tuple(shape)}, got {tuple(t.shape)} {t.dtype} {t.device}"
+
+    def _inputs(self, features, boxes, q_att, q_last):
+        B, N, V = features.shape
+        self._chk(features, (B, N, self.cfg.v_dim)); self._chk(boxes, (B, N, 4))
+        self._chk(q_att, (B, self.cfg.q_dim)); self._chk(q_last, (B, self.cfg.q_dim))
+        return B, N
+
+    def forward(self, features, boxes, q_att, q_last, return_att=False):
+        """Eval forward (train.py:136-177): logits [B, A] fp32 (+ BUTD attention weights [B,N,1])."""
+        B, N = self._inputs(features, boxes, q_att, q_last)
+        logits = torch.empty(B, self.cfg.num_answers, dtype=torch.float32, device=self.device)
+        att = torch.empty(B, N, dtype=torch.float32, device=self.device) if return_att else None
+        _lib.check(self.lib.regat_engine_forward(self._h, B, N, features.data_ptr(), boxes.data_ptr(), q_att.data_ptr(),
+                                                 q_last.data_ptr(), logits.data_ptr(), _lib.ptr(att), _stream()))
+        return (logits, att.unsqueeze(-1)) if return_att else logits
+
+    def fwd_bwd(self, features, boxes, q_att, q_last, target, grad_scale=1.0, want_logits=False, want_dq=False):
+        """GradientTape step (train.py:103-111).  Leaves dL/dW_eff + dL/db in self.grads; returns a dict with the
+        device scalars 'loss' and 'score' (views of one 2-float tensor) and optional logits / dq_att / dq_last."""
+        B, N = self._inputs(features, boxes, q_att, q_last)
+        self._chk(target, (B, self.cfg.num_answers))
+        out = {}
+        logits = torch.empty(B, self.cfg.num_answers, dtype=torch.float32, device=self.device) if want_logits else None
+        dqa = torch.empty(B, self.cfg.q_dim, dtype=torch.float32, device=self.device) if want_dq else None
+        dql = torch.empty(B, self.cfg.q_dim, dtype=torch.float32, device=self.device) if want_dq else None
+        _lib.check(self.lib.regat_engine_fwd_bwd(self._h, B, N, features.data_ptr(), boxes.data_ptr(), q_att.data_ptr(),
+                                                 q_last.data_ptr(), target.data_ptr(), float(grad_scale), self._loss.data_ptr(),
+                                                 _lib.ptr(logits), _lib.ptr(dqa), _lib.ptr(dql), _stream()))
+        out.update(loss=self._loss[0], score=self._loss[1], logits=logits, dq_att=dqa, dq_last=dql)
+        return out
+
+    def finalize_grads(self):
+        """In place: dL/dW_eff -> the reference's tape.gradient values (dv, dg)."""
+        _lib.check(self.lib.regat_engine_finalize_grads(self._h, _stream()))
+
+    def update(self, lr, step=None):
+        """Per-tensor clip_by_norm + Adamax (train.py:112-113)."""
+        self.step_count = step if step is not None else self.step_count + 1
+        _lib.check(self.lib.regat_engine_update(self._h, float(lr), int(self.step_count), _stream()))
+
+    def train_step(self, features, boxes, q_att, q_last, target, lr, step=None):
+        B, N = self._inputs(features, boxes, q_att, q_last)
+        self._chk(target, (B, self.cfg.num_answers))
+        self.step_count = step if step is not None else self.step_count + 1
+        _lib.check(self.lib.regat_engine_train_step(self._h, B, N, features.data_ptr(), boxes.data_ptr(), q_att.data_ptr(),
+                                                    q_last.data_ptr(), target.data_ptr(), float(lr), int(self.step_count),
+                                                    self._loss.data_ptr(), _stream()))
+        return self._loss
+
+    def last_launches(self):
+        return self.lib.regat_engine_last_launches(self._h)
+
+    def buffer(self, name, shape, dtype=None):
+        """Copy of a named internal activation as a torch tensor (tests)."""
+        p = C.c_void_p()
+        _lib.check(self.lib.regat_engine_buffer(self._h, name.encode(), C.byref(p)))
+        off = p.value - self.workspace.data_ptr()
+        dt = dtype or (torch.bfloat16 if self.dtype == _lib.BF16 else torch.float32)
+        n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+        return self.workspace[off:off + n].view(dt).view(*shape).clone()
