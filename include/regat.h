@@ -117,8 +117,8 @@ REGAT_API int regat_wn_alpha(const float* params, const int64_t* g_off_host, int
  *   x  = gate[r,c] > 0 ? x : 0    (if gate; same dtype/ld as given)
  *   C[r,c] = x                    (dtype c_dtype: REGAT_F32 or the activation dtype)
  *   C2[(r / c2_rows_in) * c2_rows_keep + r % c2_rows_in, c] = x  if r % c2_rows_in < c2_rows_keep
- * split_k > 1 (bf16 path, c_dtype F32, no epilogue but alpha): partial sums are atomically
- * added into C, which the caller has zeroed or wants accumulated into.                   */
+ * split_k > 1 (bf16 path, c_dtype F32, no epilogue but alpha): the K range is split over CTAs, C is
+ * zeroed by the call and partial sums are atomically added (used for weight gradients).   */
 typedef struct regat_epilogue {
   const float* alpha; int32_t alpha_cols;
   const float* bias;
@@ -149,7 +149,8 @@ REGAT_API int regat_gemm(int dtype, int transA, int transB, int M, int N, int K,
  *   wg    : dirs pointers' worth of pair_pos_fc: v [dirs][E,H] fp32 raw kernels (contiguous per
  *           dir at wg + d*wg_stride), alpha_g [dirs], bg [dirs][H] (at bg + d*bg_stride)
  *   label_c : device scalar c = WN(label FC)(1) (+bias)  (graph_att_net.py:71)
- *   s, v0 [B*N, D] ; out v1 [B*N, D] = (residual ? v0 : 0) + relu(s + sum_d O_d)
+ *   s, v0 [B*N, D] ; out v1 [B*N, D] = (residual ? v0 : 0) + relu(s + sum_d O_d);
+ *   s == NULL: v1 = sum_d O_d, the raw output of GraphSelfAttentionLayer.call (graph_att_layer.py:121)
  *   save_p, save_gbias [B,dirs,H,N,M] fp32 and gate [B*N, H] uint64 (bit e of word (row,h) set
  *   iff relu input > 0) are written when non-NULL (training).
  * Head dim must be 64; N <= 128; 16*M*dirs*H*4 bytes must fit in shared memory.          */
@@ -191,6 +192,19 @@ REGAT_API int regat_butd_pool_fwd(int dtype, int B, int N, int D, const void* v1
 REGAT_API int regat_butd_pool_bwd(int dtype, int B, int N, int D, const void* v1, const void* weff,
                         const float* att, const void* dpooled, void* dv1, void* dweff, float* dcb,
                         regat_stream_t stream);
+
+/* relation_encoder.py:13-37 concat_visual_question(q, v, mask=True):
+ *   mask[b,n] = (sum_d v[b,n,d] != 0) (optional output, fp32);  out[b,n,:] = [ v[b,n,:] || mask * q[b,:] ]   [B,N,D+Q] */
+REGAT_API int regat_concat_visual_question(int dtype, int B, int N, int D, int Q, const void* v, const void* q,
+                                 void* out, float* mask, regat_stream_t stream);
+/* fusion.py:47-52 re-associated: uw[b,c] = u[b,c] * alpha_linear * v_linear[c];  cb[b] = sum_c bias_v2att[c]*uw[b,c]
+ * + bias_linear.  u = q2attention(question) with row pitch ldu. */
+REGAT_API int regat_butd_prep(int dtype, int B, int Hd, const void* u, int ldu, const float* v_linear,
+                    const float* alpha_linear, const float* bias_v2att, const float* bias_linear, void* uw,
+                    float* cb, regat_stream_t stream);
+/* out = a * b elementwise (fusion.py:39 joint_emb = weighted_visual * question). */
+REGAT_API int regat_mul(int dtype, int rows, int cols, const void* a, int lda, const void* b, int ldb, void* out, int ldo,
+              regat_stream_t stream);
 
 /* ------------------------------------------------------------------ loss (train.py:20-26,107-108)
  * loss = A * mean_{b,a} BCEwithlogits(logits, target) (added into *loss, caller zeroes);

@@ -49,6 +49,9 @@ SIGNATURES = {
     "regat_geo_bwd": [i32] * 6 + [vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp],
     "regat_butd_pool_fwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp],
     "regat_butd_pool_bwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp],
+    "regat_concat_visual_question": [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
+    "regat_butd_prep": [i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp],
+    "regat_mul": [i32, i32, i32, vp, i32, vp, i32, vp, i32, vp],
     "regat_bce_fwd_bwd": [i32, i32, vp, i32, vp, vp, vp, vp, i32, i32, vp],
     "regat_engine_create": [C.POINTER(Config), i32, i32, i32, C.POINTER(vp)],
     "regat_engine_destroy": [vp],

@@ -1,9 +1,388 @@
-// placeholder until the tcgen05 kernel lands (next commit): reports "unsupported" so bf16 mode uses the SIMT kernel
+// Kernel (b): bf16 dense projections on the 5th-gen tensor cores.
+//   TMA (cp.async.bulk.tensor, 128B swizzle) -> shared memory ring -> tcgen05.mma (one elected thread,
+//   fp32 accumulators in TMEM) -> tcgen05.ld epilogue with the fused regat_epilogue.
+// Replaces the reference's tf.keras Dense calls and their autodiff transposes (fc.py:36-43,
+// graph_att_layer.py:47,55,117, fusion.py:32-39, classifier.py:14-19; SURVEY K2,K4,K5,K11,K13,K14).
+//
+// One kernel covers forward (A K-major, B MN-major), dgrad (both K-major) and wgrad (both MN-major)
+// without any transposed copy in HBM: the operand's major-ness only changes the TMA box shape and the
+// shared-memory matrix descriptor (UMMA canonical layouts, SWIZZLE_128B):
+//   K-major  tile: rows x 64 bf16 (128 B per row), 8-row swizzle atoms: SBO = 1024 B, +32 B per UMMA_K
+//   MN-major tile: 64-element MN chunks of [64 K-rows x 128 B]: LBO = 8192 B (next chunk), SBO = 1024 B
+//                  (next 8 K-rows), +2048 B per UMMA_K
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue
+// (warp w reads TMEM lanes 32*(w%4)..).  Every mbarrier wait is bounded and traps instead of hanging.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include "common.cuh"
+
 namespace regat {
-bool gemm_tc_supported(int, int, int, int, int, const void*, int, const void*, int) { return false; }
-int gemm_tc(int, int, int, int, int, const void*, int, const void*, int, void*, int, int, const EpiArgs&, int, cudaStream_t) {
-  set_error("gemm_tc: not built");
-  return REGAT_ERR_UNSUPPORTED;
+namespace {
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int NTHREADS = 192;
+constexpr uint32_t SPIN_LIMIT = 1u << 27;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();   // a pipeline bug must surface as a CUDA error, never as a hung GPU
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor (tcgen05 / "UMMA"): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout SWIZZLE_128B = 2 at [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, a_major bit15, b_major bit16,
+// N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(BM >> 4) << 24);
+}
+
+struct TcParams {
+  int M, N, K, ldc, c_f32, k_blocks_per_split, total_k_blocks, atomic_out;
+  void* C;
+  EpiArgs e;
+};
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                           const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+  const int kb0 = blockIdx.z * p.k_blocks_per_split;
+  const int kb1 = min(p.total_k_blocks, kb0 + p.k_blocks_per_split);
+
+  if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int it = 0;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(empty_bar + s, ph ^ 1);
+        mbar_expect_tx(full_bar + s, STAGE_BYTES);
+        unsigned char* sa = tiles + s * STAGE_BYTES;
+        unsigned char* sb = sa + A_BYTES;
+        if (!A_MN) {
+          tma_load_2d(sa, &mapA, full_bar + s, kb * BK, m0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (64 * BK * 2), &mapA, full_bar + s, m0 + c * 64, kb * BK);
+        }
+        if (!B_MN) {
+          tma_load_2d(sb, &mapB, full_bar + s, kb * BK, n0);
+        } else {
+#pragma unroll
+          for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (64 * BK * 2), &mapB, full_bar + s, n0 + c * 64, kb * BK);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (single thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+      int it = 0;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(full_bar + s, ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(tiles + s * STAGE_BYTES), sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t da = A_MN ? make_desc(sa + k * 2048, 64 * BK * 2, 1024) : make_desc(sa + k * 32, 16, 1024);
+          const uint64_t db = B_MN ? make_desc(sb + k * 2048, 64 * BK * 2, 1024) : make_desc(sb + k * 32, 16, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar + s);          // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(tmem_full);                // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> fused epilogue -> global =====
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    const int r = m0 + q * 32 + lane;
+    const bool row_ok = r < p.M && kb1 > kb0;
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 32; ++cc) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
+      const int c0 = n0 + cc * 32;
+      if (!row_ok || c0 >= p.N) continue;
+      if (p.atomic_out) {
+        float* C = static_cast<float*>(p.C);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < p.N) {
+            float x = v[j];
+            if (p.e.alpha) x *= p.e.alpha[p.e.alpha_cols ? (c0 + j) / p.e.alpha_cols : 0];
+            atomicAdd(C + (size_t)r * p.ldc + c0 + j, x);
+          }
+      } else if (p.c_f32) {
+        float* C = static_cast<float*>(p.C);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < p.N) v[j] = epi_value<float>(p.e, r, c0 + j, v[j], C, p.ldc);
+        float* dst = C + (size_t)r * p.ldc + c0;
+        if (c0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          for (int j = 0; j < 32 && c0 + j < p.N; ++j) dst[j] = v[j];
+        }
+        if (p.e.c2) {
+          const int rr = r % p.e.c2_rows_in;
+          if (rr < p.e.c2_rows_keep) {
+            float* d2 = static_cast<float*>(p.e.c2) + ((size_t)(r / p.e.c2_rows_in) * p.e.c2_rows_keep + rr) * p.e.c2_ld + c0;
+            for (int j = 0; j < 32 && c0 + j < p.N; ++j) d2[j] = v[j];
+          }
+        }
+      } else {
+        bf16* C = static_cast<bf16*>(p.C);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < p.N) v[j] = epi_value<bf16>(p.e, r, c0 + j, v[j], C, p.ldc);
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+          w[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        bf16* dst = C + (size_t)r * p.ldc + c0;
+        if (c0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        } else {
+          for (int j = 0; j < 32 && c0 + j < p.N; ++j) dst[j] = __float2bfloat16_rn(v[j]);
+        }
+        if (p.e.c2) {
+          const int rr = r % p.e.c2_rows_in;
+          if (rr < p.e.c2_rows_keep) {
+            bf16* d2 = static_cast<bf16*>(p.e.c2) + ((size_t)(r / p.e.c2_rows_in) * p.e.c2_rows_keep + rr) * p.e.c2_ld + c0;
+            if (c0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(d2) & 15) == 0)) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(d2 + 8 * j) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+            } else {
+              for (int j = 0; j < 32 && c0 + j < p.N; ++j) d2[j] = __float2bfloat16_rn(v[j]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn encode_fn() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(f);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner extent `inner` (contiguous), outer extent `outer`, row pitch ld elements; box {64, box_rows}
+int make_map(CUtensorMap* out, const void* base, long long inner, long long outer, long long ld, int box_rows) {
+  typedef std::tuple<const void*, long long, long long, long long, int> Key;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  Key key(base, inner, outer, ld, box_rows);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return REGAT_OK; }
+  }
+  EncodeFn fn = encode_fn();
+  REGAT_REQUIRE(fn, REGAT_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  REGAT_REQUIRE(r == CUDA_SUCCESS, REGAT_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled failed (%d) inner=%lld outer=%lld ld=%lld", (int)r,
+                inner, outer, ld);
+  std::lock_guard<std::mutex> lk(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = *out;
+  return REGAT_OK;
+}
+
+template <int BN, int STAGES>
+int launch_cfg(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align slack*/ + (2 * STAGES + 1) * 8 + 16;
+#define REGAT_TC_CASE(AM, BMN)                                                                              \
+  {                                                                                                         \
+    auto kern = gemm_tc_kernel<BN, STAGES, AM, BMN>;                                                        \
+    REGAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+    kern<<<grid, NTHREADS, smem, st>>>(ma, mb, p);                                                          \
+  }
+  if (!a_mn && b_mn) REGAT_TC_CASE(false, true)
+  else if (!a_mn && !b_mn) REGAT_TC_CASE(false, false)
+  else if (a_mn && b_mn) REGAT_TC_CASE(true, true)
+  else REGAT_TC_CASE(true, false)
+#undef REGAT_TC_CASE
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+
+}  // namespace
+
+bool gemm_tc_supported(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb) {
+  (void)transA; (void)transB; (void)M; (void)N; (void)K;
+  return aligned16(A) && aligned16(B) && lda % 8 == 0 && ldb % 8 == 0;
+}
+
+int gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
+            int c_dtype, const EpiArgs& e, int split_k, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return REGAT_OK;
+  REGAT_REQUIRE(K > 0, REGAT_ERR_SHAPE, "gemm: K must be positive");
+  REGAT_REQUIRE(gemm_tc_supported(transA, transB, M, N, K, A, lda, B, ldb), REGAT_ERR_ALIGN, "gemm_tc: unaligned operands");
+  const bool a_mn = transA != 0;   // A stored [K, M]: M contiguous
+  const bool b_mn = transB == 0;   // B stored [K, N]: N contiguous
+  // tile width: 256 when there are enough column tiles to keep >= 1 wave busy, else 128
+  static const int force_bn = [] { const char* s = getenv("REGAT_TC_BN"); return s ? atoi(s) : 0; }();
+  const int tiles_m = ceil_div(M, BM);
+  int bn = (force_bn == 128 || force_bn == 256) ? force_bn : ((N >= 256 && tiles_m * ceil_div(N, 256) >= num_sms()) ? 256 : 128);
+  const int tiles_n = ceil_div(N, bn);
+  const int total_kb = ceil_div(K, BK);
+  // split-K only for plain fp32 targets (weight gradients: few output tiles, very long K): fill ~2 CTAs per SM
+  int splits = 1;
+  const bool plain = c_dtype == REGAT_F32 && !e.bias && !e.addend && !e.relu && !e.gate && !e.c2 && !e.accumulate;
+  static const int auto_split = [] { const char* s = getenv("REGAT_TC_SPLITK"); return s ? atoi(s) : 1; }();
+  if (plain) {
+    if (split_k > 1) splits = split_k;
+    else if (auto_split && tiles_m * tiles_n < num_sms()) splits = (2 * num_sms()) / (tiles_m * tiles_n);
+    splits = std::max(1, std::min(splits, total_kb / 8));
+  }
+  const int kbps = ceil_div(total_kb, splits);
+  splits = ceil_div(total_kb, kbps);
+
+  CUtensorMap ma, mb;
+  if (!a_mn) REGAT_TRY(make_map(&ma, A, K, M, lda, BM)); else REGAT_TRY(make_map(&ma, A, M, K, lda, BK));
+  if (!b_mn) REGAT_TRY(make_map(&mb, B, K, N, ldb, bn)); else REGAT_TRY(make_map(&mb, B, N, K, ldb, BK));
+
+  TcParams p;
+  p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.c_f32 = c_dtype == REGAT_F32; p.k_blocks_per_split = kbps; p.total_k_blocks = total_kb;
+  p.atomic_out = splits > 1; p.C = C; p.e = e;
+  if (splits > 1) REGAT_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));   // partials are atomically added
+  dim3 grid(tiles_n, tiles_m, splits);
+  if (bn == 256) return launch_cfg<256, 4>(a_mn, b_mn, ma, mb, p, grid, st);
+  return launch_cfg<128, 3>(a_mn, b_mn, ma, mb, p, grid, st);
+}
+
 }  // namespace regat

@@ -395,8 +395,10 @@ __global__ void __launch_bounds__(256, 2) geoattn_fwd_kernel(const FwdParams p) 
       if (r < N) {
         const size_t off = ((size_t)b * N + r) * D + h * HD + 16 * t;
         float sv[16], vv[16], out[16];
-        load8c<T>(S + off, *reinterpret_cast<float(*)[8]>(&sv[0]));
-        load8c<T>(S + off + 8, *reinterpret_cast<float(*)[8]>(&sv[8]));
+        if (S) {
+          load8c<T>(S + off, *reinterpret_cast<float(*)[8]>(&sv[0]));
+          load8c<T>(S + off + 8, *reinterpret_cast<float(*)[8]>(&sv[8]));
+        }
         if (p.residual) {
           load8c<T>(V0 + off, *reinterpret_cast<float(*)[8]>(&vv[0]));
           load8c<T>(V0 + off + 8, *reinterpret_cast<float(*)[8]>(&vv[8]));
@@ -404,9 +406,13 @@ __global__ void __launch_bounds__(256, 2) geoattn_fwd_kernel(const FwdParams p) 
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
           const float o = oacc[u & 7][(u >> 3) + 2 * half];      // element 16t+u <- tile (u%8), col 2t + u/8
-          const float x = sv[u] + o;
-          if (x > 0.f) bits |= 1ull << (16 * t + u);
-          out[u] = (p.residual ? vv[u] : 0.f) + fmaxf(x, 0.f);
+          if (S) {
+            const float x = sv[u] + o;
+            if (x > 0.f) bits |= 1ull << (16 * t + u);
+            out[u] = (p.residual ? vv[u] : 0.f) + fmaxf(x, 0.f);
+          } else {
+            out[u] = o;      // raw attention output of one GraphSelfAttentionLayer (graph_att_layer.py:121)
+          }
         }
         store_n<T>(V1 + off, out, 16);
       }
@@ -812,12 +818,13 @@ extern "C" int regat_geoattn_fwd(int dtype, int B, int N, int nongt_dim, int D, 
                                  const void* s, const void* v0, int residual, void* v1, float* save_p,
                                  float* save_gbias, uint64_t* gate, regat_stream_t stream) {
   REGAT_TRY(check_common(B, N, D, H, dirs, E));
-  REGAT_REQUIRE(q && kv && wg && alpha_g && s && v1, REGAT_ERR_ARG, "geoattn_fwd: null pointer");
+  REGAT_REQUIRE(q && kv && wg && alpha_g && v1, REGAT_ERR_ARG, "geoattn_fwd: null pointer");
+  REGAT_REQUIRE(s || !residual, REGAT_ERR_ARG, "geoattn_fwd: raw-output mode (s == NULL) has no residual");
   REGAT_REQUIRE((boxes != nullptr) != (pos_emb != nullptr), REGAT_ERR_ARG,
                 "geoattn_fwd: pass exactly one of boxes / pos_emb (graph_att_net.py:42-51)");
   REGAT_REQUIRE(!boxes || wave_div_host, REGAT_ERR_ARG, "geoattn_fwd: wave_div_host missing");
   REGAT_REQUIRE(!residual || v0, REGAT_ERR_ARG, "geoattn_fwd: residual needs v0");
-  REGAT_REQUIRE(aligned16(q) && aligned16(kv) && aligned16(s) && aligned16(v1) && (!v0 || aligned16(v0)) &&
+  REGAT_REQUIRE(aligned16(q) && aligned16(kv) && (!s || aligned16(s)) && aligned16(v1) && (!v0 || aligned16(v0)) &&
                     (!pos_emb || aligned16(pos_emb)),
                 REGAT_ERR_ALIGN, "geoattn_fwd: tensors must be 16-byte aligned");
   REGAT_REQUIRE(dtype == REGAT_F32 || dtype == REGAT_BF16, REGAT_ERR_DTYPE, "geoattn_fwd: bad dtype %d", dtype);

@@ -106,6 +106,34 @@ __global__ void __launch_bounds__(256) rowmask_kernel(const T* __restrict__ v, i
   if (lane == 0) mask[r] = s != 0.f ? 1.f : 0.f;
 }
 
+
+// x[r, :] = [ v[r, :] || mask[r] * q[r / N, :] ],  mask[r] = (sum_d v[r,d] != 0)   (relation_encoder.py:13-37)
+template <typename T>
+__global__ void __launch_bounds__(256) concat_vq_kernel(const T* __restrict__ v, const T* __restrict__ q, int rows, int N, int D,
+                                                        int Q, T* __restrict__ out, float* __restrict__ mask) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float s = 0.f;
+  T* o = out + (size_t)r * (D + Q);
+  for (int c = lane * 8; c < D; c += 256) {
+    float x[8];
+    ld8<T>(v + (size_t)r * D + c, x);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += x[u];
+    st8<T>(o + c, x);
+  }
+  s = warp_sum(s);
+  const float m = s != 0.f ? 1.f : 0.f;
+  if (lane == 0 && mask) mask[r] = m;
+  for (int c = lane * 8; c < Q; c += 256) {
+    float x[8];
+    ld8<T>(q + (size_t)(r / N) * Q + c, x);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) x[u] *= m;
+    st8<T>(o + D + c, x);
+  }
+}
+
 // out[r,c] = a[r,c]*b[r,c]   (joint = visual_embed * question_embed, fusion.py:39)
 template <typename T>
 __global__ void __launch_bounds__(256) mul_kernel(const T* __restrict__ a, int lda, const T* __restrict__ b, int ldb,
@@ -618,4 +646,29 @@ extern "C" int regat_bce_fwd_bwd(int B, int A, const float* logits, int ld_logit
   REGAT_REQUIRE(ld_logits >= A && (!dlogits || ld_d >= A), REGAT_ERR_SHAPE, "bce: leading dimension smaller than A");
   if (B <= 0) return REGAT_OK;
   return k_bce(B, A, logits, ld_logits, target, 1.f, loss, score, dlogits, ld_d, d_dtype, (cudaStream_t)stream);
+}
+
+extern "C" int regat_concat_visual_question(int dtype, int B, int N, int D, int Q, const void* v, const void* q, void* out,
+                                            float* mask, regat_stream_t stream) {
+  REGAT_REQUIRE(v && q && out, REGAT_ERR_ARG, "concat_visual_question: null pointer");
+  REGAT_REQUIRE(D % 8 == 0 && Q % 8 == 0, REGAT_ERR_SHAPE, "concat_visual_question: dims must be multiples of 8");
+  REGAT_REQUIRE(aligned16(v) && aligned16(q) && aligned16(out), REGAT_ERR_ALIGN, "concat_visual_question: unaligned tensor");
+  if (B <= 0 || N <= 0) return REGAT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_T(dtype, (concat_vq_kernel<T><<<ceil_div(B * N, 8), 256, 0, st>>>(static_cast<const T*>(v), static_cast<const T*>(q), B * N, N, D, Q,
+                                                                            static_cast<T*>(out), mask)));
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+extern "C" int regat_butd_prep(int dtype, int B, int Hd, const void* u, int ldu, const float* v_linear, const float* alpha_linear,
+                               const float* bias_v2att, const float* bias_linear, void* uw, float* cb, regat_stream_t stream) {
+  REGAT_REQUIRE(u && v_linear && alpha_linear && uw && cb, REGAT_ERR_ARG, "butd_prep: null pointer");
+  if (B <= 0) return REGAT_OK;
+  return k_butd_prep(dtype, u, ldu, v_linear, alpha_linear, bias_v2att, bias_linear, uw, cb, B, Hd, (cudaStream_t)stream);
+}
+extern "C" int regat_mul(int dtype, int rows, int cols, const void* a, int lda, const void* b, int ldb, void* out, int ldo,
+                         regat_stream_t stream) {
+  REGAT_REQUIRE(a && b && out, REGAT_ERR_ARG, "mul: null pointer");
+  if (rows <= 0 || cols <= 0) return REGAT_OK;
+  return k_mul(dtype, a, lda, b, ldb, out, ldo, rows, cols, (cudaStream_t)stream);
 }
