@@ -1,0 +1,343 @@
+#!/usr/bin/env python
+"""Headline benchmark of the hot path (BASELINE.json): graphs/sec of the implicit-relation encoder + BUTD fusion +
+classifier TRAIN STEP (forward, backward, per-tensor clip, Adamax), batch 256 per GPU, K=36 boxes, 16 heads,
+synthetic 2048-d region features, random-init weights of the reference architecture.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype bf16|fp32] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL): data parallel, batch sharded by image, one gradient
+all-reduce per step (weak scaling: 256 graphs per GPU).  Rank 0 prints ONE JSON line.
+  value     : whole-job graphs/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e       : same metric through the public host-buffer API: pinned-host -> device copies of every step's inputs and a
+              device -> host read of every step's loss inside the timed region (copies double-buffered on a side stream)
+  roofline  : the dominant kernel (tcgen05 bf16 GEMM of the v2out projection, 9216x1024x2048) timed alone with CUDA
+              events on rotating operands larger than L2, against the MEASURED cuBLAS bf16 peak
+  cpu_baseline : the reference-formulation CPU restatement (oracle/, torch-CPU fp32, all host cores) on a bounded sample
+--impl reference runs only that CPU arm (TensorFlow is not installable in this image).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "graphs/sec fwd+bwd (K=36, batch 256)"
+UNIT = "graphs/s"
+TRAIN_MFLOP_PER_GRAPH = 1734.0      # SURVEY 8d, N=36, nongt=20, cheapest equivalent formulation
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        d["_source"] = "measured"
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d["_source"] = "fallback"
+    return d
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during a timed region (B200_PROFILING.md clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.rows = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 7:
+                self.rows.append(f)
+        self.proc = None
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        num = lambda s: float(s) if s.replace(".", "", 1).isdigit() else None
+        sm = [num(r[0]) for r in self.rows if num(r[0]) is not None]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": num(self.rows[0][1]),
+                "power_w_max": max((num(r[2]) or 0.0) for r in self.rows), "reasons": reasons, "samples": len(self.rows)}
+
+
+def run_reference(args):
+    """The reference arm: its own CPU path (restated, TF absent) on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.cpu_step import time_cpu_train
+    from tf_vqa_regat_b200 import synthetic as syn
+    from tf_vqa_regat_b200.config import HotPathConfig
+    cfg = HotPathConfig()
+    steps = max(1, min(args.steps, 5))
+    gps, sec, threads, n = time_cpu_train(cfg, syn.make_inputs, syn.make_params, syn.unflatten, args.cpu_sample, args.rois,
+                                          full_batch=args.batch, steps=steps, warmup=1, budget_s=120.0)
+    sample = (f"fwd+bwd timed on {args.cpu_sample} of the {args.batch} graphs of one step (K={args.rois}, full widths, fp32) and scaled "
+              f"to {args.batch}, plus one full clip+Adamax over all 19.0M parameters")
+    line = {"impl": "reference", "metric": METRIC, "value": gps, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+            "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"implicit relation + BUTD train step, batch {args.batch}, K={args.rois}, 16 heads (CPU, sampled)"},
+            "cpu_baseline": {"value": gps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": gps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=256, help="graphs per GPU per step")
+    ap.add_argument("--rois", type=int, default=36)
+    ap.add_argument("--cpu-sample", type=int, default=16, help="graphs per CPU-baseline step")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lr", type=float, default=9e-4)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from tf_vqa_regat_b200 import _lib, synthetic as syn
+    from tf_vqa_regat_b200.config import HotPathConfig
+    from tf_vqa_regat_b200.engine import HotPathEngine
+    from tf_vqa_regat_b200.dp import allreduce_flat_
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+    cfg = HotPathConfig()
+    B, N = args.batch, args.rois
+    eng = HotPathEngine(cfg, B, N, dtype=args.dtype, device=dev)
+    eng.load_params(syn.make_params(cfg, seed=7, trained_like=True))     # same weights on every rank
+
+    # two distinct synthetic batches per rank, pinned on the host and resident on the device
+    host = [{k: torch.from_numpy(v).pin_memory() for k, v in syn.make_inputs(cfg, B, N, seed=1001 + 17 * rank + i).items()
+             if k != "n_obj"} for i in range(2)]
+    order = ("features", "boxes", "q_att", "q_last", "target")
+    devb = [{k: h[k].to(dev) for k in order} for h in host]
+    h2d_bytes = sum(host[0][k].numel() * 4 for k in order)
+    main_stream = torch.cuda.Stream(dev)
+    lr = args.lr
+    step_no = [0]
+
+    def fwd_bwd(slot):
+        b = devb[slot]
+        eng.fwd_bwd(b["features"], b["boxes"], b["q_att"], b["q_last"], b["target"], grad_scale=1.0 / world)
+
+    def update():
+        step_no[0] += 1
+        eng.update(lr, step_no[0])
+
+    graphs = {}
+    launches_per_step = [0]
+
+    def build_graphs():
+        # Adamax's bias correction depends on the step number (a host scalar): the update kernel is re-launched eagerly
+        # with the right lr_t, everything else is replayed from a CUDA graph.
+        with torch.cuda.stream(main_stream):
+            for slot in range(2):
+                fwd_bwd(slot)           # warm: creates tensor maps, sets smem attributes
+            launches_per_step[0] = eng.last_launches()
+            torch.cuda.synchronize()
+            if not args.no_graph:
+                for slot in range(2):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=main_stream):
+                        fwd_bwd(slot)
+                    graphs[slot] = g
+        torch.cuda.synchronize()
+
+    def one_step(slot):
+        if graphs:
+            graphs[slot].replay()
+        else:
+            fwd_bwd(slot)
+        if world > 1:
+            allreduce_flat_(eng.grads)
+        update()
+
+    build_graphs()
+    update_launches = 2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(main_stream):
+            e0.record(main_stream)
+            for i in range(steps):
+                fn(i)
+            e1.record(main_stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    # ---------------- device-resident timing
+    with torch.cuda.stream(main_stream):
+        for i in range(args.warmup):
+            one_step(i & 1)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms = timed(lambda i: one_step(i & 1), args.steps)
+    value = world * B * args.steps / (ms * 1e-3)
+    loss_end = float(eng._loss[0])
+
+    # ---------------- end-to-end timing: pinned host inputs -> device every step, loss -> host every step
+    copy_stream = torch.cuda.Stream(dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
+    loss_host = torch.zeros(2, 2).pin_memory()
+
+    def prefetch(i):
+        slot = i & 1
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[slot])                 # the step that last used this slot has finished
+            for k in order:
+                devb[slot][k].copy_(host[slot][k], non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def e2e_step(i):
+        slot = i & 1
+        if i + 1 < args.steps + 1:
+            prefetch(i + 1)
+        main_stream.wait_event(ready[slot])
+        one_step(slot)
+        loss_host[slot].copy_(eng._loss, non_blocking=True)    # device -> host read of this step's loss and score
+        done[slot].record(main_stream)
+        if i > 0:
+            done[slot ^ 1].synchronize()                       # host really consumes the previous step's loss
+            _ = float(loss_host[slot ^ 1][0])
+
+    with torch.cuda.stream(main_stream):
+        done[0].record(main_stream); done[1].record(main_stream)
+    torch.cuda.synchronize()
+    prefetch(0)
+    ms_e2e = timed(e2e_step, args.steps)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    if rank == 0:
+        sampler.stop()
+
+    # ---------------- roofline probe of the dominant kernel (rank 0): v2out GEMM, tcgen05, alone, rotating operands > L2
+    roofline, attn_probe = None, None
+    if rank == 0:
+        import ctypes as C
+        l = _lib.lib()
+        st = torch.cuda.current_stream().cuda_stream
+        M_, N_, K_ = B * N, cfg.rel_dim, cfg.v_dim
+        code = _lib.BF16 if args.dtype == "bf16" else _lib.F32
+        tdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+        nrot = 6
+        As = [torch.randn(M_, K_, device=dev, dtype=torch.float32).to(tdt) for _ in range(nrot)]
+        Cs = [torch.empty(M_, N_, device=dev, dtype=tdt) for _ in range(nrot)]
+        Wt = torch.randn(K_, N_, device=dev, dtype=torch.float32).to(tdt)
+        alpha = torch.ones(1, device=dev); bias = torch.zeros(N_, device=dev)
+        epi = _lib.Epilogue(); epi.alpha = alpha.data_ptr(); epi.bias = bias.data_ptr(); epi.relu = 1
+        call = lambda i: _lib.check(l.regat_gemm(code, 0, 0, M_, N_, K_, As[i % nrot].data_ptr(), K_, Wt.data_ptr(), N_,
+                                                 Cs[i % nrot].data_ptr(), N_, code, C.byref(epi), st))
+        for i in range(6):
+            call(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 30
+        e0.record()
+        for i in range(reps):
+            call(i)
+        e1.record(); torch.cuda.synchronize()
+        t_ms = e0.elapsed_time(e1) / reps
+        tflops = 2.0 * M_ * N_ * K_ / (t_ms * 1e-3) / 1e12
+        peak = peaks["bf16_tflops"] if args.dtype == "bf16" else None
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get("gemm_v2out_dram_bytes_per_launch")
+        roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<256,4> v2out 9216x1024x2048 bf16 (+alpha,bias,relu)",
+                    "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": (tflops / peak) if peak else None,
+                    "peak_source": peaks["_source"] + " (burst, kernel timed alone)", "launch_ms": t_ms, "traffic": traffic}
+        del As, Cs
+        # whole-step view against the sustained peak (SURVEY 8d algorithmic FLOPs)
+        step_tflops = TRAIN_MFLOP_PER_GRAPH * 1e6 * (value / world) / 1e12
+        roofline["step_tensor_frac_of_sustained"] = step_tflops / peaks["bf16_tflops_sustained"]
+        roofline["step_algorithmic_tflops_per_gpu"] = step_tflops
+
+    # ---------------- CPU baseline (rank 0, N=1 only)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.cpu_step import time_cpu_train
+        gps, sec, threads, n = time_cpu_train(cfg, syn.make_inputs, syn.make_params, syn.unflatten, args.cpu_sample, N,
+                                              full_batch=B, steps=3, warmup=1, budget_s=45.0)
+        cpu_baseline = {"value": gps, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": sec * 1e3,
+                        "sample": f"fp32 torch-CPU reference-formulation restatement (host NumPy position embedding, materialised "
+                                  f"pos_emb, grouped conv): fwd+bwd timed on {args.cpu_sample} graphs (K={N}, full widths) scaled to "
+                                  f"{B}, plus one clip+Adamax over 19.0M parameters; best of {n}"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": args.dtype if args.dtype == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": f"implicit relation + BUTD train step, batch {B}/GPU, K={N}, 16 heads, nongt_dim 20, "
+                                       f"V=2048 D=1024 Q=768 A=3129 (BASELINE.json configs[1])",
+                           "parallelism": f"dp{world}", "global_batch": B * world, "cuda_graph": not args.no_graph,
+                           "l2": "per-step working set ~0.8 GB (activations + 4x76 MB parameter/optimizer state) >> 126 MB L2; "
+                                 "two alternating input batches; no explicit flush"},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": (launches_per_step[0] + update_launches) * args.steps,
+                "launches_per_step": launches_per_step[0] + update_launches,
+                "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": sampler.summary(), "final_loss": loss_end}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

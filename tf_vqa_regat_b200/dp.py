@@ -1,0 +1,58 @@
+"""Data-parallel training of the hot path: one process per GPU, graphs sharded by image, weights replicated,
+ONE exchange per step -- an all-reduce (sum) of the flat gradient buffer.  Every graph is independent
+end to end, so rank r simply takes graphs [r*B/R, (r+1)*B/R); with equal shards the mean over the global batch is
+the average of rank means, hence grad_scale = 1/R and a SUM all-reduce reproduce the single-GPU gradient.
+
+What is reduced is dL/dW_eff (+ bias gradients), which is linear in the batch; the weight-norm projection,
+per-tensor clip and Adamax run after the reduce on every rank (train.py:112-113)."""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(global_batch: int, rank: int, world: int):
+    """Contiguous, equal shards.  The global batch must divide evenly (the loss mean needs equal shards)."""
+    if global_batch % world != 0:
+        raise ValueError(f"global batch {global_batch} is not divisible by world size {world}")
+    per = global_batch // world
+    return rank * per, (rank + 1) * per
+
+
+def shard_batch(batch: dict, rank: int, world: int) -> dict:
+    n = next(iter(batch.values())).shape[0]
+    lo, hi = shard_range(n, rank, world)
+    return {k: v[lo:hi] for k, v in batch.items()}
+
+
+def allreduce_flat_(flat: torch.Tensor, group=None, bucket_elems: int = 0):
+    """In-place SUM all-reduce of a flat buffer, optionally in buckets (elements) so that buckets can overlap
+    with compute issued on other streams."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return flat
+    if bucket_elems <= 0 or bucket_elems >= flat.numel():
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        return flat
+    for lo in range(0, flat.numel(), bucket_elems):
+        dist.all_reduce(flat[lo:lo + bucket_elems], op=dist.ReduceOp.SUM, group=group)
+    return flat
+
+
+class DataParallelTrainer:
+    """engine: anything with fwd_bwd(..., grad_scale=) -> dict(loss, score), .grads (flat tensor), .update(lr, step)."""
+
+    def __init__(self, engine, group=None, bucket_elems: int = 0):
+        self.engine, self.group, self.bucket_elems = engine, group, bucket_elems
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.step_count = 0
+
+    def broadcast_params(self, src: int = 0):
+        if self.world > 1:
+            dist.broadcast(self.engine.params, src=src, group=self.group)
+
+    def step(self, features, boxes, q_att, q_last, target, lr):
+        """One optimizer step on this rank's shard (already sliced)."""
+        self.step_count += 1
+        out = self.engine.fwd_bwd(features, boxes, q_att, q_last, target, grad_scale=1.0 / self.world)
+        allreduce_flat_(self.engine.grads, self.group, self.bucket_elems)
+        self.engine.update(lr, self.step_count)
+        return out
