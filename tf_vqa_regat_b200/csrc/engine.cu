@@ -348,12 +348,16 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
       if (L.b_off >= 0) { z.off[z.n] = L.b_off; z.numel[z.n] = L.cols; ++z.n; }
       z.off[z.n] = L.g_off; z.numel[z.n] = 1; ++z.n;
     }
-    zero_list_kernel<<<z.n, 128, 0, st>>>(e->grads, z);
-    REGAT_POST_LAUNCH();
+    {
+      const Layer& L = e->layers[e->l_lin];
+      z.off[z.n] = L.v_off; z.numel[z.n] = (long long)L.rows * L.cols; ++z.n;
+    }
     for (int d = 0; d < dirs; ++d) {
       const Layer& L = e->layers[e->l_pos[d]];
-      REGAT_CUDA(cudaMemsetAsync(e->grads + L.v_off, 0, (size_t)L.rows * L.cols * sizeof(float), st));
+      z.off[z.n] = L.v_off; z.numel[z.n] = (long long)L.rows * L.cols; ++z.n;
     }
+    zero_list_kernel<<<z.n, 128, 0, st>>>(e->grads, z);
+    REGAT_POST_LAUNCH();
     REGAT_CUDA(cudaMemsetAsync(scal + 1, 0, 3 * sizeof(float), st));   // dc, loss, score
   }
   // loss + dlogits                                                     train.py:107-108

@@ -202,6 +202,24 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
     const int r = m0 + q * 32 + lane;
     const bool row_ok = r < p.M && kb1 > kb0;
+    const int rc = min(r, p.M - 1);
+    // per-row epilogue terms, hoisted out of the column loop
+    const float rs = (p.e.addend && p.e.row_scale) ? __ldg(p.e.row_scale + rc) : 1.f;
+    const float* arow = p.e.addend ? p.e.addend + (size_t)(rc / p.e.addend_rows) * p.e.addend_ld : nullptr;
+    const float alpha0 = (p.e.alpha && p.e.alpha_cols == 0) ? __ldg(p.e.alpha) : 1.f;
+    int r2 = -1;
+    if (p.e.c2) {
+      const int rr = rc % p.e.c2_rows_in;
+      if (rr < p.e.c2_rows_keep) r2 = (rc / p.e.c2_rows_in) * p.e.c2_rows_keep + rr;
+    }
+    // fast path needs 16-byte aligned rows for every tensor touched with vector accesses
+    const size_t esz = p.c_f32 ? 4 : 2;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.C) | ((size_t)p.ldc * esz)) & 15) == 0 &&
+                        (!p.e.bias || (reinterpret_cast<uintptr_t>(p.e.bias) & 15) == 0) &&
+                        (!p.e.addend || ((reinterpret_cast<uintptr_t>(p.e.addend) | ((size_t)p.e.addend_ld * 4)) & 15) == 0) &&
+                        (!p.e.gate || ((reinterpret_cast<uintptr_t>(p.e.gate) | ((size_t)p.e.gate_ld * esz)) & 15) == 0) &&
+                        (!p.e.c2 || ((reinterpret_cast<uintptr_t>(p.e.c2) | ((size_t)p.e.c2_ld * esz)) & 15) == 0) &&
+                        (p.e.alpha_cols % 32 == 0);
 #pragma unroll 1
     for (int cc = 0; cc < BN / 32; ++cc) {
       float v[32];
@@ -217,55 +235,107 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
             if (p.e.alpha) x *= p.e.alpha[p.e.alpha_cols ? (c0 + j) / p.e.alpha_cols : 0];
             atomicAdd(C + (size_t)r * p.ldc + c0 + j, x);
           }
-      } else if (p.c_f32) {
-        float* C = static_cast<float*>(p.C);
+      } else if (vec_ok && c0 + 32 <= p.N) {
+        // ---- vectorised, branch-free path: every load is issued before its first use
+        if (arow) {
+          const float4* ap = reinterpret_cast<const float4*>(arow + c0);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < p.N) v[j] = epi_value<float>(p.e, r, c0 + j, v[j], C, p.ldc);
-        float* dst = C + (size_t)r * p.ldc + c0;
-        if (c0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          for (int j = 0; j < 32 && c0 + j < p.N; ++j) dst[j] = v[j];
-        }
-        if (p.e.c2) {
-          const int rr = r % p.e.c2_rows_in;
-          if (rr < p.e.c2_rows_keep) {
-            float* d2 = static_cast<float*>(p.e.c2) + ((size_t)(r / p.e.c2_rows_in) * p.e.c2_rows_keep + rr) * p.e.c2_ld + c0;
-            for (int j = 0; j < 32 && c0 + j < p.N; ++j) d2[j] = v[j];
+          for (int j = 0; j < 8; ++j) {
+            const float4 a = __ldg(ap + j);
+            v[4 * j] = fmaf(rs, a.x, v[4 * j]); v[4 * j + 1] = fmaf(rs, a.y, v[4 * j + 1]);
+            v[4 * j + 2] = fmaf(rs, a.z, v[4 * j + 2]); v[4 * j + 3] = fmaf(rs, a.w, v[4 * j + 3]);
           }
         }
-      } else {
-        bf16* C = static_cast<bf16*>(p.C);
+        const float al = p.e.alpha ? (p.e.alpha_cols ? __ldg(p.e.alpha + c0 / p.e.alpha_cols) : alpha0) : 1.f;
+        if (p.e.bias) {
+          const float4* bp = reinterpret_cast<const float4*>(p.e.bias + c0);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < p.N) v[j] = epi_value<bf16>(p.e, r, c0 + j, v[j], C, p.ldc);
-        uint32_t w[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-          w[j] = *reinterpret_cast<uint32_t*>(&h);
-        }
-        bf16* dst = C + (size_t)r * p.ldc + c0;
-        if (c0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = __ldg(bp + j);
+            v[4 * j] = fmaf(v[4 * j], al, bb.x); v[4 * j + 1] = fmaf(v[4 * j + 1], al, bb.y);
+            v[4 * j + 2] = fmaf(v[4 * j + 2], al, bb.z); v[4 * j + 3] = fmaf(v[4 * j + 3], al, bb.w);
+          }
         } else {
-          for (int j = 0; j < 32 && c0 + j < p.N; ++j) dst[j] = __float2bfloat16_rn(v[j]);
-        }
-        if (p.e.c2) {
-          const int rr = r % p.e.c2_rows_in;
-          if (rr < p.e.c2_rows_keep) {
-            bf16* d2 = static_cast<bf16*>(p.e.c2) + ((size_t)(r / p.e.c2_rows_in) * p.e.c2_rows_keep + rr) * p.e.c2_ld + c0;
-            if (c0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(d2) & 15) == 0)) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(d2 + 8 * j) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-            } else {
-              for (int j = 0; j < 32 && c0 + j < p.N; ++j) d2[j] = __float2bfloat16_rn(v[j]);
+          for (int j = 0; j < 32; ++j) v[j] *= al;
+        }
+        if (p.e.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        if (p.c_f32) {
+          float* dst = static_cast<float*>(p.C) + (size_t)r * p.ldc + c0;
+          if (p.e.accumulate) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 o = *reinterpret_cast<const float4*>(dst + 4 * j);
+              v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w;
             }
           }
+          if (p.e.gate) {
+            const float4* gp = reinterpret_cast<const float4*>(static_cast<const float*>(p.e.gate) + (size_t)r * p.e.gate_ld + c0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 g4 = __ldg(gp + j);
+              v[4 * j] = g4.x > 0.f ? v[4 * j] : 0.f; v[4 * j + 1] = g4.y > 0.f ? v[4 * j + 1] : 0.f;
+              v[4 * j + 2] = g4.z > 0.f ? v[4 * j + 2] : 0.f; v[4 * j + 3] = g4.w > 0.f ? v[4 * j + 3] : 0.f;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          if (r2 >= 0) {
+            float* d2 = static_cast<float*>(p.e.c2) + (size_t)r2 * p.e.c2_ld + c0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(d2 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        } else {
+          bf16* dst = static_cast<bf16*>(p.C) + (size_t)r * p.ldc + c0;
+          if (p.e.accumulate) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 o = *reinterpret_cast<const uint4*>(dst + 8 * j);
+              const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                v[8 * j + 2 * k] += __uint_as_float(w[k] << 16);
+                v[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
+              }
+            }
+          }
+          if (p.e.gate) {
+            const uint4* gp = reinterpret_cast<const uint4*>(static_cast<const bf16*>(p.e.gate) + (size_t)r * p.e.gate_ld + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 o = __ldg(gp + j);
+              const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                v[8 * j + 2 * k] = __uint_as_float(w[k] << 16) > 0.f ? v[8 * j + 2 * k] : 0.f;
+                v[8 * j + 2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u) > 0.f ? v[8 * j + 2 * k + 1] : 0.f;
+              }
+            }
+          }
+          uint32_t w[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+            w[j] = *reinterpret_cast<uint32_t*>(&h);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          if (r2 >= 0) {
+            bf16* d2 = static_cast<bf16*>(p.e.c2) + (size_t)r2 * p.e.c2_ld + c0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(d2 + 8 * j) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          }
         }
+      } else if (p.c_f32) {
+        // ---- ragged edge / unaligned: generic per-element path
+        float* C = static_cast<float*>(p.C);
+        for (int j = 0; j < 32 && c0 + j < p.N; ++j) epi_store<float>(p.e, r, c0 + j, v[j], C, p.ldc);
+      } else {
+        bf16* C = static_cast<bf16*>(p.C);
+        for (int j = 0; j < 32 && c0 + j < p.N; ++j) epi_store<bf16>(p.e, r, c0 + j, v[j], C, p.ldc);
       }
     }
   }

@@ -179,30 +179,33 @@ __global__ void __launch_bounds__(256) butd_prep_kernel(const T* __restrict__ u,
   if (threadIdx.x == 0) cb[b] = s + (bl ? *bl : 0.f);
 }
 // duw_tot = duw + dcb[b]*bva;  du = duw_tot * wl';  dwl[c] += sum_b duw_tot*u;  dbva[c] += sum_b dcb[b]*uw[b,c];  dbl += sum_b dcb
+// grid (Hd/256, row slabs); dwl / dbva / dbl are accumulated with atomics (caller zeroes them).
 template <typename T>
 __global__ void __launch_bounds__(256) butd_prep_bwd_kernel(const T* __restrict__ duw, const float* __restrict__ dcb,
                                                             const T* __restrict__ u, int ldu, const T* __restrict__ uw,
                                                             const float* __restrict__ vl, const float* __restrict__ alpha_l,
                                                             const float* __restrict__ bva, T* __restrict__ du, int lddu,
                                                             float* dwl, float* dbva, float* dbl, int B, int Hd) {
-  // one thread per column c, loops over b (B is a few hundred): coalesced across c
   const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c < Hd) {
+  const int rpb = (B + gridDim.y - 1) / gridDim.y;
+  const int b0 = blockIdx.y * rpb, b1 = min(B, b0 + rpb);
+  if (c < Hd && b0 < b1) {
     const float wl = *alpha_l * vl[c], bv = bva ? bva[c] : 0.f;
     float sw = 0.f, sb = 0.f;
-    for (int b = 0; b < B; ++b) {
+#pragma unroll 4
+    for (int b = b0; b < b1; ++b) {
       const float g = to_f(duw[(size_t)b * Hd + c]) + dcb[b] * bv;
       du[(size_t)b * lddu + c] = from_f<T>(g * wl);
       sw = fmaf(g, to_f(u[(size_t)b * ldu + c]), sw);
       sb = fmaf(dcb[b], to_f(uw[(size_t)b * Hd + c]), sb);
     }
-    dwl[c] = sw;                 // gradient w.r.t. the effective [Hd,1] kernel of joint_emb.linear
-    if (dbva) dbva[c] = sb;
+    atomicAdd(dwl + c, sw);          // gradient w.r.t. the effective [Hd,1] kernel of joint_emb.linear
+    if (dbva) atomicAdd(dbva + c, sb);
   }
-  if (dbl && blockIdx.x == 0 && threadIdx.x == 0) {
+  if (dbl && blockIdx.x == 0 && threadIdx.x == 0 && b0 < b1) {
     float s = 0.f;
-    for (int b = 0; b < B; ++b) s += dcb[b];
-    *dbl = s;
+    for (int b = b0; b < b1; ++b) s += dcb[b];
+    atomicAdd(dbl, s);
   }
 }
 
@@ -344,9 +347,48 @@ __global__ void __launch_bounds__(256) bce_kernel(const float* __restrict__ logi
 }
 
 // ---------------------------------------------------------------- reductions for the backward
-// out[c] (+)= sum_r x[r,c]   (bias gradients).  grid.x over column blocks of 256, grid.y over row slabs; atomics.
+// out[c] += sum_r x[r,c]   (bias gradients).  A block covers 32 column groups of 8 (16 B loads for bf16) x 8 row lanes and a
+// slab of rows; 4 independent row loads in flight per thread; row lanes are combined in shared memory, slabs with atomics.
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int ld, int rows, int cols, float* out) {
+  __shared__ float red[8][32][8];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cg) * 8;
+  const int rpb = (rows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rpb, r1 = min(rows, r0 + rpb);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < cols) {
+    int r = r0 + rl;
+    for (; r + 24 < r1; r += 32) {
+      float v0[8], v1[8], v2[8], v3[8];
+      ld8<T>(x + (size_t)r * ld + c, v0); ld8<T>(x + (size_t)(r + 8) * ld + c, v1);
+      ld8<T>(x + (size_t)(r + 16) * ld + c, v2); ld8<T>(x + (size_t)(r + 24) * ld + c, v3);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += (v0[u] + v1[u]) + (v2[u] + v3[u]);
+    }
+    for (; r < r1; r += 8) {
+      float v0[8];
+      ld8<T>(x + (size_t)r * ld + c, v0);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] += v0[u];
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) red[rl][cg][u] = acc[u];
+  __syncthreads();
+  if (rl == 0 && c < cols) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += red[k][cg][u];
+      if (c + u < cols) atomicAdd(out + c + u, s);
+    }
+  }
+}
+// generic fallback (unaligned / ld not a multiple of 8)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_scalar_kernel(const T* __restrict__ x, int ld, int rows, int cols, float* out) {
   const int c = blockIdx.x * 256 + threadIdx.x;
   if (c >= cols) return;
   const int rpb = (rows + gridDim.y - 1) / gridDim.y;
@@ -550,7 +592,7 @@ int k_butd_prep(int dt, const void* u, int ldu, const float* vl, const float* al
 int k_butd_prep_bwd(int dt, const void* duw, const float* dcb, const void* u, int ldu, const void* uw, const float* vl,
                     const float* alpha_l, const float* bva, void* du, int lddu, float* dwl, float* dbva, float* dbl, int B,
                     int Hd, cudaStream_t st) {
-  DISPATCH_T(dt, (butd_prep_bwd_kernel<T><<<ceil_div(Hd, 256), 256, 0, st>>>(
+  DISPATCH_T(dt, (butd_prep_bwd_kernel<T><<<dim3(ceil_div(Hd, 256), std::max(1, std::min(B / 8, 32))), 256, 0, st>>>(
                      static_cast<const T*>(duw), dcb, static_cast<const T*>(u), ldu, static_cast<const T*>(uw), vl, alpha_l, bva,
                      static_cast<T*>(du), lddu, dwl, dbva, dbl, B, Hd)));
   REGAT_POST_LAUNCH();
@@ -564,9 +606,17 @@ int k_bce(int B, int A, const float* logits, int ldl, const float* target, float
   return REGAT_OK;
 }
 int k_colsum(int dt, const void* x, int ld, int rows, int cols, float* out, cudaStream_t st) {
-  const int slabs = std::max(1, std::min(rows / 64, 64));
-  dim3 grid(ceil_div(cols, 256), slabs);
-  DISPATCH_T(dt, (colsum_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x), ld, rows, cols, out)));
+  const bool vec = aligned16(x) && ld % 8 == 0 && cols % 8 == 0;
+  if (vec) {
+    const int gx = ceil_div(cols, 256);
+    const int slabs = std::max(1, std::min(ceil_div(rows, 64), std::max(1, 4 * num_sms() / gx)));
+    dim3 grid(gx, slabs);
+    DISPATCH_T(dt, (colsum_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x), ld, rows, cols, out)));
+  } else {
+    const int slabs = std::max(1, std::min(rows / 64, 64));
+    dim3 grid(ceil_div(cols, 256), slabs);
+    DISPATCH_T(dt, (colsum_scalar_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x), ld, rows, cols, out)));
+  }
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
