@@ -104,7 +104,8 @@ __device__ __forceinline__ void epi_store(const EpiArgs& e, int r, int c, float 
 int gemm_simt(int in_dtype, int transA, int transB, int M, int N, int K, const void* A, int lda,
               const void* B, int ldb, void* C, int ldc, int c_dtype, const EpiArgs& e, cudaStream_t st);
 int gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
-            void* C, int ldc, int c_dtype, const EpiArgs& e, int split_k, cudaStream_t st);
+            void* C, int ldc, int c_dtype, const EpiArgs& e, int split_k, cudaStream_t st, int c_block_cols = 0,
+            const long long* c_block_off = nullptr);
 bool gemm_tc_supported(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B,
                        int ldb);
 

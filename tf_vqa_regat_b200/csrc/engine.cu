@@ -53,10 +53,14 @@ struct regat_engine {
   long long ws_need = 0;
   // workspace carve (byte offsets)
   struct Buf { long long off = -1; };
-  Buf lowp, sumsq, alpha, invn, scal, stats, featT, qattT, qlastT, v0, mask, qs, s, strunc, Qb, KVb, v1, P, GB, gate, uqe,
+  Buf lowp, gbias, sumsq, alpha, invn, scal, stats, featT, qattT, qlastT, v0, mask, qs, s, strunc, Qb, KVb, v1, P, GB, gate, uqe,
       uw, cb, weff, att, pooled, pv, joint, hid, logits, dlogits, dhid, djoint, dpv, duqe, dpooled, dv1, dweff, dcb, duw,
       dQb, dKVb, ds, dstrunc, dsq;
   int a_pad = 0;
+  // bf16 mode: layers that share an input sit side by side in one wide bf16 matrix (alpha folded in)
+  long long gq_off = 0, gkv_off = 0, guqe_off = 0;      // element offsets of the groups in the lowp buffer
+  long long bq_off = 0, bkv_off = 0, buqe_off = 0;      // float offsets of the gathered biases in gbias
+  TensorList tl_gather;
   int last_launches = 0;
   int grads_final = 0;
   template <typename T> T* at(const Buf& b) const { return reinterpret_cast<T*>(ws + b.off); }
@@ -119,13 +123,31 @@ long long carve(regat_engine* e) {
   long long off = 0;
   auto take = [&](regat_engine::Buf& b, long long bytes) { b.off = off; off = rup(off + bytes, 256); };
   e->a_pad = (int)rup(A, 64);
-  // bf16 copies of the kernels (bf16 mode only); leading dimension padded to a multiple of 8 elements
+  // bf16 copies of the effective kernels alpha*v (bf16 mode only); row pitch padded to a multiple of 8 elements.
+  // Groups: [Q_0|Q_1] (ld dirs*D), [K_0|K_1|V'_0|V'_1] (ld 2*dirs*D), [q2attention|question_embed] (ld 2*Hd).
   long long lowp_elems = 0;
+  auto place = [&](int l, long long off, int ld) { e->layers[l].lowp_off = off; e->layers[l].lowp_ld = ld; };
+  e->gq_off = lowp_elems;
+  for (int d = 0; d < dirs; ++d) place(e->l_q[d], e->gq_off + d * D, (int)(dirs * D));
+  lowp_elems = rup(lowp_elems + D * dirs * D, 128);
+  e->gkv_off = lowp_elems;
+  for (int d = 0; d < dirs; ++d) {
+    place(e->l_k[d], e->gkv_off + d * D, (int)(2 * dirs * D));
+    place(e->l_out[d], e->gkv_off + (dirs + d) * D, (int)(2 * dirs * D));
+  }
+  lowp_elems = rup(lowp_elems + D * 2 * dirs * D, 128);
+  e->guqe_off = lowp_elems;
+  place(e->l_qa, e->guqe_off, (int)(2 * Hd));
+  place(e->l_qe, e->guqe_off + Hd, (int)(2 * Hd));
+  lowp_elems = rup(lowp_elems + Q * 2 * Hd, 128);
   for (auto& L : e->layers) {
+    if (L.lowp_off >= 0) continue;
     L.lowp_ld = (int)rup(L.cols, 8);
     L.lowp_off = lowp_elems;
     lowp_elems = rup(lowp_elems + (long long)L.rows * L.lowp_ld, 128);
   }
+  e->bq_off = 0; e->bkv_off = dirs * D; e->buqe_off = 3 * dirs * D;
+  take(e->gbias, (3 * dirs * D + 2 * Hd) * 4);
   take(e->lowp, e->dtype == REGAT_BF16 ? lowp_elems * 2 : 0);
   const long long nl = (long long)e->layers.size();
   take(e->sumsq, nl * 4); take(e->alpha, nl * 4); take(e->invn, nl * 4);
@@ -175,6 +197,22 @@ void build_lists(regat_engine* e) {
   }
   e->chunks_v = build_tensor_list(tv);
   e->chunks_opt = build_tensor_list(to);
+  TensorList& tg = e->tl_gather;
+  memset(&tg, 0, sizeof(tg));
+  const long long D = e->cfg.rel_dim, Hd = e->cfg.q_dim;
+  const int dirs = e->cfg.dir_num;
+  auto add = [&](int l, long long dst) {
+    const Layer& L = e->layers[l];
+    if (L.b_off < 0) return;
+    tg.off[tg.n] = L.b_off; tg.numel[tg.n] = L.cols; tg.off_lowp[tg.n] = dst; ++tg.n;
+  };
+  for (int d = 0; d < dirs; ++d) {
+    add(e->l_q[d], e->bq_off + d * D);
+    add(e->l_k[d], e->bkv_off + d * D);
+    add(e->l_out[d], e->bkv_off + (dirs + d) * D);
+  }
+  add(e->l_qa, e->buqe_off);
+  add(e->l_qe, e->buqe_off + Hd);
 }
 
 __global__ void zero_list_kernel(float* buf, TensorList tl) {
@@ -210,12 +248,15 @@ const float* biasp(const regat_engine* e, int l) { return e->layers[l].b_off >= 
 float* gradW(const regat_engine* e, int l, long long row = 0) { return e->grads + e->layers[l].v_off + row * e->layers[l].cols; }
 float* gradB(const regat_engine* e, int l) { return e->layers[l].b_off >= 0 ? e->grads + e->layers[l].b_off : nullptr; }
 const float* alphap(const regat_engine* e, int l) { return e->at<float>(e->alpha) + l; }
+// alpha for GEMM epilogues: folded into the bf16 weight copies, explicit in fp32 parity mode
+const float* alpha_epi(const regat_engine* e, int l) { return e->dtype == REGAT_F32 ? alphap(e, l) : nullptr; }
+const bf16* lowp_at(const regat_engine* e, long long off) { return reinterpret_cast<const bf16*>(e->ws + e->lowp.off) + off; }
 
 // y = act(alpha*(x W) + b)
 int fc_fwd(regat_engine* e, cudaStream_t st, int l, long long w_row0, int rows, int K, const void* x, int ldx, void* y, int ldy,
            int y_dtype, bool relu, bool with_bias = true) {
   EpiArgs ep = epi0();
-  ep.alpha = alphap(e, l);
+  ep.alpha = alpha_epi(e, l);
   ep.bias = with_bias ? biasp(e, l) : nullptr;
   ep.relu = relu;
   return dense(e, st, false, false, rows, e->layers[l].cols, K, x, ldx, W(e, l, w_row0), ldW(e, l), y, ldy, y_dtype, ep);
@@ -224,7 +265,7 @@ int fc_fwd(regat_engine* e, cudaStream_t st, int l, long long w_row0, int rows, 
 int fc_dgrad(regat_engine* e, cudaStream_t st, int l, long long w_row0, int rows, int K_in, const void* dy, int lddy, void* dx,
              int lddx, int dx_dtype, bool accumulate, const void* gate = nullptr, int gate_ld = 0) {
   EpiArgs ep = epi0();
-  ep.alpha = alphap(e, l);
+  ep.alpha = alpha_epi(e, l);
   ep.accumulate = accumulate;
   ep.gate = gate; ep.gate_ld = gate_ld;
   return dense(e, st, false, true, rows, K_in, e->layers[l].cols, dy, lddy, W(e, l, w_row0), ldW(e, l), dx, lddx, dx_dtype, ep);
@@ -242,8 +283,12 @@ int fc_wgrad(regat_engine* e, cudaStream_t st, int l, long long w_row0, int rows
 int prepare_weights(regat_engine* e, cudaStream_t st) {
   float* sumsq = e->at<float>(e->sumsq);
   REGAT_CUDA(cudaMemsetAsync(sumsq, 0, e->layers.size() * sizeof(float), st));
-  REGAT_TRY(k_wn_prepare(e->params, e->tl_v, e->chunks_v, sumsq, e->dtype == REGAT_BF16 ? e->atv(e->lowp) : nullptr, st));
+  REGAT_TRY(k_wn_prepare(e->params, e->tl_v, e->chunks_v, sumsq, nullptr, st));
   REGAT_TRY(k_wn_alpha(e->params, e->tl_v, sumsq, e->at<float>(e->alpha), e->at<float>(e->invn), st));
+  if (e->dtype == REGAT_BF16) {
+    REGAT_TRY(k_wn_scaled_copy(e->params, e->tl_v, e->chunks_v, e->at<float>(e->alpha), e->atv(e->lowp), st));
+    REGAT_TRY(k_gather(e->params, e->tl_gather, e->at<float>(e->gbias), st));
+  }
   const Layer& LL = e->layers[e->l_label];
   REGAT_TRY(k_label_const(e->params, LL.v_off, LL.b_off, alphap(e, e->l_label), e->at<float>(e->scal), st));
   return REGAT_OK;
@@ -276,17 +321,27 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
   {
     EpiArgs ep = epi0();
     REGAT_TRY(dense(e, st, false, false, B, D, Q, qatt, Q, W(e, e->l_self, D), ldW(e, e->l_self), e->atv(e->qs), D, REGAT_F32, ep));
-    ep.alpha = alphap(e, e->l_self); ep.bias = biasp(e, e->l_self);
+    ep.alpha = alpha_epi(e, e->l_self); ep.bias = biasp(e, e->l_self);
     ep.addend = e->at<float>(e->qs); ep.addend_ld = D; ep.addend_rows = N; ep.row_scale = e->at<float>(e->mask);
     ep.c2 = e->atv(e->strunc); ep.c2_ld = D; ep.c2_rows_in = N; ep.c2_rows_keep = M;
     REGAT_TRY(dense(e, st, false, false, R, D, D, v0, D, W(e, e->l_self, 0), ldW(e, e->l_self), e->atv(e->s), D, dt, ep));
   }
   // per direction: Q = query(s), K = key(s[:, :M]), V' = s[:, :M] Kc + bc   graph_att_layer.py:47,55,112-117
   const size_t es = dtype_size(dt);
-  for (int d = 0; d < dirs; ++d) {
-    REGAT_TRY(fc_fwd(e, st, e->l_q[d], 0, R, D, e->atv(e->s), D, e->at<unsigned char>(e->Qb) + (size_t)d * D * es, dirs * D, dt, false));
-    REGAT_TRY(fc_fwd(e, st, e->l_k[d], 0, Rm, D, e->atv(e->strunc), D, e->at<unsigned char>(e->KVb) + (size_t)d * D * es, 2 * dirs * D, dt, false));
-    REGAT_TRY(fc_fwd(e, st, e->l_out[d], 0, Rm, D, e->atv(e->strunc), D, e->at<unsigned char>(e->KVb) + (size_t)(dirs + d) * D * es, 2 * dirs * D, dt, false));
+  if (dt == REGAT_BF16 && e->use_tc) {
+    // one wide GEMM per input: [Q_0|Q_1] = s [W_q0|W_q1] + b,  [K_0|K_1|V'_0|V'_1] = s[:, :M] [W_k0|W_k1|Kc_0|Kc_1] + b
+    EpiArgs ep = epi0();
+    ep.bias = e->at<float>(e->gbias) + e->bq_off;
+    REGAT_TRY(dense(e, st, false, false, R, dirs * D, D, e->atv(e->s), D, lowp_at(e, e->gq_off), dirs * D, e->atv(e->Qb), dirs * D, dt, ep));
+    ep.bias = e->at<float>(e->gbias) + e->bkv_off;
+    REGAT_TRY(dense(e, st, false, false, Rm, 2 * dirs * D, D, e->atv(e->strunc), D, lowp_at(e, e->gkv_off), 2 * dirs * D, e->atv(e->KVb),
+                    2 * dirs * D, dt, ep));
+  } else {
+    for (int d = 0; d < dirs; ++d) {
+      REGAT_TRY(fc_fwd(e, st, e->l_q[d], 0, R, D, e->atv(e->s), D, e->at<unsigned char>(e->Qb) + (size_t)d * D * es, dirs * D, dt, false));
+      REGAT_TRY(fc_fwd(e, st, e->l_k[d], 0, Rm, D, e->atv(e->strunc), D, e->at<unsigned char>(e->KVb) + (size_t)d * D * es, 2 * dirs * D, dt, false));
+      REGAT_TRY(fc_fwd(e, st, e->l_out[d], 0, Rm, D, e->atv(e->strunc), D, e->at<unsigned char>(e->KVb) + (size_t)(dirs + d) * D * es, 2 * dirs * D, dt, false));
+    }
   }
   // fused geometry-bias attention + relu + residual -> v1
   {
@@ -304,13 +359,19 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
                                 training ? e->at<uint64_t>(e->gate) : nullptr, st));
   }
   // BUTD: u = q2attention(q), qe = question_embed(q)                     fusion.py:37,48
-  REGAT_TRY(fc_fwd(e, st, e->l_qa, 0, B, Q, qlast, Q, e->atv(e->uqe), 2 * Hd, dt, false));
-  REGAT_TRY(fc_fwd(e, st, e->l_qe, 0, B, Q, qlast, Q, e->at<unsigned char>(e->uqe) + (size_t)Hd * es, 2 * Hd, dt, false));
+  if (dt == REGAT_BF16 && e->use_tc) {
+    EpiArgs ep = epi0();
+    ep.bias = e->at<float>(e->gbias) + e->buqe_off;
+    REGAT_TRY(dense(e, st, false, false, B, 2 * Hd, Q, qlast, Q, lowp_at(e, e->guqe_off), 2 * Hd, e->atv(e->uqe), 2 * Hd, dt, ep));
+  } else {
+    REGAT_TRY(fc_fwd(e, st, e->l_qa, 0, B, Q, qlast, Q, e->atv(e->uqe), 2 * Hd, dt, false));
+    REGAT_TRY(fc_fwd(e, st, e->l_qe, 0, B, Q, qlast, Q, e->at<unsigned char>(e->uqe) + (size_t)Hd * es, 2 * Hd, dt, false));
+  }
   REGAT_TRY(k_butd_prep(dt, e->atv(e->uqe), 2 * Hd, e->params + e->layers[e->l_lin].v_off, alphap(e, e->l_lin), biasp(e, e->l_va),
                         biasp(e, e->l_lin), e->atv(e->uw), e->at<float>(e->cb), B, Hd, st));
   {  // weff = alpha_va * (uw Wva^T)
     EpiArgs ep = epi0();
-    ep.alpha = alphap(e, e->l_va);
+    ep.alpha = alpha_epi(e, e->l_va);
     REGAT_TRY(dense(e, st, false, true, B, D, Hd, e->atv(e->uw), Hd, W(e, e->l_va), ldW(e, e->l_va), e->atv(e->weff), D, dt, ep));
   }
   REGAT_TRY(regat_butd_pool_fwd(dt, B, N, D, e->atv(e->v1), e->atv(e->weff), e->at<float>(e->cb), e->at<float>(e->att),
@@ -379,17 +440,27 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   {  // weff = alpha_va (uw Wva^T):  dWva_eff = dweff^T uw ;  duw = alpha_va (dweff Wva)
     EpiArgs ep = epi0();
     REGAT_TRY(dense(e, st, true, false, D, Hd, B, e->atv(e->dweff), D, e->atv(e->uw), Hd, gradW(e, e->l_va), Hd, REGAT_F32, ep));
-    ep.alpha = alphap(e, e->l_va);
+    ep.alpha = alpha_epi(e, e->l_va);
     REGAT_TRY(dense(e, st, false, false, B, Hd, D, e->atv(e->dweff), D, W(e, e->l_va), ldW(e, e->l_va), e->atv(e->duw), Hd, dt, ep));
   }
   REGAT_TRY(k_butd_prep_bwd(dt, e->atv(e->duw), e->at<float>(e->dcb), e->atv(e->uqe), 2 * Hd, e->atv(e->uw),
                             e->params + e->layers[e->l_lin].v_off, alphap(e, e->l_lin), biasp(e, e->l_va), e->atv(e->duqe), 2 * Hd,
                             gradW(e, e->l_lin), gradB(e, e->l_va), gradB(e, e->l_lin), B, Hd, st));
-  REGAT_TRY(fc_wgrad(e, st, e->l_qa, 0, B, Q, qlast, Q, e->atv(e->duqe), 2 * Hd, true));
-  REGAT_TRY(fc_wgrad(e, st, e->l_qe, 0, B, Q, qlast, Q, dqe, 2 * Hd, true));
-  if (dq_last) {
-    REGAT_TRY(fc_dgrad(e, st, e->l_qa, 0, B, Q, e->atv(e->duqe), 2 * Hd, dq_last, Q, REGAT_F32, false));
-    REGAT_TRY(fc_dgrad(e, st, e->l_qe, 0, B, Q, dqe, 2 * Hd, dq_last, Q, REGAT_F32, true));
+  if (dt == REGAT_BF16 && e->use_tc) {
+    // [dW_qa | dW_qe] = q_last^T [du | dqe]  (one GEMM scattered into the two kernels' gradient slots);  dq_last = [du|dqe] [W_qa|W_qe]^T
+    const long long offs[2] = {0, e->layers[e->l_qe].v_off - e->layers[e->l_qa].v_off};
+    REGAT_TRY(gemm_tc(1, 0, Q, 2 * Hd, B, qlast, Q, e->atv(e->duqe), 2 * Hd, gradW(e, e->l_qa), Hd, REGAT_F32, epi0(), 1, st, Hd, offs));
+    REGAT_TRY(k_colsum(dt, e->atv(e->duqe), 2 * Hd, B, Hd, gradB(e, e->l_qa), st));
+    REGAT_TRY(k_colsum(dt, dqe, 2 * Hd, B, Hd, gradB(e, e->l_qe), st));
+    if (dq_last)
+      REGAT_TRY(dense(e, st, false, true, B, Q, 2 * Hd, e->atv(e->duqe), 2 * Hd, lowp_at(e, e->guqe_off), 2 * Hd, dq_last, Q, REGAT_F32, epi0()));
+  } else {
+    REGAT_TRY(fc_wgrad(e, st, e->l_qa, 0, B, Q, qlast, Q, e->atv(e->duqe), 2 * Hd, true));
+    REGAT_TRY(fc_wgrad(e, st, e->l_qe, 0, B, Q, qlast, Q, dqe, 2 * Hd, true));
+    if (dq_last) {
+      REGAT_TRY(fc_dgrad(e, st, e->l_qa, 0, B, Q, e->atv(e->duqe), 2 * Hd, dq_last, Q, REGAT_F32, false));
+      REGAT_TRY(fc_dgrad(e, st, e->l_qe, 0, B, Q, dqe, 2 * Hd, dq_last, Q, REGAT_F32, true));
+    }
   }
   // attention backward: dQ, dK, dV', dout (-> ds), dL (in place of P); then the geometry reduction
   REGAT_TRY(regat_attn_bwd(dt, B, N, cf.nongt_dim, D, H, dirs, e->atv(e->Qb), e->atv(e->KVb), e->atv(e->dv1),
@@ -403,16 +474,40 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
     const Layer& LL = e->layers[e->l_label];
     REGAT_TRY(k_label_grad(scal + 1, e->grads, LL.v_off, LL.b_off, st));
   }
-  for (int d = 0; d < dirs; ++d) {
-    unsigned char* dQd = e->at<unsigned char>(e->dQb) + (size_t)d * D * es;
-    unsigned char* dKd = e->at<unsigned char>(e->dKVb) + (size_t)d * D * es;
-    unsigned char* dVd = e->at<unsigned char>(e->dKVb) + (size_t)(dirs + d) * D * es;
-    REGAT_TRY(fc_wgrad(e, st, e->l_q[d], 0, R, D, e->atv(e->s), D, dQd, dirs * D, true));
-    REGAT_TRY(fc_dgrad(e, st, e->l_q[d], 0, R, D, dQd, dirs * D, e->atv(e->ds), D, dt, true));
-    REGAT_TRY(fc_wgrad(e, st, e->l_k[d], 0, Rm, D, e->atv(e->strunc), D, dKd, 2 * dirs * D, true));
-    REGAT_TRY(fc_dgrad(e, st, e->l_k[d], 0, Rm, D, dKd, 2 * dirs * D, e->atv(e->dstrunc), D, dt, d > 0));
-    REGAT_TRY(fc_wgrad(e, st, e->l_out[d], 0, Rm, D, e->atv(e->strunc), D, dVd, 2 * dirs * D, true));
-    REGAT_TRY(fc_dgrad(e, st, e->l_out[d], 0, Rm, D, dVd, 2 * dirs * D, e->atv(e->dstrunc), D, dt, true));
+  if (dt == REGAT_BF16 && e->use_tc) {
+    // weight gradients of side-by-side layers in one GEMM each (column blocks scattered to their own gradient slots),
+    // input gradients with the direction / kind axis folded into K
+    long long qo[2], kvo[4];
+    for (int d = 0; d < dirs; ++d) {
+      qo[d] = e->layers[e->l_q[d]].v_off - e->layers[e->l_q[0]].v_off;
+      kvo[d] = e->layers[e->l_k[d]].v_off - e->layers[e->l_k[0]].v_off;
+      kvo[dirs + d] = e->layers[e->l_out[d]].v_off - e->layers[e->l_k[0]].v_off;
+    }
+    REGAT_TRY(gemm_tc(1, 0, D, dirs * D, R, e->atv(e->s), D, e->atv(e->dQb), dirs * D, gradW(e, e->l_q[0]), D, REGAT_F32, epi0(), 1, st, D, qo));
+    REGAT_TRY(gemm_tc(1, 0, D, 2 * dirs * D, Rm, e->atv(e->strunc), D, e->atv(e->dKVb), 2 * dirs * D, gradW(e, e->l_k[0]), D, REGAT_F32, epi0(), 1,
+                      st, D, kvo));
+    for (int d = 0; d < dirs; ++d) {
+      REGAT_TRY(k_colsum(dt, e->at<unsigned char>(e->dQb) + (size_t)d * D * es, dirs * D, R, D, gradB(e, e->l_q[d]), st));
+      REGAT_TRY(k_colsum(dt, e->at<unsigned char>(e->dKVb) + (size_t)d * D * es, 2 * dirs * D, Rm, D, gradB(e, e->l_k[d]), st));
+      REGAT_TRY(k_colsum(dt, e->at<unsigned char>(e->dKVb) + (size_t)(dirs + d) * D * es, 2 * dirs * D, Rm, D, gradB(e, e->l_out[d]), st));
+    }
+    EpiArgs ep = epi0();
+    ep.accumulate = 1;                                 // ds already holds dout
+    REGAT_TRY(dense(e, st, false, true, R, D, dirs * D, e->atv(e->dQb), dirs * D, lowp_at(e, e->gq_off), dirs * D, e->atv(e->ds), D, dt, ep));
+    REGAT_TRY(dense(e, st, false, true, Rm, D, 2 * dirs * D, e->atv(e->dKVb), 2 * dirs * D, lowp_at(e, e->gkv_off), 2 * dirs * D,
+                    e->atv(e->dstrunc), D, dt, epi0()));
+  } else {
+    for (int d = 0; d < dirs; ++d) {
+      unsigned char* dQd = e->at<unsigned char>(e->dQb) + (size_t)d * D * es;
+      unsigned char* dKd = e->at<unsigned char>(e->dKVb) + (size_t)d * D * es;
+      unsigned char* dVd = e->at<unsigned char>(e->dKVb) + (size_t)(dirs + d) * D * es;
+      REGAT_TRY(fc_wgrad(e, st, e->l_q[d], 0, R, D, e->atv(e->s), D, dQd, dirs * D, true));
+      REGAT_TRY(fc_dgrad(e, st, e->l_q[d], 0, R, D, dQd, dirs * D, e->atv(e->ds), D, dt, true));
+      REGAT_TRY(fc_wgrad(e, st, e->l_k[d], 0, Rm, D, e->atv(e->strunc), D, dKd, 2 * dirs * D, true));
+      REGAT_TRY(fc_dgrad(e, st, e->l_k[d], 0, Rm, D, dKd, 2 * dirs * D, e->atv(e->dstrunc), D, dt, d > 0));
+      REGAT_TRY(fc_wgrad(e, st, e->l_out[d], 0, Rm, D, e->atv(e->strunc), D, dVd, 2 * dirs * D, true));
+      REGAT_TRY(fc_dgrad(e, st, e->l_out[d], 0, Rm, D, dVd, 2 * dirs * D, e->atv(e->dstrunc), D, dt, true));
+    }
   }
   REGAT_TRY(k_addrows(dt, e->atv(e->ds), e->atv(e->dstrunc), B, N, M, D, st));
   // self_weights: s = alpha (v0 Ws[:D] + mask (q Ws[D:])) + b

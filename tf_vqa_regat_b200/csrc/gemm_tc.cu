@@ -38,6 +38,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin) {
@@ -115,62 +118,82 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
 }
 
 struct TcParams {
-  int M, N, K, ldc, c_f32, k_blocks_per_split, total_k_blocks, atomic_out;
+  int M, N, K, ldc, c_f32, k_blocks_per_split, total_k_blocks, atomic_out, tiles_m, tiles_n, splits;
+  int c_block_cols;               // > 0: column block j = c / c_block_cols of C lives at C + c_block_off[j] (fp32 outputs only)
+  long long c_block_off[8];
   void* C;
   EpiArgs e;
 };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+// Persistent: CTA c processes work units c, c+grid, ... where a unit = (m-tile, n-tile, k-split), n fastest so that
+// concurrently running CTAs share A rows in L2.  ACC accumulator stages in TMEM (ACC*BN <= 512 columns) let the epilogue
+// of unit i overlap the MMAs of unit i+1.
+template <int BN, int STAGES, int ACC, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                            const __grid_constant__ CUtensorMap mapB, const TcParams p) {
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = ACC * BN;
+  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tmem_full = empty_bar + STAGES;       // [ACC]
+  uint64_t* tmem_empty = tmem_full + ACC;         // [ACC]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
-  const int kb0 = blockIdx.z * p.k_blocks_per_split;
-  const int kb1 = min(p.total_k_blocks, kb0 + p.k_blocks_per_split);
+  const int tiles_n = p.tiles_n, splits = p.splits;
+  const int units = p.tiles_m * tiles_n * splits;
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    mbar_init(tmem_full, 1);
+    for (int a = 0; a < ACC; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // unit -> (m0, n0, kb0, kb1)
+  auto decode = [&](int u, int& m0, int& n0, int& kb0, int& kb1) {
+    const int tile = u / splits, z = u - tile * splits;
+    const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+    m0 = tm * BM; n0 = tn * BN;
+    kb0 = z * p.k_blocks_per_split;
+    kb1 = min(p.total_k_blocks, kb0 + p.k_blocks_per_split);
+  };
+
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
       int it = 0;
-      for (int kb = kb0; kb < kb1; ++kb, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(empty_bar + s, ph ^ 1);
-        mbar_expect_tx(full_bar + s, STAGE_BYTES);
-        unsigned char* sa = tiles + s * STAGE_BYTES;
-        unsigned char* sb = sa + A_BYTES;
-        if (!A_MN) {
-          tma_load_2d(sa, &mapA, full_bar + s, kb * BK, m0);
-        } else {
+      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+        int m0, n0, kb0, kb1;
+        decode(u, m0, n0, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(empty_bar + s, ph ^ 1);
+          mbar_expect_tx(full_bar + s, STAGE_BYTES);
+          unsigned char* sa = tiles + s * STAGE_BYTES;
+          unsigned char* sb = sa + A_BYTES;
+          if (!A_MN) {
+            tma_load_2d(sa, &mapA, full_bar + s, kb * BK, m0);
+          } else {
 #pragma unroll
-          for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (64 * BK * 2), &mapA, full_bar + s, m0 + c * 64, kb * BK);
-        }
-        if (!B_MN) {
-          tma_load_2d(sb, &mapB, full_bar + s, kb * BK, n0);
-        } else {
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (64 * BK * 2), &mapA, full_bar + s, m0 + c * 64, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &mapB, full_bar + s, kb * BK, n0);
+          } else {
 #pragma unroll
-          for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (64 * BK * 2), &mapB, full_bar + s, n0 + c * 64, kb * BK);
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (64 * BK * 2), &mapB, full_bar + s, n0 + c * 64, kb * BK);
+          }
         }
       }
     }
@@ -178,28 +201,43 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
     // ===== MMA issuer (single thread) =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
-      int it = 0;
-      for (int kb = kb0; kb < kb1; ++kb, ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        mbar_wait(full_bar + s, ph);
+      int it = 0, ui = 0;
+      for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
+        int m0, n0, kb0, kb1;
+        decode(u, m0, n0, kb0, kb1);
+        const int a = ui % ACC;
+        const uint32_t aph = (ui / ACC) & 1;
+        mbar_wait(tmem_empty + a, aph ^ 1);          // epilogue has drained this accumulator stage
         tc_fence_after();
-        const uint32_t sa = smem_u32(tiles + s * STAGE_BYTES), sb = sa + A_BYTES;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(full_bar + s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + s * STAGE_BYTES), sb = sa + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t da = A_MN ? make_desc(sa + k * 2048, 64 * BK * 2, 1024) : make_desc(sa + k * 32, 16, 1024);
-          const uint64_t db = B_MN ? make_desc(sb + k * 2048, 64 * BK * 2, 1024) : make_desc(sb + k * 32, 16, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = A_MN ? make_desc(sa + k * 2048, 64 * BK * 2, 1024) : make_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_desc(sb + k * 2048, 64 * BK * 2, 1024) : make_desc(sb + k * 32, 16, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(empty_bar + s);          // frees the smem slot once these MMAs have read it
         }
-        umma_commit(empty_bar + s);          // frees the smem slot once these MMAs have read it
+        umma_commit(tmem_full + a);            // accumulator of this unit complete
       }
-      umma_commit(tmem_full);                // accumulator complete
     }
   } else {
     // ===== epilogue: TMEM -> registers -> fused epilogue -> global =====
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    int ui = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
+    int m0, n0, kb0, kb1;
+    decode(u, m0, n0, kb0, kb1);
+    const int acc_stage = ui % ACC;
+    mbar_wait(tmem_full + acc_stage, (ui / ACC) & 1);
+    tc_fence_after();
+    const uint32_t tmem_acc = tmem_base + (uint32_t)(acc_stage * BN);
     const int r = m0 + q * 32 + lane;
     const bool row_ok = r < p.M && kb1 > kb0;
     const int rc = min(r, p.M - 1);
@@ -223,17 +261,19 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
 #pragma unroll 1
     for (int cc = 0; cc < BN / 32; ++cc) {
       float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
+      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
       const int c0 = n0 + cc * 32;
       if (!row_ok || c0 >= p.N) continue;
       if (p.atomic_out) {
         float* C = static_cast<float*>(p.C);
+        int cl = c0;
+        if (p.c_block_cols) { const int jb = c0 / p.c_block_cols; C += p.c_block_off[jb]; cl = c0 - jb * p.c_block_cols; }
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (c0 + j < p.N) {
             float x = v[j];
             if (p.e.alpha) x *= p.e.alpha[p.e.alpha_cols ? (c0 + j) / p.e.alpha_cols : 0];
-            atomicAdd(C + (size_t)r * p.ldc + c0 + j, x);
+            atomicAdd(C + (size_t)r * p.ldc + cl + j, x);
           }
       } else if (vec_ok && c0 + 32 <= p.N) {
         // ---- vectorised, branch-free path: every load is issued before its first use
@@ -265,6 +305,10 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
         }
         if (p.c_f32) {
           float* dst = static_cast<float*>(p.C) + (size_t)r * p.ldc + c0;
+          if (p.c_block_cols) {
+            const int jb = c0 / p.c_block_cols;
+            dst = static_cast<float*>(p.C) + p.c_block_off[jb] + (size_t)r * p.ldc + (c0 - jb * p.c_block_cols);
+          }
           if (p.e.accumulate) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -338,12 +382,17 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
         for (int j = 0; j < 32 && c0 + j < p.N; ++j) epi_store<bf16>(p.e, r, c0 + j, v[j], C, p.ldc);
       }
     }
+    // this warp has finished reading the accumulator stage: hand it back to the MMA issuer
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tmem_empty + acc_stage);
+    }  // units
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -392,14 +441,18 @@ int make_map(CUtensorMap* out, const void* base, long long inner, long long oute
   return REGAT_OK;
 }
 
-template <int BN, int STAGES>
-int launch_cfg(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, dim3 grid, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align slack*/ + (2 * STAGES + 1) * 8 + 16;
+template <int BN, int STAGES, int ACC>
+int launch_cfg(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int ctas, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align slack*/ + (2 * STAGES + 2 * ACC) * 8 + 16;
 #define REGAT_TC_CASE(AM, BMN)                                                                              \
   {                                                                                                         \
-    auto kern = gemm_tc_kernel<BN, STAGES, AM, BMN>;                                                        \
-    REGAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
-    kern<<<grid, NTHREADS, smem, st>>>(ma, mb, p);                                                          \
+    auto kern = gemm_tc_kernel<BN, STAGES, ACC, AM, BMN>;                                                   \
+    static bool attr_set = false;                                                                           \
+    if (!attr_set) {                                                                                        \
+      REGAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
+      attr_set = true;                                                                                      \
+    }                                                                                                       \
+    kern<<<ctas, NTHREADS, smem, st>>>(ma, mb, p);                                                          \
   }
   if (!a_mn && b_mn) REGAT_TC_CASE(false, true)
   else if (!a_mn && !b_mn) REGAT_TC_CASE(false, false)
@@ -418,7 +471,7 @@ bool gemm_tc_supported(int transA, int transB, int M, int N, int K, const void* 
 }
 
 int gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
-            int c_dtype, const EpiArgs& e, int split_k, cudaStream_t st) {
+            int c_dtype, const EpiArgs& e, int split_k, cudaStream_t st, int c_block_cols, const long long* c_block_off) {
   if (M <= 0 || N <= 0) return REGAT_OK;
   REGAT_REQUIRE(K > 0, REGAT_ERR_SHAPE, "gemm: K must be positive");
   REGAT_REQUIRE(gemm_tc_supported(transA, transB, M, N, K, A, lda, B, ldb), REGAT_ERR_ALIGN, "gemm_tc: unaligned operands");
@@ -449,10 +502,24 @@ int gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int lda,
   TcParams p;
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.c_f32 = c_dtype == REGAT_F32; p.k_blocks_per_split = kbps; p.total_k_blocks = total_kb;
   p.atomic_out = splits > 1; p.C = C; p.e = e;
-  if (splits > 1) REGAT_CUDA(cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));   // partials are atomically added
-  dim3 grid(tiles_n, tiles_m, splits);
-  if (bn == 256) return launch_cfg<256, 4>(a_mn, b_mn, ma, mb, p, grid, st);
-  return launch_cfg<128, 3>(a_mn, b_mn, ma, mb, p, grid, st);
+  p.c_block_cols = 0;
+  for (int j = 0; j < 8; ++j) p.c_block_off[j] = 0;
+  if (c_block_cols > 0) {
+    REGAT_REQUIRE(c_dtype == REGAT_F32 && plain && c_block_cols % 32 == 0 && N % c_block_cols == 0 && N / c_block_cols <= 8 && c_block_off,
+                  REGAT_ERR_ARG, "gemm_tc: column-block scatter needs a plain fp32 output and <= 8 blocks of a multiple of 32 columns");
+    p.c_block_cols = c_block_cols;
+    for (int j = 0; j < N / c_block_cols; ++j) p.c_block_off[j] = c_block_off[j];
+  }
+  if (splits > 1) {   // partials are atomically added: zero the destination(s)
+    const int nb = c_block_cols > 0 ? N / c_block_cols : 1, bw = c_block_cols > 0 ? c_block_cols : N;
+    for (int j = 0; j < nb; ++j)
+      REGAT_CUDA(cudaMemset2DAsync(static_cast<float*>(C) + p.c_block_off[j], (size_t)ldc * 4, 0, (size_t)bw * 4, (size_t)M, st));
+  }
+  p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.splits = splits;
+  const int units = tiles_m * tiles_n * splits;
+  // BN=256: 4 stages x 48 KB + 2 x 256 TMEM columns, one CTA per SM.  BN=128: 3 stages x 32 KB + 2 x 128 columns, two per SM.
+  if (bn == 256) return launch_cfg<256, 4, 2>(a_mn, b_mn, ma, mb, p, std::min(units, num_sms()), st);
+  return launch_cfg<128, 3, 2>(a_mn, b_mn, ma, mb, p, std::min(units, 2 * num_sms()), st);
 }
 
 }  // namespace regat

@@ -99,6 +99,11 @@ template <bool S3, int NR> struct Opnd {
     hi[i] = tf32_of(x);
     if constexpr (S3) lo[i] = tf32_of(x - __uint_as_float(hi[i]));
   }
+  // EXACT: x came from a bf16 load, i.e. is already a tf32 value -- no conversion instruction needed
+  template <bool EXACT> __device__ __forceinline__ void put(int i, float x) {
+    if constexpr (EXACT && !S3) hi[i] = __float_as_uint(x);
+    else set(i, x);
+  }
 };
 template <bool S3>
 __device__ __forceinline__ void mma_acc(float (&c)[4], const Opnd<S3, 4>& a, const Opnd<S3, 2>& b) {
@@ -292,6 +297,7 @@ __global__ void __launch_bounds__(256, 2) geoattn_fwd_kernel(const FwdParams p) 
   __syncthreads();
 
   // ---- phase 2: attention.  warp <-> head; lane (g = lane/4, t = lane%4) in mma fragment terms.
+  constexpr bool EX = sizeof(T) == 2;      // bf16 inputs are exact tf32 values
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const T* Q = static_cast<const T*>(p.q);
   const T* KV = static_cast<const T*>(p.kv);
@@ -322,8 +328,9 @@ __global__ void __launch_bounds__(256, 2) geoattn_fwd_kernel(const FwdParams p) 
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
             Opnd<S3, 4> a; Opnd<S3, 2> bb;
-            a.set(0, qa[2 * ks]); a.set(1, qb[2 * ks]); a.set(2, qa[2 * ks + 1]); a.set(3, qb[2 * ks + 1]);
-            bb.set(0, kr[2 * ks]); bb.set(1, kr[2 * ks + 1]);
+            a.template put<EX>(0, qa[2 * ks]); a.template put<EX>(1, qb[2 * ks]);
+            a.template put<EX>(2, qa[2 * ks + 1]); a.template put<EX>(3, qb[2 * ks + 1]);
+            bb.template put<EX>(0, kr[2 * ks]); bb.template put<EX>(1, kr[2 * ks + 1]);
             mma_acc<S3>(sacc[nt], a, bb);
           }
         }
@@ -358,8 +365,13 @@ __global__ void __launch_bounds__(256, 2) geoattn_fwd_kernel(const FwdParams p) 
           const int c0 = nt * 8 + 2 * t;
           float* pr0 = p.save_p + (((size_t)b * DH + dh) * N + r0) * M;
           float* pr1 = p.save_p + (((size_t)b * DH + dh) * N + r1) * M;
-          if (r0 < N) { if (c0 < M) pr0[c0] = sacc[nt][0]; if (c0 + 1 < M) pr0[c0 + 1] = sacc[nt][1]; }
-          if (r1 < N) { if (c0 < M) pr1[c0] = sacc[nt][2]; if (c0 + 1 < M) pr1[c0 + 1] = sacc[nt][3]; }
+          if ((M & 1) == 0) {       // rows start 8-byte aligned: one 64-bit store per row
+            if (r0 < N && c0 < M) *reinterpret_cast<float2*>(pr0 + c0) = make_float2(sacc[nt][0], sacc[nt][1]);
+            if (r1 < N && c0 < M) *reinterpret_cast<float2*>(pr1 + c0) = make_float2(sacc[nt][2], sacc[nt][3]);
+          } else {
+            if (r0 < N) { if (c0 < M) pr0[c0] = sacc[nt][0]; if (c0 + 1 < M) pr0[c0 + 1] = sacc[nt][1]; }
+            if (r1 < N) { if (c0 < M) pr1[c0] = sacc[nt][2]; if (c0 + 1 < M) pr1[c0 + 1] = sacc[nt][3]; }
+          }
         }
       }
       // O += P V'.  k-step nt uses keys (8nt+2t, 8nt+2t+1) as (k=t, k=t+4): the C fragment of P is already
@@ -377,7 +389,7 @@ __global__ void __launch_bounds__(256, 2) geoattn_fwd_kernel(const FwdParams p) 
 #pragma unroll
           for (int ot = 0; ot < 8; ++ot) {
             Opnd<S3, 2> bb;
-            bb.set(0, va[ot]); bb.set(1, vb[ot]);
+            bb.template put<EX>(0, va[ot]); bb.template put<EX>(1, vb[ot]);
             mma_acc<S3>(oacc[ot], a, bb);
           }
         }
@@ -439,6 +451,7 @@ template <int NTS> __host__ __device__ constexpr int tile_ld() { return (NTS * 8
 template <typename T, bool S3, int NTS>
 __global__ void __launch_bounds__(128) attn_bwd_kernel(const BwdParams p) {
   constexpr int LDT = tile_ld<NTS>();        // stride of the dL / P tiles, == 8 (mod 32)
+  constexpr bool EX = sizeof(T) == 2;        // bf16 inputs are exact tf32 values
   constexpr int MJ = (NTS + 1) / 2;          // 16-row tiles over keys
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* Qs = reinterpret_cast<float*>(smem_raw);   // [NP][LDX]
@@ -502,8 +515,9 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const BwdParams p) {
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
           Opnd<S3, 4> a; Opnd<S3, 2> bb;
-          a.set(0, da[2 * ks]); a.set(1, db[2 * ks]); a.set(2, da[2 * ks + 1]); a.set(3, db[2 * ks + 1]);
-          bb.set(0, vr[2 * ks]); bb.set(1, vr[2 * ks + 1]);
+          a.template put<EX>(0, da[2 * ks]); a.template put<EX>(1, db[2 * ks]);
+          a.template put<EX>(2, da[2 * ks + 1]); a.template put<EX>(3, db[2 * ks + 1]);
+          bb.template put<EX>(0, vr[2 * ks]); bb.template put<EX>(1, vr[2 * ks + 1]);
           mma_acc<S3>(sacc[nt], a, bb);
         }
       }
@@ -513,10 +527,17 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const BwdParams p) {
 #pragma unroll
     for (int nt = 0; nt < NTS; ++nt) {
       const int c0 = nt * 8 + 2 * t;
-      pr[nt][0] = (r0 < N && c0 < M) ? P_g[(size_t)r0 * M + c0] : 0.f;
-      pr[nt][1] = (r0 < N && c0 + 1 < M) ? P_g[(size_t)r0 * M + c0 + 1] : 0.f;
-      pr[nt][2] = (r1 < N && c0 < M) ? P_g[(size_t)r1 * M + c0] : 0.f;
-      pr[nt][3] = (r1 < N && c0 + 1 < M) ? P_g[(size_t)r1 * M + c0 + 1] : 0.f;
+      if ((M & 1) == 0) {
+        const float2 z2 = make_float2(0.f, 0.f);
+        const float2 p0 = (r0 < N && c0 < M) ? *reinterpret_cast<const float2*>(P_g + (size_t)r0 * M + c0) : z2;
+        const float2 p1 = (r1 < N && c0 < M) ? *reinterpret_cast<const float2*>(P_g + (size_t)r1 * M + c0) : z2;
+        pr[nt][0] = p0.x; pr[nt][1] = p0.y; pr[nt][2] = p1.x; pr[nt][3] = p1.y;
+      } else {
+        pr[nt][0] = (r0 < N && c0 < M) ? P_g[(size_t)r0 * M + c0] : 0.f;
+        pr[nt][1] = (r0 < N && c0 + 1 < M) ? P_g[(size_t)r0 * M + c0 + 1] : 0.f;
+        pr[nt][2] = (r1 < N && c0 < M) ? P_g[(size_t)r1 * M + c0] : 0.f;
+        pr[nt][3] = (r1 < N && c0 + 1 < M) ? P_g[(size_t)r1 * M + c0 + 1] : 0.f;
+      }
       dl0 += pr[nt][0] * sacc[nt][0] + pr[nt][1] * sacc[nt][1];
       dl1 += pr[nt][2] * sacc[nt][2] + pr[nt][3] * sacc[nt][3];
     }
@@ -530,8 +551,13 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const BwdParams p) {
       float dl[4];
       dl[0] = pr[nt][0] * (sacc[nt][0] - dl0); dl[1] = pr[nt][1] * (sacc[nt][1] - dl0);
       dl[2] = pr[nt][2] * (sacc[nt][2] - dl1); dl[3] = pr[nt][3] * (sacc[nt][3] - dl1);
-      if (r0 < N) { if (c0 < M) P_g[(size_t)r0 * M + c0] = dl[0]; if (c0 + 1 < M) P_g[(size_t)r0 * M + c0 + 1] = dl[1]; }
-      if (r1 < N) { if (c0 < M) P_g[(size_t)r1 * M + c0] = dl[2]; if (c0 + 1 < M) P_g[(size_t)r1 * M + c0 + 1] = dl[3]; }
+      if ((M & 1) == 0) {
+        if (r0 < N && c0 < M) *reinterpret_cast<float2*>(P_g + (size_t)r0 * M + c0) = make_float2(dl[0], dl[1]);
+        if (r1 < N && c0 < M) *reinterpret_cast<float2*>(P_g + (size_t)r1 * M + c0) = make_float2(dl[2], dl[3]);
+      } else {
+        if (r0 < N) { if (c0 < M) P_g[(size_t)r0 * M + c0] = dl[0]; if (c0 + 1 < M) P_g[(size_t)r0 * M + c0 + 1] = dl[1]; }
+        if (r1 < N) { if (c0 < M) P_g[(size_t)r1 * M + c0] = dl[2]; if (c0 + 1 < M) P_g[(size_t)r1 * M + c0 + 1] = dl[3]; }
+      }
       if (c0 < NTS * 8) {
         *reinterpret_cast<float2*>(Ls + r0 * LDT + c0) = make_float2(dl[0], dl[1]);
         *reinterpret_cast<float2*>(Ls + r1 * LDT + c0) = make_float2(dl[2], dl[3]);
@@ -548,7 +574,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const BwdParams p) {
 #pragma unroll
         for (int ot = 0; ot < 8; ++ot) {
           Opnd<S3, 2> bb;
-          bb.set(0, ka[ot]); bb.set(1, kb[ot]);
+          bb.template put<EX>(0, ka[ot]); bb.template put<EX>(1, kb[ot]);
           mma_acc<S3>(dqacc[ot], a, bb);
         }
       }
@@ -582,8 +608,8 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const BwdParams p) {
     const float2 o0 = *reinterpret_cast<const float2*>(dOs + i0 * LDX + 16 * warp + 2 * g);
     const float2 o1 = *reinterpret_cast<const float2*>(dOs + i1 * LDX + 16 * warp + 2 * g);
     Opnd<S3, 2> bq[2], bo[2];
-    bq[0].set(0, q0.x); bq[0].set(1, q1.x); bq[1].set(0, q0.y); bq[1].set(1, q1.y);
-    bo[0].set(0, o0.x); bo[0].set(1, o1.x); bo[1].set(0, o0.y); bo[1].set(1, o1.y);
+    bq[0].template put<EX>(0, q0.x); bq[0].template put<EX>(1, q1.x); bq[1].template put<EX>(0, q0.y); bq[1].template put<EX>(1, q1.y);
+    bo[0].template put<EX>(0, o0.x); bo[0].template put<EX>(1, o1.x); bo[1].template put<EX>(0, o0.y); bo[1].template put<EX>(1, o1.y);
 #pragma unroll
     for (int jm = 0; jm < MJ; ++jm) {
       if (jm * 16 < M) {

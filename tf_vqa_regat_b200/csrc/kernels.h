@@ -28,6 +28,8 @@ struct OptHyper {
 };
 
 int k_wn_prepare(const float* params, const TensorList& tl, int chunks, float* sumsq, void* lowp, cudaStream_t st);
+int k_wn_scaled_copy(const float* params, const TensorList& tl, int chunks, const float* alpha, void* lowp, cudaStream_t st);
+int k_gather(const float* src, const TensorList& tl, float* dst, cudaStream_t st);
 int k_wn_alpha(const float* params, const TensorList& tl, const float* sumsq, float* alpha, float* inv_norm, cudaStream_t st);
 int k_cast(int to_dtype, const float* in, void* out, long long n, cudaStream_t st);
 int k_rowmask(int dt, const void* v, int rows, int D, float* mask, cudaStream_t st);

@@ -70,6 +70,41 @@ __global__ void __launch_bounds__(256) wn_prepare_kernel(const float* __restrict
   if (threadIdx.x == 0) atomicAdd(sumsq + l, ss);
 }
 
+// second pass of the bf16 weight preparation: lowp = bf16(alpha_l * v) = bf16(W_eff), placed at (off_lowp, ld_lowp) so that
+// layers sharing an input can sit side by side in one wide matrix (Q_0|Q_1, K_0|K_1|V'_0|V'_1, q2attention|question_embed).
+__global__ void __launch_bounds__(256) wn_scaled_copy_kernel(const float* __restrict__ params, TensorList tl,
+                                                             const float* __restrict__ alpha, bf16* __restrict__ lowp) {
+  int l = 0;
+  while (l + 1 < tl.n && (int)blockIdx.x >= tl.chunk_start[l + 1]) ++l;
+  const long long base = (long long)(blockIdx.x - tl.chunk_start[l]) * WN_CHUNK;
+  const float* v = params + tl.off[l];
+  const long long n = tl.numel[l];
+  const float a = alpha[tl.layer[l]];
+  const int cols = tl.cols[l], ld = tl.ld_lowp[l];
+  bf16* dst = lowp + tl.off_lowp[l];
+  if ((cols & 7) == 0 && (ld & 7) == 0) {
+    for (long long i = base + threadIdx.x * 8; i < min(base + (long long)WN_CHUNK, n); i += 256 * 8) {
+      float x[8];
+      ld8<float>(v + i, x);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x[u] *= a;
+      const long long r = i / cols, c = i - r * cols;
+      st8<bf16>(dst + r * ld + c, x);
+    }
+  } else {
+    for (long long i = base + threadIdx.x; i < min(base + (long long)WN_CHUNK, n); i += 256) {
+      const long long r = i / cols, c = i - r * cols;
+      dst[r * ld + c] = __float2bfloat16_rn(a * v[i]);
+    }
+  }
+}
+
+// dst[dst_off[l] + i] = src[off[l] + i]: biases of side-by-side layers gathered into one contiguous vector
+__global__ void gather_kernel(const float* __restrict__ src, TensorList tl, float* __restrict__ dst) {
+  for (int l = blockIdx.x; l < tl.n; l += gridDim.x)
+    for (long long i = threadIdx.x; i < tl.numel[l]; i += blockDim.x) dst[tl.off_lowp[l] + i] = src[tl.off[l] + i];
+}
+
 __global__ void wn_alpha_kernel(const float* __restrict__ params, TensorList tl, const float* __restrict__ sumsq,
                                 float* alpha, float* inv_norm) {
   const int l = threadIdx.x;
@@ -545,6 +580,16 @@ int build_tensor_list(TensorList& tl) {
 
 int k_wn_prepare(const float* params, const TensorList& tl, int chunks, float* sumsq, void* lowp, cudaStream_t st) {
   wn_prepare_kernel<<<chunks, 256, 0, st>>>(params, tl, sumsq, static_cast<bf16*>(lowp));
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+int k_wn_scaled_copy(const float* params, const TensorList& tl, int chunks, const float* alpha, void* lowp, cudaStream_t st) {
+  wn_scaled_copy_kernel<<<chunks, 256, 0, st>>>(params, tl, alpha, static_cast<bf16*>(lowp));
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+int k_gather(const float* src, const TensorList& tl, float* dst, cudaStream_t st) {
+  gather_kernel<<<tl.n, 256, 0, st>>>(src, tl, dst);
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
