@@ -55,7 +55,7 @@ struct regat_engine {
   struct Buf { long long off = -1; };
   Buf lowp, gbias, sumsq, alpha, invn, scal, stats, featT, qattT, qlastT, v0, mask, qs, s, strunc, Qb, KVb, v1, P, GB, gate, uqe,
       uw, cb, weff, att, pooled, pv, joint, hid, logits, dlogits, dhid, djoint, dpv, duqe, dpooled, dv1, dweff, dcb, duw,
-      dQb, dKVb, ds, dstrunc, dsq;
+      dQb, dKVb, ds, dstrunc, dsq, dwc3;
   int a_pad = 0;
   // bf16 mode: layers that share an input sit side by side in one wide bf16 matrix (alpha folded in)
   long long gq_off = 0, gkv_off = 0, guqe_off = 0;      // element offsets of the groups in the lowp buffer
@@ -167,7 +167,8 @@ long long carve(regat_engine* e) {
   take(e->uqe, B * 2 * Hd * es); take(e->uw, B * Hd * es); take(e->cb, B * 4);
   take(e->weff, B * D * es); take(e->att, B * N * 4); take(e->pooled, B * D * es);
   take(e->pv, B * Hd * es); take(e->joint, B * Hd * es); take(e->hid, B * 2 * Hd * es);
-  take(e->logits, B * A * 4);
+  take(e->logits, B * e->a_pad * 4);
+  take(e->dwc3, e->dtype == REGAT_BF16 ? 2 * Hd * (long long)e->a_pad * 4 : 0);
   take(e->dlogits, B * e->a_pad * es);
   take(e->dhid, B * 2 * Hd * es); take(e->djoint, B * Hd * es); take(e->dpv, B * Hd * es); take(e->duqe, B * 2 * Hd * es);
   take(e->dpooled, B * D * es); take(e->dv1, R * D * es); take(e->dweff, B * D * es); take(e->dcb, B * 4);
@@ -381,9 +382,11 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
   REGAT_TRY(k_mul(dt, e->atv(e->pv), Hd, e->at<unsigned char>(e->uqe) + (size_t)Hd * es, 2 * Hd, e->atv(e->joint), Hd, B, Hd, st));
   // classifier                                                          classifier.py:14-25
   REGAT_TRY(fc_fwd(e, st, e->l_c0, 0, B, Hd, e->atv(e->joint), Hd, e->atv(e->hid), 2 * Hd, dt, true));
-  REGAT_TRY(fc_fwd(e, st, e->l_c3, 0, B, 2 * Hd, e->atv(e->hid), 2 * Hd, e->atv(e->logits), A, REGAT_F32, false));
+  // logits live in a buffer whose row pitch is padded to 16 bytes (3129 -> 3136) so the epilogue can use vector stores
+  REGAT_TRY(fc_fwd(e, st, e->l_c3, 0, B, 2 * Hd, e->atv(e->hid), 2 * Hd, e->atv(e->logits), e->a_pad, REGAT_F32, false));
   if (logits_out)
-    REGAT_CUDA(cudaMemcpyAsync(logits_out, e->atv(e->logits), (size_t)B * A * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    REGAT_CUDA(cudaMemcpy2DAsync(logits_out, (size_t)A * sizeof(float), e->atv(e->logits), (size_t)e->a_pad * sizeof(float),
+                                 (size_t)A * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
   return REGAT_OK;
 }
 
@@ -422,9 +425,18 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
     REGAT_CUDA(cudaMemsetAsync(scal + 1, 0, 3 * sizeof(float), st));   // dc, loss, score
   }
   // loss + dlogits                                                     train.py:107-108
-  REGAT_TRY(k_bce(B, A, e->at<float>(e->logits), A, target, grad_scale, scal + 2, scal + 3, e->atv(e->dlogits), e->a_pad, dt, st));
+  REGAT_TRY(k_bce(B, A, e->at<float>(e->logits), e->a_pad, target, grad_scale, scal + 2, scal + 3, e->atv(e->dlogits), e->a_pad, dt, st));
   // classifier
-  REGAT_TRY(fc_wgrad(e, st, e->l_c3, 0, B, 2 * Hd, e->atv(e->hid), 2 * Hd, e->atv(e->dlogits), e->a_pad, true));
+  if (dt == REGAT_BF16 && e->use_tc && (A % 4) != 0) {
+    // the [2Hd, A] gradient has unaligned rows (A = 3129): compute it with a padded pitch, then compact into the flat buffer
+    REGAT_TRY(dense(e, st, true, false, 2 * Hd, A, B, e->atv(e->hid), 2 * Hd, e->atv(e->dlogits), e->a_pad, e->atv(e->dwc3), e->a_pad,
+                    REGAT_F32, epi0()));
+    REGAT_CUDA(cudaMemcpy2DAsync(gradW(e, e->l_c3), (size_t)A * sizeof(float), e->atv(e->dwc3), (size_t)e->a_pad * sizeof(float),
+                                 (size_t)A * sizeof(float), 2 * Hd, cudaMemcpyDeviceToDevice, st));
+    REGAT_TRY(k_colsum(dt, e->atv(e->dlogits), e->a_pad, B, A, gradB(e, e->l_c3), st));
+  } else {
+    REGAT_TRY(fc_wgrad(e, st, e->l_c3, 0, B, 2 * Hd, e->atv(e->hid), 2 * Hd, e->atv(e->dlogits), e->a_pad, true));
+  }
   REGAT_TRY(fc_dgrad(e, st, e->l_c3, 0, B, 2 * Hd, e->atv(e->dlogits), e->a_pad, e->atv(e->dhid), 2 * Hd, dt, false, e->atv(e->hid), 2 * Hd));
   REGAT_TRY(fc_wgrad(e, st, e->l_c0, 0, B, Hd, e->atv(e->joint), Hd, e->atv(e->dhid), 2 * Hd, true));
   REGAT_TRY(fc_dgrad(e, st, e->l_c0, 0, B, Hd, e->atv(e->dhid), 2 * Hd, e->atv(e->djoint), Hd, dt, false));

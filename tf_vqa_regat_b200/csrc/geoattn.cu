@@ -80,30 +80,30 @@ __device__ __forceinline__ void pair_embedding(const float4& oi, const float4& o
 
 // ------------------------------------------------------------------------------------------
 // mma.sync m16n8k8 tf32 helpers
-__device__ __forceinline__ uint32_t tf32_of(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-// operand prepared once, used for 1 (bf16 mode) or 3 (fp32 mode, 3xTF32) mma
+// Operand prepared once, used for 1 (bf16 mode) or 3 (fp32 mode, 3xTF32) mma.
+// cvt.rna.tf32.f32 is emulated with ~6 integer instructions on sm_100a (measured: it was 40% of this kernel), so:
+//   * single-pass mode feeds the fp32 bit pattern as is -- the tensor core reads only the upper 19 bits (truncation; bf16
+//     inputs are exact, probabilities lose < 2^-10 relative, inside the bf16-mode tolerance);
+//   * 3xTF32 splits with one mask: hi = x & ~0x1fff (exact tf32), lo = x - hi (exact in fp32, then truncated by the MMA):
+//     hi*hi + hi*lo + lo*hi reproduces the fp32 product to ~2^-21.
 template <bool S3, int NR> struct Opnd {
   uint32_t hi[NR];
   uint32_t lo[S3 ? NR : 1];
   __device__ __forceinline__ void set(int i, float x) {
-    hi[i] = tf32_of(x);
-    if constexpr (S3) lo[i] = tf32_of(x - __uint_as_float(hi[i]));
+    if constexpr (S3) {
+      hi[i] = __float_as_uint(x) & 0xffffe000u;
+      lo[i] = __float_as_uint(x - __uint_as_float(hi[i]));
+    } else {
+      hi[i] = __float_as_uint(x);
+    }
   }
-  // EXACT: x came from a bf16 load, i.e. is already a tf32 value -- no conversion instruction needed
-  template <bool EXACT> __device__ __forceinline__ void put(int i, float x) {
-    if constexpr (EXACT && !S3) hi[i] = __float_as_uint(x);
-    else set(i, x);
-  }
+  template <bool EXACT> __device__ __forceinline__ void put(int i, float x) { set(i, x); }
 };
 template <bool S3>
 __device__ __forceinline__ void mma_acc(float (&c)[4], const Opnd<S3, 4>& a, const Opnd<S3, 2>& b) {
@@ -479,8 +479,10 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const BwdParams p) {
       for (int u = 0; u < 8; ++u) dv[u] = ((bits >> (e0 + u)) & 1ull) ? dv[u] : 0.f;
       if (d == 0) store_n<T>(static_cast<T*>(p.dout) + ((size_t)b * N + i) * D + h * HD + e0, dv, 8);
     }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) { Qs[i * LDX + e0 + u] = qv[u]; dOs[i * LDX + e0 + u] = dv[u]; }
+    *reinterpret_cast<float4*>(Qs + i * LDX + e0) = make_float4(qv[0], qv[1], qv[2], qv[3]);
+    *reinterpret_cast<float4*>(Qs + i * LDX + e0 + 4) = make_float4(qv[4], qv[5], qv[6], qv[7]);
+    *reinterpret_cast<float4*>(dOs + i * LDX + e0) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+    *reinterpret_cast<float4*>(dOs + i * LDX + e0 + 4) = make_float4(dv[4], dv[5], dv[6], dv[7]);
   }
   // zero the key padding of the dL / P tiles (columns >= M are never written below)
   for (int x = tid; x < NP * LDT; x += 128) { Ls[x] = 0.f; Ps[x] = 0.f; }
