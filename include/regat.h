@@ -250,6 +250,12 @@ REGAT_API int regat_engine_train_step(regat_engine* e, int B, int N, const float
                             const float* boxes, const float* q_att, const float* q_last,
                             const float* target, float lr, int step, float* loss_out,
                             regat_stream_t stream);
+/* Data parallel: fn(user, offset, numel) is called from inside regat_engine_fwd_bwd (on the calling thread, while the
+ * call is still enqueueing) each time a contiguous range of the grads buffer has received its last write on `stream`:
+ * first the BUTD + classifier tail, then self_weights + attention layers, then v2out.  The callee typically records an
+ * event on `stream` and starts an all-reduce of that range on another stream, overlapping the rest of the backward.  */
+typedef void (*regat_grad_ready_fn)(void* user, int64_t offset, int64_t numel);
+REGAT_API int regat_engine_set_grad_callback(regat_engine* e, regat_grad_ready_fn fn, void* user);
 /* Number of kernel launches the last engine call issued (for bench.py's gpu_launches). */
 REGAT_API int regat_engine_last_launches(const regat_engine* e);
 /* Copies the configuration the engine was created with. */

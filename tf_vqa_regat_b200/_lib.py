@@ -31,6 +31,7 @@ class Epilogue(C.Structure):
                 ("split_k", C.c_int32)]
 
 
+GRAD_READY_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int64, C.c_int64)
 _lib = None
 vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
 
@@ -62,6 +63,7 @@ SIGNATURES = {
     "regat_engine_fwd_bwd": [vp, i32, i32, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp],
     "regat_engine_update": [vp, f32, i32, vp],
     "regat_engine_train_step": [vp, i32, i32, vp, vp, vp, vp, vp, f32, i32, vp, vp],
+    "regat_engine_set_grad_callback": [vp, vp, vp],
     "regat_engine_last_launches": [vp],
     "regat_engine_config": [vp, C.POINTER(Config)],
     "regat_engine_set_wave_div": [vp, vp],

@@ -63,6 +63,8 @@ struct regat_engine {
   TensorList tl_gather;
   int last_launches = 0;
   int grads_final = 0;
+  regat_grad_ready_fn grad_cb = nullptr;   // data parallel: called when a range of `grads` is final on the stream
+  void* grad_cb_user = nullptr;
   template <typename T> T* at(const Buf& b) const { return reinterpret_cast<T*>(ws + b.off); }
   void* atv(const Buf& b) const { return ws + b.off; }
 };
@@ -390,6 +392,14 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
   return REGAT_OK;
 }
 
+// [first layer's v, end of last layer) of the flat buffer is final: tell the data-parallel layer (it may start the all-reduce)
+void grads_ready(regat_engine* e, int l_first, int l_last) {
+  if (!e->grad_cb) return;
+  const long long lo = e->layers[l_first].v_off;
+  const long long hi = (l_last + 1 < (int)e->layers.size()) ? e->layers[l_last + 1].v_off : e->param_elems;
+  e->grad_cb(e->grad_cb_user, lo, hi - lo);
+}
+
 int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float* dq_last) {
   regat_engine* e = c.e;
   cudaStream_t st = c.st;
@@ -474,6 +484,7 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
       REGAT_TRY(fc_dgrad(e, st, e->l_qe, 0, B, Q, dqe, 2 * Hd, dq_last, Q, REGAT_F32, true));
     }
   }
+  grads_ready(e, e->l_va, e->l_c3);       // BUTD + classifier gradients are final: the tail of the flat buffer
   // attention backward: dQ, dK, dV', dout (-> ds), dL (in place of P); then the geometry reduction
   REGAT_TRY(regat_attn_bwd(dt, B, N, cf.nongt_dim, D, H, dirs, e->atv(e->Qb), e->atv(e->KVb), e->atv(e->dv1),
                            e->at<uint64_t>(e->gate), e->at<float>(e->P), e->atv(e->dQb), e->atv(e->dKVb), e->atv(e->ds), st));
@@ -526,11 +537,13 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   REGAT_TRY(fc_wgrad(e, st, e->l_self, 0, R, D, v0, D, e->atv(e->ds), D, true));
   REGAT_TRY(k_segsum(dt, e->atv(e->ds), e->at<float>(e->mask), B, N, D, e->atv(e->dsq), st));
   REGAT_TRY(fc_wgrad(e, st, e->l_self, D, B, Q, qatt, Q, e->atv(e->dsq), D, false));
+  grads_ready(e, e->l_self, e->l_va - 1);   // self_weights, label FC and both attention layers
   if (dq_att) REGAT_TRY(fc_dgrad(e, st, e->l_self, D, B, Q, e->atv(e->dsq), D, dq_att, Q, REGAT_F32, false));
   if (e->l_v2out >= 0) {
     // dv0 = (dv1 [residual] + alpha ds Ws[:D]^T) o (v0 > 0), in place in the dv1 buffer; then v2out's gradients
     REGAT_TRY(fc_dgrad(e, st, e->l_self, 0, R, D, e->atv(e->ds), D, e->atv(e->dv1), D, dt, cf.residual != 0, v0, D));
     REGAT_TRY(fc_wgrad(e, st, e->l_v2out, 0, R, V, feat, V, e->atv(e->dv1), D, true));
+    grads_ready(e, e->l_v2out, e->l_v2out);
   }
   e->grads_final = 0;
   return REGAT_OK;
@@ -681,6 +694,12 @@ extern "C" int regat_engine_train_step(regat_engine* e, int B, int N, const floa
 }
 
 extern "C" int regat_engine_last_launches(const regat_engine* e) { return e ? e->last_launches : 0; }
+
+extern "C" int regat_engine_set_grad_callback(regat_engine* e, regat_grad_ready_fn fn, void* user) {
+  REGAT_REQUIRE(e, REGAT_ERR_ARG, "engine is null");
+  e->grad_cb = fn; e->grad_cb_user = user;
+  return REGAT_OK;
+}
 
 extern "C" int regat_engine_set_wave_div(regat_engine* e, const float* wave_div_host) {
   REGAT_REQUIRE(e && wave_div_host, REGAT_ERR_ARG, "engine_set_wave_div: null pointer");

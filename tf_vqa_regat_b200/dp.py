@@ -37,22 +37,47 @@ def allreduce_flat_(flat: torch.Tensor, group=None, bucket_elems: int = 0):
 
 
 class DataParallelTrainer:
-    """engine: anything with fwd_bwd(..., grad_scale=) -> dict(loss, score), .grads (flat tensor), .update(lr, step)."""
+    """engine: anything with fwd_bwd(..., grad_scale=) -> dict(loss, score), .grads (flat tensor), .update(lr, step) and
+    optionally set_grad_callback(fn) (HotPathEngine): with it, each range of the flat gradient buffer is all-reduced on a side
+    stream as soon as the backward pass has finished writing it, overlapping the remaining backward kernels."""
 
-    def __init__(self, engine, group=None, bucket_elems: int = 0):
+    def __init__(self, engine, group=None, bucket_elems: int = 0, overlap: bool = True):
         self.engine, self.group, self.bucket_elems = engine, group, bucket_elems
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.step_count = 0
+        self.overlap = bool(overlap and self.world > 1 and hasattr(engine, "set_grad_callback") and engine.grads.is_cuda)
+        self._reduced = 0
+        if self.overlap:
+            self.comm_stream = torch.cuda.Stream(engine.grads.device)
+            engine.set_grad_callback(self._on_ready)
+
+    def _on_ready(self, offset, numel):
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            dist.all_reduce(self.engine.grads[offset:offset + numel], op=dist.ReduceOp.SUM, group=self.group)
+        self._reduced += numel
 
     def broadcast_params(self, src: int = 0):
         if self.world > 1:
             dist.broadcast(self.engine.params, src=src, group=self.group)
 
+    def fwd_bwd_allreduce(self, features, boxes, q_att, q_last, target):
+        """Forward + backward on this rank's shard with the gradient all-reduce (overlapped when possible)."""
+        self._reduced = 0
+        out = self.engine.fwd_bwd(features, boxes, q_att, q_last, target, grad_scale=1.0 / self.world)
+        if self.overlap and self._reduced == self.engine.grads.numel():
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        else:
+            allreduce_flat_(self.engine.grads, self.group, self.bucket_elems)
+        return out
+
     def step(self, features, boxes, q_att, q_last, target, lr):
         """One optimizer step on this rank's shard (already sliced)."""
         self.step_count += 1
-        out = self.engine.fwd_bwd(features, boxes, q_att, q_last, target, grad_scale=1.0 / self.world)
-        allreduce_flat_(self.engine.grads, self.group, self.bucket_elems)
+        out = self.fwd_bwd_allreduce(features, boxes, q_att, q_last, target)
         self.engine.update(lr, self.step_count)
         return out

@@ -130,6 +130,16 @@ class HotPathEngine:
                                                     self._loss.data_ptr(), _stream()))
         return self._loss
 
+    def set_grad_callback(self, fn):
+        """fn(offset, numel) is invoked inside fwd_bwd whenever grads[offset:offset+numel] is final on the current stream
+        (tail of the buffer first).  Pass None to remove it."""
+        if fn is None:
+            self._cb = None
+            _lib.check(self.lib.regat_engine_set_grad_callback(self._h, None, None))
+            return
+        self._cb = _lib.GRAD_READY_FN(lambda user, off, n: fn(int(off), int(n)))
+        _lib.check(self.lib.regat_engine_set_grad_callback(self._h, C.cast(self._cb, C.c_void_p), None))
+
     def last_launches(self):
         return self.lib.regat_engine_last_launches(self._h)
 
