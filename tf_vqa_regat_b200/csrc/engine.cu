@@ -63,6 +63,9 @@ struct regat_engine {
   TensorList tl_gather;
   int last_launches = 0;
   int grads_final = 0;
+  // small independent work (BUTD question branch, tiny weight gradients) runs on a side stream, forked / joined with events
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   regat_grad_ready_fn grad_cb = nullptr;   // data parallel: called when a range of `grads` is final on the stream
   void* grad_cb_user = nullptr;
   template <typename T> T* at(const Buf& b) const { return reinterpret_cast<T*>(ws + b.off); }
@@ -297,6 +300,19 @@ int prepare_weights(regat_engine* e, cudaStream_t st) {
   return REGAT_OK;
 }
 
+int ensure_side(regat_engine* e) {
+  if (e->side) return REGAT_OK;
+  REGAT_CUDA(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+  for (int i = 0; i < 6; ++i) REGAT_CUDA(cudaEventCreateWithFlags(&e->ev[i], cudaEventDisableTiming));
+  return REGAT_OK;
+}
+// side stream waits for everything enqueued on `from` so far
+int fork_to(cudaStream_t from, cudaStream_t to, cudaEvent_t ev) {
+  REGAT_CUDA(cudaEventRecord(ev, from));
+  REGAT_CUDA(cudaStreamWaitEvent(to, ev, 0));
+  return REGAT_OK;
+}
+
 int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
   regat_engine* e = c.e;
   cudaStream_t st = c.st;
@@ -304,14 +320,38 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
   const int dt = e->dtype, B = c.B, N = c.N, M = c.M, R = c.R, Rm = c.Rm;
   const int V = cf.v_dim, Q = cf.q_dim, D = cf.rel_dim, H = cf.num_heads, A = cf.num_answers, Hd = cf.q_dim, dirs = cf.dir_num;
 
+  REGAT_TRY(ensure_side(e));
+  cudaStream_t sd = e->side;
+  const size_t es = dtype_size(dt);
   REGAT_TRY(prepare_weights(e, st));
   // activations in the compute dtype
   const void* feat = c.features; const void* qatt = c.q_att; const void* qlast = c.q_last;
   if (dt == REGAT_BF16) {
+    REGAT_TRY(k_cast(REGAT_BF16, c.q_last, e->atv(e->qlastT), (long long)B * Q, st));
+    qlast = e->atv(e->qlastT);
+  }
+  // ---- side stream: the question branch of BUTD depends only on q_last and the weights (fusion.py:37,47-52)
+  REGAT_TRY(fork_to(st, sd, e->ev[0]));
+  if (dt == REGAT_BF16 && e->use_tc) {
+    EpiArgs ep = epi0();
+    ep.bias = e->at<float>(e->gbias) + e->buqe_off;
+    REGAT_TRY(dense(e, sd, false, false, B, 2 * Hd, Q, qlast, Q, lowp_at(e, e->guqe_off), 2 * Hd, e->atv(e->uqe), 2 * Hd, dt, ep));
+  } else {
+    REGAT_TRY(fc_fwd(e, sd, e->l_qa, 0, B, Q, qlast, Q, e->atv(e->uqe), 2 * Hd, dt, false));
+    REGAT_TRY(fc_fwd(e, sd, e->l_qe, 0, B, Q, qlast, Q, e->at<unsigned char>(e->uqe) + (size_t)Hd * es, 2 * Hd, dt, false));
+  }
+  REGAT_TRY(k_butd_prep(dt, e->atv(e->uqe), 2 * Hd, e->params + e->layers[e->l_lin].v_off, alphap(e, e->l_lin), biasp(e, e->l_va),
+                        biasp(e, e->l_lin), e->atv(e->uw), e->at<float>(e->cb), B, Hd, sd));
+  {  // weff = alpha_va * (uw Wva^T)
+    EpiArgs ep = epi0();
+    ep.alpha = alpha_epi(e, e->l_va);
+    REGAT_TRY(dense(e, sd, false, true, B, D, Hd, e->atv(e->uw), Hd, W(e, e->l_va), ldW(e, e->l_va), e->atv(e->weff), D, dt, ep));
+  }
+  // ---- main stream: the encoder
+  if (dt == REGAT_BF16) {
     REGAT_TRY(k_cast(REGAT_BF16, c.features, e->atv(e->featT), (long long)R * V, st));
     REGAT_TRY(k_cast(REGAT_BF16, c.q_att, e->atv(e->qattT), (long long)B * Q, st));
-    REGAT_TRY(k_cast(REGAT_BF16, c.q_last, e->atv(e->qlastT), (long long)B * Q, st));
-    feat = e->atv(e->featT); qatt = e->atv(e->qattT); qlast = e->atv(e->qlastT);
+    feat = e->atv(e->featT); qatt = e->atv(e->qattT);
   }
   // v0 = relu(v2out(visual))                                            relation_encoder.py:78-79
   const void* v0 = feat;
@@ -330,7 +370,6 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
     REGAT_TRY(dense(e, st, false, false, R, D, D, v0, D, W(e, e->l_self, 0), ldW(e, e->l_self), e->atv(e->s), D, dt, ep));
   }
   // per direction: Q = query(s), K = key(s[:, :M]), V' = s[:, :M] Kc + bc   graph_att_layer.py:47,55,112-117
-  const size_t es = dtype_size(dt);
   if (dt == REGAT_BF16 && e->use_tc) {
     // one wide GEMM per input: [Q_0|Q_1] = s [W_q0|W_q1] + b,  [K_0|K_1|V'_0|V'_1] = s[:, :M] [W_k0|W_k1|Kc_0|Kc_1] + b
     EpiArgs ep = epi0();
@@ -361,22 +400,7 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
                                 training ? e->at<float>(e->P) : nullptr, training ? e->at<float>(e->GB) : nullptr,
                                 training ? e->at<uint64_t>(e->gate) : nullptr, st));
   }
-  // BUTD: u = q2attention(q), qe = question_embed(q)                     fusion.py:37,48
-  if (dt == REGAT_BF16 && e->use_tc) {
-    EpiArgs ep = epi0();
-    ep.bias = e->at<float>(e->gbias) + e->buqe_off;
-    REGAT_TRY(dense(e, st, false, false, B, 2 * Hd, Q, qlast, Q, lowp_at(e, e->guqe_off), 2 * Hd, e->atv(e->uqe), 2 * Hd, dt, ep));
-  } else {
-    REGAT_TRY(fc_fwd(e, st, e->l_qa, 0, B, Q, qlast, Q, e->atv(e->uqe), 2 * Hd, dt, false));
-    REGAT_TRY(fc_fwd(e, st, e->l_qe, 0, B, Q, qlast, Q, e->at<unsigned char>(e->uqe) + (size_t)Hd * es, 2 * Hd, dt, false));
-  }
-  REGAT_TRY(k_butd_prep(dt, e->atv(e->uqe), 2 * Hd, e->params + e->layers[e->l_lin].v_off, alphap(e, e->l_lin), biasp(e, e->l_va),
-                        biasp(e, e->l_lin), e->atv(e->uw), e->at<float>(e->cb), B, Hd, st));
-  {  // weff = alpha_va * (uw Wva^T)
-    EpiArgs ep = epi0();
-    ep.alpha = alpha_epi(e, e->l_va);
-    REGAT_TRY(dense(e, st, false, true, B, D, Hd, e->atv(e->uw), Hd, W(e, e->l_va), ldW(e, e->l_va), e->atv(e->weff), D, dt, ep));
-  }
+  REGAT_TRY(fork_to(sd, st, e->ev[1]));   // join: weff / cb / uqe are ready
   REGAT_TRY(regat_butd_pool_fwd(dt, B, N, D, e->atv(e->v1), e->atv(e->weff), e->at<float>(e->cb), e->at<float>(e->att),
                                 e->atv(e->pooled), st));
   if (att_out) REGAT_CUDA(cudaMemcpyAsync(att_out, e->atv(e->att), (size_t)B * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -436,55 +460,60 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   }
   // loss + dlogits                                                     train.py:107-108
   REGAT_TRY(k_bce(B, A, e->at<float>(e->logits), e->a_pad, target, grad_scale, scal + 2, scal + 3, e->atv(e->dlogits), e->a_pad, dt, st));
-  // classifier
+  // The input-gradient chain (dhid -> djoint -> dpv -> dpooled -> dv1) stays on the main stream; every weight / bias gradient of
+  // the classifier and of BUTD is off the critical path and goes to the side stream as soon as its operands exist.
+  cudaStream_t sd = e->side;
+  unsigned char* dqe = e->at<unsigned char>(e->duqe) + (size_t)Hd * es;
+  REGAT_TRY(fork_to(st, sd, e->ev[2]));                    // dlogits ready
   if (dt == REGAT_BF16 && e->use_tc && (A % 4) != 0) {
     // the [2Hd, A] gradient has unaligned rows (A = 3129): compute it with a padded pitch, then compact into the flat buffer
-    REGAT_TRY(dense(e, st, true, false, 2 * Hd, A, B, e->atv(e->hid), 2 * Hd, e->atv(e->dlogits), e->a_pad, e->atv(e->dwc3), e->a_pad,
+    REGAT_TRY(dense(e, sd, true, false, 2 * Hd, A, B, e->atv(e->hid), 2 * Hd, e->atv(e->dlogits), e->a_pad, e->atv(e->dwc3), e->a_pad,
                     REGAT_F32, epi0()));
     REGAT_CUDA(cudaMemcpy2DAsync(gradW(e, e->l_c3), (size_t)A * sizeof(float), e->atv(e->dwc3), (size_t)e->a_pad * sizeof(float),
-                                 (size_t)A * sizeof(float), 2 * Hd, cudaMemcpyDeviceToDevice, st));
-    REGAT_TRY(k_colsum(dt, e->atv(e->dlogits), e->a_pad, B, A, gradB(e, e->l_c3), st));
+                                 (size_t)A * sizeof(float), 2 * Hd, cudaMemcpyDeviceToDevice, sd));
+    REGAT_TRY(k_colsum(dt, e->atv(e->dlogits), e->a_pad, B, A, gradB(e, e->l_c3), sd));
   } else {
-    REGAT_TRY(fc_wgrad(e, st, e->l_c3, 0, B, 2 * Hd, e->atv(e->hid), 2 * Hd, e->atv(e->dlogits), e->a_pad, true));
+    REGAT_TRY(fc_wgrad(e, sd, e->l_c3, 0, B, 2 * Hd, e->atv(e->hid), 2 * Hd, e->atv(e->dlogits), e->a_pad, true));
   }
   REGAT_TRY(fc_dgrad(e, st, e->l_c3, 0, B, 2 * Hd, e->atv(e->dlogits), e->a_pad, e->atv(e->dhid), 2 * Hd, dt, false, e->atv(e->hid), 2 * Hd));
-  REGAT_TRY(fc_wgrad(e, st, e->l_c0, 0, B, Hd, e->atv(e->joint), Hd, e->atv(e->dhid), 2 * Hd, true));
+  REGAT_TRY(fork_to(st, sd, e->ev[3]));                    // dhid ready
+  REGAT_TRY(fc_wgrad(e, sd, e->l_c0, 0, B, Hd, e->atv(e->joint), Hd, e->atv(e->dhid), 2 * Hd, true));
   REGAT_TRY(fc_dgrad(e, st, e->l_c0, 0, B, Hd, e->atv(e->dhid), 2 * Hd, e->atv(e->djoint), Hd, dt, false));
   // joint = pv * qe
-  unsigned char* dqe = e->at<unsigned char>(e->duqe) + (size_t)Hd * es;
   REGAT_TRY(k_mul_bwd(dt, e->atv(e->djoint), Hd, e->atv(e->pv), Hd, e->at<unsigned char>(e->uqe) + (size_t)Hd * es, 2 * Hd,
                       e->atv(e->dpv), Hd, dqe, 2 * Hd, B, Hd, st));
-  REGAT_TRY(fc_wgrad(e, st, e->l_ve, 0, B, D, e->atv(e->pooled), D, e->atv(e->dpv), Hd, true));
+  REGAT_TRY(fork_to(st, sd, e->ev[4]));                    // dpv, dqe ready
+  REGAT_TRY(fc_wgrad(e, sd, e->l_ve, 0, B, D, e->atv(e->pooled), D, e->atv(e->dpv), Hd, true));
   REGAT_TRY(fc_dgrad(e, st, e->l_ve, 0, B, D, e->atv(e->dpv), Hd, e->atv(e->dpooled), D, dt, false));
   // attention pooling
   REGAT_TRY(regat_butd_pool_bwd(dt, B, N, D, e->atv(e->v1), e->atv(e->weff), e->at<float>(e->att), e->atv(e->dpooled),
                                 e->atv(e->dv1), e->atv(e->dweff), e->at<float>(e->dcb), st));
+  REGAT_TRY(fork_to(st, sd, e->ev[5]));                    // dweff, dcb ready: the rest of the question branch is side work
   {  // weff = alpha_va (uw Wva^T):  dWva_eff = dweff^T uw ;  duw = alpha_va (dweff Wva)
     EpiArgs ep = epi0();
-    REGAT_TRY(dense(e, st, true, false, D, Hd, B, e->atv(e->dweff), D, e->atv(e->uw), Hd, gradW(e, e->l_va), Hd, REGAT_F32, ep));
+    REGAT_TRY(dense(e, sd, true, false, D, Hd, B, e->atv(e->dweff), D, e->atv(e->uw), Hd, gradW(e, e->l_va), Hd, REGAT_F32, ep));
     ep.alpha = alpha_epi(e, e->l_va);
-    REGAT_TRY(dense(e, st, false, false, B, Hd, D, e->atv(e->dweff), D, W(e, e->l_va), ldW(e, e->l_va), e->atv(e->duw), Hd, dt, ep));
+    REGAT_TRY(dense(e, sd, false, false, B, Hd, D, e->atv(e->dweff), D, W(e, e->l_va), ldW(e, e->l_va), e->atv(e->duw), Hd, dt, ep));
   }
   REGAT_TRY(k_butd_prep_bwd(dt, e->atv(e->duw), e->at<float>(e->dcb), e->atv(e->uqe), 2 * Hd, e->atv(e->uw),
                             e->params + e->layers[e->l_lin].v_off, alphap(e, e->l_lin), biasp(e, e->l_va), e->atv(e->duqe), 2 * Hd,
-                            gradW(e, e->l_lin), gradB(e, e->l_va), gradB(e, e->l_lin), B, Hd, st));
+                            gradW(e, e->l_lin), gradB(e, e->l_va), gradB(e, e->l_lin), B, Hd, sd));
   if (dt == REGAT_BF16 && e->use_tc) {
     // [dW_qa | dW_qe] = q_last^T [du | dqe]  (one GEMM scattered into the two kernels' gradient slots);  dq_last = [du|dqe] [W_qa|W_qe]^T
     const long long offs[2] = {0, e->layers[e->l_qe].v_off - e->layers[e->l_qa].v_off};
-    REGAT_TRY(gemm_tc(1, 0, Q, 2 * Hd, B, qlast, Q, e->atv(e->duqe), 2 * Hd, gradW(e, e->l_qa), Hd, REGAT_F32, epi0(), 1, st, Hd, offs));
-    REGAT_TRY(k_colsum(dt, e->atv(e->duqe), 2 * Hd, B, Hd, gradB(e, e->l_qa), st));
-    REGAT_TRY(k_colsum(dt, dqe, 2 * Hd, B, Hd, gradB(e, e->l_qe), st));
+    REGAT_TRY(gemm_tc(1, 0, Q, 2 * Hd, B, qlast, Q, e->atv(e->duqe), 2 * Hd, gradW(e, e->l_qa), Hd, REGAT_F32, epi0(), 1, sd, Hd, offs));
+    REGAT_TRY(k_colsum(dt, e->atv(e->duqe), 2 * Hd, B, Hd, gradB(e, e->l_qa), sd));
+    REGAT_TRY(k_colsum(dt, dqe, 2 * Hd, B, Hd, gradB(e, e->l_qe), sd));
     if (dq_last)
-      REGAT_TRY(dense(e, st, false, true, B, Q, 2 * Hd, e->atv(e->duqe), 2 * Hd, lowp_at(e, e->guqe_off), 2 * Hd, dq_last, Q, REGAT_F32, epi0()));
+      REGAT_TRY(dense(e, sd, false, true, B, Q, 2 * Hd, e->atv(e->duqe), 2 * Hd, lowp_at(e, e->guqe_off), 2 * Hd, dq_last, Q, REGAT_F32, epi0()));
   } else {
-    REGAT_TRY(fc_wgrad(e, st, e->l_qa, 0, B, Q, qlast, Q, e->atv(e->duqe), 2 * Hd, true));
-    REGAT_TRY(fc_wgrad(e, st, e->l_qe, 0, B, Q, qlast, Q, dqe, 2 * Hd, true));
+    REGAT_TRY(fc_wgrad(e, sd, e->l_qa, 0, B, Q, qlast, Q, e->atv(e->duqe), 2 * Hd, true));
+    REGAT_TRY(fc_wgrad(e, sd, e->l_qe, 0, B, Q, qlast, Q, dqe, 2 * Hd, true));
     if (dq_last) {
-      REGAT_TRY(fc_dgrad(e, st, e->l_qa, 0, B, Q, e->atv(e->duqe), 2 * Hd, dq_last, Q, REGAT_F32, false));
-      REGAT_TRY(fc_dgrad(e, st, e->l_qe, 0, B, Q, dqe, 2 * Hd, dq_last, Q, REGAT_F32, true));
+      REGAT_TRY(fc_dgrad(e, sd, e->l_qa, 0, B, Q, e->atv(e->duqe), 2 * Hd, dq_last, Q, REGAT_F32, false));
+      REGAT_TRY(fc_dgrad(e, sd, e->l_qe, 0, B, Q, dqe, 2 * Hd, dq_last, Q, REGAT_F32, true));
     }
   }
-  grads_ready(e, e->l_va, e->l_c3);       // BUTD + classifier gradients are final: the tail of the flat buffer
   // attention backward: dQ, dK, dV', dout (-> ds), dL (in place of P); then the geometry reduction
   REGAT_TRY(regat_attn_bwd(dt, B, N, cf.nongt_dim, D, H, dirs, e->atv(e->Qb), e->atv(e->KVb), e->atv(e->dv1),
                            e->at<uint64_t>(e->gate), e->at<float>(e->P), e->atv(e->dQb), e->atv(e->dKVb), e->atv(e->ds), st));
@@ -497,6 +526,8 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
     const Layer& LL = e->layers[e->l_label];
     REGAT_TRY(k_label_grad(scal + 1, e->grads, LL.v_off, LL.b_off, st));
   }
+  REGAT_TRY(fork_to(sd, st, e->ev[0]));   // join the side stream: BUTD + classifier gradients (the tail of the flat buffer) are final
+  grads_ready(e, e->l_va, e->l_c3);
   if (dt == REGAT_BF16 && e->use_tc) {
     // weight gradients of side-by-side layers in one GEMM each (column blocks scattered to their own gradient slots),
     // input gradients with the direction / kind axis folded into K
@@ -596,7 +627,14 @@ extern "C" int regat_engine_create(const regat_config* cfg, int dtype, int max_b
   *out = e;
   return REGAT_OK;
 }
-extern "C" int regat_engine_destroy(regat_engine* e) { delete e; return REGAT_OK; }
+extern "C" int regat_engine_destroy(regat_engine* e) {
+  if (e) {
+    for (int i = 0; i < 6; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    if (e->side) cudaStreamDestroy(e->side);
+    delete e;
+  }
+  return REGAT_OK;
+}
 
 extern "C" int regat_engine_sizes(const regat_engine* e, int64_t* param_elems, int64_t* workspace_bytes) {
   REGAT_REQUIRE(e, REGAT_ERR_ARG, "engine is null");

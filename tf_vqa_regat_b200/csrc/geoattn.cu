@@ -314,24 +314,67 @@ __global__ void __launch_bounds__(256, 2) geoattn_fwd_kernel(const FwdParams p) 
     for (int d = 0; d < p.dirs; ++d) {
       const int dh = d * H + h;
       // S = Q K^T
-      float qa[16], qb[16];
-      load_row16<T>(Q + ((size_t)b * N + r0c) * ldq + d * D + h * HD, t, qa);
-      load_row16<T>(Q + ((size_t)b * N + r1c) * ldq + d * D + h * HD, t, qb);
       float sacc[NTS][4];
 #pragma unroll
       for (int nt = 0; nt < NTS; ++nt) { sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f; }
+      constexpr bool PACKED = sizeof(T) == 2 && !S3;
+      // bf16 mode: every operand of this (dir, head) is requested up front as packed 128-bit registers -- one memory round
+      // trip instead of one per key tile -- and unpacked (a shift / a mask per value) right at the mma.
+      uint4 qw[2][2], kw[NTS][2], vw[NTS][2];
+      if constexpr (PACKED) {
+        const bf16* qp0 = reinterpret_cast<const bf16*>(Q) + ((size_t)b * N + r0c) * ldq + d * D + h * HD + 8 * t;
+        const bf16* qp1 = reinterpret_cast<const bf16*>(Q) + ((size_t)b * N + r1c) * ldq + d * D + h * HD + 8 * t;
 #pragma unroll
-      for (int nt = 0; nt < NTS; ++nt) {
-        if (nt * 8 < M) {
-          float kr[16];
-          load_row16<T>(KV + ((size_t)b * M + min(nt * 8 + g, M - 1)) * ldkv + d * D + h * HD, t, kr);
+        for (int kk = 0; kk < 2; ++kk) {
+          qw[0][kk] = __ldg(reinterpret_cast<const uint4*>(qp0 + 32 * kk));
+          qw[1][kk] = __ldg(reinterpret_cast<const uint4*>(qp1 + 32 * kk));
+        }
 #pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            Opnd<S3, 4> a; Opnd<S3, 2> bb;
-            a.template put<EX>(0, qa[2 * ks]); a.template put<EX>(1, qb[2 * ks]);
-            a.template put<EX>(2, qa[2 * ks + 1]); a.template put<EX>(3, qb[2 * ks + 1]);
-            bb.template put<EX>(0, kr[2 * ks]); bb.template put<EX>(1, kr[2 * ks + 1]);
-            mma_acc<S3>(sacc[nt], a, bb);
+        for (int nt = 0; nt < NTS; ++nt) {
+          if (nt * 8 < M) {
+            const bf16* kp = reinterpret_cast<const bf16*>(KV) + ((size_t)b * M + min(nt * 8 + g, M - 1)) * ldkv + d * D + h * HD + 8 * t;
+            kw[nt][0] = __ldg(reinterpret_cast<const uint4*>(kp));
+            kw[nt][1] = __ldg(reinterpret_cast<const uint4*>(kp + 32));
+            const int j0 = min(nt * 8 + 2 * t, M - 1), j1 = min(nt * 8 + 2 * t + 1, M - 1);
+            const bf16* vp = reinterpret_cast<const bf16*>(KV) + (size_t)b * M * ldkv + (p.dirs + d) * D + h * HD + 8 * g;
+            vw[nt][0] = __ldg(reinterpret_cast<const uint4*>(vp + (size_t)j0 * ldkv));
+            vw[nt][1] = __ldg(reinterpret_cast<const uint4*>(vp + (size_t)j1 * ldkv));
+          }
+        }
+#pragma unroll
+        for (int nt = 0; nt < NTS; ++nt) {
+          if (nt * 8 < M) {
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+              const uint32_t q0[4] = {qw[0][kk].x, qw[0][kk].y, qw[0][kk].z, qw[0][kk].w};
+              const uint32_t q1[4] = {qw[1][kk].x, qw[1][kk].y, qw[1][kk].z, qw[1][kk].w};
+              const uint32_t k4[4] = {kw[nt][kk].x, kw[nt][kk].y, kw[nt][kk].z, kw[nt][kk].w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint32_t a[4] = {q0[i] << 16, q1[i] << 16, q0[i] & 0xffff0000u, q1[i] & 0xffff0000u};
+                const uint32_t bb[2] = {k4[i] << 16, k4[i] & 0xffff0000u};
+                mma_tf32(sacc[nt], a, bb);
+              }
+            }
+          }
+        }
+      } else {
+        float qa[16], qb[16];
+        load_row16<T>(Q + ((size_t)b * N + r0c) * ldq + d * D + h * HD, t, qa);
+        load_row16<T>(Q + ((size_t)b * N + r1c) * ldq + d * D + h * HD, t, qb);
+#pragma unroll
+        for (int nt = 0; nt < NTS; ++nt) {
+          if (nt * 8 < M) {
+            float kr[16];
+            load_row16<T>(KV + ((size_t)b * M + min(nt * 8 + g, M - 1)) * ldkv + d * D + h * HD, t, kr);
+#pragma unroll
+            for (int ks = 0; ks < 8; ++ks) {
+              Opnd<S3, 4> a; Opnd<S3, 2> bb;
+              a.template put<EX>(0, qa[2 * ks]); a.template put<EX>(1, qb[2 * ks]);
+              a.template put<EX>(2, qa[2 * ks + 1]); a.template put<EX>(3, qb[2 * ks + 1]);
+              bb.template put<EX>(0, kr[2 * ks]); bb.template put<EX>(1, kr[2 * ks + 1]);
+              mma_acc<S3>(sacc[nt], a, bb);
+            }
           }
         }
       }
@@ -380,17 +423,30 @@ __global__ void __launch_bounds__(256, 2) geoattn_fwd_kernel(const FwdParams p) 
 #pragma unroll
       for (int nt = 0; nt < NTS; ++nt) {
         if (nt * 8 < M) {
-          float va[8], vb[8];
-          const int j0 = min(nt * 8 + 2 * t, M - 1), j1 = min(nt * 8 + 2 * t + 1, M - 1);
-          load8c<T>(KV + ((size_t)b * M + j0) * ldkv + (p.dirs + d) * D + h * HD + 8 * g, va);
-          load8c<T>(KV + ((size_t)b * M + j1) * ldkv + (p.dirs + d) * D + h * HD + 8 * g, vb);
-          Opnd<S3, 4> a;
-          a.set(0, sacc[nt][0]); a.set(1, sacc[nt][2]); a.set(2, sacc[nt][1]); a.set(3, sacc[nt][3]);
+          if constexpr (PACKED) {
+            const uint32_t a[4] = {__float_as_uint(sacc[nt][0]), __float_as_uint(sacc[nt][2]), __float_as_uint(sacc[nt][1]),
+                                   __float_as_uint(sacc[nt][3])};
+            const uint32_t v0w[4] = {vw[nt][0].x, vw[nt][0].y, vw[nt][0].z, vw[nt][0].w};
+            const uint32_t v1w[4] = {vw[nt][1].x, vw[nt][1].y, vw[nt][1].z, vw[nt][1].w};
 #pragma unroll
-          for (int ot = 0; ot < 8; ++ot) {
-            Opnd<S3, 2> bb;
-            bb.template put<EX>(0, va[ot]); bb.template put<EX>(1, vb[ot]);
-            mma_acc<S3>(oacc[ot], a, bb);
+            for (int ot = 0; ot < 8; ++ot) {
+              const uint32_t bb[2] = {(ot & 1) ? (v0w[ot >> 1] & 0xffff0000u) : (v0w[ot >> 1] << 16),
+                                      (ot & 1) ? (v1w[ot >> 1] & 0xffff0000u) : (v1w[ot >> 1] << 16)};
+              mma_tf32(oacc[ot], a, bb);
+            }
+          } else {
+            float va[8], vb[8];
+            const int j0 = min(nt * 8 + 2 * t, M - 1), j1 = min(nt * 8 + 2 * t + 1, M - 1);
+            load8c<T>(KV + ((size_t)b * M + j0) * ldkv + (p.dirs + d) * D + h * HD + 8 * g, va);
+            load8c<T>(KV + ((size_t)b * M + j1) * ldkv + (p.dirs + d) * D + h * HD + 8 * g, vb);
+            Opnd<S3, 4> a;
+            a.set(0, sacc[nt][0]); a.set(1, sacc[nt][2]); a.set(2, sacc[nt][1]); a.set(3, sacc[nt][3]);
+#pragma unroll
+            for (int ot = 0; ot < 8; ++ot) {
+              Opnd<S3, 2> bb;
+              bb.template put<EX>(0, va[ot]); bb.template put<EX>(1, vb[ot]);
+              mma_acc<S3>(oacc[ot], a, bb);
+            }
           }
         }
       }
@@ -468,21 +524,34 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const BwdParams p) {
   const T* dV1 = static_cast<const T*>(p.dv1);
 
   // ---- fill Qs, dOs (gated by the saved relu mask) with coalesced loads; direction 0 also emits dout
-  for (int x = tid; x < NP * (HD / 8); x += 128) {
-    const int i = x / (HD / 8), e0 = (x % (HD / 8)) * 8;
-    float qv[8] = {0, 0, 0, 0, 0, 0, 0, 0}, dv[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (i < N) {
-      load8c<T>(Q + ((size_t)b * N + i) * ldq + d * D + h * HD + e0, qv);
-      load8c<T>(dV1 + ((size_t)b * N + i) * D + h * HD + e0, dv);
-      const unsigned long long bits = __ldg(p.gate + ((size_t)b * N + i) * H + h);
+  for (int x0 = tid; x0 < NP * (HD / 8); x0 += 128 * 4) {
+    float qv[4][8], dv[4][8];
+    unsigned long long bits[4];
+    // all global loads of four items first (one latency), then the gating / stores
 #pragma unroll
-      for (int u = 0; u < 8; ++u) dv[u] = ((bits >> (e0 + u)) & 1ull) ? dv[u] : 0.f;
-      if (d == 0) store_n<T>(static_cast<T*>(p.dout) + ((size_t)b * N + i) * D + h * HD + e0, dv, 8);
+    for (int u = 0; u < 4; ++u) {
+      const int x = x0 + u * 128, i = x / (HD / 8), e0 = (x % (HD / 8)) * 8;
+      bits[u] = 0ull;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { qv[u][k] = 0.f; dv[u][k] = 0.f; }
+      if (x < NP * (HD / 8) && i < N) {
+        load8c<T>(Q + ((size_t)b * N + i) * ldq + d * D + h * HD + e0, qv[u]);
+        load8c<T>(dV1 + ((size_t)b * N + i) * D + h * HD + e0, dv[u]);
+        bits[u] = __ldg(p.gate + ((size_t)b * N + i) * H + h);
+      }
     }
-    *reinterpret_cast<float4*>(Qs + i * LDX + e0) = make_float4(qv[0], qv[1], qv[2], qv[3]);
-    *reinterpret_cast<float4*>(Qs + i * LDX + e0 + 4) = make_float4(qv[4], qv[5], qv[6], qv[7]);
-    *reinterpret_cast<float4*>(dOs + i * LDX + e0) = make_float4(dv[0], dv[1], dv[2], dv[3]);
-    *reinterpret_cast<float4*>(dOs + i * LDX + e0 + 4) = make_float4(dv[4], dv[5], dv[6], dv[7]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int x = x0 + u * 128, i = x / (HD / 8), e0 = (x % (HD / 8)) * 8;
+      if (x >= NP * (HD / 8)) continue;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) dv[u][k] = ((bits[u] >> (e0 + k)) & 1ull) ? dv[u][k] : 0.f;
+      if (d == 0 && i < N) store_n<T>(static_cast<T*>(p.dout) + ((size_t)b * N + i) * D + h * HD + e0, dv[u], 8);
+      *reinterpret_cast<float4*>(Qs + i * LDX + e0) = make_float4(qv[u][0], qv[u][1], qv[u][2], qv[u][3]);
+      *reinterpret_cast<float4*>(Qs + i * LDX + e0 + 4) = make_float4(qv[u][4], qv[u][5], qv[u][6], qv[u][7]);
+      *reinterpret_cast<float4*>(dOs + i * LDX + e0) = make_float4(dv[u][0], dv[u][1], dv[u][2], dv[u][3]);
+      *reinterpret_cast<float4*>(dOs + i * LDX + e0 + 4) = make_float4(dv[u][4], dv[u][5], dv[u][6], dv[u][7]);
+    }
   }
   // zero the key padding of the dL / P tiles (columns >= M are never written below)
   for (int x = tid; x < NP * LDT; x += 128) { Ls[x] = 0.f; Ps[x] = 0.f; }
@@ -492,6 +561,66 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const BwdParams p) {
   float* P_g = p.p_dl + ((size_t)b * p.dirs * H + dh) * N * M;
   for (int mt = warp; mt * 16 < N; mt += 4) {
     const int r0 = mt * 16 + g, r1 = r0 + 8;
+    constexpr bool PACKED = sizeof(T) == 2 && !S3;
+    float sacc[NTS][4];
+#pragma unroll
+    for (int nt = 0; nt < NTS; ++nt) { sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f; }
+    uint4 kw[NTS][2];        // K rows (8nt+2t, 8nt+2t+1) at head-dim elements [8g, 8g+8): B operand of dQ = dL K
+    if constexpr (PACKED) {
+      // every global operand of this row tile is requested up front, packed (one memory round trip)
+      const int r0c = min(r0, N - 1), r1c = min(r1, N - 1);
+      uint4 dw[2][2], vw[NTS][2];
+      const bf16* dp0 = reinterpret_cast<const bf16*>(dV1) + ((size_t)b * N + r0c) * D + h * HD + 8 * t;
+      const bf16* dp1 = reinterpret_cast<const bf16*>(dV1) + ((size_t)b * N + r1c) * D + h * HD + 8 * t;
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        dw[0][kk] = __ldg(reinterpret_cast<const uint4*>(dp0 + 32 * kk));
+        dw[1][kk] = __ldg(reinterpret_cast<const uint4*>(dp1 + 32 * kk));
+      }
+      const unsigned long long g0 = r0 < N ? __ldg(p.gate + ((size_t)b * N + r0c) * H + h) : 0ull;
+      const unsigned long long g1 = r1 < N ? __ldg(p.gate + ((size_t)b * N + r1c) * H + h) : 0ull;
+#pragma unroll
+      for (int nt = 0; nt < NTS; ++nt) {
+        if (nt * 8 < M) {
+          const bf16* vp = reinterpret_cast<const bf16*>(KV) + ((size_t)b * M + min(nt * 8 + g, M - 1)) * ldkv + (p.dirs + d) * D + h * HD + 8 * t;
+          vw[nt][0] = __ldg(reinterpret_cast<const uint4*>(vp));
+          vw[nt][1] = __ldg(reinterpret_cast<const uint4*>(vp + 32));
+          const int j0 = min(nt * 8 + 2 * t, M - 1), j1 = min(nt * 8 + 2 * t + 1, M - 1);
+          const bf16* kp = reinterpret_cast<const bf16*>(KV) + (size_t)b * M * ldkv + d * D + h * HD + 8 * g;
+          kw[nt][0] = __ldg(reinterpret_cast<const uint4*>(kp + (size_t)j0 * ldkv));
+          kw[nt][1] = __ldg(reinterpret_cast<const uint4*>(kp + (size_t)j1 * ldkv));
+        }
+      }
+      // relu gate applied to the packed words: element e <-> bit e of the (row, head) gate word
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        uint32_t* w0 = reinterpret_cast<uint32_t*>(&dw[0][kk]);
+        uint32_t* w1 = reinterpret_cast<uint32_t*>(&dw[1][kk]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int e = 32 * kk + 8 * t + 2 * i;
+          w0[i] &= (((g0 >> e) & 1ull) ? 0x0000ffffu : 0u) | (((g0 >> (e + 1)) & 1ull) ? 0xffff0000u : 0u);
+          w1[i] &= (((g1 >> e) & 1ull) ? 0x0000ffffu : 0u) | (((g1 >> (e + 1)) & 1ull) ? 0xffff0000u : 0u);
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < NTS; ++nt) {
+        if (nt * 8 < M) {
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk) {
+            const uint32_t a0[4] = {dw[0][kk].x, dw[0][kk].y, dw[0][kk].z, dw[0][kk].w};
+            const uint32_t a1[4] = {dw[1][kk].x, dw[1][kk].y, dw[1][kk].z, dw[1][kk].w};
+            const uint32_t v4[4] = {vw[nt][kk].x, vw[nt][kk].y, vw[nt][kk].z, vw[nt][kk].w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t a[4] = {a0[i] << 16, a1[i] << 16, a0[i] & 0xffff0000u, a1[i] & 0xffff0000u};
+              const uint32_t bb[2] = {v4[i] << 16, v4[i] & 0xffff0000u};
+              mma_tf32(sacc[nt], a, bb);
+            }
+          }
+        }
+      }
+    } else {
     // gated dO rows as A fragments, same per-lane element map as the V' rows below
     float da[16], db[16];
     {
@@ -507,10 +636,8 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const BwdParams p) {
         db[u] = ((g1 >> e) & 1ull) ? db[u] : 0.f;
       }
     }
-    float sacc[NTS][4];
 #pragma unroll
     for (int nt = 0; nt < NTS; ++nt) {
-      sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f;
       if (nt * 8 < M) {
         float vr[16];
         load_row16<T>(KV + ((size_t)b * M + min(nt * 8 + g, M - 1)) * ldkv + (p.dirs + d) * D + h * HD, t, vr);
@@ -523,6 +650,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const BwdParams p) {
           mma_acc<S3>(sacc[nt], a, bb);
         }
       }
+    }
     }
     float pr[NTS][4];
     float dl0 = 0.f, dl1 = 0.f;
@@ -567,17 +695,29 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const BwdParams p) {
         *reinterpret_cast<float2*>(Ps + r1 * LDT + c0) = make_float2(pr[nt][2], pr[nt][3]);
       }
       if (nt * 8 < M) {
-        float ka[8], kb[8];
-        const int j0 = min(nt * 8 + 2 * t, M - 1), j1 = min(nt * 8 + 2 * t + 1, M - 1);
-        load8c<T>(KV + ((size_t)b * M + j0) * ldkv + d * D + h * HD + 8 * g, ka);
-        load8c<T>(KV + ((size_t)b * M + j1) * ldkv + d * D + h * HD + 8 * g, kb);
-        Opnd<S3, 4> a;
-        a.set(0, dl[0]); a.set(1, dl[2]); a.set(2, dl[1]); a.set(3, dl[3]);
+        if constexpr (PACKED) {
+          const uint32_t a[4] = {__float_as_uint(dl[0]), __float_as_uint(dl[2]), __float_as_uint(dl[1]), __float_as_uint(dl[3])};
+          const uint32_t k0w[4] = {kw[nt][0].x, kw[nt][0].y, kw[nt][0].z, kw[nt][0].w};
+          const uint32_t k1w[4] = {kw[nt][1].x, kw[nt][1].y, kw[nt][1].z, kw[nt][1].w};
 #pragma unroll
-        for (int ot = 0; ot < 8; ++ot) {
-          Opnd<S3, 2> bb;
-          bb.template put<EX>(0, ka[ot]); bb.template put<EX>(1, kb[ot]);
-          mma_acc<S3>(dqacc[ot], a, bb);
+          for (int ot = 0; ot < 8; ++ot) {
+            const uint32_t bb[2] = {(ot & 1) ? (k0w[ot >> 1] & 0xffff0000u) : (k0w[ot >> 1] << 16),
+                                    (ot & 1) ? (k1w[ot >> 1] & 0xffff0000u) : (k1w[ot >> 1] << 16)};
+            mma_tf32(dqacc[ot], a, bb);
+          }
+        } else {
+          float ka[8], kb[8];
+          const int j0 = min(nt * 8 + 2 * t, M - 1), j1 = min(nt * 8 + 2 * t + 1, M - 1);
+          load8c<T>(KV + ((size_t)b * M + j0) * ldkv + d * D + h * HD + 8 * g, ka);
+          load8c<T>(KV + ((size_t)b * M + j1) * ldkv + d * D + h * HD + 8 * g, kb);
+          Opnd<S3, 4> a;
+          a.set(0, dl[0]); a.set(1, dl[2]); a.set(2, dl[1]); a.set(3, dl[3]);
+#pragma unroll
+          for (int ot = 0; ot < 8; ++ot) {
+            Opnd<S3, 2> bb;
+            bb.template put<EX>(0, ka[ot]); bb.template put<EX>(1, kb[ot]);
+            mma_acc<S3>(dqacc[ot], a, bb);
+          }
         }
       }
     }
