@@ -122,6 +122,7 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=16, help="graphs per CPU-baseline step")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--comm-dtype", default="auto", choices=["auto", "fp32", "bf16"], help="gradient all-reduce precision (auto = engine dtype)")
     ap.add_argument("--no-overlap", action="store_true", help="data parallel: one all-reduce after the backward pass instead of overlapped buckets")
     ap.add_argument("--lr", type=float, default=9e-4)
     args = ap.parse_args()
@@ -163,7 +164,7 @@ def main():
 
     from tf_vqa_regat_b200.dp import DataParallelTrainer
     # data parallel: bucketed gradient all-reduce on a side stream, started from inside the backward pass (dp.py)
-    trainer = DataParallelTrainer(eng, overlap=not args.no_overlap) if world > 1 else None
+    trainer = DataParallelTrainer(eng, overlap=not args.no_overlap, comm_dtype=args.comm_dtype) if world > 1 else None
     if trainer:
         trainer.broadcast_params(0)
 
@@ -335,7 +336,7 @@ def main():
                 "config": {"workload": f"implicit relation + BUTD train step, batch {B}/GPU, K={N}, 16 heads, nongt_dim 20, "
                                        f"V=2048 D=1024 Q=768 A=3129 (BASELINE.json configs[1])",
                            "parallelism": f"dp{world}", "global_batch": B * world, "cuda_graph": bool(graphs),
-                           "allreduce": (None if world == 1 else ("3 buckets overlapped with backward" if trainer.overlap else "single, after backward")),
+                           "allreduce": (None if world == 1 else (("3 buckets overlapped with backward" if trainer.overlap else "single, after backward") + ", " + trainer.comm_dtype)),
                            "l2": "per-step working set ~0.8 GB (activations + 4x76 MB parameter/optimizer state) >> 126 MB L2; "
                                  "two alternating input batches; no explicit flush"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,

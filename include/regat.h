@@ -193,6 +193,10 @@ REGAT_API int regat_butd_pool_bwd(int dtype, int B, int N, int D, const void* v1
                         const float* att, const void* dpooled, void* dv1, void* dweff, float* dcb,
                         regat_stream_t stream);
 
+/* Elementwise fp32 <-> bf16 conversion of n (multiple of 8) elements -- used for the reduced-precision gradient exchange of the
+ * data-parallel path and by hosts that hold fp32 tensors. */
+REGAT_API int regat_cast(int from_dtype, int to_dtype, const void* in, void* out, int64_t n, regat_stream_t stream);
+
 /* relation_encoder.py:13-37 concat_visual_question(q, v, mask=True):
  *   mask[b,n] = (sum_d v[b,n,d] != 0) (optional output, fp32);  out[b,n,:] = [ v[b,n,:] || mask * q[b,:] ]   [B,N,D+Q] */
 REGAT_API int regat_concat_visual_question(int dtype, int B, int N, int D, int Q, const void* v, const void* q,

@@ -1,0 +1,61 @@
+"""Data parallel on real GPUs (needs >= 2 devices: run with `gpurun --gpus 2`): R ranks on shards of the batch with the overlapped
+bucketed NCCL all-reduce reach the same parameters as one GPU on the whole batch."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tf_vqa_regat_b200 import synthetic as syn
+from tf_vqa_regat_b200.config import HotPathConfig
+
+pytestmark = pytest.mark.gpu
+SMALL = dict(v_dim=192, q_dim=96, rel_dim=256, num_heads=4, nongt_dim=20, num_answers=301)
+
+
+def _worker(rank, world, port, cfg_kw, B, N, steps, lr, out):
+    import torch.distributed as dist
+    from tf_vqa_regat_b200.dp import DataParallelTrainer, shard_batch
+    from tf_vqa_regat_b200.engine import HotPathEngine
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    cfg = HotPathConfig(**cfg_kw)
+    inp = syn.make_inputs(cfg, B, N, seed=1000, adaptive=True)
+    eng = HotPathEngine(cfg, B // world, N, dtype="fp32", device=f"cuda:{rank}")
+    eng.load_params(syn.make_params(cfg, seed=7 + rank, trained_like=True))     # ranks start DIFFERENT: broadcast must fix it
+    tr = DataParallelTrainer(eng, overlap=True)
+    tr.broadcast_params(0)
+    shard = shard_batch({k: v for k, v in inp.items() if k != "n_obj"}, rank, world)
+    dev = {k: torch.tensor(v).cuda() for k, v in shard.items()}
+    losses = []
+    for _ in range(steps):
+        o = tr.step(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"], dev["target"], lr)
+        losses.append(float(o["loss"]))
+    torch.cuda.synchronize()
+    out[rank] = (eng.params.cpu().numpy(), losses, tr.overlap)
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_gpus_equal_one_gpu():
+    import torch.multiprocessing as mp
+    from tf_vqa_regat_b200.engine import HotPathEngine
+    B, N, steps, lr = 8, 36, 2, 1e-3
+    cfg = HotPathConfig(**SMALL)
+    inp = syn.make_inputs(cfg, B, N, seed=1000, adaptive=True)
+    ref = HotPathEngine(cfg, B, N, dtype="fp32", device="cuda:0")
+    ref.load_params(syn.make_params(cfg, seed=7, trained_like=True))
+    dev = {k: torch.tensor(v).cuda() for k, v in inp.items() if k != "n_obj"}
+    ref_losses = [float(ref.train_step(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"], dev["target"], lr, s + 1)[0])
+                  for s in range(steps)]
+    p_ref = ref.params.cpu().numpy()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(2, 29533, SMALL, B, N, steps, lr, out), nprocs=2, join=True)
+    assert out[0][2] is True                                        # the overlapped bucketed path ran
+    np.testing.assert_array_equal(out[0][0], out[1][0])             # replicas stay bit-identical
+    # rank losses are shard means: their average is the global-batch loss
+    np.testing.assert_allclose(np.mean([out[0][1], out[1][1]], axis=0), ref_losses, rtol=1e-5)
+    # Adamax moves every element by <= lr per step: agreement far inside that (summation order differs across shards)
+    assert np.abs(out[0][0] - p_ref).max() < 0.02 * steps * lr

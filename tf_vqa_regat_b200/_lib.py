@@ -50,6 +50,7 @@ SIGNATURES = {
     "regat_geo_bwd": [i32] * 6 + [vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp],
     "regat_butd_pool_fwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp],
     "regat_butd_pool_bwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp],
+    "regat_cast": [i32, i32, vp, vp, i64, vp],
     "regat_concat_visual_question": [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
     "regat_butd_prep": [i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp],
     "regat_mul": [i32, i32, i32, vp, i32, vp, i32, vp, i32, vp],

@@ -518,8 +518,11 @@ int gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int lda,
   p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.splits = splits;
   const int units = tiles_m * tiles_n * splits;
   // BN=256: 4 stages x 48 KB + 2 x 256 TMEM columns, one CTA per SM.  BN=128: 3 stages x 32 KB + 2 x 128 columns, two per SM.
-  if (bn == 256) return launch_cfg<256, 4, 2>(a_mn, b_mn, ma, mb, p, std::min(units, num_sms()), st);
-  return launch_cfg<128, 3, 2>(a_mn, b_mn, ma, mb, p, std::min(units, 2 * num_sms()), st);
+  // REGAT_SM_RESERVE=n leaves n SMs free of persistent GEMM CTAs so that a concurrent NCCL all-reduce can make progress
+  static const int reserve = [] { const char* s = getenv("REGAT_SM_RESERVE"); return s ? std::max(0, atoi(s)) : 0; }();
+  const int sms = std::max(1, num_sms() - reserve);
+  if (bn == 256) return launch_cfg<256, 4, 2>(a_mn, b_mn, ma, mb, p, std::min(units, sms), st);
+  return launch_cfg<128, 3, 2>(a_mn, b_mn, ma, mb, p, std::min(units, 2 * sms), st);
 }
 
 }  // namespace regat

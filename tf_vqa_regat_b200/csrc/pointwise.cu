@@ -116,11 +116,11 @@ __global__ void wn_alpha_kernel(const float* __restrict__ params, TensorList tl,
 }
 
 // ---------------------------------------------------------------- casts / elementwise
-template <typename TO>
-__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in, TO* __restrict__ out, long long n8) {
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, long long n8) {
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n8; i += (long long)gridDim.x * 256) {
     float v[8];
-    ld8<float>(in + i * 8, v);
+    ld8<TI>(in + i * 8, v);
     st8<TO>(out + i * 8, v);
   }
 }
@@ -600,8 +600,8 @@ int k_wn_alpha(const float* params, const TensorList& tl, const float* sumsq, fl
 }
 int k_cast(int to_dtype, const float* in, void* out, long long n, cudaStream_t st) {
   REGAT_REQUIRE(n % 8 == 0, REGAT_ERR_SHAPE, "cast: element count must be a multiple of 8");
-  if (to_dtype == REGAT_BF16) cast_kernel<bf16><<<grid_for(n / 8), 256, 0, st>>>(in, static_cast<bf16*>(out), n / 8);
-  else cast_kernel<float><<<grid_for(n / 8), 256, 0, st>>>(in, static_cast<float*>(out), n / 8);
+  if (to_dtype == REGAT_BF16) cast_kernel<float, bf16><<<grid_for(n / 8), 256, 0, st>>>(in, static_cast<bf16*>(out), n / 8);
+  else cast_kernel<float, float><<<grid_for(n / 8), 256, 0, st>>>(in, static_cast<float*>(out), n / 8);
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
@@ -766,4 +766,17 @@ extern "C" int regat_mul(int dtype, int rows, int cols, const void* a, int lda, 
   REGAT_REQUIRE(a && b && out, REGAT_ERR_ARG, "mul: null pointer");
   if (rows <= 0 || cols <= 0) return REGAT_OK;
   return k_mul(dtype, a, lda, b, ldb, out, ldo, rows, cols, (cudaStream_t)stream);
+}
+
+extern "C" int regat_cast(int from_dtype, int to_dtype, const void* in, void* out, int64_t n, regat_stream_t stream) {
+  REGAT_REQUIRE(in && out, REGAT_ERR_ARG, "cast: null pointer");
+  REGAT_REQUIRE(n % 8 == 0 && aligned16(in) && aligned16(out), REGAT_ERR_ALIGN, "cast: needs 16-byte aligned buffers and a multiple of 8 elements");
+  if (n == 0) return REGAT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int g = grid_for(n / 8);
+  if (from_dtype == REGAT_F32 && to_dtype == REGAT_BF16) cast_kernel<float, bf16><<<g, 256, 0, st>>>(static_cast<const float*>(in), static_cast<bf16*>(out), n / 8);
+  else if (from_dtype == REGAT_BF16 && to_dtype == REGAT_F32) cast_kernel<bf16, float><<<g, 256, 0, st>>>(static_cast<const bf16*>(in), static_cast<float*>(out), n / 8);
+  else REGAT_REQUIRE(false, REGAT_ERR_DTYPE, "cast: only fp32 <-> bf16");
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
 }

@@ -41,8 +41,14 @@ class DataParallelTrainer:
     optionally set_grad_callback(fn) (HotPathEngine): with it, each range of the flat gradient buffer is all-reduced on a side
     stream as soon as the backward pass has finished writing it, overlapping the remaining backward kernels."""
 
-    def __init__(self, engine, group=None, bucket_elems: int = 0, overlap: bool = True):
+    def __init__(self, engine, group=None, bucket_elems: int = 0, overlap: bool = True, comm_dtype: str = "auto"):
+        """comm_dtype: "fp32", "bf16" or "auto" (bf16 when the engine computes in bf16: the gradients were produced from bf16
+        activations anyway, and halving the exchanged bytes is what keeps the all-reduce hidden behind the backward pass)."""
         self.engine, self.group, self.bucket_elems = engine, group, bucket_elems
+        if comm_dtype == "auto":
+            comm_dtype = "bf16" if getattr(engine, "dtype_name", "fp32") == "bf16" else "fp32"
+        self.comm_dtype = comm_dtype
+        self._g16 = None
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.step_count = 0
@@ -58,8 +64,22 @@ class DataParallelTrainer:
         ev.record(main)
         self.comm_stream.wait_event(ev)
         with torch.cuda.stream(self.comm_stream):
-            dist.all_reduce(self.engine.grads[offset:offset + numel], op=dist.ReduceOp.SUM, group=self.group)
+            self._allreduce_range(offset, numel)
         self._reduced += numel
+
+    def _allreduce_range(self, offset, numel):
+        g = self.engine.grads
+        if self.comm_dtype == "bf16" and g.is_cuda:
+            from . import _lib
+            if self._g16 is None:
+                self._g16 = torch.empty(g.numel(), dtype=torch.bfloat16, device=g.device)
+            st = torch.cuda.current_stream().cuda_stream
+            l = _lib.lib()
+            _lib.check(l.regat_cast(_lib.F32, _lib.BF16, g.data_ptr() + 4 * offset, self._g16.data_ptr() + 2 * offset, numel, st))
+            dist.all_reduce(self._g16[offset:offset + numel], op=dist.ReduceOp.SUM, group=self.group)
+            _lib.check(l.regat_cast(_lib.BF16, _lib.F32, self._g16.data_ptr() + 2 * offset, g.data_ptr() + 4 * offset, numel, st))
+        else:
+            dist.all_reduce(g[offset:offset + numel], op=dist.ReduceOp.SUM, group=self.group)
 
     def broadcast_params(self, src: int = 0):
         if self.world > 1:
@@ -71,6 +91,8 @@ class DataParallelTrainer:
         out = self.engine.fwd_bwd(features, boxes, q_att, q_last, target, grad_scale=1.0 / self.world)
         if self.overlap and self._reduced == self.engine.grads.numel():
             torch.cuda.current_stream().wait_stream(self.comm_stream)
+        elif self.world > 1 and self.comm_dtype == "bf16" and self.engine.grads.is_cuda:
+            self._allreduce_range(0, self.engine.grads.numel())
         else:
             allreduce_flat_(self.engine.grads, self.group, self.bucket_elems)
         return out
