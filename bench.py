@@ -123,6 +123,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--comm-dtype", default="auto", choices=["auto", "fp32", "bf16"], help="gradient all-reduce precision (auto = engine dtype)")
+    ap.add_argument("--dp-graph", action="store_true", help="N>1: capture forward+backward+all-reduce in a CUDA graph too")
     ap.add_argument("--no-overlap", action="store_true", help="data parallel: one all-reduce after the backward pass instead of overlapped buckets")
     ap.add_argument("--lr", type=float, default=9e-4)
     args = ap.parse_args()
@@ -190,7 +191,7 @@ def main():
                 fwd_bwd(slot)           # warm: creates tensor maps, sets smem attributes
             launches_per_step[0] = eng.last_launches()
             torch.cuda.synchronize()
-            if not args.no_graph and world == 1:       # with NCCL in the step the launches stay eager (host cost ~0.3 ms < GPU time)
+            if not args.no_graph and (world == 1 or args.dp_graph):   # N>1: NCCL inside the captured step only on request
                 for slot in range(2):
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=main_stream):

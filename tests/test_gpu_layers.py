@@ -64,7 +64,7 @@ def test_layer_model_matches_oracle_and_engine(N, nongt, lazy):
 def test_single_attention_layer_and_butd_vs_oracle():
     from tf_vqa_regat_b200.model import BUTD, GraphSelfAttentionLayer, prepare_graph_variables
     from tf_vqa_regat_b200.model import _rt
-    cfg = HotPathConfig(**SMALL)
+    cfg = HotPathConfig(**dict(SMALL, rel_dim=512, num_heads=8))      # one direction: num_heads must be a multiple of 8
     B, N, D, H = 2, 36, cfg.rel_dim, cfg.num_heads
     rng = np.random.default_rng(5)
     roi = rng.standard_normal((B, N, D)).astype(np.float32)

@@ -122,7 +122,7 @@ extern "C" int regat_wn_alpha(const float* params, const int64_t* g_off_host, in
   REGAT_REQUIRE(n_layers <= 32, REGAT_ERR_SHAPE, "wn_alpha: at most 32 layers per call");
   TensorList tl;
   REGAT_TRY(fill_list(tl, nullptr, nullptr, nullptr, g_off_host, nullptr, nullptr, n_layers));
-  return k_wn_alpha(params, tl, sumsq, alpha, inv_norm, (cudaStream_t)stream);
+  return k_wn_alpha(params, tl, const_cast<float*>(sumsq), alpha, inv_norm, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ DLPack front door

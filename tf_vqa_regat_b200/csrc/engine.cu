@@ -53,7 +53,7 @@ struct regat_engine {
   long long ws_need = 0;
   // workspace carve (byte offsets)
   struct Buf { long long off = -1; };
-  Buf lowp, gbias, sumsq, alpha, invn, scal, stats, featT, qattT, qlastT, v0, mask, qs, s, strunc, Qb, KVb, v1, P, GB, gate, uqe,
+  Buf lowp, gbias, sumsq, alpha, invn, scal, stats, partials, featT, qattT, qlastT, v0, mask, qs, s, strunc, Qb, KVb, v1, P, GB, gate, uqe,
       uw, cb, weff, att, pooled, pv, joint, hid, logits, dlogits, dhid, djoint, dpv, duqe, dpooled, dv1, dweff, dcb, duw,
       dQb, dKVb, ds, dstrunc, dsq, dwc3;
   int a_pad = 0;
@@ -158,6 +158,7 @@ long long carve(regat_engine* e) {
   take(e->sumsq, nl * 4); take(e->alpha, nl * 4); take(e->invn, nl * 4);
   take(e->scal, 64 * 4);                       // [0]=label const c, [1]=dc, [2]=loss, [3]=score
   take(e->stats, 2 * MAX_TENSORS * 4);
+  take(e->partials, 2 * 8192 * 4);             // per-chunk partial sums of the weight-norm / optimizer reductions
   take(e->featT, e->dtype == REGAT_BF16 ? R * V * 2 : 0);
   take(e->qattT, e->dtype == REGAT_BF16 ? B * Q * 2 : 0);
   take(e->qlastT, e->dtype == REGAT_BF16 ? B * Q * 2 : 0);
@@ -288,9 +289,9 @@ int fc_wgrad(regat_engine* e, cudaStream_t st, int l, long long w_row0, int rows
 
 int prepare_weights(regat_engine* e, cudaStream_t st) {
   float* sumsq = e->at<float>(e->sumsq);
-  REGAT_CUDA(cudaMemsetAsync(sumsq, 0, e->layers.size() * sizeof(float), st));
-  REGAT_TRY(k_wn_prepare(e->params, e->tl_v, e->chunks_v, sumsq, nullptr, st));
-  REGAT_TRY(k_wn_alpha(e->params, e->tl_v, sumsq, e->at<float>(e->alpha), e->at<float>(e->invn), st));
+  REGAT_REQUIRE(e->chunks_v <= 8192 && e->chunks_opt <= 8192, REGAT_ERR_UNSUPPORTED, "engine: parameter buffer too large for the partial-sum scratch");
+  REGAT_TRY(k_wn_prepare(e->params, e->tl_v, e->chunks_v, sumsq, nullptr, st, e->at<float>(e->partials)));
+  REGAT_TRY(k_wn_alpha(e->params, e->tl_v, sumsq, e->at<float>(e->alpha), e->at<float>(e->invn), st, e->at<float>(e->partials)));
   if (e->dtype == REGAT_BF16) {
     REGAT_TRY(k_wn_scaled_copy(e->params, e->tl_v, e->chunks_v, e->at<float>(e->alpha), e->atv(e->lowp), st));
     REGAT_TRY(k_gather(e->params, e->tl_gather, e->at<float>(e->gbias), st));
@@ -581,9 +582,7 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
 }
 
 int opt_stats(regat_engine* e, cudaStream_t st) {
-  float* stats = e->at<float>(e->stats);
-  REGAT_CUDA(cudaMemsetAsync(stats, 0, 2 * MAX_TENSORS * sizeof(float), st));
-  return k_opt_reduce(e->params, e->grads, e->tl_opt, e->chunks_opt, stats, st);
+  return k_opt_reduce(e->params, e->grads, e->tl_opt, e->chunks_opt, e->at<float>(e->partials), e->at<float>(e->stats), st);
 }
 
 int check_call(regat_engine* e, int B, int N, bool need_opt) {

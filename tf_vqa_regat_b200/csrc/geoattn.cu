@@ -53,11 +53,40 @@ __device__ __forceinline__ void pair_log_geometry(const float4& oi, const float4
   P[3] = logf(__fdiv_rn(oi.y, oj.y));
 }
 
+// sin and cos for |x| < ~1e4 (here |x| <= 100*|log 1e-3| = 691): two-constant Cody-Waite reduction to [-pi/4, pi/4] and
+// degree-7/8 minimax polynomials; absolute error ~1e-7, i.e. the accuracy of sincosf() without its slow-path machinery
+// (the library call was ~85 instructions per evaluation in this kernel).
+__device__ __forceinline__ void sincos_cw(float x, float* sn, float* cs) {
+  const float n = rintf(x * 0.636619772367581f);            // x * 2/pi
+  const int q = (int)n;
+  float r = fmaf(n, -1.57079637050628662f, x);               // pi/2 = hi + lo,  hi = float(pi/2)
+  r = fmaf(n, 4.37113882867379e-08f, r);                     // -lo
+  const float z = r * r;
+  float sp = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+  sp = fmaf(sp, z, -1.6666654611e-1f);
+  sp = fmaf(sp * z, r, r);
+  float cp = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  cp = fmaf(cp, z, 4.166664568298827e-2f);
+  cp = fmaf(cp, z * z, fmaf(z, -0.5f, 1.0f));
+  const float s1 = (q & 1) ? cp : sp, c1 = (q & 1) ? sp : cp;
+  *sn = (q & 2) ? -s1 : s1;
+  *cs = ((q + 1) & 2) ? -c1 : c1;
+}
+
+// one term c of the pairwise log-geometry (position_emb.py:127-142), branch-free
+__device__ __forceinline__ float pair_log_term(const float4& oi, const float4& oj, int c) {
+  const float num = c == 0 ? oi.z - oj.z : (c == 1 ? oi.w - oj.w : (c == 2 ? oi.x : oi.y));
+  const float den = c == 0 ? oi.x : (c == 1 ? oi.y : (c == 2 ? oj.x : oj.y));
+  float qv = __fdiv_rn(num, den);
+  if (c < 2) { qv = fabsf(qv); qv = qv < 1e-3f ? 1e-3f : qv; }
+  return logf(qv);
+}
+
 // the 16 features of one geometry term: [k] = sin(100*P/div_k), [8+k] = cos(...)  (position_emb.py:104-113)
 __device__ __forceinline__ void embedding_group(float Pc, const WaveDiv& wd, float (&emb)[16]) {
   const float x = 100.0f * Pc;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) sincosf(__fdiv_rn(x, wd.d[k]), &emb[k], &emb[8 + k]);
+  for (int k = 0; k < 8; ++k) sincos_cw(__fdiv_rn(x, wd.d[k]), &emb[k], &emb[8 + k]);
 }
 
 // feature c*16+k = sin(100*P_c/div_k), c*16+8+k = cos(...)   (position_emb.py:104-113)
@@ -71,7 +100,7 @@ __device__ __forceinline__ void pair_embedding(const float4& oi, const float4& o
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float sn, cs;
-      sincosf(__fdiv_rn(x, wd.d[k]), &sn, &cs);
+      sincos_cw(__fdiv_rn(x, wd.d[k]), &sn, &cs);
       emb[c * 16 + k] = sn;
       emb[c * 16 + 8 + k] = cs;
     }
@@ -226,8 +255,12 @@ __global__ void __launch_bounds__(256, 2) geoattn_fwd_kernel(const FwdParams p) 
 
   // ---- phase 0: per-object terms and the pair_pos_fc weights into shared memory
   for (int n = tid; n < N; n += 256) obj[n] = p.boxes ? box_terms(p.boxes + ((size_t)b * N + n) * 4) : make_float4(1, 1, 0, 0);
+  // pair_pos_fc kernels of all directions, stored in mma B-fragment order: wgs[((ks*NTD + nt)*32 + lane)*2 + r] =
+  // W_g[feature 8ks + lane%4 + 4r][dh = 8nt + lane/4]  -> every lane reads its (b0, b1) with one conflict-free 64-bit load
+  const int NTD = DH >> 3;
   for (int x = tid; x < EMB * DH; x += 256) {
-    int e = x / DH, dh = x - e * DH, d = dh / H, h = dh - d * H;
+    const int r = x & 1, ln = (x >> 1) & 31, rest = x >> 6, nt = rest % NTD, ks = rest / NTD;
+    const int e = 8 * ks + (ln & 3) + 4 * r, dh = 8 * nt + (ln >> 2), d = dh / H, h = dh - d * H;
     wgs[x] = p.wg[(size_t)d * p.wg_stride + e * H + h];
   }
   for (int dh = tid; dh < DH; dh += 256) {
@@ -238,60 +271,79 @@ __global__ void __launch_bounds__(256, 2) geoattn_fwd_kernel(const FwdParams p) 
   __syncthreads();
 
   // ---- phase 1: geometry bias for the 16 x M pairs of this row tile, all heads and directions.
-  // bias[i,j] belongs to box pair (f / N, f % N), f = i*M + j  (graph_att_layer.py:74,81 raw reshape of
-  // the row-sliced [M,N] tensor from position_emb.py:146).
-  for (int pi = tid; pi < ROWS * M; pi += 256) {
-    const int il = pi / M, j = pi - il * M, i = i0 + il;
-    if (i < N) {
-      const int f = i * M + j;
-      float P[4] = {0.f, 0.f, 0.f, 0.f};
-      const float4* src = nullptr;
-      if (p.pos_emb) {
-        src = reinterpret_cast<const float4*>(p.pos_emb + ((size_t)b * M * N + f) * EMB);
-      } else {
-        const int ip = f / N, jp = f - ip * N;
-        pair_log_geometry(obj[ip], obj[jp], P);
+  // bias[i,j] belongs to box pair (f / N, f % N), f = i*M + j  (graph_att_layer.py:74,81 raw reshape of the row-sliced [M,N]
+  // tensor from position_emb.py:146).  The 64 -> dirs*H projection runs on the tensor cores: a warp takes 16 consecutive
+  // pairs as one mma m-tile; lane (g, t) evaluates exactly the sin/cos values its A fragments need (pairs g and g+8, wave
+  // numbers t and t+4 of every geometry term -- 16 sincos per lane per tile, none computed twice), the quad shares the four
+  // log-geometry terms by shuffle, and z lands in C fragments where alpha, bias, relu, max and log are applied.
+  {
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const int npairs = ROWS * M;
+    for (int mt = warp; mt * 16 < npairs; mt += 8) {
+      int il[2], jj[2], fidx[2];
+      bool inb[2], rowok[2];
+      float mine[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int pi = mt * 16 + g + 8 * u;
+        inb[u] = pi < npairs;
+        il[u] = min(pi, npairs - 1) / M; jj[u] = min(pi, npairs - 1) - il[u] * M;
+        const int i = i0 + il[u];
+        rowok[u] = inb[u] && i < N;
+        fidx[u] = min(i, N - 1) * M + jj[u];
+        const int ip = fidx[u] / N, jp = fidx[u] - ip * N;
+        mine[u] = p.pos_emb ? 0.f : pair_log_term(obj[ip], obj[jp], t);     // lane t owns geometry term t of its two pairs
       }
-      // z[dh] accumulated over the four 16-feature groups (sin x8, cos x8 of one geometry term), so only
-      // 16 embedding values are live at a time.
-      float zacc[MAX_DH];
+      float zc[MAX_DH / 8][4];
 #pragma unroll
-      for (int u = 0; u < MAX_DH; ++u) zacc[u] = 0.f;
-#pragma unroll 1
+      for (int nt = 0; nt < MAX_DH / 8; ++nt) { zc[nt][0] = zc[nt][1] = zc[nt][2] = zc[nt][3] = 0.f; }
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        float emb[16];
-        if (src) {
+        float sv[2][2], cv[2][2];        // [pair][wave number t / t+4]
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float4 x = __ldg(src + 4 * c + k);
-            emb[4 * k] = x.x; emb[4 * k + 1] = x.y; emb[4 * k + 2] = x.z; emb[4 * k + 3] = x.w;
+        for (int u = 0; u < 2; ++u) {
+          if (p.pos_emb) {
+            const float* er = p.pos_emb + ((size_t)b * M * N + fidx[u]) * EMB + c * 16;
+            sv[u][0] = __ldg(er + t); sv[u][1] = __ldg(er + t + 4); cv[u][0] = __ldg(er + 8 + t); cv[u][1] = __ldg(er + 12 + t);
+          } else {
+            const float x = 100.0f * __shfl_sync(0xffffffffu, mine[u], (lane & ~3) | c);
+            sincos_cw(__fdiv_rn(x, p.wd.d[t]), &sv[u][0], &cv[u][0]);
+            sincos_cw(__fdiv_rn(x, p.wd.d[t + 4]), &sv[u][1], &cv[u][1]);
           }
-        } else {
-          embedding_group(P[c], p.wd, emb);
         }
+        Opnd<true, 4> as, ac;      // 3xTF32 in both modes: log() amplifies any error of z near 0
+        as.set(0, sv[0][0]); as.set(1, sv[1][0]); as.set(2, sv[0][1]); as.set(3, sv[1][1]);
+        ac.set(0, cv[0][0]); ac.set(1, cv[1][0]); ac.set(2, cv[0][1]); ac.set(3, cv[1][1]);
 #pragma unroll
-        for (int dh0 = 0; dh0 < MAX_DH; dh0 += 4) {
-          if (dh0 < DH) {
+        for (int nt = 0; nt < MAX_DH / 8; ++nt) {
+          if (nt < NTD) {
+            const float2 ws = *reinterpret_cast<const float2*>(wgs + (((2 * c) * NTD + nt) * 32 + lane) * 2);
+            const float2 wc = *reinterpret_cast<const float2*>(wgs + (((2 * c + 1) * NTD + nt) * 32 + lane) * 2);
+            Opnd<true, 2> bs, bc;
+            bs.set(0, ws.x); bs.set(1, ws.y); bc.set(0, wc.x); bc.set(1, wc.y);
+            mma_acc<true>(zc[nt], as, bs);
+            mma_acc<true>(zc[nt], ac, bc);
+          }
+        }
+      }
 #pragma unroll
-            for (int e = 0; e < 16; ++e) {
-              const float4 w = *reinterpret_cast<const float4*>(wgs + (c * 16 + e) * DH + dh0);
-              zacc[dh0] = fmaf(emb[e], w.x, zacc[dh0]); zacc[dh0 + 1] = fmaf(emb[e], w.y, zacc[dh0 + 1]);
-              zacc[dh0 + 2] = fmaf(emb[e], w.z, zacc[dh0 + 2]); zacc[dh0 + 3] = fmaf(emb[e], w.w, zacc[dh0 + 3]);
+      for (int nt = 0; nt < MAX_DH / 8; ++nt) {
+        if (nt < NTD) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int u = e >> 1, dh = 8 * nt + 2 * t + (e & 1);
+            if (inb[u]) {
+              float gb = 0.f;
+              if (rowok[u]) {
+                const float z = fmaf(ags[dh], zc[nt][e], bgs[dh]);
+                gb = logf(fmaxf(fmaxf(z, 0.f), 1e-6f));                   // graph_att_layer.py:79,86,88
+                if (p.save_gb) p.save_gb[(((size_t)b * DH + dh) * N + i0 + il[u]) * M + jj[u]] = gb;
+              }
+              tile[(dh * ROWS + il[u]) * MP + jj[u]] = gb;
             }
           }
         }
       }
-#pragma unroll
-      for (int dh = 0; dh < MAX_DH; ++dh) {
-        if (dh < DH) {
-          const float z = fmaf(ags[dh], zacc[dh], bgs[dh]);
-          const float gb = logf(fmaxf(fmaxf(z, 0.f), 1e-6f));           // graph_att_layer.py:79,86,88
-          tile[(dh * ROWS + il) * MP + j] = gb;
-          if (p.save_gb) p.save_gb[(((size_t)b * DH + dh) * N + i) * M + j] = gb;
-        }
-      }
-    } else {
-      for (int dh = 0; dh < DH; ++dh) tile[(dh * ROWS + il) * MP + j] = 0.f;
     }
   }
   __syncthreads();
@@ -793,99 +845,121 @@ struct GeoBwdParams {
   const float* dl; const float* gbias;
   float* dwg; long long dwg_stride; float* dbg; long long dbg_stride; float* dc;
 };
-constexpr int GB_PAIRS = 256, GB_LDE = EMB + 1;
-
-template <int DH>   // DH = dirs*H, multiple of 8, <= 32
-__global__ void __launch_bounds__(256) geo_bwd_kernel(const GeoBwdParams p) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* embS = reinterpret_cast<float*>(smem_raw);        // [GB_PAIRS][GB_LDE]
-  float* dzS = embS + GB_PAIRS * GB_LDE;                   // [GB_PAIRS][DH]
-  __shared__ float red[8];
-  const int tid = threadIdx.x;
-  const int N = p.N, M = p.M, NM = p.N * p.M;
+// One warp = one mma pipeline: per k-step it takes 8 consecutive (graph, pair) items.  D[feature, dh] += Emb^T[feature, pair] *
+// dz[pair, dh] with the 64 features as 4 m-tiles (one per geometry term c: rows g = sin, g+8 = cos of wave number g) and dh as
+// n-tiles.  Lane (g, t) evaluates sincos(term c, wave g) of pairs t and t+4 -- exactly its A fragments, nothing twice; the 32
+// log-geometry terms of a k-step are computed one per lane and exchanged by shuffle.  3xTF32 keeps fp32 accuracy.
+template <int DH>
+__global__ void __launch_bounds__(256, 2) geo_bwd_kernel(const GeoBwdParams p) {
+  constexpr int NTD = DH / 8;
+  __shared__ float red[EMB * DH];
+  __shared__ float redb[DH];
+  __shared__ float redc;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int N = p.N, NM = p.N * p.M;
   const long long total = (long long)p.B * NM;
   const float LOGMIN = logf(1e-6f);
-  constexpr int G = DH / 8;              // dh groups of 8
-  constexpr int EPT = EMB * G / 256 > 0 ? EMB * G / 256 : 1;   // e's per thread (1 for DH=32)
-  // thread -> (e, dh group): for DH=32: e = tid/4, grp = tid%4
-  const int grp = tid % G, e_base = (tid / G) * EPT;
-  const bool active = (tid / G) * EPT < EMB;
-  float acc[EPT][8];
-  float bsum[8];
-#pragma unroll
-  for (int u = 0; u < 8; ++u) { bsum[u] = 0.f;
-#pragma unroll
-    for (int q = 0; q < EPT; ++q) acc[q][u] = 0.f; }
-  float csum = 0.f;
+  for (int x = tid; x < EMB * DH; x += 256) red[x] = 0.f;
+  if (tid < DH) redb[tid] = 0.f;
+  if (tid == 0) redc = 0.f;
+  __syncthreads();
 
-  for (long long base = (long long)blockIdx.x * GB_PAIRS; base < total; base += (long long)gridDim.x * GB_PAIRS) {
-    const long long pi = base + tid;
-    float emb[EMB];
-    if (pi < total) {
-      const int b = (int)(pi / NM), f = (int)(pi - (long long)b * NM);
-      if (p.pos_emb) {
-        const float4* src = reinterpret_cast<const float4*>(p.pos_emb + ((size_t)b * NM + f) * EMB);
+  float acc[4][NTD][4];
+  float bsum[NTD];
+  float csum = 0.f;
 #pragma unroll
-        for (int k = 0; k < EMB / 4; ++k) {
-          float4 x = __ldg(src + k);
-          emb[4 * k] = x.x; emb[4 * k + 1] = x.y; emb[4 * k + 2] = x.z; emb[4 * k + 3] = x.w;
-        }
-      } else {
-        const int ip = f / N, jp = f - ip * N;
-        pair_embedding(box_terms(p.boxes + ((size_t)b * N + ip) * 4), box_terms(p.boxes + ((size_t)b * N + jp) * 4), p.wd, emb);
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int nt = 0; nt < NTD; ++nt) { acc[c][nt][0] = acc[c][nt][1] = acc[c][nt][2] = acc[c][nt][3] = 0.f; }
+#pragma unroll
+  for (int nt = 0; nt < NTD; ++nt) bsum[nt] = 0.f;
+
+  const long long nsteps = (total + 7) / 8;
+  for (long long ks = (long long)blockIdx.x * 8 + warp; ks < nsteps; ks += (long long)gridDim.x * 8) {
+    const long long pb = ks * 8;
+    // lane L evaluates geometry term L%4 of pair pb + L/4
+    float mine = 0.f;
+    {
+      const long long pq = pb + g;
+      if (pq < total && !p.pos_emb) {
+        const int bq = (int)(pq / NM), f = (int)(pq - (long long)bq * NM), ip = f / N, jp = f - ip * N;
+        mine = pair_log_term(box_terms(p.boxes + ((size_t)bq * N + ip) * 4), box_terms(p.boxes + ((size_t)bq * N + jp) * 4), t);
       }
+    }
+    const long long pA = pb + t, pB = pb + t + 4;
+    const bool vA = pA < total, vB = pB < total;
+    const int bA = vA ? (int)(pA / NM) : 0, fA = vA ? (int)(pA - (long long)bA * NM) : 0;
+    const int bB = vB ? (int)(pB / NM) : 0, fB = vB ? (int)(pB - (long long)bB * NM) : 0;
+    // B fragments: dz = dL / z where z = exp(gbias) >= 1e-6, else 0    (d log(max(relu(z), 1e-6)) / dz)
+    Opnd<true, 2> bz[NTD];
 #pragma unroll
-      for (int dh = 0; dh < DH; ++dh) {
-        const size_t idx = ((size_t)b * DH + dh) * NM + f;
+    for (int nt = 0; nt < NTD; ++nt) {
+      const int dh = 8 * nt + g;
+      float dzA = 0.f, dzB = 0.f;
+      if (vA) {
+        const size_t idx = ((size_t)bA * DH + dh) * NM + fA;
         const float dl = __ldg(p.dl + idx), gb = __ldg(p.gbias + idx);
         csum += dl;
-        dzS[tid * DH + dh] = gb > LOGMIN ? dl * expf(-gb) : 0.f;     // d log(max(relu(z),1e-6)) / dz
+        dzA = gb > LOGMIN ? dl * expf(-gb) : 0.f;
       }
-    } else {
-#pragma unroll
-      for (int e = 0; e < EMB; ++e) emb[e] = 0.f;
-#pragma unroll
-      for (int dh = 0; dh < DH; ++dh) dzS[tid * DH + dh] = 0.f;
+      if (vB) {
+        const size_t idx = ((size_t)bB * DH + dh) * NM + fB;
+        const float dl = __ldg(p.dl + idx), gb = __ldg(p.gbias + idx);
+        csum += dl;
+        dzB = gb > LOGMIN ? dl * expf(-gb) : 0.f;
+      }
+      bsum[nt] += dzA + dzB;
+      bz[nt].set(0, dzA); bz[nt].set(1, dzB);
     }
 #pragma unroll
-    for (int e = 0; e < EMB; ++e) embS[tid * GB_LDE + e] = emb[e];
-    __syncthreads();
-    if (active) {
-      for (int q = 0; q < GB_PAIRS; ++q) {
-        const float4 z0 = *reinterpret_cast<const float4*>(dzS + q * DH + 8 * grp);
-        const float4 z1 = *reinterpret_cast<const float4*>(dzS + q * DH + 8 * grp + 4);
-        const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
-#pragma unroll
-        for (int qq = 0; qq < EPT; ++qq) {
-          const float ev = embS[q * GB_LDE + e_base + qq];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) acc[qq][u] = fmaf(ev, zz[u], acc[qq][u]);
-        }
-        if (e_base == 0) {
-#pragma unroll
-          for (int u = 0; u < 8; ++u) bsum[u] += zz[u];
-        }
+    for (int c = 0; c < 4; ++c) {
+      float sA, cA, sB, cB;
+      if (p.pos_emb) {
+        const float* eA = p.pos_emb + ((size_t)bA * NM + fA) * EMB + 16 * c;
+        const float* eB = p.pos_emb + ((size_t)bB * NM + fB) * EMB + 16 * c;
+        sA = vA ? __ldg(eA + g) : 0.f; cA = vA ? __ldg(eA + 8 + g) : 0.f;
+        sB = vB ? __ldg(eB + g) : 0.f; cB = vB ? __ldg(eB + 8 + g) : 0.f;
+      } else {
+        const float xA = 100.0f * __shfl_sync(0xffffffffu, mine, 4 * t + c);
+        const float xB = 100.0f * __shfl_sync(0xffffffffu, mine, 4 * (t + 4) + c);
+        sincos_cw(__fdiv_rn(xA, p.wd.d[g]), &sA, &cA);
+        sincos_cw(__fdiv_rn(xB, p.wd.d[g]), &sB, &cB);
+        if (!vA) { sA = 0.f; cA = 0.f; }
+        if (!vB) { sB = 0.f; cB = 0.f; }
       }
+      Opnd<true, 4> a;
+      a.set(0, sA); a.set(1, cA); a.set(2, sB); a.set(3, cB);
+#pragma unroll
+      for (int nt = 0; nt < NTD; ++nt) mma_acc<true>(acc[c][nt], a, bz[nt]);
     }
-    __syncthreads();
   }
-  if (active) {
+  // ---- CTA reduction in shared memory, then one set of global atomics per CTA
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int dh = 8 * grp + u, d = dh / p.H, h = dh - d * p.H;
+  for (int c = 0; c < 4; ++c)
 #pragma unroll
-      for (int qq = 0; qq < EPT; ++qq) atomicAdd(p.dwg + (size_t)d * p.dwg_stride + (e_base + qq) * p.H + h, acc[qq][u]);
-      if (e_base == 0 && p.dbg) atomicAdd(p.dbg + (size_t)d * p.dbg_stride + h, bsum[u]);
-    }
+    for (int nt = 0; nt < NTD; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        atomicAdd(&red[(16 * c + g + 8 * (e >> 1)) * DH + 8 * nt + 2 * t + (e & 1)], acc[c][nt][e]);
+#pragma unroll
+  for (int nt = 0; nt < NTD; ++nt) {
+    float v = bsum[nt];
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if (t == 0) atomicAdd(&redb[8 * nt + g], v);
   }
   csum = warp_sum(csum);
-  if ((tid & 31) == 0) red[tid >> 5] = csum;
+  if (lane == 0) atomicAdd(&redc, csum);
   __syncthreads();
-  if (tid == 0 && p.dc) {
-    float s = 0.f;
-    for (int w = 0; w < 8; ++w) s += red[w];
-    atomicAdd(p.dc, s);
+  for (int x = tid; x < EMB * DH; x += 256) {
+    const int e = x / DH, dh = x - e * DH, d = dh / p.H, h = dh - d * p.H;
+    atomicAdd(p.dwg + (size_t)d * p.dwg_stride + e * p.H + h, red[x]);
   }
+  if (tid < DH && p.dbg) {
+    const int d = tid / p.H, h = tid - d * p.H;
+    atomicAdd(p.dbg + (size_t)d * p.dbg_stride + h, redb[tid]);
+  }
+  if (tid == 0 && p.dc) atomicAdd(p.dc, redc);
 }
 
 // ==========================================================================================
@@ -953,8 +1027,8 @@ int check_common(int B, int N, int D, int H, int dirs, int E) {
   REGAT_REQUIRE(H > 0 && D == H * HD, REGAT_ERR_UNSUPPORTED, "geoattn: head dim must be 64 (rel_dim=%d, heads=%d)", D, H);
   REGAT_REQUIRE(dirs >= 1 && dirs <= 2, REGAT_ERR_SHAPE, "geoattn: dir_num must be 1 or 2 (graph_att_net.py:18)");
   REGAT_REQUIRE(E == EMB, REGAT_ERR_UNSUPPORTED, "geoattn: pos_emb_dim must be 64");
-  REGAT_REQUIRE((dirs * H) % 4 == 0 && dirs * H <= MAX_DH, REGAT_ERR_UNSUPPORTED,
-                "geoattn: dir_num*num_heads must be a multiple of 4 and <= 32");
+  REGAT_REQUIRE((dirs * H) % 8 == 0 && dirs * H <= MAX_DH, REGAT_ERR_UNSUPPORTED,
+                "geoattn: dir_num*num_heads must be a multiple of 8 and <= 32");
   return REGAT_OK;
 }
 
@@ -1040,19 +1114,15 @@ extern "C" int regat_geo_bwd(int B, int N, int nongt_dim, int H, int dirs, int E
   for (int k = 0; k < 8; ++k) p.wd.d[k] = wave_div_host ? wave_div_host[k] : 1.f;
   p.dl = dl; p.gbias = gbias; p.dwg = dwg; p.dwg_stride = dwg_stride; p.dbg = dbg; p.dbg_stride = dbg_stride; p.dc = dc;
   const int DH = dirs * H;
-  const size_t smem = sizeof(float) * (size_t)GB_PAIRS * (GB_LDE + DH);
-  const long long tiles = ((long long)B * p.N * p.M + GB_PAIRS - 1) / GB_PAIRS;
-  const int blocks = (int)std::min<long long>(tiles, (long long)num_sms() * 2);
+  const long long ksteps = ((long long)B * p.N * p.M + 7) / 8;
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((ksteps + 7) / 8, (long long)num_sms() * 2));
   cudaStream_t st = (cudaStream_t)stream;
-#define REGAT_GB_CASE(X)                                                   \
-  {                                                                        \
-    REGAT_TRY(set_smem(geo_bwd_kernel<X>, smem));                          \
-    geo_bwd_kernel<X><<<blocks, 256, smem, st>>>(p);                       \
-  }
+#define REGAT_GB_CASE(X) { geo_bwd_kernel<X><<<blocks, 256, 0, st>>>(p); }
   if (DH == 32) REGAT_GB_CASE(32)
+  else if (DH == 24) REGAT_GB_CASE(24)
   else if (DH == 16) REGAT_GB_CASE(16)
   else if (DH == 8) REGAT_GB_CASE(8)
-  else REGAT_REQUIRE(false, REGAT_ERR_UNSUPPORTED, "geo_bwd: dir_num*num_heads must be 8, 16 or 32 (got %d)", DH);
+  else REGAT_REQUIRE(false, REGAT_ERR_UNSUPPORTED, "geo_bwd: dir_num*num_heads must be 8, 16, 24 or 32 (got %d)", DH);
 #undef REGAT_GB_CASE
   REGAT_POST_LAUNCH();
   return REGAT_OK;

@@ -27,10 +27,10 @@ struct OptHyper {
   int grads_are_final;
 };
 
-int k_wn_prepare(const float* params, const TensorList& tl, int chunks, float* sumsq, void* lowp, cudaStream_t st);
+int k_wn_prepare(const float* params, const TensorList& tl, int chunks, float* sumsq, void* lowp, cudaStream_t st, float* partials = nullptr);
 int k_wn_scaled_copy(const float* params, const TensorList& tl, int chunks, const float* alpha, void* lowp, cudaStream_t st);
 int k_gather(const float* src, const TensorList& tl, float* dst, cudaStream_t st);
-int k_wn_alpha(const float* params, const TensorList& tl, const float* sumsq, float* alpha, float* inv_norm, cudaStream_t st);
+int k_wn_alpha(const float* params, const TensorList& tl, float* sumsq, float* alpha, float* inv_norm, cudaStream_t st, const float* partials = nullptr);
 int k_cast(int to_dtype, const float* in, void* out, long long n, cudaStream_t st);
 int k_rowmask(int dt, const void* v, int rows, int D, float* mask, cudaStream_t st);
 int k_mul(int dt, const void* a, int lda, const void* b, int ldb, void* out, int ldo, int rows, int cols, cudaStream_t st);
@@ -46,7 +46,7 @@ int k_bce(int B, int A, const float* logits, int ldl, const float* target, float
 int k_colsum(int dt, const void* x, int ld, int rows, int cols, float* out, cudaStream_t st);
 int k_segsum(int dt, const void* x, const float* w, int B, int N, int D, void* out, cudaStream_t st);
 int k_addrows(int dt, void* dst, const void* src, int B, int N, int M, int D, cudaStream_t st);
-int k_opt_reduce(const float* params, const float* grads, const TensorList& tl, int chunks, float* stats, cudaStream_t st);
+int k_opt_reduce(const float* params, const float* grads, const TensorList& tl, int chunks, float* partials, float* stats, cudaStream_t st);
 int k_opt_update(float* params, const float* grads, float* m, float* u, const TensorList& tl, int chunks, const float* stats,
                  const float* alpha, const float* inv_norm, const OptHyper& hp, cudaStream_t st);
 int k_opt_finalize(const float* params, float* grads, const TensorList& tl, int chunks, const float* stats, const float* alpha,

@@ -49,7 +49,7 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {   // block
 // ---------------------------------------------------------------- weight norm (weight_norm.py:35-41)
 constexpr int WN_CHUNK = 4096;   // elements per block
 __global__ void __launch_bounds__(256) wn_prepare_kernel(const float* __restrict__ params, TensorList tl, float* sumsq,
-                                                         bf16* lowp) {
+                                                         bf16* lowp, float* partials) {
   __shared__ float red[8];
   int l = 0;
   while (l + 1 < tl.n && (int)blockIdx.x >= tl.chunk_start[l + 1]) ++l;
@@ -67,7 +67,10 @@ __global__ void __launch_bounds__(256) wn_prepare_kernel(const float* __restrict
     }
   }
   ss = block_sum_256(ss, red);
-  if (threadIdx.x == 0) atomicAdd(sumsq + l, ss);
+  if (threadIdx.x == 0) {
+    if (partials) partials[blockIdx.x] = ss;      // deterministic: summed in chunk order by wn_alpha_kernel
+    else atomicAdd(sumsq + l, ss);
+  }
 }
 
 // second pass of the bf16 weight preparation: lowp = bf16(alpha_l * v) = bf16(W_eff), placed at (off_lowp, ld_lowp) so that
@@ -105,11 +108,23 @@ __global__ void gather_kernel(const float* __restrict__ src, TensorList tl, floa
     for (long long i = threadIdx.x; i < tl.numel[l]; i += blockDim.x) dst[tl.off_lowp[l] + i] = src[tl.off[l] + i];
 }
 
-__global__ void wn_alpha_kernel(const float* __restrict__ params, TensorList tl, const float* __restrict__ sumsq,
-                                float* alpha, float* inv_norm) {
-  const int l = threadIdx.x;
-  if (l < tl.n) {
-    const float inv = rsqrtf(fmaxf(sumsq[l], 1e-12f));     // tf.nn.l2_normalize epsilon
+__global__ void wn_alpha_kernel(const float* __restrict__ params, TensorList tl, float* __restrict__ sumsq,
+                                const float* __restrict__ partials, float* alpha, float* inv_norm) {
+  // one warp per tensor; with `partials` the per-chunk sums are added in a fixed order (bitwise reproducible, so data-parallel
+  // replicas that hold identical parameters compute identical alpha)
+  const int l = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (l >= tl.n) return;
+  float ss;
+  if (partials) {
+    ss = 0.f;
+    for (int c = tl.chunk_start[l] + lane; c < tl.chunk_start[l + 1]; c += 32) ss += partials[c];
+    ss = warp_sum(ss);
+    if (lane == 0) sumsq[l] = ss;
+  } else {
+    ss = sumsq[l];
+  }
+  if (lane == 0) {
+    const float inv = rsqrtf(fmaxf(ss, 1e-12f));     // tf.nn.l2_normalize epsilon
     inv_norm[l] = inv;
     alpha[l] = params[tl.g_off[l]] * inv;
   }
@@ -488,7 +503,17 @@ __global__ void __launch_bounds__(256) opt_reduce_kernel(const float* __restrict
   }
   dot = block_sum_256(dot, red);
   gg = block_sum_256(gg, red);
-  if (threadIdx.x == 0) { atomicAdd(stats + 2 * l, dot); atomicAdd(stats + 2 * l + 1, gg); }
+  if (threadIdx.x == 0) { stats[2 * blockIdx.x] = dot; stats[2 * blockIdx.x + 1] = gg; }   // per-chunk partials
+}
+
+// fixed-order sum of the per-chunk partials: stats[l] = (sum G*v, sum G^2) of tensor l.  One warp per tensor.
+__global__ void opt_stats_kernel(TensorList tl, const float* __restrict__ partials, float* __restrict__ stats) {
+  const int l = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (l >= tl.n) return;
+  float dot = 0.f, gg = 0.f;
+  for (int c = tl.chunk_start[l] + lane; c < tl.chunk_start[l + 1]; c += 32) { dot += partials[2 * c]; gg += partials[2 * c + 1]; }
+  dot = warp_sum(dot); gg = warp_sum(gg);
+  if (lane == 0) { stats[2 * l] = dot; stats[2 * l + 1] = gg; }
 }
 
 // pass 2: tensors are listed as kind 0 (v of a weight-normed layer, grads hold dL/dW_eff), 1 (bias, plain).
@@ -578,8 +603,8 @@ int build_tensor_list(TensorList& tl) {
   return c;
 }
 
-int k_wn_prepare(const float* params, const TensorList& tl, int chunks, float* sumsq, void* lowp, cudaStream_t st) {
-  wn_prepare_kernel<<<chunks, 256, 0, st>>>(params, tl, sumsq, static_cast<bf16*>(lowp));
+int k_wn_prepare(const float* params, const TensorList& tl, int chunks, float* sumsq, void* lowp, cudaStream_t st, float* partials) {
+  wn_prepare_kernel<<<chunks, 256, 0, st>>>(params, tl, sumsq, static_cast<bf16*>(lowp), partials);
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
@@ -593,8 +618,9 @@ int k_gather(const float* src, const TensorList& tl, float* dst, cudaStream_t st
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
-int k_wn_alpha(const float* params, const TensorList& tl, const float* sumsq, float* alpha, float* inv_norm, cudaStream_t st) {
-  wn_alpha_kernel<<<1, 32, 0, st>>>(params, tl, sumsq, alpha, inv_norm);
+int k_wn_alpha(const float* params, const TensorList& tl, float* sumsq, float* alpha, float* inv_norm, cudaStream_t st, const float* partials) {
+  REGAT_REQUIRE(tl.n <= 32, REGAT_ERR_SHAPE, "wn_alpha: at most 32 tensors");
+  wn_alpha_kernel<<<1, 1024, 0, st>>>(params, tl, sumsq, partials, alpha, inv_norm);
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
@@ -679,9 +705,20 @@ int k_addrows(int dt, void* dst, const void* src, int B, int N, int M, int D, cu
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
-int k_opt_reduce(const float* params, const float* grads, const TensorList& tl, int chunks, float* stats, cudaStream_t st) {
-  opt_reduce_kernel<<<chunks, 256, 0, st>>>(params, grads, tl, stats);
+int k_opt_reduce(const float* params, const float* grads, const TensorList& tl, int chunks, float* partials, float* stats, cudaStream_t st) {
+  opt_reduce_kernel<<<chunks, 256, 0, st>>>(params, grads, tl, partials);
   REGAT_POST_LAUNCH();
+  REGAT_REQUIRE(tl.n <= MAX_TENSORS, REGAT_ERR_SHAPE, "opt_reduce: too many tensors");
+  for (int l0 = 0; l0 < tl.n; l0 += 32) {   // 32 warps (tensors) per block
+    TensorList part = tl;
+    if (l0) {
+      for (int i = 0; i + l0 < tl.n; ++i) part.chunk_start[i] = tl.chunk_start[i + l0];
+      part.chunk_start[tl.n - l0] = tl.chunk_start[tl.n];
+    }
+    part.n = std::min(32, tl.n - l0);
+    opt_stats_kernel<<<1, 1024, 0, st>>>(part, partials, stats + 2 * l0);
+    REGAT_POST_LAUNCH();
+  }
   return REGAT_OK;
 }
 int k_opt_update(float* params, const float* grads, float* m, float* u, const TensorList& tl, int chunks, const float* stats,
