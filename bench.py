@@ -123,7 +123,6 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--comm-dtype", default="auto", choices=["auto", "fp32", "bf16"], help="gradient all-reduce precision (auto = engine dtype)")
-    ap.add_argument("--dp-graph", action="store_true", help="N>1: capture forward+backward+all-reduce in a CUDA graph too")
     ap.add_argument("--no-overlap", action="store_true", help="data parallel: one all-reduce after the backward pass instead of overlapped buckets")
     ap.add_argument("--lr", type=float, default=9e-4)
     args = ap.parse_args()
@@ -191,12 +190,18 @@ def main():
                 fwd_bwd(slot)           # warm: creates tensor maps, sets smem attributes
             launches_per_step[0] = eng.last_launches()
             torch.cuda.synchronize()
-            if not args.no_graph and (world == 1 or args.dp_graph):   # N>1: NCCL inside the captured step only on request
+            if not args.no_graph and world == 1:
                 for slot in range(2):
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=main_stream):
                         fwd_bwd(slot)
                     graphs[slot] = g
+            elif not args.no_graph and trainer.overlap:
+                # N>1: compute-only graph segments split at the gradient-ready points, NCCL eagerly in between (dp.GraphedDPStep)
+                from tf_vqa_regat_b200.dp import GraphedDPStep
+                for slot in range(2):
+                    b = devb[slot]
+                    graphs[slot] = GraphedDPStep(trainer, b["features"], b["boxes"], b["q_att"], b["q_last"], b["target"], main_stream)
         torch.cuda.synchronize()
 
     def one_step(slot):

@@ -278,12 +278,18 @@ int fc_dgrad(regat_engine* e, cudaStream_t st, int l, long long w_row0, int rows
   return dense(e, st, false, true, rows, K_in, e->layers[l].cols, dy, lddy, W(e, l, w_row0), ldW(e, l), dx, lddx, dx_dtype, ep);
 }
 // dW_eff[w_row0 : w_row0+K_in, :] = x^T dy  (fp32, into the grads buffer);  db += colsum(dy)
+// the bias gradient (a column sum of dy) is either launched right away or queued in `batch` for one multi-problem launch
+int bias_grad(regat_engine* e, cudaStream_t st, const void* dy, int lddy, int rows, int cols, float* out, ColsumBatch* batch) {
+  if (!out) return REGAT_OK;
+  if (batch && aligned16(dy) && lddy % 8 == 0 && cols % 8 == 0 && batch->n < 12) { batch->add(dy, lddy, rows, cols, out); return REGAT_OK; }
+  return k_colsum(e->dtype, dy, lddy, rows, cols, out, st);
+}
 int fc_wgrad(regat_engine* e, cudaStream_t st, int l, long long w_row0, int rows, int K_in, const void* x, int ldx, const void* dy,
-             int lddy, bool with_bias) {
+             int lddy, bool with_bias, ColsumBatch* batch = nullptr) {
   EpiArgs ep = epi0();
   REGAT_TRY(dense(e, st, true, false, K_in, e->layers[l].cols, rows, x, ldx, dy, lddy, gradW(e, l, w_row0), e->layers[l].cols,
                   REGAT_F32, ep));
-  if (with_bias && gradB(e, l)) REGAT_TRY(k_colsum(e->dtype, dy, lddy, rows, e->layers[l].cols, gradB(e, l), st));
+  if (with_bias) REGAT_TRY(bias_grad(e, st, dy, lddy, rows, e->layers[l].cols, gradB(e, l), batch));
   return REGAT_OK;
 }
 
@@ -465,6 +471,7 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   // the classifier and of BUTD is off the critical path and goes to the side stream as soon as its operands exist.
   cudaStream_t sd = e->side;
   unsigned char* dqe = e->at<unsigned char>(e->duqe) + (size_t)Hd * es;
+  ColsumBatch cb_side, cb_mid;       // bias gradients, one multi-problem launch per backward stage
   REGAT_TRY(fork_to(st, sd, e->ev[2]));                    // dlogits ready
   if (dt == REGAT_BF16 && e->use_tc && (A % 4) != 0) {
     // the [2Hd, A] gradient has unaligned rows (A = 3129): compute it with a padded pitch, then compact into the flat buffer
@@ -472,19 +479,19 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
                     REGAT_F32, epi0()));
     REGAT_CUDA(cudaMemcpy2DAsync(gradW(e, e->l_c3), (size_t)A * sizeof(float), e->atv(e->dwc3), (size_t)e->a_pad * sizeof(float),
                                  (size_t)A * sizeof(float), 2 * Hd, cudaMemcpyDeviceToDevice, sd));
-    REGAT_TRY(k_colsum(dt, e->atv(e->dlogits), e->a_pad, B, A, gradB(e, e->l_c3), sd));
+    REGAT_TRY(bias_grad(e, sd, e->atv(e->dlogits), e->a_pad, B, A, gradB(e, e->l_c3), &cb_side));
   } else {
-    REGAT_TRY(fc_wgrad(e, sd, e->l_c3, 0, B, 2 * Hd, e->atv(e->hid), 2 * Hd, e->atv(e->dlogits), e->a_pad, true));
+    REGAT_TRY(fc_wgrad(e, sd, e->l_c3, 0, B, 2 * Hd, e->atv(e->hid), 2 * Hd, e->atv(e->dlogits), e->a_pad, true, &cb_side));
   }
   REGAT_TRY(fc_dgrad(e, st, e->l_c3, 0, B, 2 * Hd, e->atv(e->dlogits), e->a_pad, e->atv(e->dhid), 2 * Hd, dt, false, e->atv(e->hid), 2 * Hd));
   REGAT_TRY(fork_to(st, sd, e->ev[3]));                    // dhid ready
-  REGAT_TRY(fc_wgrad(e, sd, e->l_c0, 0, B, Hd, e->atv(e->joint), Hd, e->atv(e->dhid), 2 * Hd, true));
+  REGAT_TRY(fc_wgrad(e, sd, e->l_c0, 0, B, Hd, e->atv(e->joint), Hd, e->atv(e->dhid), 2 * Hd, true, &cb_side));
   REGAT_TRY(fc_dgrad(e, st, e->l_c0, 0, B, Hd, e->atv(e->dhid), 2 * Hd, e->atv(e->djoint), Hd, dt, false));
   // joint = pv * qe
   REGAT_TRY(k_mul_bwd(dt, e->atv(e->djoint), Hd, e->atv(e->pv), Hd, e->at<unsigned char>(e->uqe) + (size_t)Hd * es, 2 * Hd,
                       e->atv(e->dpv), Hd, dqe, 2 * Hd, B, Hd, st));
   REGAT_TRY(fork_to(st, sd, e->ev[4]));                    // dpv, dqe ready
-  REGAT_TRY(fc_wgrad(e, sd, e->l_ve, 0, B, D, e->atv(e->pooled), D, e->atv(e->dpv), Hd, true));
+  REGAT_TRY(fc_wgrad(e, sd, e->l_ve, 0, B, D, e->atv(e->pooled), D, e->atv(e->dpv), Hd, true, &cb_side));
   REGAT_TRY(fc_dgrad(e, st, e->l_ve, 0, B, D, e->atv(e->dpv), Hd, e->atv(e->dpooled), D, dt, false));
   // attention pooling
   REGAT_TRY(regat_butd_pool_bwd(dt, B, N, D, e->atv(e->v1), e->atv(e->weff), e->at<float>(e->att), e->atv(e->dpooled),
@@ -503,13 +510,13 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
     // [dW_qa | dW_qe] = q_last^T [du | dqe]  (one GEMM scattered into the two kernels' gradient slots);  dq_last = [du|dqe] [W_qa|W_qe]^T
     const long long offs[2] = {0, e->layers[e->l_qe].v_off - e->layers[e->l_qa].v_off};
     REGAT_TRY(gemm_tc(1, 0, Q, 2 * Hd, B, qlast, Q, e->atv(e->duqe), 2 * Hd, gradW(e, e->l_qa), Hd, REGAT_F32, epi0(), 1, sd, Hd, offs));
-    REGAT_TRY(k_colsum(dt, e->atv(e->duqe), 2 * Hd, B, Hd, gradB(e, e->l_qa), sd));
-    REGAT_TRY(k_colsum(dt, dqe, 2 * Hd, B, Hd, gradB(e, e->l_qe), sd));
+    REGAT_TRY(bias_grad(e, sd, e->atv(e->duqe), 2 * Hd, B, Hd, gradB(e, e->l_qa), &cb_side));
+    REGAT_TRY(bias_grad(e, sd, dqe, 2 * Hd, B, Hd, gradB(e, e->l_qe), &cb_side));
     if (dq_last)
       REGAT_TRY(dense(e, sd, false, true, B, Q, 2 * Hd, e->atv(e->duqe), 2 * Hd, lowp_at(e, e->guqe_off), 2 * Hd, dq_last, Q, REGAT_F32, epi0()));
   } else {
-    REGAT_TRY(fc_wgrad(e, sd, e->l_qa, 0, B, Q, qlast, Q, e->atv(e->duqe), 2 * Hd, true));
-    REGAT_TRY(fc_wgrad(e, sd, e->l_qe, 0, B, Q, qlast, Q, dqe, 2 * Hd, true));
+    REGAT_TRY(fc_wgrad(e, sd, e->l_qa, 0, B, Q, qlast, Q, e->atv(e->duqe), 2 * Hd, true, &cb_side));
+    REGAT_TRY(fc_wgrad(e, sd, e->l_qe, 0, B, Q, qlast, Q, dqe, 2 * Hd, true, &cb_side));
     if (dq_last) {
       REGAT_TRY(fc_dgrad(e, sd, e->l_qa, 0, B, Q, e->atv(e->duqe), 2 * Hd, dq_last, Q, REGAT_F32, false));
       REGAT_TRY(fc_dgrad(e, sd, e->l_qe, 0, B, Q, dqe, 2 * Hd, dq_last, Q, REGAT_F32, true));
@@ -527,6 +534,7 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
     const Layer& LL = e->layers[e->l_label];
     REGAT_TRY(k_label_grad(scal + 1, e->grads, LL.v_off, LL.b_off, st));
   }
+  REGAT_TRY(k_colsum_multi(dt, cb_side, sd));
   REGAT_TRY(fork_to(sd, st, e->ev[0]));   // join the side stream: BUTD + classifier gradients (the tail of the flat buffer) are final
   grads_ready(e, e->l_va, e->l_c3);
   if (dt == REGAT_BF16 && e->use_tc) {
@@ -542,9 +550,9 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
     REGAT_TRY(gemm_tc(1, 0, D, 2 * dirs * D, Rm, e->atv(e->strunc), D, e->atv(e->dKVb), 2 * dirs * D, gradW(e, e->l_k[0]), D, REGAT_F32, epi0(), 1,
                       st, D, kvo));
     for (int d = 0; d < dirs; ++d) {
-      REGAT_TRY(k_colsum(dt, e->at<unsigned char>(e->dQb) + (size_t)d * D * es, dirs * D, R, D, gradB(e, e->l_q[d]), st));
-      REGAT_TRY(k_colsum(dt, e->at<unsigned char>(e->dKVb) + (size_t)d * D * es, 2 * dirs * D, Rm, D, gradB(e, e->l_k[d]), st));
-      REGAT_TRY(k_colsum(dt, e->at<unsigned char>(e->dKVb) + (size_t)(dirs + d) * D * es, 2 * dirs * D, Rm, D, gradB(e, e->l_out[d]), st));
+      REGAT_TRY(bias_grad(e, st, e->at<unsigned char>(e->dQb) + (size_t)d * D * es, dirs * D, R, D, gradB(e, e->l_q[d]), &cb_mid));
+      REGAT_TRY(bias_grad(e, st, e->at<unsigned char>(e->dKVb) + (size_t)d * D * es, 2 * dirs * D, Rm, D, gradB(e, e->l_k[d]), &cb_mid));
+      REGAT_TRY(bias_grad(e, st, e->at<unsigned char>(e->dKVb) + (size_t)(dirs + d) * D * es, 2 * dirs * D, Rm, D, gradB(e, e->l_out[d]), &cb_mid));
     }
     EpiArgs ep = epi0();
     ep.accumulate = 1;                                 // ds already holds dout
@@ -556,19 +564,20 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
       unsigned char* dQd = e->at<unsigned char>(e->dQb) + (size_t)d * D * es;
       unsigned char* dKd = e->at<unsigned char>(e->dKVb) + (size_t)d * D * es;
       unsigned char* dVd = e->at<unsigned char>(e->dKVb) + (size_t)(dirs + d) * D * es;
-      REGAT_TRY(fc_wgrad(e, st, e->l_q[d], 0, R, D, e->atv(e->s), D, dQd, dirs * D, true));
+      REGAT_TRY(fc_wgrad(e, st, e->l_q[d], 0, R, D, e->atv(e->s), D, dQd, dirs * D, true, &cb_mid));
       REGAT_TRY(fc_dgrad(e, st, e->l_q[d], 0, R, D, dQd, dirs * D, e->atv(e->ds), D, dt, true));
-      REGAT_TRY(fc_wgrad(e, st, e->l_k[d], 0, Rm, D, e->atv(e->strunc), D, dKd, 2 * dirs * D, true));
+      REGAT_TRY(fc_wgrad(e, st, e->l_k[d], 0, Rm, D, e->atv(e->strunc), D, dKd, 2 * dirs * D, true, &cb_mid));
       REGAT_TRY(fc_dgrad(e, st, e->l_k[d], 0, Rm, D, dKd, 2 * dirs * D, e->atv(e->dstrunc), D, dt, d > 0));
-      REGAT_TRY(fc_wgrad(e, st, e->l_out[d], 0, Rm, D, e->atv(e->strunc), D, dVd, 2 * dirs * D, true));
+      REGAT_TRY(fc_wgrad(e, st, e->l_out[d], 0, Rm, D, e->atv(e->strunc), D, dVd, 2 * dirs * D, true, &cb_mid));
       REGAT_TRY(fc_dgrad(e, st, e->l_out[d], 0, Rm, D, dVd, 2 * dirs * D, e->atv(e->dstrunc), D, dt, true));
     }
   }
   REGAT_TRY(k_addrows(dt, e->atv(e->ds), e->atv(e->dstrunc), B, N, M, D, st));
   // self_weights: s = alpha (v0 Ws[:D] + mask (q Ws[D:])) + b
-  REGAT_TRY(fc_wgrad(e, st, e->l_self, 0, R, D, v0, D, e->atv(e->ds), D, true));
+  REGAT_TRY(fc_wgrad(e, st, e->l_self, 0, R, D, v0, D, e->atv(e->ds), D, true, &cb_mid));
   REGAT_TRY(k_segsum(dt, e->atv(e->ds), e->at<float>(e->mask), B, N, D, e->atv(e->dsq), st));
   REGAT_TRY(fc_wgrad(e, st, e->l_self, D, B, Q, qatt, Q, e->atv(e->dsq), D, false));
+  REGAT_TRY(k_colsum_multi(dt, cb_mid, st));
   grads_ready(e, e->l_self, e->l_va - 1);   // self_weights, label FC and both attention layers
   if (dq_att) REGAT_TRY(fc_dgrad(e, st, e->l_self, D, B, Q, e->atv(e->dsq), D, dq_att, Q, REGAT_F32, false));
   if (e->l_v2out >= 0) {

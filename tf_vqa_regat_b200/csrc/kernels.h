@@ -43,6 +43,15 @@ int k_butd_prep_bwd(int dt, const void* duw, const float* dcb, const void* u, in
                     int Hd, cudaStream_t st);
 int k_bce(int B, int A, const float* logits, int ldl, const float* target, float gscale, float* loss, float* score,
           void* dlog, int ldd, int d_dtype, cudaStream_t st);
+constexpr int COLSUM_SLAB = 128;     // rows per block of the batched column-sum kernel
+struct ColsumBatch {
+  int n = 0;
+  const void* x[12]; float* out[12];
+  int ld[12], rows[12], cols[12];
+  int slab_start[13];
+  void add(const void* xp, int ldp, int r, int c, float* o) { if (o && r > 0) { x[n] = xp; ld[n] = ldp; rows[n] = r; cols[n] = c; out[n] = o; ++n; } }
+};
+int k_colsum_multi(int dt, ColsumBatch& cb, cudaStream_t st);
 int k_colsum(int dt, const void* x, int ld, int rows, int cols, float* out, cudaStream_t st);
 int k_segsum(int dt, const void* x, const float* w, int B, int N, int D, void* out, cudaStream_t st);
 int k_addrows(int dt, void* dst, const void* src, int B, int N, int M, int D, cudaStream_t st);

@@ -436,6 +436,51 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, in
     }
   }
 }
+// Several column-sum problems in one launch (the bias gradients of one backward stage).  blockIdx.y walks the row slabs of all
+// problems back to back; each block sums a slab of 128 rows x 256 columns with 8 independent 16-byte loads in flight per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_multi_kernel(ColsumBatch cb) {
+  __shared__ float red[8][32][8];
+  int pi = 0;
+  while (pi + 1 < cb.n && (int)blockIdx.y >= cb.slab_start[pi + 1]) ++pi;
+  const T* x = static_cast<const T*>(cb.x[pi]);
+  const int ld = cb.ld[pi], rows = cb.rows[pi], cols = cb.cols[pi];
+  float* out = cb.out[pi];
+  const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cg) * 8;
+  if (blockIdx.x * 256 >= cols) return;
+  const int r0 = ((int)blockIdx.y - cb.slab_start[pi]) * COLSUM_SLAB, r1 = min(rows, r0 + COLSUM_SLAB);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < cols) {
+    int r = r0 + rl;
+    for (; r + 56 < r1; r += 64) {
+      float v[8][8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) ld8<T>(x + (size_t)(r + 8 * u) * ld + c, v[u]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += ((v[0][k] + v[1][k]) + (v[2][k] + v[3][k])) + ((v[4][k] + v[5][k]) + (v[6][k] + v[7][k]));
+    }
+    for (; r < r1; r += 8) {
+      float v0[8];
+      ld8<T>(x + (size_t)r * ld + c, v0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v0[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[rl][cg][k] = acc[k];
+  __syncthreads();
+  if (rl == 0 && c < cols) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float sum = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += red[j][cg][k];
+      if (c + k < cols) atomicAdd(out + c + k, sum);
+    }
+  }
+}
+
 // generic fallback (unaligned / ld not a multiple of 8)
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_scalar_kernel(const T* __restrict__ x, int ld, int rows, int cols, float* out) {
@@ -688,6 +733,22 @@ int k_colsum(int dt, const void* x, int ld, int rows, int cols, float* out, cuda
     dim3 grid(ceil_div(cols, 256), slabs);
     DISPATCH_T(dt, (colsum_scalar_kernel<T><<<grid, 256, 0, st>>>(static_cast<const T*>(x), ld, rows, cols, out)));
   }
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+// all problems must be 16-byte aligned with ld and cols multiples of 8; others go through k_colsum
+int k_colsum_multi(int dt, ColsumBatch& cb, cudaStream_t st) {
+  if (cb.n == 0) return REGAT_OK;
+  int slabs = 0, maxcols = 0;
+  for (int i = 0; i < cb.n; ++i) {
+    REGAT_REQUIRE(aligned16(cb.x[i]) && cb.ld[i] % 8 == 0 && cb.cols[i] % 8 == 0, REGAT_ERR_ALIGN, "colsum_multi: unaligned problem %d", i);
+    cb.slab_start[i] = slabs;
+    slabs += ceil_div(cb.rows[i], COLSUM_SLAB);
+    maxcols = std::max(maxcols, cb.cols[i]);
+  }
+  cb.slab_start[cb.n] = slabs;
+  dim3 grid(ceil_div(maxcols, 256), slabs);
+  DISPATCH_T(dt, (colsum_multi_kernel<T><<<grid, 256, 0, st>>>(cb)));
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }

@@ -103,3 +103,45 @@ class DataParallelTrainer:
         out = self.fwd_bwd_allreduce(features, boxes, q_att, q_last, target)
         self.engine.update(lr, self.step_count)
         return out
+
+
+class GraphedDPStep:
+    """CUDA-graph replay of the data-parallel forward+backward for ONE fixed set of input tensors, without putting NCCL inside
+    a graph: the engine's gradient-ready callbacks split the capture into compute-only segments; on replay the bucketed
+    all-reduces are issued eagerly on the comm stream between the segments (so they still overlap the following segment)."""
+
+    def __init__(self, trainer: DataParallelTrainer, features, boxes, q_att, q_last, target, stream):
+        self.tr, self.stream = trainer, stream
+        eng = trainer.engine
+        self.graphs, self.ranges = [torch.cuda.CUDAGraph()], []
+        pool = torch.cuda.graph_pool_handle()
+
+        def on_ready(offset, numel):               # called from inside fwd_bwd while it is being captured
+            self.graphs[-1].capture_end()
+            self.ranges.append((offset, numel))
+            self.graphs.append(torch.cuda.CUDAGraph())
+            self.graphs[-1].capture_begin(pool=pool)
+
+        eng.set_grad_callback(on_ready)
+        try:
+            with torch.cuda.stream(stream):
+                self.graphs[0].capture_begin(pool=pool)
+                eng.fwd_bwd(features, boxes, q_att, q_last, target, grad_scale=1.0 / trainer.world)
+                self.graphs[-1].capture_end()
+        finally:
+            eng.set_grad_callback(trainer._on_ready if trainer.overlap else None)
+        assert sum(n for _, n in self.ranges) == eng.grads.numel(), "gradient-ready ranges do not cover the flat buffer"
+
+    def replay(self):
+        """Enqueue on self.stream (must be the current stream): segments + overlapped all-reduces; joined at the end."""
+        tr = self.tr
+        for k, g in enumerate(self.graphs):
+            g.replay()
+            if k < len(self.ranges):
+                off, n = self.ranges[k]
+                ev = torch.cuda.Event()
+                ev.record(self.stream)
+                tr.comm_stream.wait_event(ev)
+                with torch.cuda.stream(tr.comm_stream):
+                    tr._allreduce_range(off, n)
+        self.stream.wait_stream(tr.comm_stream)
