@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 METRIC = "graphs/sec fwd+bwd (K=36, batch 256)"
+TRAIN_MFLOP = {"train36": 1734.0, "adaptive100": 3828.7, "eval100": 1416.0}   # SURVEY 8d per-graph algorithmic MFLOP
 UNIT = "graphs/s"
 TRAIN_MFLOP_PER_GRAPH = 1734.0      # SURVEY 8d, N=36, nongt=20, cheapest equivalent formulation
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
@@ -120,6 +121,9 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="graphs per GPU per step")
     ap.add_argument("--rois", type=int, default=36)
     ap.add_argument("--cpu-sample", type=int, default=16, help="graphs per CPU-baseline step")
+    ap.add_argument("--workload", default="train36", choices=["train36", "adaptive100", "eval100"],
+                    help="train36 = BASELINE configs[1] (headline); adaptive100 = configs[2] (K=10..100 zero-padded, train); "
+                         "eval100 = configs[4] (forward only, batch 128/GPU, K=100 adaptive)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--comm-dtype", default="auto", choices=["auto", "fp32", "bf16"], help="gradient all-reduce precision (auto = engine dtype)")
@@ -127,6 +131,11 @@ def main():
     ap.add_argument("--lr", type=float, default=9e-4)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    if args.workload != "train36":
+        args.rois = 100
+        args.no_cpu_baseline = True
+        if args.workload == "eval100":
+            args.batch = 128
     if args.impl == "reference":
         return run_reference(args)
 
@@ -149,11 +158,13 @@ def main():
     peaks = load_peaks()
     cfg = HotPathConfig()
     B, N = args.batch, args.rois
-    eng = HotPathEngine(cfg, B, N, dtype=args.dtype, device=dev)
+    adaptive = args.workload != "train36"
+    eval_only = args.workload == "eval100"
+    eng = HotPathEngine(cfg, B, N, dtype=args.dtype, device=dev, training=not eval_only)
     eng.load_params(syn.make_params(cfg, seed=7, trained_like=True))     # same weights on every rank
 
     # two distinct synthetic batches per rank, pinned on the host and resident on the device
-    host = [{k: torch.from_numpy(v).pin_memory() for k, v in syn.make_inputs(cfg, B, N, seed=1001 + 17 * rank + i).items()
+    host = [{k: torch.from_numpy(v).pin_memory() for k, v in syn.make_inputs(cfg, B, N, seed=1001 + 17 * rank + i, adaptive=adaptive).items()
              if k != "n_obj"} for i in range(2)]
     order = ("features", "boxes", "q_att", "q_last", "target")
     devb = [{k: h[k].to(dev) for k in order} for h in host]
@@ -164,18 +175,25 @@ def main():
 
     from tf_vqa_regat_b200.dp import DataParallelTrainer
     # data parallel: bucketed gradient all-reduce on a side stream, started from inside the backward pass (dp.py)
-    trainer = DataParallelTrainer(eng, overlap=not args.no_overlap, comm_dtype=args.comm_dtype) if world > 1 else None
+    trainer = DataParallelTrainer(eng, overlap=not args.no_overlap, comm_dtype=args.comm_dtype) if (world > 1 and not eval_only) else None
     if trainer:
         trainer.broadcast_params(0)
 
+    logits_buf = torch.empty(B, cfg.num_answers, device=dev) if eval_only else None
+
     def fwd_bwd(slot):
         b = devb[slot]
-        if trainer:
+        if eval_only:
+            eng.lib.regat_engine_forward(eng._h, B, N, b["features"].data_ptr(), b["boxes"].data_ptr(), b["q_att"].data_ptr(),
+                                         b["q_last"].data_ptr(), logits_buf.data_ptr(), None, torch.cuda.current_stream().cuda_stream)
+        elif trainer:
             trainer.fwd_bwd_allreduce(b["features"], b["boxes"], b["q_att"], b["q_last"], b["target"])
         else:
             eng.fwd_bwd(b["features"], b["boxes"], b["q_att"], b["q_last"], b["target"], grad_scale=1.0)
 
     def update():
+        if eval_only:
+            return
         step_no[0] += 1
         eng.update(lr, step_no[0])
 
@@ -190,13 +208,13 @@ def main():
                 fwd_bwd(slot)           # warm: creates tensor maps, sets smem attributes
             launches_per_step[0] = eng.last_launches()
             torch.cuda.synchronize()
-            if not args.no_graph and world == 1:
+            if not args.no_graph and (world == 1 or eval_only):
                 for slot in range(2):
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=main_stream):
                         fwd_bwd(slot)
                     graphs[slot] = g
-            elif not args.no_graph and trainer.overlap:
+            elif not args.no_graph and trainer is not None and trainer.overlap:
                 # N>1: compute-only graph segments split at the gradient-ready points, NCCL eagerly in between (dp.GraphedDPStep)
                 from tf_vqa_regat_b200.dp import GraphedDPStep
                 for slot in range(2):
@@ -212,7 +230,7 @@ def main():
         update()
 
     build_graphs()
-    update_launches = 2
+    update_launches = 0 if eval_only else 3
 
     def barrier():
         if world > 1:
@@ -244,7 +262,7 @@ def main():
         sampler.start()
     ms = timed(lambda i: one_step(i & 1), args.steps)
     value = world * B * args.steps / (ms * 1e-3)
-    loss_end = float(eng._loss[0])
+    loss_end = float(eng._loss[0]) if not eval_only else None
 
     # ---------------- end-to-end timing: pinned host inputs -> device every step, loss -> host every step
     copy_stream = torch.cuda.Stream(dev)
@@ -266,7 +284,7 @@ def main():
             prefetch(i + 1)
         main_stream.wait_event(ready[slot])
         one_step(slot)
-        loss_host[slot].copy_(eng._loss, non_blocking=True)    # device -> host read of this step's loss and score
+        loss_host[slot].copy_(eng._loss if not eval_only else logits_buf[0, :2], non_blocking=True)    # device -> host read of the step's result
         done[slot].record(main_stream)
         if i > 0:
             done[slot ^ 1].synchronize()                       # host really consumes the previous step's loss
@@ -315,12 +333,12 @@ def main():
         if os.path.exists(tp):
             with open(tp) as f:
                 traffic = json.load(f).get("gemm_v2out_dram_bytes_per_launch")
-        roofline = {"bound": "tensor", "kernel": "gemm_tc_kernel<256,4> v2out 9216x1024x2048 bf16 (+alpha,bias,relu)",
+        roofline = {"bound": "tensor", "kernel": f"gemm_tc_kernel<256,4,2> v2out {M_}x{N_}x{K_} bf16 (+alpha,bias,relu)",
                     "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": (tflops / peak) if peak else None,
                     "peak_source": peaks["_source"] + " (burst, kernel timed alone)", "launch_ms": t_ms, "traffic": traffic}
         del As, Cs
         # whole-step view against the sustained peak (SURVEY 8d algorithmic FLOPs)
-        step_tflops = TRAIN_MFLOP_PER_GRAPH * 1e6 * (value / world) / 1e12
+        step_tflops = TRAIN_MFLOP[args.workload] * 1e6 * (value / world) / 1e12
         roofline["step_tensor_frac_of_sustained"] = step_tflops / peaks["bf16_tflops_sustained"]
         roofline["step_algorithmic_tflops_per_gpu"] = step_tflops
 
@@ -336,11 +354,13 @@ def main():
                                   f"{B}, plus one clip+Adamax over 19.0M parameters; best of {n}"}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        line = {"metric": METRIC if args.workload == "train36" else f"graphs/sec ({args.workload})", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.dtype if args.dtype == "bf16" else "f32", "data": "synthetic",
-                "config": {"workload": f"implicit relation + BUTD train step, batch {B}/GPU, K={N}, 16 heads, nongt_dim 20, "
-                                       f"V=2048 D=1024 Q=768 A=3129 (BASELINE.json configs[1])",
+                "config": {"workload": {"train36": f"implicit relation + BUTD train step, batch {B}/GPU, K={N}, 16 heads, nongt_dim 20, "
+                                                    f"V=2048 D=1024 Q=768 A=3129 (BASELINE.json configs[1])",
+                                        "adaptive100": f"train step, adaptive K=10..100 zero-padded to {N}, batch {B}/GPU (BASELINE.json configs[2])",
+                                        "eval100": f"eval forward bf16, batch {B}/GPU, K=100 adaptive (BASELINE.json configs[4])"}[args.workload],
                            "parallelism": f"dp{world}", "global_batch": B * world, "cuda_graph": bool(graphs),
                            "allreduce": (None if world == 1 else (("3 buckets overlapped with backward" if trainer.overlap else "single, after backward") + ", " + trainer.comm_dtype)),
                            "l2": "per-step working set ~0.8 GB (activations + 4x76 MB parameter/optimizer state) >> 126 MB L2; "
