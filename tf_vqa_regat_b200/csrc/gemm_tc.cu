@@ -10,8 +10,13 @@
 //   K-major  tile: rows x 64 bf16 (128 B per row), 8-row swizzle atoms: SBO = 1024 B, +32 B per UMMA_K
 //   MN-major tile: 64-element MN chunks of [64 K-rows x 128 B]: LBO = 8192 B (next chunk), SBO = 1024 B
 //                  (next 8 K-rows), +2048 B per UMMA_K
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2-5 = epilogue
-// (warp w reads TMEM lanes 32*(w%4)..).  Every mbarrier wait is bounded and traps instead of hanging.
+// Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2.. = EPIW (4 or 8) epilogue warps
+// (warp w reads TMEM lanes 32*(w%4)..; with 8, the two warps of a lane quarter interleave the 32-column blocks).  Every mbarrier wait is bounded and traps instead of hanging.
+// Epilogue data path: tcgen05.ld hands each thread one accumulator ROW, which is the wrong shape for global memory
+// (a warp store would touch 32 different lines).  Each epilogue warp therefore transposes 32x32 fp32 blocks through a
+// private 4 KB XOR-swizzled shared-memory patch: row-per-lane in, 8 lanes per 128-byte row out, so every global access
+// of the fused epilogue (C, accumulate, gate, addend, second output, split-K reductions) is a run of full 32-byte
+// sectors, and the next block's tcgen05.ld is in flight while the current one drains.
 #include <cuda.h>
 
 #include <algorithm>
@@ -26,8 +31,8 @@ namespace regat {
 namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
-constexpr int NTHREADS = 192;
 constexpr uint32_t SPIN_LIMIT = 1u << 27;
+constexpr int EPI_PATCH_BYTES = 32 * 32 * 4;   // one 32x32 fp32 transpose patch per epilogue warp
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -43,6 +48,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
   for (uint32_t spin = 0; spin < SPIN_LIMIT; ++spin) {
     uint32_t done;
     asm volatile(
@@ -83,8 +89,7 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -94,10 +99,59 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// the "+r" ties keep every use of the loaded registers behind the wait
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// C / gate / c2 arrive as generic pointers; they are global memory by contract, and saying so keeps the accesses off the
+// generic path (which the compiler must order against the shared-memory patch)
+__device__ __forceinline__ void stg_v4(void* p, float4 v) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
+}
+__device__ __forceinline__ void stg_v2(void* p, uint2 v) {
+  asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y));
+}
+__device__ __forceinline__ float4 ldg_v4(const void* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_nc_v4(const void* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint2 ldg_nc_v2(const void* p) {
+  uint2 v;
+  asm volatile("ld.global.nc.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ uint2 ldg_v2(const void* p) {
+  uint2 v;
+  asm volatile("ld.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
 // shared-memory matrix descriptor (tcgen05 / "UMMA"): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout SWIZZLE_128B = 2 at [61,64)
@@ -121,22 +175,44 @@ struct TcParams {
   int M, N, K, ldc, c_f32, k_blocks_per_split, total_k_blocks, atomic_out, tiles_m, tiles_n, splits;
   int c_block_cols;               // > 0: column block j = c / c_block_cols of C lives at C + c_block_off[j] (fp32 outputs only)
   long long c_block_off[8];
+  long long c_block_off_or;       // OR of all block offsets (alignment test)
   void* C;
   EpiArgs e;
 };
 
+// Generic per-element epilogue for ragged edges and unaligned tensors (4 consecutive columns of one row).
+__device__ __noinline__ void epi_slow(const TcParams& p, int r, int c, float4 x) {
+  const float xs[4] = {x.x, x.y, x.z, x.w};
+  for (int j = 0; j < 4 && c + j < p.N; ++j) {
+    if (p.atomic_out) {
+      float y = xs[j];
+      if (p.e.alpha) y *= p.e.alpha[p.e.alpha_cols ? (c + j) / p.e.alpha_cols : 0];
+      int cj = c + j;
+      long long off = 0;
+      if (p.c_block_cols) { const int jb = cj / p.c_block_cols; off = p.c_block_off[jb]; cj -= jb * p.c_block_cols; }
+      atomicAdd(static_cast<float*>(p.C) + off + (size_t)r * p.ldc + cj, y);
+    } else if (p.c_f32) {
+      epi_store<float>(p.e, r, c + j, xs[j], static_cast<float*>(p.C), p.ldc);
+    } else {
+      epi_store<bf16>(p.e, r, c + j, xs[j], static_cast<bf16*>(p.C), p.ldc);
+    }
+  }
+}
+
 // Persistent: CTA c processes work units c, c+grid, ... where a unit = (m-tile, n-tile, k-split), n fastest so that
 // concurrently running CTAs share A rows in L2.  ACC accumulator stages in TMEM (ACC*BN <= 512 columns) let the epilogue
 // of unit i overlap the MMAs of unit i+1.
-template <int BN, int STAGES, int ACC, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                           const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+template <int BN, int STAGES, int ACC, int EPIW, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                           const __grid_constant__ CUtensorMap mapB, const __grid_constant__ TcParams p) {
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = ACC * BN;
   static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* tiles = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
+  unsigned char* tiles = smem;            // SWIZZLE_128B tiles need 1024-byte alignment: the dynamic window provides it (checked)
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  float* stage = reinterpret_cast<float*>(tiles + STAGES * STAGE_BYTES);                 // EPIW epilogue warps x 4 KB
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES + EPIW * EPI_PATCH_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;       // [ACC]
   uint64_t* tmem_empty = tmem_full + ACC;         // [ACC]
@@ -150,7 +226,7 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int a = 0; a < ACC; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, 4); }
+    for (int a = 0; a < ACC; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, EPIW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
@@ -228,164 +304,196 @@ __global__ void __launch_bounds__(NTHREADS) gemm_tc_kernel(const __grid_constant
       }
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> fused epilogue -> global =====
+    // ===== epilogue: TMEM -> registers -> swizzled smem patch -> fused epilogue -> coalesced global =====
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    int ui = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
-    int m0, n0, kb0, kb1;
-    decode(u, m0, n0, kb0, kb1);
-    const int acc_stage = ui % ACC;
-    mbar_wait(tmem_full + acc_stage, (ui / ACC) & 1);
-    tc_fence_after();
-    const uint32_t tmem_acc = tmem_base + (uint32_t)(acc_stage * BN);
-    const int r = m0 + q * 32 + lane;
-    const bool row_ok = r < p.M && kb1 > kb0;
-    const int rc = min(r, p.M - 1);
-    // per-row epilogue terms, hoisted out of the column loop
-    const float rs = (p.e.addend && p.e.row_scale) ? __ldg(p.e.row_scale + rc) : 1.f;
-    const float* arow = p.e.addend ? p.e.addend + (size_t)(rc / p.e.addend_rows) * p.e.addend_ld : nullptr;
-    const float alpha0 = (p.e.alpha && p.e.alpha_cols == 0) ? __ldg(p.e.alpha) : 1.f;
-    int r2 = -1;
-    if (p.e.c2) {
-      const int rr = rc % p.e.c2_rows_in;
-      if (rr < p.e.c2_rows_keep) r2 = (rc / p.e.c2_rows_in) * p.e.c2_rows_keep + rr;
-    }
-    // fast path needs 16-byte aligned rows for every tensor touched with vector accesses
+    float* patch = stage + (warp - 2) * (32 * 32);          // this warp's 32 x 32 fp32 transpose patch
+    const int lr = lane >> 3, lc = lane & 7; // drain phase: lane handles the 16-byte column group lc of rows lr + 4 i
     const size_t esz = p.c_f32 ? 4 : 2;
+    // vector path needs 16-byte aligned rows for every tensor touched with vector accesses
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.C) | ((size_t)p.ldc * esz)) & 15) == 0 &&
                         (!p.e.bias || (reinterpret_cast<uintptr_t>(p.e.bias) & 15) == 0) &&
                         (!p.e.addend || ((reinterpret_cast<uintptr_t>(p.e.addend) | ((size_t)p.e.addend_ld * 4)) & 15) == 0) &&
                         (!p.e.gate || ((reinterpret_cast<uintptr_t>(p.e.gate) | ((size_t)p.e.gate_ld * esz)) & 15) == 0) &&
                         (!p.e.c2 || ((reinterpret_cast<uintptr_t>(p.e.c2) | ((size_t)p.e.c2_ld * esz)) & 15) == 0) &&
-                        (p.e.alpha_cols % 32 == 0);
-#pragma unroll 1
-    for (int cc = 0; cc < BN / 32; ++cc) {
-      float v[32];
-      tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(cc * 32), v);
-      const int c0 = n0 + cc * 32;
-      if (!row_ok || c0 >= p.N) continue;
-      if (p.atomic_out) {
-        float* C = static_cast<float*>(p.C);
-        int cl = c0;
-        if (p.c_block_cols) { const int jb = c0 / p.c_block_cols; C += p.c_block_off[jb]; cl = c0 - jb * p.c_block_cols; }
+                        (p.e.alpha_cols % 32 == 0) && (p.c_block_off_or & 3) == 0;
+    const float alpha0 = (p.e.alpha && p.e.alpha_cols == 0) ? __ldg(p.e.alpha) : 1.f;
+    int ui = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
+      int m0, n0, kb0, kb1;
+      decode(u, m0, n0, kb0, kb1);
+      const int acc_stage = ui % ACC;
+      mbar_wait(tmem_full + acc_stage, (ui / ACC) & 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc_stage * BN) + ((uint32_t)(q * 32) << 16);
+      const int rbase = m0 + q * 32;
+      // 32-column blocks this warp really has to move (none if its rows or the unit's K range are empty)
+      const int nblk = (rbase < p.M && kb1 > kb0) ? min(BN / 32, (p.N - n0 + 31) / 32) : 0;
+      // per-row terms of the 8 rows this lane drains, hoisted out of the column loop
+      float rs[8];
+      int arow[8], r2[8];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < p.N) {
-            float x = v[j];
-            if (p.e.alpha) x *= p.e.alpha[p.e.alpha_cols ? (c0 + j) / p.e.alpha_cols : 0];
-            atomicAdd(C + (size_t)r * p.ldc + cl + j, x);
-          }
-      } else if (vec_ok && c0 + 32 <= p.N) {
-        // ---- vectorised, branch-free path: every load is issued before its first use
-        if (arow) {
-          const float4* ap = reinterpret_cast<const float4*>(arow + c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 a = __ldg(ap + j);
-            v[4 * j] = fmaf(rs, a.x, v[4 * j]); v[4 * j + 1] = fmaf(rs, a.y, v[4 * j + 1]);
-            v[4 * j + 2] = fmaf(rs, a.z, v[4 * j + 2]); v[4 * j + 3] = fmaf(rs, a.w, v[4 * j + 3]);
-          }
+      for (int i = 0; i < 8; ++i) {
+        const int r = min(rbase + lr + 4 * i, p.M - 1);
+        rs[i] = (p.e.addend && p.e.row_scale) ? __ldg(p.e.row_scale + r) : 1.f;
+        arow[i] = p.e.addend ? (r / p.e.addend_rows) * p.e.addend_ld : 0;
+        r2[i] = -1;
+        if (p.e.c2) {
+          const int rr = r % p.e.c2_rows_in;
+          if (rr < p.e.c2_rows_keep) r2[i] = (r / p.e.c2_rows_in) * p.e.c2_rows_keep + rr;
         }
-        const float al = p.e.alpha ? (p.e.alpha_cols ? __ldg(p.e.alpha + c0 / p.e.alpha_cols) : alpha0) : 1.f;
-        if (p.e.bias) {
-          const float4* bp = reinterpret_cast<const float4*>(p.e.bias + c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bb = __ldg(bp + j);
-            v[4 * j] = fmaf(v[4 * j], al, bb.x); v[4 * j + 1] = fmaf(v[4 * j + 1], al, bb.y);
-            v[4 * j + 2] = fmaf(v[4 * j + 2], al, bb.z); v[4 * j + 3] = fmaf(v[4 * j + 3], al, bb.w);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= al;
-        }
-        if (p.e.relu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        if (p.c_f32) {
-          float* dst = static_cast<float*>(p.C) + (size_t)r * p.ldc + c0;
-          if (p.c_block_cols) {
-            const int jb = c0 / p.c_block_cols;
-            dst = static_cast<float*>(p.C) + p.c_block_off[jb] + (size_t)r * p.ldc + (c0 - jb * p.c_block_cols);
-          }
-          if (p.e.accumulate) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 o = *reinterpret_cast<const float4*>(dst + 4 * j);
-              v[4 * j] += o.x; v[4 * j + 1] += o.y; v[4 * j + 2] += o.z; v[4 * j + 3] += o.w;
-            }
-          }
-          if (p.e.gate) {
-            const float4* gp = reinterpret_cast<const float4*>(static_cast<const float*>(p.e.gate) + (size_t)r * p.e.gate_ld + c0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 g4 = __ldg(gp + j);
-              v[4 * j] = g4.x > 0.f ? v[4 * j] : 0.f; v[4 * j + 1] = g4.y > 0.f ? v[4 * j + 1] : 0.f;
-              v[4 * j + 2] = g4.z > 0.f ? v[4 * j + 2] : 0.f; v[4 * j + 3] = g4.w > 0.f ? v[4 * j + 3] : 0.f;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          if (r2 >= 0) {
-            float* d2 = static_cast<float*>(p.e.c2) + (size_t)r2 * p.e.c2_ld + c0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(d2 + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-        } else {
-          bf16* dst = static_cast<bf16*>(p.C) + (size_t)r * p.ldc + c0;
-          if (p.e.accumulate) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 o = *reinterpret_cast<const uint4*>(dst + 8 * j);
-              const uint32_t w[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                v[8 * j + 2 * k] += __uint_as_float(w[k] << 16);
-                v[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xffff0000u);
-              }
-            }
-          }
-          if (p.e.gate) {
-            const uint4* gp = reinterpret_cast<const uint4*>(static_cast<const bf16*>(p.e.gate) + (size_t)r * p.e.gate_ld + c0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 o = __ldg(gp + j);
-              const uint32_t w[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                v[8 * j + 2 * k] = __uint_as_float(w[k] << 16) > 0.f ? v[8 * j + 2 * k] : 0.f;
-                v[8 * j + 2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u) > 0.f ? v[8 * j + 2 * k + 1] : 0.f;
-              }
-            }
-          }
-          uint32_t w[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
-            w[j] = *reinterpret_cast<uint32_t*>(&h);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + 8 * j) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-          if (r2 >= 0) {
-            bf16* d2 = static_cast<bf16*>(p.e.c2) + (size_t)r2 * p.e.c2_ld + c0;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(d2 + 8 * j) = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-          }
-        }
-      } else if (p.c_f32) {
-        // ---- ragged edge / unaligned: generic per-element path
-        float* C = static_cast<float*>(p.C);
-        for (int j = 0; j < 32 && c0 + j < p.N; ++j) epi_store<float>(p.e, r, c0 + j, v[j], C, p.ldc);
-      } else {
-        bf16* C = static_cast<bf16*>(p.C);
-        for (int j = 0; j < 32 && c0 + j < p.N; ++j) epi_store<bf16>(p.e, r, c0 + j, v[j], C, p.ldc);
       }
-    }
-    // this warp has finished reading the accumulator stage: hand it back to the MMA issuer
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(tmem_empty + acc_stage);
+      uint32_t acc[32];
+      constexpr int CSTEP = EPIW / 4;                      // warps sharing a lane quarter interleave the column blocks
+      const int cfirst = (warp - 2) >> 2;
+      if (cfirst < nblk) tmem_ld32_issue(tmem_acc + (uint32_t)(cfirst * 32), acc);
+#pragma unroll 1
+      for (int cc = cfirst; cc < nblk; cc += CSTEP) {
+        const int c = n0 + cc * 32 + lc * 4;               // first of this lane's 4 columns in the drain phase
+        const bool vec = vec_ok && c + 4 <= p.N;
+        // column terms: issued before the TMEM wait so their latency is hidden
+        float al = alpha0;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (vec) {
+          if (p.e.alpha && p.e.alpha_cols) al = __ldg(p.e.alpha + c / p.e.alpha_cols);
+          if (p.e.bias) bv = __ldg(reinterpret_cast<const float4*>(p.e.bias + c));
+        }
+        tmem_ld32_wait(acc);
+        // transpose in: lane = row, 16-byte group g lands at slot g ^ (row & 7)  (conflict-free both ways)
+        {
+          float4* prow = reinterpret_cast<float4*>(patch + lane * 32);
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            prow[g ^ (lane & 7)] = make_float4(__uint_as_float(acc[4 * g]), __uint_as_float(acc[4 * g + 1]),
+                                               __uint_as_float(acc[4 * g + 2]), __uint_as_float(acc[4 * g + 3]));
+        }
+        if (cc + CSTEP < nblk) {
+          tmem_ld32_issue(tmem_acc + (uint32_t)((cc + CSTEP) * 32), acc);   // overlaps the drain below
+        } else {
+          // every TMEM read of this unit has completed: hand the accumulator stage back to the MMA issuer early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty + acc_stage);
+        }
+        __syncwarp();
+        // column-block scatter (weight gradients of side-by-side layers): block j of C lives at C + c_block_off[j]
+        long long cboff = 0;
+        int cl = c;
+        if (p.c_block_cols) { const int jb = c / p.c_block_cols; cboff = p.c_block_off[jb]; cl = c - jb * p.c_block_cols; }
+        if (!vec) {
+          // ragged edge / unaligned tensors: generic per-element path (kept out of line: it must not bloat the hot loop)
+          if (c < p.N) {
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+              const int rl = lr + 4 * i, r = rbase + rl;
+              if (r < p.M) epi_slow(p, r, c, reinterpret_cast<const float4*>(patch + rl * 32)[lc ^ (rl & 7)]);
+            }
+          }
+        } else {
+          // Staged, branch-free drain: every load of a stage is issued before the first use (shared-memory and global
+          // latencies are paid once per stage, not once per row); rows past M are clamped for loads, predicated for stores.
+          float4 x[8];
+          const uint32_t pbase = smem_u32(patch);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = lr + 4 * i;
+            x[i] = lds_v4(pbase + (uint32_t)(rl * 128 + ((lc ^ (rl & 7)) << 4)));
+          }
+          if (p.e.addend) {
+            float4 a[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = ldg_nc_v4(p.e.addend + arow[i] + c);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              x[i].x = fmaf(rs[i], a[i].x, x[i].x); x[i].y = fmaf(rs[i], a[i].y, x[i].y);
+              x[i].z = fmaf(rs[i], a[i].z, x[i].z); x[i].w = fmaf(rs[i], a[i].w, x[i].w);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            x[i].x = fmaf(x[i].x, al, bv.x); x[i].y = fmaf(x[i].y, al, bv.y); x[i].z = fmaf(x[i].z, al, bv.z); x[i].w = fmaf(x[i].w, al, bv.w);
+          }
+          if (p.e.relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              x[i].x = fmaxf(x[i].x, 0.f); x[i].y = fmaxf(x[i].y, 0.f); x[i].z = fmaxf(x[i].z, 0.f); x[i].w = fmaxf(x[i].w, 0.f);
+            }
+          }
+          const int rows_ok = p.M - rbase - lr;        // row i of this lane is valid iff 4 i < rows_ok
+          const int rcl = min(rbase + lr, p.M - 1);    // clamped first row (loads only)
+          if (p.c_f32) {
+            float* dst0 = static_cast<float*>(p.C) + cboff + cl;
+            if (p.atomic_out) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (4 * i < rows_ok) red_add_v4(dst0 + (size_t)(rbase + lr + 4 * i) * p.ldc, x[i]);
+            } else {
+              if (p.e.accumulate) {
+                float4 o[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) o[i] = ldg_v4(dst0 + (size_t)min(rcl + 4 * i, p.M - 1) * p.ldc);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { x[i].x += o[i].x; x[i].y += o[i].y; x[i].z += o[i].z; x[i].w += o[i].w; }
+              }
+              if (p.e.gate) {
+                const float* g0 = static_cast<const float*>(p.e.gate) + c;
+                float4 g[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) g[i] = ldg_nc_v4(g0 + (size_t)min(rcl + 4 * i, p.M - 1) * p.e.gate_ld);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  x[i].x = g[i].x > 0.f ? x[i].x : 0.f; x[i].y = g[i].y > 0.f ? x[i].y : 0.f;
+                  x[i].z = g[i].z > 0.f ? x[i].z : 0.f; x[i].w = g[i].w > 0.f ? x[i].w : 0.f;
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (4 * i < rows_ok) stg_v4(dst0 + (size_t)(rbase + lr + 4 * i) * p.ldc, x[i]);
+              if (p.e.c2) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                  if (4 * i < rows_ok && r2[i] >= 0) stg_v4(static_cast<float*>(p.e.c2) + (size_t)r2[i] * p.e.c2_ld + c, x[i]);
+              }
+            }
+          } else {
+            bf16* dst0 = static_cast<bf16*>(p.C) + c;
+            if (p.e.accumulate) {
+              uint2 o[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = ldg_v2(dst0 + (size_t)min(rcl + 4 * i, p.M - 1) * p.ldc);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) { x[i].x += bf_lo(o[i].x); x[i].y += bf_hi(o[i].x); x[i].z += bf_lo(o[i].y); x[i].w += bf_hi(o[i].y); }
+            }
+            if (p.e.gate) {
+              const bf16* g0 = static_cast<const bf16*>(p.e.gate) + c;
+              uint2 g[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) g[i] = ldg_nc_v2(g0 + (size_t)min(rcl + 4 * i, p.M - 1) * p.e.gate_ld);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                x[i].x = bf_lo(g[i].x) > 0.f ? x[i].x : 0.f; x[i].y = bf_hi(g[i].x) > 0.f ? x[i].y : 0.f;
+                x[i].z = bf_lo(g[i].y) > 0.f ? x[i].z : 0.f; x[i].w = bf_hi(g[i].y) > 0.f ? x[i].w : 0.f;
+              }
+            }
+            uint2 w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = make_uint2(pack_bf16(x[i].x, x[i].y), pack_bf16(x[i].z, x[i].w));
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (4 * i < rows_ok) stg_v2(dst0 + (size_t)(rbase + lr + 4 * i) * p.ldc, w[i]);
+            if (p.e.c2) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (4 * i < rows_ok && r2[i] >= 0) stg_v2(static_cast<bf16*>(p.e.c2) + (size_t)r2[i] * p.e.c2_ld + c, w[i]);
+            }
+          }
+        }
+        __syncwarp();    // the patch is rewritten by the next block
+      }
+      if (cfirst >= nblk) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty + acc_stage);
+      }
     }  // units
   }
   tc_fence_before();
@@ -441,18 +549,18 @@ int make_map(CUtensorMap* out, const void* base, long long inner, long long oute
   return REGAT_OK;
 }
 
-template <int BN, int STAGES, int ACC>
+template <int BN, int STAGES, int ACC, int EPIW>
 int launch_cfg(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int ctas, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + 1024 /*align slack*/ + (2 * STAGES + 2 * ACC) * 8 + 16;
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + EPIW * EPI_PATCH_BYTES + (2 * STAGES + 2 * ACC) * 8 + 16;
 #define REGAT_TC_CASE(AM, BMN)                                                                              \
   {                                                                                                         \
-    auto kern = gemm_tc_kernel<BN, STAGES, ACC, AM, BMN>;                                                   \
+    auto kern = gemm_tc_kernel<BN, STAGES, ACC, EPIW, AM, BMN>;                                                   \
     static bool attr_set = false;                                                                           \
     if (!attr_set) {                                                                                        \
       REGAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
       attr_set = true;                                                                                      \
     }                                                                                                       \
-    kern<<<ctas, NTHREADS, smem, st>>>(ma, mb, p);                                                          \
+    kern<<<ctas, 64 + 32 * EPIW, smem, st>>>(ma, mb, p);                                                          \
   }
   if (!a_mn && b_mn) REGAT_TC_CASE(false, true)
   else if (!a_mn && !b_mn) REGAT_TC_CASE(false, false)
@@ -502,13 +610,13 @@ int gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int lda,
   TcParams p;
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.c_f32 = c_dtype == REGAT_F32; p.k_blocks_per_split = kbps; p.total_k_blocks = total_kb;
   p.atomic_out = splits > 1; p.C = C; p.e = e;
-  p.c_block_cols = 0;
+  p.c_block_cols = 0; p.c_block_off_or = 0;
   for (int j = 0; j < 8; ++j) p.c_block_off[j] = 0;
   if (c_block_cols > 0) {
     REGAT_REQUIRE(c_dtype == REGAT_F32 && plain && c_block_cols % 32 == 0 && N % c_block_cols == 0 && N / c_block_cols <= 8 && c_block_off,
                   REGAT_ERR_ARG, "gemm_tc: column-block scatter needs a plain fp32 output and <= 8 blocks of a multiple of 32 columns");
     p.c_block_cols = c_block_cols;
-    for (int j = 0; j < N / c_block_cols; ++j) p.c_block_off[j] = c_block_off[j];
+    for (int j = 0; j < N / c_block_cols; ++j) { p.c_block_off[j] = c_block_off[j]; p.c_block_off_or |= c_block_off[j]; }
   }
   if (splits > 1) {   // partials are atomically added: zero the destination(s)
     const int nb = c_block_cols > 0 ? N / c_block_cols : 1, bw = c_block_cols > 0 ? c_block_cols : N;
@@ -521,8 +629,8 @@ int gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int lda,
   // REGAT_SM_RESERVE=n leaves n SMs free of persistent GEMM CTAs so that a concurrent NCCL all-reduce can make progress
   static const int reserve = [] { const char* s = getenv("REGAT_SM_RESERVE"); return s ? std::max(0, atoi(s)) : 0; }();
   const int sms = std::max(1, num_sms() - reserve);
-  if (bn == 256) return launch_cfg<256, 4, 2>(a_mn, b_mn, ma, mb, p, std::min(units, sms), st);
-  return launch_cfg<128, 3, 2>(a_mn, b_mn, ma, mb, p, std::min(units, 2 * sms), st);
+  if (bn == 256) return launch_cfg<256, 4, 2, 8>(a_mn, b_mn, ma, mb, p, std::min(units, sms), st);
+  return launch_cfg<128, 3, 2, 4>(a_mn, b_mn, ma, mb, p, std::min(units, 2 * sms), st);
 }
 
 }  // namespace regat
