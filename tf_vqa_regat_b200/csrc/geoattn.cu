@@ -23,6 +23,7 @@
 //     (head-dim slices over warps) dK, dV' from shared-memory copies; dL overwrites P in place and a
 //     separate pair-tiled kernel reduces dW_g/db_g with recomputed embeddings.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -189,9 +190,11 @@ template <> __device__ __forceinline__ void load8c<bf16>(const bf16* p, float (&
 }
 template <typename T> __device__ __forceinline__ void store_n(T* p, const float* v, int n);  // n multiple of 4 (fp32) / 8 (bf16)
 template <> __device__ __forceinline__ void store_n<float>(float* p, const float* v, int n) {
+#pragma unroll
   for (int i = 0; i < n; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
 }
 template <> __device__ __forceinline__ void store_n<bf16>(bf16* p, const float* v, int n) {
+#pragma unroll
   for (int i = 0; i < n; i += 8) {
     uint32_t w[4];
 #pragma unroll
@@ -535,6 +538,299 @@ __global__ void __launch_bounds__(256, 2) geoattn_fwd_kernel(const FwdParams p) 
           }
         }
         store_n<T>(V1 + off, out, 16);
+      }
+      if (p.gate) {
+        bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+        bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+        if (t == 0 && r < N) p.gate[((size_t)b * N + r) * H + h] = bits;
+      }
+    }
+  }
+}
+
+// ==========================================================================================
+// forward, bf16 fast path (boxes given, M <= 8 NTS).  Same CTA shape and phase structure as geoattn_fwd_kernel, sized for
+// instruction count (the generic kernel is issue-bound at ~270k warp instructions per graph):
+//   * phase 1 only walks the pairs of rows that exist; sin/cos go through a 2-constant Cody-Waite reduction to [-pi, pi]
+//     and the SFU (abs. error 2^-21, below the 1-ulp argument noise at |x| ~ 690 that the reference itself has across NumPy
+//     builds); divisions by the wavelengths become multiplications; the 64 -> dirs*H projection is one TF32 pass;
+//   * phase 2 runs on mma.sync.m16n8k16 bf16: the 128-bit global loads ARE the fragments (k-permutation), so QK^T has no
+//     unpacking at all, and P V' needs one PRMT per B register.  P is rounded to bf16 only as an MMA operand; the saved
+//     probabilities stay fp32.
+// The fp32 parity mode keeps the exact kernel above.
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void sincos_sfu(float x, float* sn, float* cs) {
+  const float n = rintf(x * 0.15915494309189535f);          // x / 2pi
+  float r = fmaf(n, -6.2831854820251465f, x);                // 2pi = hi + lo, hi = float(2pi)
+  r = fmaf(n, 1.7484555e-07f, r);                            // -lo
+  *sn = __sinf(r);
+  *cs = __cosf(r);
+}
+__device__ __forceinline__ float pair_log_term_fast(const float4& oi, const float4& oj, int c) {
+  const float num = c == 0 ? oi.z - oj.z : (c == 1 ? oi.w - oj.w : (c == 2 ? oi.x : oi.y));
+  const float den = c == 0 ? oi.x : (c == 1 ? oi.y : (c == 2 ? oj.x : oj.y));
+  float qv = __fdividef(num, den);
+  if (c < 2) { qv = fabsf(qv); qv = qv < 1e-3f ? 1e-3f : qv; }
+  return __logf(qv);
+}
+// volatile: keeps the load where the source puts it relative to the (volatile) mma instructions -- the V' quads are
+// requested after the QK^T mmas have consumed the Q / K registers, and arrive during the softmax
+__device__ __forceinline__ uint4 ldg128(const bf16* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+// word i (compile-time after unrolling) of a 128-bit register quad, without taking its address
+__device__ __forceinline__ uint32_t word(const uint4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
+
+template <int NTS>
+__global__ void __launch_bounds__(256, 2) geoattn_fwd_bf16_kernel(const FwdParams p) {
+  constexpr int NKS = (NTS + 1) / 2;             // 16-key k-steps of P V'
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int DH = p.dirs * p.H;
+  float4* obj = reinterpret_cast<float4*>(smem_raw);                 // [MAX_ROIS]
+  float* wgs = reinterpret_cast<float*>(obj + MAX_ROIS);             // [EMB][DH] in B-fragment order
+  float* bgs = wgs + EMB * DH;                                       // [DH]
+  float* ags = bgs + DH;                                             // [DH]
+  float* tile = ags + DH;                                            // [DH][TS]  (TS = ROWS*MP + 4: conflict-free scatter)
+  const int tid = threadIdx.x, b = blockIdx.y, i0 = blockIdx.x * ROWS;
+  const int N = p.N, M = p.M, MP = p.MP, D = p.D, H = p.H, TS = ROWS * MP + 4;
+  const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+
+  for (int n = tid; n < N; n += 256) obj[n] = box_terms(p.boxes + ((size_t)b * N + n) * 4);
+  const int NTD = DH >> 3;
+  for (int x = tid; x < EMB * DH; x += 256) {
+    const int r = x & 1, ln = (x >> 1) & 31, rest = x >> 6, nt = rest % NTD, ks = rest / NTD;
+    const int e = 8 * ks + (ln & 3) + 4 * r, dh = 8 * nt + (ln >> 2), d = dh / H, h = dh - d * H;
+    wgs[x] = p.wg[(size_t)d * p.wg_stride + e * H + h];
+  }
+  for (int dh = tid; dh < DH; dh += 256) {
+    int d = dh / H, h = dh - d * H;
+    bgs[dh] = p.bg ? p.bg[(size_t)d * p.bg_stride + h] : 0.f;
+    ags[dh] = p.alpha_g[d];
+  }
+  __syncthreads();
+
+  // ---- phase 1: log-bias of the (rows of this tile that exist) x M pairs, all heads and directions
+  {
+    const int npairs = min(ROWS, N - i0) * M;
+    const float winv0 = 100.0f / p.wd.d[t], winv1 = 100.0f / p.wd.d[t + 4];
+    for (int mt = warp; mt * 16 < npairs; mt += 8) {
+      int il[2], jj[2];
+      bool inb[2];
+      float mine[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int pi = mt * 16 + g + 8 * u;
+        inb[u] = pi < npairs;
+        const int pc = min(pi, npairs - 1);
+        il[u] = pc / M; jj[u] = pc - il[u] * M;
+        const int f = (i0 + il[u]) * M + jj[u];              // raw-reshape scramble (graph_att_layer.py:74,81)
+        const int ip = f / N, jp = f - ip * N;
+        mine[u] = pair_log_term_fast(obj[ip], obj[jp], t);
+      }
+      float zc[MAX_DH / 8][4];
+#pragma unroll
+      for (int nt = 0; nt < MAX_DH / 8; ++nt) { zc[nt][0] = zc[nt][1] = zc[nt][2] = zc[nt][3] = 0.f; }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float x0 = __shfl_sync(0xffffffffu, mine[0], (lane & ~3) | c);
+        const float x1 = __shfl_sync(0xffffffffu, mine[1], (lane & ~3) | c);
+        float s00, c00, s01, c01, s10, c10, s11, c11;            // [pair][wave number t / t+4]
+        sincos_sfu(x0 * winv0, &s00, &c00); sincos_sfu(x0 * winv1, &s01, &c01);
+        sincos_sfu(x1 * winv0, &s10, &c10); sincos_sfu(x1 * winv1, &s11, &c11);
+        const uint32_t as[4] = {__float_as_uint(s00), __float_as_uint(s10), __float_as_uint(s01), __float_as_uint(s11)};
+        const uint32_t ac[4] = {__float_as_uint(c00), __float_as_uint(c10), __float_as_uint(c01), __float_as_uint(c11)};
+#pragma unroll
+        for (int nt = 0; nt < MAX_DH / 8; ++nt) {
+          if (nt < NTD) {
+            const float2 ws = *reinterpret_cast<const float2*>(wgs + (((2 * c) * NTD + nt) * 32 + lane) * 2);
+            const float2 wc = *reinterpret_cast<const float2*>(wgs + (((2 * c + 1) * NTD + nt) * 32 + lane) * 2);
+            const uint32_t bs[2] = {__float_as_uint(ws.x), __float_as_uint(ws.y)};
+            const uint32_t bc[2] = {__float_as_uint(wc.x), __float_as_uint(wc.y)};
+            mma_tf32(zc[nt], as, bs);
+            mma_tf32(zc[nt], ac, bc);
+          }
+        }
+      }
+#pragma unroll
+      for (int nt = 0; nt < MAX_DH / 8; ++nt) {
+        if (nt < NTD) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int u = e >> 1, dh = 8 * nt + 2 * t + (e & 1);
+            if (inb[u]) {
+              const float z = fmaf(ags[dh], zc[nt][e], bgs[dh]);
+              const float gb = __logf(fmaxf(z, 1e-6f));                   // graph_att_layer.py:79,86,88
+              if (p.save_gb) p.save_gb[(((size_t)b * DH + dh) * N + i0 + il[u]) * M + jj[u]] = gb;
+              tile[dh * TS + il[u] * MP + jj[u]] = gb;
+            }
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: attention.  warp <-> head; lane (g, t) in mma fragment terms
+  const bf16* Q = static_cast<const bf16*>(p.q);
+  const bf16* KV = static_cast<const bf16*>(p.kv);
+  const int ldq = p.dirs * D, ldkv = 2 * p.dirs * D;
+  const float c_label = p.label_c ? __ldg(p.label_c) : 0.f;
+  const int r0 = i0 + g, r1 = i0 + g + 8;
+  const int r0c = min(r0, N - 1), r1c = min(r1, N - 1);
+
+  for (int h = warp; h < H; h += 8) {
+    float oacc[8][4];
+#pragma unroll
+    for (int ot = 0; ot < 8; ++ot) { oacc[ot][0] = oacc[ot][1] = oacc[ot][2] = oacc[ot][3] = 0.f; }
+
+    for (int d = 0; d < p.dirs; ++d) {
+      const int dh = d * H + h;
+      // Q and K of this (dir, head) are requested up front (one memory round trip)
+      uint4 qw[2][2], kw[NTS][2], vw[NKS][4];
+      {
+        const bf16* qp0 = Q + ((size_t)b * N + r0c) * ldq + d * D + h * HD + 8 * t;
+        const bf16* qp1 = Q + ((size_t)b * N + r1c) * ldq + d * D + h * HD + 8 * t;
+        qw[0][0] = ldg128(qp0); qw[0][1] = ldg128(qp0 + 32);
+        qw[1][0] = ldg128(qp1); qw[1][1] = ldg128(qp1 + 32);
+        const bf16* kbase = KV + (size_t)b * M * ldkv + d * D + h * HD + 8 * t;
+#pragma unroll
+        for (int nt = 0; nt < NTS; ++nt) {
+          const bf16* kp = kbase + (size_t)min(nt * 8 + g, M - 1) * ldkv;
+          kw[nt][0] = ldg128(kp); kw[nt][1] = ldg128(kp + 32);
+        }
+      }
+      // S = Q K^T: k-step s takes words (2(s&1), 2(s&1)+1) of load s>>1 from A and B alike
+      float sacc[NTS][4];
+#pragma unroll
+      for (int nt = 0; nt < NTS; ++nt) { sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f; }
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        const int w0 = 2 * (s & 1);
+        const uint32_t a[4] = {word(qw[0][s >> 1], w0), word(qw[1][s >> 1], w0), word(qw[0][s >> 1], w0 + 1), word(qw[1][s >> 1], w0 + 1)};
+#pragma unroll
+        for (int nt = 0; nt < NTS; ++nt) mma_bf16(sacc[nt], a, word(kw[nt][s >> 1], w0), word(kw[nt][s >> 1], w0 + 1));
+      }
+      {
+        const bf16* vbase = KV + (size_t)b * M * ldkv + (p.dirs + d) * D + h * HD + 8 * g;
+#pragma unroll
+        for (int ks = 0; ks < NKS; ++ks) {
+          const int j = 16 * ks + 2 * t;
+          vw[ks][0] = ldg128(vbase + (size_t)min(j, M - 1) * ldkv);
+          vw[ks][1] = ldg128(vbase + (size_t)min(j + 1, M - 1) * ldkv);
+          vw[ks][2] = ldg128(vbase + (size_t)min(j + 8, M - 1) * ldkv);
+          vw[ks][3] = ldg128(vbase + (size_t)min(j + 9, M - 1) * ldkv);
+        }
+      }
+      // logits = S/sqrt(dh) + geometry bias + label const; mask padded key columns; softmax over keys
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+      const float* trow = tile + dh * TS;
+#pragma unroll
+      for (int nt = 0; nt < NTS; ++nt) {
+        const int c0 = nt * 8 + 2 * t;
+        const float2 b0 = *reinterpret_cast<const float2*>(trow + g * MP + min(c0, MP - 2));
+        const float2 b1 = *reinterpret_cast<const float2*>(trow + (g + 8) * MP + min(c0, MP - 2));
+        sacc[nt][0] = c0 < M ? fmaf(sacc[nt][0], 0.125f, b0.x + c_label) : -INFINITY;
+        sacc[nt][1] = c0 + 1 < M ? fmaf(sacc[nt][1], 0.125f, b0.y + c_label) : -INFINITY;
+        sacc[nt][2] = c0 < M ? fmaf(sacc[nt][2], 0.125f, b1.x + c_label) : -INFINITY;
+        sacc[nt][3] = c0 + 1 < M ? fmaf(sacc[nt][3], 0.125f, b1.y + c_label) : -INFINITY;
+        mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
+      }
+      mx0 = quad_max(mx0); mx1 = quad_max(mx1);
+      float sm0 = 0.f, sm1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NTS; ++nt) {
+        sacc[nt][0] = __expf(sacc[nt][0] - mx0); sacc[nt][1] = __expf(sacc[nt][1] - mx0);
+        sacc[nt][2] = __expf(sacc[nt][2] - mx1); sacc[nt][3] = __expf(sacc[nt][3] - mx1);
+        sm0 += sacc[nt][0] + sacc[nt][1]; sm1 += sacc[nt][2] + sacc[nt][3];
+      }
+      const float inv0 = __fdividef(1.f, quad_sum(sm0)), inv1 = __fdividef(1.f, quad_sum(sm1));
+#pragma unroll
+      for (int nt = 0; nt < NTS; ++nt) {
+        sacc[nt][0] *= inv0; sacc[nt][1] *= inv0; sacc[nt][2] *= inv1; sacc[nt][3] *= inv1;
+        if (p.save_p) {
+          const int c0 = nt * 8 + 2 * t;
+          float* pr0 = p.save_p + (((size_t)b * DH + dh) * N + r0) * M;
+          float* pr1 = p.save_p + (((size_t)b * DH + dh) * N + r1) * M;
+          if ((M & 1) == 0) {       // rows start 8-byte aligned: one 64-bit store per row
+            if (r0 < N && c0 < M) *reinterpret_cast<float2*>(pr0 + c0) = make_float2(sacc[nt][0], sacc[nt][1]);
+            if (r1 < N && c0 < M) *reinterpret_cast<float2*>(pr1 + c0) = make_float2(sacc[nt][2], sacc[nt][3]);
+          } else {
+            if (r0 < N) { if (c0 < M) pr0[c0] = sacc[nt][0]; if (c0 + 1 < M) pr0[c0 + 1] = sacc[nt][1]; }
+            if (r1 < N) { if (c0 < M) pr1[c0] = sacc[nt][2]; if (c0 + 1 < M) pr1[c0 + 1] = sacc[nt][3]; }
+          }
+        }
+      }
+      // O += P V'.  k-step ks covers keys 16ks..16ks+15: the C fragments of key tiles 2ks, 2ks+1 are the A fragment.
+      // Output n-tile ot, column n stands for head-dim element 8n+ot, so the lane's 8 contiguous V' elements per key
+      // feed n-tile ot from element ot (one PRMT per register) and the lane ends up owning 16 contiguous outputs per row.
+#pragma unroll
+      for (int ks = 0; ks < NKS; ++ks) {
+        uint32_t a[4];
+        a[0] = pack2_bf16(sacc[2 * ks][0], sacc[2 * ks][1]);
+        a[1] = pack2_bf16(sacc[2 * ks][2], sacc[2 * ks][3]);
+        if (2 * ks + 1 < NTS) {
+          a[2] = pack2_bf16(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1]);
+          a[3] = pack2_bf16(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3]);
+        } else {
+          a[2] = 0u; a[3] = 0u;
+        }
+#pragma unroll
+        for (int ot = 0; ot < 8; ++ot) {
+          const uint32_t sel = (ot & 1) ? 0x7632u : 0x5410u;
+          const uint32_t b0 = __byte_perm(word(vw[ks][0], ot >> 1), word(vw[ks][1], ot >> 1), sel);
+          const uint32_t b1 = __byte_perm(word(vw[ks][2], ot >> 1), word(vw[ks][3], ot >> 1), sel);
+          mma_bf16(oacc[ot], a, b0, b1);
+        }
+      }
+    }  // dirs
+
+    // epilogue: lane owns head-dim elements [16t, 16t+16) of rows r0 and r1
+    const bf16* S = static_cast<const bf16*>(p.s);
+    const bf16* V0 = static_cast<const bf16*>(p.v0);
+    bf16* V1 = static_cast<bf16*>(p.v1);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int r = half ? r1 : r0;
+      unsigned long long bits = 0ull;
+      if (r < N) {
+        const size_t off = ((size_t)b * N + r) * D + h * HD + 16 * t;
+        const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+        uint4 sw[2] = {zero4, zero4}, vv[2] = {zero4, zero4};
+        if (S) { sw[0] = ldg128(S + off); sw[1] = ldg128(S + off + 8); }
+        if (p.residual) { vv[0] = ldg128(V0 + off); vv[1] = ldg128(V0 + off + 8); }
+        uint32_t ow[8];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          float o2[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int u = 2 * w + e;
+            const float o = oacc[u & 7][(u >> 3) + 2 * half];      // element 16t+u <- tile (u%8), col 2t + u/8
+            if (S) {
+              const uint32_t sword = word(sw[w >> 2], w & 3), vword = word(vv[w >> 2], w & 3);
+              const float x = __uint_as_float(e ? (sword & 0xffff0000u) : (sword << 16)) + o;
+              if (x > 0.f) bits |= 1ull << (16 * t + u);
+              o2[e] = __uint_as_float(e ? (vword & 0xffff0000u) : (vword << 16)) + fmaxf(x, 0.f);
+            } else {
+              o2[e] = o;
+            }
+          }
+          ow[w] = pack2_bf16(o2[0], o2[1]);
+        }
+        *reinterpret_cast<uint4*>(V1 + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        *reinterpret_cast<uint4*>(V1 + off + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
       }
       if (p.gate) {
         bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
@@ -1003,6 +1299,16 @@ int launch_fwd(const FwdParams& p, cudaStream_t st) {
   return REGAT_OK;
 }
 
+int launch_fwd_bf16(const FwdParams& p, cudaStream_t st) {
+  const int DH = p.dirs * p.H;
+  const size_t smem = sizeof(float4) * MAX_ROIS + sizeof(float) * ((size_t)EMB * DH + 2 * DH + (size_t)DH * (ROWS * p.MP + 4));
+  REGAT_TRY(set_smem(geoattn_fwd_bf16_kernel<3>, smem));
+  dim3 grid(ceil_div(p.N, ROWS), p.B);
+  geoattn_fwd_bf16_kernel<3><<<grid, 256, smem, st>>>(p);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+
 template <typename T, bool S3, int NTS>
 int launch_bwd_nts(const BwdParams& p, cudaStream_t st) {
   const size_t smem = sizeof(float) * (size_t)p.NP * (2 * LDX + 2 * tile_ld<NTS>());
@@ -1079,6 +1385,8 @@ extern "C" int regat_geoattn_fwd(int dtype, int B, int N, int nongt_dim, int D, 
   p.s = s; p.v0 = v0; p.v1 = v1; p.save_p = save_p; p.save_gb = save_gbias;
   p.gate = reinterpret_cast<unsigned long long*>(gate);
   if (dtype == REGAT_F32) return launch_fwd<float, true>(p, (cudaStream_t)stream);
+  static const int no_fast = [] { const char* e = getenv("REGAT_ATTN_GENERIC"); return e ? atoi(e) : 0; }();
+  if (boxes && p.M <= 24 && !no_fast) return launch_fwd_bf16(p, (cudaStream_t)stream);
   return launch_fwd<bf16, false>(p, (cudaStream_t)stream);
 }
 
