@@ -75,6 +75,15 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -207,7 +216,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
                                                            const __grid_constant__ CUtensorMap mapB, const __grid_constant__ TcParams p) {
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = ACC * BN;
-  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
+  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* tiles = smem;            // SWIZZLE_128B tiles need 1024-byte alignment: the dynamic window provides it (checked)
   if ((smem_u32(smem) & 1023u) != 0) __trap();
@@ -245,16 +254,17 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
   };
 
   if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      int it = 0;
+    // ===== TMA producer: warp-uniform loop, one elected lane issues =====
+    {
+      const bool leader = elect_one();
+      int s = 0;
+      uint32_t ph = 0;
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
         int m0, n0, kb0, kb1;
         decode(u, m0, n0, kb0, kb1);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + s, ph ^ 1);
+          if (leader) {
           mbar_expect_tx(full_bar + s, STAGE_BYTES);
           unsigned char* sa = tiles + s * STAGE_BYTES;
           unsigned char* sb = sa + A_BYTES;
@@ -270,38 +280,50 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
 #pragma unroll
             for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (64 * BK * 2), &mapB, full_bar + s, n0 + c * 64, kb * BK);
           }
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (single thread) =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
-      int it = 0, ui = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
-        int m0, n0, kb0, kb1;
-        decode(u, m0, n0, kb0, kb1);
-        const int a = ui % ACC;
-        const uint32_t aph = (ui / ACC) & 1;
-        mbar_wait(tmem_empty + a, aph ^ 1);          // epilogue has drained this accumulator stage
+    // ===== MMA issuer: the whole warp walks the pipeline (uniform control flow), one elected lane issues =====
+    // The issue loop is on the critical path of every k-block (4 MMAs of 128 x BN x 16 take only ~128 BN/256 ns), so it is
+    // kept to a wait, four descriptor adds and the instructions themselves: descriptors are built once and advanced by
+    // adding the byte offset >> 4 to their start-address field (shared memory addresses fit its 14 bits without carry).
+    constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+    constexpr uint32_t KSTEP_A = A_MN ? 2048u : 32u, KSTEP_B = B_MN ? 2048u : 32u;   // bytes per UMMA_K step
+    const uint32_t tiles_addr = smem_u32(tiles);
+    const uint64_t da0 = A_MN ? make_desc(tiles_addr, 64 * BK * 2, 1024) : make_desc(tiles_addr, 16, 1024);
+    const uint64_t db0 = B_MN ? make_desc(tiles_addr + A_BYTES, 64 * BK * 2, 1024) : make_desc(tiles_addr + A_BYTES, 16, 1024);
+    const bool leader = elect_one();
+    int s = 0, ui = 0;
+    uint32_t ph = 0;
+    for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
+      int m0, n0, kb0, kb1;
+      decode(u, m0, n0, kb0, kb1);
+      const int a = ui % ACC;
+      const uint32_t aph = (ui / ACC) & 1;
+      mbar_wait(tmem_empty + a, aph ^ 1);          // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
+      uint32_t acc_flag = 0u;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar + s, ph);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (it / STAGES) & 1;
-          mbar_wait(full_bar + s, ph);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(tiles + s * STAGE_BYTES), sb = sa + A_BYTES;
+        if (leader) {
+          const uint64_t da = da0 + (uint64_t)((uint32_t)s * (STAGE_BYTES >> 4));
+          const uint64_t db = db0 + (uint64_t)((uint32_t)s * (STAGE_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = A_MN ? make_desc(sa + k * 2048, 64 * BK * 2, 1024) : make_desc(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_desc(sb + k * 2048, 64 * BK * 2, 1024) : make_desc(sb + k * 32, 16, 1024);
-            umma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_bf16(tmem_d, da + (uint64_t)(k * (KSTEP_A >> 4)), db + (uint64_t)(k * (KSTEP_B >> 4)), idesc, k == 0 ? acc_flag : 1u);
           }
           umma_commit(empty_bar + s);          // frees the smem slot once these MMAs have read it
         }
-        umma_commit(tmem_full + a);            // accumulator of this unit complete
+        acc_flag = 1u;
+        if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
+      if (leader) umma_commit(tmem_full + a);  // accumulator of this unit complete
+      __syncwarp();
     }
   } else {
     // ===== epilogue: TMEM -> registers -> swizzled smem patch -> fused epilogue -> coalesced global =====
@@ -588,7 +610,11 @@ int gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int lda,
   // tile width: 256 when there are enough column tiles to keep >= 1 wave busy, else 128
   static const int force_bn = [] { const char* s = getenv("REGAT_TC_BN"); return s ? atoi(s) : 0; }();
   const int tiles_m = ceil_div(M, BM);
-  int bn = (force_bn == 128 || force_bn == 256) ? force_bn : ((N >= 256 && tiles_m * ceil_div(N, 256) >= num_sms()) ? 256 : 128);
+  int bn = (force_bn == 64 || force_bn == 128 || force_bn == 256) ? force_bn : ((N >= 256 && tiles_m * ceil_div(N, 256) >= num_sms()) ? 256 : 128);
+  // skinny problems (a batch-sized M, long K): the 128-wide tiling leaves most SMs idle behind a serial K loop that is
+  // bound by TMA latency at 3 stages -- narrower tiles double the CTAs and the 24 KB stages allow an 8-deep ring
+  static const int skinny = [] { const char* s = getenv("REGAT_TC_SKINNY"); return s ? atoi(s) : 1; }();
+  if (!force_bn && skinny && bn == 128 && tiles_m * ceil_div(N, 128) * 2 <= num_sms() && K >= 512) bn = 64;
   const int tiles_n = ceil_div(N, bn);
   const int total_kb = ceil_div(K, BK);
   // split-K only for plain fp32 targets (weight gradients: few output tiles, very long K): fill ~2 CTAs per SM
@@ -630,6 +656,7 @@ int gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int lda,
   static const int reserve = [] { const char* s = getenv("REGAT_SM_RESERVE"); return s ? std::max(0, atoi(s)) : 0; }();
   const int sms = std::max(1, num_sms() - reserve);
   if (bn == 256) return launch_cfg<256, 4, 2, 8>(a_mn, b_mn, ma, mb, p, std::min(units, sms), st);
+  if (bn == 64) return launch_cfg<64, 8, 2, 4>(a_mn, b_mn, ma, mb, p, std::min(units, sms), st);
   return launch_cfg<128, 3, 2, 4>(a_mn, b_mn, ma, mb, p, std::min(units, 2 * sms), st);
 }
 

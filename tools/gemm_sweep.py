@@ -27,10 +27,18 @@ def run(M, N, K, tA=0, tB=0, epi_kind="plain", c_f32=False, reps=20, nrot=4):
     for i in range(4):
         call(i)
     torch.cuda.synchronize()
+    # replay from a CUDA graph: the Python / ctypes launch path (~10 us per call on these hosts) must not be what is timed
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for i in range(reps):
+                call(i)
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(reps):
-        call(i)
+    g.replay()
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / reps * 1e3
     return us, 2.0 * M * N * K / us / 1e6
