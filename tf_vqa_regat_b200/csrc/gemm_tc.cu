@@ -614,7 +614,7 @@ int gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int lda,
   // skinny problems (a batch-sized M, long K): the 128-wide tiling leaves most SMs idle behind a serial K loop that is
   // bound by TMA latency at 3 stages -- narrower tiles double the CTAs and the 24 KB stages allow an 8-deep ring
   static const int skinny = [] { const char* s = getenv("REGAT_TC_SKINNY"); return s ? atoi(s) : 1; }();
-  if (!force_bn && skinny && bn == 128 && tiles_m * ceil_div(N, 128) * 2 <= num_sms() && K >= 512) bn = 64;
+  if (!force_bn && skinny && bn == 128 && tiles_m <= 2 && tiles_m * ceil_div(N, 128) * 2 <= num_sms() && K >= 512) bn = 64;
   const int tiles_n = ceil_div(N, bn);
   const int total_kb = ceil_div(K, BK);
   // split-K only for plain fp32 targets (weight gradients: few output tiles, very long K): fill ~2 CTAs per SM

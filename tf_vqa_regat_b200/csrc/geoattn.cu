@@ -1134,6 +1134,230 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const BwdParams p) {
 }
 
 // ==========================================================================================
+// attention backward, bf16 fast path (M <= 24 keys): one CTA (4 warps) per (graph, dir, head), bf16 m16n8k16 throughout.
+//   phase A (warp <-> 16-query tile): dO = gate o dV1 (packed), dP = dO V'^T, dL = P o (dP - rowsum(P o dP)), dQ = dL K / 8.
+//            dL replaces P in HBM (fp32, read by the geometry reduction); dL^T, P^T (bf16) and the gated dO go to shared memory.
+//   phase B (warp <-> {dK, dV'} x key tile): dK = dL^T Q / 8, dV' = P^T dO with the query index as k: the A fragments are
+//            32-bit reads of the transposed tiles, the B fragments are 8-element row pieces paired across two query rows by
+//            one PRMT each (Q straight from global memory, dO from shared memory).
+// Same fragment conventions as the forward fast path; dL and P are rounded to bf16 only as MMA operands.
+template <int NTS>
+__global__ void __launch_bounds__(128, 4) attn_bwd_bf16_kernel(const BwdParams p) {
+  constexpr int NKS = (NTS + 1) / 2;          // 16-key k-steps (dQ) = 16-key m-tiles (dK, dV')
+  constexpr int LDO = HD + 8;                 // bf16 row stride of the gated dO tile (144 B: 16-byte aligned, conflict-free)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int N = p.N, M = p.M, D = p.D, H = p.H, NP = p.NP;
+  const int LDT = NP + 8;                     // bf16 row stride of the transposed tiles
+  bf16* dOs = reinterpret_cast<bf16*>(smem_raw);                      // [NP][LDO]
+  bf16* LT = dOs + NP * LDO;                                          // [16 NKS][LDT]   dL^T
+  bf16* PT = LT + 16 * NKS * LDT;                                     // [16 NKS][LDT]   P^T
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int h = blockIdx.x % H, d = (blockIdx.x / H) % p.dirs, b = blockIdx.x / (H * p.dirs);
+  const int dh = d * H + h;
+  const int ldq = p.dirs * D, ldkv = 2 * p.dirs * D;
+  const bf16* Q = static_cast<const bf16*>(p.q);
+  const bf16* KV = static_cast<const bf16*>(p.kv);
+  const bf16* dV1 = static_cast<const bf16*>(p.dv1);
+  float* P_g = p.p_dl + ((size_t)b * p.dirs * H + dh) * N * M;
+  const bf16* kbase = KV + (size_t)b * M * ldkv + d * D + h * HD;
+  const bf16* vbase = KV + (size_t)b * M * ldkv + (p.dirs + d) * D + h * HD;
+
+  // ---- phase A
+  for (int mt = warp; mt * 16 < N; mt += 4) {
+    const int r0 = mt * 16 + g, r1 = r0 + 8;
+    const int r0c = min(r0, N - 1), r1c = min(r1, N - 1);
+    uint4 dw[2][2], vw[NTS][2], kw[NKS][4];
+    {
+      const bf16* dp0 = dV1 + ((size_t)b * N + r0c) * D + h * HD + 8 * t;
+      const bf16* dp1 = dV1 + ((size_t)b * N + r1c) * D + h * HD + 8 * t;
+      dw[0][0] = ldg128(dp0); dw[0][1] = ldg128(dp0 + 32);
+      dw[1][0] = ldg128(dp1); dw[1][1] = ldg128(dp1 + 32);
+#pragma unroll
+      for (int nt = 0; nt < NTS; ++nt) {
+        const bf16* vp = vbase + (size_t)min(nt * 8 + g, M - 1) * ldkv + 8 * t;
+        vw[nt][0] = ldg128(vp); vw[nt][1] = ldg128(vp + 32);
+      }
+    }
+    const unsigned long long g0 = r0 < N ? __ldg(p.gate + ((size_t)b * N + r0c) * H + h) : 0ull;
+    const unsigned long long g1 = r1 < N ? __ldg(p.gate + ((size_t)b * N + r1c) * H + h) : 0ull;
+    float pr[NTS][4];
+#pragma unroll
+    for (int nt = 0; nt < NTS; ++nt) {
+      const int c0 = nt * 8 + 2 * t;
+      if ((M & 1) == 0) {
+        const float2 z2 = make_float2(0.f, 0.f);
+        const float2 p0 = (r0 < N && c0 < M) ? *reinterpret_cast<const float2*>(P_g + (size_t)r0 * M + c0) : z2;
+        const float2 p1 = (r1 < N && c0 < M) ? *reinterpret_cast<const float2*>(P_g + (size_t)r1 * M + c0) : z2;
+        pr[nt][0] = p0.x; pr[nt][1] = p0.y; pr[nt][2] = p1.x; pr[nt][3] = p1.y;
+      } else {
+        pr[nt][0] = (r0 < N && c0 < M) ? P_g[(size_t)r0 * M + c0] : 0.f;
+        pr[nt][1] = (r0 < N && c0 + 1 < M) ? P_g[(size_t)r0 * M + c0 + 1] : 0.f;
+        pr[nt][2] = (r1 < N && c0 < M) ? P_g[(size_t)r1 * M + c0] : 0.f;
+        pr[nt][3] = (r1 < N && c0 + 1 < M) ? P_g[(size_t)r1 * M + c0 + 1] : 0.f;
+      }
+    }
+    // relu gate applied to the packed words: element e <-> bit e of the (row, head) gate word
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      uint32_t w0[4] = {dw[0][kk].x, dw[0][kk].y, dw[0][kk].z, dw[0][kk].w};
+      uint32_t w1[4] = {dw[1][kk].x, dw[1][kk].y, dw[1][kk].z, dw[1][kk].w};
+      const uint32_t m0 = (uint32_t)(g0 >> (32 * kk + 8 * t)) & 0xffu, m1 = (uint32_t)(g1 >> (32 * kk + 8 * t)) & 0xffu;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        w0[i] &= ((m0 >> (2 * i)) & 1u ? 0x0000ffffu : 0u) | ((m0 >> (2 * i + 1)) & 1u ? 0xffff0000u : 0u);
+        w1[i] &= ((m1 >> (2 * i)) & 1u ? 0x0000ffffu : 0u) | ((m1 >> (2 * i + 1)) & 1u ? 0xffff0000u : 0u);
+      }
+      dw[0][kk] = make_uint4(w0[0], w0[1], w0[2], w0[3]);
+      dw[1][kk] = make_uint4(w1[0], w1[1], w1[2], w1[3]);
+      *reinterpret_cast<uint4*>(dOs + r0 * LDO + 8 * t + 32 * kk) = dw[0][kk];
+      *reinterpret_cast<uint4*>(dOs + r1 * LDO + 8 * t + 32 * kk) = dw[1][kk];
+      if (d == 0) {   // the gated gradient also flows to s directly (v1 = v0 + relu(s + O_0 + O_1)): emitted once per head
+        bf16* dout = static_cast<bf16*>(p.dout);
+        if (r0 < N) *reinterpret_cast<uint4*>(dout + ((size_t)b * N + r0) * D + h * HD + 8 * t + 32 * kk) = dw[0][kk];
+        if (r1 < N) *reinterpret_cast<uint4*>(dout + ((size_t)b * N + r1) * D + h * HD + 8 * t + 32 * kk) = dw[1][kk];
+      }
+    }
+    // dP = dO V'^T
+    float sacc[NTS][4];
+#pragma unroll
+    for (int nt = 0; nt < NTS; ++nt) { sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f; }
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int w0 = 2 * (s & 1);
+      const uint32_t a[4] = {word(dw[0][s >> 1], w0), word(dw[1][s >> 1], w0), word(dw[0][s >> 1], w0 + 1), word(dw[1][s >> 1], w0 + 1)};
+#pragma unroll
+      for (int nt = 0; nt < NTS; ++nt) mma_bf16(sacc[nt], a, word(vw[nt][s >> 1], w0), word(vw[nt][s >> 1], w0 + 1));
+    }
+    // K row pieces for dQ = dL K: requested now, arrive during the softmax backward
+#pragma unroll
+    for (int ks = 0; ks < NKS; ++ks) {
+      const int j = 16 * ks + 2 * t;
+      kw[ks][0] = ldg128(kbase + (size_t)min(j, M - 1) * ldkv + 8 * g);
+      kw[ks][1] = ldg128(kbase + (size_t)min(j + 1, M - 1) * ldkv + 8 * g);
+      kw[ks][2] = ldg128(kbase + (size_t)min(j + 8, M - 1) * ldkv + 8 * g);
+      kw[ks][3] = ldg128(kbase + (size_t)min(j + 9, M - 1) * ldkv + 8 * g);
+    }
+    float dl0 = 0.f, dl1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NTS; ++nt) {
+      dl0 += pr[nt][0] * sacc[nt][0] + pr[nt][1] * sacc[nt][1];
+      dl1 += pr[nt][2] * sacc[nt][2] + pr[nt][3] * sacc[nt][3];
+    }
+    dl0 = quad_sum(dl0); dl1 = quad_sum(dl1);
+#pragma unroll
+    for (int nt = 0; nt < NTS; ++nt) {
+      const int c0 = nt * 8 + 2 * t;
+      float dl[4];
+      dl[0] = pr[nt][0] * (sacc[nt][0] - dl0); dl[1] = pr[nt][1] * (sacc[nt][1] - dl0);
+      dl[2] = pr[nt][2] * (sacc[nt][2] - dl1); dl[3] = pr[nt][3] * (sacc[nt][3] - dl1);
+      if ((M & 1) == 0) {
+        if (r0 < N && c0 < M) *reinterpret_cast<float2*>(P_g + (size_t)r0 * M + c0) = make_float2(dl[0], dl[1]);
+        if (r1 < N && c0 < M) *reinterpret_cast<float2*>(P_g + (size_t)r1 * M + c0) = make_float2(dl[2], dl[3]);
+      } else {
+        if (r0 < N) { if (c0 < M) P_g[(size_t)r0 * M + c0] = dl[0]; if (c0 + 1 < M) P_g[(size_t)r0 * M + c0 + 1] = dl[1]; }
+        if (r1 < N) { if (c0 < M) P_g[(size_t)r1 * M + c0] = dl[2]; if (c0 + 1 < M) P_g[(size_t)r1 * M + c0 + 1] = dl[3]; }
+      }
+      // transposed bf16 copies for phase B: tile[key][query]
+      LT[(c0) * LDT + r0] = __float2bfloat16_rn(dl[0]); LT[(c0 + 1) * LDT + r0] = __float2bfloat16_rn(dl[1]);
+      LT[(c0) * LDT + r1] = __float2bfloat16_rn(dl[2]); LT[(c0 + 1) * LDT + r1] = __float2bfloat16_rn(dl[3]);
+      PT[(c0) * LDT + r0] = __float2bfloat16_rn(pr[nt][0]); PT[(c0 + 1) * LDT + r0] = __float2bfloat16_rn(pr[nt][1]);
+      PT[(c0) * LDT + r1] = __float2bfloat16_rn(pr[nt][2]); PT[(c0 + 1) * LDT + r1] = __float2bfloat16_rn(pr[nt][3]);
+      sacc[nt][0] = dl[0]; sacc[nt][1] = dl[1]; sacc[nt][2] = dl[2]; sacc[nt][3] = dl[3];
+    }
+    // dQ = dL K / 8
+    float dqacc[8][4];
+#pragma unroll
+    for (int ot = 0; ot < 8; ++ot) { dqacc[ot][0] = dqacc[ot][1] = dqacc[ot][2] = dqacc[ot][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < NKS; ++ks) {
+      uint32_t a[4];
+      a[0] = pack2_bf16(sacc[2 * ks][0], sacc[2 * ks][1]);
+      a[1] = pack2_bf16(sacc[2 * ks][2], sacc[2 * ks][3]);
+      if (2 * ks + 1 < NTS) {
+        a[2] = pack2_bf16(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1]);
+        a[3] = pack2_bf16(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3]);
+      } else {
+        a[2] = 0u; a[3] = 0u;
+      }
+#pragma unroll
+      for (int ot = 0; ot < 8; ++ot) {
+        const uint32_t sel = (ot & 1) ? 0x7632u : 0x5410u;
+        const uint32_t b0 = __byte_perm(word(kw[ks][0], ot >> 1), word(kw[ks][1], ot >> 1), sel);
+        const uint32_t b1 = __byte_perm(word(kw[ks][2], ot >> 1), word(kw[ks][3], ot >> 1), sel);
+        mma_bf16(dqacc[ot], a, b0, b1);
+      }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int r = half ? r1 : r0;
+      if (r < N) {
+        uint32_t ow[8];
+#pragma unroll
+        for (int w = 0; w < 8; ++w)     // element 16t+u <- tile (u%8), col 2t + u/8
+          ow[w] = pack2_bf16(0.125f * dqacc[(2 * w) & 7][((2 * w) >> 3) + 2 * half], 0.125f * dqacc[(2 * w + 1) & 7][((2 * w + 1) >> 3) + 2 * half]);
+        bf16* dst = static_cast<bf16*>(p.dq) + ((size_t)b * N + r) * ldq + d * D + h * HD + 16 * t;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        *reinterpret_cast<uint4*>(dst + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase B: warp = (kind, key tile).  kind 0: dK = dL^T Q / 8;  kind 1: dV' = P^T dO
+  const int kind = warp & 1;
+  const bf16* XT = kind ? PT : LT;
+  for (int jm = warp >> 1; jm * 16 < M; jm += 2) {
+    float acc[8][4];
+#pragma unroll
+    for (int ot = 0; ot < 8; ++ot) { acc[ot][0] = acc[ot][1] = acc[ot][2] = acc[ot][3] = 0.f; }
+    const bf16* xr0 = XT + (jm * 16 + g) * LDT + 2 * t;
+    const bf16* xr1 = xr0 + 8 * LDT;
+    for (int ks = 0; ks * 16 < NP; ++ks) {
+      uint32_t a[4];
+      a[0] = *reinterpret_cast<const uint32_t*>(xr0 + 16 * ks);
+      a[1] = *reinterpret_cast<const uint32_t*>(xr1 + 16 * ks);
+      a[2] = *reinterpret_cast<const uint32_t*>(xr0 + 16 * ks + 8);
+      a[3] = *reinterpret_cast<const uint32_t*>(xr1 + 16 * ks + 8);
+      uint4 bw[4];
+      const int q0 = 16 * ks + 2 * t;
+      if (kind == 0) {
+        const bf16* qb = Q + (size_t)b * N * ldq + d * D + h * HD + 8 * g;
+        bw[0] = ldg128(qb + (size_t)min(q0, N - 1) * ldq);
+        bw[1] = ldg128(qb + (size_t)min(q0 + 1, N - 1) * ldq);
+        bw[2] = ldg128(qb + (size_t)min(q0 + 8, N - 1) * ldq);
+        bw[3] = ldg128(qb + (size_t)min(q0 + 9, N - 1) * ldq);
+      } else {
+        bw[0] = *reinterpret_cast<const uint4*>(dOs + (q0) * LDO + 8 * g);
+        bw[1] = *reinterpret_cast<const uint4*>(dOs + (q0 + 1) * LDO + 8 * g);
+        bw[2] = *reinterpret_cast<const uint4*>(dOs + (q0 + 8) * LDO + 8 * g);
+        bw[3] = *reinterpret_cast<const uint4*>(dOs + (q0 + 9) * LDO + 8 * g);
+      }
+#pragma unroll
+      for (int ot = 0; ot < 8; ++ot) {
+        const uint32_t sel = (ot & 1) ? 0x7632u : 0x5410u;
+        const uint32_t b0 = __byte_perm(word(bw[0], ot >> 1), word(bw[1], ot >> 1), sel);
+        const uint32_t b1 = __byte_perm(word(bw[2], ot >> 1), word(bw[3], ot >> 1), sel);
+        mma_bf16(acc[ot], a, b0, b1);
+      }
+    }
+    const float sc = kind ? 1.f : 0.125f;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int j = jm * 16 + g + 8 * half;
+      if (j < M) {
+        uint32_t ow[8];
+#pragma unroll
+        for (int w = 0; w < 8; ++w)
+          ow[w] = pack2_bf16(sc * acc[(2 * w) & 7][((2 * w) >> 3) + 2 * half], sc * acc[(2 * w + 1) & 7][((2 * w + 1) >> 3) + 2 * half]);
+        bf16* dst = static_cast<bf16*>(p.dkv) + ((size_t)b * M + j) * ldkv + (kind ? (p.dirs + d) : d) * D + h * HD + 16 * t;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        *reinterpret_cast<uint4*>(dst + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+      }
+    }
+  }
+}
+
+// ==========================================================================================
 // geometry backward: dWg[d][e][h] += sum_pairs Emb[e] * dz[d,h],  dbg += sum dz,  dc += sum dL
 struct GeoBwdParams {
   int B, N, M, H, dirs;
@@ -1318,6 +1542,14 @@ int launch_bwd_nts(const BwdParams& p, cudaStream_t st) {
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
+int launch_bwd_bf16(const BwdParams& p, cudaStream_t st) {
+  constexpr int NTS = 3, NKS = 2;
+  const size_t smem = sizeof(bf16) * ((size_t)p.NP * (HD + 8) + 2 * (size_t)16 * NKS * (p.NP + 8));
+  REGAT_TRY(set_smem(attn_bwd_bf16_kernel<NTS>, smem));
+  attn_bwd_bf16_kernel<NTS><<<p.B * p.dirs * p.H, 128, smem, st>>>(p);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
 template <typename T, bool S3>
 int launch_bwd(const BwdParams& p, cudaStream_t st) {
   const int nts = ceil_div(p.M, 8);
@@ -1404,6 +1636,8 @@ extern "C" int regat_attn_bwd(int dtype, int B, int N, int nongt_dim, int D, int
   p.q = q; p.kv = kv; p.dv1 = dv1; p.gate = reinterpret_cast<const unsigned long long*>(gate);
   p.p_dl = p_inout_dl; p.dq = dq; p.dkv = dkv; p.dout = dout;
   if (dtype == REGAT_F32) return launch_bwd<float, true>(p, (cudaStream_t)stream);
+  static const int no_fast = [] { const char* e = getenv("REGAT_ATTN_GENERIC"); return e ? atoi(e) : 0; }();
+  if (p.M <= 24 && !no_fast) return launch_bwd_bf16(p, (cudaStream_t)stream);
   return launch_bwd<bf16, false>(p, (cudaStream_t)stream);
 }
 
