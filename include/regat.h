@@ -181,6 +181,13 @@ REGAT_API int regat_geo_bwd(int B, int N, int nongt_dim, int H, int dirs, int E,
                   const float* dl, const float* gbias,
                   float* dwg, int64_t dwg_stride, float* dbg, int64_t dbg_stride, float* dc,
                   regat_stream_t stream);
+/* Same reduction; fast_math != 0 (bf16 training mode, boxes path) evaluates sin/cos/log/exp on the SFU and the
+ * 64 x (dirs*H) outer products in one TF32 pass instead of 3xTF32 -- the precision class of the bf16 forward path. */
+REGAT_API int regat_geo_bwd_ex(int B, int N, int nongt_dim, int H, int dirs, int E,
+                  const float* boxes, const float* pos_emb, const float* wave_div_host,
+                  const float* dl, const float* gbias,
+                  float* dwg, int64_t dwg_stride, float* dbg, int64_t dbg_stride, float* dc,
+                  int fast_math, regat_stream_t stream);
 
 /* ------------------------------------------------------------------ BUTD pooling --------
  * fusion.py:43-54 + :34 with the (linear) v2attention FC re-associated:

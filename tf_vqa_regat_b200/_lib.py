@@ -48,6 +48,7 @@ SIGNATURES = {
     "regat_geoattn_fwd": [i32] * 8 + [vp, vp, vp, vp, vp, vp, i64, vp, vp, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "regat_attn_bwd": [i32] * 7 + [vp] * 9,
     "regat_geo_bwd": [i32] * 6 + [vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp],
+    "regat_geo_bwd_ex": [i32] * 6 + [vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, i32, vp],
     "regat_butd_pool_fwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp],
     "regat_butd_pool_bwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp],
     "regat_cast": [i32, i32, vp, vp, i64, vp],

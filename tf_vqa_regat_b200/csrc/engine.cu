@@ -529,8 +529,9 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
     const Layer& P0 = e->layers[e->l_pos[0]];
     const long long wstride = dirs > 1 ? e->layers[e->l_pos[1]].v_off - P0.v_off : 0;
     const long long bstride = dirs > 1 ? e->layers[e->l_pos[1]].b_off - P0.b_off : 0;
-    REGAT_TRY(regat_geo_bwd(B, N, cf.nongt_dim, H, dirs, cf.pos_emb_dim, c.boxes, nullptr, e->wave_div, e->at<float>(e->P),
-                            e->at<float>(e->GB), e->grads + P0.v_off, wstride, e->grads + P0.b_off, bstride, scal + 1, st));
+    REGAT_TRY(regat_geo_bwd_ex(B, N, cf.nongt_dim, H, dirs, cf.pos_emb_dim, c.boxes, nullptr, e->wave_div, e->at<float>(e->P),
+                               e->at<float>(e->GB), e->grads + P0.v_off, wstride, e->grads + P0.b_off, bstride, scal + 1,
+                               dt == REGAT_BF16, st));
     const Layer& LL = e->layers[e->l_label];
     REGAT_TRY(k_label_grad(scal + 1, e->grads, LL.v_off, LL.b_off, st));
   }

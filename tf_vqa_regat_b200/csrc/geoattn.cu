@@ -1361,7 +1361,7 @@ __global__ void __launch_bounds__(128, 4) attn_bwd_bf16_kernel(const BwdParams p
 // geometry backward: dWg[d][e][h] += sum_pairs Emb[e] * dz[d,h],  dbg += sum dz,  dc += sum dL
 struct GeoBwdParams {
   int B, N, M, H, dirs;
-  const float* boxes; const float* pos_emb; WaveDiv wd;
+  const float* boxes; const float* pos_emb; WaveDiv wd; int fast;
   const float* dl; const float* gbias;
   float* dwg; long long dwg_stride; float* dbg; long long dbg_stride; float* dc;
 };
@@ -1369,7 +1369,9 @@ struct GeoBwdParams {
 // dz[pair, dh] with the 64 features as 4 m-tiles (one per geometry term c: rows g = sin, g+8 = cos of wave number g) and dh as
 // n-tiles.  Lane (g, t) evaluates sincos(term c, wave g) of pairs t and t+4 -- exactly its A fragments, nothing twice; the 32
 // log-geometry terms of a k-step are computed one per lane and exchanged by shuffle.  3xTF32 keeps fp32 accuracy.
-template <int DH>
+// FAST (bf16 training mode): SFU sincos / log / exp and one TF32 pass, like the forward fast path; the fp32 parity mode
+// keeps accurate transcendentals and 3xTF32.
+template <int DH, bool FAST>
 __global__ void __launch_bounds__(256, 2) geo_bwd_kernel(const GeoBwdParams p) {
   constexpr int NTD = DH / 8;
   __shared__ float red[EMB * DH];
@@ -1395,6 +1397,7 @@ __global__ void __launch_bounds__(256, 2) geo_bwd_kernel(const GeoBwdParams p) {
   for (int nt = 0; nt < NTD; ++nt) bsum[nt] = 0.f;
 
   const long long nsteps = (total + 7) / 8;
+  const float winv = 1.0f / p.wd.d[g];
   for (long long ks = (long long)blockIdx.x * 8 + warp; ks < nsteps; ks += (long long)gridDim.x * 8) {
     const long long pb = ks * 8;
     // lane L evaluates geometry term L%4 of pair pb + L/4
@@ -1403,7 +1406,8 @@ __global__ void __launch_bounds__(256, 2) geo_bwd_kernel(const GeoBwdParams p) {
       const long long pq = pb + g;
       if (pq < total && !p.pos_emb) {
         const int bq = (int)(pq / NM), f = (int)(pq - (long long)bq * NM), ip = f / N, jp = f - ip * N;
-        mine = pair_log_term(box_terms(p.boxes + ((size_t)bq * N + ip) * 4), box_terms(p.boxes + ((size_t)bq * N + jp) * 4), t);
+        const float4 oi = box_terms(p.boxes + ((size_t)bq * N + ip) * 4), oj = box_terms(p.boxes + ((size_t)bq * N + jp) * 4);
+        mine = FAST ? pair_log_term_fast(oi, oj, t) : pair_log_term(oi, oj, t);
       }
     }
     const long long pA = pb + t, pB = pb + t + 4;
@@ -1411,7 +1415,7 @@ __global__ void __launch_bounds__(256, 2) geo_bwd_kernel(const GeoBwdParams p) {
     const int bA = vA ? (int)(pA / NM) : 0, fA = vA ? (int)(pA - (long long)bA * NM) : 0;
     const int bB = vB ? (int)(pB / NM) : 0, fB = vB ? (int)(pB - (long long)bB * NM) : 0;
     // B fragments: dz = dL / z where z = exp(gbias) >= 1e-6, else 0    (d log(max(relu(z), 1e-6)) / dz)
-    Opnd<true, 2> bz[NTD];
+    Opnd<!FAST, 2> bz[NTD];
 #pragma unroll
     for (int nt = 0; nt < NTD; ++nt) {
       const int dh = 8 * nt + g;
@@ -1420,13 +1424,13 @@ __global__ void __launch_bounds__(256, 2) geo_bwd_kernel(const GeoBwdParams p) {
         const size_t idx = ((size_t)bA * DH + dh) * NM + fA;
         const float dl = __ldg(p.dl + idx), gb = __ldg(p.gbias + idx);
         csum += dl;
-        dzA = gb > LOGMIN ? dl * expf(-gb) : 0.f;
+        dzA = gb > LOGMIN ? dl * (FAST ? __expf(-gb) : expf(-gb)) : 0.f;
       }
       if (vB) {
         const size_t idx = ((size_t)bB * DH + dh) * NM + fB;
         const float dl = __ldg(p.dl + idx), gb = __ldg(p.gbias + idx);
         csum += dl;
-        dzB = gb > LOGMIN ? dl * expf(-gb) : 0.f;
+        dzB = gb > LOGMIN ? dl * (FAST ? __expf(-gb) : expf(-gb)) : 0.f;
       }
       bsum[nt] += dzA + dzB;
       bz[nt].set(0, dzA); bz[nt].set(1, dzB);
@@ -1442,15 +1446,20 @@ __global__ void __launch_bounds__(256, 2) geo_bwd_kernel(const GeoBwdParams p) {
       } else {
         const float xA = 100.0f * __shfl_sync(0xffffffffu, mine, 4 * t + c);
         const float xB = 100.0f * __shfl_sync(0xffffffffu, mine, 4 * (t + 4) + c);
-        sincos_cw(__fdiv_rn(xA, p.wd.d[g]), &sA, &cA);
-        sincos_cw(__fdiv_rn(xB, p.wd.d[g]), &sB, &cB);
+        if constexpr (FAST) {
+          sincos_sfu(xA * winv, &sA, &cA);
+          sincos_sfu(xB * winv, &sB, &cB);
+        } else {
+          sincos_cw(__fdiv_rn(xA, p.wd.d[g]), &sA, &cA);
+          sincos_cw(__fdiv_rn(xB, p.wd.d[g]), &sB, &cB);
+        }
         if (!vA) { sA = 0.f; cA = 0.f; }
         if (!vB) { sB = 0.f; cB = 0.f; }
       }
-      Opnd<true, 4> a;
+      Opnd<!FAST, 4> a;
       a.set(0, sA); a.set(1, cA); a.set(2, sB); a.set(3, cB);
 #pragma unroll
-      for (int nt = 0; nt < NTD; ++nt) mma_acc<true>(acc[c][nt], a, bz[nt]);
+      for (int nt = 0; nt < NTD; ++nt) mma_acc<!FAST>(acc[c][nt], a, bz[nt]);
     }
   }
   // ---- CTA reduction in shared memory, then one set of global atomics per CTA
@@ -1645,6 +1654,14 @@ extern "C" int regat_geo_bwd(int B, int N, int nongt_dim, int H, int dirs, int E
                              const float* pos_emb, const float* wave_div_host, const float* dl, const float* gbias,
                              float* dwg, int64_t dwg_stride, float* dbg, int64_t dbg_stride, float* dc,
                              regat_stream_t stream) {
+  return regat_geo_bwd_ex(B, N, nongt_dim, H, dirs, E, boxes, pos_emb, wave_div_host, dl, gbias, dwg, dwg_stride, dbg, dbg_stride, dc,
+                          0, stream);
+}
+
+extern "C" int regat_geo_bwd_ex(int B, int N, int nongt_dim, int H, int dirs, int E, const float* boxes,
+                                const float* pos_emb, const float* wave_div_host, const float* dl, const float* gbias,
+                                float* dwg, int64_t dwg_stride, float* dbg, int64_t dbg_stride, float* dc, int fast_math,
+                                regat_stream_t stream) {
   REGAT_REQUIRE(E == EMB, REGAT_ERR_UNSUPPORTED, "geo_bwd: pos_emb_dim must be 64");
   REGAT_REQUIRE(dl && gbias && dwg, REGAT_ERR_ARG, "geo_bwd: null pointer");
   REGAT_REQUIRE((boxes != nullptr) != (pos_emb != nullptr), REGAT_ERR_ARG, "geo_bwd: pass exactly one of boxes / pos_emb");
@@ -1652,14 +1669,14 @@ extern "C" int regat_geo_bwd(int B, int N, int nongt_dim, int H, int dirs, int E
   if (B <= 0 || N <= 0) return REGAT_OK;
   GeoBwdParams p;
   p.B = B; p.N = N; p.M = nongt_dim < N ? nongt_dim : N; p.H = H; p.dirs = dirs;
-  p.boxes = boxes; p.pos_emb = pos_emb;
+  p.boxes = boxes; p.pos_emb = pos_emb; p.fast = (fast_math && boxes) ? 1 : 0;
   for (int k = 0; k < 8; ++k) p.wd.d[k] = wave_div_host ? wave_div_host[k] : 1.f;
   p.dl = dl; p.gbias = gbias; p.dwg = dwg; p.dwg_stride = dwg_stride; p.dbg = dbg; p.dbg_stride = dbg_stride; p.dc = dc;
   const int DH = dirs * H;
   const long long ksteps = ((long long)B * p.N * p.M + 7) / 8;
   const int blocks = (int)std::max<long long>(1, std::min<long long>((ksteps + 7) / 8, (long long)num_sms() * 2));
   cudaStream_t st = (cudaStream_t)stream;
-#define REGAT_GB_CASE(X) { geo_bwd_kernel<X><<<blocks, 256, 0, st>>>(p); }
+#define REGAT_GB_CASE(X) { if (p.fast) geo_bwd_kernel<X, true><<<blocks, 256, 0, st>>>(p); else geo_bwd_kernel<X, false><<<blocks, 256, 0, st>>>(p); }
   if (DH == 32) REGAT_GB_CASE(32)
   else if (DH == 24) REGAT_GB_CASE(24)
   else if (DH == 16) REGAT_GB_CASE(16)
