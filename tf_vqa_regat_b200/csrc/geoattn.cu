@@ -1139,7 +1139,7 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const BwdParams p) {
 //            dL replaces P in HBM (fp32, read by the geometry reduction); dL^T, P^T (bf16) and the gated dO go to shared memory.
 //   phase B (warp <-> {dK, dV'} x key tile): dK = dL^T Q / 8, dV' = P^T dO with the query index as k: the A fragments are
 //            32-bit reads of the transposed tiles, the B fragments are 8-element row pieces paired across two query rows by
-//            one PRMT each (Q straight from global memory, dO from shared memory).
+//            one PRMT each (Q is copied to shared memory with cp.async while phase A runs, dO is written there by phase A).
 // Same fragment conventions as the forward fast path; dL and P are rounded to bf16 only as MMA operands.
 template <int NTS>
 __global__ void __launch_bounds__(128, 4) attn_bwd_bf16_kernel(const BwdParams p) {
@@ -1148,8 +1148,9 @@ __global__ void __launch_bounds__(128, 4) attn_bwd_bf16_kernel(const BwdParams p
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = p.N, M = p.M, D = p.D, H = p.H, NP = p.NP;
   const int LDT = NP + 8;                     // bf16 row stride of the transposed tiles
-  bf16* dOs = reinterpret_cast<bf16*>(smem_raw);                      // [NP][LDO]
-  bf16* LT = dOs + NP * LDO;                                          // [16 NKS][LDT]   dL^T
+  bf16* dOs = reinterpret_cast<bf16*>(smem_raw);                      // [NP][LDO]   gated dO
+  bf16* Qs = dOs + NP * LDO;                                          // [NP][LDO]   Q (cp.async, lands during phase A)
+  bf16* LT = Qs + NP * LDO;                                           // [16 NKS][LDT]   dL^T
   bf16* PT = LT + 16 * NKS * LDT;                                     // [16 NKS][LDT]   P^T
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int h = blockIdx.x % H, d = (blockIdx.x / H) % p.dirs, b = blockIdx.x / (H * p.dirs);
@@ -1161,6 +1162,18 @@ __global__ void __launch_bounds__(128, 4) attn_bwd_bf16_kernel(const BwdParams p
   float* P_g = p.p_dl + ((size_t)b * p.dirs * H + dh) * N * M;
   const bf16* kbase = KV + (size_t)b * M * ldkv + d * D + h * HD;
   const bf16* vbase = KV + (size_t)b * M * ldkv + (p.dirs + d) * D + h * HD;
+
+  // Q tile of this (dir, head) -> shared memory, asynchronously: phase B reads it exactly like the gated dO tile
+  {
+    const bf16* qsrc = Q + (size_t)b * N * ldq + d * D + h * HD;
+    for (int x = tid; x < NP * (HD / 8); x += 128) {
+      const int i = x >> 3, c8 = (x & 7) * 8;
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(Qs + i * LDO + c8);
+      const bf16* src = qsrc + (size_t)min(i, N - 1) * ldq + c8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
 
   // ---- phase A
   for (int mt = warp; mt * 16 < N; mt += 4) {
@@ -1301,11 +1314,13 @@ __global__ void __launch_bounds__(128, 4) attn_bwd_bf16_kernel(const BwdParams p
       }
     }
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
 
   // ---- phase B: warp = (kind, key tile).  kind 0: dK = dL^T Q / 8;  kind 1: dV' = P^T dO
   const int kind = warp & 1;
   const bf16* XT = kind ? PT : LT;
+  const bf16* Bs = kind ? dOs : Qs;
   for (int jm = warp >> 1; jm * 16 < M; jm += 2) {
     float acc[8][4];
 #pragma unroll
@@ -1320,18 +1335,10 @@ __global__ void __launch_bounds__(128, 4) attn_bwd_bf16_kernel(const BwdParams p
       a[3] = *reinterpret_cast<const uint32_t*>(xr1 + 16 * ks + 8);
       uint4 bw[4];
       const int q0 = 16 * ks + 2 * t;
-      if (kind == 0) {
-        const bf16* qb = Q + (size_t)b * N * ldq + d * D + h * HD + 8 * g;
-        bw[0] = ldg128(qb + (size_t)min(q0, N - 1) * ldq);
-        bw[1] = ldg128(qb + (size_t)min(q0 + 1, N - 1) * ldq);
-        bw[2] = ldg128(qb + (size_t)min(q0 + 8, N - 1) * ldq);
-        bw[3] = ldg128(qb + (size_t)min(q0 + 9, N - 1) * ldq);
-      } else {
-        bw[0] = *reinterpret_cast<const uint4*>(dOs + (q0) * LDO + 8 * g);
-        bw[1] = *reinterpret_cast<const uint4*>(dOs + (q0 + 1) * LDO + 8 * g);
-        bw[2] = *reinterpret_cast<const uint4*>(dOs + (q0 + 8) * LDO + 8 * g);
-        bw[3] = *reinterpret_cast<const uint4*>(dOs + (q0 + 9) * LDO + 8 * g);
-      }
+      bw[0] = *reinterpret_cast<const uint4*>(Bs + (q0) * LDO + 8 * g);
+      bw[1] = *reinterpret_cast<const uint4*>(Bs + (q0 + 1) * LDO + 8 * g);
+      bw[2] = *reinterpret_cast<const uint4*>(Bs + (q0 + 8) * LDO + 8 * g);
+      bw[3] = *reinterpret_cast<const uint4*>(Bs + (q0 + 9) * LDO + 8 * g);
 #pragma unroll
       for (int ot = 0; ot < 8; ++ot) {
         const uint32_t sel = (ot & 1) ? 0x7632u : 0x5410u;
@@ -1379,7 +1386,6 @@ __global__ void __launch_bounds__(256, 2) geo_bwd_kernel(const GeoBwdParams p) {
   __shared__ float redc;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int N = p.N, NM = p.N * p.M;
-  const long long total = (long long)p.B * NM;
   const float LOGMIN = logf(1e-6f);
   for (int x = tid; x < EMB * DH; x += 256) red[x] = 0.f;
   if (tid < DH) redb[tid] = 0.f;
@@ -1396,42 +1402,42 @@ __global__ void __launch_bounds__(256, 2) geo_bwd_kernel(const GeoBwdParams p) {
 #pragma unroll
   for (int nt = 0; nt < NTD; ++nt) bsum[nt] = 0.f;
 
-  const long long nsteps = (total + 7) / 8;
+  // k-step = 8 consecutive pairs of ONE graph (the last k-step of a graph is padded), so all index math is 32-bit
+  const int KPG = (NM + 7) / 8;
+  const int nsteps = p.B * KPG;
   const float winv = 1.0f / p.wd.d[g];
-  for (long long ks = (long long)blockIdx.x * 8 + warp; ks < nsteps; ks += (long long)gridDim.x * 8) {
-    const long long pb = ks * 8;
-    // lane L evaluates geometry term L%4 of pair pb + L/4
+  for (int ks = blockIdx.x * 8 + warp; ks < nsteps; ks += gridDim.x * 8) {
+    const int bq = ks / KPG, f0 = (ks - bq * KPG) * 8;
+    // lane L evaluates geometry term L%4 of pair f0 + L/4
     float mine = 0.f;
     {
-      const long long pq = pb + g;
-      if (pq < total && !p.pos_emb) {
-        const int bq = (int)(pq / NM), f = (int)(pq - (long long)bq * NM), ip = f / N, jp = f - ip * N;
-        const float4 oi = box_terms(p.boxes + ((size_t)bq * N + ip) * 4), oj = box_terms(p.boxes + ((size_t)bq * N + jp) * 4);
+      const int fq = f0 + g;
+      if (fq < NM && !p.pos_emb) {
+        const int ip = fq / N, jp = fq - ip * N;
+        const float* bx = p.boxes + (size_t)bq * N * 4;
+        const float4 oi = box_terms(bx + ip * 4), oj = box_terms(bx + jp * 4);
         mine = FAST ? pair_log_term_fast(oi, oj, t) : pair_log_term(oi, oj, t);
       }
     }
-    const long long pA = pb + t, pB = pb + t + 4;
-    const bool vA = pA < total, vB = pB < total;
-    const int bA = vA ? (int)(pA / NM) : 0, fA = vA ? (int)(pA - (long long)bA * NM) : 0;
-    const int bB = vB ? (int)(pB / NM) : 0, fB = vB ? (int)(pB - (long long)bB * NM) : 0;
+    const int fA = f0 + t, fB = fA + 4;
+    const bool vA = fA < NM, vB = fB < NM;
+    const int bA = bq, bB = bq;
     // B fragments: dz = dL / z where z = exp(gbias) >= 1e-6, else 0    (d log(max(relu(z), 1e-6)) / dz)
+    const float* dlb = p.dl + (size_t)bq * DH * NM;
+    const float* gbb = p.gbias + (size_t)bq * DH * NM;
     Opnd<!FAST, 2> bz[NTD];
+    float dlA[NTD], dlB[NTD], gbA[NTD], gbB[NTD];
+#pragma unroll
+    for (int nt = 0; nt < NTD; ++nt) {      // all loads of the k-step first
+      const int off = (8 * nt + g) * NM;
+      dlA[nt] = vA ? __ldg(dlb + off + fA) : 0.f; gbA[nt] = vA ? __ldg(gbb + off + fA) : 0.f;
+      dlB[nt] = vB ? __ldg(dlb + off + fB) : 0.f; gbB[nt] = vB ? __ldg(gbb + off + fB) : 0.f;
+    }
 #pragma unroll
     for (int nt = 0; nt < NTD; ++nt) {
-      const int dh = 8 * nt + g;
-      float dzA = 0.f, dzB = 0.f;
-      if (vA) {
-        const size_t idx = ((size_t)bA * DH + dh) * NM + fA;
-        const float dl = __ldg(p.dl + idx), gb = __ldg(p.gbias + idx);
-        csum += dl;
-        dzA = gb > LOGMIN ? dl * (FAST ? __expf(-gb) : expf(-gb)) : 0.f;
-      }
-      if (vB) {
-        const size_t idx = ((size_t)bB * DH + dh) * NM + fB;
-        const float dl = __ldg(p.dl + idx), gb = __ldg(p.gbias + idx);
-        csum += dl;
-        dzB = gb > LOGMIN ? dl * (FAST ? __expf(-gb) : expf(-gb)) : 0.f;
-      }
+      csum += dlA[nt] + dlB[nt];
+      const float dzA = (vA && gbA[nt] > LOGMIN) ? dlA[nt] * (FAST ? __expf(-gbA[nt]) : expf(-gbA[nt])) : 0.f;
+      const float dzB = (vB && gbB[nt] > LOGMIN) ? dlB[nt] * (FAST ? __expf(-gbB[nt]) : expf(-gbB[nt])) : 0.f;
       bsum[nt] += dzA + dzB;
       bz[nt].set(0, dzA); bz[nt].set(1, dzB);
     }
@@ -1553,7 +1559,7 @@ int launch_bwd_nts(const BwdParams& p, cudaStream_t st) {
 }
 int launch_bwd_bf16(const BwdParams& p, cudaStream_t st) {
   constexpr int NTS = 3, NKS = 2;
-  const size_t smem = sizeof(bf16) * ((size_t)p.NP * (HD + 8) + 2 * (size_t)16 * NKS * (p.NP + 8));
+  const size_t smem = sizeof(bf16) * (2 * (size_t)p.NP * (HD + 8) + 2 * (size_t)16 * NKS * (p.NP + 8));
   REGAT_TRY(set_smem(attn_bwd_bf16_kernel<NTS>, smem));
   attn_bwd_bf16_kernel<NTS><<<p.B * p.dirs * p.H, 128, smem, st>>>(p);
   REGAT_POST_LAUNCH();
