@@ -269,6 +269,13 @@ typedef void (*regat_grad_ready_fn)(void* user, int64_t offset, int64_t numel);
 REGAT_API int regat_engine_set_grad_callback(regat_engine* e, regat_grad_ready_fn fn, void* user);
 /* Number of kernel launches the last engine call issued (for bench.py's gpu_launches). */
 REGAT_API int regat_engine_last_launches(const regat_engine* e);
+/* Tell the engine that the caller wrote the parameter buffer (checkpoint load, set_weights).  The engine caches what it
+ * derives from the parameters -- the per-tensor ||v||^2 partial sums that regat_engine_update leaves behind for the next
+ * forward pass, and (between updates) alpha = g/||v|| and the bf16 copies of the effective kernels, so that forward-only
+ * callers do not re-derive them on every call; this call drops those caches.  Not needed after regat_engine_bind or
+ * regat_engine_update (they invalidate what they must themselves).  A CUDA graph captured from an engine call contains
+ * only the work that call needed at capture time: re-capture after changing the parameters from outside. */
+REGAT_API int regat_engine_params_changed(regat_engine* e);
 /* Copies the configuration the engine was created with. */
 REGAT_API int regat_engine_config(const regat_engine* e, regat_config* cfg);
 /* Overrides the 8 sinusoid divisors 1000^(k/8) (default: powf in C).  The Python binding passes the

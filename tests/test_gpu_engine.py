@@ -167,3 +167,29 @@ def test_gradients_bf16_close():
         g, r = got[name].ravel().astype(np.float64), grads[name].ravel()
         cos = float(g @ r / (np.linalg.norm(g) * np.linalg.norm(r) + 1e-30))
         assert cos > 0.995, (name, cos)
+
+
+@pytest.mark.parametrize("dtype,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_cached_weight_state_follows_the_parameters(dtype, tol):
+    """The engine caches alpha / low-precision kernels between updates and lets the update hand ||v||^2 to the next pass:
+    forward after load_params, after an update and after a second load_params must each see the current parameters."""
+    cfg, inp, flat, eng, dev, named64, args64 = _setup(SMALL, 3, 36, False, True, dtype)
+    ref0 = onp.forward(named64, cfg, *args64)["logits"]
+    a = eng.forward(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"])
+    b = eng.forward(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"])      # served from the cached state
+    assert torch.equal(a, b)
+    assert _rel(a.cpu().numpy(), ref0) < tol
+    # one train step: the next forward must use the UPDATED parameters (same as a fresh engine loaded with them)
+    eng.fwd_bwd(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"], dev["target"])
+    eng.update(1e-2, 1)
+    after = eng.forward(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"])
+    from tf_vqa_regat_b200.engine import HotPathEngine
+    fresh = HotPathEngine(cfg, 3, 36, dtype=dtype)
+    fresh.load_params(eng.params.clone())
+    want = fresh.forward(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"])
+    assert _rel(after.cpu().numpy(), want.cpu().numpy()) < 1e-5      # ||v||^2 summed in a different order only
+    assert _rel(after.cpu().numpy(), ref0) > 10 * _rel(after.cpu().numpy(), want.cpu().numpy())
+    # an outside write announced with load_params / params_changed drops the caches
+    eng.load_params(flat)
+    again = eng.forward(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"])
+    assert _rel(again.cpu().numpy(), a.cpu().numpy()) < 1e-6

@@ -67,6 +67,7 @@ SIGNATURES = {
     "regat_engine_train_step": [vp, i32, i32, vp, vp, vp, vp, vp, f32, i32, vp, vp],
     "regat_engine_set_grad_callback": [vp, vp, vp],
     "regat_engine_last_launches": [vp],
+    "regat_engine_params_changed": [vp],
     "regat_engine_config": [vp, C.POINTER(Config)],
     "regat_engine_set_wave_div": [vp, vp],
     "regat_engine_finalize_grads": [vp, vp],

@@ -53,7 +53,7 @@ struct regat_engine {
   long long ws_need = 0;
   // workspace carve (byte offsets)
   struct Buf { long long off = -1; };
-  Buf lowp, gbias, sumsq, alpha, invn, scal, stats, partials, featT, qattT, qlastT, v0, mask, qs, s, strunc, Qb, KVb, v1, P, GB, gate, uqe,
+  Buf lowp, gbias, sumsq, alpha, invn, scal, stats, partials, vpart, featT, qattT, qlastT, v0, mask, qs, s, strunc, Qb, KVb, v1, P, GB, gate, uqe,
       uw, cb, weff, att, pooled, pv, joint, hid, logits, dlogits, dhid, djoint, dpv, duqe, dpooled, dv1, dweff, dcb, duw,
       dQb, dKVb, ds, dstrunc, dsq, dwc3;
   int a_pad = 0;
@@ -63,6 +63,8 @@ struct regat_engine {
   TensorList tl_gather;
   int last_launches = 0;
   int grads_final = 0;
+  int sumsq_fresh = 0;             // the per-chunk ||v||^2 partials were written by the last update and params are untouched since
+  int lowp_fresh = 0;              // alpha / bf16 weight copies / gathered biases match params (forward-only callers reuse them)
   // small independent work (BUTD question branch, tiny weight gradients) runs on a side stream, forked / joined with events
   cudaStream_t side = nullptr;
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -158,7 +160,8 @@ long long carve(regat_engine* e) {
   take(e->sumsq, nl * 4); take(e->alpha, nl * 4); take(e->invn, nl * 4);
   take(e->scal, 64 * 4);                       // [0]=label const c, [1]=dc, [2]=loss, [3]=score
   take(e->stats, 2 * MAX_TENSORS * 4);
-  take(e->partials, 2 * 8192 * 4);             // per-chunk partial sums of the weight-norm / optimizer reductions
+  take(e->partials, 2 * 8192 * 4);             // per-chunk partial sums of the optimizer reductions
+  take(e->vpart, 8192 * 4);                    // per-chunk ||v||^2 (written by wn_prepare or, after a step, by the update itself)
   take(e->featT, e->dtype == REGAT_BF16 ? R * V * 2 : 0);
   take(e->qattT, e->dtype == REGAT_BF16 ? B * Q * 2 : 0);
   take(e->qlastT, e->dtype == REGAT_BF16 ? B * Q * 2 : 0);
@@ -204,6 +207,10 @@ void build_lists(regat_engine* e) {
   }
   e->chunks_v = build_tensor_list(tv);
   e->chunks_opt = build_tensor_list(to);
+  for (int j = 0, i = 0; j < to.n; ++j) {       // kernels appear in the same order in both lists
+    to.vchunk_start[j] = 0;
+    if (to.kind[j] == 0) to.vchunk_start[j] = tv.chunk_start[i++];
+  }
   TensorList& tg = e->tl_gather;
   memset(&tg, 0, sizeof(tg));
   const long long D = e->cfg.rel_dim, Hd = e->cfg.q_dim;
@@ -294,16 +301,18 @@ int fc_wgrad(regat_engine* e, cudaStream_t st, int l, long long w_row0, int rows
 }
 
 int prepare_weights(regat_engine* e, cudaStream_t st) {
+  if (e->lowp_fresh) return REGAT_OK;
   float* sumsq = e->at<float>(e->sumsq);
   REGAT_REQUIRE(e->chunks_v <= 8192 && e->chunks_opt <= 8192, REGAT_ERR_UNSUPPORTED, "engine: parameter buffer too large for the partial-sum scratch");
-  REGAT_TRY(k_wn_prepare(e->params, e->tl_v, e->chunks_v, sumsq, nullptr, st, e->at<float>(e->partials)));
-  REGAT_TRY(k_wn_alpha(e->params, e->tl_v, sumsq, e->at<float>(e->alpha), e->at<float>(e->invn), st, e->at<float>(e->partials)));
+  if (!e->sumsq_fresh) REGAT_TRY(k_wn_prepare(e->params, e->tl_v, e->chunks_v, sumsq, nullptr, st, e->at<float>(e->vpart)));
+  REGAT_TRY(k_wn_alpha(e->params, e->tl_v, sumsq, e->at<float>(e->alpha), e->at<float>(e->invn), st, e->at<float>(e->vpart)));
   if (e->dtype == REGAT_BF16) {
     REGAT_TRY(k_wn_scaled_copy(e->params, e->tl_v, e->chunks_v, e->at<float>(e->alpha), e->atv(e->lowp), st));
     REGAT_TRY(k_gather(e->params, e->tl_gather, e->at<float>(e->gbias), st));
   }
   const Layer& LL = e->layers[e->l_label];
   REGAT_TRY(k_label_const(e->params, LL.v_off, LL.b_off, alphap(e, e->l_label), e->at<float>(e->scal), st));
+  e->lowp_fresh = 1;
   return REGAT_OK;
 }
 
@@ -670,6 +679,7 @@ extern "C" int regat_engine_bind(regat_engine* e, float* params, float* grads, f
                 REGAT_ERR_ALIGN, "engine_bind: buffers must be 256-byte aligned");
   e->params = params; e->grads = grads; e->am = adamax_m; e->au = adamax_u;
   e->ws = static_cast<unsigned char*>(workspace); e->ws_bytes = workspace_bytes;
+  e->sumsq_fresh = 0; e->lowp_fresh = 0;
   return REGAT_OK;
 }
 
@@ -723,8 +733,11 @@ extern "C" int regat_engine_update(regat_engine* e, float lr, int step, regat_st
   hp.lr_t = (float)((double)lr / (1.0 - pow((double)e->cfg.beta1, (double)step)));
   hp.beta1 = e->cfg.beta1; hp.beta2 = e->cfg.beta2; hp.eps = e->cfg.eps; hp.clip = e->cfg.grad_clip;
   hp.grads_are_final = e->grads_final;
+  // the update leaves ||v_new||^2 per chunk in `vpart`: the next forward pass skips wn_prepare's read of the parameters
   REGAT_TRY(k_opt_update(e->params, e->grads, e->am, e->au, e->tl_opt, e->chunks_opt, e->at<float>(e->stats), e->at<float>(e->alpha),
-                         e->at<float>(e->invn), hp, st));
+                         e->at<float>(e->invn), hp, st, e->at<float>(e->vpart)));
+  e->sumsq_fresh = 1;
+  e->lowp_fresh = 0;
   e->last_launches = launch_counter() - l0;
   return REGAT_OK;
 }
@@ -741,6 +754,13 @@ extern "C" int regat_engine_train_step(regat_engine* e, int B, int N, const floa
 }
 
 extern "C" int regat_engine_last_launches(const regat_engine* e) { return e ? e->last_launches : 0; }
+
+// The caller has written the parameter buffer (checkpoint load, set_weights, ...): cached weight-norm statistics are stale.
+extern "C" int regat_engine_params_changed(regat_engine* e) {
+  REGAT_REQUIRE(e, REGAT_ERR_ARG, "engine is null");
+  e->sumsq_fresh = 0; e->lowp_fresh = 0;
+  return REGAT_OK;
+}
 
 extern "C" int regat_engine_set_grad_callback(regat_engine* e, regat_grad_ready_fn fn, void* user) {
   REGAT_REQUIRE(e, REGAT_ERR_ARG, "engine is null");

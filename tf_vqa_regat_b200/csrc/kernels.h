@@ -18,6 +18,7 @@ struct TensorList {
   int kind[MAX_TENSORS];            // 0 = weight-normed kernel v, 1 = bias
   int layer[MAX_TENSORS];           // index into alpha / inv_norm
   int chunk_start[MAX_TENSORS + 1]; // first block handling each tensor (filled by build_tensor_list)
+  int vchunk_start[MAX_TENSORS];    // kind-0 tensors of the optimizer list: first chunk of the same tensor in the weight-norm list
 };
 int build_tensor_list(TensorList& tl);  // returns number of blocks
 
@@ -57,7 +58,7 @@ int k_segsum(int dt, const void* x, const float* w, int B, int N, int D, void* o
 int k_addrows(int dt, void* dst, const void* src, int B, int N, int M, int D, cudaStream_t st);
 int k_opt_reduce(const float* params, const float* grads, const TensorList& tl, int chunks, float* partials, float* stats, cudaStream_t st);
 int k_opt_update(float* params, const float* grads, float* m, float* u, const TensorList& tl, int chunks, const float* stats,
-                 const float* alpha, const float* inv_norm, const OptHyper& hp, cudaStream_t st);
+                 const float* alpha, const float* inv_norm, const OptHyper& hp, cudaStream_t st, float* vpartials = nullptr);
 int k_opt_finalize(const float* params, float* grads, const TensorList& tl, int chunks, const float* stats, const float* alpha,
                    const float* inv_norm, cudaStream_t st);
 int k_label_const(const float* params, long long v_off, long long b_off, const float* alpha_l, float* c, cudaStream_t st);

@@ -55,15 +55,25 @@ __global__ void __launch_bounds__(256) wn_prepare_kernel(const float* __restrict
   while (l + 1 < tl.n && (int)blockIdx.x >= tl.chunk_start[l + 1]) ++l;
   const long long base = (long long)(blockIdx.x - tl.chunk_start[l]) * WN_CHUNK;
   const float* v = params + tl.off[l];
-  const long long n = tl.numel[l];
+  const long long n = tl.numel[l], end = min(base + (long long)WN_CHUNK, n);
   float ss = 0.f;
-  for (long long i = base + threadIdx.x; i < min(base + (long long)WN_CHUNK, n); i += 256) {
-    const float x = v[i];
-    ss = fmaf(x, x, ss);
-    if (lowp) {
-      const int cols = tl.cols[l];
-      const long long r = i / cols, c = i - r * cols;
-      lowp[tl.off_lowp[l] + r * tl.ld_lowp[l] + c] = __float2bfloat16_rn(x);
+  if (!lowp && (end - base) == WN_CHUNK) {
+    // full chunk (tensors start 256-byte aligned, chunks are 16 KB): four independent 128-bit loads per thread
+    const float4* v4 = reinterpret_cast<const float4*>(v + base);
+    float4 x[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) x[u] = __ldg(v4 + threadIdx.x + 256 * u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ss += x[u].x * x[u].x + x[u].y * x[u].y + x[u].z * x[u].z + x[u].w * x[u].w;
+  } else {
+    for (long long i = base + threadIdx.x; i < end; i += 256) {
+      const float x = v[i];
+      ss = fmaf(x, x, ss);
+      if (lowp) {
+        const int cols = tl.cols[l];
+        const long long r = i / cols, c = i - r * cols;
+        lowp[tl.off_lowp[l] + r * tl.ld_lowp[l] + c] = __float2bfloat16_rn(x);
+      }
     }
   }
   ss = block_sum_256(ss, red);
@@ -86,13 +96,22 @@ __global__ void __launch_bounds__(256) wn_scaled_copy_kernel(const float* __rest
   const int cols = tl.cols[l], ld = tl.ld_lowp[l];
   bf16* dst = lowp + tl.off_lowp[l];
   if ((cols & 7) == 0 && (ld & 7) == 0) {
-    for (long long i = base + threadIdx.x * 8; i < min(base + (long long)WN_CHUNK, n); i += 256 * 8) {
-      float x[8];
-      ld8<float>(v + i, x);
+    const long long end = min(base + (long long)WN_CHUNK, n);
+    const long long i0 = base + threadIdx.x * 8, i1 = i0 + 256 * 8;      // WN_CHUNK = 2 x 256 x 8
+    float x0[8], x1[8];
+    if (i0 < end) ld8<float>(v + i0, x0);
+    if (i1 < end) ld8<float>(v + i1, x1);
+    if (i0 < end) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) x[u] *= a;
-      const long long r = i / cols, c = i - r * cols;
-      st8<bf16>(dst + r * ld + c, x);
+      for (int u = 0; u < 8; ++u) x0[u] *= a;
+      if (cols == ld) { st8<bf16>(dst + i0, x0); }
+      else { const long long r = i0 / cols, c = i0 - r * cols; st8<bf16>(dst + r * ld + c, x0); }
+    }
+    if (i1 < end) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) x1[u] *= a;
+      if (cols == ld) { st8<bf16>(dst + i1, x1); }
+      else { const long long r = i1 / cols, c = i1 - r * cols; st8<bf16>(dst + r * ld + c, x1); }
     }
   } else {
     for (long long i = base + threadIdx.x; i < min(base + (long long)WN_CHUNK, n); i += 256) {
@@ -568,7 +587,9 @@ __global__ void opt_stats_kernel(TensorList tl, const float* __restrict__ partia
 __global__ void __launch_bounds__(256) opt_update_kernel(float* __restrict__ params, const float* __restrict__ grads,
                                                          float* __restrict__ am, float* __restrict__ au, TensorList tl,
                                                          const float* __restrict__ stats, const float* __restrict__ alpha,
-                                                         const float* __restrict__ inv_norm, OptHyper hp) {
+                                                         const float* __restrict__ inv_norm, OptHyper hp,
+                                                         float* __restrict__ vpartials) {
+  __shared__ float red[8];
   int l = 0;
   while (l + 1 < tl.n && (int)blockIdx.x >= tl.chunk_start[l + 1]) ++l;
   const long long base = (long long)(blockIdx.x - tl.chunk_start[l]) * WN_CHUNK;
@@ -586,13 +607,21 @@ __global__ void __launch_bounds__(256) opt_update_kernel(float* __restrict__ par
     nrm = sqrtf(gg);
   }
   const float cs = hp.clip / fmaxf(nrm, hp.clip);           // tf.clip_by_norm
+  float ss = 0.f;
   for (long long i = base + threadIdx.x; i < end; i += 256) {
     const float w = params[off + i];
     const float g = cs * a * (grads[off + i] - proj * w);
     const float m = hp.beta1 * am[off + i] + (1.f - hp.beta1) * g;
     const float u = fmaxf(hp.beta2 * au[off + i], fabsf(g));
     am[off + i] = m; au[off + i] = u;
-    params[off + i] = w - hp.lr_t * m / (u + hp.eps);
+    const float wn = w - hp.lr_t * m / (u + hp.eps);
+    params[off + i] = wn;
+    ss = fmaf(wn, wn, ss);
+  }
+  // ||v_new||^2 per chunk, laid out like wn_prepare_kernel's partials: the next forward pass skips that read of the parameters
+  if (vpartials && tl.kind[l] == 0) {
+    ss = block_sum_256(ss, red);
+    if (threadIdx.x == 0) vpartials[tl.vchunk_start[l] + (blockIdx.x - tl.chunk_start[l])] = ss;
   }
   if (tl.kind[l] == 0 && base == 0 && threadIdx.x == 0) {    // the scalar g of this layer
     const long long go = tl.g_off[l];
@@ -783,8 +812,8 @@ int k_opt_reduce(const float* params, const float* grads, const TensorList& tl, 
   return REGAT_OK;
 }
 int k_opt_update(float* params, const float* grads, float* m, float* u, const TensorList& tl, int chunks, const float* stats,
-                 const float* alpha, const float* inv_norm, const OptHyper& hp, cudaStream_t st) {
-  opt_update_kernel<<<chunks, 256, 0, st>>>(params, grads, m, u, tl, stats, alpha, inv_norm, hp);
+                 const float* alpha, const float* inv_norm, const OptHyper& hp, cudaStream_t st, float* vpartials) {
+  opt_update_kernel<<<chunks, 256, 0, st>>>(params, grads, m, u, tl, stats, alpha, inv_norm, hp, vpartials);
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }

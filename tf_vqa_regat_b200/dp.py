@@ -84,6 +84,8 @@ class DataParallelTrainer:
     def broadcast_params(self, src: int = 0):
         if self.world > 1:
             dist.broadcast(self.engine.params, src=src, group=self.group)
+            if hasattr(self.engine, "params_changed"):
+                self.engine.params_changed()
 
     def fwd_bwd_allreduce(self, features, boxes, q_att, q_last, target):
         """Forward + backward on this rank's shard with the gradient all-reduce (overlapped when possible)."""

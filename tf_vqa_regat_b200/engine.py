@@ -70,6 +70,11 @@ class HotPathEngine:
         t = torch.as_tensor(np.asarray(flat, dtype=np.float32)) if not isinstance(flat, torch.Tensor) else flat
         assert t.numel() == self.param_elems
         self.params.copy_(t.to(self.device, torch.float32))
+        self.params_changed()
+
+    def params_changed(self):
+        """Call after writing `self.params` in place: cached weight-norm statistics are recomputed on the next pass."""
+        _lib.check(self.lib.regat_engine_params_changed(self._h))
 
     def named(self, buf=None):
         """name -> view into a flat buffer (default: params)."""
