@@ -67,7 +67,8 @@ struct regat_engine {
   int lowp_fresh = 0;              // alpha / bf16 weight copies / gathered biases match params (forward-only callers reuse them)
   // small independent work (BUTD question branch, tiny weight gradients) runs on a side stream, forked / joined with events
   cudaStream_t side = nullptr;
-  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  static constexpr int NEV = 10;
+  cudaEvent_t ev[NEV] = {};
   regat_grad_ready_fn grad_cb = nullptr;   // data parallel: called when a range of `grads` is final on the stream
   void* grad_cb_user = nullptr;
   template <typename T> T* at(const Buf& b) const { return reinterpret_cast<T*>(ws + b.off); }
@@ -319,7 +320,7 @@ int prepare_weights(regat_engine* e, cudaStream_t st) {
 int ensure_side(regat_engine* e) {
   if (e->side) return REGAT_OK;
   REGAT_CUDA(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
-  for (int i = 0; i < 6; ++i) REGAT_CUDA(cudaEventCreateWithFlags(&e->ev[i], cudaEventDisableTiming));
+  for (int i = 0; i < regat_engine::NEV; ++i) REGAT_CUDA(cudaEventCreateWithFlags(&e->ev[i], cudaEventDisableTiming));
   return REGAT_OK;
 }
 // side stream waits for everything enqueued on `from` so far
@@ -480,7 +481,7 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   // the classifier and of BUTD is off the critical path and goes to the side stream as soon as its operands exist.
   cudaStream_t sd = e->side;
   unsigned char* dqe = e->at<unsigned char>(e->duqe) + (size_t)Hd * es;
-  ColsumBatch cb_side, cb_mid;       // bias gradients, one multi-problem launch per backward stage
+  ColsumBatch cb_side, cb_qkv, cb_ds, cb_v0;   // bias gradients, one multi-problem launch per backward stage (all on the side stream)
   REGAT_TRY(fork_to(st, sd, e->ev[2]));                    // dlogits ready
   if (dt == REGAT_BF16 && e->use_tc && (A % 4) != 0) {
     // the [2Hd, A] gradient has unaligned rows (A = 3129): compute it with a padded pitch, then compact into the flat buffer
@@ -547,7 +548,17 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   REGAT_TRY(k_colsum_multi(dt, cb_side, sd));
   REGAT_TRY(fork_to(sd, st, e->ev[0]));   // join the side stream: BUTD + classifier gradients (the tail of the flat buffer) are final
   grads_ready(e, e->l_va, e->l_c3);
+  // The bias gradients (column sums -- HBM-bound) and the small question-side products run on the side stream next to the
+  // tensor-bound GEMMs of the main stream.  Gradient ranges are announced in the order they become final: attention layers,
+  // then self_weights + label FC, then v2out -- the data-parallel layer starts each all-reduce behind the rest of the backward.
+  REGAT_TRY(fork_to(st, sd, e->ev[6]));                    // dQb, dKVb final
   if (dt == REGAT_BF16 && e->use_tc) {
+    for (int d = 0; d < dirs; ++d) {
+      REGAT_TRY(bias_grad(e, sd, e->at<unsigned char>(e->dQb) + (size_t)d * D * es, dirs * D, R, D, gradB(e, e->l_q[d]), &cb_qkv));
+      REGAT_TRY(bias_grad(e, sd, e->at<unsigned char>(e->dKVb) + (size_t)d * D * es, 2 * dirs * D, Rm, D, gradB(e, e->l_k[d]), &cb_qkv));
+      REGAT_TRY(bias_grad(e, sd, e->at<unsigned char>(e->dKVb) + (size_t)(dirs + d) * D * es, 2 * dirs * D, Rm, D, gradB(e, e->l_out[d]), &cb_qkv));
+    }
+    REGAT_TRY(k_colsum_multi(dt, cb_qkv, sd));
     // weight gradients of side-by-side layers in one GEMM each (column blocks scattered to their own gradient slots),
     // input gradients with the direction / kind axis folded into K
     long long qo[2], kvo[4];
@@ -559,11 +570,8 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
     REGAT_TRY(gemm_tc(1, 0, D, dirs * D, R, e->atv(e->s), D, e->atv(e->dQb), dirs * D, gradW(e, e->l_q[0]), D, REGAT_F32, epi0(), 1, st, D, qo));
     REGAT_TRY(gemm_tc(1, 0, D, 2 * dirs * D, Rm, e->atv(e->strunc), D, e->atv(e->dKVb), 2 * dirs * D, gradW(e, e->l_k[0]), D, REGAT_F32, epi0(), 1,
                       st, D, kvo));
-    for (int d = 0; d < dirs; ++d) {
-      REGAT_TRY(bias_grad(e, st, e->at<unsigned char>(e->dQb) + (size_t)d * D * es, dirs * D, R, D, gradB(e, e->l_q[d]), &cb_mid));
-      REGAT_TRY(bias_grad(e, st, e->at<unsigned char>(e->dKVb) + (size_t)d * D * es, 2 * dirs * D, Rm, D, gradB(e, e->l_k[d]), &cb_mid));
-      REGAT_TRY(bias_grad(e, st, e->at<unsigned char>(e->dKVb) + (size_t)(dirs + d) * D * es, 2 * dirs * D, Rm, D, gradB(e, e->l_out[d]), &cb_mid));
-    }
+    REGAT_TRY(fork_to(sd, st, e->ev[7]));
+    grads_ready(e, e->l_pos[0], e->l_out[dirs - 1]);     // both attention layers
     EpiArgs ep = epi0();
     ep.accumulate = 1;                                 // ds already holds dout
     REGAT_TRY(dense(e, st, false, true, R, D, dirs * D, e->atv(e->dQb), dirs * D, lowp_at(e, e->gq_off), dirs * D, e->atv(e->ds), D, dt, ep));
@@ -574,27 +582,43 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
       unsigned char* dQd = e->at<unsigned char>(e->dQb) + (size_t)d * D * es;
       unsigned char* dKd = e->at<unsigned char>(e->dKVb) + (size_t)d * D * es;
       unsigned char* dVd = e->at<unsigned char>(e->dKVb) + (size_t)(dirs + d) * D * es;
-      REGAT_TRY(fc_wgrad(e, st, e->l_q[d], 0, R, D, e->atv(e->s), D, dQd, dirs * D, true, &cb_mid));
+      REGAT_TRY(fc_wgrad(e, st, e->l_q[d], 0, R, D, e->atv(e->s), D, dQd, dirs * D, true, &cb_qkv));
       REGAT_TRY(fc_dgrad(e, st, e->l_q[d], 0, R, D, dQd, dirs * D, e->atv(e->ds), D, dt, true));
-      REGAT_TRY(fc_wgrad(e, st, e->l_k[d], 0, Rm, D, e->atv(e->strunc), D, dKd, 2 * dirs * D, true, &cb_mid));
+      REGAT_TRY(fc_wgrad(e, st, e->l_k[d], 0, Rm, D, e->atv(e->strunc), D, dKd, 2 * dirs * D, true, &cb_qkv));
       REGAT_TRY(fc_dgrad(e, st, e->l_k[d], 0, Rm, D, dKd, 2 * dirs * D, e->atv(e->dstrunc), D, dt, d > 0));
-      REGAT_TRY(fc_wgrad(e, st, e->l_out[d], 0, Rm, D, e->atv(e->strunc), D, dVd, 2 * dirs * D, true, &cb_mid));
+      REGAT_TRY(fc_wgrad(e, st, e->l_out[d], 0, Rm, D, e->atv(e->strunc), D, dVd, 2 * dirs * D, true, &cb_qkv));
       REGAT_TRY(fc_dgrad(e, st, e->l_out[d], 0, Rm, D, dVd, 2 * dirs * D, e->atv(e->dstrunc), D, dt, true));
     }
+    REGAT_TRY(k_colsum_multi(dt, cb_qkv, sd));
+    REGAT_TRY(fork_to(sd, st, e->ev[7]));
+    grads_ready(e, e->l_pos[0], e->l_out[dirs - 1]);
   }
   REGAT_TRY(k_addrows(dt, e->atv(e->ds), e->atv(e->dstrunc), B, N, M, D, st));
-  // self_weights: s = alpha (v0 Ws[:D] + mask (q Ws[D:])) + b
-  REGAT_TRY(fc_wgrad(e, st, e->l_self, 0, R, D, v0, D, e->atv(e->ds), D, true, &cb_mid));
-  REGAT_TRY(k_segsum(dt, e->atv(e->ds), e->at<float>(e->mask), B, N, D, e->atv(e->dsq), st));
-  REGAT_TRY(fc_wgrad(e, st, e->l_self, D, B, Q, qatt, Q, e->atv(e->dsq), D, false));
-  REGAT_TRY(k_colsum_multi(dt, cb_mid, st));
-  grads_ready(e, e->l_self, e->l_va - 1);   // self_weights, label FC and both attention layers
-  if (dq_att) REGAT_TRY(fc_dgrad(e, st, e->l_self, D, B, Q, e->atv(e->dsq), D, dq_att, Q, REGAT_F32, false));
+  // self_weights: s = alpha (v0 Ws[:D] + mask (q Ws[D:])) + b.   ds is final: its column sum, the masked segment sum and the
+  // question-side products go to the side stream
+  REGAT_TRY(fork_to(st, sd, e->ev[8]));
+  REGAT_TRY(bias_grad(e, sd, e->atv(e->ds), D, R, D, gradB(e, e->l_self), &cb_ds));
+  REGAT_TRY(k_colsum_multi(dt, cb_ds, sd));
+  REGAT_TRY(k_segsum(dt, e->atv(e->ds), e->at<float>(e->mask), B, N, D, e->atv(e->dsq), sd));
+  REGAT_TRY(fc_wgrad(e, sd, e->l_self, D, B, Q, qatt, Q, e->atv(e->dsq), D, false));
+  if (dq_att) REGAT_TRY(fc_dgrad(e, sd, e->l_self, D, B, Q, e->atv(e->dsq), D, dq_att, Q, REGAT_F32, false));
+  REGAT_TRY(fork_to(sd, sd, e->ev[9]));                    // (record only: the main stream waits for it below)
   if (e->l_v2out >= 0) {
-    // dv0 = (dv1 [residual] + alpha ds Ws[:D]^T) o (v0 > 0), in place in the dv1 buffer; then v2out's gradients
+    // dv0 = (dv1 [residual] + alpha ds Ws[:D]^T) o (v0 > 0), in place in the dv1 buffer: the critical chain goes first
     REGAT_TRY(fc_dgrad(e, st, e->l_self, 0, R, D, e->atv(e->ds), D, e->atv(e->dv1), D, dt, cf.residual != 0, v0, D));
-    REGAT_TRY(fc_wgrad(e, st, e->l_v2out, 0, R, V, feat, V, e->atv(e->dv1), D, true));
+    REGAT_TRY(fork_to(st, sd, e->ev[2]));
+    REGAT_TRY(bias_grad(e, sd, e->atv(e->dv1), D, R, D, gradB(e, e->l_v2out), &cb_v0));
+    REGAT_TRY(k_colsum_multi(dt, cb_v0, sd));
+  }
+  REGAT_TRY(fc_wgrad(e, st, e->l_self, 0, R, D, v0, D, e->atv(e->ds), D, false));
+  REGAT_CUDA(cudaStreamWaitEvent(st, e->ev[9], 0));
+  grads_ready(e, e->l_self, e->l_label);                   // self_weights and the label FC
+  if (e->l_v2out >= 0) {
+    REGAT_TRY(fc_wgrad(e, st, e->l_v2out, 0, R, V, feat, V, e->atv(e->dv1), D, false));
+    REGAT_TRY(fork_to(sd, st, e->ev[3]));
     grads_ready(e, e->l_v2out, e->l_v2out);
+  } else {
+    REGAT_TRY(fork_to(sd, st, e->ev[3]));
   }
   e->grads_final = 0;
   return REGAT_OK;
@@ -647,7 +671,7 @@ extern "C" int regat_engine_create(const regat_config* cfg, int dtype, int max_b
 }
 extern "C" int regat_engine_destroy(regat_engine* e) {
   if (e) {
-    for (int i = 0; i < 6; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    for (int i = 0; i < regat_engine::NEV; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     if (e->side) cudaStreamDestroy(e->side);
     delete e;
   }
