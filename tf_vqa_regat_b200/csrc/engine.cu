@@ -306,13 +306,13 @@ int prepare_weights(regat_engine* e, cudaStream_t st) {
   float* sumsq = e->at<float>(e->sumsq);
   REGAT_REQUIRE(e->chunks_v <= 8192 && e->chunks_opt <= 8192, REGAT_ERR_UNSUPPORTED, "engine: parameter buffer too large for the partial-sum scratch");
   if (!e->sumsq_fresh) REGAT_TRY(k_wn_prepare(e->params, e->tl_v, e->chunks_v, sumsq, nullptr, st, e->at<float>(e->vpart)));
-  REGAT_TRY(k_wn_alpha(e->params, e->tl_v, sumsq, e->at<float>(e->alpha), e->at<float>(e->invn), st, e->at<float>(e->vpart)));
-  if (e->dtype == REGAT_BF16) {
-    REGAT_TRY(k_wn_scaled_copy(e->params, e->tl_v, e->chunks_v, e->at<float>(e->alpha), e->atv(e->lowp), st));
-    REGAT_TRY(k_gather(e->params, e->tl_gather, e->at<float>(e->gbias), st));
-  }
+  // alpha = g/||v|| per layer; the same one-block kernel also gathers the biases of side-by-side layers and evaluates the
+  // label-FC constant (graph_att_net.py:71)
   const Layer& LL = e->layers[e->l_label];
-  REGAT_TRY(k_label_const(e->params, LL.v_off, LL.b_off, alphap(e, e->l_label), e->at<float>(e->scal), st));
+  REGAT_TRY(k_wn_alpha(e->params, e->tl_v, sumsq, e->at<float>(e->alpha), e->at<float>(e->invn), st, e->at<float>(e->vpart),
+                       e->dtype == REGAT_BF16 ? &e->tl_gather : nullptr, e->at<float>(e->gbias), e->l_label, LL.v_off, LL.b_off,
+                       e->at<float>(e->scal)));
+  if (e->dtype == REGAT_BF16) REGAT_TRY(k_wn_scaled_copy(e->params, e->tl_v, e->chunks_v, e->at<float>(e->alpha), e->atv(e->lowp), st));
   e->lowp_fresh = 1;
   return REGAT_OK;
 }
@@ -340,15 +340,26 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
   REGAT_TRY(ensure_side(e));
   cudaStream_t sd = e->side;
   const size_t es = dtype_size(dt);
-  REGAT_TRY(prepare_weights(e, st));
-  // activations in the compute dtype
+  // activations in the compute dtype: the casts do not depend on the weights, so they run on the side stream while the main
+  // stream derives alpha and the bf16 kernels from the parameters (both HBM-bound, neither saturates the memory system alone)
   const void* feat = c.features; const void* qatt = c.q_att; const void* qlast = c.q_last;
   if (dt == REGAT_BF16) {
-    REGAT_TRY(k_cast(REGAT_BF16, c.q_last, e->atv(e->qlastT), (long long)B * Q, st));
-    qlast = e->atv(e->qlastT);
+    REGAT_TRY(fork_to(st, sd, e->ev[2]));
+    REGAT_TRY(k_cast(REGAT_BF16, c.features, e->atv(e->featT), (long long)R * V, sd));
+    REGAT_TRY(k_cast(REGAT_BF16, c.q_last, e->atv(e->qlastT), (long long)B * Q, sd));
+    REGAT_TRY(k_cast(REGAT_BF16, c.q_att, e->atv(e->qattT), (long long)B * Q, sd));
+    feat = e->atv(e->featT); qatt = e->atv(e->qattT); qlast = e->atv(e->qlastT);
+    REGAT_CUDA(cudaEventRecord(e->ev[3], sd));                       // casts done
   }
-  // ---- side stream: the question branch of BUTD depends only on q_last and the weights (fusion.py:37,47-52)
+  REGAT_TRY(prepare_weights(e, st));
+  // ---- side stream: the question branches depend only on q_last / q_att and the weights (fusion.py:37,47-52)
   REGAT_TRY(fork_to(st, sd, e->ev[0]));
+  if (dt == REGAT_BF16) REGAT_CUDA(cudaStreamWaitEvent(st, e->ev[3], 0));      // main stream: the bf16 features are ready
+  {  // qs = q_att Ws[D:]  (the question half of self_weights' input, relation_encoder.py:31-35); consumed by the s GEMM below
+    EpiArgs ep = epi0();
+    REGAT_TRY(dense(e, sd, false, false, B, D, Q, qatt, Q, W(e, e->l_self, D), ldW(e, e->l_self), e->atv(e->qs), D, REGAT_F32, ep));
+    REGAT_TRY(fork_to(sd, sd, e->ev[4]));                            // record: qs ready
+  }
   if (dt == REGAT_BF16 && e->use_tc) {
     EpiArgs ep = epi0();
     ep.bias = e->at<float>(e->gbias) + e->buqe_off;
@@ -365,11 +376,6 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
     REGAT_TRY(dense(e, sd, false, true, B, D, Hd, e->atv(e->uw), Hd, W(e, e->l_va), ldW(e, e->l_va), e->atv(e->weff), D, dt, ep));
   }
   // ---- main stream: the encoder
-  if (dt == REGAT_BF16) {
-    REGAT_TRY(k_cast(REGAT_BF16, c.features, e->atv(e->featT), (long long)R * V, st));
-    REGAT_TRY(k_cast(REGAT_BF16, c.q_att, e->atv(e->qattT), (long long)B * Q, st));
-    feat = e->atv(e->featT); qatt = e->atv(e->qattT);
-  }
   // v0 = relu(v2out(visual))                                            relation_encoder.py:78-79
   const void* v0 = feat;
   if (e->l_v2out >= 0) {
@@ -380,7 +386,7 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
   REGAT_TRY(k_rowmask(dt, v0, R, D, e->at<float>(e->mask), st));
   {
     EpiArgs ep = epi0();
-    REGAT_TRY(dense(e, st, false, false, B, D, Q, qatt, Q, W(e, e->l_self, D), ldW(e, e->l_self), e->atv(e->qs), D, REGAT_F32, ep));
+    REGAT_CUDA(cudaStreamWaitEvent(st, e->ev[4], 0));                // qs from the side stream
     ep.alpha = alpha_epi(e, e->l_self); ep.bias = biasp(e, e->l_self);
     ep.addend = e->at<float>(e->qs); ep.addend_ld = D; ep.addend_rows = N; ep.row_scale = e->at<float>(e->mask);
     ep.c2 = e->atv(e->strunc); ep.c2_ld = D; ep.c2_rows_in = N; ep.c2_rows_keep = M;
@@ -535,23 +541,24 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   // attention backward: dQ, dK, dV', dout (-> ds), dL (in place of P); then the geometry reduction
   REGAT_TRY(regat_attn_bwd(dt, B, N, cf.nongt_dim, D, H, dirs, e->atv(e->Qb), e->atv(e->KVb), e->atv(e->dv1),
                            e->at<uint64_t>(e->gate), e->at<float>(e->P), e->atv(e->dQb), e->atv(e->dKVb), e->atv(e->ds), st));
-  {
-    const Layer& P0 = e->layers[e->l_pos[0]];
-    const long long wstride = dirs > 1 ? e->layers[e->l_pos[1]].v_off - P0.v_off : 0;
-    const long long bstride = dirs > 1 ? e->layers[e->l_pos[1]].b_off - P0.b_off : 0;
-    REGAT_TRY(regat_geo_bwd_ex(B, N, cf.nongt_dim, H, dirs, cf.pos_emb_dim, c.boxes, nullptr, e->wave_div, e->at<float>(e->P),
-                               e->at<float>(e->GB), e->grads + P0.v_off, wstride, e->grads + P0.b_off, bstride, scal + 1,
-                               dt == REGAT_BF16, st));
-    const Layer& LL = e->layers[e->l_label];
-    REGAT_TRY(k_label_grad(scal + 1, e->grads, LL.v_off, LL.b_off, st));
-  }
   REGAT_TRY(k_colsum_multi(dt, cb_side, sd));
   REGAT_TRY(fork_to(sd, st, e->ev[0]));   // join the side stream: BUTD + classifier gradients (the tail of the flat buffer) are final
   grads_ready(e, e->l_va, e->l_c3);
   // The bias gradients (column sums -- HBM-bound) and the small question-side products run on the side stream next to the
   // tensor-bound GEMMs of the main stream.  Gradient ranges are announced in the order they become final: attention layers,
   // then self_weights + label FC, then v2out -- the data-parallel layer starts each all-reduce behind the rest of the backward.
-  REGAT_TRY(fork_to(st, sd, e->ev[6]));                    // dQb, dKVb final
+  REGAT_TRY(fork_to(st, sd, e->ev[6]));                    // dQb, dKVb, dL final
+  // the geometry reduction (SFU / issue bound, produces only dW_g, db_g, dc) runs beside the tensor-bound GEMMs
+  {
+    const Layer& P0 = e->layers[e->l_pos[0]];
+    const long long wstride = dirs > 1 ? e->layers[e->l_pos[1]].v_off - P0.v_off : 0;
+    const long long bstride = dirs > 1 ? e->layers[e->l_pos[1]].b_off - P0.b_off : 0;
+    REGAT_TRY(regat_geo_bwd_ex(B, N, cf.nongt_dim, H, dirs, cf.pos_emb_dim, c.boxes, nullptr, e->wave_div, e->at<float>(e->P),
+                               e->at<float>(e->GB), e->grads + P0.v_off, wstride, e->grads + P0.b_off, bstride, scal + 1,
+                               dt == REGAT_BF16, sd));
+    const Layer& LL = e->layers[e->l_label];
+    REGAT_TRY(k_label_grad(scal + 1, e->grads, LL.v_off, LL.b_off, sd));
+  }
   if (dt == REGAT_BF16 && e->use_tc) {
     for (int d = 0; d < dirs; ++d) {
       REGAT_TRY(bias_grad(e, sd, e->at<unsigned char>(e->dQb) + (size_t)d * D * es, dirs * D, R, D, gradB(e, e->l_q[d]), &cb_qkv));

@@ -31,7 +31,9 @@ struct OptHyper {
 int k_wn_prepare(const float* params, const TensorList& tl, int chunks, float* sumsq, void* lowp, cudaStream_t st, float* partials = nullptr);
 int k_wn_scaled_copy(const float* params, const TensorList& tl, int chunks, const float* alpha, void* lowp, cudaStream_t st);
 int k_gather(const float* src, const TensorList& tl, float* dst, cudaStream_t st);
-int k_wn_alpha(const float* params, const TensorList& tl, float* sumsq, float* alpha, float* inv_norm, cudaStream_t st, const float* partials = nullptr);
+int k_wn_alpha(const float* params, const TensorList& tl, float* sumsq, float* alpha, float* inv_norm, cudaStream_t st, const float* partials = nullptr,
+               const TensorList* gather = nullptr, float* gather_out = nullptr, int label_layer = -1, long long label_v_off = 0,
+               long long label_b_off = -1, float* label_c = nullptr);
 int k_cast(int to_dtype, const float* in, void* out, long long n, cudaStream_t st);
 int k_rowmask(int dt, const void* v, int rows, int D, float* mask, cudaStream_t st);
 int k_mul(int dt, const void* a, int lda, const void* b, int ldb, void* out, int ldo, int rows, int cols, cudaStream_t st);

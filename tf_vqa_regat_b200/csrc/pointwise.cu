@@ -85,38 +85,41 @@ __global__ void __launch_bounds__(256) wn_prepare_kernel(const float* __restrict
 
 // second pass of the bf16 weight preparation: lowp = bf16(alpha_l * v) = bf16(W_eff), placed at (off_lowp, ld_lowp) so that
 // layers sharing an input can sit side by side in one wide matrix (Q_0|Q_1, K_0|K_1|V'_0|V'_1, q2attention|question_embed).
-__global__ void __launch_bounds__(256) wn_scaled_copy_kernel(const float* __restrict__ params, TensorList tl,
+__global__ void __launch_bounds__(256) wn_scaled_copy_kernel(const float* __restrict__ params, TensorList tl, int chunks,
                                                              const float* __restrict__ alpha, bf16* __restrict__ lowp) {
+  // persistent: a few fat blocks per SM walk the 16 KB chunks (4634 two-iteration blocks spent their time being scheduled)
   int l = 0;
-  while (l + 1 < tl.n && (int)blockIdx.x >= tl.chunk_start[l + 1]) ++l;
-  const long long base = (long long)(blockIdx.x - tl.chunk_start[l]) * WN_CHUNK;
-  const float* v = params + tl.off[l];
-  const long long n = tl.numel[l];
-  const float a = alpha[tl.layer[l]];
-  const int cols = tl.cols[l], ld = tl.ld_lowp[l];
-  bf16* dst = lowp + tl.off_lowp[l];
-  if ((cols & 7) == 0 && (ld & 7) == 0) {
-    const long long end = min(base + (long long)WN_CHUNK, n);
-    const long long i0 = base + threadIdx.x * 8, i1 = i0 + 256 * 8;      // WN_CHUNK = 2 x 256 x 8
-    float x0[8], x1[8];
-    if (i0 < end) ld8<float>(v + i0, x0);
-    if (i1 < end) ld8<float>(v + i1, x1);
-    if (i0 < end) {
+  for (int chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
+    while (l + 1 < tl.n && chunk >= tl.chunk_start[l + 1]) ++l;
+    const long long base = (long long)(chunk - tl.chunk_start[l]) * WN_CHUNK;
+    const float* v = params + tl.off[l];
+    const long long n = tl.numel[l];
+    const float a = alpha[tl.layer[l]];
+    const int cols = tl.cols[l], ld = tl.ld_lowp[l];
+    bf16* dst = lowp + tl.off_lowp[l];
+    if ((cols & 7) == 0 && (ld & 7) == 0) {
+      const long long end = min(base + (long long)WN_CHUNK, n);
+      const long long i0 = base + threadIdx.x * 8, i1 = i0 + 256 * 8;      // WN_CHUNK = 2 x 256 x 8
+      float x0[8], x1[8];
+      if (i0 < end) ld8<float>(v + i0, x0);
+      if (i1 < end) ld8<float>(v + i1, x1);
+      if (i0 < end) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) x0[u] *= a;
-      if (cols == ld) { st8<bf16>(dst + i0, x0); }
-      else { const long long r = i0 / cols, c = i0 - r * cols; st8<bf16>(dst + r * ld + c, x0); }
-    }
-    if (i1 < end) {
+        for (int u = 0; u < 8; ++u) x0[u] *= a;
+        if (cols == ld) { st8<bf16>(dst + i0, x0); }
+        else { const long long r = i0 / cols, c = i0 - r * cols; st8<bf16>(dst + r * ld + c, x0); }
+      }
+      if (i1 < end) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u) x1[u] *= a;
-      if (cols == ld) { st8<bf16>(dst + i1, x1); }
-      else { const long long r = i1 / cols, c = i1 - r * cols; st8<bf16>(dst + r * ld + c, x1); }
-    }
-  } else {
-    for (long long i = base + threadIdx.x; i < min(base + (long long)WN_CHUNK, n); i += 256) {
-      const long long r = i / cols, c = i - r * cols;
-      dst[r * ld + c] = __float2bfloat16_rn(a * v[i]);
+        for (int u = 0; u < 8; ++u) x1[u] *= a;
+        if (cols == ld) { st8<bf16>(dst + i1, x1); }
+        else { const long long r = i1 / cols, c = i1 - r * cols; st8<bf16>(dst + r * ld + c, x1); }
+      }
+    } else {
+      for (long long i = base + threadIdx.x; i < min(base + (long long)WN_CHUNK, n); i += 256) {
+        const long long r = i / cols, c = i - r * cols;
+        dst[r * ld + c] = __float2bfloat16_rn(a * v[i]);
+      }
     }
   }
 }
@@ -127,26 +130,40 @@ __global__ void gather_kernel(const float* __restrict__ src, TensorList tl, floa
     for (long long i = threadIdx.x; i < tl.numel[l]; i += blockDim.x) dst[tl.off_lowp[l] + i] = src[tl.off[l] + i];
 }
 
+struct AlphaExtras {          // small per-forward chores folded into the one-block alpha kernel (two launches fewer per step)
+  int gather_n;
+  long long g_src[8], g_dst[8], g_numel[8];       // biases of side-by-side layers -> one contiguous vector
+  float* g_out;
+  int label_layer;                                 // index of the label FC in alpha[]; < 0: none
+  long long label_v_off, label_b_off;
+  float* label_c;
+};
 __global__ void wn_alpha_kernel(const float* __restrict__ params, TensorList tl, float* __restrict__ sumsq,
-                                const float* __restrict__ partials, float* alpha, float* inv_norm) {
+                                const float* __restrict__ partials, float* alpha, float* inv_norm, AlphaExtras ex) {
   // one warp per tensor; with `partials` the per-chunk sums are added in a fixed order (bitwise reproducible, so data-parallel
   // replicas that hold identical parameters compute identical alpha)
   const int l = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (l >= tl.n) return;
-  float ss;
-  if (partials) {
-    ss = 0.f;
-    for (int c = tl.chunk_start[l] + lane; c < tl.chunk_start[l + 1]; c += 32) ss += partials[c];
-    ss = warp_sum(ss);
-    if (lane == 0) sumsq[l] = ss;
-  } else {
-    ss = sumsq[l];
+  if (l < tl.n) {
+    float ss;
+    if (partials) {
+      ss = 0.f;
+      for (int c = tl.chunk_start[l] + lane; c < tl.chunk_start[l + 1]; c += 32) ss += partials[c];
+      ss = warp_sum(ss);
+      if (lane == 0) sumsq[l] = ss;
+    } else {
+      ss = sumsq[l];
+    }
+    if (lane == 0) {
+      const float inv = rsqrtf(fmaxf(ss, 1e-12f));     // tf.nn.l2_normalize epsilon
+      inv_norm[l] = inv;
+      const float a = params[tl.g_off[l]] * inv;
+      alpha[l] = a;
+      if (l == ex.label_layer)      // graph_att_net.py:71 on an all-ones adjacency
+        *ex.label_c = a * params[ex.label_v_off] + (ex.label_b_off >= 0 ? params[ex.label_b_off] : 0.f);
+    }
   }
-  if (lane == 0) {
-    const float inv = rsqrtf(fmaxf(ss, 1e-12f));     // tf.nn.l2_normalize epsilon
-    inv_norm[l] = inv;
-    alpha[l] = params[tl.g_off[l]] * inv;
-  }
+  for (int k = 0; k < ex.gather_n; ++k)
+    for (long long i = threadIdx.x; i < ex.g_numel[k]; i += blockDim.x) ex.g_out[ex.g_dst[k] + i] = params[ex.g_src[k] + i];
 }
 
 // ---------------------------------------------------------------- casts / elementwise
@@ -683,7 +700,7 @@ int k_wn_prepare(const float* params, const TensorList& tl, int chunks, float* s
   return REGAT_OK;
 }
 int k_wn_scaled_copy(const float* params, const TensorList& tl, int chunks, const float* alpha, void* lowp, cudaStream_t st) {
-  wn_scaled_copy_kernel<<<chunks, 256, 0, st>>>(params, tl, alpha, static_cast<bf16*>(lowp));
+  wn_scaled_copy_kernel<<<std::min(chunks, num_sms() * 8), 256, 0, st>>>(params, tl, chunks, alpha, static_cast<bf16*>(lowp));
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
@@ -692,9 +709,18 @@ int k_gather(const float* src, const TensorList& tl, float* dst, cudaStream_t st
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
-int k_wn_alpha(const float* params, const TensorList& tl, float* sumsq, float* alpha, float* inv_norm, cudaStream_t st, const float* partials) {
+int k_wn_alpha(const float* params, const TensorList& tl, float* sumsq, float* alpha, float* inv_norm, cudaStream_t st, const float* partials,
+               const TensorList* gather, float* gather_out, int label_layer, long long label_v_off, long long label_b_off, float* label_c) {
   REGAT_REQUIRE(tl.n <= 32, REGAT_ERR_SHAPE, "wn_alpha: at most 32 tensors");
-  wn_alpha_kernel<<<1, 1024, 0, st>>>(params, tl, sumsq, partials, alpha, inv_norm);
+  AlphaExtras ex;
+  ex.gather_n = 0; ex.g_out = gather_out; ex.label_layer = label_c ? label_layer : -1;
+  ex.label_v_off = label_v_off; ex.label_b_off = label_b_off; ex.label_c = label_c;
+  if (gather && gather_out) {
+    REGAT_REQUIRE(gather->n <= 8, REGAT_ERR_SHAPE, "wn_alpha: at most 8 gathered biases");
+    ex.gather_n = gather->n;
+    for (int k = 0; k < gather->n; ++k) { ex.g_src[k] = gather->off[k]; ex.g_dst[k] = gather->off_lowp[k]; ex.g_numel[k] = gather->numel[k]; }
+  }
+  wn_alpha_kernel<<<1, 1024, 0, st>>>(params, tl, sumsq, partials, alpha, inv_norm, ex);
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
