@@ -53,7 +53,7 @@ struct regat_engine {
   long long ws_need = 0;
   // workspace carve (byte offsets)
   struct Buf { long long off = -1; };
-  Buf lowp, gbias, sumsq, alpha, invn, scal, stats, partials, vpart, featT, qattT, qlastT, v0, mask, qs, s, strunc, Qb, KVb, v1, P, GB, gate, uqe,
+  Buf lowp, gbias, sumsq, alpha, invn, scal, stats, partials, vpart, counters, featT, qattT, qlastT, v0, mask, qs, s, strunc, Qb, KVb, v1, P, GB, gate, uqe,
       uw, cb, weff, att, pooled, pv, joint, hid, logits, dlogits, dhid, djoint, dpv, duqe, dpooled, dv1, dweff, dcb, duw,
       dQb, dKVb, ds, dstrunc, dsq, dwc3;
   int a_pad = 0;
@@ -162,6 +162,7 @@ long long carve(regat_engine* e) {
   take(e->scal, 64 * 4);                       // [0]=label const c, [1]=dc, [2]=loss, [3]=score
   take(e->stats, 2 * MAX_TENSORS * 4);
   take(e->partials, 2 * 8192 * 4);             // per-chunk partial sums of the optimizer reductions
+  take(e->counters, MAX_TENSORS * 4);          // per-tensor "chunks finished" counters of the optimizer reduction (self-resetting)
   take(e->vpart, 8192 * 4);                    // per-chunk ||v||^2 (written by wn_prepare or, after a step, by the update itself)
   take(e->featT, e->dtype == REGAT_BF16 ? R * V * 2 : 0);
   take(e->qattT, e->dtype == REGAT_BF16 ? B * Q * 2 : 0);
@@ -632,7 +633,8 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
 }
 
 int opt_stats(regat_engine* e, cudaStream_t st) {
-  return k_opt_reduce(e->params, e->grads, e->tl_opt, e->chunks_opt, e->at<float>(e->partials), e->at<float>(e->stats), st);
+  return k_opt_reduce(e->params, e->grads, e->tl_opt, e->chunks_opt, e->at<float>(e->partials), e->at<float>(e->stats), st,
+                      e->at<unsigned int>(e->counters));
 }
 
 int check_call(regat_engine* e, int B, int N, bool need_opt) {
@@ -711,6 +713,7 @@ extern "C" int regat_engine_bind(regat_engine* e, float* params, float* grads, f
   e->params = params; e->grads = grads; e->am = adamax_m; e->au = adamax_u;
   e->ws = static_cast<unsigned char*>(workspace); e->ws_bytes = workspace_bytes;
   e->sumsq_fresh = 0; e->lowp_fresh = 0;
+  REGAT_CUDA(cudaMemset(e->ws + e->counters.off, 0, MAX_TENSORS * 4));    // setup-time: the counters reset themselves afterwards
   return REGAT_OK;
 }
 

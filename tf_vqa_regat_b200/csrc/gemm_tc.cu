@@ -344,6 +344,18 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
       int m0, n0, kb0, kb1;
       decode(u, m0, n0, kb0, kb1);
       const int acc_stage = ui % ACC;
+      // read-modify-write epilogues (bf16 C): pull the old C / gate tiles into L2 while the MMAs of this unit are still running
+      if (!p.c_f32 && (p.e.accumulate || p.e.gate)) {
+        const int et = (warp - 2) * 32 + lane;
+        constexpr int LPR = BN / 64;                    // 128-byte lines per tile row
+        for (int id = et; id < BM * LPR; id += 32 * EPIW) {
+          const int row = m0 + id / LPR, col = n0 + (id % LPR) * 64;
+          if (row < p.M && col < p.N) {
+            if (p.e.accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const bf16*>(p.C) + (size_t)row * p.ldc + col));
+            if (p.e.gate) asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const bf16*>(p.e.gate) + (size_t)row * p.e.gate_ld + col));
+          }
+        }
+      }
       mbar_wait(tmem_full + acc_stage, (ui / ACC) & 1);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + (uint32_t)(acc_stage * BN) + ((uint32_t)(q * 32) << 16);
@@ -378,6 +390,21 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
         if (vec) {
           if (p.e.alpha && p.e.alpha_cols) al = __ldg(p.e.alpha + c / p.e.alpha_cols);
           if (p.e.bias) bv = __ldg(reinterpret_cast<const float4*>(p.e.bias + c));
+        }
+        // bf16 outputs: the read-modify-write terms (old C for accumulate, the relu gate) are requested here too -- their
+        // DRAM latency then runs under the TMEM wait and the transpose instead of stalling the drain
+        const int rcl = min(rbase + lr, p.M - 1);      // clamped first row of this lane (loads only)
+        uint2 oldc[8], gt[8];
+        const bool pre_acc = vec && !p.c_f32 && p.e.accumulate, pre_gate = vec && !p.c_f32 && p.e.gate;
+        if (pre_acc) {
+          const bf16* c0p = static_cast<const bf16*>(p.C) + c;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) oldc[i] = ldg_v2(c0p + (size_t)min(rcl + 4 * i, p.M - 1) * p.ldc);
+        }
+        if (pre_gate) {
+          const bf16* g0 = static_cast<const bf16*>(p.e.gate) + c;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) gt[i] = ldg_nc_v2(g0 + (size_t)min(rcl + 4 * i, p.M - 1) * p.e.gate_ld);
         }
         tmem_ld32_wait(acc);
         // transpose in: lane = row, 16-byte group g lands at slot g ^ (row & 7)  (conflict-free both ways)
@@ -441,7 +468,6 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
             }
           }
           const int rows_ok = p.M - rbase - lr;        // row i of this lane is valid iff 4 i < rows_ok
-          const int rcl = min(rbase + lr, p.M - 1);    // clamped first row (loads only)
           if (p.c_f32) {
             float* dst0 = static_cast<float*>(p.C) + cboff + cl;
             if (p.atomic_out) {
@@ -479,21 +505,14 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
           } else {
             bf16* dst0 = static_cast<bf16*>(p.C) + c;
             if (p.e.accumulate) {
-              uint2 o[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = ldg_v2(dst0 + (size_t)min(rcl + 4 * i, p.M - 1) * p.ldc);
-#pragma unroll
-              for (int i = 0; i < 8; ++i) { x[i].x += bf_lo(o[i].x); x[i].y += bf_hi(o[i].x); x[i].z += bf_lo(o[i].y); x[i].w += bf_hi(o[i].y); }
+              for (int i = 0; i < 8; ++i) { x[i].x += bf_lo(oldc[i].x); x[i].y += bf_hi(oldc[i].x); x[i].z += bf_lo(oldc[i].y); x[i].w += bf_hi(oldc[i].y); }
             }
             if (p.e.gate) {
-              const bf16* g0 = static_cast<const bf16*>(p.e.gate) + c;
-              uint2 g[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) g[i] = ldg_nc_v2(g0 + (size_t)min(rcl + 4 * i, p.M - 1) * p.e.gate_ld);
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                x[i].x = bf_lo(g[i].x) > 0.f ? x[i].x : 0.f; x[i].y = bf_hi(g[i].x) > 0.f ? x[i].y : 0.f;
-                x[i].z = bf_lo(g[i].y) > 0.f ? x[i].z : 0.f; x[i].w = bf_hi(g[i].y) > 0.f ? x[i].w : 0.f;
+                x[i].x = bf_lo(gt[i].x) > 0.f ? x[i].x : 0.f; x[i].y = bf_hi(gt[i].x) > 0.f ? x[i].y : 0.f;
+                x[i].z = bf_lo(gt[i].y) > 0.f ? x[i].z : 0.f; x[i].w = bf_hi(gt[i].y) > 0.f ? x[i].w : 0.f;
               }
             }
             uint2 w[8];

@@ -58,7 +58,8 @@ int k_colsum_multi(int dt, ColsumBatch& cb, cudaStream_t st);
 int k_colsum(int dt, const void* x, int ld, int rows, int cols, float* out, cudaStream_t st);
 int k_segsum(int dt, const void* x, const float* w, int B, int N, int D, void* out, cudaStream_t st);
 int k_addrows(int dt, void* dst, const void* src, int B, int N, int M, int D, cudaStream_t st);
-int k_opt_reduce(const float* params, const float* grads, const TensorList& tl, int chunks, float* partials, float* stats, cudaStream_t st);
+int k_opt_reduce(const float* params, const float* grads, const TensorList& tl, int chunks, float* partials, float* stats, cudaStream_t st,
+                 unsigned int* counters = nullptr);
 int k_opt_update(float* params, const float* grads, float* m, float* u, const TensorList& tl, int chunks, const float* stats,
                  const float* alpha, const float* inv_norm, const OptHyper& hp, cudaStream_t st, float* vpartials = nullptr);
 int k_opt_finalize(const float* params, float* grads, const TensorList& tl, int chunks, const float* stats, const float* alpha,

@@ -568,8 +568,11 @@ __global__ void __launch_bounds__(256) addrows_kernel(T* __restrict__ dst, const
 // ---------------------------------------------------------------- optimizer (train.py:112-113, weight_norm.py:41 backward)
 // pass 1: per tensor: dot = sum G*v, gg = sum G^2 (v tensors);  gg = sum g^2 (bias tensors)
 __global__ void __launch_bounds__(256) opt_reduce_kernel(const float* __restrict__ params, const float* __restrict__ grads,
-                                                         TensorList tl, float* stats /* [n][2] */) {
+                                                         TensorList tl, float* stats /* per-chunk partials [chunks][2] */,
+                                                         float* __restrict__ tstats /* per-tensor [n][2] */,
+                                                         unsigned int* __restrict__ counters) {
   __shared__ float red[8];
+  __shared__ bool last;
   int l = 0;
   while (l + 1 < tl.n && (int)blockIdx.x >= tl.chunk_start[l + 1]) ++l;
   const long long base = (long long)(blockIdx.x - tl.chunk_start[l]) * WN_CHUNK;
@@ -585,6 +588,25 @@ __global__ void __launch_bounds__(256) opt_reduce_kernel(const float* __restrict
   dot = block_sum_256(dot, red);
   gg = block_sum_256(gg, red);
   if (threadIdx.x == 0) { stats[2 * blockIdx.x] = dot; stats[2 * blockIdx.x + 1] = gg; }   // per-chunk partials
+  if (!counters) return;
+  // The block that finishes a tensor last adds its per-chunk partials in chunk order (bitwise reproducible, so data-parallel
+  // replicas holding identical gradients derive identical statistics) -- no separate one-block kernels after this one.
+  const int nchunks = tl.chunk_start[l + 1] - tl.chunk_start[l];
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int done = atomicAdd(counters + l, 1u) + 1u;
+    last = done == (unsigned int)nchunks;
+    if (last) counters[l] = 0u;                     // self-resetting: ready for the next step
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float d2 = 0.f, g2 = 0.f;
+  const volatile float* vs = stats;
+  for (int c = tl.chunk_start[l] + (int)threadIdx.x; c < tl.chunk_start[l + 1]; c += 256) { d2 += vs[2 * c]; g2 += vs[2 * c + 1]; }
+  d2 = block_sum_256(d2, red);
+  g2 = block_sum_256(g2, red);
+  if (threadIdx.x == 0) { tstats[2 * l] = d2; tstats[2 * l + 1] = g2; }
 }
 
 // fixed-order sum of the per-chunk partials: stats[l] = (sum G*v, sum G^2) of tensor l.  One warp per tensor.
@@ -821,10 +843,12 @@ int k_addrows(int dt, void* dst, const void* src, int B, int N, int M, int D, cu
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
-int k_opt_reduce(const float* params, const float* grads, const TensorList& tl, int chunks, float* partials, float* stats, cudaStream_t st) {
-  opt_reduce_kernel<<<chunks, 256, 0, st>>>(params, grads, tl, partials);
-  REGAT_POST_LAUNCH();
+int k_opt_reduce(const float* params, const float* grads, const TensorList& tl, int chunks, float* partials, float* stats, cudaStream_t st,
+                 unsigned int* counters) {
   REGAT_REQUIRE(tl.n <= MAX_TENSORS, REGAT_ERR_SHAPE, "opt_reduce: too many tensors");
+  opt_reduce_kernel<<<chunks, 256, 0, st>>>(params, grads, tl, partials, stats, counters);
+  REGAT_POST_LAUNCH();
+  if (counters) return REGAT_OK;
   for (int l0 = 0; l0 < tl.n; l0 += 32) {   // 32 warps (tensors) per block
     TensorList part = tl;
     if (l0) {
