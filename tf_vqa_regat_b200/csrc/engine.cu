@@ -448,6 +448,10 @@ void grads_ready(regat_engine* e, int l_first, int l_last) {
   e->grad_cb(e->grad_cb_user, lo, hi - lo);
 }
 
+void grads_ready_range(regat_engine* e, long long lo, long long hi) {
+  if (e->grad_cb && hi > lo) e->grad_cb(e->grad_cb_user, lo, hi - lo);
+}
+
 int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float* dq_last) {
   regat_engine* e = c.e;
   cudaStream_t st = c.st;
@@ -602,32 +606,31 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
     grads_ready(e, e->l_pos[0], e->l_out[dirs - 1]);
   }
   REGAT_TRY(k_addrows(dt, e->atv(e->ds), e->atv(e->dstrunc), B, N, M, D, st));
-  // self_weights: s = alpha (v0 Ws[:D] + mask (q Ws[D:])) + b.   ds is final: its column sum, the masked segment sum and the
-  // question-side products go to the side stream
+  // self_weights: s = alpha (v0 Ws[:D] + mask (q Ws[D:])) + b.   ds is final: its column sum and the masked segment sum go to
+  // the side stream.  The order below puts the dependency chain first (dv0 -> v2out's weight gradient) and ends with the
+  // smallest product (the question rows of self_weights, 0.8 M elements): that last range is the only all-reduce a
+  // data-parallel step cannot hide behind compute.
   REGAT_TRY(fork_to(st, sd, e->ev[8]));
   REGAT_TRY(bias_grad(e, sd, e->atv(e->ds), D, R, D, gradB(e, e->l_self), &cb_ds));
   REGAT_TRY(k_colsum_multi(dt, cb_ds, sd));
   REGAT_TRY(k_segsum(dt, e->atv(e->ds), e->at<float>(e->mask), B, N, D, e->atv(e->dsq), sd));
-  REGAT_TRY(fc_wgrad(e, sd, e->l_self, D, B, Q, qatt, Q, e->atv(e->dsq), D, false));
-  if (dq_att) REGAT_TRY(fc_dgrad(e, sd, e->l_self, D, B, Q, e->atv(e->dsq), D, dq_att, Q, REGAT_F32, false));
-  REGAT_TRY(fork_to(sd, sd, e->ev[9]));                    // (record only: the main stream waits for it below)
+  const Layer& LS = e->layers[e->l_self];
   if (e->l_v2out >= 0) {
-    // dv0 = (dv1 [residual] + alpha ds Ws[:D]^T) o (v0 > 0), in place in the dv1 buffer: the critical chain goes first
+    // dv0 = (dv1 [residual] + alpha ds Ws[:D]^T) o (v0 > 0), in place in the dv1 buffer
     REGAT_TRY(fc_dgrad(e, st, e->l_self, 0, R, D, e->atv(e->ds), D, e->atv(e->dv1), D, dt, cf.residual != 0, v0, D));
     REGAT_TRY(fork_to(st, sd, e->ev[2]));
     REGAT_TRY(bias_grad(e, sd, e->atv(e->dv1), D, R, D, gradB(e, e->l_v2out), &cb_v0));
     REGAT_TRY(k_colsum_multi(dt, cb_v0, sd));
-  }
-  REGAT_TRY(fc_wgrad(e, st, e->l_self, 0, R, D, v0, D, e->atv(e->ds), D, false));
-  REGAT_CUDA(cudaStreamWaitEvent(st, e->ev[9], 0));
-  grads_ready(e, e->l_self, e->l_label);                   // self_weights and the label FC
-  if (e->l_v2out >= 0) {
     REGAT_TRY(fc_wgrad(e, st, e->l_v2out, 0, R, V, feat, V, e->atv(e->dv1), D, false));
-    REGAT_TRY(fork_to(sd, st, e->ev[3]));
-    grads_ready(e, e->l_v2out, e->l_v2out);
-  } else {
-    REGAT_TRY(fork_to(sd, st, e->ev[3]));
   }
+  // every announcement is a full join of the side stream (a data-parallel caller may end a CUDA-graph capture segment there)
+  REGAT_TRY(fork_to(sd, st, e->ev[9]));
+  if (e->l_v2out >= 0) grads_ready(e, e->l_v2out, e->l_v2out);
+  REGAT_TRY(fc_wgrad(e, st, e->l_self, 0, R, D, v0, D, e->atv(e->ds), D, false));
+  grads_ready_range(e, LS.v_off, LS.v_off + (long long)D * D);                 // visual rows of self_weights
+  REGAT_TRY(fc_wgrad(e, st, e->l_self, D, B, Q, qatt, Q, e->atv(e->dsq), D, false));
+  if (dq_att) REGAT_TRY(fc_dgrad(e, st, e->l_self, D, B, Q, e->atv(e->dsq), D, dq_att, Q, REGAT_F32, false));
+  grads_ready_range(e, LS.v_off + (long long)D * D, e->layers[e->l_label + 1].v_off);   // question rows, g, bias, label FC
   e->grads_final = 0;
   return REGAT_OK;
 }

@@ -5,6 +5,8 @@ the average of rank means, hence grad_scale = 1/R and a SUM all-reduce reproduce
 
 What is reduced is dL/dW_eff (+ bias gradients), which is linear in the batch; the weight-norm projection,
 per-tensor clip and Adamax run after the reduce on every rank (train.py:112-113)."""
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -41,6 +43,8 @@ class DataParallelTrainer:
     optionally set_grad_callback(fn) (HotPathEngine): with it, each range of the flat gradient buffer is all-reduced on a side
     stream as soon as the backward pass has finished writing it, overlapping the remaining backward kernels."""
 
+    SMALL_FP32 = 1 << 20     # ranges below this many elements are latency-bound: reduce them in fp32, without the two cast launches
+
     def __init__(self, engine, group=None, bucket_elems: int = 0, overlap: bool = True, comm_dtype: str = "auto"):
         """comm_dtype: "fp32", "bf16" or "auto" (bf16 when the engine computes in bf16: the gradients were produced from bf16
         activations anyway, and halving the exchanged bytes is what keeps the all-reduce hidden behind the backward pass)."""
@@ -69,14 +73,18 @@ class DataParallelTrainer:
 
     def _allreduce_range(self, offset, numel):
         g = self.engine.grads
-        if self.comm_dtype == "bf16" and g.is_cuda:
+        dbg = os.environ.get("REGAT_DP_DEBUG", "")      # timing experiments only: "skip" = no exchange at all, "nocomm" = casts only
+        if dbg == "skip":
+            return
+        if self.comm_dtype == "bf16" and g.is_cuda and numel >= self.SMALL_FP32:
             from . import _lib
             if self._g16 is None:
                 self._g16 = torch.empty(g.numel(), dtype=torch.bfloat16, device=g.device)
             st = torch.cuda.current_stream().cuda_stream
             l = _lib.lib()
             _lib.check(l.regat_cast(_lib.F32, _lib.BF16, g.data_ptr() + 4 * offset, self._g16.data_ptr() + 2 * offset, numel, st))
-            dist.all_reduce(self._g16[offset:offset + numel], op=dist.ReduceOp.SUM, group=self.group)
+            if dbg != "nocomm":
+                dist.all_reduce(self._g16[offset:offset + numel], op=dist.ReduceOp.SUM, group=self.group)
             _lib.check(l.regat_cast(_lib.BF16, _lib.F32, self._g16.data_ptr() + 2 * offset, g.data_ptr() + 4 * offset, numel, st))
         else:
             dist.all_reduce(g[offset:offset + numel], op=dist.ReduceOp.SUM, group=self.group)
