@@ -204,6 +204,22 @@ REGAT_API int regat_butd_pool_bwd(int dtype, int B, int N, int D, const void* v1
  * data-parallel path and by hosts that hold fp32 tensors. */
 REGAT_API int regat_cast(int from_dtype, int to_dtype, const void* in, void* out, int64_t n, regat_stream_t stream);
 
+/* Data-parallel gradient exchange over NVLink / NVSwitch peer memory (the reference is single-GPU, train.py:111
+ * produces the gradients this sums over replicas).  The caller owns two SYMMETRIC allocations, identical on every rank and
+ * mapped into every peer: a bf16 staging buffer as long as the flat gradient buffer, and a zero-initialised flag buffer of
+ * 2 x 16 uint32.  stage_ptrs / flag_ptrs are HOST arrays of `world` device addresses (entry r = rank r's copy as mapped into
+ * this process); multicast_ptr is the NVSwitch multicast address of the staging buffer, or 0 (then peers are read and
+ * written one by one).  Per range of the flat buffer, on one stream and in the same order on every rank:
+ *     regat_cast(fp32 -> bf16, grads + offset -> local staging + offset)
+ *     regat_dp_reduce_bcast(...)     rank r sums slice r of the range over all ranks and writes the sum to all of them
+ *     regat_dp_wait_unpack(...)      waits for every slice, then staging + offset -> dst (fp32, dst = grads + offset)
+ * epoch: a counter the caller increments per range exchanged (same sequence on every rank, starting at 1).  offset and numel
+ * in elements, multiples of 8.  blocks: CTAs of the reduce kernel (<= 0: default 32); few, so it runs beside compute. */
+REGAT_API int regat_dp_reduce_bcast(const uint64_t* stage_ptrs, uint64_t multicast_ptr, const uint64_t* flag_ptrs,
+                  int rank, int world, int64_t offset, int64_t numel, uint32_t epoch, int blocks, regat_stream_t stream);
+REGAT_API int regat_dp_wait_unpack(const void* stage_local, float* dst, const uint64_t* flag_ptrs, int rank, int world,
+                  int64_t offset, int64_t numel, uint32_t epoch, regat_stream_t stream);
+
 /* relation_encoder.py:13-37 concat_visual_question(q, v, mask=True):
  *   mask[b,n] = (sum_d v[b,n,d] != 0) (optional output, fp32);  out[b,n,:] = [ v[b,n,:] || mask * q[b,:] ]   [B,N,D+Q] */
 REGAT_API int regat_concat_visual_question(int dtype, int B, int N, int D, int Q, const void* v, const void* q,

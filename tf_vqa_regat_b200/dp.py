@@ -58,6 +58,16 @@ class DataParallelTrainer:
         self.step_count = 0
         self.overlap = bool(overlap and self.world > 1 and hasattr(engine, "set_grad_callback") and engine.grads.is_cuda)
         self._reduced = 0
+        # Exchange backend: "symm" = our kernels over symmetric (peer-mapped / NVSwitch-multicast) memory, "nccl" = NCCL all-reduce
+        self.backend = "nccl"
+        want = os.environ.get("REGAT_DP_COMM", "symm")
+        if want == "symm" and self.world > 1 and self.comm_dtype == "bf16" and engine.grads.is_cuda:
+            try:
+                self._setup_symm(group)
+                self.backend = "symm"
+            except Exception as ex:                      # no symmetric memory on this system: NCCL carries the exchange
+                if self.rank == 0:
+                    print(f"[regat dp] symmetric-memory exchange unavailable ({type(ex).__name__}: {ex}); using NCCL", flush=True)
         if self.overlap:
             self.comm_stream = torch.cuda.Stream(engine.grads.device)
             engine.set_grad_callback(self._on_ready)
@@ -71,8 +81,45 @@ class DataParallelTrainer:
             self._allreduce_range(offset, numel)
         self._reduced += numel
 
+    def _setup_symm(self, group):
+        """Symmetric staging + flag buffers (torch.distributed._symmetric_memory does the allocation and the address exchange;
+        the data path is ours: csrc/dp_exchange.cu)."""
+        import ctypes as C
+        import torch.distributed._symmetric_memory as symm_mem
+        g = self.engine.grads
+        gname = (group or dist.group.WORLD).group_name
+        self._g16 = symm_mem.empty(g.numel(), dtype=torch.bfloat16, device=g.device)
+        h = symm_mem.rendezvous(self._g16, gname)
+        self._flags = symm_mem.empty(64, dtype=torch.int32, device=g.device)
+        self._flags.zero_()
+        hf = symm_mem.rendezvous(self._flags, gname)
+        torch.cuda.synchronize(g.device)
+        dist.barrier(group)                            # every rank's flags are zero before anyone signals
+        self._stage_ptrs = (C.c_uint64 * self.world)(*[int(p) for p in h.buffer_ptrs])
+        self._flag_ptrs = (C.c_uint64 * self.world)(*[int(p) for p in hf.buffer_ptrs])
+        self._mc = int(getattr(h, "multicast_ptr", 0) or 0)         # 0 where the fabric has no multicast: peers one by one
+        if os.environ.get("REGAT_DP_MULTICAST", "1") == "0":
+            self._mc = 0
+        self._epoch = 0
+        self._blocks = int(os.environ.get("REGAT_DP_BLOCKS", "32"))
+        self._symm_handles = (h, hf)
+
+    def _exchange_symm(self, offset, numel):
+        from . import _lib
+        g = self.engine.grads
+        st = torch.cuda.current_stream().cuda_stream
+        l = _lib.lib()
+        self._epoch += 1
+        _lib.check(l.regat_cast(_lib.F32, _lib.BF16, g.data_ptr() + 4 * offset, self._g16.data_ptr() + 2 * offset, numel, st))
+        _lib.check(l.regat_dp_reduce_bcast(self._stage_ptrs, self._mc, self._flag_ptrs, self.rank, self.world, offset, numel,
+                                           self._epoch, self._blocks, st))
+        _lib.check(l.regat_dp_wait_unpack(self._g16.data_ptr(), g.data_ptr() + 4 * offset, self._flag_ptrs, self.rank, self.world,
+                                          offset, numel, self._epoch, st))
+
     def _allreduce_range(self, offset, numel):
         g = self.engine.grads
+        if self.backend == "symm" and os.environ.get("REGAT_DP_DEBUG", "") == "":
+            return self._exchange_symm(offset, numel)
         dbg = os.environ.get("REGAT_DP_DEBUG", "")      # timing experiments only: "skip" = no exchange at all, "nocomm" = casts only
         if dbg == "skip":
             return
@@ -115,6 +162,12 @@ class DataParallelTrainer:
         return out
 
 
+def _timed_event(stream):
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record(stream)
+    return ev
+
+
 class GraphedDPStep:
     """CUDA-graph replay of the data-parallel forward+backward for ONE fixed set of input tensors, without putting NCCL inside
     a graph: the engine's gradient-ready callbacks split the capture into compute-only segments; on replay the bucketed
@@ -141,17 +194,26 @@ class GraphedDPStep:
         finally:
             eng.set_grad_callback(trainer._on_ready if trainer.overlap else None)
         assert sum(n for _, n in self.ranges) == eng.grads.numel(), "gradient-ready ranges do not cover the flat buffer"
+        self.trace = None
 
     def replay(self):
         """Enqueue on self.stream (must be the current stream): segments + overlapped all-reduces; joined at the end."""
         tr = self.tr
+        trace = self.trace          # None, or a list that receives (label, event) pairs with timing enabled (tools/dp_timeline.py)
+        mark = (lambda label, stream: trace.append((label, _timed_event(stream)))) if trace is not None else (lambda *a: None)
+        mark("step begin", self.stream)
         for k, g in enumerate(self.graphs):
             g.replay()
             if k < len(self.ranges):
                 off, n = self.ranges[k]
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
+                mark(f"range {k} ready ({n} el)", self.stream)
                 tr.comm_stream.wait_event(ev)
                 with torch.cuda.stream(tr.comm_stream):
+                    mark(f"range {k} comm begin", tr.comm_stream)
                     tr._allreduce_range(off, n)
+                    mark(f"range {k} comm end", tr.comm_stream)
+        mark("compute end", self.stream)
         self.stream.wait_stream(tr.comm_stream)
+        mark("step end", self.stream)
