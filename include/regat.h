@@ -217,6 +217,11 @@ REGAT_API int regat_cast(int from_dtype, int to_dtype, const void* in, void* out
  * in elements, multiples of 8.  blocks: CTAs of the reduce kernel (<= 0: default 32); few, so it runs beside compute. */
 REGAT_API int regat_dp_reduce_bcast(const uint64_t* stage_ptrs, uint64_t multicast_ptr, const uint64_t* flag_ptrs,
                   int rank, int world, int64_t offset, int64_t numel, uint32_t epoch, int blocks, regat_stream_t stream);
+/* fp32 wire format, in place: the flat gradient buffer ITSELF is the symmetric allocation (grad_ptrs[r] = rank r's copy,
+ * multicast_ptr its multicast address or 0).  One call sums [offset, offset+numel) over all ranks into every rank's buffer
+ * (reduce/broadcast kernel + a one-block completion wait); no staging, no pack / unpack passes.  Multiples of 4 elements. */
+REGAT_API int regat_dp_allreduce_f32(const uint64_t* grad_ptrs, uint64_t multicast_ptr, const uint64_t* flag_ptrs,
+                  int rank, int world, int64_t offset, int64_t numel, uint32_t epoch, int blocks, regat_stream_t stream);
 REGAT_API int regat_dp_wait_unpack(const void* stage_local, float* dst, const uint64_t* flag_ptrs, int rank, int world,
                   int64_t offset, int64_t numel, uint32_t epoch, regat_stream_t stream);
 

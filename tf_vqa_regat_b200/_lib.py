@@ -53,6 +53,7 @@ SIGNATURES = {
     "regat_butd_pool_bwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp],
     "regat_cast": [i32, i32, vp, vp, i64, vp],
     "regat_dp_reduce_bcast": [vp, C.c_uint64, vp, i32, i32, i64, i64, C.c_uint32, i32, vp],
+    "regat_dp_allreduce_f32": [vp, C.c_uint64, vp, i32, i32, i64, i64, C.c_uint32, i32, vp],
     "regat_dp_wait_unpack": [vp, vp, vp, i32, i32, i64, i64, C.c_uint32, vp],
     "regat_concat_visual_question": [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
     "regat_butd_prep": [i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp],

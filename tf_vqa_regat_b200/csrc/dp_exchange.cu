@@ -136,6 +136,65 @@ __global__ void __launch_bounds__(256) dp_wait_unpack_kernel(const bf16* __restr
   }
 }
 
+// fp32 variant, in place on a SYMMETRIC gradient buffer: no staging copy and no pack / unpack passes over HBM -- the only
+// traffic is the reduction itself.  Twice the link bytes of the bf16 wire format, which NVLink 5 absorbs (76 MB per step and
+// GPU in each direction at 8 ranks); what it buys is zero extra kernels beside the backward pass and unrounded gradients.
+template <bool MULTICAST>
+__global__ void __launch_bounds__(512) dp_reduce_bcast_f32_kernel(PeerPtrs grads, unsigned char* mc, PeerPtrs flags, int rank, int world,
+                                                                   long long offset, long long numel, unsigned int epoch) {
+  __shared__ unsigned int* fl[MAX_RANKS];
+  if ((int)threadIdx.x < world) fl[threadIdx.x] = static_cast<unsigned int*>(flags.p[threadIdx.x]);
+  __syncthreads();
+  if (blockIdx.x == 0) signal_all(fl, 0, rank, world, epoch);          // the kernels that produced this range have completed
+  wait_all(fl[rank], 0, world, epoch);                                  // ... on every rank
+  const long long chunks = numel / 4, per = (chunks + world - 1) / world;       // 16-byte (4 x fp32) chunks
+  const long long c0 = (long long)rank * per, c1 = min(chunks, c0 + per);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if constexpr (MULTICAST) {
+    constexpr int U = 4;
+    for (long long c = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; c < c1; c += U * stride) {
+      float v[U][4];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long cu = c + u * stride;
+        if (cu < c1)
+          asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                       : "=f"(v[u][0]), "=f"(v[u][1]), "=f"(v[u][2]), "=f"(v[u][3])
+                       : "l"(mc + (offset + cu * 4) * 4)
+                       : "memory");
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long cu = c + u * stride;
+        if (cu < c1)
+          asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc + (offset + cu * 4) * 4), "f"(v[u][0]),
+                       "f"(v[u][1]), "f"(v[u][2]), "f"(v[u][3])
+                       : "memory");
+      }
+    }
+  } else {
+    for (long long c = c0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; c < c1; c += stride) {
+      const long long byte = (offset + c * 4) * 4;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int r = 0; r < world; ++r) {
+        const float4 x = __ldcv(reinterpret_cast<const float4*>(static_cast<unsigned char*>(grads.p[r]) + byte));
+        acc.x += x.x; acc.y += x.y; acc.z += x.z; acc.w += x.w;
+      }
+      for (int r = 0; r < world; ++r) *reinterpret_cast<float4*>(static_cast<unsigned char*>(grads.p[r]) + byte) = acc;
+    }
+  }
+  __threadfence_system();
+}
+
+// one block: "my slice is broadcast" to every peer, then wait for every peer's -- after it the whole range is final here
+__global__ void __launch_bounds__(32) dp_wait_kernel(PeerPtrs flags, int rank, int world, unsigned int epoch) {
+  __shared__ unsigned int* fl[MAX_RANKS];
+  if ((int)threadIdx.x < world) fl[threadIdx.x] = static_cast<unsigned int*>(flags.p[threadIdx.x]);
+  __syncthreads();
+  signal_all(fl, 1, rank, world, epoch);
+  wait_all(fl[rank], 1, world, epoch);
+}
+
 int fill(PeerPtrs& pp, const uint64_t* host_ptrs, int world) {
   for (int r = 0; r < MAX_RANKS; ++r) pp.p[r] = r < world ? reinterpret_cast<void*>(host_ptrs[r]) : nullptr;
   return REGAT_OK;
@@ -174,6 +233,29 @@ extern "C" int regat_dp_wait_unpack(const void* stage_local, float* dst, const u
   fill(fl, flag_ptrs, world);
   const int nb = (int)std::min<long long>((numel / 8 + 255) / 256, (long long)num_sms() * 2);
   dp_wait_unpack_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(static_cast<const bf16*>(stage_local), dst, fl, rank, world, offset, numel, epoch);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+
+extern "C" int regat_dp_allreduce_f32(const uint64_t* grad_ptrs, uint64_t multicast_ptr, const uint64_t* flag_ptrs, int rank, int world,
+                                      int64_t offset, int64_t numel, uint32_t epoch, int blocks, regat_stream_t stream) {
+  REGAT_REQUIRE(grad_ptrs && flag_ptrs, REGAT_ERR_ARG, "dp_allreduce_f32: null pointer table");
+  REGAT_REQUIRE(world >= 1 && world <= MAX_RANKS && rank >= 0 && rank < world, REGAT_ERR_ARG, "dp_allreduce_f32: bad rank %d / world %d", rank, world);
+  REGAT_REQUIRE(offset % 4 == 0 && numel % 4 == 0 && numel >= 0, REGAT_ERR_ALIGN, "dp_allreduce_f32: offset and count must be multiples of 4 elements");
+  if (numel == 0) return REGAT_OK;
+  PeerPtrs gp, fl;
+  fill(gp, grad_ptrs, world); fill(fl, flag_ptrs, world);
+  // 32 x 512 threads measured best at 2 and 8 ranks: enough reductions in flight to cover the switch round trip, few enough
+  // CTAs to leave the backward pass its SMs (64 x 256 threads at 40 registers, which would fit beside a resident GEMM CTA, was
+  // slower: the register cap costs the memory-level parallelism the kernel lives on).
+  const int nb = blocks > 0 ? blocks : 32;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (multicast_ptr)
+    dp_reduce_bcast_f32_kernel<true><<<nb, 512, 0, s>>>(gp, reinterpret_cast<unsigned char*>(multicast_ptr), fl, rank, world, offset, numel, epoch);
+  else
+    dp_reduce_bcast_f32_kernel<false><<<nb, 512, 0, s>>>(gp, nullptr, fl, rank, world, offset, numel, epoch);
+  REGAT_POST_LAUNCH();
+  dp_wait_kernel<<<1, 32, 0, s>>>(fl, rank, world, epoch);
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }

@@ -608,8 +608,8 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   REGAT_TRY(k_addrows(dt, e->atv(e->ds), e->atv(e->dstrunc), B, N, M, D, st));
   // self_weights: s = alpha (v0 Ws[:D] + mask (q Ws[D:])) + b.   ds is final: its column sum and the masked segment sum go to
   // the side stream.  The order below puts the dependency chain first (dv0 -> v2out's weight gradient) and ends with the
-  // smallest product (the question rows of self_weights, 0.8 M elements): that last range is the only all-reduce a
-  // data-parallel step cannot hide behind compute.
+  // smallest layer (self_weights, 1.8 M elements): that last range is the only exchange a data-parallel step cannot hide
+  // behind compute.
   REGAT_TRY(fork_to(st, sd, e->ev[8]));
   REGAT_TRY(bias_grad(e, sd, e->atv(e->ds), D, R, D, gradB(e, e->l_self), &cb_ds));
   REGAT_TRY(k_colsum_multi(dt, cb_ds, sd));
@@ -626,11 +626,12 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   // every announcement is a full join of the side stream (a data-parallel caller may end a CUDA-graph capture segment there)
   REGAT_TRY(fork_to(sd, st, e->ev[9]));
   if (e->l_v2out >= 0) grads_ready(e, e->l_v2out, e->l_v2out);
+  // self_weights last, as ONE range: an exchange has a fixed cost of ~40 us (three launches, two cross-GPU flag rounds), so
+  // the tail of the step is one such exchange, not two
   REGAT_TRY(fc_wgrad(e, st, e->l_self, 0, R, D, v0, D, e->atv(e->ds), D, false));
-  grads_ready_range(e, LS.v_off, LS.v_off + (long long)D * D);                 // visual rows of self_weights
   REGAT_TRY(fc_wgrad(e, st, e->l_self, D, B, Q, qatt, Q, e->atv(e->dsq), D, false));
   if (dq_att) REGAT_TRY(fc_dgrad(e, st, e->l_self, D, B, Q, e->atv(e->dsq), D, dq_att, Q, REGAT_F32, false));
-  grads_ready_range(e, LS.v_off + (long long)D * D, e->layers[e->l_label + 1].v_off);   // question rows, g, bias, label FC
+  grads_ready_range(e, LS.v_off, e->layers[e->l_label + 1].v_off);             // self_weights (kernel, g, bias) and the label FC
   e->grads_final = 0;
   return REGAT_OK;
 }

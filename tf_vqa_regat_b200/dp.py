@@ -61,7 +61,7 @@ class DataParallelTrainer:
         # Exchange backend: "symm" = our kernels over symmetric (peer-mapped / NVSwitch-multicast) memory, "nccl" = NCCL all-reduce
         self.backend = "nccl"
         want = os.environ.get("REGAT_DP_COMM", "symm")
-        if want == "symm" and self.world > 1 and self.comm_dtype == "bf16" and engine.grads.is_cuda:
+        if want == "symm" and self.world > 1 and engine.grads.is_cuda:
             try:
                 self._setup_symm(group)
                 self.backend = "symm"
@@ -88,8 +88,19 @@ class DataParallelTrainer:
         import torch.distributed._symmetric_memory as symm_mem
         g = self.engine.grads
         gname = (group or dist.group.WORLD).group_name
-        self._g16 = symm_mem.empty(g.numel(), dtype=torch.bfloat16, device=g.device)
-        h = symm_mem.rendezvous(self._g16, gname)
+        self.wire = os.environ.get("REGAT_DP_WIRE", "f32" if hasattr(self.engine, "rebind_grads") else "bf16")
+        if self.comm_dtype == "fp32":
+            self.wire = "f32"
+        if self.wire == "f32":
+            # the gradient buffer itself becomes the symmetric allocation: reduced in place, no staging, no casts
+            g32 = symm_mem.empty(g.numel(), dtype=torch.float32, device=g.device)
+            g32.zero_()
+            h = symm_mem.rendezvous(g32, gname)
+            self.engine.rebind_grads(g32)
+            g = g32
+        else:
+            self._g16 = symm_mem.empty(g.numel(), dtype=torch.bfloat16, device=g.device)
+            h = symm_mem.rendezvous(self._g16, gname)
         self._flags = symm_mem.empty(64, dtype=torch.int32, device=g.device)
         self._flags.zero_()
         hf = symm_mem.rendezvous(self._flags, gname)
@@ -110,6 +121,10 @@ class DataParallelTrainer:
         st = torch.cuda.current_stream().cuda_stream
         l = _lib.lib()
         self._epoch += 1
+        if self.wire == "f32":
+            _lib.check(l.regat_dp_allreduce_f32(self._stage_ptrs, self._mc, self._flag_ptrs, self.rank, self.world, offset, numel,
+                                                self._epoch, self._blocks, st))
+            return
         _lib.check(l.regat_cast(_lib.F32, _lib.BF16, g.data_ptr() + 4 * offset, self._g16.data_ptr() + 2 * offset, numel, st))
         _lib.check(l.regat_dp_reduce_bcast(self._stage_ptrs, self._mc, self._flag_ptrs, self.rank, self.world, offset, numel,
                                            self._epoch, self._blocks, st))

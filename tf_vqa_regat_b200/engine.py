@@ -58,6 +58,14 @@ class HotPathEngine:
         self._loss = torch.zeros(2, dtype=torch.float32, device=self.device)
         self.step_count = 0
 
+    def rebind_grads(self, grads: torch.Tensor):
+        """Use `grads` (fp32, param_elems long, 256-byte aligned) as the flat gradient buffer from now on -- the data-parallel
+        layer passes a symmetric (peer-mapped) allocation so that gradients are reduced in place over NVLink."""
+        assert grads.dtype == torch.float32 and grads.numel() == self.param_elems and grads.is_cuda
+        self.grads = grads
+        _lib.check(self.lib.regat_engine_bind(self._h, self.params.data_ptr(), _lib.ptr(self.grads), _lib.ptr(self.adamax_m),
+                                              _lib.ptr(self.adamax_u), self.workspace.data_ptr(), self.workspace_bytes))
+
     def __del__(self):
         h = getattr(self, "_h", None)
         if h:
