@@ -349,6 +349,55 @@ def main():
         roofline["step_tensor_frac_of_sustained"] = step_tflops / peaks["bf16_tflops_sustained"]
         roofline["step_algorithmic_tflops_per_gpu"] = step_tflops
 
+    # ---------------- second roofline probe (rank 0): the fused geometry-attention forward kernel, HBM-bound by construction
+    if rank == 0 and args.dtype == "bf16":
+        try:
+            import ctypes as C
+            l = _lib.lib()
+            ents = {e.name: e for e in eng.entries}
+            pre = "v_relation.implicit_relation.neighbor_net."
+            w0, w1 = ents[pre + "0.pair_pos_fc/v"], ents.get(pre + "1.pair_pos_fc/v")
+            b0, b1 = ents[pre + "0.pair_pos_fc/bias"], ents.get(pre + "1.pair_pos_fc/bias")
+            named = eng.named()
+            alphas = torch.stack([named[pre + f"{d}.pair_pos_fc/g"].reshape(()) / named[pre + f"{d}.pair_pos_fc/v"].norm()
+                                  for d in range(cfg.dir_num)]).float().contiguous()
+            def buf(name):
+                ptr_ = C.c_void_p()
+                _lib.check(l.regat_engine_buffer(eng._h, name.encode(), C.byref(ptr_)))
+                return ptr_.value
+            training = not eval_only
+            bx = devb[0]["boxes"]
+            wd = _lib.wave_divisors(cfg.pos_emb_dim)
+            st = torch.cuda.current_stream().cuda_stream
+            call = lambda: _lib.check(l.regat_geoattn_fwd(
+                _lib.BF16, B, N, cfg.nongt_dim, cfg.rel_dim, cfg.num_heads, cfg.dir_num, cfg.pos_emb_dim, buf("Qb"), buf("KVb"),
+                bx.data_ptr(), None, wd.ctypes.data, eng.params.data_ptr() + 4 * w0.offset,
+                (w1.offset - w0.offset) if w1 else 0, alphas.data_ptr(), eng.params.data_ptr() + 4 * b0.offset,
+                (b1.offset - b0.offset) if b1 else 0, None, buf("s"), buf("v0"), 1 if cfg.residual else 0, buf("v1"),
+                buf("P") if training else None, buf("GB") if training else None, None, st))
+            for _ in range(3):
+                call()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 20
+            e0.record()
+            for _ in range(reps):
+                call()
+            e1.record(); torch.cuda.synchronize()
+            t_ms = e0.elapsed_time(e1) / reps
+            M_k = min(cfg.nongt_dim, N)
+            D_, H_, dirs_ = cfg.rel_dim, cfg.num_heads, cfg.dir_num
+            # read Q (N D), K, V' (M D each) per direction + boxes once; write O (N D) + LSE per direction  (bf16)
+            alg = B * (dirs_ * (N * D_ + 2 * M_k * D_ + N * D_) * 2 + 16 * N + dirs_ * 4 * N * H_)
+            saved = B * dirs_ * H_ * N * M_k * 4 * 2 if training else 0
+            attn_probe = {"bound": "hbm", "kernel": "geoattn_fwd_bf16_kernel (fused box geometry + graph attention forward)",
+                          "achieved": alg / (t_ms * 1e-3) / 1e9, "achieved_incl_saved_p_and_bias": (alg + saved) / (t_ms * 1e-3) / 1e9,
+                          "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg / (t_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                          "launch_ms": t_ms, "algorithmic_bytes_per_launch": alg, "saved_for_backward_bytes": saved,
+                          "note": "issue-bound today (33.6 M warp instructions per launch, profiles/r01_ncu_final_metrics.csv), not bandwidth-bound"}
+        except Exception as ex:          # the probe must never take the headline number down with it
+            attn_probe = {"error": f"{type(ex).__name__}: {ex}"[:200]}
+
     # ---------------- CPU baseline (rank 0, N=1 only)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -376,7 +425,7 @@ def main():
                         "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": (launches_per_step[0] + update_launches) * args.steps,
                 "launches_per_step": launches_per_step[0] + update_launches,
-                "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": sampler.summary(), "final_loss": loss_end}
+                "roofline": roofline, "roofline_attention": attn_probe, "cpu_baseline": cpu_baseline, "clocks": sampler.summary(), "final_loss": loss_end}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
