@@ -66,3 +66,37 @@ def test_two_gpus_equal_one_gpu():
             continue
         d = np.abs(out[0][0][e.offset:e.offset + e.numel] - p_ref[e.offset:e.offset + e.numel]).max()
         assert d < 0.05 * steps * lr + 1e-6, (e.name, d)
+
+
+def test_exchange_kernels_single_rank_identity():
+    """csrc/dp_exchange.cu with world = 1 (no peer, no multicast address): the flag protocol must complete with the rank
+    signalling itself, the fp32 in-place reduction must leave the range unchanged, the bf16 staging path must return the
+    bf16 rounding of the range, and ranges outside [offset, offset+numel) must not be touched.  Several epochs in a row."""
+    import ctypes as C
+    from tf_vqa_regat_b200 import _lib
+    l = _lib.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    n, off, cnt = 1 << 16, 1024, 40000
+    g = torch.randn(n, device="cuda")
+    ref = g.clone()
+    flags = torch.zeros(64, dtype=torch.int32, device="cuda")
+    gp = (C.c_uint64 * 1)(g.data_ptr())
+    fp = (C.c_uint64 * 1)(flags.data_ptr())
+    for epoch in (1, 2, 3):
+        _lib.check(l.regat_dp_allreduce_f32(gp, 0, fp, 0, 1, off, cnt, epoch, 4, st))
+    torch.cuda.synchronize()
+    assert torch.equal(g, ref)
+    assert int(flags[0]) == 3 and int(flags[16]) == 3          # [kind 0][rank 0], [kind 1][rank 0]
+    stage = torch.zeros(n, dtype=torch.bfloat16, device="cuda")
+    sp = (C.c_uint64 * 1)(stage.data_ptr())
+    for epoch in (4, 5):
+        _lib.check(l.regat_cast(_lib.F32, _lib.BF16, g.data_ptr() + 4 * off, stage.data_ptr() + 2 * off, cnt, st))
+        _lib.check(l.regat_dp_reduce_bcast(sp, 0, fp, 0, 1, off, cnt, epoch, 4, st))
+        _lib.check(l.regat_dp_wait_unpack(stage.data_ptr(), g.data_ptr() + 4 * off, fp, 0, 1, off, cnt, epoch, st))
+    torch.cuda.synchronize()
+    want = ref.clone()
+    want[off:off + cnt] = ref[off:off + cnt].bfloat16().float()
+    assert torch.equal(g, want)
+    # argument errors surface as status codes, not as launches
+    assert l.regat_dp_allreduce_f32(gp, 0, fp, 0, 1, 2, cnt, 6, 4, st) == -5          # offset not a multiple of 4
+    assert l.regat_dp_allreduce_f32(gp, 0, fp, 1, 1, off, cnt, 6, 4, st) == -1          # rank >= world
