@@ -1,0 +1,64 @@
+"""Checkpoint I/O for the hot path's variables, by ORDER like Keras-2 `save_weights` / `load_weights`.
+
+The reference saves with `model.save_weights(path)` / restores with `model.load_weights(path)` (main.py:145,155): an HDF5 file
+whose arrays are matched to variables by their order inside each top-level layer, not by name.  h5py is not available in this
+image, so the container here is `.npz`; the ORDER is the contract and is the same one -- per WeightNorm wrapper `[v, g, bias]`
+(weight_norm.py:21-31), layers in attribute-assignment order (rel_graph_net.py:16-21, relation_encoder.py:53-58,
+graph_att_net.py:24-36, graph_att_layer.py:25-37, fusion.py:15-20, classifier.py:14-19) -- i.e. `config.param_layout`.
+A maintainer with h5py converts a reference checkpoint by listing its datasets in file order and passing them to
+`arrays_to_flat` (the language front-end's variables, which precede these in the file, are outside this path).
+
+Arrays are stored under keys "000:<name>", "001:<name>", ... so that the file is self-describing, but loading goes by index
+and validates count and shapes the way Keras does (ValueError naming the offending variable)."""
+import json
+from typing import Iterable, List
+
+import numpy as np
+
+from .config import HotPathConfig, param_layout
+
+FORMAT = "regat-b200-weights/1"
+
+
+def flat_to_arrays(cfg: HotPathConfig, flat) -> List[np.ndarray]:
+    """Flat fp32 buffer (engine.params layout, with alignment padding) -> list of arrays in Keras variable order."""
+    flat = np.asarray(flat, dtype=np.float32).reshape(-1)
+    entries, total = param_layout(cfg)
+    if flat.size != total:
+        raise ValueError(f"flat buffer has {flat.size} elements, the layout needs {total}")
+    return [flat[e.offset:e.offset + e.numel].reshape(e.shape).copy() for e in entries]
+
+
+def arrays_to_flat(cfg: HotPathConfig, arrays: Iterable) -> np.ndarray:
+    """List of arrays in Keras variable order -> flat fp32 buffer.  Count and shapes must match (Keras: 'You called
+    `set_weights(weights)` ... with a weight list of length N, but the layer was expecting M weights')."""
+    arrays = list(arrays)
+    entries, total = param_layout(cfg)
+    if len(arrays) != len(entries):
+        raise ValueError(f"weight list of length {len(arrays)}, but the hot path expects {len(entries)} variables")
+    flat = np.zeros(total, dtype=np.float32)
+    for e, a in zip(entries, arrays):
+        a = np.asarray(a, dtype=np.float32)
+        if tuple(a.shape) != tuple(e.shape):
+            raise ValueError(f"variable {e.name} has shape {tuple(e.shape)}, but the checkpoint holds {tuple(a.shape)}")
+        flat[e.offset:e.offset + e.numel] = a.reshape(-1)
+    return flat
+
+
+def save_weights(path: str, cfg: HotPathConfig, flat) -> None:
+    """Write the variables of `flat` to `path` (.npz) in Keras variable order."""
+    entries, _ = param_layout(cfg)
+    arrays = flat_to_arrays(cfg, flat)
+    meta = {"format": FORMAT, "config": {k: getattr(cfg, k) for k in cfg.__dataclass_fields__}, "variables": [e.name for e in entries]}
+    payload = {f"{i:03d}:{e.name}": a for i, (e, a) in enumerate(zip(entries, arrays))}
+    payload["__meta__"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    with open(path, "wb") as f:
+        np.savez(f, **payload)
+
+
+def load_weights(path: str, cfg: HotPathConfig) -> np.ndarray:
+    """Read a file written by save_weights (or any .npz whose arrays sort into Keras variable order) -> flat fp32 buffer."""
+    with np.load(path) as z:
+        keys = sorted(k for k in z.files if k != "__meta__")
+        arrays = [z[k] for k in keys]
+    return arrays_to_flat(cfg, arrays)

@@ -83,13 +83,6 @@ __device__ __forceinline__ float pair_log_term(const float4& oi, const float4& o
   return logf(qv);
 }
 
-// the 16 features of one geometry term: [k] = sin(100*P/div_k), [8+k] = cos(...)  (position_emb.py:104-113)
-__device__ __forceinline__ void embedding_group(float Pc, const WaveDiv& wd, float (&emb)[16]) {
-  const float x = 100.0f * Pc;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) sincos_cw(__fdiv_rn(x, wd.d[k]), &emb[k], &emb[8 + k]);
-}
-
 // feature c*16+k = sin(100*P_c/div_k), c*16+8+k = cos(...)   (position_emb.py:104-113)
 __device__ __forceinline__ void pair_embedding(const float4& oi, const float4& oj, const WaveDiv& wd,
                                                float (&emb)[EMB]) {

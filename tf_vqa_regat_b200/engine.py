@@ -84,6 +84,16 @@ class HotPathEngine:
         """Call after writing `self.params` in place: cached weight-norm statistics are recomputed on the next pass."""
         _lib.check(self.lib.regat_engine_params_changed(self._h))
 
+    def save_weights(self, path: str):
+        """model.save_weights (main.py:145): the hot path's variables in Keras variable order (checkpoint.py)."""
+        from . import checkpoint
+        checkpoint.save_weights(path, self.cfg, self.params.detach().cpu().numpy())
+
+    def load_weights(self, path: str):
+        """model.load_weights (main.py:155), by order."""
+        from . import checkpoint
+        self.load_params(checkpoint.load_weights(path, self.cfg))
+
     def named(self, buf=None):
         """name -> view into a flat buffer (default: params)."""
         buf = self.params if buf is None else buf
