@@ -12,7 +12,11 @@ all-reduce per step (weak scaling: 256 graphs per GPU).  Rank 0 prints ONE JSON 
               device -> host read of every step's loss inside the timed region (copies double-buffered on a side stream)
   roofline  : the dominant kernel (tcgen05 bf16 GEMM of the v2out projection, 9216x1024x2048) timed alone with CUDA
               events on rotating operands larger than L2, against the MEASURED cuBLAS bf16 peak
+              (traffic = DRAM bytes of that launch from the ncu capture recorded in profiles/roofline_traffic.json)
+  roofline_attention : the fused geometry + graph-attention forward kernel timed alone against the measured HBM copy peak
   cpu_baseline : the reference-formulation CPU restatement (oracle/, torch-CPU fp32, all host cores) on a bounded sample
+N > 1: gradients are reduced in place over NVSwitch multicast by csrc/dp_exchange.cu (REGAT_DP_COMM=nccl for NCCL,
+REGAT_DP_WIRE=bf16 for the staged bf16 wire format), overlapped with the backward pass in 4 ranges.
 --impl reference runs only that CPU arm (TensorFlow is not installable in this image).
 """
 import argparse
