@@ -127,3 +127,17 @@ def test_wave_divisors_follow_numpy_fp32():
     k = np.arange(0, 8, dtype=np.float32)
     np.testing.assert_array_equal(wd, np.power(np.full((1,), 1000, dtype=np.float32), (8.0 / 64) * k))
     assert wd.dtype == np.float32 and wd[0] == 1.0
+
+
+def test_dp_exchange_argument_errors_need_no_gpu():
+    """csrc/dp_exchange.cu validates before it launches: bad tables / ranks / alignment come back as status codes."""
+    l = _lib.lib()
+    ptrs = (C.c_uint64 * 2)(0x1000, 0x2000)
+    assert l.regat_dp_allreduce_f32(None, 0, ptrs, 0, 2, 0, 1024, 1, 0, None) == -1
+    assert l.regat_dp_allreduce_f32(ptrs, 0, ptrs, 2, 2, 0, 1024, 1, 0, None) == -1           # rank >= world
+    assert l.regat_dp_allreduce_f32(ptrs, 0, ptrs, 0, 17, 0, 1024, 1, 0, None) == -1          # more ranks than the flag layout holds
+    assert l.regat_dp_allreduce_f32(ptrs, 0, ptrs, 0, 2, 2, 1024, 1, 0, None) == -5           # offset not a multiple of 4 elements
+    assert l.regat_dp_allreduce_f32(ptrs, 0, ptrs, 0, 2, 0, 0, 1, 0, None) == 0               # empty range: nothing to do
+    assert l.regat_dp_reduce_bcast(ptrs, 0, ptrs, 0, 2, 4, 1024, 1, 0, None) == -5            # bf16 wire: multiples of 8
+    assert l.regat_dp_wait_unpack(None, None, ptrs, 0, 2, 0, 1024, 1, None) == -1
+    assert "dp_" in _lib.last_error()
