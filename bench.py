@@ -422,7 +422,8 @@ def main():
                                         "adaptive100": f"train step, adaptive K=10..100 zero-padded to {N}, batch {B}/GPU (BASELINE.json configs[2])",
                                         "eval100": f"eval forward bf16, batch {B}/GPU, K=100 adaptive (BASELINE.json configs[4])"}[args.workload],
                            "parallelism": f"dp{world}", "global_batch": B * world, "cuda_graph": bool(graphs),
-                           "allreduce": (None if world == 1 else (("4 ranges overlapped with backward" if trainer.overlap else "single, after backward") + ", " + trainer.comm_dtype + ", " + getattr(trainer, "backend", "nccl") + ("/" + trainer.wire if getattr(trainer, "backend", "") == "symm" else ""))),
+                           "allreduce": (None if world == 1 else (("4 ranges overlapped with backward" if trainer.overlap else "single, after backward") + ", " + ("own multimem kernel in place on the symmetric gradient buffer, wire " + trainer.wire if getattr(trainer, "backend", "") == "symm"
+                                                                         else "NCCL, wire " + trainer.comm_dtype))),
                            "l2": "per-step working set ~0.8 GB (activations + 4x76 MB parameter/optimizer state) >> 126 MB L2; "
                                  "two alternating input batches; no explicit flush"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,

@@ -1,5 +1,6 @@
 """Data-parallel training of the hot path: one process per GPU, graphs sharded by image, weights replicated,
-ONE exchange per step -- an all-reduce (sum) of the flat gradient buffer.  Every graph is independent
+ONE exchange per step -- an all-reduce (sum) of the flat gradient buffer, carried by our own kernels over
+symmetric NVLink / NVSwitch-multicast memory (csrc/dp_exchange.cu; REGAT_DP_COMM=nccl selects NCCL instead).  Every graph is independent
 end to end, so rank r simply takes graphs [r*B/R, (r+1)*B/R); with equal shards the mean over the global batch is
 the average of rank means, hence grad_scale = 1/R and a SUM all-reduce reproduce the single-GPU gradient.
 
