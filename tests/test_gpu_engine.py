@@ -48,6 +48,7 @@ CASES = [  # kw, B, N, adaptive, trained_like
     (dict(SMALL, nongt_dim=20), 2, 100, True, True),   # adaptive up to 100 boxes
     (dict(SMALL, v_dim=256), 2, 20, False, True),      # v_dim == rel_dim: no v2out (relation_encoder.py:52-55)
     (dict(SMALL, dir_num=1, num_heads=8, rel_dim=512, residual=False, label_bias=True), 2, 24, False, True),
+    (SMALL, 3, 13, True, True),            # odd key count (rows of the saved probabilities are not 8-byte aligned)
 ]
 
 
@@ -65,7 +66,7 @@ def test_forward_fp32_parity(kw, B, N, adaptive, tl):
     assert np.array_equal(logits.argmax(1).cpu().numpy(), ref["logits"].argmax(1))
 
 
-@pytest.mark.parametrize("kw,B,N,adaptive,tl", CASES[:5])
+@pytest.mark.parametrize("kw,B,N,adaptive,tl", CASES[:5] + [CASES[7]])
 def test_forward_bf16_parity(kw, B, N, adaptive, tl):
     cfg, inp, flat, eng, dev, named64, args64 = _setup(kw, B, N, adaptive, tl, "bf16")
     logits = eng.forward(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"])
@@ -100,7 +101,7 @@ def test_attention_intermediates_fp32():
             (np.abs((GB[:, d] == np.float32(np.log(np.float32(1e-6)))).astype(int) - (z <= 1e-6).astype(int)).mean() < 1e-3)
 
 
-@pytest.mark.parametrize("kw,B,N,adaptive,tl", [CASES[1], CASES[2], CASES[6]])
+@pytest.mark.parametrize("kw,B,N,adaptive,tl", [CASES[1], CASES[2], CASES[6], CASES[7]])
 def test_gradients_fp32_parity(kw, B, N, adaptive, tl):
     cfg, inp, flat, eng, dev, named64, args64 = _setup(kw, B, N, adaptive, tl, "fp32")
     out = eng.fwd_bwd(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"], dev["target"], want_dq=True, want_logits=True)
@@ -153,9 +154,10 @@ def test_train_steps_fp32_track_oracle():
         assert np.abs(got[k] - p[k]).max() < 0.05 * 3 * lr + 1e-6, k
 
 
-def test_gradients_bf16_close():
-    kw, B, N = SMALL, 4, 36
-    cfg, inp, flat, eng, dev, named64, args64 = _setup(kw, B, N, False, True, "bf16")
+@pytest.mark.parametrize("B,N,adaptive", [(4, 36, False), (3, 13, True)])       # M = 20, and an odd M = 13
+def test_gradients_bf16_close(B, N, adaptive):
+    kw = SMALL
+    cfg, inp, flat, eng, dev, named64, args64 = _setup(kw, B, N, adaptive, True, "bf16")
     out = eng.fwd_bwd(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"], dev["target"])
     eng.finalize_grads()
     loss, grads, _, _, _ = ot.loss_and_grads(named64, cfg, inp)
