@@ -9,8 +9,15 @@ Pinning status:
   * stage 1 (position_emb.py)  -- PINNED: checked against outputs of the
     reference's own /root/reference/model/position_emb.py, committed as
     tests/golden/stage1_*.npz by oracle/make_golden.py.
-  * stages 2-3, loss, optimizer -- PARITY UNPINNED: the reference needs
-    TensorFlow, which is not installable here, and ships no tests or golden
-    vectors.  The restatement follows the reference source op for op and is
-    cross-checked two ways (NumPy vs torch-CPU autograd), nothing more.
+  * stages 2-3, loss, clip, Adamax -- PINNED TO THE REFERENCE'S OWN CODE, with
+    TensorFlow's primitives restated: the reference needs TensorFlow, which is
+    not installable here, and ships no tests or golden vectors.
+    oracle/make_golden_ref.py therefore executes the reference's unmodified
+    model/*.py and train.py (forward, GradientTape, train(), evaluate()) on
+    top of oracle/tf_shim -- a stand-in that restates the ~40 TensorFlow/Keras
+    primitives those files call -- and commits the outputs as
+    tests/golden/refexec_*.npz.  The restatements below agree with them to
+    1e-10 (tests/test_refexec.py).  What stays an assumption is that the
+    stand-in's primitives do what TensorFlow's documentation says; they are
+    checked against independent implementations, not against TensorFlow.
 """

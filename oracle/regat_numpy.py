@@ -14,7 +14,8 @@ TensorFlow semantics restated (TF itself is absent):
   sigmoid_cross_entropy_with_logits = max(x,0) - x*z + log1p(exp(-|x|)).
 Dropout layers are identities (train.py:104 never passes training=True).
 
-PARITY UNPINNED for these stages -- see oracle/__init__.py.  TEST INFRASTRUCTURE.
+Pinned by tests/golden/refexec_*.npz (the reference's own files executed over oracle/tf_shim;
+see oracle/__init__.py for what that does and does not establish).  TEST INFRASTRUCTURE.
 """
 import numpy as np
 

@@ -7,7 +7,8 @@ cores as the "reference-formulation CPU restatement" baseline (BASELINE.md secti
 Also restates the train-step glue: per-tensor clip_by_norm (train.py:112) and Keras
 Adamax (train.py:48,113).
 
-PARITY UNPINNED (no TensorFlow here) -- see oracle/__init__.py.  TEST INFRASTRUCTURE.
+Pinned by tests/golden/refexec_*.npz (the reference's own files executed over oracle/tf_shim;
+see oracle/__init__.py for what that does and does not establish).  TEST INFRASTRUCTURE.
 """
 import numpy as np
 import torch
