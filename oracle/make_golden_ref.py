@@ -114,8 +114,8 @@ def _summ(a, rng_seed, full):
     a = np.asarray(a, dtype=np.float64)
     r = np.random.default_rng(rng_seed).standard_normal(a.size)
     idx = np.random.default_rng(rng_seed + 1).choice(a.size, size=min(SAMPLE, a.size), replace=False)
-    d = dict(sum=a.sum(), norm=np.sqrt((a * a).sum()), proj=float(a.ravel() @ r), idx=idx.astype(np.int64),
-             sample=a.ravel()[idx])
+    d = dict(sum=a.sum(), norm=np.sqrt((a * a).sum()), absmax=np.abs(a).max(), proj=float(a.ravel() @ r),
+             idx=idx.astype(np.int64), sample=a.ravel()[idx])
     if full:
         d["full"] = a
     return d
