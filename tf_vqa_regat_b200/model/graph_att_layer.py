@@ -8,7 +8,6 @@ returns the layer's raw output [B, N, hidden] (graph_att_layer.py:121).  The ari
     raw-reshape index scramble (graph_att_layer.py:74,81);
   * adj_mat must be the implicit relation's all-ones adjacency (relation_encoder.py:76): tf.where is then a no-op;
     label_att must be the constant produced by the label FC on ones (graph_att_net.py:71) -- its first element is used."""
-import torch
 
 from .. import _lib
 from . import _rt
@@ -68,8 +67,6 @@ class GraphSelfAttentionLayer(Layer):
         self.project(roi, q.data_ptr(), D, kv.data_ptr(), 2 * D, 0, D)
         out = _rt.empty(B, N, D, device=roi.device)
         pp = self.pair_pos_fc.dense
-        alpha_g = torch.empty(1, device=roi.device)
-        alpha_g.copy_(torch.frombuffer(b"\0\0\0\0", dtype=torch.float32)) if False else None
         a_ptr = pp.alpha_ptr()
         label_ptr = _rt.need_cuda(label_att, "label_att").data_ptr() if label_att is not None else None
         boxes, pe = _geometry_args(pos_emb, B, N, M, self.pos_emb_dim)
