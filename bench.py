@@ -39,6 +39,14 @@ TRAIN_MFLOP_PER_GRAPH = 1734.0      # SURVEY 8d, N=36, nongt=20, cheapest equiva
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
 
 
+def workload_name(workload, B, N):
+    """config.workload of the JSON line; both arms (ours and --impl reference) print the same string."""
+    return {"train36": f"implicit relation + BUTD train step, batch {B}/GPU, K={N}, 16 heads, nongt_dim 20, "
+                       f"V=2048 D=1024 Q=768 A=3129 (BASELINE.json configs[1])",
+            "adaptive100": f"train step, adaptive K=10..100 zero-padded to {N}, batch {B}/GPU (BASELINE.json configs[2])",
+            "eval100": f"eval forward bf16, batch {B}/GPU, K=100 adaptive (BASELINE.json configs[4])"}[workload]
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -109,7 +117,8 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": gps, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
             "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"implicit relation + BUTD train step, batch {args.batch}, K={args.rois}, 16 heads (CPU, sampled)"},
+            "config": {"workload": workload_name("train36", args.batch, args.rois), "parallelism": "cpu", "global_batch": args.batch,
+                       "note": "CPU arm: each step is a bounded sample of the workload (see cpu_baseline.sample), scaled to the batch"},
             "cpu_baseline": {"value": gps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": gps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -417,10 +426,7 @@ def main():
         line = {"metric": METRIC if args.workload == "train36" else f"graphs/sec ({args.workload})", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.dtype if args.dtype == "bf16" else "f32", "data": "synthetic",
-                "config": {"workload": {"train36": f"implicit relation + BUTD train step, batch {B}/GPU, K={N}, 16 heads, nongt_dim 20, "
-                                                    f"V=2048 D=1024 Q=768 A=3129 (BASELINE.json configs[1])",
-                                        "adaptive100": f"train step, adaptive K=10..100 zero-padded to {N}, batch {B}/GPU (BASELINE.json configs[2])",
-                                        "eval100": f"eval forward bf16, batch {B}/GPU, K=100 adaptive (BASELINE.json configs[4])"}[args.workload],
+                "config": {"workload": workload_name(args.workload, B, N),
                            "parallelism": f"dp{world}", "global_batch": B * world, "cuda_graph": bool(graphs),
                            "allreduce": (None if world == 1 else (("4 ranges overlapped with backward" if trainer.overlap else "single, after backward") + ", " + ("own multimem kernel in place on the symmetric gradient buffer, wire " + trainer.wire if getattr(trainer, "backend", "") == "symm"
                                                                          else "NCCL, wire " + trainer.comm_dtype))),
