@@ -47,7 +47,7 @@ CASES = {
     "small_nov2out": (dict(SMALL, v_dim=256), 2, 20, False, True, 2),
     "small_dir1_labelbias_nores": (dict(SMALL, dir_num=1, num_heads=8, rel_dim=512, residual=False, label_bias=True),
                                    2, 24, False, True, 2),
-    "full_b2_n36_m20": (dict(), 2, 36, False, True, 2),
+    "full_b4_n36_m20": (dict(), 4, 36, False, True, 2),   # BASELINE.json configs[0]: batch 4, K=36, full widths
 }
 LR = 1e-3
 SAMPLE = 64            # elements kept per tensor for the large cases

@@ -17,7 +17,7 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 # the kernels need head dim 64: the small_* and full_* fixtures qualify, tiny_* do not
 ORDER = ["small_n36_m20", "small_n12_clamped", "small_dir1_labelbias_nores", "small_n36_m36_fullkk", "small_n100_m20_adaptive",
-         "small_nov2out", "small_n36_m20_init", "full_b2_n36_m20"]
+         "small_nov2out", "small_n36_m20_init", "full_b4_n36_m20"]
 FILES = [os.path.join(HERE, "golden", f"refexec_{n}.npz") for n in ORDER]
 IDS = ORDER
 
@@ -110,7 +110,7 @@ def test_gradients_fp32_vs_reference_tape(path):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("path", [f for f in FILES if "full_b2" not in f], ids=[i for i in IDS if "full_b2" not in i])
+@pytest.mark.parametrize("path", [f for f in FILES if "full_b4" not in f], ids=[i for i in IDS if "full_b4" not in i])
 def test_train_steps_fp32_vs_reference_train_loop(path):
     """The reference's train.train() ran `steps` batches (GradientTape, per-tensor clip_by_norm, Adamax, lr 1e-3) and then
     train.evaluate() on one more: per-step losses, parameters afterwards, evaluation logits."""

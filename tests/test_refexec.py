@@ -90,7 +90,7 @@ def test_fp32_noise_floor_of_the_reference(path):
     assert err < 2e-6, err
 
 
-@pytest.mark.parametrize("path", [f for f in FILES if "full_b2" not in f], ids=[i for i in IDS if "full_b2" not in i])
+@pytest.mark.parametrize("path", [f for f in FILES if "full_b4" not in f], ids=[i for i in IDS if "full_b4" not in i])
 def test_train_loop_matches_reference_train(path):
     """train.train(): GradientTape -> per-tensor clip_by_norm(0.25) -> Adamax, `steps` batches; then train.evaluate()."""
     g, cfg, batches, flat = load_case(path)
