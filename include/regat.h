@@ -200,6 +200,16 @@ REGAT_API int regat_butd_pool_bwd(int dtype, int B, int N, int D, const void* v1
                         const float* att, const void* dpooled, void* dv1, void* dweff, float* dcb,
                         regat_stream_t stream);
 
+/* Device half of the reference's batch assembly (dataset.py:329-346: keras pad_sequences(padding='post', maxlen = longest
+ * sample)): a batch shipped RAGGED -- packed[total_rows, width] holds the samples' rows back to back, offsets[B+1] (int32,
+ * device) the first row of each sample -- becomes padded[B, N, width] with zero rows after each sample's own, exactly what
+ * the host-side collate produces, without moving the padding over PCIe.  width must be a multiple of 4 floats, buffers
+ * 16-byte aligned.  Offsets live on the device, so the call cannot return an error for them: a sample whose offsets are
+ * invalid (negative or decreasing, more than N rows, rows past total_rows) is never read -- it comes out all zero -- and,
+ * if `bad` (one int32 on the device, zeroed by the caller) is given, `bad` receives 1 + the index of such a sample. */
+REGAT_API int regat_pad_ragged(int B, int N, int width, int64_t total_rows, const float* packed, const int32_t* offsets,
+                     float* padded, int32_t* bad, regat_stream_t stream);
+
 /* Elementwise fp32 <-> bf16 conversion of n (multiple of 8) elements -- used for the reduced-precision gradient exchange of the
  * data-parallel path and by hosts that hold fp32 tensors. */
 REGAT_API int regat_cast(int from_dtype, int to_dtype, const void* in, void* out, int64_t n, regat_stream_t stream);

@@ -141,3 +141,16 @@ def test_dp_exchange_argument_errors_need_no_gpu():
     assert l.regat_dp_reduce_bcast(ptrs, 0, ptrs, 0, 2, 4, 1024, 1, 0, None) == -5            # bf16 wire: multiples of 8
     assert l.regat_dp_wait_unpack(None, None, ptrs, 0, 2, 0, 1024, 1, None) == -1
     assert "dp_" in _lib.last_error()
+
+
+def test_pad_ragged_argument_errors_need_no_gpu():
+    l = _lib.lib()
+    a = np.zeros(64, np.float32)
+    off = np.zeros(3, np.int32)
+    p, o = a.ctypes.data, off.ctypes.data
+    assert l.regat_pad_ragged(2, 4, 6, 8, p, o, p, None, None) == -2            # width not a multiple of 4 floats
+    assert "multiple of 4" in _lib.last_error()
+    assert l.regat_pad_ragged(-1, 4, 4, 8, p, o, p, None, None) == -2
+    assert l.regat_pad_ragged(0, 4, 4, 0, None, None, None, None, None) == 0     # empty batch: nothing to do
+    assert l.regat_pad_ragged(2, 4, 4, 8, p, None, p, None, None) == -1          # null offsets
+    assert l.regat_pad_ragged(2, 4, 4, 8, p + 4, o, p, None, None) == -5         # unaligned packed buffer

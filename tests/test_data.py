@@ -58,3 +58,82 @@ def test_store_validates_shapes():
         AdaptiveFeatureStore(feats, nbb[:-1], bb, pos)
     with pytest.raises(ValueError):
         AdaptiveFeatureStore(feats, nbb, bb, pos.reshape(-1))
+
+
+def test_ragged_collate_packs_the_same_rows():
+    feats, nbb, bb, pos = _store(seed=2)
+    st = AdaptiveFeatureStore(feats, nbb, bb, pos)
+    ids = [5, 3, 3, 0, 8]
+    rg = st.collate_ragged(ids)
+    f0, _, b0, _ = oc.collate(feats, nbb, bb, pos, ids, [None] * 5, [None] * 5, 3)
+    off = rg["offsets"].numpy()
+    assert rg["offsets"].dtype == torch.int32 and off[0] == 0 and rg["max_rois"] == 100
+    assert rg["features"].shape[0] == off[-1] == sum(pos[i, 1] - pos[i, 0] for i in ids)
+    for k, i in enumerate(ids):                      # un-padding the reference's batch gives the packed rows back
+        c = pos[i, 1] - pos[i, 0]
+        np.testing.assert_array_equal(rg["features"][off[k]:off[k + 1]].numpy(), f0[k, :c])
+        np.testing.assert_array_equal(rg["boxes"][off[k]:off[k + 1]].numpy(), b0[k, :c])
+    out = st.ragged_buffers(5, 500, pin=False)
+    rg2 = st.collate_ragged(ids[:2], out=out)        # reusable buffers
+    assert rg2["features"].shape[0] == rg2["offsets"][-1] and rg2["features"].data_ptr() == out["features"].data_ptr()
+    with pytest.raises(ValueError, match="too small"):
+        st.collate_ragged([3] * 6, out=out)
+
+
+def test_pad_on_device_refuses_to_run_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from tf_vqa_regat_b200._lib import RegatError
+    from tf_vqa_regat_b200.data import pad_on_device
+    feats, nbb, bb, pos = _store()
+    with pytest.raises(RegatError):
+        pad_on_device(AdaptiveFeatureStore(feats, nbb, bb, pos).collate_ragged([0, 1]), "cuda:0")
+
+
+@pytest.mark.gpu
+def test_pad_on_device_is_bit_exact_with_host_padding():
+    from tf_vqa_regat_b200.data import pad_on_device
+    feats, nbb, bb, pos = _store(seed=3, images=12, V=2048)
+    st = AdaptiveFeatureStore(feats, nbb, bb, pos)
+    ids = [5, 3, 3, 0, 8, 11, 1]
+    want = st.collate(ids)
+    got = pad_on_device(st.collate_ragged(ids), "cuda:0")
+    assert torch.equal(got["features"].cpu(), want["features"]) and torch.equal(got["boxes"].cpu(), want["boxes"])
+    assert torch.equal(got["n_obj"].cpu(), want["n_obj"])
+    # shorter batch, wider padding, into reused (dirty) output buffers: nothing stale survives
+    out = {"features": torch.full((7, 100, 2048), 7.0, device="cuda:0"), "boxes": torch.full((7, 100, 4), 7.0, device="cuda:0")}
+    ids2 = [0, 1]
+    got2 = pad_on_device(st.collate_ragged(ids2), "cuda:0", pad_to=100, out=out)
+    want2 = st.collate(ids2, pad_to=100)
+    assert torch.equal(got2["features"].cpu(), want2["features"]) and torch.equal(got2["boxes"].cpu(), want2["boxes"])
+    # invalid offsets (a sample longer than N) are flagged, never read
+    rg = st.collate_ragged(ids)
+    rg["max_rois"] = 100
+    rg["offsets"] = rg["offsets"].clone()
+    rg["offsets"][1] = -5
+    with pytest.raises(ValueError, match="invalid"):
+        pad_on_device(rg, "cuda:0")
+
+
+@pytest.mark.gpu
+def test_engine_on_device_padded_batch_matches_host_padded_batch():
+    """The hot path sees the same bits either way: logits are identical for a ragged-shipped and a host-padded batch."""
+    from tf_vqa_regat_b200 import synthetic as syn
+    from tf_vqa_regat_b200.config import HotPathConfig
+    from tf_vqa_regat_b200.data import pad_on_device
+    from tf_vqa_regat_b200.engine import HotPathEngine
+    cfg = HotPathConfig(v_dim=192, q_dim=96, rel_dim=256, num_heads=4, nongt_dim=20, num_answers=301)
+    rng = np.random.default_rng(5)
+    counts = np.array([36, 12, 20, 29]); ends = np.cumsum(counts); T = int(ends[-1])
+    feats = np.maximum(rng.standard_normal((T, 192)), 0).astype(np.float32)
+    bb = np.sort(rng.uniform(0, 400, (T, 4)), axis=1).astype(np.float32)
+    st = AdaptiveFeatureStore(feats, np.zeros((T, 6), np.float32), bb, np.stack([ends - counts, ends], 1))
+    ids = [1, 0, 3, 2]
+    host = st.collate(ids)
+    devp = pad_on_device(st.collate_ragged(ids), "cuda:0")
+    eng = HotPathEngine(cfg, 4, 36, dtype="fp32")
+    eng.load_params(syn.make_params(cfg, seed=7, trained_like=True))
+    q = torch.tensor(rng.standard_normal((2, 4, 96)).astype(np.float32)).cuda()
+    a = eng.forward(host["features"].cuda(), host["boxes"].cuda(), q[0], q[1])
+    b = eng.forward(devp["features"], devp["boxes"], q[0], q[1])
+    assert torch.equal(a, b)

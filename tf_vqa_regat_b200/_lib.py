@@ -51,6 +51,7 @@ SIGNATURES = {
     "regat_geo_bwd_ex": [i32] * 6 + [vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, i32, vp],
     "regat_butd_pool_fwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp],
     "regat_butd_pool_bwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp],
+    "regat_pad_ragged": [i32, i32, i32, i64, vp, vp, vp, vp, vp],
     "regat_cast": [i32, i32, vp, vp, i64, vp],
     "regat_dp_reduce_bcast": [vp, C.c_uint64, vp, i32, i32, i64, i64, C.c_uint32, i32, vp],
     "regat_dp_allreduce_f32": [vp, C.c_uint64, vp, i32, i32, i64, i64, C.c_uint32, i32, vp],

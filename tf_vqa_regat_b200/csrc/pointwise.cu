@@ -699,6 +699,30 @@ __global__ void label_grad_kernel(const float* dc, float* grads, long long v_off
   if (b_off >= 0) grads[b_off] = *dc;
 }
 
+// dataset.py:329-346 (pad_sequences, padding='post') on the device: packed rows -> [B, N, width] with zero rows after each
+// sample's own.  One thread per 16 bytes of OUTPUT: every output byte is written exactly once, the read side touches only
+// the real rows.  width4 = width / 4.
+__global__ void pad_ragged_kernel(const float4* __restrict__ packed, const int* __restrict__ offsets, int N, int width4,
+                                  long long total4, long long total_rows, float4* __restrict__ padded) {
+  const long long row4 = (long long)N * width4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
+    const int b = (int)(i / row4);
+    const long long r = i - (long long)b * row4;
+    const int n = (int)(r / width4), c = (int)(r - (long long)n * width4);
+    const int lo = offsets[b], hi = offsets[b + 1];
+    const bool valid = lo >= 0 && hi >= lo && hi - lo <= N && (long long)hi <= total_rows;   // else: an all-zero sample
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid && n < hi - lo) v = packed[(long long)(lo + n) * width4 + c];
+    padded[i] = v;
+  }
+}
+__global__ void pad_ragged_check_kernel(const int* __restrict__ offsets, int B, int N, long long total_rows, int* bad) {
+  for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < B; b += gridDim.x * blockDim.x) {
+    const int lo = offsets[b], hi = offsets[b + 1];
+    if (lo < 0 || hi < lo || hi - lo > N || (long long)hi > total_rows) atomicExch(bad, b + 1);
+  }
+}
+
 inline int grid_for(long long n, int per_block = 256) {
   return (int)std::max<long long>(1, std::min<long long>((n + per_block - 1) / per_block, (long long)num_sms() * 8));
 }
@@ -943,6 +967,25 @@ extern "C" int regat_mul(int dtype, int rows, int cols, const void* a, int lda, 
   REGAT_REQUIRE(a && b && out, REGAT_ERR_ARG, "mul: null pointer");
   if (rows <= 0 || cols <= 0) return REGAT_OK;
   return k_mul(dtype, a, lda, b, ldb, out, ldo, rows, cols, (cudaStream_t)stream);
+}
+
+extern "C" int regat_pad_ragged(int B, int N, int width, int64_t total_rows, const float* packed, const int32_t* offsets,
+                                float* padded, int32_t* bad, regat_stream_t stream) {
+  REGAT_REQUIRE(B >= 0 && N >= 0 && width > 0 && total_rows >= 0, REGAT_ERR_SHAPE, "pad_ragged: negative size");
+  REGAT_REQUIRE(width % 4 == 0, REGAT_ERR_SHAPE, "pad_ragged: width (%d) must be a multiple of 4 floats", width);
+  if (B == 0 || N == 0) return REGAT_OK;
+  REGAT_REQUIRE(offsets && padded && (packed || total_rows == 0), REGAT_ERR_ARG, "pad_ragged: null pointer");
+  REGAT_REQUIRE(aligned16(packed) && aligned16(padded), REGAT_ERR_ALIGN, "pad_ragged: buffers must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (bad) {
+    pad_ragged_check_kernel<<<ceil_div(B, 256), 256, 0, st>>>(offsets, B, N, (long long)total_rows, bad);
+    REGAT_POST_LAUNCH();
+  }
+  const long long total4 = (long long)B * N * (width / 4);
+  pad_ragged_kernel<<<grid_for(total4), 256, 0, st>>>(reinterpret_cast<const float4*>(packed), offsets, N, width / 4, total4,
+                                                     (long long)total_rows, reinterpret_cast<float4*>(padded));
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
 }
 
 extern "C" int regat_cast(int from_dtype, int to_dtype, const void* in, void* out, int64_t n, regat_stream_t stream) {

@@ -5,7 +5,11 @@ The reference keeps the whole feature store in host memory -- `image_features [T
 `pad_sequences` (zero post-padding to the longest sample, dataset.py:334-346).  Here the same result is written straight
 into reusable (optionally pinned) buffers with one contiguous block copy per sample, ready for a single host->device copy;
 the padded rows are exactly zero, which is what the hot path's padded-object handling relies on (relation_encoder.py:20-21,
-SURVEY A.2-Q7/Q8)."""
+SURVEY A.2-Q7/Q8).
+
+`collate_ragged` + `pad_on_device` split the same assembly across the host link: only the real rows cross PCIe (packed back to
+back, plus B+1 offsets) and `regat_pad_ragged` writes the zero post-padded [B, N, .] tensors in HBM -- for K ~ U(10, 100)
+that is ~45 % fewer host->device bytes, which is what bounds the end-to-end step."""
 from typing import Dict, Optional, Sequence
 
 import numpy as np
@@ -59,6 +63,70 @@ class AdaptiveFeatureStore:
         out["n_obj"][:B] = torch.from_numpy(n)
         return {"features": out["features"][:B, :N], "normalized_bb": out["normalized_bb"][:B, :N], "boxes": out["boxes"][:B, :N],
                 "n_obj": out["n_obj"][:B]}
+
+
+    # ---- ragged transfer: real rows only over the host link, zero post-padding written on the device
+    def ragged_buffers(self, batch: int, max_total_rows: int, pin: bool = True) -> Dict[str, torch.Tensor]:
+        pin = bool(pin and torch.cuda.is_available())
+        return {"features": torch.zeros(max_total_rows, self.features.shape[1], dtype=torch.float32, pin_memory=pin),
+                "boxes": torch.zeros(max_total_rows, self.bb.shape[1], dtype=torch.float32, pin_memory=pin),
+                "offsets": torch.zeros(batch + 1, dtype=torch.int32, pin_memory=pin)}
+
+    def collate_ragged(self, image_ids: Sequence[int], out: Optional[Dict[str, torch.Tensor]] = None):
+        """-> dict(features [T, V], boxes [T, 4], offsets int32 [B+1], max_rois): the samples' rows back to back in batch order
+        (dataset.py:302-304 slices, no padding).  normalized_bb is not shipped: the hot path ignores it (rel_graph_net.py:23)."""
+        ids = np.asarray(image_ids, dtype=np.int64)
+        n = self.counts(ids)
+        B, T = len(ids), int(n.sum())
+        if out is None:
+            out = self.ragged_buffers(B, T, pin=False)
+        if out["features"].shape[0] < T or out["boxes"].shape[0] < T or out["offsets"].shape[0] < B + 1:
+            raise ValueError(f"ragged buffers are too small for {B} samples with {T} rows in total")
+        off = np.zeros(B + 1, dtype=np.int64)
+        np.cumsum(n, out=off[1:])
+        if T >= 2 ** 31:
+            raise ValueError("more than 2^31 rows in one batch")
+        f, bb = out["features"].numpy(), out["boxes"].numpy()
+        for i, img in enumerate(ids):
+            lo, hi = self.pos_boxes[img]
+            f[off[i]:off[i + 1]] = self.features[lo:hi]
+            bb[off[i]:off[i + 1]] = self.bb[lo:hi]
+        out["offsets"][:B + 1] = torch.from_numpy(off.astype(np.int32))
+        return {"features": out["features"][:T], "boxes": out["boxes"][:T], "offsets": out["offsets"][:B + 1],
+                "max_rois": int(n.max()) if B else 0}
+
+
+def pad_on_device(ragged: Dict[str, torch.Tensor], device, pad_to: Optional[int] = None, out: Optional[Dict[str, torch.Tensor]] = None,
+                  check: bool = True, non_blocking: bool = True) -> Dict[str, torch.Tensor]:
+    """Host-ragged batch (from `collate_ragged`) -> zero post-padded device tensors features [B, N, V], boxes [B, N, 4], as
+    dataset.py:329-346 would have built them on the host.  Copies only the packed rows and the offsets to the device, then
+    one `regat_pad_ragged` launch per tensor on the current stream.  With check=True invalid offsets raise (one device->host
+    read of a flag); `out` (dict with 'features' and 'boxes' of at least [B, N, .]) avoids allocation."""
+    from . import _lib
+    if not torch.cuda.is_available():
+        raise _lib.RegatError(-6, "pad_on_device needs a CUDA device; use AdaptiveFeatureStore.collate for host-side padding")
+    dev = torch.device(device)
+    off = ragged["offsets"]
+    B = off.numel() - 1
+    N = int(pad_to if pad_to is not None else ragged["max_rois"])
+    if N < ragged["max_rois"]:
+        raise ValueError(f"pad_to={N} is shorter than the longest sample ({ragged['max_rois']} objects)")
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    off_d = off.to(dev, non_blocking=non_blocking)
+    bad = torch.zeros(1, dtype=torch.int32, device=dev) if check else None
+    res = {}
+    for k in ("features", "boxes"):
+        src = ragged[k].to(dev, non_blocking=non_blocking)
+        T, W = src.shape
+        dst = out[k][:B, :N] if out is not None else torch.empty(B, N, W, dtype=torch.float32, device=dev)
+        if not dst.is_contiguous():
+            raise ValueError(f"out['{k}'] must be exactly [B={B}, N={N}, {W}] or larger only in the batch dimension")
+        _lib.check(_lib.lib().regat_pad_ragged(B, N, W, T, src.data_ptr(), off_d.data_ptr(), dst.data_ptr(), _lib.ptr(bad), stream))
+        res[k] = dst
+    if check and int(bad.item()):
+        raise ValueError(f"ragged batch: offsets of sample {int(bad.item()) - 1} are invalid (more than {N} rows, or out of range)")
+    res["n_obj"] = (off_d[1:] - off_d[:-1]).to(torch.int64)
+    return res
 
 
 def targets_from_answers(labels, scores, num_answers: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
