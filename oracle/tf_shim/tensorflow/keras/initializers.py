@@ -35,4 +35,11 @@ def get(name):
             lim = math.sqrt(6.0 / (fi + fo))
             return ((torch.rand(shape, generator=_random._gen, dtype=torch.float64) * 2 - 1) * lim).to(dt)
         return init
+    if name == "orthogonal":
+        def init(shape, dt):
+            a = torch.randn(shape, generator=_random._gen, dtype=torch.float64)
+            q, r = torch.linalg.qr(a if shape[0] >= shape[1] else a.T)
+            q = q * torch.sign(torch.diagonal(r))
+            return (q if shape[0] >= shape[1] else q.T).to(dt)
+        return init
     raise ValueError(f"initializer {name!r} is not part of the stand-in")

@@ -1,5 +1,6 @@
 """tf.keras.layers stand-in: the Layer protocol (build on first call, weight tracking in
-Keras-2 order) and the five stock layers the hot path instantiates.  TEST INFRASTRUCTURE.
+Keras-2 order) and the stock layers the reference instantiates (five on the hot path, GRU in the
+question front-end).  TEST INFRASTRUCTURE.
 
 Keras-2 semantics restated here (keras/engine/base_layer.py):
   * __call__ converts inputs, builds the layer on first use (build(input_shape), then
@@ -66,10 +67,24 @@ class Layer:
 
     @property
     def trainable_weights(self):
-        return [w for w in self.weights if getattr(w, "trainable", True)] if self.trainable else []
+        """Keras: a layer with trainable=False contributes none of its variables, nor do its sub-layers'."""
+        if not self.trainable:
+            return []
+        out, seen = [], set()
+        own = [w for w in self._own_weights if getattr(w, "trainable", True)]
+        for w in own + [w for c in self._children() for w in c.trainable_weights]:
+            if id(w) not in seen:
+                seen.add(id(w))
+                out.append(w)
+        return out
 
-    trainable_variables = trainable_weights
-    variables = weights
+    @property
+    def trainable_variables(self):
+        return self.trainable_weights
+
+    @property
+    def variables(self):
+        return self.weights
 
     def named_weights(self, prefix=""):
         """(path, variable) in `weights` order; paths are attribute names joined by '.', list elements by index."""
@@ -186,12 +201,41 @@ class Activation(Layer):
 
 
 class GRU(Layer):
-    """Constructor only: the question front-end (language_model.py) is outside the hot path and is
-    never called by oracle/make_golden_ref.py; the class exists so that its module imports."""
+    """keras.layers.GRU (TF2 defaults: activation tanh, recurrent_activation sigmoid, use_bias, reset_after=True, zero
+    initial state, no masking unless a mask is passed -- the reference passes none).  Variables in Keras order:
+    kernel [in, 3u], recurrent_kernel [u, 3u], bias [2, 3u] (row 0 input bias, row 1 recurrent bias); gate blocks z | r | h.
 
-    def __init__(self, units, **kwargs):
+        x_t W + b_0 -> (xz, xr, xh);  h_{t-1} U + b_1 -> (hz, hr, hh)
+        z = sigmoid(xz + hz);  r = sigmoid(xr + hr);  c = tanh(xh + r * hh);  h_t = z * h_{t-1} + (1 - z) * c
+
+    The question front-end (language_model.py:96-131) is the only user; dropout is forced to 0 there (:105)."""
+
+    def __init__(self, units, dropout=0.0, return_sequences=False, return_state=False, **kwargs):
         super().__init__()
-        self.units = units
+        assert not dropout, "the reference forces GRU dropout to 0 (language_model.py:105)"
+        self.units, self.return_sequences, self.return_state = int(units), return_sequences, return_state
 
-    def call(self, *a, **k):
-        raise NotImplementedError("GRU is outside the pinned path")
+    def build(self, input_shape):
+        u = self.units
+        self.kernel = self.add_weight("kernel", shape=[int(input_shape[-1]), 3 * u])
+        self.recurrent_kernel = self.add_weight("recurrent_kernel", shape=[u, 3 * u], initializer="orthogonal")
+        self.bias = self.add_weight("bias", shape=[2, 3 * u], initializer="zeros")
+        self.built = True
+
+    def call(self, inputs):
+        x = _t(inputs)
+        B, T, _ = x.shape
+        u = self.units
+        W, U, b = _t(self.kernel), _t(self.recurrent_kernel), _t(self.bias)
+        h = torch.zeros(B, u, dtype=x.dtype)
+        seq = []
+        for t in range(T):
+            xi = torch.matmul(x[:, t], W) + b[0]
+            hi = torch.matmul(h, U) + b[1]
+            z = torch.sigmoid(xi[:, :u] + hi[:, :u])
+            r = torch.sigmoid(xi[:, u:2 * u] + hi[:, u:2 * u])
+            c = torch.tanh(xi[:, 2 * u:] + r * hi[:, 2 * u:])
+            h = z * h + (1 - z) * c
+            seq.append(h)
+        out = _w(torch.stack(seq, dim=1)) if self.return_sequences else _w(h)
+        return (out, _w(h)) if self.return_state else out
