@@ -335,6 +335,49 @@ REGAT_API int regat_engine_train_step_dl(regat_engine* e, struct DLManagedTensor
                                struct DLManagedTensor* q_last, struct DLManagedTensor* target,
                                float lr, int step, float* loss_out, regat_stream_t stream);
 
+/* ------------------------------------------------------------------ question front-end (next row) ---------
+ * model/language_model.py:10-174, fp32: what is not a GEMM.  The dense products (x_t W, h U, the two attention FCs and all
+ * of their transposes) are regat_gemm calls; tf_vqa_regat_b200/question.py sequences them with the kernels below.
+ *
+ * regat_q_embed_fwd   language_model.py:33-40 (+ :88-90 when emb2 != NULL, op 'c'): out[r,:] = [emb[tok_r] | emb2[tok_r]],
+ *                     zero for tok_r == n_token (the padding index); tables [n_token+1, E]; out [BT, E or 2E].
+ * regat_q_embed_bwd   its transpose: demb[tok_r] += dX[r, :E], demb2[tok_r] += dX[r, E:] (atomic; caller zeroes the tables;
+ *                     a NULL table is skipped -- the frozen second table, language_model.py:58).
+ * regat_q_gru_gates_* one step of keras.layers.GRU (reset_after, blocks z|r|h, language_model.py:106-108): given
+ *                     xi = x_t W + b0 (row pitch ld_xi) and hi = h_{t-1} U + b1 [B,3H]:
+ *                       z = sig(xz+hz), r = sig(xr+hr), c = tanh(xh + r*hh), h_t = z*h_{t-1} + (1-z)*c
+ *                     fwd saves z, r, c and a copy of h_{t-1} ([B,H] each; hp == NULL means the zero initial state);
+ *                     bwd takes dh = dh_seq (+ dh_rec) and writes dxi = (dz, dr, da), dhi = (dz, dr, da*r) and
+ *                     dhp = dh*z; the caller then accumulates dhi . U^T onto dhp with regat_gemm.
+ * regat_q_batch_softmax_*  language_model.py:159-165: P[T,B] = softmax over the BATCH of logits[B,T] transposed.
+ * regat_q_pool_*      :165-170: P's memory re-read as w[B,T] (raw reshape); q_att[b,:] = sum_t w[b,t] seq[b,t,:].
+ *                     bwd: dseq[b,t,:] = w[b,t] dq_att[b,:] (+ dq_last[b,:] at t = T-1, :120), dW[b,t] = <dq_att[b], seq[b,t]>.
+ * regat_q_dot         out[0] += sum a*b (caller zeroes out).   regat_q_wn_alpha: alpha = g / sqrt(max(vv, 1e-12)).
+ * regat_q_wn_bwd      weight_norm.py:41 backward from G = dL/dW_eff: dv = alpha (G - Gv v / vv), dg = Gv / sqrt(vv).
+ * regat_q_clip_adamax train.py:112-113 for one tensor: clip_by_norm with ||g||^2 = *gsumsq, then Keras Adamax step `step`. */
+REGAT_API int regat_q_embed_fwd(const int32_t* tokens, int64_t BT, int n_token, int E, const float* emb, const float* emb2,
+                      float* out, regat_stream_t stream);
+REGAT_API int regat_q_embed_bwd(const int32_t* tokens, int64_t BT, int n_token, int E, int width, const float* dX, float* demb,
+                      float* demb2, regat_stream_t stream);
+REGAT_API int regat_q_gru_gates_fwd(int B, int H, const float* xi, int64_t ld_xi, const float* hi, const float* hp, int64_t ld_hp,
+                          float* h_out, int64_t ld_h, float* z, float* r, float* c, float* hp_copy, regat_stream_t stream);
+REGAT_API int regat_q_gru_gates_bwd(int B, int H, const float* dh_seq, int64_t ld_dseq, const float* dh_rec, const float* z,
+                          const float* r, const float* c, const float* hp_copy, const float* hi, float* dxi, int64_t ld_dxi,
+                          float* dhi, float* dhp, regat_stream_t stream);
+REGAT_API int regat_q_tanh_fwd(float* x, int64_t n, regat_stream_t stream);
+REGAT_API int regat_q_tanh_bwd(float* dy, const float* y, int64_t n, regat_stream_t stream);
+REGAT_API int regat_q_batch_softmax_fwd(const float* logits, int B, int T, float* P, regat_stream_t stream);
+REGAT_API int regat_q_batch_softmax_bwd(const float* P, const float* dP, int B, int T, float* dlogits, regat_stream_t stream);
+REGAT_API int regat_q_pool_fwd(const float* w_flat, const float* seq, int B, int T, int H, float* q_att, regat_stream_t stream);
+REGAT_API int regat_q_pool_bwd(const float* w_flat, const float* seq, const float* dq_att, const float* dq_last, int B, int T, int H,
+                     float* dseq, float* dW, regat_stream_t stream);
+REGAT_API int regat_q_dot(const float* a, const float* b, int64_t n, float* out, regat_stream_t stream);
+REGAT_API int regat_q_wn_alpha(const float* g, const float* vv, float* alpha, regat_stream_t stream);
+REGAT_API int regat_q_wn_bwd(const float* G, const float* v, const float* g, const float* vv, const float* Gv, int64_t n, float* dv,
+                   float* dg, regat_stream_t stream);
+REGAT_API int regat_q_clip_adamax(float* w, const float* grad, float* m, float* u, int64_t n, const float* gsumsq, float clip,
+                        float lr, int step, float beta1, float beta2, float eps, regat_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,95 @@
+"""Host logic of tf_vqa_regat_b200/question.py (the launch sequence of the question front-end) dry-run on the
+CPU: the module runs unchanged, with the library's entry points replaced by tests/_host_emulation.py, and must reproduce
+the oracle that is pinned to the executed reference (tests/golden/refexec_question_*.npz).  What this covers: operand
+shapes / transposes / leading dimensions of every GEMM, buffer offsets, the back-propagation through time, weight-norm
+backward, clip + Adamax.  What it cannot cover -- the CUDA kernels themselves -- is tests/test_gpu_question.py."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import language_model as olm
+from oracle import regat_torch as ot
+from tf_vqa_regat_b200.question import QuestionFrontEnd, question_layout
+
+from _host_emulation import HostOps
+
+
+def _setup(op, B, emb2_trainable, n_token=40, E=10, H=24, T=14, max_batch=None):
+    fe = QuestionFrontEnd(n_token, E, H, op=op, seq_len=T, max_batch=max_batch or B, emb2_trainable=emb2_trainable, device="cpu",
+                          _ops=HostOps())
+    front = olm.make_params(n_token, E, H, op, seed=11)
+    fe.load_named(front)
+    tok = olm.make_tokens(B, n_token, T, seed=21)
+    return fe, front, tok
+
+
+def _oracle(front, tok, n_token, op, dq_att, dq_last, trainable):
+    p = {k: torch.tensor(np.asarray(v, dtype=np.float64), requires_grad=True) for k, v in front.items()}
+    q = olm.forward(p, tok, n_token, op)
+    loss = (q["q_att"] * torch.tensor(dq_att, dtype=torch.float64)).sum() + (q["q_last"] * torch.tensor(dq_last, dtype=torch.float64)).sum()
+    loss.backward()
+    return q, {k: (v.grad.numpy() if v.grad is not None else np.zeros(v.shape)) for k, v in p.items()}
+
+
+def test_layout_matches_the_oracle_order():
+    ent, total = question_layout(40, 10, 24, "c")
+    assert [(n, tuple(s)) for n, s, _ in ent] == [(n, tuple(s)) for n, s, _ in olm.param_shapes(40, 10, 24, "c")]
+    assert all(o % 64 == 0 for _, _, o in ent) and total % 64 == 0
+    assert [n for n, _, _ in question_layout(40, 10, 24, "")[0]][1] == "q_emb.gru/kernel"
+
+
+@pytest.mark.parametrize("op,B,emb2_tr,max_batch", [("c", 3, False, None), ("c", 4, True, 6), ("", 2, False, None)])
+def test_forward_backward_sequence_matches_oracle(op, B, emb2_tr, max_batch):
+    fe, front, tok = _setup(op, B, emb2_tr, max_batch=max_batch)
+    q_att, q_last = fe.forward(torch.tensor(tok, dtype=torch.int32))
+    rng = np.random.default_rng(5)
+    dqa, dql = rng.standard_normal((B, 24)).astype(np.float32), rng.standard_normal((B, 24)).astype(np.float32)
+    q, grads = _oracle(front, tok, 40, op, dqa, dql, None)
+    np.testing.assert_allclose(q_att.numpy(), q["q_att"].detach().numpy(), rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(q_last.numpy(), q["q_last"].detach().numpy(), rtol=2e-5, atol=2e-6)
+    fe.backward(torch.tensor(dqa), torch.tensor(dql))
+    got = {k: v.numpy() for k, v in fe.named(fe.grads).items()}
+    for name in got:
+        if name == "w_emb.emb_/emb_" and not emb2_tr:
+            assert not got[name].any()                                   # frozen table: no gradient is produced
+            continue
+        scale = max(np.abs(grads[name]).max(), 1e-6)
+        assert np.abs(got[name] - grads[name]).max() < 5e-5 * scale + 1e-7, name
+    pad_rows = got["w_emb.emb/emb"][40]
+    assert not pad_rows.any()                                             # the padding row never receives gradient
+
+
+def test_update_is_per_tensor_clip_then_adamax():
+    fe, front, tok = _setup("c", 3, True)
+    rng = np.random.default_rng(6)
+    dqa, dql = rng.standard_normal((3, 24)).astype(np.float32), rng.standard_normal((3, 24)).astype(np.float32)
+    p = {k: np.asarray(v, dtype=np.float64) for k, v in front.items()}
+    m = {k: np.zeros_like(v) for k, v in p.items()}; u = {k: np.zeros_like(v) for k, v in p.items()}
+    for step in (1, 2, 3):                                                # m / u carry over between steps
+        fe.forward(torch.tensor(tok, dtype=torch.int32))
+        fe.backward(torch.tensor(dqa), torch.tensor(dql))
+        fe.update(1e-3, step)
+        _, grads = _oracle(p, tok, 40, "c", dqa, dql, None)
+        for k in p:
+            p[k], m[k], u[k] = ot.adamax_step(p[k], ot.clip_by_norm(grads[k], 0.25), m[k], u[k], step, 1e-3)
+    got = {k: v.numpy() for k, v in fe.named().items()}
+    for k in p:
+        if k == "q_att.linear2/bias":
+            continue     # a constant added to every logit of a position: softmax-shift invariant, gradient is rounding noise -> +-lr
+        # an Adamax step is at most lr per element; fp32 storage of the parameters and of m / u is the only difference
+        assert np.abs(got[k] - p[k]).max() < 0.02 * 3 * 1e-3, k
+    assert np.abs(got["w_emb.emb/emb"] - np.asarray(front["w_emb.emb/emb"])).max() > 1e-3      # it did move
+
+
+def test_input_validation():
+    fe, _, tok = _setup("c", 3, False)
+    with pytest.raises(ValueError):
+        fe.forward(torch.tensor(tok[:1], dtype=torch.int32))             # batch 1 (language_model.py:159 squeeze)
+    with pytest.raises(ValueError):
+        fe.forward(torch.tensor(tok, dtype=torch.int64))
+    with pytest.raises(RuntimeError):
+        fe.backward(torch.zeros(3, 24), torch.zeros(3, 24))
+    from tf_vqa_regat_b200._lib import RegatError
+    if not torch.cuda.is_available():
+        with pytest.raises(RegatError):
+            QuestionFrontEnd(40, 10, 24)                                 # no CUDA, no emulation handed in: refuses

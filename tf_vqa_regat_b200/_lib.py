@@ -78,6 +78,20 @@ SIGNATURES = {
     "regat_engine_buffer": [vp, C.c_char_p, C.POINTER(vp)],
     "regat_engine_forward_dl": [vp, vp, vp, vp, vp, vp, vp],
     "regat_engine_train_step_dl": [vp, vp, vp, vp, vp, vp, f32, i32, vp, vp],
+    "regat_q_embed_fwd": [vp, i64, i32, i32, vp, vp, vp, vp],
+    "regat_q_embed_bwd": [vp, i64, i32, i32, i32, vp, vp, vp, vp],
+    "regat_q_gru_gates_fwd": [i32, i32, vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp],
+    "regat_q_gru_gates_bwd": [i32, i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp],
+    "regat_q_tanh_fwd": [vp, i64, vp],
+    "regat_q_tanh_bwd": [vp, vp, i64, vp],
+    "regat_q_batch_softmax_fwd": [vp, i32, i32, vp, vp],
+    "regat_q_batch_softmax_bwd": [vp, vp, i32, i32, vp, vp],
+    "regat_q_pool_fwd": [vp, vp, i32, i32, i32, vp, vp],
+    "regat_q_pool_bwd": [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp],
+    "regat_q_dot": [vp, vp, i64, vp, vp],
+    "regat_q_wn_alpha": [vp, vp, vp, vp],
+    "regat_q_wn_bwd": [vp, vp, vp, vp, vp, i64, vp, vp, vp],
+    "regat_q_clip_adamax": [vp, vp, vp, vp, i64, vp, f32, f32, i32, f32, f32, f32, vp],
 }
 
 

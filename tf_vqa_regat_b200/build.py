@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libregat.so")
-SOURCES = ["capi.cu", "engine.cu", "pointwise.cu", "geoattn.cu", "gemm_simt.cu", "gemm_tc.cu", "dp_exchange.cu"]
+SOURCES = ["capi.cu", "engine.cu", "pointwise.cu", "geoattn.cu", "gemm_simt.cu", "gemm_tc.cu", "dp_exchange.cu", "question.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "kernels.h"),
            os.path.join(os.path.dirname(HERE), "include", "regat.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
