@@ -50,6 +50,50 @@ def main():
     with open(path, "w") as f:
         json.dump(api, f, indent=1, sort_keys=True)
     print("wrote", path, len(api), "entries")
+    variable_order()
+
+
+def variable_order():
+    """`model.weights` of the reference's RelationGraphAttentionNetwork (built and called once, as rel_graph_net.py:113-123
+    does) under the stand-in's Keras-2 tracking rules: [keras-style path, normalised name, shape, trainable] per variable, in
+    the order `save_weights` / `load_weights` use (main.py:145,155): HDF5 checkpoints store, per top-level layer
+    (w_emb, q_emb, q_att, v_relation, joint_emb, classifier -- rel_graph_net.py:16-21), that layer's `weights`.  (Keras lists a
+    layer's non-trainable variables after its trainable ones; the only frozen variable, w_emb.emb_, already comes last within
+    its layer, so the per-layer order is the same either way.)  Two builds: label_bias off (the shipped config) and on."""
+    sys.path.insert(0, ROOT)
+    import numpy as np
+    import tensorflow as tf
+    from model import relation_encoder as ref_enc
+    from model.classifier import SimpleClassifier
+    from model.fusion import BUTD
+    from model.language_model import QuestionEmbedding, QuestionSelfAttention, WordEmbedding
+    from model.position_emb import prepare_graph_variables
+    from model.rel_graph_net import RelationGraphAttentionNetwork
+    from oracle.make_golden_ref import _norm_name
+    dims = dict(n_token=60, emb_dim=12, v_dim=192, q_dim=96, rel_dim=256, num_heads=4, nongt_dim=20, num_answers=301, dir_num=2,
+                pos_emb_dim=64)
+    out = {"dims": dims}
+    for label_bias in (False, True):
+        d = dims
+        model = RelationGraphAttentionNetwork(
+            WordEmbedding(d["n_token"], d["emb_dim"], 0.2, "c"), QuestionEmbedding(2 * d["emb_dim"], d["q_dim"], 1, False, 0.2),
+            QuestionSelfAttention(d["q_dim"], 0.2),
+            ref_enc.ImplicitRelationEncoder(d["v_dim"], d["q_dim"], d["rel_dim"], d["dir_num"], d["pos_emb_dim"], d["nongt_dim"],
+                                            num_heads=d["num_heads"], num_steps=1, residual_connection=True, label_bias=label_bias),
+            BUTD(d["rel_dim"], d["q_dim"], d["q_dim"]), SimpleClassifier(d["q_dim"], 2 * d["q_dim"], d["num_answers"], 0.2),
+            "butd", "implicit")
+        rng = np.random.default_rng(0)
+        bb = np.sort(rng.uniform(0, 400, (2, 24, 4)).astype(np.float32), -1)
+        pos, _, _ = prepare_graph_variables("implicit", bb, None, None, 24, d["nongt_dim"], 64, 11, 15)
+        model(np.abs(rng.standard_normal((2, 24, d["v_dim"]))).astype(np.float32), None,
+              tf.constant(rng.integers(0, d["n_token"], (2, 14))), pos, None, None)
+        tv = model.trainable_variables
+        out["label_bias_%s" % str(label_bias).lower()] = [
+            [n, _norm_name(n), list(w.shape), any(w is t for t in tv)] for n, w in model.named_weights()]
+    path = os.path.join(ROOT, "tests", "golden", "reference_variable_order.json")
+    with open(path, "w") as f:
+        json.dump(out, f, indent=1)
+    print("wrote", path, len(out["label_bias_false"]), "variables")
 
 
 if __name__ == "__main__":

@@ -54,3 +54,43 @@ def test_mismatches_raise_like_keras(tmp_path):
     other = HotPathConfig(**{**{k: getattr(SMALL, k) for k in SMALL.__dataclass_fields__}, "label_bias": True})
     with pytest.raises(ValueError):
         ck.arrays_to_flat(other, arrays)
+
+
+def test_variable_order_is_the_executed_reference_order():
+    """tests/golden/reference_variable_order.json: `model.weights` of the reference's own RelationGraphAttentionNetwork, built and
+    called over the TensorFlow stand-in (oracle/make_reference_api.py).  The flat layouts used on the device follow it."""
+    import json
+    import os
+    from tf_vqa_regat_b200.question import question_layout
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_variable_order.json")))
+    d = ref["dims"]
+    for label_bias in (False, True):
+        cfg = HotPathConfig(v_dim=d["v_dim"], q_dim=d["q_dim"], rel_dim=d["rel_dim"], num_heads=d["num_heads"], nongt_dim=d["nongt_dim"],
+                            num_answers=d["num_answers"], dir_num=d["dir_num"], pos_emb_dim=d["pos_emb_dim"], label_bias=label_bias)
+        mine = [(n, list(s)) for n, s, _ in question_layout(d["n_token"], d["emb_dim"], d["q_dim"], "c")[0]] + \
+               [(e.name, list(e.shape)) for e in param_layout(cfg)[0]]
+        theirs = [(norm, shape) for _, norm, shape, _ in ref["label_bias_%s" % str(label_bias).lower()]]
+        assert mine == theirs
+    frozen = [norm for _, norm, _, tr in ref["label_bias_false"] if not tr]
+    assert frozen == ["w_emb.emb_/emb_"]                     # language_model.py:58: the second table starts frozen
+    assert ("v_relation.implicit_relation.bias/bias" in [r[1] for r in ref["label_bias_true"]]
+            and "v_relation.implicit_relation.bias/bias" not in [r[1] for r in ref["label_bias_false"]])
+
+
+def test_whole_model_checkpoint_round_trip(tmp_path):
+    from tf_vqa_regat_b200.question import question_layout
+    from oracle import language_model as olm
+    front = olm.make_params(60, 12, SMALL.q_dim, "c", seed=11)
+    shapes = [(n, s) for n, s, _ in question_layout(60, 12, SMALL.q_dim, "c")[0]]
+    flat = syn.make_params(SMALL, seed=5, trained_like=True)
+    p = tmp_path / "model.npz"
+    ck.save_model_weights(str(p), [front[n] for n, _ in shapes], SMALL, flat)
+    fa, back = ck.load_model_weights(str(p), SMALL, shapes)
+    for (n, _), a in zip(shapes, fa):
+        np.testing.assert_array_equal(a, np.asarray(front[n], dtype=np.float32))
+    for e in param_layout(SMALL)[0]:
+        np.testing.assert_array_equal(back[e.offset:e.offset + e.numel], flat[e.offset:e.offset + e.numel])
+    with pytest.raises(ValueError, match="q_emb.gru/kernel"):
+        ck.load_model_weights(str(p), SMALL, [(n, (s if n != "q_emb.gru/kernel" else (5, 5))) for n, s in shapes])
+    with pytest.raises(ValueError):
+        ck.load_model_weights(str(p), SMALL, shapes[:-1])      # one front-end variable short: the hot-path count no longer fits

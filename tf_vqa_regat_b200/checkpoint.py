@@ -6,7 +6,9 @@ image, so the container here is `.npz`; the ORDER is the contract and is the sam
 (weight_norm.py:21-31), layers in attribute-assignment order (rel_graph_net.py:16-21, relation_encoder.py:53-58,
 graph_att_net.py:24-36, graph_att_layer.py:25-37, fusion.py:15-20, classifier.py:14-19) -- i.e. `config.param_layout`.
 A maintainer with h5py converts a reference checkpoint by listing its datasets in file order and passing them to
-`arrays_to_flat` (the language front-end's variables, which precede these in the file, are outside this path).
+`arrays_to_flat`; the question front-end's variables precede the hot path's in the file (w_emb, q_emb, q_att come first,
+rel_graph_net.py:16-18) -- `save_model_weights` / `load_model_weights` keep that whole-model order
+(tests/golden/reference_variable_order.json is the order recorded from the executed reference).
 
 Arrays are stored under keys "000:<name>", "001:<name>", ... so that the file is self-describing, but loading goes by index
 and validates count and shapes the way Keras does (ValueError naming the offending variable)."""
@@ -62,3 +64,26 @@ def load_weights(path: str, cfg: HotPathConfig) -> np.ndarray:
         keys = sorted(k for k in z.files if k != "__meta__")
         arrays = [z[k] for k in keys]
     return arrays_to_flat(cfg, arrays)
+
+
+# ---- whole model: question front-end (question.py) + hot path, in the reference's top-level layer order
+def save_model_weights(path: str, front_arrays: Iterable, cfg: HotPathConfig, flat) -> None:
+    """front_arrays: the front-end's variables in Keras order (QuestionFrontEnd.named().values()); then the hot path's."""
+    arrays = [np.asarray(a, dtype=np.float32) for a in front_arrays] + flat_to_arrays(cfg, flat)
+    with open(path, "wb") as f:
+        np.savez(f, **{f"{i:03d}": a for i, a in enumerate(arrays)})
+
+
+def load_model_weights(path: str, cfg: HotPathConfig, front_shapes):
+    """-> (front-end arrays in order, hot-path flat buffer).  front_shapes: [(name, shape)] the front-end expects
+    (question.question_layout); count and shapes are validated like load_weights."""
+    with np.load(path) as z:
+        arrays = [z[k] for k in sorted(z.files) if k != "__meta__"]
+    front_shapes = list(front_shapes)
+    n = len(front_shapes)
+    if len(arrays) < n:
+        raise ValueError(f"weight list of length {len(arrays)}, but the front-end alone expects {n} variables")
+    for (name, shape), a in zip(front_shapes, arrays[:n]):
+        if tuple(a.shape) != tuple(shape):
+            raise ValueError(f"variable {name} has shape {tuple(shape)}, but the checkpoint holds {tuple(a.shape)}")
+    return arrays[:n], arrays_to_flat(cfg, arrays[n:])
