@@ -16,7 +16,7 @@ import types
 
 import numpy as np
 
-from .make_golden_ref import GOLD, LR, ROOT, SMALL, TINY, _import_reference, _norm_name
+from .make_golden_ref import GOLD, LR, SMALL, TINY, _import_reference, _norm_name
 
 CASES = {
     # name: (hot-path cfg kwargs, B, N, adaptive, n_token, emb_dim, op, emb_ trainable (tf-idf init ran, language_model.py:79), steps)

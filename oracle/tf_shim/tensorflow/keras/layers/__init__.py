@@ -13,13 +13,11 @@ Keras-2 semantics restated here (keras/engine/base_layer.py):
   * assigning to an attribute that currently holds a tracked variable un-tracks that variable
     (Layer.__setattr__ deletes the old attribute first) -- weight_norm.py:31 relies on it.
 """
-import math as _math
-
 import numpy as np
 import torch
 
 from .. import initializers as _init
-from ..._core import Tensor, Variable, _dt, _t, _w, floatx
+from ..._core import Variable, _dt, _t, _w, floatx
 
 
 class Layer:

@@ -11,7 +11,7 @@ import torch
 
 from oracle import language_model as olm
 from tf_vqa_regat_b200 import synthetic as syn
-from tf_vqa_regat_b200.config import HotPathConfig, param_layout
+from tf_vqa_regat_b200.config import HotPathConfig
 
 from _host_emulation import HostOps
 
