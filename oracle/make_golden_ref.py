@@ -39,6 +39,7 @@ CASES = {
     # name: (cfg kwargs, B, N, adaptive, trained_like, train steps)
     "tiny_n9_m5": (TINY, 3, 9, True, True, 3),
     "tiny_n4_m5_init": (TINY, 2, 4, False, False, 2),
+    "tiny_n100_m100_fullkk": (dict(TINY, nongt_dim=100), 2, 100, True, True, 2),      # K x K bias at the adaptive maximum
     "small_n36_m20": (SMALL, 3, 36, True, True, 3),
     "small_n36_m20_init": (SMALL, 3, 36, True, False, 2),
     "small_n12_clamped": (SMALL, 2, 12, False, True, 2),
