@@ -20,4 +20,9 @@ Pinning status:
     1e-10 (tests/test_refexec.py).  What stays an assumption is that the
     stand-in's primitives do what TensorFlow's documentation says; they are
     checked against independent implementations, not against TensorFlow.
+  * question front-end (language_model.py) -- oracle/language_model.py,
+    pinned the same way by tests/golden/refexec_question_*.npz
+    (oracle/make_golden_ref_question.py), whole model tokens -> logits included.
+  * batch assembly (dataset.py:288-355) -- oracle/dataset_collate.py, a plain-NumPy
+    restatement (Keras' pad_sequences is absent); no reference vectors exist for it.
 """
