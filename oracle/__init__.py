@@ -23,6 +23,8 @@ Pinning status:
   * question front-end (language_model.py) -- oracle/language_model.py,
     pinned the same way by tests/golden/refexec_question_*.npz
     (oracle/make_golden_ref_question.py), whole model tokens -> logits included.
-  * batch assembly (dataset.py:288-355) -- oracle/dataset_collate.py, a plain-NumPy
-    restatement (Keras' pad_sequences is absent); no reference vectors exist for it.
+  * batch assembly (dataset.py:270-355) -- oracle/dataset_collate.py, pinned by
+    tests/golden/refexec_collate.npz: the reference's own dataset.py (tensorize /
+    split_entries / trim_collate) executed on an in-memory store
+    (oracle/make_golden_ref_collate.py; Keras' pad_sequences restated in the stand-in).
 """

@@ -6,6 +6,8 @@ Reference semantics restated:
   * dataset.py:314-318   target = zeros(num_ans); np.put_along_axis(target, labels, scores, 0)   (a later duplicate label wins)
   * dataset.py:334,340,346  keras pad_sequences(..., padding='post', maxlen=<longest in the batch>, dtype=float32):
                          zero rows appended after the real ones, every sample padded to the batch maximum
+Pinned by tests/golden/refexec_collate.npz: the reference's own dataset.py (tensorize / split_entries / trim_collate) executed on
+an in-memory store over oracle/tf_shim (oracle/make_golden_ref_collate.py).
 Keras is not installed here; `pad_sequences` with padding='post' and maxlen equal to the longest sequence neither truncates
 nor reorders, it only appends zeros (keras/utils/sequence_utils.py), which is what `_pad_post` does."""
 import numpy as np

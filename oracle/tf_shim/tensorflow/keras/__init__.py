@@ -1,5 +1,5 @@
 """tf.keras stand-in: layers, Model, backend.set_floatx, optimizers.experimental.Adamax.  TEST INFRASTRUCTURE."""
-from . import initializers, layers, optimizers  # noqa: F401
+from . import initializers, layers, optimizers, preprocessing, utils  # noqa: F401
 from .. import _core
 
 

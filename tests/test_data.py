@@ -137,3 +137,34 @@ def test_engine_on_device_padded_batch_matches_host_padded_batch():
     a = eng.forward(host["features"].cuda(), host["boxes"].cuda(), q[0], q[1])
     b = eng.forward(devp["features"], devp["boxes"], q[0], q[1])
     assert torch.equal(a, b)
+
+
+def test_collate_matches_the_executed_reference(golden_dir):
+    """tests/golden/refexec_collate.npz: the reference's own dataset.py (tensorize / split_entries / trim_collate) executed on
+    an in-memory store (oracle/make_golden_ref_collate.py).  Host collate, ragged collate and the oracle restatement all
+    reproduce it bit for bit."""
+    import os
+    g = np.load(os.path.join(golden_dir, "refexec_collate.npz"))
+    st = AdaptiveFeatureStore(g["image_features"], g["spatial_features"], g["image_bb"], g["pos_boxes"])
+    ids = g["ids"].tolist()
+    parse = lambda s, t: [t(x) for x in str(s).split(",")] if str(s) else []
+    labels = [parse(s, int) for s in g["labels"]]
+    scores = [parse(s, float) for s in g["scores"]]
+    got = st.collate(ids)
+    assert got["features"].dtype == torch.float32
+    np.testing.assert_array_equal(got["features"].numpy(), g["features"])
+    np.testing.assert_array_equal(got["normalized_bb"].numpy(), g["normalized_bb"])
+    np.testing.assert_array_equal(got["boxes"].numpy(), g["boxes"])
+    t = targets_from_answers(labels, scores, int(g["num_ans"])).numpy()
+    np.testing.assert_array_equal(t, g["targets"])
+    assert t[0, 4] == np.float32(0.9) and t[5, 1] == np.float32(0.9) and not t[1].any()      # last duplicate wins; no answers -> zeros
+    f0, n0, b0, t0 = oc.collate(g["image_features"], g["spatial_features"], g["image_bb"], g["pos_boxes"], ids,
+                                [l if l else None for l in labels], scores, int(g["num_ans"]))
+    np.testing.assert_array_equal(f0, g["features"]); np.testing.assert_array_equal(n0, g["normalized_bb"])
+    np.testing.assert_array_equal(b0, g["boxes"]); np.testing.assert_array_equal(t0, g["targets"])
+    rg = st.collate_ragged(ids)
+    off = rg["offsets"].numpy()
+    for k in range(len(ids)):
+        c = off[k + 1] - off[k]
+        np.testing.assert_array_equal(rg["features"][off[k]:off[k + 1]].numpy(), g["features"][k, :c])
+        assert not g["features"][k, c:].any()
