@@ -168,3 +168,20 @@ def test_collate_matches_the_executed_reference(golden_dir):
         c = off[k + 1] - off[k]
         np.testing.assert_array_equal(rg["features"][off[k]:off[k + 1]].numpy(), g["features"][k, :c])
         assert not g["features"][k, c:].any()
+
+
+def test_tokenize_questions_matches_the_executed_reference(golden_dir):
+    """tests/golden/refexec_tokens.json: Dictionary.tokenize + VQAFeatureDataset.tokenize of the reference's dataset.py, executed."""
+    import json
+    import os
+    from tf_vqa_regat_b200.data import tokenize_questions
+    g = json.load(open(os.path.join(golden_dir, "refexec_tokens.json")))
+    t = tokenize_questions(g["questions"], g["word2idx"])
+    assert t.dtype == torch.int32 and tuple(t.shape) == (len(g["questions"]), 14)
+    assert t.tolist() == g["q_token"]
+    assert g["padding_idx"] == g["ntoken"] and (t[6] == g["ntoken"]).all()                # the empty question is all padding
+    assert t[0, 4].item() == g["word2idx"]["'s"]                                           # "man's" -> "man", "'s"
+    unk = g["ntoken"] - 1
+    assert unk in t[7].tolist() and len([x for x in t[7].tolist() if x != g["ntoken"]]) == 14   # unknown -> last word; cut at 14
+    buf = torch.zeros(16, 14, dtype=torch.int32)
+    assert tokenize_questions(g["questions"][:2], g["word2idx"], out=buf).data_ptr() == buf.data_ptr()

@@ -129,6 +129,23 @@ def pad_on_device(ragged: Dict[str, torch.Tensor], device, pad_to: Optional[int]
     return res
 
 
+def tokenize_questions(questions: Sequence[str], word2idx: Dict[str, int], max_length: int = 14, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Question strings -> int32 token ids [B, max_length] for QuestionFrontEnd.forward.  dataset.py:63-77 (Dictionary.tokenize
+    with add_word=False: lower-case, drop ',' and '?', split "'s" off, whitespace split, unknown words -> ntoken - 1, the least
+    frequent word standing in for UNK) followed by dataset.py:250-263 (cut to max_length, pad AT THE BACK with padding_idx =
+    ntoken)."""
+    ntoken = len(word2idx)
+    B = len(questions)
+    t = out[:B] if out is not None else torch.empty(B, max_length, dtype=torch.int32)
+    a = t.numpy()
+    a[...] = ntoken
+    for i, q in enumerate(questions):
+        words = q.lower().replace(',', '').replace('?', '').replace("'s", " 's").split()
+        ids = [word2idx.get(w, ntoken - 1) for w in words][:max_length]
+        a[i, :len(ids)] = ids
+    return t
+
+
 def targets_from_answers(labels, scores, num_answers: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """dataset.py:314-318: soft-score targets [B, num_answers]; a later duplicate label overwrites an earlier one
     (np.put_along_axis); entries with labels None stay zero."""
