@@ -228,3 +228,48 @@ def test_committed_fixture_is_what_the_reference_produces_now():
                 np.testing.assert_allclose(again[k], g[k], rtol=1e-12, atol=1e-14, err_msg=k)
             else:
                 assert np.array_equal(again[k], g[k]), k
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/model"), reason="reference tree only exists in the build container")
+def test_random_configurations_against_the_reference_executed_live():
+    """Beyond the committed cases: random small configurations (widths, heads, K, nongt_dim, directions, label bias, residual,
+    adaptive padding, init-like or trained-like weights) are run through the reference's own files in a subprocess and through
+    the oracle here; logits, loss, q-mask, dq and every weight gradient must agree."""
+    import json
+    import subprocess
+    import tempfile
+    root = os.path.dirname(HERE)
+    rng = np.random.default_rng(20261018)
+    cases = {}
+    for i in range(6):
+        H = int(rng.choice([1, 2, 4]))
+        kw = dict(v_dim=int(rng.choice([32, 48, 16 * H])), q_dim=int(rng.choice([16, 24])), rel_dim=16 * H, num_heads=H,
+                  nongt_dim=int(rng.choice([3, 5, 8, 20])), num_answers=int(rng.integers(12, 40)), dir_num=int(rng.choice([1, 2])),
+                  label_bias=bool(rng.integers(0, 2)), residual=bool(rng.integers(0, 2)))
+        cases[f"rand{i}"] = (kw, int(rng.integers(1, 4)), int(rng.integers(2, 12)), bool(rng.integers(0, 2)), bool(rng.integers(0, 2)), 1)
+    code = ("import sys, json, numpy as np; sys.path.insert(0, %r)\n"
+            "from oracle import make_golden_ref as m\n"
+            "cases = json.loads(sys.argv[1]); mods = m._import_reference()\n"
+            "for name, c in cases.items():\n"
+            "    m.CASES[name] = (c[0], c[1], c[2], c[3], c[4], c[5])\n"
+            "    out = m.run_case(name, mods, save=False)\n"
+            "    np.savez(sys.argv[2] + '/' + name + '.npz', **out)\n") % root
+    with tempfile.TemporaryDirectory() as tmp:
+        r = subprocess.run([sys.executable, "-c", code, json.dumps(cases), tmp], capture_output=True, text=True, cwd=root, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        for name, (kw, B, N, adaptive, tl, _) in cases.items():
+            g = np.load(os.path.join(tmp, name + ".npz"))
+            cfg = HotPathConfig(**kw)
+            inp = syn.make_inputs(cfg, B, N, seed=1000, adaptive=adaptive)
+            named = syn.unflatten(cfg, syn.make_params(cfg, seed=7, trained_like=tl).astype(np.float64))
+            loss, grads, dq_att, dq_last, out = ot.loss_and_grads(named, cfg, inp)
+            np.testing.assert_allclose(out["logits"], g["logits"], rtol=1e-9, atol=1e-12, err_msg=name)
+            np.testing.assert_allclose(loss, float(g["loss"]), rtol=1e-11, err_msg=name)
+            np.testing.assert_allclose(dq_att, g["dq_att"], rtol=1e-8, atol=1e-13, err_msg=name)
+            np.testing.assert_allclose(dq_last, g["dq_last"], rtol=1e-8, atol=1e-13, err_msg=name)
+            f64 = lambda a: a.astype(np.float64)
+            a = onp.forward(named, cfg, f64(inp["features"]), inp["boxes"], f64(inp["q_att"]), f64(inp["q_last"]), f64(inp["target"]))
+            np.testing.assert_array_equal(a["mask"], g["mask"], err_msg=name)
+            for i, e in enumerate(param_layout(cfg)[0]):
+                np.testing.assert_allclose(grads[e.name], g["grad.full/" + e.name], rtol=0,
+                                           atol=1e-9 * max(np.abs(grads[e.name]).max(), 1e-12) + 1e-14, err_msg=f"{name} {e.name}")
