@@ -93,3 +93,56 @@ def test_input_validation():
     if not torch.cuda.is_available():
         with pytest.raises(RegatError):
             QuestionFrontEnd(40, 10, 24)                                 # no CUDA, no emulation handed in: refuses
+
+
+def _dp_worker(rank, world, port, out):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    n_token, E, H, T, Bg = 40, 10, 24, 14, 6
+    front = olm.make_params(n_token, E, H, "c", seed=11)
+    tok = olm.make_tokens(Bg, n_token, T, seed=21)
+    rng = np.random.default_rng(5)
+    dqa, dql = rng.standard_normal((Bg, H)).astype(np.float32), rng.standard_normal((Bg, H)).astype(np.float32)
+    Bl = Bg // world
+    sl = slice(rank * Bl, (rank + 1) * Bl)
+    fe = QuestionFrontEnd(n_token, E, H, op="c", seq_len=T, max_batch=Bl, emb2_trainable=True, device="cpu", group=dist.group.WORLD,
+                          _ops=HostOps())
+    fe.load_named(front)
+    q_att, q_last = fe.forward(torch.tensor(tok[sl], dtype=torch.int32))
+    fe.backward(torch.tensor(dqa[sl]), torch.tensor(dql[sl]))
+    fe.allreduce_grads()
+    out[rank] = (q_att.numpy().copy(), q_last.numpy().copy(), {k: v.numpy().copy() for k, v in fe.named(fe.grads).items()})
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_front_end_reproduces_the_global_batch():
+    """SURVEY 8e for the front-end: its softmax runs over the batch axis (language_model.py:163-167), so sharding needs an
+    exchange -- the ranks gather each other's [B_local, T] logits (and dW rows in the backward pass).  Two gloo ranks on halves
+    of a batch of 6 must give the single-process oracle's q_att / q_last rows and, after summing over ranks, its gradients."""
+    import torch.multiprocessing as mp
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dp_worker, args=(2, 29523, out), nprocs=2, join=True)
+    n_token, E, H, T, Bg = 40, 10, 24, 14, 6
+    front = olm.make_params(n_token, E, H, "c", seed=11)
+    tok = olm.make_tokens(Bg, n_token, T, seed=21)
+    rng = np.random.default_rng(5)
+    dqa, dql = rng.standard_normal((Bg, H)).astype(np.float32), rng.standard_normal((Bg, H)).astype(np.float32)
+    q, grads = _oracle(front, tok, n_token, "c", dqa, dql, None)
+    for r in range(2):
+        sl = slice(r * 3, (r + 1) * 3)
+        np.testing.assert_allclose(out[r][0], q["q_att"].detach().numpy()[sl], rtol=2e-5, atol=2e-6)
+        np.testing.assert_allclose(out[r][1], q["q_last"].detach().numpy()[sl], rtol=2e-5, atol=2e-6)
+        for name, g in out[r][2].items():
+            if name == "q_att.linear2/bias":
+                assert np.abs(g).max() < 1e-5          # softmax-shift direction: exactly zero in real arithmetic, rounding noise here
+                continue
+            scale = max(np.abs(grads[name]).max(), 1e-6)
+            assert np.abs(g - grads[name]).max() < 5e-5 * scale + 1e-7, (r, name)
+    # and it matters: a rank that normalised over its own half only would be far off
+    p = {k: torch.tensor(np.asarray(v, dtype=np.float64)) for k, v in front.items()}
+    local_only = olm.forward(p, tok[:3], n_token, "c")["q_att"].numpy()
+    assert np.abs(local_only - q["q_att"].detach().numpy()[:3]).max() > 1e-2

@@ -12,6 +12,11 @@ runs over the BATCH axis and its [T,B] result is raw-reshaped to [B,1,T] (:163-1
 on the other questions of the batch, and batch 1 is refused.  The reference runs the GRU twice per step on the same input
 (rel_graph_net.py:44,57); the second run reproduces the first bit for bit, so it is computed once here.
 
+Data parallel (group given): the batch-axis softmax is the front-end's one real exchange step.  Every rank gathers the
+[B_local, T] attention logits of all ranks (14 floats per question), normalises over the GLOBAL batch and reads its own rows
+of the raw-reshaped weight matrix; backward gathers the dW rows the same way.  With equal shards this reproduces the
+reference's single-process numbers; weight gradients are then summed over ranks (allreduce_grads) like the hot path's.
+
 Status: first correct path, one launch sequence per call (about 3T + 12 launches forward); not tuned.
 """
 import ctypes as C
@@ -45,7 +50,7 @@ def question_layout(n_token, emb_dim, num_hid, op="c"):
 
 class QuestionFrontEnd:
     def __init__(self, n_token, emb_dim, num_hid, op="c", seq_len=14, max_batch=256, emb2_trainable=False, device="cuda:0",
-                 grad_clip=0.25, beta1=0.9, beta2=0.999, eps=1e-8, _ops=None):
+                 grad_clip=0.25, beta1=0.9, beta2=0.999, eps=1e-8, group=None, _ops=None):
         self.n_token, self.E, self.H, self.op, self.T, self.max_batch = n_token, emb_dim, num_hid, op, seq_len, max_batch
         self.Ein = emb_dim * (2 if "c" in op else 1)
         self.emb2_trainable = bool(emb2_trainable and "c" in op)
@@ -57,13 +62,19 @@ class QuestionFrontEnd:
         else:
             self.L = _ops                                   # tests only: a host emulation of the entry points (dry run of the sequencing)
         self.device = torch.device(device)
+        self.group, self.world, self.rank = group, 1, 0
+        if group is not None:
+            import torch.distributed as dist
+            self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.entries, total = question_layout(n_token, emb_dim, num_hid, op)
         f = lambda n: torch.zeros(int(n), dtype=torch.float32, device=self.device)
         self.params, self.grads, self.adamax_m, self.adamax_u = f(total), f(total), f(total), f(total)
         B, T, H, Ein = max_batch, seq_len, num_hid, self.Ein
         self._X, self._XI, self._HI = f(B * T * Ein), f(B * T * 3 * H), f(T * B * 3 * H)
         self._Z, self._R, self._C, self._HP = f(T * B * H), f(T * B * H), f(T * B * H), f(T * B * H)
-        self._SEQ, self._A1, self._LOG, self._P = f(B * T * H), f(B * T * H), f(B * T), f(B * T)
+        self._SEQ, self._A1, self._LOG, self._P = f(B * T * H), f(B * T * H), f(B * T), f(self.world * B * T)
+        if self.world > 1:                                  # global-batch copies of the attention logits and of their gradients
+            self._LOG_G, self._DW_G, self._DLOG_G = f(self.world * B * T), f(self.world * B * T), f(self.world * B * T)
         self._ZERO = f(B * H)
         self._DSEQ, self._DW, self._DLOG, self._DA1 = f(B * T * H), f(B * T), f(B * T), f(B * T * H)
         self._DXI, self._DHI, self._DX = f(B * T * 3 * H), f(T * B * 3 * H), f(B * T * Ein)
@@ -135,9 +146,16 @@ class QuestionFrontEnd:
         self._gemm(0, 0, B * T, H, H, seq, H, v1, H, ptr(self._A1), H, alpha=sc + 8, bias=self._p("q_att.linear1/bias"))
         ck(L.regat_q_tanh_fwd(ptr(self._A1), B * T * H, st))
         self._gemm(0, 0, B * T, 1, H, ptr(self._A1), H, v2, 1, ptr(self._LOG), 1, alpha=sc + 12, bias=self._p("q_att.linear2/bias"))
-        ck(L.regat_q_batch_softmax_fwd(ptr(self._LOG), B, T, ptr(self._P), st))
+        log_ptr, Bg, roff = ptr(self._LOG), B, 0
+        if self.world > 1:                                  # language_model.py:163-165 normalises over the whole batch
+            import torch.distributed as dist
+            Bg, roff = B * self.world, 4 * self.rank * B * T
+            dist.all_gather_into_tensor(self._LOG_G[:Bg * T], self._LOG[:B * T], group=self.group)
+            log_ptr = ptr(self._LOG_G)
+        self._Bg, self._roff = Bg, roff
+        ck(L.regat_q_batch_softmax_fwd(log_ptr, Bg, T, ptr(self._P), st))
         q_att = torch.empty(B, H, dtype=torch.float32, device=self.device)
-        ck(L.regat_q_pool_fwd(ptr(self._P), seq, B, T, H, ptr(q_att), st))
+        ck(L.regat_q_pool_fwd(ptr(self._P) + roff, seq, B, T, H, ptr(q_att), st))
         q_last = self._SEQ[:B * T * H].view(B, T, H)[:, T - 1].contiguous()         # language_model.py:120 output[:, -1]
         return q_att, q_last
 
@@ -156,12 +174,19 @@ class QuestionFrontEnd:
         self._scal[4:6].zero_()
         sc, seq, ones = ptr(self._scal), ptr(self._SEQ), ptr(self._ONES)
         v1, v2 = self._p("q_att.linear1/v"), self._p("q_att.linear2/v")
-        ck(L.regat_q_pool_bwd(ptr(self._P), seq, ptr(dq_att), ptr(dq_last), B, T, H, ptr(self._DSEQ), ptr(self._DW), st))
-        ck(L.regat_q_batch_softmax_bwd(ptr(self._P), ptr(self._DW), B, T, ptr(self._DLOG), st))
+        Bg, roff = self._Bg, self._roff
+        ck(L.regat_q_pool_bwd(ptr(self._P) + roff, seq, ptr(dq_att), ptr(dq_last), B, T, H, ptr(self._DSEQ), ptr(self._DW), st))
+        dw_ptr, dlog = ptr(self._DW), ptr(self._DLOG)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(self._DW_G[:Bg * T], self._DW[:B * T], group=self.group)
+            dw_ptr, dlog = ptr(self._DW_G), ptr(self._DLOG_G)
+        ck(L.regat_q_batch_softmax_bwd(ptr(self._P), dw_ptr, Bg, T, dlog, st))
+        dlog += roff                                        # this rank's rows of the global dlogits
         # linear2 (H -> 1): G2 = a1^T dlogits, bias gradient, da1 = dlogits (alpha2 v2)^T
-        self._gemm(1, 0, H, 1, B * T, ptr(self._A1), H, ptr(self._DLOG), 1, ptr(self._G2), 1)
-        self._gemm(0, 0, 1, 1, B * T, ones, B * T, ptr(self._DLOG), 1, g("q_att.linear2/bias"), 1)
-        self._gemm(0, 1, B * T, H, 1, ptr(self._DLOG), 1, v2, 1, ptr(self._DA1), H, alpha=sc + 12)
+        self._gemm(1, 0, H, 1, B * T, ptr(self._A1), H, dlog, 1, ptr(self._G2), 1)
+        self._gemm(0, 0, 1, 1, B * T, ones, B * T, dlog, 1, g("q_att.linear2/bias"), 1)
+        self._gemm(0, 1, B * T, H, 1, dlog, 1, v2, 1, ptr(self._DA1), H, alpha=sc + 12)
         ck(L.regat_q_tanh_bwd(ptr(self._DA1), ptr(self._A1), B * T * H, st))
         # linear1 (H -> H): G1 = seq^T da1, bias gradient, dseq += da1 (alpha1 v1)^T
         self._gemm(1, 0, H, H, B * T, seq, H, ptr(self._DA1), H, ptr(self._G1), H)
@@ -190,6 +215,13 @@ class QuestionFrontEnd:
         self._gemm(0, 1, B * T, Ein, 3 * H, ptr(self._DXI), 3 * H, Wk, 3 * H, ptr(self._DX), Ein)
         demb2 = g("w_emb.emb_/emb_") if self.emb2_trainable else None
         ck(L.regat_q_embed_bwd(ptr(self._tok), B * T, self.n_token, E, Ein, ptr(self._DX), g("w_emb.emb/emb"), demb2, st))
+
+    def allreduce_grads(self):
+        """Data parallel: sum the front-end's weight gradients over the ranks (the hot path hands over dq_att / dq_last already
+        scaled by 1/R when its loss is the mean over the global batch)."""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grads, group=self.group)
 
     # ---- train.py:112-113 for the front-end's variables
     def update(self, lr, step=None):
