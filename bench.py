@@ -5,21 +5,28 @@ synthetic 2048-d region features, random-init weights of the reference architect
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--dtype bf16|fp32] [--impl ours|reference]
 
-N > 1 is launched by torchrun (one rank per GPU, NCCL): data parallel, batch sharded by image, one gradient
-all-reduce per step (weak scaling: 256 graphs per GPU).  Rank 0 prints ONE JSON line.
-  value     : whole-job graphs/s with inputs resident in HBM (CUDA events, max over ranks)
-  e2e       : same metric through the public host-buffer API: pinned-host -> device copies of every step's inputs and a
-              device -> host read of every step's loss inside the timed region (copies double-buffered on a side stream)
-  roofline  : the dominant kernel (tcgen05 bf16 GEMM of the v2out projection, 9216x1024x2048) timed alone with CUDA
-              events on rotating operands larger than L2, against the MEASURED cuBLAS bf16 peak
-              (traffic = DRAM bytes of that launch from the ncu capture recorded in profiles/roofline_traffic.json)
-  roofline_attention : the fused geometry + graph-attention forward kernel timed alone against the measured HBM copy peak
-  cpu_baseline : the reference-formulation CPU restatement (oracle/, torch-CPU fp32, all host cores) on a bounded sample
-N > 1: gradients are reduced in place over NVSwitch multicast by csrc/dp_exchange.cu (REGAT_DP_COMM=nccl for NCCL,
-REGAT_DP_WIRE=bf16 for the staged bf16 wire format), overlapped with the backward pass in 4 ranges.
+N > 1 is launched by torchrun (one rank per GPU): data parallel, batch sharded by image, every gradient range reduced in
+place over NVSwitch multicast by csrc/dp_exchange.cu from inside the engine (weak scaling: 256 graphs per GPU).  A step --
+forward, backward, exchange, clip + Adamax, re-derived bf16 kernels -- is ONE CUDA-graph replay; nothing runs eagerly between
+replays.  Rank 0 prints ONE JSON line:
+  value        whole-job graphs/s with inputs resident in HBM (CUDA events, max over ranks), K steps
+  sustained    the same step back to back for >= 3 s (clock sampler running), against the sustained bf16 peak
+  e2e          same metric through the public host-buffer API: pinned-host -> device copies of every step's inputs and a
+               device -> host read of every step's loss inside the timed region (copies double-buffered on a copy stream)
+  e2e_host_bf16  same with the host feature store kept in bf16 (changes the host storage contract; not the headline)
+  workloads    short legs of BASELINE.json configs[2] (adaptive K=10..100, train) and configs[4] (bf16 eval, K=100, 128/GPU)
+               with their own roofline fraction; the adaptive leg's e2e ships only the real rows (ragged) and pads on the device
+  roofline     dominant kernel (tcgen05 bf16 GEMM of the v2out projection) timed alone on rotating operands larger than L2,
+               plus the GEMM class inside the real step (events around every dense product) and the whole-step fraction
+  roofline_attention   the fused geometry + graph-attention forward kernel timed alone against the measured HBM copy peak
+  dp_check     N > 1: the shipped exchange against NCCL on the same gradients, replica bit-identity, and the N-rank step
+               against one GPU on the concatenated batch; a mismatch makes the run exit non-zero
+  cpu_baseline the reference-formulation CPU restatement (oracle/, torch-CPU fp32, all host cores): the FULL 256-graph step,
+               2 warm-ups, best of 5, plus BASELINE.json configs[0] (forward, batch 4, K=36)
 --impl reference runs only that CPU arm (TensorFlow is not installable in this image).
 """
 import argparse
+import ctypes as C
 import json
 import os
 import statistics
@@ -33,10 +40,11 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 METRIC = "graphs/sec fwd+bwd (K=36, batch 256)"
-TRAIN_MFLOP = {"train36": 1734.0, "adaptive100": 3828.7, "eval100": 1416.0}   # SURVEY 8d per-graph algorithmic MFLOP
+# SURVEY 8d per-graph algorithmic MFLOP, cheapest equivalent formulation (train = fwd + bwd; eval = fwd only, N=100, M=20)
+ALG_MFLOP = {"train36": 1734.0, "adaptive100": 3828.7, "eval100": 1416.0}
 UNIT = "graphs/s"
-TRAIN_MFLOP_PER_GRAPH = 1734.0      # SURVEY 8d, N=36, nongt=20, cheapest equivalent formulation
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+ORDER = ("features", "boxes", "q_att", "q_last", "target")
 
 
 def workload_name(workload, B, N):
@@ -60,17 +68,19 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during a timed region (B200_PROFILING.md clocks line)."""
+    """nvidia-smi clocks / throttle reasons while timed regions run (B200_PROFILING.md clocks line).  One process for the
+    whole bench, 50 ms period; `mark()` returns the number of samples so far so a leg can be cut out of the stream."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.proc, self.rows = index, None, []
+        self.index, self.proc, self.rows, self.t0 = index, None, [], None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu=timestamp,{self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t0 = time.time()
         except OSError:
             self.proc = None
 
@@ -85,43 +95,398 @@ class ClockSampler:
             out, _ = self.proc.communicate()
         for line in out.splitlines():
             f = [x.strip() for x in line.split(",")]
-            if len(f) >= 7:
+            if len(f) >= 8:
                 self.rows.append(f)
         self.proc = None
 
-    def summary(self):
-        if not self.rows:
+    @staticmethod
+    def _ts(s):
+        # "2026/10/18 16:24:01.123"
+        try:
+            d, t = s.split(" ")
+            hh, mm, ss = t.split(":")
+            return int(hh) * 3600 + int(mm) * 60 + float(ss)
+        except Exception:       # noqa: BLE001
+            return None
+
+    def summary(self, window=None):
+        """window = (t_start, t_end) in time.time() seconds: only samples inside it (local wall clock of nvidia-smi's stamps)."""
+        rows = self.rows
+        if window is not None:
+            lo = time.localtime(window[0]); hi = time.localtime(window[1])
+            a = lo.tm_hour * 3600 + lo.tm_min * 60 + lo.tm_sec + (window[0] % 1.0)
+            b = hi.tm_hour * 3600 + hi.tm_min * 60 + hi.tm_sec + (window[1] % 1.0)
+            rows = [r for r in rows if (self._ts(r[0]) is not None and a <= self._ts(r[0]) <= b)]
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         num = lambda s: float(s) if s.replace(".", "", 1).isdigit() else None
-        sm = [num(r[0]) for r in self.rows if num(r[0]) is not None]
+        sm = [num(r[1]) for r in rows if num(r[1]) is not None]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": num(self.rows[0][1]),
-                "power_w_max": max((num(r[2]) or 0.0) for r in self.rows), "reasons": reasons, "samples": len(self.rows)}
+        reasons = [n for i, n in enumerate(names) if any(r[4 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": num(rows[0][2]),
+                "power_w_max": max((num(r[3]) or 0.0) for r in rows), "reasons": reasons, "samples": len(rows)}
+
+
+def cpu_legs(args, cfg, steps, warmup, budget_s):
+    """CPU arm shared by --impl reference and the cpu_baseline key: the FULL batch, no extrapolation."""
+    from oracle.cpu_step import time_cpu_forward, time_cpu_train_full
+    from tf_vqa_regat_b200 import synthetic as syn
+    gps, sec, threads, n, w = time_cpu_train_full(cfg, syn.make_inputs, syn.make_params, syn.unflatten, args.batch, args.rois,
+                                                  steps=steps, warmup=warmup, budget_s=budget_s)
+    fgps, fsec, _ = time_cpu_forward(cfg, syn.make_inputs, syn.make_params, syn.unflatten, 4, 36, steps=5, warmup=2)
+    sample = (f"the whole step on all {args.batch} graphs (K={args.rois}, full widths, fp32): host NumPy position embedding, "
+              f"reference-formulation forward (materialised pos_emb, grouped conv), autograd, per-tensor clip + Adamax over 19.0M "
+              f"parameters; torch-CPU, {threads} threads; {w} warm-ups, best of {n}")
+    base = {"value": gps, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": sec * 1e3, "sample": sample,
+            "steps_timed": n, "warmups": w,
+            "forward_b4": {"value": fgps, "unit": UNIT, "ms": fsec * 1e3, "config": "BASELINE.json configs[0]: forward, batch 4, K=36 fixed, "
+                           "fp32 CPU (reference formulation), best of 5 after 2 warm-ups"}}
+    return base
 
 
 def run_reference(args):
-    """The reference arm: its own CPU path (restated, TF absent) on all host cores, bounded sample per step."""
+    """The reference arm: its own CPU path (restated, TF absent) on all host cores -- the full 256-graph step per timed step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle.cpu_step import time_cpu_train
-    from tf_vqa_regat_b200 import synthetic as syn
     from tf_vqa_regat_b200.config import HotPathConfig
     cfg = HotPathConfig()
-    steps = max(1, min(args.steps, 5))
-    gps, sec, threads, n = time_cpu_train(cfg, syn.make_inputs, syn.make_params, syn.unflatten, args.cpu_sample, args.rois,
-                                          full_batch=args.batch, steps=steps, warmup=1, budget_s=120.0)
-    sample = (f"fwd+bwd timed on {args.cpu_sample} of the {args.batch} graphs of one step (K={args.rois}, full widths, fp32) and scaled "
-              f"to {args.batch}, plus one full clip+Adamax over all 19.0M parameters")
-    line = {"impl": "reference", "metric": METRIC, "value": gps, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
-            "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+    cap = 8
+    steps = max(1, min(args.steps, cap))
+    warm = max(1, min(args.warmup, 2))
+    base = cpu_legs(args, cfg, steps, warm, budget_s=150.0)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": base["steps_timed"],
+            "warmup": base["warmups"], "steps_cap": cap, "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name("train36", args.batch, args.rois), "parallelism": "cpu", "global_batch": args.batch,
-                       "note": "CPU arm: each step is a bounded sample of the workload (see cpu_baseline.sample), scaled to the batch"},
-            "cpu_baseline": {"value": gps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": gps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                       "note": "CPU arm: every timed step is the full batch (no sampling); value = best step; a CPU step takes "
+                               "seconds, so --steps is capped at steps_cap"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def pin_numa_local(dev_index):
+    """Bind this process to the CPUs of the NUMA node the GPU hangs off, so that the pinned host buffers allocated next are
+    first-touched on that node (at N > 1 every rank then feeds its GPU from its own socket's DRAM).  Returns a description."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(dev_index)
+        bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"numa_node": None}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cpus_bound": len(allowed)}
+    except Exception as ex:      # noqa: BLE001  (best effort: containers often hide /sys)
+        return {"numa_node": None, "note": f"{type(ex).__name__}"[:60]}
+
+
+class Leg:
+    """One workload on this rank: engine (+ data-parallel trainer), two alternating synthetic batches pinned on the host and
+    resident on the device, the captured graphs, and the timed loops."""
+
+    def __init__(self, args, workload, dev, rank, world, cfg):
+        import torch
+        from tf_vqa_regat_b200 import synthetic as syn
+        from tf_vqa_regat_b200.dp import DataParallelTrainer
+        from tf_vqa_regat_b200.engine import HotPathEngine
+        self.torch, self.args, self.workload, self.dev, self.rank, self.world, self.cfg = torch, args, workload, dev, rank, world, cfg
+        self.adaptive = workload != "train36"
+        self.eval_only = workload == "eval100"
+        self.B = 128 if self.eval_only else args.batch
+        self.N = 100 if self.adaptive else args.rois
+        B, N = self.B, self.N
+        self.eng = HotPathEngine(cfg, B, N, dtype=args.dtype, device=dev, training=not self.eval_only)
+        self.eng.load_params(syn.make_params(cfg, seed=7, trained_like=True))     # same weights on every rank
+        self.raw = [syn.make_inputs(cfg, B, N, seed=1001 + 17 * rank + i + (100 if self.adaptive else 0), adaptive=self.adaptive) for i in range(2)]
+        self.host = [{k: torch.from_numpy(r[k]).pin_memory() for k in ORDER} for r in self.raw]
+        self.devb = [{k: h[k].to(dev) for k in ORDER} for h in self.host]
+        self.h2d_bytes = sum(self.host[0][k].numel() * 4 for k in ORDER)
+        self.stream = torch.cuda.Stream(dev)
+        self.trainer = DataParallelTrainer(self.eng, overlap=False, comm_dtype="fp32") if (world > 1 and not self.eval_only) else None
+        if self.trainer:
+            self.trainer.broadcast_params(0)
+            if not self.trainer.fused and rank == 0:
+                print("[bench] fused in-place exchange unavailable on this system: eager steps with the callback-free exchange", flush=True)
+        self.logits = torch.empty(B, cfg.num_answers, device=dev) if self.eval_only else None
+        self.graphs, self.launches = {}, 0
+        if not self.eval_only:
+            self.eng.set_lr(args.lr)
+            self.eng.set_step(0)
+        self._build()
+
+    # ---- one step on the device-resident batch `slot`
+    def _eager(self, slot):
+        b, eng = self.devb[slot], self.eng
+        if self.eval_only:
+            eng.lib.regat_engine_forward(eng._h, self.B, self.N, b["features"].data_ptr(), b["boxes"].data_ptr(), b["q_att"].data_ptr(),
+                                         b["q_last"].data_ptr(), self.logits.data_ptr(), None, self.torch.cuda.current_stream().cuda_stream)
+        elif self.trainer is not None and not self.trainer.fused:
+            self.trainer.step(*[b[k] for k in ORDER], self.args.lr)
+        else:
+            eng.train_step_dev(*[b[k] for k in ORDER])
+
+    def _build(self):
+        torch, eng = self.torch, self.eng
+        with torch.cuda.stream(self.stream):
+            if self.eval_only:
+                for slot in range(2):
+                    self._eager(slot)
+            else:
+                for slot in range(2):       # warm without touching the parameters: tensor maps, shared-memory attributes, streams
+                    b = self.devb[slot]
+                    eng.fwd_bwd(*[b[k] for k in ORDER])
+            torch.cuda.synchronize()
+            fused_ok = self.trainer is None or self.trainer.fused
+            if not self.args.no_graph and fused_ok:
+                for slot in range(2):
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=self.stream):
+                        self._eager(slot)
+                    self.graphs[slot] = g
+                self.launches = eng.last_launches()
+            else:
+                self._eager(0)
+                self.launches = eng.last_launches()
+        torch.cuda.synchronize()
+
+    def step(self, slot):
+        if self.graphs:
+            self.graphs[slot].replay()
+        else:
+            self._eager(slot)
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        with torch.cuda.stream(self.stream):
+            e0.record(self.stream)
+            for i in range(steps):
+                fn(i)
+            e1.record(self.stream)
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms], device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    def resident(self, steps, warmup):
+        with self.torch.cuda.stream(self.stream):
+            for i in range(warmup):
+                self.step(i & 1)
+        ms = self.timed(lambda i: self.step(i & 1), steps)
+        return ms / steps, self.world * self.B * steps / (ms * 1e-3)
+
+    # ---- end to end: pinned host inputs -> device every step, loss -> host every step
+    def e2e(self, steps, mode="fp32"):
+        """mode: "fp32" (the reference's host contract: fp32 features), "bf16" (host feature store in bf16, widened on the device),
+        "ragged" (adaptive batches: only the real rows cross the link, regat_pad_ragged writes the zero padding in HBM)."""
+        torch, eng, dev, args = self.torch, self.eng, self.dev, self.args
+        from tf_vqa_regat_b200 import _lib
+        copy_stream = torch.cuda.Stream(dev)
+        ready = [torch.cuda.Event() for _ in range(2)]
+        done = [torch.cuda.Event() for _ in range(2)]
+        loss_host = torch.zeros(2, 2).pin_memory()
+        small = [k for k in ORDER if k not in ("features", "boxes")]
+        bytes_in = self.h2d_bytes
+        if mode == "bf16":
+            host16 = [self.host[s]["features"].to(torch.bfloat16).pin_memory() for s in range(2)]
+            stage16 = [torch.empty(host16[s].shape, dtype=torch.bfloat16, device=dev) for s in range(2)]
+            nfeat = host16[0].numel()
+            bytes_in = self.h2d_bytes - 2 * nfeat
+        elif mode == "ragged":
+            packs = []
+            for s in range(2):
+                n = self.raw[s]["n_obj"].astype(np.int64)
+                off = np.zeros(self.B + 1, dtype=np.int32); off[1:] = np.cumsum(n)
+                rows_f = np.concatenate([self.raw[s]["features"][b, :n[b]] for b in range(self.B)], 0)
+                rows_b = np.concatenate([self.raw[s]["boxes"][b, :n[b]] for b in range(self.B)], 0)
+                packs.append({"features": torch.from_numpy(np.ascontiguousarray(rows_f)).pin_memory(),
+                              "boxes": torch.from_numpy(np.ascontiguousarray(rows_b)).pin_memory(),
+                              "offsets": torch.from_numpy(off).pin_memory(), "T": int(off[-1])})
+            maxT = max(p["T"] for p in packs)
+            dpack = [{"features": torch.empty(maxT, self.cfg.v_dim, device=dev), "boxes": torch.empty(maxT, 4, device=dev),
+                      "offsets": torch.empty(self.B + 1, dtype=torch.int32, device=dev)} for _ in range(2)]
+            bytes_in = int(statistics.mean(p["T"] * (self.cfg.v_dim + 4) * 4 + (self.B + 1) * 4 for p in packs)
+                           + sum(self.host[0][k].numel() * 4 for k in small))
+        l = _lib.lib()
+
+        def prefetch(i):
+            slot = i & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(done[slot])                 # the step that last used this slot has finished
+                cs = copy_stream.cuda_stream
+                if mode == "bf16":
+                    stage16[slot].copy_(host16[slot], non_blocking=True)
+                    _lib.check(l.regat_cast(_lib.BF16, _lib.F32, stage16[slot].data_ptr(), self.devb[slot]["features"].data_ptr(), nfeat, cs))
+                    self.devb[slot]["boxes"].copy_(self.host[slot]["boxes"], non_blocking=True)
+                elif mode == "ragged":
+                    p, d = packs[slot], dpack[slot]
+                    T = p["T"]
+                    d["features"][:T].copy_(p["features"], non_blocking=True)
+                    d["boxes"][:T].copy_(p["boxes"], non_blocking=True)
+                    d["offsets"].copy_(p["offsets"], non_blocking=True)
+                    _lib.check(l.regat_pad_ragged(self.B, self.N, self.cfg.v_dim, T, d["features"].data_ptr(), d["offsets"].data_ptr(),
+                                                  self.devb[slot]["features"].data_ptr(), None, cs))
+                    _lib.check(l.regat_pad_ragged(self.B, self.N, 4, T, d["boxes"].data_ptr(), d["offsets"].data_ptr(),
+                                                  self.devb[slot]["boxes"].data_ptr(), None, cs))
+                else:
+                    self.devb[slot]["features"].copy_(self.host[slot]["features"], non_blocking=True)
+                    self.devb[slot]["boxes"].copy_(self.host[slot]["boxes"], non_blocking=True)
+                for k in small:
+                    self.devb[slot][k].copy_(self.host[slot][k], non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        def e2e_step(i):
+            slot = i & 1
+            if i + 1 < steps + 1:
+                prefetch(i + 1)
+            self.stream.wait_event(ready[slot])
+            self.step(slot)
+            loss_host[slot].copy_(eng._loss if not self.eval_only else self.logits[0, :2], non_blocking=True)    # device -> host read of the result
+            done[slot].record(self.stream)
+            if i > 0:
+                done[slot ^ 1].synchronize()                       # host really consumes the previous step's loss
+                _ = float(loss_host[slot ^ 1][0])
+
+        with torch.cuda.stream(self.stream):
+            done[0].record(self.stream); done[1].record(self.stream)
+        torch.cuda.synchronize()
+        prefetch(0)
+        ms = self.timed(e2e_step, steps)
+        # restore the device-resident fp32 inputs (the bf16 / ragged legs rewrite them with identical or rounded values)
+        if mode == "bf16":
+            for s in range(2):
+                self.devb[s]["features"].copy_(self.host[s]["features"])
+        torch.cuda.synchronize()
+        out = {"value": self.world * self.B * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(bytes_in), "d2h_bytes_per_step": 8,
+               "ms_per_step": ms / steps, "h2d_gbs_per_gpu": bytes_in / (ms / steps * 1e-3) / 1e9}
+        return out
+
+    def close(self):
+        self.graphs.clear()
+        if self.trainer is not None and hasattr(self.eng, "set_dp"):
+            self.eng.set_dp(None, 0, None, 0, 1)
+        self.trainer = None
+
+
+def dp_check(leg, cfg, rank, world, dev):
+    """world > 1, before anything is timed.  (1) the shipped in-place exchange (regat_dp_allreduce_f32, multimem over NVSwitch)
+    against NCCL's fp32 all-reduce of the SAME local gradients; (2) bit-identity of the exchanged buffer across replicas;
+    (3) one optimizer step of the R-rank job (fused exchange inside the engine, as timed) against ONE GPU on the concatenated
+    batch: gradients norm-wise, parameters within what Adamax can move."""
+    import torch
+    import torch.distributed as dist
+    from tf_vqa_regat_b200 import synthetic as syn
+    from tf_vqa_regat_b200.engine import HotPathEngine
+    eng, tr = leg.eng, leg.trainer
+    B, N = leg.B, leg.N
+    per = B // world                                     # the check's global batch is ONE engine batch, sharded R ways
+    glob = syn.make_inputs(cfg, per * world, N, seed=4242)
+    shard = {k: torch.from_numpy(np.ascontiguousarray(glob[k][rank * per:(rank + 1) * per])).to(dev) for k in ORDER}
+    out = {"world": world, "graphs_per_rank": per, "backend": tr.backend, "fused": bool(tr.fused), "wire": getattr(tr, "wire", None),
+           "multicast": bool(getattr(tr, "_mc", 0))}
+    params0 = eng.params.clone()
+    # ---- (1) exchange kernel vs NCCL on identical inputs
+    eng.fwd_bwd(*[shard[k] for k in ORDER], grad_scale=1.0 / world)
+    torch.cuda.synchronize()
+    local = eng.grads.clone()
+    via_nccl = local.clone()
+    dist.all_reduce(via_nccl, op=dist.ReduceOp.SUM)
+    tr._allreduce_range(0, eng.grads.numel())            # host-epoch entry point of the same kernels, whole buffer
+    torch.cuda.synchronize()
+    dist.barrier()
+    mine = eng.grads
+    worst_rel, worst_abs = 0.0, 0.0
+    for e in eng.entries:
+        a, b = mine[e.offset:e.offset + e.numel], via_nccl[e.offset:e.offset + e.numel]
+        d = float((a - b).abs().max())
+        worst_abs = max(worst_abs, d)
+        worst_rel = max(worst_rel, d / max(float(b.abs().max()), 1e-30))
+    out["max_abs_diff"], out["max_rel_diff"] = worst_abs, worst_rel
+    # ---- (2) replicas bit-identical after the exchange (64-bit sum and xor-fold of the raw words)
+    words = mine.view(torch.int32).to(torch.int64)
+    sig = torch.stack([words.sum(), (words * torch.arange(1, words.numel() + 1, device=dev) % 1000003).sum()])
+    sigs = [torch.zeros_like(sig) for _ in range(world)]
+    dist.all_gather(sigs, sig)
+    out["replicas_bit_identical"] = bool(all(torch.equal(s, sigs[0]) for s in sigs))
+    # ---- (3) one real step, R ranks (as timed: fused exchange + per-range optimizer) vs one GPU on the concatenated batch
+    lr = 1e-3
+    eng.adamax_m.zero_(); eng.adamax_u.zero_()
+    if tr.fused:
+        eng.set_lr(lr); eng.set_step(0)
+        eng.train_step_dev(*[shard[k] for k in ORDER])
+    else:
+        tr.step_count = 0
+        tr.step(*[shard[k] for k in ORDER], lr)
+    torch.cuda.synchronize()
+    g_dp = eng.grads.clone()
+    p_dp = eng.params.clone()
+    psig = p_dp.view(torch.int32).to(torch.int64).sum().reshape(1)
+    psigs = [torch.zeros_like(psig) for _ in range(world)]
+    dist.all_gather(psigs, psig)
+    out["replica_params_bit_identical"] = bool(all(torch.equal(s, psigs[0]) for s in psigs))
+    if rank == 0:
+        one = HotPathEngine(cfg, per * world, N, dtype=leg.args.dtype, device=dev)
+        one.load_params(params0)
+        full = {k: torch.from_numpy(glob[k]).to(dev) for k in ORDER}
+        one.fwd_bwd(*[full[k] for k in ORDER])
+        torch.cuda.synchronize()
+        g_one = one.grads.clone()
+        one.update(lr, 1)
+        torch.cuda.synchronize()
+        gr, pm, pmean = 0.0, 0.0, 0.0
+        zero_dir = lambda n: ("implicit_relation.bias/" in n or n.endswith(".key/bias") or n in ("joint_emb.linear/bias", "joint_emb.v2attention/bias"))
+        for e in eng.entries:
+            if zero_dir(e.name) or e.kind == "g":
+                continue            # g's slot in the dL/dW_eff buffer is unused; zero directions carry rounding noise only (DESIGN.md)
+            a, b = g_dp[e.offset:e.offset + e.numel], g_one[e.offset:e.offset + e.numel]
+            gr = max(gr, float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30))
+        for e in eng.entries:
+            if zero_dir(e.name):
+                continue
+            d = (p_dp[e.offset:e.offset + e.numel] - one.params[e.offset:e.offset + e.numel]).abs()
+            pm = max(pm, float(d.max())); pmean = max(pmean, float(d.mean()))
+        out["vs_single_gpu_grads_max_rel_diff"] = gr
+        out["vs_single_gpu_params_max_diff"] = pm
+        out["vs_single_gpu_params_max_mean_diff"] = pmean
+        out["lr"] = lr
+        del one
+    # restore the state the timed legs start from
+    eng.load_params(params0)
+    eng.adamax_m.zero_(); eng.adamax_u.zero_()
+    eng.set_lr(leg.args.lr); eng.set_step(0)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ok = out["replicas_bit_identical"] and out["replica_params_bit_identical"] and out["max_rel_diff"] < 1e-5
+    if rank == 0:
+        # shard-wise summation order differs from the one-GPU order (fp32 accumulation of bf16 products): 1e-3 of the tensor's
+        # scale; one Adamax step moves an element by at most lr (sign flips of near-zero gradients move it by up to 2 lr)
+        ok = ok and out["vs_single_gpu_grads_max_rel_diff"] < 2e-3 and out["vs_single_gpu_params_max_diff"] <= 2.0 * lr + 1e-7 \
+            and out["vs_single_gpu_params_max_mean_diff"] < 0.05 * lr
+    out["ok"] = bool(ok)
+    return out
 
 
 def main():
@@ -133,34 +498,22 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=256, help="graphs per GPU per step")
     ap.add_argument("--rois", type=int, default=36)
-    ap.add_argument("--cpu-sample", type=int, default=16, help="graphs per CPU-baseline step")
     ap.add_argument("--workload", default="train36", choices=["train36", "adaptive100", "eval100"],
-                    help="train36 = BASELINE configs[1] (headline); adaptive100 = configs[2] (K=10..100 zero-padded, train); "
-                         "eval100 = configs[4] (forward only, batch 128/GPU, K=100 adaptive)")
+                    help="headline leg: train36 = BASELINE configs[1]; the other two always run as short extra legs (key `workloads`)")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--comm-dtype", default="auto", choices=["auto", "fp32", "bf16"], help="gradient all-reduce precision (auto = engine dtype)")
-    ap.add_argument("--no-overlap", action="store_true", help="data parallel: one all-reduce after the backward pass instead of overlapped buckets")
+    ap.add_argument("--no-extra-legs", action="store_true", help="skip the sustained / adaptive100 / eval100 / e2e_host_bf16 legs")
+    ap.add_argument("--sustained-seconds", type=float, default=3.0)
     ap.add_argument("--lr", type=float, default=9e-4)
-    ap.add_argument("--e2e-host-bf16", action="store_true",
-                    help="extra leg (key e2e_host_bf16): the host keeps the region features in bf16 (what the bf16 engine rounds them to "
-                         "anyway), halving the host->device bytes; not part of the default line")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    if args.workload != "train36":
-        args.rois = 100
-        args.no_cpu_baseline = True
-        if args.workload == "eval100":
-            args.batch = 128
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
     import torch.distributed as dist
-    from tf_vqa_regat_b200 import _lib, synthetic as syn
+    from tf_vqa_regat_b200 import _lib
     from tf_vqa_regat_b200.config import HotPathConfig
-    from tf_vqa_regat_b200.engine import HotPathEngine
-    from tf_vqa_regat_b200.dp import allreduce_flat_
 
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -168,208 +521,75 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = pin_numa_local(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     peaks = load_peaks()
     cfg = HotPathConfig()
-    B, N = args.batch, args.rois
-    adaptive = args.workload != "train36"
-    eval_only = args.workload == "eval100"
-    eng = HotPathEngine(cfg, B, N, dtype=args.dtype, device=dev, training=not eval_only)
-    eng.load_params(syn.make_params(cfg, seed=7, trained_like=True))     # same weights on every rank
-
-    # two distinct synthetic batches per rank, pinned on the host and resident on the device
-    host = [{k: torch.from_numpy(v).pin_memory() for k, v in syn.make_inputs(cfg, B, N, seed=1001 + 17 * rank + i, adaptive=adaptive).items()
-             if k != "n_obj"} for i in range(2)]
-    order = ("features", "boxes", "q_att", "q_last", "target")
-    devb = [{k: h[k].to(dev) for k in order} for h in host]
-    h2d_bytes = sum(host[0][k].numel() * 4 for k in order)
-    main_stream = torch.cuda.Stream(dev)
-    lr = args.lr
-    step_no = [0]
-
-    from tf_vqa_regat_b200.dp import DataParallelTrainer
-    # data parallel: bucketed gradient all-reduce on a side stream, started from inside the backward pass (dp.py)
-    trainer = DataParallelTrainer(eng, overlap=not args.no_overlap, comm_dtype=args.comm_dtype) if (world > 1 and not eval_only) else None
-    if trainer:
-        trainer.broadcast_params(0)
-
-    logits_buf = torch.empty(B, cfg.num_answers, device=dev) if eval_only else None
-
-    def fwd_bwd(slot):
-        b = devb[slot]
-        if eval_only:
-            eng.lib.regat_engine_forward(eng._h, B, N, b["features"].data_ptr(), b["boxes"].data_ptr(), b["q_att"].data_ptr(),
-                                         b["q_last"].data_ptr(), logits_buf.data_ptr(), None, torch.cuda.current_stream().cuda_stream)
-        elif trainer:
-            trainer.fwd_bwd_allreduce(b["features"], b["boxes"], b["q_att"], b["q_last"], b["target"])
-        else:
-            eng.fwd_bwd(b["features"], b["boxes"], b["q_att"], b["q_last"], b["target"], grad_scale=1.0)
-
-    def update():
-        if eval_only:
-            return
-        step_no[0] += 1
-        eng.update(lr, step_no[0])
-
-    graphs = {}
-    launches_per_step = [0]
-    upd_launches = [0]
-
-    def build_graphs():
-        # Adamax's bias correction depends on the step number (a host scalar): the update kernel is re-launched eagerly
-        # with the right lr_t, everything else is replayed from a CUDA graph.
-        with torch.cuda.stream(main_stream):
-            for slot in range(2):
-                fwd_bwd(slot)           # warm: creates tensor maps, sets smem attributes
-            # one real optimizer step before capture: the update leaves the weight-norm statistics of the new parameters behind,
-            # so the captured forward pass is the steady-state one (no separate ||v||^2 pass over the parameters)
-            if not eval_only:
-                update()
-                upd_launches[0] = eng.last_launches()
-            fwd_bwd(0)
-            launches_per_step[0] = eng.last_launches()
-            torch.cuda.synchronize()
-            if not args.no_graph and (world == 1 or eval_only):
-                for slot in range(2):
-                    g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g, stream=main_stream):
-                        fwd_bwd(slot)
-                    graphs[slot] = g
-            elif not args.no_graph and trainer is not None and trainer.overlap:
-                # N>1: compute-only graph segments split at the gradient-ready points, NCCL eagerly in between (dp.GraphedDPStep)
-                from tf_vqa_regat_b200.dp import GraphedDPStep
-                for slot in range(2):
-                    b = devb[slot]
-                    graphs[slot] = GraphedDPStep(trainer, b["features"], b["boxes"], b["q_att"], b["q_last"], b["target"], main_stream)
-        torch.cuda.synchronize()
-
-    def one_step(slot):
-        if graphs:
-            graphs[slot].replay()
-        else:
-            fwd_bwd(slot)
-        update()
-
-    build_graphs()
-    update_launches = upd_launches[0]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        with torch.cuda.stream(main_stream):
-            e0.record(main_stream)
-            for i in range(steps):
-                fn(i)
-            e1.record(main_stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t)
-        return ms
-
-    # ---------------- device-resident timing
-    with torch.cuda.stream(main_stream):
-        for i in range(args.warmup):
-            one_step(i & 1)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms = timed(lambda i: one_step(i & 1), args.steps)
-    value = world * B * args.steps / (ms * 1e-3)
+
+    leg = Leg(args, args.workload, dev, rank, world, cfg)
+    B, N, eng = leg.B, leg.N, leg.eng
+    eval_only = leg.eval_only
+
+    # ---------------- N > 1: prove the exchange before timing anything
+    check = None
+    if world > 1 and leg.trainer is not None:
+        check = dp_check(leg, cfg, rank, world, dev)
+
+    # ---------------- device-resident timing (the headline `value`)
+    t_a = time.time()
+    ms_step, value = leg.resident(args.steps, args.warmup)
+    t_b = time.time()
     loss_end = float(eng._loss[0]) if not eval_only else None
+    clocks = None
 
-    # ---------------- end-to-end timing: pinned host inputs -> device every step, loss -> host every step
-    copy_stream = torch.cuda.Stream(dev)
-    ready = [torch.cuda.Event() for _ in range(2)]
-    done = [torch.cuda.Event() for _ in range(2)]
-    loss_host = torch.zeros(2, 2).pin_memory()
+    # ---------------- sustained leg: the same replay back to back for >= sustained_seconds
+    sustained = None
+    if not args.no_extra_legs and args.sustained_seconds > 0:
+        n_sus = max(args.steps, int(args.sustained_seconds / (ms_step * 1e-3)) + 1)
+        time.sleep(0.5)                                  # the sampler has been running since start-up; leave a visible gap
+        t0 = time.time()
+        ms_sus = leg.timed(lambda i: leg.step(i & 1), n_sus) / n_sus
+        t1 = time.time()
+        sustained = {"steps": n_sus, "seconds": ms_sus * n_sus * 1e-3, "ms_per_step": ms_sus, "value": world * B * 1e3 / ms_sus, "unit": UNIT,
+                     "window": (t0, t1)}
 
-    def prefetch(i):
-        slot = i & 1
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(done[slot])                 # the step that last used this slot has finished
-            for k in order:
-                devb[slot][k].copy_(host[slot][k], non_blocking=True)
-            ready[slot].record(copy_stream)
-
-    def e2e_step(i):
-        slot = i & 1
-        if i + 1 < args.steps + 1:
-            prefetch(i + 1)
-        main_stream.wait_event(ready[slot])
-        one_step(slot)
-        loss_host[slot].copy_(eng._loss if not eval_only else logits_buf[0, :2], non_blocking=True)    # device -> host read of the step's result
-        done[slot].record(main_stream)
-        if i > 0:
-            done[slot ^ 1].synchronize()                       # host really consumes the previous step's loss
-            _ = float(loss_host[slot ^ 1][0])
-
-    with torch.cuda.stream(main_stream):
-        done[0].record(main_stream); done[1].record(main_stream)
-    torch.cuda.synchronize()
-    prefetch(0)
-    ms_e2e = timed(e2e_step, args.steps)
-    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
-    # ---------------- optional: same end-to-end loop with a bf16 host feature store (opt-in, bf16 engine only)
+    # ---------------- end to end
+    e2e = leg.e2e(args.steps, "fp32")
     e2e_bf16 = None
-    if args.e2e_host_bf16 and args.dtype == "bf16":
-        # The bf16 engine rounds the fp32 features to bf16 as its first step (round-to-nearest-even); a host store that keeps them
-        # in bf16 (rounded once, when the dataset is loaded) therefore gives bit-identical results and moves half the bytes.  On the
-        # device regat_cast widens them back into the fp32 input buffer on the COPY stream, so the engine's interface is unchanged.
-        host16 = [host[s]["features"].to(torch.bfloat16).pin_memory() for s in range(2)]
-        stage16 = [torch.empty(host16[s].shape, dtype=torch.bfloat16, device=dev) for s in range(2)]
-        nfeat = host16[0].numel()
+    if not args.no_extra_legs and args.dtype == "bf16":
+        e2e_bf16 = leg.e2e(args.steps, "bf16")
+        e2e_bf16["note"] = ("host feature store in bf16 (the value the bf16 engine rounds the fp32 features to as its first step, so results are "
+                            "bit-identical), widened on the device by regat_cast on the copy stream; changes the host storage contract of the "
+                            "reference's API (fp32 features), hence not the headline")
 
-        def prefetch16(i):
-            slot = i & 1
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(done[slot])
-                stage16[slot].copy_(host16[slot], non_blocking=True)
-                _lib.check(eng.lib.regat_cast(_lib.BF16, _lib.F32, stage16[slot].data_ptr(), devb[slot]["features"].data_ptr(), nfeat,
-                                              copy_stream.cuda_stream))
-                for k in order[1:]:
-                    devb[slot][k].copy_(host[slot][k], non_blocking=True)
-                ready[slot].record(copy_stream)
-
-        def e2e_step16(i):
-            slot = i & 1
-            if i + 1 < args.steps + 1:
-                prefetch16(i + 1)
-            main_stream.wait_event(ready[slot])
-            one_step(slot)
-            loss_host[slot].copy_(eng._loss if not eval_only else logits_buf[0, :2], non_blocking=True)
-            done[slot].record(main_stream)
-            if i > 0:
-                done[slot ^ 1].synchronize()
-                _ = float(loss_host[slot ^ 1][0])
-
-        with torch.cuda.stream(main_stream):
-            done[0].record(main_stream); done[1].record(main_stream)
-        torch.cuda.synchronize()
-        prefetch16(0)
-        ms16 = timed(e2e_step16, args.steps)
-        e2e_bf16 = {"value": world * B * args.steps / (ms16 * 1e-3), "unit": UNIT, "ms_per_step": ms16 / args.steps,
-                    "h2d_bytes_per_step": h2d_bytes - 2 * nfeat, "d2h_bytes_per_step": 8,
-                    "note": "host feature store in bf16 (the value the bf16 engine rounds to), widened on the device by regat_cast on the copy stream"}
-    if rank == 0:
-        sampler.stop()
+    # ---------------- GEMM class inside the real step (rank 0): events around every dense product of one eager step
+    gemm_class = None
+    if rank == 0 and not eval_only and (leg.trainer is None or leg.trainer.fused) and world == 1:
+        try:
+            with torch.cuda.stream(leg.stream):
+                leg._eager(0)
+                recs = eng.profile_gemms(lambda: leg._eager(1))
+            fl = sum(2.0 * m * n * k for m, n, k, _ in recs)
+            tms = sum(t for *_, t in recs)
+            small = [(m, n, k, t) for m, n, k, t in recs if min(m, n) <= 256 or k <= 256]
+            gemm_class = {"launches": len(recs), "sum_ms": tms, "tflops": fl / (tms * 1e-3) / 1e12 if tms > 0 else None,
+                          "share_of_step": tms / ms_step, "batch_sized_launches": len(small), "batch_sized_ms": sum(t for *_, t in small),
+                          "note": "eager step, CUDA events around each dense product on its own stream (side-stream work overlaps as in the "
+                                  "real step; eager launch gaps are outside the brackets); share = sum / graph-replayed ms_per_step"}
+        except Exception as ex:      # noqa: BLE001
+            gemm_class = {"error": f"{type(ex).__name__}: {ex}"[:200]}
 
     # ---------------- roofline probe of the dominant kernel (rank 0): v2out GEMM, tcgen05, alone, rotating operands > L2
     roofline, attn_probe = None, None
     if rank == 0:
-        import ctypes as C
         l = _lib.lib()
         st = torch.cuda.current_stream().cuda_stream
-        M_, N_, K_ = B * N, cfg.rel_dim, cfg.v_dim
+        M_, N_, K_ = 256 * 36, cfg.rel_dim, cfg.v_dim
         code = _lib.BF16 if args.dtype == "bf16" else _lib.F32
         tdt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
         nrot = 6
@@ -397,19 +617,28 @@ def main():
         if os.path.exists(tp):
             with open(tp) as f:
                 traffic = json.load(f).get("gemm_v2out_dram_bytes_per_launch")
-        roofline = {"bound": "tensor", "kernel": f"gemm_tc_kernel<256,4,2> v2out {M_}x{N_}x{K_} bf16 (+alpha,bias,relu)",
+        roofline = {"bound": "tensor", "kernel": f"gemm_tc_kernel v2out {M_}x{N_}x{K_} bf16 (+alpha,bias,relu)",
                     "achieved": tflops, "peak": peak, "unit": "TFLOP/s", "frac": (tflops / peak) if peak else None,
-                    "peak_source": peaks["_source"] + " (burst, kernel timed alone)", "launch_ms": t_ms, "traffic": traffic}
+                    "peak_source": peaks["_source"] + " (burst, kernel timed alone)", "launch_ms": t_ms, "traffic": traffic,
+                    "note": "single-kernel probe (quality of the dominant kernel); the path's fraction is step_tensor_frac"}
         del As, Cs
-        # whole-step view against the sustained peak (SURVEY 8d algorithmic FLOPs)
-        step_tflops = TRAIN_MFLOP[args.workload] * 1e6 * (value / world) / 1e12
-        roofline["step_tensor_frac_of_sustained"] = step_tflops / peaks["bf16_tflops_sustained"]
+        # whole-step view: the K-step leg is a burst measurement (tens of ms) -> burst peak; the sustained leg -> sustained peak
+        step_tflops = ALG_MFLOP[args.workload] * 1e6 * (value / world) / 1e12
         roofline["step_algorithmic_tflops_per_gpu"] = step_tflops
+        roofline["step_tensor_frac"] = step_tflops / peaks["bf16_tflops"]
+        roofline["step_tensor_frac_peak"] = "burst (bf16_tflops): the timed region lasts tens of milliseconds"
+        if sustained is not None:
+            sus_tflops = ALG_MFLOP[args.workload] * 1e6 * (sustained["value"] / world) / 1e12
+            roofline["sustained_step_tensor_frac"] = sus_tflops / peaks["bf16_tflops_sustained"]
+            roofline["sustained_step_algorithmic_tflops_per_gpu"] = sus_tflops
+        if gemm_class is not None and "tflops" in gemm_class:
+            roofline["gemm_class_tflops"] = gemm_class["tflops"]
+            roofline["gemm_class_share"] = gemm_class["share_of_step"]
+            roofline["gemm_class"] = gemm_class
 
     # ---------------- second roofline probe (rank 0): the fused geometry-attention forward kernel, HBM-bound by construction
     if rank == 0 and args.dtype == "bf16":
         try:
-            import ctypes as C
             l = _lib.lib()
             ents = {e.name: e for e in eng.entries}
             pre = "v_relation.implicit_relation.neighbor_net."
@@ -418,12 +647,13 @@ def main():
             named = eng.named()
             alphas = torch.stack([named[pre + f"{d}.pair_pos_fc/g"].reshape(()) / named[pre + f"{d}.pair_pos_fc/v"].norm()
                                   for d in range(cfg.dir_num)]).float().contiguous()
+
             def buf(name):
                 ptr_ = C.c_void_p()
                 _lib.check(l.regat_engine_buffer(eng._h, name.encode(), C.byref(ptr_)))
                 return ptr_.value
             training = not eval_only
-            bx = devb[0]["boxes"]
+            bx = leg.devb[0]["boxes"]
             wd = _lib.wave_divisors(cfg.pos_emb_dim)
             st = torch.cuda.current_stream().cuda_stream
             call = lambda: _lib.check(l.regat_geoattn_fwd(
@@ -450,42 +680,94 @@ def main():
             attn_probe = {"bound": "hbm", "kernel": "geoattn_fwd_bf16_kernel (fused box geometry + graph attention forward)",
                           "achieved": alg / (t_ms * 1e-3) / 1e9, "achieved_incl_saved_p_and_bias": (alg + saved) / (t_ms * 1e-3) / 1e9,
                           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg / (t_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
-                          "launch_ms": t_ms, "algorithmic_bytes_per_launch": alg, "saved_for_backward_bytes": saved,
-                          "note": "issue-bound today (33.6 M warp instructions per launch, profiles/r01_ncu_final_metrics.csv), not bandwidth-bound"}
+                          "launch_ms": t_ms, "algorithmic_bytes_per_launch": alg, "saved_for_backward_bytes": saved}
         except Exception as ex:          # the probe must never take the headline number down with it
             attn_probe = {"error": f"{type(ex).__name__}: {ex}"[:200]}
 
+    # ---------------- BASELINE.json configs[2] and configs[4] as short legs at this N
+    workloads = {}
+    if not args.no_extra_legs:
+        leg.close()
+        for wl in ("adaptive100", "eval100"):
+            if wl == args.workload:
+                continue
+            try:
+                lg = Leg(args, wl, dev, rank, world, cfg)
+                ws, wu = 10, 3
+                ms_w, val_w = lg.resident(ws, wu)
+                tfl = ALG_MFLOP[wl] * 1e6 * (val_w / world) / 1e12
+                entry = {"value": val_w, "unit": UNIT, "ms_per_step": ms_w, "steps": ws, "warmup": wu, "batch_per_gpu": lg.B, "K": lg.N,
+                         "config": workload_name(wl, lg.B, lg.N), "algorithmic_tflops_per_gpu": tfl,
+                         "step_tensor_frac": tfl / peaks["bf16_tflops"], "cuda_graph": bool(lg.graphs),
+                         "e2e": lg.e2e(ws, "fp32")}
+                if wl == "adaptive100":
+                    entry["e2e_ragged"] = lg.e2e(ws, "ragged")
+                    entry["e2e_ragged"]["note"] = ("only the real rows cross the host link (packed back to back + B+1 offsets); regat_pad_ragged "
+                                                   "writes the zero post-padding in HBM (dataset.py:329-346 on the device)")
+                workloads[wl] = entry
+                lg.close()
+                del lg
+            except Exception as ex:      # noqa: BLE001  (an extra leg must never take the headline down)
+                workloads[wl] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+
     # ---------------- CPU baseline (rank 0, N=1 only)
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.cpu_step import time_cpu_train
-        gps, sec, threads, n = time_cpu_train(cfg, syn.make_inputs, syn.make_params, syn.unflatten, args.cpu_sample, N,
-                                              full_batch=B, steps=3, warmup=1, budget_s=45.0)
-        cpu_baseline = {"value": gps, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": sec * 1e3,
-                        "sample": f"fp32 torch-CPU reference-formulation restatement (host NumPy position embedding, materialised "
-                                  f"pos_emb, grouped conv): fwd+bwd timed on {args.cpu_sample} graphs (K={N}, full widths) scaled to "
-                                  f"{B}, plus one clip+Adamax over 19.0M parameters; best of {n}"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "train36":
+        cpu_baseline = cpu_legs(args, cfg, steps=5, warmup=2, budget_s=90.0)
 
     if rank == 0:
-        line = {"metric": METRIC if args.workload == "train36" else f"graphs/sec ({args.workload})", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        sampler.stop()
+        # headline clocks = the sustained leg's window (seconds of back-to-back steps: every sample is under load); the K-step leg
+        # lasts tens of milliseconds, shorter than nvidia-smi's sampling period, so its own window usually holds 0-1 samples
+        whole = sampler.summary()
+        if sustained is not None:
+            clocks = sampler.summary(sustained.pop("window"))
+            clocks["window"] = "sustained leg"
+        else:
+            clocks = dict(whole)
+            clocks["window"] = "whole run"
+        if clocks["samples"] == 0:
+            clocks = dict(whole); clocks["window"] = "whole run"
+        clocks["timed_leg"] = sampler.summary((t_a - 0.05, t_b + 0.05))
+        clocks["whole_run"] = whole
+    elif sustained is not None:
+        sustained.pop("window")
+
+    rc = 0
+    if rank == 0:
+        tr = leg.trainer
+        line = {"metric": METRIC if args.workload == "train36" else f"graphs/sec ({args.workload})", "value": value, "unit": UNIT,
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.dtype if args.dtype == "bf16" else "f32", "data": "synthetic",
                 "config": {"workload": workload_name(args.workload, B, N),
-                           "parallelism": f"dp{world}", "global_batch": B * world, "cuda_graph": bool(graphs),
-                           "allreduce": (None if world == 1 else (("4 ranges overlapped with backward" if trainer.overlap else "single, after backward") + ", " + ("own multimem kernel in place on the symmetric gradient buffer, wire " + trainer.wire if getattr(trainer, "backend", "") == "symm"
-                                                                         else "NCCL, wire " + trainer.comm_dtype))),
+                           "parallelism": f"dp{world}", "global_batch": B * world, "cuda_graph": bool(leg.graphs),
+                           "step": "one CUDA-graph replay = forward + backward + (exchange) + clip + Adamax + re-derived bf16 kernels",
+                           "allreduce": (None if world == 1 else check and ("in-place " + str(check["wire"]) + " exchange inside the engine, 4 ranges "
+                                         "behind the backward pass, multicast=" + str(check["multicast"]) + ", backend " + str(check["backend"]))),
+                           "numa": numa,
                            "l2": "per-step working set ~0.8 GB (activations + 4x76 MB parameter/optimizer state) >> 126 MB L2; "
                                  "two alternating input batches; no explicit flush"},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 8,
-                        "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": (launches_per_step[0] + update_launches) * args.steps,
-                "launches_per_step": launches_per_step[0] + update_launches,
-                "roofline": roofline, "roofline_attention": attn_probe, "cpu_baseline": cpu_baseline, "clocks": sampler.summary(), "final_loss": loss_end}
+                "e2e": e2e, "gpu_launches": leg.launches * args.steps, "launches_per_step": leg.launches,
+                "sustained": sustained, "roofline": roofline, "roofline_attention": attn_probe, "workloads": workloads,
+                "cpu_baseline": cpu_baseline, "clocks": clocks, "final_loss": loss_end}
         if e2e_bf16 is not None:
             line["e2e_host_bf16"] = e2e_bf16
+        if check is not None:
+            line["dp_check"] = check
+            if not check["ok"]:
+                rc = 3
         print(json.dumps(line), flush=True)
     if world > 1:
+        flag = torch.tensor([rc], device=dev)
+        dist.broadcast(flag, 0)
+        rc = int(flag)
         dist.destroy_process_group()
+    if rc:
+        sys.exit(rc)
 
 
 if __name__ == "__main__":

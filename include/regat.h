@@ -232,6 +232,11 @@ REGAT_API int regat_dp_reduce_bcast(const uint64_t* stage_ptrs, uint64_t multica
  * (reduce/broadcast kernel + a one-block completion wait); no staging, no pack / unpack passes.  Multiples of 4 elements. */
 REGAT_API int regat_dp_allreduce_f32(const uint64_t* grad_ptrs, uint64_t multicast_ptr, const uint64_t* flag_ptrs,
                   int rank, int world, int64_t offset, int64_t numel, uint32_t epoch, int blocks, regat_stream_t stream);
+/* Same, with the call counter in device memory (*epoch_dev, zero-initialised, ordinary device memory of this rank): each call
+ * uses *epoch_dev + 1 and stores it back when the range is complete, so the launch takes no host scalar that changes from
+ * call to call and can sit inside a replayed CUDA graph.  Uses its own flag buffer (do not share one with the host-epoch calls). */
+REGAT_API int regat_dp_allreduce_f32_dev(const uint64_t* grad_ptrs, uint64_t multicast_ptr, const uint64_t* flag_ptrs,
+                  int rank, int world, int64_t offset, int64_t numel, uint32_t* epoch_dev, int blocks, regat_stream_t stream);
 REGAT_API int regat_dp_wait_unpack(const void* stage_local, float* dst, const uint64_t* flag_ptrs, int rank, int world,
                   int64_t offset, int64_t numel, uint32_t epoch, regat_stream_t stream);
 
@@ -292,20 +297,50 @@ REGAT_API int regat_engine_train_step(regat_engine* e, int B, int N, const float
                             const float* boxes, const float* q_att, const float* q_last,
                             const float* target, float lr, int step, float* loss_out,
                             regat_stream_t stream);
+/* Device-resident optimizer scalars.  regat_engine_train_step_dev runs one whole step (forward, backward, per-tensor clip,
+ * Adamax, train.py:103-113) without any host scalar in a launch: the learning rate and the number of steps taken live in the
+ * workspace (set_lr / set_step write them with a one-thread kernel on `stream`; the step itself increments the counter and
+ * derives lr_t = lr / (1 - beta1^t)).  The call is therefore capturable in ONE CUDA graph and replayable; clip + Adamax of each
+ * gradient range run on an internal stream behind the rest of the backward pass, and everything the next forward pass derives
+ * from the parameters (alpha = g/||v||, bf16 kernels, gathered biases) is rebuilt there too.
+ * regat_engine_update / regat_engine_train_step (host lr, 1-based step) are the same kernels after writing those scalars.
+ * regat_engine_get_step synchronises `stream` (tests / checkpoints only).                                                  */
+REGAT_API int regat_engine_set_lr(regat_engine* e, float lr, regat_stream_t stream);
+REGAT_API int regat_engine_set_step(regat_engine* e, int steps_done, regat_stream_t stream);
+REGAT_API int regat_engine_get_step(regat_engine* e, int* steps_done, float* lr, regat_stream_t stream);
+REGAT_API int regat_engine_train_step_dev(regat_engine* e, int B, int N, const float* features,
+                                const float* boxes, const float* q_att, const float* q_last,
+                                const float* target, float* loss_out, regat_stream_t stream);
+/* Data parallel inside the engine (train.py:111-113 on every replica after the exchange).  The bound grads buffer is
+ * this rank's part of a SYMMETRIC allocation: grad_ptrs[r] / flag_ptrs[r] are rank r's mappings of the gradient buffer and of a
+ * zero-initialised flag buffer of >= 32 uint32 (multicast_ptr: the NVSwitch multicast mapping of the gradient buffer, 0 if
+ * none).  regat_engine_train_step[_dev] then uses grad_scale = 1/world and reduces each gradient range in place
+ * (csrc/dp_exchange.cu) as soon as the backward pass has finished it, before that range's clip + Adamax.  Every rank must
+ * issue the same sequence of steps.  world <= 1 switches it off.                                                            */
+REGAT_API int regat_engine_set_dp(regat_engine* e, const uint64_t* grad_ptrs, uint64_t multicast_ptr,
+                        const uint64_t* flag_ptrs, int rank, int world, int blocks);
+/* Re-derives alpha, the bf16 kernels, the gathered biases and the label constant from the parameter buffer on `stream`, now.
+ * Needed only when the parameters were written from outside AND the next engine work is the replay of an already captured
+ * graph (eager calls do it themselves after regat_engine_params_changed / regat_engine_bind).                               */
+REGAT_API int regat_engine_refresh_weights(regat_engine* e, regat_stream_t stream);
 /* Data parallel: fn(user, offset, numel) is called from inside regat_engine_fwd_bwd (on the calling thread, while the
  * call is still enqueueing) each time a contiguous range of the grads buffer has received its last write on `stream`:
  * first the BUTD + classifier tail, then self_weights + attention layers, then v2out.  The callee typically records an
  * event on `stream` and starts an all-reduce of that range on another stream, overlapping the rest of the backward.  */
 typedef void (*regat_grad_ready_fn)(void* user, int64_t offset, int64_t numel);
 REGAT_API int regat_engine_set_grad_callback(regat_engine* e, regat_grad_ready_fn fn, void* user);
+/* Measurement aid (bench.py's GEMM-class figure): with on != 0 every dense product of the following EAGER engine calls is
+ * bracketed by CUDA timing events; profile_read synchronises the device, returns up to max_records entries -- mnk[3i..3i+2] =
+ * (M, N, K), ms[i] -- in launch order and clears the list.  Never enable it while a CUDA graph is being captured. */
+REGAT_API int regat_engine_profile(regat_engine* e, int on);
+REGAT_API int regat_engine_profile_read(regat_engine* e, int max_records, int32_t* mnk, float* ms, int* count);
 /* Number of kernel launches the last engine call issued (for bench.py's gpu_launches). */
 REGAT_API int regat_engine_last_launches(const regat_engine* e);
-/* Tell the engine that the caller wrote the parameter buffer (checkpoint load, set_weights).  The engine caches what it
- * derives from the parameters -- the per-tensor ||v||^2 partial sums that regat_engine_update leaves behind for the next
- * forward pass, and (between updates) alpha = g/||v|| and the bf16 copies of the effective kernels, so that forward-only
- * callers do not re-derive them on every call; this call drops those caches.  Not needed after regat_engine_bind or
- * regat_engine_update (they invalidate what they must themselves).  A CUDA graph captured from an engine call contains
- * only the work that call needed at capture time: re-capture after changing the parameters from outside. */
+/* Tell the engine that the caller wrote the parameter buffer (checkpoint load, set_weights).  The engine keeps what it
+ * derives from the parameters (per-tensor ||v||^2, alpha = g/||v||, the bf16 copies of the effective kernels, gathered biases)
+ * up to date itself across its own calls -- the optimizer rebuilds them for the tensors it writes -- so nothing is re-derived
+ * per forward pass; this call marks that state stale and the next eager engine call rebuilds it first.  Not needed after
+ * regat_engine_bind.  Before REPLAYING a captured graph after an outside write, call regat_engine_refresh_weights. */
 REGAT_API int regat_engine_params_changed(regat_engine* e);
 /* Copies the configuration the engine was created with. */
 REGAT_API int regat_engine_config(const regat_engine* e, regat_config* cfg);

@@ -67,3 +67,51 @@ def time_cpu_train(cfg, make_inputs, make_params, unflatten, sample_batch, n_roi
         if time.perf_counter() - t_begin > budget_s:
             break
     return full_batch / best, best, tr.threads, n
+
+
+def time_cpu_train_full(cfg, make_inputs, make_params, unflatten, batch, n_rois, steps=5, warmup=2, budget_s=120.0, adaptive=False):
+    """The WHOLE step on `batch` graphs (no sampling, no extrapolation): `warmup` untimed steps, then best of up to `steps`
+    (stops early once `budget_s` of wall clock is spent, but always times at least one).  Returns
+    (graphs_per_s, seconds_per_step, threads, steps_timed, warmups_run)."""
+    tr = CpuTrainer(cfg, make_params(cfg, seed=7, trained_like=True), unflatten)
+    inp = make_inputs(cfg, batch, n_rois, seed=1001, adaptive=adaptive)
+    t_begin = time.perf_counter()
+    w = 0
+    for _ in range(warmup):
+        tr.step(inp)
+        w += 1
+        if time.perf_counter() - t_begin > budget_s / 2:
+            break
+    best, n = None, 0
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        tr.step(inp)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        n += 1
+        if time.perf_counter() - t_begin > budget_s:
+            break
+    return batch / best, best, tr.threads, n, w
+
+
+def time_cpu_forward(cfg, make_inputs, make_params, unflatten, batch, n_rois, steps=5, warmup=2, adaptive=False):
+    """Forward only (host position embedding + reference-formulation forward, no autograd): BASELINE.json configs[0] is this at
+    batch 4, K=36.  Best of `steps` after `warmup`.  Returns (graphs_per_s, seconds, threads)."""
+    tr = CpuTrainer(cfg, make_params(cfg, seed=7, trained_like=True), unflatten)
+    inp = make_inputs(cfg, batch, n_rois, seed=1001, adaptive=adaptive)
+    f, q1, q2, tg = (torch.from_numpy(inp[k]) for k in ("features", "q_att", "q_last", "target"))
+
+    def fwd():
+        pos_emb = pe.prepare_graph_variables("implicit", inp["boxes"], None, None, n_rois, cfg.nongt_dim, cfg.pos_emb_dim, 11, 15)[0]
+        with torch.no_grad():
+            return ot.forward(tr.p, cfg, f, inp["boxes"], q1, q2, tg, pos_emb=torch.from_numpy(pos_emb))["logits"]
+
+    for _ in range(warmup):
+        fwd()
+    best = None
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        fwd()
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return batch / best, best, tr.threads

@@ -1,5 +1,8 @@
-"""Data parallel on real GPUs (needs >= 2 devices: run with `gpurun --gpus 2`): R ranks on shards of the batch with the overlapped
-bucketed NCCL all-reduce reach the same parameters as one GPU on the whole batch."""
+"""Data parallel on real GPUs (needs >= 2 devices: `gpurun --gpus 2 -- python -m pytest tests/test_gpu_dp.py -m gpu`): R ranks on
+shards of the batch, gradients exchanged by every backend the package ships -- the engine-driven in-place exchange of
+csrc/dp_exchange.cu (eager and replayed from ONE CUDA graph per step), the same kernels driven by the Python callbacks with a
+host epoch, without multicast (peer pointers), the staged bf16 wire format, and NCCL -- reach the same parameters as one GPU
+on the whole batch ("N-rank result equals 1-rank result on the concatenated batch")."""
 import os
 
 import numpy as np
@@ -12,39 +15,63 @@ from tf_vqa_regat_b200.config import HotPathConfig
 pytestmark = pytest.mark.gpu
 SMALL = dict(v_dim=192, q_dim=96, rel_dim=256, num_heads=4, nongt_dim=20, num_answers=301)
 
+# name -> (environment, engine dtype, use the one-graph replay)
+MODES = {
+    "fused_f32": (dict(REGAT_DP_COMM="symm"), "fp32", False),
+    "fused_f32_graph": (dict(REGAT_DP_COMM="symm"), "fp32", True),
+    "fused_bf16engine_graph": (dict(REGAT_DP_COMM="symm"), "bf16", True),
+    "fused_no_multicast": (dict(REGAT_DP_COMM="symm", REGAT_DP_MULTICAST="0"), "fp32", True),
+    "callback_symm_f32": (dict(REGAT_DP_COMM="symm", REGAT_DP_FUSED="0"), "fp32", False),
+    "callback_symm_bf16wire": (dict(REGAT_DP_COMM="symm", REGAT_DP_FUSED="0", REGAT_DP_WIRE="bf16"), "fp32", False),
+    "callback_nccl": (dict(REGAT_DP_COMM="nccl"), "fp32", False),
+}
 
-def _worker(rank, world, port, cfg_kw, B, N, steps, lr, out):
+
+def _worker(rank, world, port, cfg_kw, B, N, steps, lr, env, dtype, graph, out):
     import torch.distributed as dist
     from tf_vqa_regat_b200.dp import DataParallelTrainer, shard_batch
     from tf_vqa_regat_b200.engine import HotPathEngine
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    os.environ.update(env)
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     cfg = HotPathConfig(**cfg_kw)
     inp = syn.make_inputs(cfg, B, N, seed=1000, adaptive=True)
-    eng = HotPathEngine(cfg, B // world, N, dtype="fp32", device=f"cuda:{rank}")
+    eng = HotPathEngine(cfg, B // world, N, dtype=dtype, device=f"cuda:{rank}")
     eng.load_params(syn.make_params(cfg, seed=7 + rank, trained_like=True))     # ranks start DIFFERENT: broadcast must fix it
-    tr = DataParallelTrainer(eng, overlap=True)
+    tr = DataParallelTrainer(eng, overlap=True, comm_dtype="fp32" if env.get("REGAT_DP_WIRE") != "bf16" else "bf16")
     tr.broadcast_params(0)
     shard = shard_batch({k: v for k, v in inp.items() if k != "n_obj"}, rank, world)
     dev = {k: torch.tensor(v).cuda() for k, v in shard.items()}
+    args = (dev["features"], dev["boxes"], dev["q_att"], dev["q_last"], dev["target"])
     losses = []
-    for _ in range(steps):
-        o = tr.step(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"], dev["target"], lr)
-        losses.append(float(o["loss"]))
+    if graph:
+        g = tr.capture_step(*args)
+        eng.set_lr(lr); eng.set_step(0)
+        for _ in range(steps):
+            losses.append(float(g.replay()[0]))
+    else:
+        for _ in range(steps):
+            o = tr.step(*args, lr)
+            losses.append(float(o["loss"]))
     torch.cuda.synchronize()
-    out[rank] = (eng.params.cpu().numpy(), losses, tr.overlap)
+    out[rank] = (eng.params.cpu().numpy(), losses, dict(backend=tr.backend, fused=tr.fused, wire=getattr(tr, "wire", None),
+                                                       multicast=bool(getattr(tr, "_mc", 0))))
+    dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
-def test_two_gpus_equal_one_gpu():
+@pytest.mark.parametrize("mode", list(MODES))
+def test_ranks_equal_one_gpu(mode):
     import torch.multiprocessing as mp
     from tf_vqa_regat_b200.engine import HotPathEngine
-    B, N, steps, lr = 8, 36, 2, 1e-3
+    env, dtype, graph = MODES[mode]
+    world = min(torch.cuda.device_count(), int(os.environ.get("REGAT_TEST_WORLD", "2")))
+    B, N, steps, lr = 8, 36, 3, 1e-3
     cfg = HotPathConfig(**SMALL)
     inp = syn.make_inputs(cfg, B, N, seed=1000, adaptive=True)
-    ref = HotPathEngine(cfg, B, N, dtype="fp32", device="cuda:0")
+    ref = HotPathEngine(cfg, B, N, dtype=dtype, device="cuda:0")
     ref.load_params(syn.make_params(cfg, seed=7, trained_like=True))
     dev = {k: torch.tensor(v).cuda() for k, v in inp.items() if k != "n_obj"}
     ref_losses = [float(ref.train_step(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"], dev["target"], lr, s + 1)[0])
@@ -52,20 +79,34 @@ def test_two_gpus_equal_one_gpu():
     p_ref = ref.params.cpu().numpy()
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(2, 29533, SMALL, B, N, steps, lr, out), nprocs=2, join=True)
-    assert out[0][2], "the overlapped bucketed path did not run"
-    assert np.array_equal(out[0][0], out[1][0]), \
-        f"replicas diverged: max |diff| {np.abs(out[0][0] - out[1][0]).max()}"      # post-all-reduce math is deterministic
+    port = 29533 + list(MODES).index(mode)
+    mp.spawn(_worker, args=(world, port, SMALL, B, N, steps, lr, env, dtype, graph, out), nprocs=world, join=True)
+    info = out[0][2]
+    print(f"[dp] {mode}: world {world}, {info}")
+    if mode.startswith("fused"):
+        assert info["fused"] and info["backend"] == "symm", info
+    if mode == "callback_nccl":
+        assert info["backend"] == "nccl"
+    if mode == "fused_no_multicast":
+        assert not info["multicast"]
+    for r in range(1, world):
+        assert np.array_equal(out[0][0], out[r][0]), \
+            f"replicas diverged: max |diff| {np.abs(out[0][0] - out[r][0]).max()}"      # post-exchange math is deterministic
     # rank losses are shard means: their average is the global-batch loss
-    np.testing.assert_allclose(np.mean([out[0][1], out[1][1]], axis=0), ref_losses, rtol=1e-5)
-    # Adamax moves every element by <= lr per step: agreement far inside that (summation order differs across shards).  The
-    # softmax-shift "zero directions" only carry rounding noise, which Adamax normalises to +-lr: excluded.
+    np.testing.assert_allclose(np.mean([out[r][1] for r in range(world)], axis=0), ref_losses, rtol=1e-5 if dtype == "fp32" else 2e-3)
+    # Adamax moves every element by <= lr per step: agreement far inside that (summation order differs across shards; the bf16
+    # wire format rounds the exchanged gradients).  The softmax-shift "zero directions" only carry rounding noise, which Adamax
+    # normalises to +-lr: excluded.
+    loose = dtype == "bf16" or "bf16wire" in mode
     from tf_vqa_regat_b200.config import param_layout
     for e in param_layout(cfg)[0]:
         if "implicit_relation.bias/" in e.name or e.name.endswith(".key/bias") or e.name in ("joint_emb.linear/bias", "joint_emb.v2attention/bias"):
             continue
-        d = np.abs(out[0][0][e.offset:e.offset + e.numel] - p_ref[e.offset:e.offset + e.numel]).max()
-        assert d < 0.05 * steps * lr + 1e-6, (e.name, d)
+        dd = np.abs(out[0][0][e.offset:e.offset + e.numel] - p_ref[e.offset:e.offset + e.numel])
+        if loose:
+            assert dd.max() <= 2.0 * steps * lr + 1e-6 and dd.mean() < 0.1 * steps * lr, (e.name, dd.max(), dd.mean())
+        else:
+            assert dd.max() < 0.05 * steps * lr + 1e-6, (e.name, dd.max())
 
 
 def test_exchange_kernels_single_rank_identity():
@@ -97,6 +138,15 @@ def test_exchange_kernels_single_rank_identity():
     want = ref.clone()
     want[off:off + cnt] = ref[off:off + cnt].bfloat16().float()
     assert torch.equal(g, want)
+    # device-resident call counter (the variant that sits inside a replayed CUDA graph): three calls advance it to 3
+    g2 = torch.randn(n, device="cuda"); ref2 = g2.clone()
+    flags2 = torch.zeros(64, dtype=torch.int32, device="cuda")
+    ctr = torch.zeros(1, dtype=torch.int32, device="cuda")
+    gp2 = (C.c_uint64 * 1)(g2.data_ptr()); fp2 = (C.c_uint64 * 1)(flags2.data_ptr())
+    for _ in range(3):
+        _lib.check(l.regat_dp_allreduce_f32_dev(gp2, 0, fp2, 0, 1, off, cnt, ctr.data_ptr(), 4, st))
+    torch.cuda.synchronize()
+    assert torch.equal(g2, ref2) and int(ctr[0]) == 3 and int(flags2[0]) == 3 and int(flags2[16]) == 3
     # argument errors surface as status codes, not as launches
     assert l.regat_dp_allreduce_f32(gp, 0, fp, 0, 1, 2, cnt, 6, 4, st) == -5          # offset not a multiple of 4
     assert l.regat_dp_allreduce_f32(gp, 0, fp, 1, 1, off, cnt, 6, 4, st) == -1          # rank >= world

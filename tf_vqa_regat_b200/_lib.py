@@ -55,6 +55,7 @@ SIGNATURES = {
     "regat_cast": [i32, i32, vp, vp, i64, vp],
     "regat_dp_reduce_bcast": [vp, C.c_uint64, vp, i32, i32, i64, i64, C.c_uint32, i32, vp],
     "regat_dp_allreduce_f32": [vp, C.c_uint64, vp, i32, i32, i64, i64, C.c_uint32, i32, vp],
+    "regat_dp_allreduce_f32_dev": [vp, C.c_uint64, vp, i32, i32, i64, i64, vp, i32, vp],
     "regat_dp_wait_unpack": [vp, vp, vp, i32, i32, i64, i64, C.c_uint32, vp],
     "regat_concat_visual_question": [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp],
     "regat_butd_prep": [i32, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp],
@@ -69,6 +70,14 @@ SIGNATURES = {
     "regat_engine_fwd_bwd": [vp, i32, i32, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp],
     "regat_engine_update": [vp, f32, i32, vp],
     "regat_engine_train_step": [vp, i32, i32, vp, vp, vp, vp, vp, f32, i32, vp, vp],
+    "regat_engine_set_lr": [vp, f32, vp],
+    "regat_engine_set_step": [vp, i32, vp],
+    "regat_engine_get_step": [vp, C.POINTER(C.c_int), C.POINTER(C.c_float), vp],
+    "regat_engine_train_step_dev": [vp, i32, i32, vp, vp, vp, vp, vp, vp, vp],
+    "regat_engine_set_dp": [vp, vp, C.c_uint64, vp, i32, i32, i32],
+    "regat_engine_refresh_weights": [vp, vp],
+    "regat_engine_profile": [vp, i32],
+    "regat_engine_profile_read": [vp, i32, vp, vp, C.POINTER(C.c_int)],
     "regat_engine_set_grad_callback": [vp, vp, vp],
     "regat_engine_last_launches": [vp],
     "regat_engine_params_changed": [vp],

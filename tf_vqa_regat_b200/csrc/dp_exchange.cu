@@ -141,8 +141,10 @@ __global__ void __launch_bounds__(256) dp_wait_unpack_kernel(const bf16* __restr
 // GPU in each direction at 8 ranks); what it buys is zero extra kernels beside the backward pass and unrounded gradients.
 template <bool MULTICAST>
 __global__ void __launch_bounds__(512) dp_reduce_bcast_f32_kernel(PeerPtrs grads, unsigned char* mc, PeerPtrs flags, int rank, int world,
-                                                                   long long offset, long long numel, unsigned int epoch) {
+                                                                   long long offset, long long numel, unsigned int epoch,
+                                                                   const unsigned int* epoch_dev) {
   __shared__ unsigned int* fl[MAX_RANKS];
+  if (epoch_dev) epoch = *epoch_dev + 1u;      // device-resident call counter (CUDA-graph replay): advanced by dp_wait_kernel
   if ((int)threadIdx.x < world) fl[threadIdx.x] = static_cast<unsigned int*>(flags.p[threadIdx.x]);
   __syncthreads();
   if (blockIdx.x == 0) signal_all(fl, 0, rank, world, epoch);          // the kernels that produced this range have completed
@@ -187,12 +189,14 @@ __global__ void __launch_bounds__(512) dp_reduce_bcast_f32_kernel(PeerPtrs grads
 }
 
 // one block: "my slice is broadcast" to every peer, then wait for every peer's -- after it the whole range is final here
-__global__ void __launch_bounds__(32) dp_wait_kernel(PeerPtrs flags, int rank, int world, unsigned int epoch) {
+__global__ void __launch_bounds__(32) dp_wait_kernel(PeerPtrs flags, int rank, int world, unsigned int epoch, unsigned int* epoch_dev) {
   __shared__ unsigned int* fl[MAX_RANKS];
+  if (epoch_dev) epoch = *epoch_dev + 1u;
   if ((int)threadIdx.x < world) fl[threadIdx.x] = static_cast<unsigned int*>(flags.p[threadIdx.x]);
   __syncthreads();
   signal_all(fl, 1, rank, world, epoch);
   wait_all(fl[rank], 1, world, epoch);
+  if (epoch_dev && threadIdx.x == 0) *epoch_dev = epoch;      // the next exchange on this stream uses epoch + 1
 }
 
 int fill(PeerPtrs& pp, const uint64_t* host_ptrs, int world) {
@@ -237,8 +241,21 @@ extern "C" int regat_dp_wait_unpack(const void* stage_local, float* dst, const u
   return REGAT_OK;
 }
 
+namespace regat {
+int dp_allreduce_f32_impl(const uint64_t* grad_ptrs, uint64_t multicast_ptr, const uint64_t* flag_ptrs, int rank, int world,
+                          int64_t offset, int64_t numel, uint32_t epoch, uint32_t* epoch_dev, int blocks, cudaStream_t stream);
+}
 extern "C" int regat_dp_allreduce_f32(const uint64_t* grad_ptrs, uint64_t multicast_ptr, const uint64_t* flag_ptrs, int rank, int world,
                                       int64_t offset, int64_t numel, uint32_t epoch, int blocks, regat_stream_t stream) {
+  return dp_allreduce_f32_impl(grad_ptrs, multicast_ptr, flag_ptrs, rank, world, offset, numel, epoch, nullptr, blocks, (cudaStream_t)stream);
+}
+extern "C" int regat_dp_allreduce_f32_dev(const uint64_t* grad_ptrs, uint64_t multicast_ptr, const uint64_t* flag_ptrs, int rank, int world,
+                                          int64_t offset, int64_t numel, uint32_t* epoch_dev, int blocks, regat_stream_t stream) {
+  REGAT_REQUIRE(epoch_dev, REGAT_ERR_ARG, "dp_allreduce_f32_dev: null epoch counter");
+  return dp_allreduce_f32_impl(grad_ptrs, multicast_ptr, flag_ptrs, rank, world, offset, numel, 0, epoch_dev, blocks, (cudaStream_t)stream);
+}
+int regat::dp_allreduce_f32_impl(const uint64_t* grad_ptrs, uint64_t multicast_ptr, const uint64_t* flag_ptrs, int rank, int world,
+                                 int64_t offset, int64_t numel, uint32_t epoch, uint32_t* epoch_dev, int blocks, cudaStream_t stream) {
   REGAT_REQUIRE(grad_ptrs && flag_ptrs, REGAT_ERR_ARG, "dp_allreduce_f32: null pointer table");
   REGAT_REQUIRE(world >= 1 && world <= MAX_RANKS && rank >= 0 && rank < world, REGAT_ERR_ARG, "dp_allreduce_f32: bad rank %d / world %d", rank, world);
   REGAT_REQUIRE(offset % 4 == 0 && numel % 4 == 0 && numel >= 0, REGAT_ERR_ALIGN, "dp_allreduce_f32: offset and count must be multiples of 4 elements");
@@ -251,11 +268,11 @@ extern "C" int regat_dp_allreduce_f32(const uint64_t* grad_ptrs, uint64_t multic
   const int nb = blocks > 0 ? blocks : 32;
   cudaStream_t s = (cudaStream_t)stream;
   if (multicast_ptr)
-    dp_reduce_bcast_f32_kernel<true><<<nb, 512, 0, s>>>(gp, reinterpret_cast<unsigned char*>(multicast_ptr), fl, rank, world, offset, numel, epoch);
+    dp_reduce_bcast_f32_kernel<true><<<nb, 512, 0, s>>>(gp, reinterpret_cast<unsigned char*>(multicast_ptr), fl, rank, world, offset, numel, epoch, epoch_dev);
   else
-    dp_reduce_bcast_f32_kernel<false><<<nb, 512, 0, s>>>(gp, nullptr, fl, rank, world, offset, numel, epoch);
+    dp_reduce_bcast_f32_kernel<false><<<nb, 512, 0, s>>>(gp, nullptr, fl, rank, world, offset, numel, epoch, epoch_dev);
   REGAT_POST_LAUNCH();
-  dp_wait_kernel<<<1, 32, 0, s>>>(fl, rank, world, epoch);
+  dp_wait_kernel<<<1, 32, 0, s>>>(fl, rank, world, epoch, epoch_dev);
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }

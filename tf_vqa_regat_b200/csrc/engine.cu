@@ -30,6 +30,23 @@ struct Layer {
 
 struct Entry { long long off, numel; int layer, kind; };
 
+// A contiguous interval of layers whose gradients become final together in the backward pass: the unit of the gradient exchange
+// (data parallel) and of the optimizer, which both run on the `opt` stream behind the rest of the backward pass.
+struct OptRange {
+  int l_first = 0, l_last = -1;       // layers [l_first, l_last]; empty if l_last < l_first
+  long long lo = 0, hi = 0;           // element interval of the flat buffers
+  TensorList tl_opt, tl_v, tl_gather; // this range's slices of the engine-wide lists (chunk numbering local to the range)
+  int chunks_opt = 0, chunks_v = 0;
+  int cbase = 0;                      // first per-chunk slot in `partials`
+  int tbase = 0;                      // first per-tensor slot in `stats` / `counters`
+  int vbase = 0;                      // first chunk of the range's kernels in the engine-wide ||v||^2 partials (`vpart`)
+  int label_local = -1;               // index of the label FC inside tl_v, or -1
+};
+constexpr int N_RANGES = 4;           // announcement order: BUTD + classifier, attention layers, v2out, self_weights + label FC
+
+int dp_allreduce_f32_impl(const uint64_t* grad_ptrs, uint64_t multicast_ptr, const uint64_t* flag_ptrs, int rank, int world,
+                          int64_t offset, int64_t numel, uint32_t epoch, uint32_t* epoch_dev, int blocks, cudaStream_t stream);
+
 }  // namespace regat
 
 using namespace regat;
@@ -53,7 +70,7 @@ struct regat_engine {
   long long ws_need = 0;
   // workspace carve (byte offsets)
   struct Buf { long long off = -1; };
-  Buf lowp, gbias, sumsq, alpha, invn, scal, stats, partials, vpart, counters, featT, qattT, qlastT, v0, mask, qs, s, strunc, Qb, KVb, v1, P, GB, gate, uqe,
+  Buf lowp, gbias, sumsq, alpha, invn, scal, hyp, stats, partials, vpart, counters, featT, qattT, qlastT, v0, mask, qs, s, strunc, Qb, KVb, v1, P, GB, gate, uqe,
       uw, cb, weff, att, pooled, pv, joint, hid, logits, dlogits, dhid, djoint, dpv, duqe, dpooled, dv1, dweff, dcb, duw,
       dQb, dKVb, ds, dstrunc, dsq, dwc3;
   int a_pad = 0;
@@ -63,12 +80,24 @@ struct regat_engine {
   TensorList tl_gather;
   int last_launches = 0;
   int grads_final = 0;
-  int sumsq_fresh = 0;             // the per-chunk ||v||^2 partials were written by the last update and params are untouched since
-  int lowp_fresh = 0;              // alpha / bf16 weight copies / gathered biases match params (forward-only callers reuse them)
+  // Everything derived from the parameters (per-chunk ||v||^2, alpha = g/||v||, the bf16 copies of alpha*v, the gathered biases,
+  // the label constant) matches `params`.  This is an invariant of the DEVICE state that every engine call restores before it
+  // returns: the optimizer re-derives the state of the tensors it has just written, and a call that finds the flag down (after
+  // bind / params_changed) derives everything first.  A captured CUDA graph therefore never depends on a host-side shortcut.
+  int weights_ready = 0;
+  OptRange rng[N_RANGES];
   // small independent work (BUTD question branch, tiny weight gradients) runs on a side stream, forked / joined with events
   cudaStream_t side = nullptr;
-  static constexpr int NEV = 10;
+  cudaStream_t opt = nullptr;      // gradient exchange + optimizer, range by range, behind the rest of the backward pass
+  static constexpr int NEV = 18;
   cudaEvent_t ev[NEV] = {};
+  // data parallel (regat_engine_set_dp): the grads buffer is a symmetric allocation, reduced in place by csrc/dp_exchange.cu
+  int dp_world = 1, dp_rank = 0, dp_blocks = 32;
+  uint64_t dp_grad_ptrs[16] = {}, dp_flag_ptrs[16] = {}, dp_mc = 0;
+  // measurement aid (regat_engine_profile): CUDA events around every dense product of an EAGER call
+  struct GemmRec { int M, N, K; cudaEvent_t a, b; };
+  std::vector<GemmRec> prof;
+  int prof_on = 0;
   regat_grad_ready_fn grad_cb = nullptr;   // data parallel: called when a range of `grads` is final on the stream
   void* grad_cb_user = nullptr;
   template <typename T> T* at(const Buf& b) const { return reinterpret_cast<T*>(ws + b.off); }
@@ -160,6 +189,7 @@ long long carve(regat_engine* e) {
   const long long nl = (long long)e->layers.size();
   take(e->sumsq, nl * 4); take(e->alpha, nl * 4); take(e->invn, nl * 4);
   take(e->scal, 64 * 4);                       // [0]=label const c, [1]=dc, [2]=loss, [3]=score
+  take(e->hyp, 64 * 4);                        // Hyper {lr, step, lr_t} at [0], the exchange's call counter (uint32) at [8]
   take(e->stats, 2 * MAX_TENSORS * 4);
   take(e->partials, 2 * 8192 * 4);             // per-chunk partial sums of the optimizer reductions
   take(e->counters, MAX_TENSORS * 4);          // per-tensor "chunks finished" counters of the optimizer reduction (self-resetting)
@@ -220,7 +250,7 @@ void build_lists(regat_engine* e) {
   auto add = [&](int l, long long dst) {
     const Layer& L = e->layers[l];
     if (L.b_off < 0) return;
-    tg.off[tg.n] = L.b_off; tg.numel[tg.n] = L.cols; tg.off_lowp[tg.n] = dst; ++tg.n;
+    tg.off[tg.n] = L.b_off; tg.numel[tg.n] = L.cols; tg.off_lowp[tg.n] = dst; tg.layer[tg.n] = l; ++tg.n;
   };
   for (int d = 0; d < dirs; ++d) {
     add(e->l_q[d], e->bq_off + d * D);
@@ -229,11 +259,51 @@ void build_lists(regat_engine* e) {
   }
   add(e->l_qa, e->buqe_off);
   add(e->l_qe, e->buqe_off + Hd);
+
+  // ---- ranges, in the order the backward pass finishes them
+  const int nl = (int)e->layers.size();
+  e->rng[0].l_first = e->l_va; e->rng[0].l_last = e->l_c3;
+  e->rng[1].l_first = e->l_pos[0]; e->rng[1].l_last = e->l_out[dirs - 1];
+  if (e->l_v2out >= 0) { e->rng[2].l_first = e->l_v2out; e->rng[2].l_last = e->l_v2out; }
+  e->rng[3].l_first = e->l_self; e->rng[3].l_last = e->l_label;
+  int cbase = 0, tbase = 0;
+  for (int r = 0; r < N_RANGES; ++r) {
+    OptRange& R = e->rng[r];
+    memset(&R.tl_opt, 0, sizeof(TensorList)); memset(&R.tl_v, 0, sizeof(TensorList)); memset(&R.tl_gather, 0, sizeof(TensorList));
+    if (R.l_last < R.l_first) continue;
+    R.lo = e->layers[R.l_first].v_off;
+    R.hi = R.l_last + 1 < nl ? e->layers[R.l_last + 1].v_off : e->param_elems;
+    auto copy = [](TensorList& d, const TensorList& src, int j) {
+      const int i = d.n++;
+      d.off[i] = src.off[j]; d.numel[i] = src.numel[j]; d.g_off[i] = src.g_off[j]; d.off_lowp[i] = src.off_lowp[j];
+      d.ld_lowp[i] = src.ld_lowp[j]; d.cols[i] = src.cols[j]; d.kind[i] = src.kind[j]; d.layer[i] = src.layer[j];
+      return i;
+    };
+    for (int j = 0; j < to.n; ++j)
+      if (to.layer[j] >= R.l_first && to.layer[j] <= R.l_last) {
+        const int i = copy(R.tl_opt, to, j);
+        R.tl_opt.vchunk_start[i] = to.vchunk_start[j];        // engine-wide ||v||^2 chunk numbering
+      }
+    for (int j = 0; j < tv.n; ++j)
+      if (tv.layer[j] >= R.l_first && tv.layer[j] <= R.l_last) {
+        const int i = copy(R.tl_v, tv, j);
+        if (tv.layer[j] == e->l_label) R.label_local = i;
+      }
+    for (int j = 0; j < tg.n; ++j)
+      if (tg.layer[j] >= R.l_first && tg.layer[j] <= R.l_last) copy(R.tl_gather, tg, j);
+    R.chunks_opt = build_tensor_list(R.tl_opt);
+    R.chunks_v = build_tensor_list(R.tl_v);
+    R.vbase = tv.chunk_start[R.l_first];                       // tl_v holds one entry per layer, in layer order
+    R.cbase = cbase; R.tbase = tbase;
+    cbase += R.chunks_opt; tbase += R.tl_opt.n;
+  }
 }
 
-__global__ void zero_list_kernel(float* buf, TensorList tl) {
+// zeroes the atomically accumulated gradient slots; with `hyp` it also opens the optimizer step (++step, lr_t) -- one launch
+__global__ void zero_list_kernel(float* buf, TensorList tl, Hyper* hyp, float beta1) {
   for (int l = blockIdx.x; l < tl.n; l += gridDim.x)
     for (long long i = threadIdx.x; i < tl.numel[l]; i += blockDim.x) buf[tl.off[l] + i] = 0.f;
+  if (hyp && blockIdx.x == 0 && threadIdx.x == 0) hyper_tick(hyp, beta1);
 }
 
 struct Ctx {
@@ -241,16 +311,38 @@ struct Ctx {
   cudaStream_t st;
   int B, N, M, R, Rm;
   const float* features; const float* boxes; const float* q_att; const float* q_last;
+  bool fused_opt = false;    // train step: exchange + optimizer of each gradient range on the `opt` stream as soon as it is final
 };
 
 EpiArgs epi0() { EpiArgs x; memset(&x, 0, sizeof(x)); return x; }
 
+// brackets one dense product with timing events when regat_engine_profile is on (eager calls only)
+struct ProfScope {
+  regat_engine* e; cudaStream_t st; int idx = -1;
+  ProfScope(regat_engine* e_, cudaStream_t st_, int M, int N, int K) : e(e_), st(st_) {
+    if (!e->prof_on) return;
+    regat_engine::GemmRec r{M, N, K, nullptr, nullptr};
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    idx = (int)e->prof.size();
+    e->prof.push_back(r);
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(e->prof[idx].b, st); }
+};
+
 int dense(regat_engine* e, cudaStream_t st, bool tA, bool tB, int M, int N, int K, const void* A, int lda, const void* Bm,
           int ldb, void* C, int ldc, int c_dtype, const EpiArgs& ep, int split_k = 1) {
+  ProfScope prof(e, st, M, N, K);
   if (e->dtype == REGAT_F32) return gemm_simt(REGAT_F32, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, REGAT_F32, ep, st);
   if (e->use_tc && gemm_tc_supported(tA, tB, M, N, K, A, lda, Bm, ldb))
     return gemm_tc(tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, c_dtype, ep, split_k, st);
   return gemm_simt(REGAT_BF16, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, c_dtype, ep, st);
+}
+// weight gradients of side-by-side layers: one product whose column blocks land in the layers' own gradient slots
+int dense_scatter(regat_engine* e, cudaStream_t st, int M, int N, int K, const void* A, int lda, const void* Bm, int ldb, float* C,
+                  int ldc, int block_cols, const long long* block_off) {
+  ProfScope prof(e, st, M, N, K);
+  return gemm_tc(1, 0, M, N, K, A, lda, Bm, ldb, C, ldc, REGAT_F32, epi0(), 1, st, block_cols, block_off);
 }
 
 // kernel operand of layer l: fp32 master weights in parity mode, bf16 copy otherwise
@@ -302,25 +394,65 @@ int fc_wgrad(regat_engine* e, cudaStream_t st, int l, long long w_row0, int rows
   return REGAT_OK;
 }
 
-int prepare_weights(regat_engine* e, cudaStream_t st) {
-  if (e->lowp_fresh) return REGAT_OK;
-  float* sumsq = e->at<float>(e->sumsq);
-  REGAT_REQUIRE(e->chunks_v <= 8192 && e->chunks_opt <= 8192, REGAT_ERR_UNSUPPORTED, "engine: parameter buffer too large for the partial-sum scratch");
-  if (!e->sumsq_fresh) REGAT_TRY(k_wn_prepare(e->params, e->tl_v, e->chunks_v, sumsq, nullptr, st, e->at<float>(e->vpart)));
-  // alpha = g/||v|| per layer; the same one-block kernel also gathers the biases of side-by-side layers and evaluates the
-  // label-FC constant (graph_att_net.py:71)
+// alpha = g/||v|| (from the per-chunk ||v||^2 partials), gathered biases, label constant and -- bf16 mode -- the bf16 copies of
+// alpha*v, for the layers of one range (r < 0: all layers)
+int derive_weights(regat_engine* e, int r, cudaStream_t st) {
+  const bool all = r < 0;
+  const TensorList& tv = all ? e->tl_v : e->rng[r].tl_v;
+  const TensorList& tg = all ? e->tl_gather : e->rng[r].tl_gather;
+  const int l0 = all ? 0 : e->rng[r].l_first;
+  const int chunks = all ? e->chunks_v : e->rng[r].chunks_v;
+  const int vbase = all ? 0 : e->rng[r].vbase;
+  const int label_local = all ? e->l_label : e->rng[r].label_local;
+  if (tv.n == 0) return REGAT_OK;
+  // the same one-block kernel also gathers the biases of side-by-side layers and evaluates the label-FC constant
+  // (graph_att_net.py:71)
   const Layer& LL = e->layers[e->l_label];
-  REGAT_TRY(k_wn_alpha(e->params, e->tl_v, sumsq, e->at<float>(e->alpha), e->at<float>(e->invn), st, e->at<float>(e->vpart),
-                       e->dtype == REGAT_BF16 ? &e->tl_gather : nullptr, e->at<float>(e->gbias), e->l_label, LL.v_off, LL.b_off,
-                       e->at<float>(e->scal)));
-  if (e->dtype == REGAT_BF16) REGAT_TRY(k_wn_scaled_copy(e->params, e->tl_v, e->chunks_v, e->at<float>(e->alpha), e->atv(e->lowp), st));
-  e->lowp_fresh = 1;
+  REGAT_TRY(k_wn_alpha(e->params, tv, e->at<float>(e->sumsq) + l0, e->at<float>(e->alpha) + l0, e->at<float>(e->invn) + l0, st,
+                       e->at<float>(e->vpart) + vbase, (e->dtype == REGAT_BF16 && tg.n) ? &tg : nullptr, e->at<float>(e->gbias),
+                       label_local, LL.v_off, LL.b_off, label_local >= 0 ? e->at<float>(e->scal) : nullptr));
+  if (e->dtype == REGAT_BF16) REGAT_TRY(k_wn_scaled_copy(e->params, tv, chunks, e->at<float>(e->alpha), e->atv(e->lowp), st));
   return REGAT_OK;
+}
+
+// Full derivation from the parameters (first call after bind / params_changed).
+int prepare_weights(regat_engine* e, cudaStream_t st) {
+  if (e->weights_ready) return REGAT_OK;
+  REGAT_REQUIRE(e->chunks_v <= 8192 && e->chunks_opt <= 8192, REGAT_ERR_UNSUPPORTED, "engine: parameter buffer too large for the partial-sum scratch");
+  REGAT_TRY(k_wn_prepare(e->params, e->tl_v, e->chunks_v, e->at<float>(e->sumsq), nullptr, st, e->at<float>(e->vpart)));
+  REGAT_TRY(derive_weights(e, -1, st));
+  e->weights_ready = 1;
+  return REGAT_OK;
+}
+
+OptHyper opt_hyper(const regat_engine* e) {
+  OptHyper hp;
+  hp.lr_t = 0.f; hp.beta1 = e->cfg.beta1; hp.beta2 = e->cfg.beta2; hp.eps = e->cfg.eps; hp.clip = e->cfg.grad_clip;
+  hp.grads_are_final = e->grads_final;
+  hp.lr_t_dev = &e->at<Hyper>(e->hyp)->lr_t;
+  return hp;
+}
+
+// clip + Adamax of one range (r < 0: everything), then the derived state of the tensors just written
+int optimize_range(regat_engine* e, int r, cudaStream_t st) {
+  const bool all = r < 0;
+  const TensorList& to = all ? e->tl_opt : e->rng[r].tl_opt;
+  const int chunks = all ? e->chunks_opt : e->rng[r].chunks_opt;
+  const int cbase = all ? 0 : e->rng[r].cbase, tbase = all ? 0 : e->rng[r].tbase;
+  if (to.n == 0) return REGAT_OK;
+  float* stats = e->at<float>(e->stats) + 2 * tbase;
+  REGAT_TRY(k_opt_reduce(e->params, e->grads, to, chunks, e->at<float>(e->partials) + 2 * cbase, stats, st,
+                         e->at<unsigned int>(e->counters) + tbase));
+  // the update leaves ||v_new||^2 per chunk in `vpart` (engine-wide chunk numbering)
+  REGAT_TRY(k_opt_update(e->params, e->grads, e->am, e->au, to, chunks, stats, e->at<float>(e->alpha), e->at<float>(e->invn),
+                         opt_hyper(e), st, e->at<float>(e->vpart)));
+  return derive_weights(e, r, st);
 }
 
 int ensure_side(regat_engine* e) {
   if (e->side) return REGAT_OK;
   REGAT_CUDA(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
+  REGAT_CUDA(cudaStreamCreateWithFlags(&e->opt, cudaStreamNonBlocking));
   for (int i = 0; i < regat_engine::NEV; ++i) REGAT_CUDA(cudaEventCreateWithFlags(&e->ev[i], cudaEventDisableTiming));
   return REGAT_OK;
 }
@@ -440,16 +572,24 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
   return REGAT_OK;
 }
 
-// [first layer's v, end of last layer) of the flat buffer is final: tell the data-parallel layer (it may start the all-reduce)
-void grads_ready(regat_engine* e, int l_first, int l_last) {
-  if (!e->grad_cb) return;
-  const long long lo = e->layers[l_first].v_off;
-  const long long hi = (l_last + 1 < (int)e->layers.size()) ? e->layers[l_last + 1].v_off : e->param_elems;
-  e->grad_cb(e->grad_cb_user, lo, hi - lo);
-}
-
-void grads_ready_range(regat_engine* e, long long lo, long long hi) {
-  if (e->grad_cb && hi > lo) e->grad_cb(e->grad_cb_user, lo, hi - lo);
+// Range r of the flat gradient buffer has received its last write on the main stream.
+//   callback set (library all-reduce driven from Python): tell the data-parallel layer, it may start the all-reduce;
+//   fused train step: the `opt` stream waits for the main stream, exchanges the range over NVLink (data parallel) and --
+//   unless `defer_opt` -- runs clip + Adamax and re-derives alpha / the bf16 copies for it.
+int range_ready(Ctx& c, int r, bool defer_opt = false) {
+  regat_engine* e = c.e;
+  const OptRange& R = e->rng[r];
+  if (R.l_last < R.l_first) return REGAT_OK;
+  if (!c.fused_opt) {
+    if (e->grad_cb) e->grad_cb(e->grad_cb_user, R.lo, R.hi - R.lo);
+    return REGAT_OK;
+  }
+  REGAT_TRY(fork_to(c.st, e->opt, e->ev[10 + r]));
+  if (e->dp_world > 1)
+    REGAT_TRY(dp_allreduce_f32_impl(e->dp_grad_ptrs, e->dp_mc, e->dp_flag_ptrs, e->dp_rank, e->dp_world, R.lo, R.hi - R.lo, 0,
+                                    e->at<uint32_t>(e->hyp) + 8, e->dp_blocks, e->opt));
+  if (!defer_opt) REGAT_TRY(optimize_range(e, r, e->opt));
+  return REGAT_OK;
 }
 
 int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float* dq_last) {
@@ -464,6 +604,7 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   const void* qlast = dt == REGAT_BF16 ? e->atv(e->qlastT) : (const void*)c.q_last;
   const void* v0 = e->l_v2out >= 0 ? e->atv(e->v0) : feat;
   float* scal = e->at<float>(e->scal);
+  e->grads_final = 0;
 
   // bias / pair_pos_fc / label gradients are accumulated with atomics: zero those slots (kernels' gradients are overwritten)
   {
@@ -482,7 +623,7 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
       const Layer& L = e->layers[e->l_pos[d]];
       z.off[z.n] = L.v_off; z.numel[z.n] = (long long)L.rows * L.cols; ++z.n;
     }
-    zero_list_kernel<<<z.n, 128, 0, st>>>(e->grads, z);
+    zero_list_kernel<<<z.n, 128, 0, st>>>(e->grads, z, c.fused_opt ? e->at<Hyper>(e->hyp) : nullptr, cf.beta1);
     REGAT_POST_LAUNCH();
     REGAT_CUDA(cudaMemsetAsync(scal + 1, 0, 3 * sizeof(float), st));   // dc, loss, score
   }
@@ -530,7 +671,7 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   if (dt == REGAT_BF16 && e->use_tc) {
     // [dW_qa | dW_qe] = q_last^T [du | dqe]  (one GEMM scattered into the two kernels' gradient slots);  dq_last = [du|dqe] [W_qa|W_qe]^T
     const long long offs[2] = {0, e->layers[e->l_qe].v_off - e->layers[e->l_qa].v_off};
-    REGAT_TRY(gemm_tc(1, 0, Q, 2 * Hd, B, qlast, Q, e->atv(e->duqe), 2 * Hd, gradW(e, e->l_qa), Hd, REGAT_F32, epi0(), 1, sd, Hd, offs));
+    REGAT_TRY(dense_scatter(e, sd, Q, 2 * Hd, B, qlast, Q, e->atv(e->duqe), 2 * Hd, gradW(e, e->l_qa), Hd, Hd, offs));
     REGAT_TRY(bias_grad(e, sd, e->atv(e->duqe), 2 * Hd, B, Hd, gradB(e, e->l_qa), &cb_side));
     REGAT_TRY(bias_grad(e, sd, dqe, 2 * Hd, B, Hd, gradB(e, e->l_qe), &cb_side));
     if (dq_last)
@@ -548,7 +689,7 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
                            e->at<uint64_t>(e->gate), e->at<float>(e->P), e->atv(e->dQb), e->atv(e->dKVb), e->atv(e->ds), st));
   REGAT_TRY(k_colsum_multi(dt, cb_side, sd));
   REGAT_TRY(fork_to(sd, st, e->ev[0]));   // join the side stream: BUTD + classifier gradients (the tail of the flat buffer) are final
-  grads_ready(e, e->l_va, e->l_c3);
+  REGAT_TRY(range_ready(c, 0));
   // The bias gradients (column sums -- HBM-bound) and the small question-side products run on the side stream next to the
   // tensor-bound GEMMs of the main stream.  Gradient ranges are announced in the order they become final: attention layers,
   // then self_weights + label FC, then v2out -- the data-parallel layer starts each all-reduce behind the rest of the backward.
@@ -579,16 +720,21 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
       kvo[d] = e->layers[e->l_k[d]].v_off - e->layers[e->l_k[0]].v_off;
       kvo[dirs + d] = e->layers[e->l_out[d]].v_off - e->layers[e->l_k[0]].v_off;
     }
-    REGAT_TRY(gemm_tc(1, 0, D, dirs * D, R, e->atv(e->s), D, e->atv(e->dQb), dirs * D, gradW(e, e->l_q[0]), D, REGAT_F32, epi0(), 1, st, D, qo));
-    REGAT_TRY(gemm_tc(1, 0, D, 2 * dirs * D, Rm, e->atv(e->strunc), D, e->atv(e->dKVb), 2 * dirs * D, gradW(e, e->l_k[0]), D, REGAT_F32, epi0(), 1,
-                      st, D, kvo));
+    REGAT_TRY(dense_scatter(e, st, D, dirs * D, R, e->atv(e->s), D, e->atv(e->dQb), dirs * D, gradW(e, e->l_q[0]), D, D, qo));
+    REGAT_TRY(dense_scatter(e, st, D, 2 * dirs * D, Rm, e->atv(e->strunc), D, e->atv(e->dKVb), 2 * dirs * D, gradW(e, e->l_k[0]), D, D, kvo));
     REGAT_TRY(fork_to(sd, st, e->ev[7]));
-    grads_ready(e, e->l_pos[0], e->l_out[dirs - 1]);     // both attention layers
+    // both attention layers: exchanged from here on; their optimizer step rewrites the bf16 kernels the two input-gradient
+    // products below still read, so it is queued behind them
+    REGAT_TRY(range_ready(c, 1, /*defer_opt=*/true));
     EpiArgs ep = epi0();
     ep.accumulate = 1;                                 // ds already holds dout
     REGAT_TRY(dense(e, st, false, true, R, D, dirs * D, e->atv(e->dQb), dirs * D, lowp_at(e, e->gq_off), dirs * D, e->atv(e->ds), D, dt, ep));
     REGAT_TRY(dense(e, st, false, true, Rm, D, 2 * dirs * D, e->atv(e->dKVb), 2 * dirs * D, lowp_at(e, e->gkv_off), 2 * dirs * D,
                     e->atv(e->dstrunc), D, dt, epi0()));
+    if (c.fused_opt) {
+      REGAT_TRY(fork_to(st, e->opt, e->ev[14]));
+      REGAT_TRY(optimize_range(e, 1, e->opt));
+    }
   } else {
     for (int d = 0; d < dirs; ++d) {
       unsigned char* dQd = e->at<unsigned char>(e->dQb) + (size_t)d * D * es;
@@ -603,7 +749,7 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
     }
     REGAT_TRY(k_colsum_multi(dt, cb_qkv, sd));
     REGAT_TRY(fork_to(sd, st, e->ev[7]));
-    grads_ready(e, e->l_pos[0], e->l_out[dirs - 1]);
+    REGAT_TRY(range_ready(c, 1));                      // every product that reads these layers' kernels has been issued
   }
   REGAT_TRY(k_addrows(dt, e->atv(e->ds), e->atv(e->dstrunc), B, N, M, D, st));
   // self_weights: s = alpha (v0 Ws[:D] + mask (q Ws[D:])) + b.   ds is final: its column sum and the masked segment sum go to
@@ -625,18 +771,20 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   }
   // every announcement is a full join of the side stream (a data-parallel caller may end a CUDA-graph capture segment there)
   REGAT_TRY(fork_to(sd, st, e->ev[9]));
-  if (e->l_v2out >= 0) grads_ready(e, e->l_v2out, e->l_v2out);
+  REGAT_TRY(range_ready(c, 2));
   // self_weights last, as ONE range: an exchange has a fixed cost of ~40 us (three launches, two cross-GPU flag rounds), so
   // the tail of the step is one such exchange, not two
   REGAT_TRY(fc_wgrad(e, st, e->l_self, 0, R, D, v0, D, e->atv(e->ds), D, false));
   REGAT_TRY(fc_wgrad(e, st, e->l_self, D, B, Q, qatt, Q, e->atv(e->dsq), D, false));
   if (dq_att) REGAT_TRY(fc_dgrad(e, st, e->l_self, D, B, Q, e->atv(e->dsq), D, dq_att, Q, REGAT_F32, false));
-  grads_ready_range(e, LS.v_off, e->layers[e->l_label + 1].v_off);             // self_weights (kernel, g, bias) and the label FC
-  e->grads_final = 0;
+  (void)LS;
+  REGAT_TRY(range_ready(c, 3));                        // self_weights (kernel, g, bias) and the label FC
+  if (c.fused_opt) REGAT_TRY(fork_to(e->opt, st, e->ev[15]));      // the step is complete on the caller's stream
   return REGAT_OK;
 }
 
 int opt_stats(regat_engine* e, cudaStream_t st) {
+  REGAT_TRY(prepare_weights(e, st));
   return k_opt_reduce(e->params, e->grads, e->tl_opt, e->chunks_opt, e->at<float>(e->partials), e->at<float>(e->stats), st,
                       e->at<unsigned int>(e->counters));
 }
@@ -686,6 +834,7 @@ extern "C" int regat_engine_destroy(regat_engine* e) {
   if (e) {
     for (int i = 0; i < regat_engine::NEV; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     if (e->side) cudaStreamDestroy(e->side);
+    if (e->opt) cudaStreamDestroy(e->opt);
     delete e;
   }
   return REGAT_OK;
@@ -716,8 +865,9 @@ extern "C" int regat_engine_bind(regat_engine* e, float* params, float* grads, f
                 REGAT_ERR_ALIGN, "engine_bind: buffers must be 256-byte aligned");
   e->params = params; e->grads = grads; e->am = adamax_m; e->au = adamax_u;
   e->ws = static_cast<unsigned char*>(workspace); e->ws_bytes = workspace_bytes;
-  e->sumsq_fresh = 0; e->lowp_fresh = 0;
-  REGAT_CUDA(cudaMemset(e->ws + e->counters.off, 0, MAX_TENSORS * 4));    // setup-time: the counters reset themselves afterwards
+  e->weights_ready = 0;
+  REGAT_CUDA(cudaMemset(e->ws + e->counters.off, 0, MAX_TENSORS * 4));
+  REGAT_CUDA(cudaMemset(e->ws + e->hyp.off, 0, 64 * 4));    // setup-time: the counters reset themselves afterwards
   return REGAT_OK;
 }
 
@@ -766,17 +916,28 @@ extern "C" int regat_engine_update(regat_engine* e, float lr, int step, regat_st
   REGAT_REQUIRE(step >= 1, REGAT_ERR_ARG, "engine_update: step is 1-based");
   cudaStream_t st = (cudaStream_t)stream;
   const int l0 = launch_counter();
-  REGAT_TRY(opt_stats(e, st));
-  OptHyper hp;
-  hp.lr_t = (float)((double)lr / (1.0 - pow((double)e->cfg.beta1, (double)step)));
-  hp.beta1 = e->cfg.beta1; hp.beta2 = e->cfg.beta2; hp.eps = e->cfg.eps; hp.clip = e->cfg.grad_clip;
-  hp.grads_are_final = e->grads_final;
-  // the update leaves ||v_new||^2 per chunk in `vpart`: the next forward pass skips wn_prepare's read of the parameters
-  REGAT_TRY(k_opt_update(e->params, e->grads, e->am, e->au, e->tl_opt, e->chunks_opt, e->at<float>(e->stats), e->at<float>(e->alpha),
-                         e->at<float>(e->invn), hp, st, e->at<float>(e->vpart)));
-  e->sumsq_fresh = 1;
-  e->lowp_fresh = 0;
+  REGAT_TRY(prepare_weights(e, st));          // alpha / ||v|| of the CURRENT parameters (no-op unless they were written from outside)
+  REGAT_TRY(k_hyper(e->at<Hyper>(e->hyp), lr, step - 1, e->cfg.beta1, HYPER_SET_LR | HYPER_SET_STEP | HYPER_TICK, st));
+  REGAT_TRY(optimize_range(e, -1, st));       // clip + Adamax, then alpha / bf16 copies of the new parameters
   e->last_launches = launch_counter() - l0;
+  return REGAT_OK;
+}
+
+extern "C" int regat_engine_set_lr(regat_engine* e, float lr, regat_stream_t stream) {
+  REGAT_REQUIRE(e && e->ws, REGAT_ERR_ARG, "engine_set_lr: not bound");
+  return k_hyper(e->at<Hyper>(e->hyp), lr, 0, e->cfg.beta1, HYPER_SET_LR, (cudaStream_t)stream);
+}
+extern "C" int regat_engine_set_step(regat_engine* e, int steps_done, regat_stream_t stream) {
+  REGAT_REQUIRE(e && e->ws && steps_done >= 0, REGAT_ERR_ARG, "engine_set_step: not bound / negative step count");
+  return k_hyper(e->at<Hyper>(e->hyp), 0.f, steps_done, e->cfg.beta1, HYPER_SET_STEP, (cudaStream_t)stream);
+}
+extern "C" int regat_engine_get_step(regat_engine* e, int* steps_done, float* lr, regat_stream_t stream) {
+  REGAT_REQUIRE(e && e->ws, REGAT_ERR_ARG, "engine_get_step: not bound");
+  Hyper h;
+  REGAT_CUDA(cudaMemcpyAsync(&h, e->at<Hyper>(e->hyp), sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  REGAT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (steps_done) *steps_done = h.step;
+  if (lr) *lr = h.lr;
   return REGAT_OK;
 }
 
@@ -784,10 +945,80 @@ extern "C" int regat_engine_train_step(regat_engine* e, int B, int N, const floa
                                        const float* q_last, const float* target, float lr, int step, float* loss_out,
                                        regat_stream_t stream) {
   REGAT_TRY(check_call(e, B, N, true));
+  REGAT_REQUIRE(step >= 1, REGAT_ERR_ARG, "engine_train_step: step is 1-based");
   const int l0 = launch_counter();
-  REGAT_TRY(regat_engine_fwd_bwd(e, B, N, features, boxes, q_att, q_last, target, 1.0f, loss_out, nullptr, nullptr, nullptr, stream));
-  REGAT_TRY(regat_engine_update(e, lr, step, stream));
+  REGAT_TRY(k_hyper(e->at<Hyper>(e->hyp), lr, step - 1, e->cfg.beta1, HYPER_SET_LR | HYPER_SET_STEP, (cudaStream_t)stream));
+  REGAT_TRY(regat_engine_train_step_dev(e, B, N, features, boxes, q_att, q_last, target, loss_out, stream));
   e->last_launches = launch_counter() - l0;
+  return REGAT_OK;
+}
+
+// One whole train step from device-resident optimizer state: no host scalar enters any launch, so the call can be captured
+// in ONE CUDA graph and replayed (also with the in-place gradient exchange of regat_engine_set_dp).
+extern "C" int regat_engine_train_step_dev(regat_engine* e, int B, int N, const float* features, const float* boxes, const float* q_att,
+                                           const float* q_last, const float* target, float* loss_out, regat_stream_t stream) {
+  REGAT_TRY(check_call(e, B, N, true));
+  REGAT_REQUIRE(features && boxes && q_att && q_last && target, REGAT_ERR_ARG, "engine_train_step: null input");
+  const int l0 = launch_counter();
+  cudaStream_t st = (cudaStream_t)stream;
+  Ctx c{e, st, B, N, std::min(e->cfg.nongt_dim, N), B * N, B * std::min(e->cfg.nongt_dim, N), features, boxes, q_att, q_last};
+  c.fused_opt = true;
+  REGAT_TRY(forward(c, true, nullptr, nullptr));
+  REGAT_TRY(backward(c, target, 1.0f / (float)e->dp_world, nullptr, nullptr));
+  if (loss_out) REGAT_CUDA(cudaMemcpyAsync(loss_out, e->at<float>(e->scal) + 2, 2 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  e->last_launches = launch_counter() - l0;
+  return REGAT_OK;
+}
+
+// Data parallel: the bound grads buffer is a symmetric allocation (same layout on every rank, peer-mapped, optionally bound to an
+// NVSwitch multicast address); regat_engine_train_step[_dev] then reduces every gradient range in place over NVLink on the
+// engine's own stream as soon as the backward pass has finished it, with grad_scale = 1/world.  world = 1 switches it off.
+extern "C" int regat_engine_set_dp(regat_engine* e, const uint64_t* grad_ptrs, uint64_t multicast_ptr, const uint64_t* flag_ptrs,
+                                   int rank, int world, int blocks) {
+  REGAT_REQUIRE(e, REGAT_ERR_ARG, "engine is null");
+  if (world <= 1) { e->dp_world = 1; e->dp_rank = 0; return REGAT_OK; }
+  REGAT_REQUIRE(grad_ptrs && flag_ptrs && world <= 16 && rank >= 0 && rank < world, REGAT_ERR_ARG, "engine_set_dp: bad rank %d / world %d", rank, world);
+  REGAT_REQUIRE(e->grads && (uint64_t)(uintptr_t)e->grads == grad_ptrs[rank], REGAT_ERR_ARG,
+                "engine_set_dp: the bound grads buffer must be this rank's entry of the symmetric pointer table");
+  for (int r = 0; r < world; ++r) { e->dp_grad_ptrs[r] = grad_ptrs[r]; e->dp_flag_ptrs[r] = flag_ptrs[r]; }
+  e->dp_mc = multicast_ptr; e->dp_rank = rank; e->dp_world = world; e->dp_blocks = blocks > 0 ? blocks : 32;
+  REGAT_CUDA(cudaMemset(e->at<uint32_t>(e->hyp) + 8, 0, sizeof(uint32_t)));      // exchange call counter: every rank starts at 0
+  return REGAT_OK;
+}
+
+// Derives alpha, the bf16 kernels, the gathered biases and the label constant from the parameters NOW (on `stream`).  Call it
+// after writing the parameter buffer from outside when captured graphs of engine calls are going to be replayed next.
+extern "C" int regat_engine_refresh_weights(regat_engine* e, regat_stream_t stream) {
+  REGAT_REQUIRE(e && e->params && e->ws, REGAT_ERR_ARG, "engine_refresh_weights: not bound");
+  e->weights_ready = 0;
+  return prepare_weights(e, (cudaStream_t)stream);
+}
+
+// Measurement aid: with on != 0 every dense product of the following EAGER engine calls is bracketed by timing events (never
+// enable it while capturing a graph); regat_engine_profile_read synchronises the device and returns (M, N, K, ms) per product
+// in launch order, then clears the list.  Products run beside the side-stream work they overlap with in the real step.
+extern "C" int regat_engine_profile(regat_engine* e, int on) {
+  REGAT_REQUIRE(e, REGAT_ERR_ARG, "engine is null");
+  for (auto& r : e->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  e->prof.clear();
+  e->prof_on = on != 0;
+  return REGAT_OK;
+}
+extern "C" int regat_engine_profile_read(regat_engine* e, int max_records, int32_t* mnk, float* ms, int* count) {
+  REGAT_REQUIRE(e && mnk && ms && count, REGAT_ERR_ARG, "engine_profile_read: null pointer");
+  REGAT_CUDA(cudaDeviceSynchronize());
+  int n = 0;
+  for (auto& r : e->prof) {
+    if (n < max_records) {
+      float t = 0.f;
+      REGAT_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+      mnk[3 * n] = r.M; mnk[3 * n + 1] = r.N; mnk[3 * n + 2] = r.K; ms[n] = t;
+      ++n;
+    }
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  e->prof.clear();
+  *count = n;
   return REGAT_OK;
 }
 
@@ -796,7 +1027,7 @@ extern "C" int regat_engine_last_launches(const regat_engine* e) { return e ? e-
 // The caller has written the parameter buffer (checkpoint load, set_weights, ...): cached weight-norm statistics are stale.
 extern "C" int regat_engine_params_changed(regat_engine* e) {
   REGAT_REQUIRE(e, REGAT_ERR_ARG, "engine is null");
-  e->sumsq_fresh = 0; e->lowp_fresh = 0;
+  e->weights_ready = 0;
   return REGAT_OK;
 }
 

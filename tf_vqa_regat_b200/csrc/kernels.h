@@ -26,7 +26,18 @@ struct OptHyper {
   float lr_t;       // lr / (1 - beta1^t)
   float beta1, beta2, eps, clip;
   int grads_are_final;
+  const float* lr_t_dev = nullptr;   // when set, lr_t is read from device memory (written by k_hyper: CUDA-graph capturable steps)
 };
+
+// Device-resident optimizer scalars (engine workspace): lr, the number of optimizer steps taken, lr_t of the current step.
+struct Hyper { float lr; int step; float lr_t; int pad; };
+constexpr int HYPER_SET_LR = 1, HYPER_SET_STEP = 2, HYPER_TICK = 4;
+// one thread: optionally overwrite lr / step, then (TICK) ++step and lr_t = lr / (1 - beta1^step)   (Keras Adamax, train.py:48)
+int k_hyper(Hyper* h, float lr, int step, float beta1, int mode, cudaStream_t st);
+__device__ __forceinline__ void hyper_tick(Hyper* h, float beta1) {
+  const int t = ++h->step;
+  h->lr_t = (float)((double)h->lr / (1.0 - pow((double)beta1, (double)t)));
+}
 
 int k_wn_prepare(const float* params, const TensorList& tl, int chunks, float* sumsq, void* lowp, cudaStream_t st, float* partials = nullptr);
 int k_wn_scaled_copy(const float* params, const TensorList& tl, int chunks, const float* alpha, void* lowp, cudaStream_t st);

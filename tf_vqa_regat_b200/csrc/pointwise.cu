@@ -641,11 +641,14 @@ __global__ void __launch_bounds__(256) opt_update_kernel(float* __restrict__ par
     const float inv = inv_norm[wl];
     a = alpha[wl];
     proj = dot * inv * inv;
-    nrm = fabsf(a) * sqrtf(fmaxf(gg - dot * dot * inv * inv, 0.f));
+    // ||dv||^2 = alpha^2 (||G||^2 - <G,v>^2/||v||^2): the difference is combined in double (the two terms nearly cancel when G is
+    // almost parallel to v)
+    nrm = fabsf(a) * (float)sqrt(fmax((double)gg - (double)dot * (double)dot * (double)inv * (double)inv, 0.0));
   } else {
     nrm = sqrtf(gg);
   }
   const float cs = hp.clip / fmaxf(nrm, hp.clip);           // tf.clip_by_norm
+  const float lr_t = hp.lr_t_dev ? __ldg(hp.lr_t_dev) : hp.lr_t;
   float ss = 0.f;
   for (long long i = base + threadIdx.x; i < end; i += 256) {
     const float w = params[off + i];
@@ -653,7 +656,7 @@ __global__ void __launch_bounds__(256) opt_update_kernel(float* __restrict__ par
     const float m = hp.beta1 * am[off + i] + (1.f - hp.beta1) * g;
     const float u = fmaxf(hp.beta2 * au[off + i], fabsf(g));
     am[off + i] = m; au[off + i] = u;
-    const float wn = w - hp.lr_t * m / (u + hp.eps);
+    const float wn = w - lr_t * m / (u + hp.eps);
     params[off + i] = wn;
     ss = fmaf(wn, wn, ss);
   }
@@ -669,7 +672,7 @@ __global__ void __launch_bounds__(256) opt_update_kernel(float* __restrict__ par
     const float m = hp.beta1 * am[go] + (1.f - hp.beta1) * dg;
     const float u = fmaxf(hp.beta2 * au[go], fabsf(dg));
     am[go] = m; au[go] = u;
-    params[go] -= hp.lr_t * m / (u + hp.eps);
+    params[go] -= lr_t * m / (u + hp.eps);
   }
 }
 
@@ -688,6 +691,12 @@ __global__ void __launch_bounds__(256) opt_finalize_kernel(const float* __restri
   for (long long i = base + threadIdx.x; i < end; i += 256)
     grads[off + i] = a * (grads[off + i] - dot * inv * inv * params[off + i]);
   if (base == 0 && threadIdx.x == 0) grads[tl.g_off[l]] = dot * inv;
+}
+
+__global__ void hyper_kernel(Hyper* h, float lr, int step, float beta1, int mode) {
+  if (mode & HYPER_SET_LR) h->lr = lr;
+  if (mode & HYPER_SET_STEP) h->step = step;
+  if (mode & HYPER_TICK) hyper_tick(h, beta1);
 }
 
 __global__ void label_const_kernel(const float* __restrict__ params, long long v_off, long long b_off, const float* alpha_l,
@@ -888,6 +897,11 @@ int k_opt_reduce(const float* params, const float* grads, const TensorList& tl, 
 int k_opt_update(float* params, const float* grads, float* m, float* u, const TensorList& tl, int chunks, const float* stats,
                  const float* alpha, const float* inv_norm, const OptHyper& hp, cudaStream_t st, float* vpartials) {
   opt_update_kernel<<<chunks, 256, 0, st>>>(params, grads, m, u, tl, stats, alpha, inv_norm, hp, vpartials);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+int k_hyper(Hyper* h, float lr, int step, float beta1, int mode, cudaStream_t st) {
+  hyper_kernel<<<1, 1, 0, st>>>(h, lr, step, beta1, mode);
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }

@@ -5,7 +5,15 @@ end to end, so rank r simply takes graphs [r*B/R, (r+1)*B/R); with equal shards 
 the average of rank means, hence grad_scale = 1/R and a SUM all-reduce reproduce the single-GPU gradient.
 
 What is reduced is dL/dW_eff (+ bias gradients), which is linear in the batch; the weight-norm projection,
-per-tensor clip and Adamax run after the reduce on every rank (train.py:112-113)."""
+per-tensor clip and Adamax run after the reduce on every rank (train.py:112-113).
+
+Two ways to drive the exchange:
+  fused   (default with symmetric memory, fp32 wire): the ENGINE launches the in-place exchange of each gradient range on its
+          own stream as soon as the backward pass has finished the range, followed by that range's clip + Adamax
+          (regat_engine_set_dp + regat_engine_train_step[_dev]); the whole step is one launch sequence without host
+          scalars, so it replays from ONE CUDA graph (engine.GraphedTrainStep).
+  callback: regat_engine_fwd_bwd announces each finished range to Python, which starts the exchange (own kernels with a
+          host-side epoch, the staged bf16 wire format, or NCCL) on a communication stream; the optimizer follows eagerly."""
 import os
 
 import torch
@@ -59,6 +67,8 @@ class DataParallelTrainer:
         self.step_count = 0
         self.overlap = bool(overlap and self.world > 1 and hasattr(engine, "set_grad_callback") and engine.grads.is_cuda)
         self._reduced = 0
+        self._cb_error = None
+        self.fused = False
         # Exchange backend: "symm" = our kernels over symmetric (peer-mapped / NVSwitch-multicast) memory, "nccl" = NCCL all-reduce
         self.backend = "nccl"
         want = os.environ.get("REGAT_DP_COMM", "symm")
@@ -69,18 +79,28 @@ class DataParallelTrainer:
             except Exception as ex:                      # no symmetric memory on this system: NCCL carries the exchange
                 if self.rank == 0:
                     print(f"[regat dp] symmetric-memory exchange unavailable ({type(ex).__name__}: {ex}); using NCCL", flush=True)
+        # fused: the engine itself exchanges + optimizes each range (one CUDA graph per step); needs the in-place fp32 wire format
+        if (self.backend == "symm" and self.wire == "f32" and hasattr(engine, "set_dp")
+                and os.environ.get("REGAT_DP_FUSED", "1") != "0"):
+            engine.set_dp(self._stage_ptrs, self._mc, self._flag_ptrs_dev, self.rank, self.world, self._blocks)
+            self.fused = True
         if self.overlap:
             self.comm_stream = torch.cuda.Stream(engine.grads.device)
             engine.set_grad_callback(self._on_ready)
 
     def _on_ready(self, offset, numel):
-        main = torch.cuda.current_stream()
-        ev = torch.cuda.Event()
-        ev.record(main)
-        self.comm_stream.wait_event(ev)
-        with torch.cuda.stream(self.comm_stream):
-            self._allreduce_range(offset, numel)
-        self._reduced += numel
+        # runs inside a ctypes callback: an exception here would be swallowed, so it is kept and re-raised after fwd_bwd
+        try:
+            main = torch.cuda.current_stream()
+            ev = torch.cuda.Event()
+            ev.record(main)
+            self.comm_stream.wait_event(ev)
+            with torch.cuda.stream(self.comm_stream):
+                self._allreduce_range(offset, numel)
+            self._reduced += numel
+        except BaseException as ex:             # noqa: BLE001
+            if self._cb_error is None:
+                self._cb_error = ex
 
     def _setup_symm(self, group):
         """Symmetric staging + flag buffers (torch.distributed._symmetric_memory does the allocation and the address exchange;
@@ -102,13 +122,14 @@ class DataParallelTrainer:
         else:
             self._g16 = symm_mem.empty(g.numel(), dtype=torch.bfloat16, device=g.device)
             h = symm_mem.rendezvous(self._g16, gname)
-        self._flags = symm_mem.empty(64, dtype=torch.int32, device=g.device)
+        self._flags = symm_mem.empty(128, dtype=torch.int32, device=g.device)    # [0,64): host-epoch calls, [64,128): the engine's
         self._flags.zero_()
         hf = symm_mem.rendezvous(self._flags, gname)
         torch.cuda.synchronize(g.device)
         dist.barrier(group)                            # every rank's flags are zero before anyone signals
         self._stage_ptrs = (C.c_uint64 * self.world)(*[int(p) for p in h.buffer_ptrs])
         self._flag_ptrs = (C.c_uint64 * self.world)(*[int(p) for p in hf.buffer_ptrs])
+        self._flag_ptrs_dev = (C.c_uint64 * self.world)(*[int(p) + 256 for p in hf.buffer_ptrs])
         self._mc = int(getattr(h, "multicast_ptr", 0) or 0)         # 0 where the fabric has no multicast: peers one by one
         if os.environ.get("REGAT_DP_MULTICAST", "1") == "0":
             self._mc = 0
@@ -159,12 +180,19 @@ class DataParallelTrainer:
                 self.engine.params_changed()
 
     def fwd_bwd_allreduce(self, features, boxes, q_att, q_last, target):
-        """Forward + backward on this rank's shard with the gradient all-reduce (overlapped when possible)."""
+        """Forward + backward on this rank's shard with the gradient all-reduce (overlapped when possible); the optimizer has
+        NOT run.  Callback-driven path (see the module docstring)."""
         self._reduced = 0
+        self._cb_error = None
         out = self.engine.fwd_bwd(features, boxes, q_att, q_last, target, grad_scale=1.0 / self.world)
-        if self.overlap and self._reduced == self.engine.grads.numel():
-            torch.cuda.current_stream().wait_stream(self.comm_stream)
-        elif self.world > 1 and self.comm_dtype == "bf16" and self.engine.grads.is_cuda:
+        if self.overlap:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)       # always joined, whatever happened in the callbacks
+            if self._cb_error is not None:
+                raise self._cb_error
+            if self._reduced != self.engine.grads.numel():
+                raise RuntimeError(f"gradient-ready ranges covered {self._reduced} of {self.engine.grads.numel()} elements: "
+                                   "refusing to guess which ranges were exchanged")
+        elif self.world > 1 and (self.backend == "symm" or (self.comm_dtype == "bf16" and self.engine.grads.is_cuda)):
             self._allreduce_range(0, self.engine.grads.numel())
         else:
             allreduce_flat_(self.engine.grads, self.group, self.bucket_elems)
@@ -173,9 +201,25 @@ class DataParallelTrainer:
     def step(self, features, boxes, q_att, q_last, target, lr):
         """One optimizer step on this rank's shard (already sliced)."""
         self.step_count += 1
+        if self.fused:
+            loss = self.engine.train_step(features, boxes, q_att, q_last, target, lr, self.step_count)
+            return {"loss": loss[0], "score": loss[1]}
         out = self.fwd_bwd_allreduce(features, boxes, q_att, q_last, target)
         self.engine.update(lr, self.step_count)
         return out
+
+    def capture_step(self, features, boxes, q_att, q_last, target, stream=None):
+        """ONE CUDA graph of the whole data-parallel step on these input tensors (fused mode only): forward, backward, the
+        in-place exchange of every gradient range, clip + Adamax.  lr / step live on the device (engine.set_lr / set_step)."""
+        if not self.fused:
+            raise RuntimeError("capture_step needs the fused exchange (symmetric memory, fp32 wire)")
+        from .engine import GraphedTrainStep
+        self.engine.set_grad_callback(None)           # the warm-up fwd_bwd inside must not start a Python-driven exchange
+        try:
+            return GraphedTrainStep(self.engine, features, boxes, q_att, q_last, target, stream)
+        finally:
+            if self.overlap:
+                self.engine.set_grad_callback(self._on_ready)
 
 
 def _timed_event(stream):

@@ -81,8 +81,10 @@ class HotPathEngine:
         self.params_changed()
 
     def params_changed(self):
-        """Call after writing `self.params` in place: cached weight-norm statistics are recomputed on the next pass."""
+        """Call after writing `self.params` in place: alpha = g/||v||, the bf16 kernels and the gathered biases are re-derived
+        right away on the current stream, so that eager calls AND replays of already captured graphs see the new weights."""
         _lib.check(self.lib.regat_engine_params_changed(self._h))
+        _lib.check(self.lib.regat_engine_refresh_weights(self._h, _stream()))
 
     def save_weights(self, path: str):
         """model.save_weights (main.py:145): the hot path's variables in Keras variable order (checkpoint.py)."""
@@ -153,6 +155,40 @@ class HotPathEngine:
                                                     self._loss.data_ptr(), _stream()))
         return self._loss
 
+    # ---- device-resident optimizer state: whole train steps without host scalars (one CUDA graph per step)
+    def set_lr(self, lr):
+        _lib.check(self.lib.regat_engine_set_lr(self._h, float(lr), _stream()))
+
+    def set_step(self, steps_done):
+        """Number of optimizer steps already taken (Adamax bias correction uses steps_done + 1 in the next step)."""
+        self.step_count = int(steps_done)
+        _lib.check(self.lib.regat_engine_set_step(self._h, int(steps_done), _stream()))
+
+    def get_step(self):
+        """(steps taken, learning rate) as stored on the device; synchronises the current stream."""
+        n, lr = C.c_int(), C.c_float()
+        _lib.check(self.lib.regat_engine_get_step(self._h, C.byref(n), C.byref(lr), _stream()))
+        return n.value, lr.value
+
+    def train_step_dev(self, features, boxes, q_att, q_last, target):
+        """One whole step (train.py:103-113) with lr / step taken from the device (set_lr, set_step): capturable in one CUDA
+        graph.  Returns the 2-float device tensor (loss, score)."""
+        B, N = self._inputs(features, boxes, q_att, q_last)
+        self._chk(target, (B, self.cfg.num_answers))
+        _lib.check(self.lib.regat_engine_train_step_dev(self._h, B, N, features.data_ptr(), boxes.data_ptr(), q_att.data_ptr(),
+                                                        q_last.data_ptr(), target.data_ptr(), self._loss.data_ptr(), _stream()))
+        return self._loss
+
+    def set_dp(self, grad_ptrs, multicast_ptr, flag_ptrs, rank, world, blocks=32):
+        """Data parallel inside train_step / train_step_dev: in-place exchange of each gradient range over NVLink
+        (regat_engine_set_dp).  grad_ptrs / flag_ptrs: sequences of `world` device addresses."""
+        if world <= 1:
+            _lib.check(self.lib.regat_engine_set_dp(self._h, None, 0, None, 0, 1, 0))
+            return
+        gp = (C.c_uint64 * world)(*[int(p) for p in grad_ptrs])
+        fp = (C.c_uint64 * world)(*[int(p) for p in flag_ptrs])
+        _lib.check(self.lib.regat_engine_set_dp(self._h, gp, int(multicast_ptr), fp, int(rank), int(world), int(blocks)))
+
     def set_grad_callback(self, fn):
         """fn(offset, numel) is invoked inside fwd_bwd whenever grads[offset:offset+numel] is final on the current stream
         (tail of the buffer first).  Pass None to remove it."""
@@ -166,6 +202,23 @@ class HotPathEngine:
     def last_launches(self):
         return self.lib.regat_engine_last_launches(self._h)
 
+    def profile_gemms(self, fn):
+        """Runs fn() (eager engine calls) with timing events around every dense product; returns [(M, N, K, ms), ...] in
+        launch order.  Measurement aid of bench.py (GEMM-class throughput inside the real step)."""
+        _lib.check(self.lib.regat_engine_profile(self._h, 1))
+        try:
+            fn()
+        finally:
+            cap = 256
+            mnk, ms, n = (C.c_int32 * (3 * cap))(), (C.c_float * cap)(), C.c_int()
+            _lib.check(self.lib.regat_engine_profile_read(self._h, cap, mnk, ms, C.byref(n)))
+            _lib.check(self.lib.regat_engine_profile(self._h, 0))
+        return [(mnk[3 * i], mnk[3 * i + 1], mnk[3 * i + 2], ms[i]) for i in range(n.value)]
+
+    def capture_train_step(self, features, boxes, q_att, q_last, target, stream=None):
+        """CUDA graph of one whole train step on these (static) input tensors; see GraphedTrainStep."""
+        return GraphedTrainStep(self, features, boxes, q_att, q_last, target, stream)
+
     def buffer(self, name, shape, dtype=None):
         """Copy of a named internal activation as a torch tensor (tests)."""
         p = C.c_void_p()
@@ -174,3 +227,28 @@ class HotPathEngine:
         dt = dtype or (torch.bfloat16 if self.dtype == _lib.BF16 else torch.float32)
         n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
         return self.workspace[off:off + n].view(dt).view(*shape).clone()
+
+
+class GraphedTrainStep:
+    """ONE CUDA graph = one whole train step (forward, backward, gradient exchange when data parallel, per-tensor clip, Adamax,
+    re-derived bf16 kernels) on fixed input tensors.  Nothing in it depends on a host scalar: the learning rate and the step
+    counter live on the device (HotPathEngine.set_lr / set_step), so `replay()` is the entire step.  The engine must have run
+    at least one eager call before (streams, tensor maps and kernel attributes are created on first use)."""
+
+    def __init__(self, engine: HotPathEngine, features, boxes, q_att, q_last, target, stream=None):
+        self.engine = engine
+        self.stream = stream or torch.cuda.current_stream()
+        self.graph = torch.cuda.CUDAGraph()
+        self.inputs = (features, boxes, q_att, q_last, target)      # keep the captured addresses alive
+        with torch.cuda.stream(self.stream):
+            # eager warm-up that leaves the parameters alone: creates the side streams, tensor maps, shared-memory attributes
+            engine.fwd_bwd(features, boxes, q_att, q_last, target)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                engine.train_step_dev(features, boxes, q_att, q_last, target)
+            self.launches = engine.last_launches()
+
+    def replay(self):
+        self.graph.replay()
+        self.engine.step_count += 1
+        return self.engine._loss
