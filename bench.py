@@ -573,14 +573,22 @@ def main():
         try:
             with torch.cuda.stream(leg.stream):
                 leg._eager(0)
-                recs = eng.profile_gemms(lambda: leg._eager(1))
+
+                def one():
+                    # a ~3 ms spin kernel first: every launch of the step is queued behind it, so the GPU never waits for the
+                    # host and the brackets contain no launch gaps
+                    torch.cuda._sleep(6_000_000)
+                    leg._eager(1)
+                recs = eng.profile_gemms(one)
             fl = sum(2.0 * m * n * k for m, n, k, _ in recs)
             tms = sum(t for *_, t in recs)
             small = [(m, n, k, t) for m, n, k, t in recs if min(m, n) <= 256 or k <= 256]
             gemm_class = {"launches": len(recs), "sum_ms": tms, "tflops": fl / (tms * 1e-3) / 1e12 if tms > 0 else None,
                           "share_of_step": tms / ms_step, "batch_sized_launches": len(small), "batch_sized_ms": sum(t for *_, t in small),
-                          "note": "eager step, CUDA events around each dense product on its own stream (side-stream work overlaps as in the "
-                                  "real step; eager launch gaps are outside the brackets); share = sum / graph-replayed ms_per_step"}
+                          "note": "one eager step queued behind a 3 ms spin kernel (no host launch gaps), CUDA events around each dense product "
+                                  "on its own stream; products on the side streams overlap the main stream as in the real step, so the sum "
+                                  "can exceed their share of the critical path; share = sum / graph-replayed ms_per_step",
+                          "records": [[m, n, k, round(t * 1e3, 1)] for m, n, k, t in recs]}
         except Exception as ex:      # noqa: BLE001
             gemm_class = {"error": f"{type(ex).__name__}: {ex}"[:200]}
 

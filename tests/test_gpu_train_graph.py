@@ -54,12 +54,13 @@ def test_graph_replay_equals_eager_steps(dtype):
     for e in param_layout(cfg)[0]:
         if _zero_direction(e.name):
             continue
-        d = np.abs(pe[e.offset:e.offset + e.numel] - pg[e.offset:e.offset + e.numel]).max()
-        # same kernels in the same order; only atomics (split-K, bias sums) reorder additions
-        assert d < 0.05 * steps * lr + 1e-6, (e.name, d)
-    # Adamax slots follow too
-    assert torch.allclose(eager.adamax_u, graphed.adamax_u, rtol=1e-3, atol=1e-6) or \
-        float((eager.adamax_u - graphed.adamax_u).abs().max()) < 1e-3 * float(eager.adamax_u.abs().max())
+        d = np.abs(pe[e.offset:e.offset + e.numel] - pg[e.offset:e.offset + e.numel])
+        # same kernels in the same order; only atomics (split-K, bias sums) reorder additions.  Adamax turns a gradient whose
+        # sign that reordering decides (g ~ 0) into a +-lr move, so single elements may differ by a step; on average nothing does
+        assert d.max() <= 2.0 * lr + 1e-6 and (d.mean() < 0.02 * lr or e.numel == 1), (e.name, d.max(), d.mean())
+    # Adamax slots follow too (the trajectories drift apart by the sign decisions above, hence a bound relative to the largest slot)
+    du = float((eager.adamax_u - graphed.adamax_u).abs().max()) / float(eager.adamax_u.abs().max())
+    assert du < (1e-4 if dtype == "fp32" else 2e-2), du
 
 
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])

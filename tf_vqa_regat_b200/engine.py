@@ -237,9 +237,10 @@ class GraphedTrainStep:
 
     def __init__(self, engine: HotPathEngine, features, boxes, q_att, q_last, target, stream=None):
         self.engine = engine
-        self.stream = stream or torch.cuda.current_stream()
+        self.stream = stream or torch.cuda.Stream(engine.device)      # graphs cannot be captured on the default stream
         self.graph = torch.cuda.CUDAGraph()
         self.inputs = (features, boxes, q_att, q_last, target)      # keep the captured addresses alive
+        self.stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):
             # eager warm-up that leaves the parameters alone: creates the side streams, tensor maps, shared-memory attributes
             engine.fwd_bwd(features, boxes, q_att, q_last, target)
@@ -249,6 +250,7 @@ class GraphedTrainStep:
             self.launches = engine.last_launches()
 
     def replay(self):
+        """Enqueues the step on the CURRENT stream (stream-ordered after whatever the caller enqueued there, e.g. input copies)."""
         self.graph.replay()
         self.engine.step_count += 1
         return self.engine._loss

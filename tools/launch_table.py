@@ -5,8 +5,9 @@ with open(path) as f:
     lines = [l for l in f if l.startswith('"')]
 r = csv.reader(lines); hdr = next(r); idx = {h: i for i, h in enumerate(hdr)}
 data = list(r)
-ups = [i for i, d in enumerate(data) if 'opt_update' in d[idx['Kernel Name']]]
-a, b = ups[-2] + 1, ups[-1] + 1
+# one bce_kernel per train step: the window between the last two holds exactly one step's kernels (backward of step k, forward of k+1)
+ups = [i for i, d in enumerate(data) if 'bce_kernel' in d[idx['Kernel Name']]]
+a, b = ups[-2], ups[-1]
 tot = 0
 agg = {}
 for d in data[a:b]:
