@@ -220,7 +220,7 @@ class Leg:
             if not self.trainer.fused and rank == 0:
                 print("[bench] fused in-place exchange unavailable on this system: eager steps with the callback-free exchange", flush=True)
         self.logits = torch.empty(B, cfg.num_answers, device=dev) if self.eval_only else None
-        self.graphs, self.launches = {}, 0
+        self.graphs, self.launches, self.graphed = {}, 0, False
         if not self.eval_only:
             self.eng.set_lr(args.lr)
             self.eng.set_step(0)
@@ -256,6 +256,7 @@ class Leg:
                         self._eager(slot)
                     self.graphs[slot] = g
                 self.launches = eng.last_launches()
+                self.graphed = True
             else:
                 self._eager(0)
                 self.launches = eng.last_launches()
@@ -706,7 +707,7 @@ def main():
                 tfl = ALG_MFLOP[wl] * 1e6 * (val_w / world) / 1e12
                 entry = {"value": val_w, "unit": UNIT, "ms_per_step": ms_w, "steps": ws, "warmup": wu, "batch_per_gpu": lg.B, "K": lg.N,
                          "config": workload_name(wl, lg.B, lg.N), "algorithmic_tflops_per_gpu": tfl,
-                         "step_tensor_frac": tfl / peaks["bf16_tflops"], "cuda_graph": bool(lg.graphs),
+                         "step_tensor_frac": tfl / peaks["bf16_tflops"], "cuda_graph": lg.graphed,
                          "e2e": lg.e2e(ws, "fp32")}
                 if wl == "adaptive100":
                     entry["e2e_ragged"] = lg.e2e(ws, "ragged")
@@ -752,7 +753,7 @@ def main():
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.dtype if args.dtype == "bf16" else "f32", "data": "synthetic",
                 "config": {"workload": workload_name(args.workload, B, N),
-                           "parallelism": f"dp{world}", "global_batch": B * world, "cuda_graph": bool(leg.graphs),
+                           "parallelism": f"dp{world}", "global_batch": B * world, "cuda_graph": leg.graphed,
                            "step": "one CUDA-graph replay = forward + backward + (exchange) + clip + Adamax + re-derived bf16 kernels",
                            "allreduce": (None if world == 1 else check and ("in-place " + str(check["wire"]) + " exchange inside the engine, 4 ranges "
                                          "behind the backward pass, multicast=" + str(check["multicast"]) + ", backend " + str(check["backend"]))),

@@ -88,8 +88,9 @@ struct regat_engine {
   OptRange rng[N_RANGES];
   // small independent work (BUTD question branch, tiny weight gradients) runs on a side stream, forked / joined with events
   cudaStream_t side = nullptr;
-  cudaStream_t opt = nullptr;      // gradient exchange + optimizer, range by range, behind the rest of the backward pass
-  static constexpr int NEV = 18;
+  cudaStream_t opt = nullptr;      // clip + Adamax + re-derived weights, range by range, behind the rest of the backward pass
+  cudaStream_t comm = nullptr;     // data parallel: the in-place gradient exchange of each range (runs beside the previous range's optimizer)
+  static constexpr int NEV = 24;   // 0-9 forward / backward forks, 10-13 range ready (main), 14 dgrads done, 15 final join, 16-19 range ready (side), 20-23 range exchanged
   cudaEvent_t ev[NEV] = {};
   // data parallel (regat_engine_set_dp): the grads buffer is a symmetric allocation, reduced in place by csrc/dp_exchange.cu
   int dp_world = 1, dp_rank = 0, dp_blocks = 32;
@@ -453,6 +454,7 @@ int ensure_side(regat_engine* e) {
   if (e->side) return REGAT_OK;
   REGAT_CUDA(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
   REGAT_CUDA(cudaStreamCreateWithFlags(&e->opt, cudaStreamNonBlocking));
+  REGAT_CUDA(cudaStreamCreateWithFlags(&e->comm, cudaStreamNonBlocking));
   for (int i = 0; i < regat_engine::NEV; ++i) REGAT_CUDA(cudaEventCreateWithFlags(&e->ev[i], cudaEventDisableTiming));
   return REGAT_OK;
 }
@@ -572,22 +574,29 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
   return REGAT_OK;
 }
 
-// Range r of the flat gradient buffer has received its last write on the main stream.
-//   callback set (library all-reduce driven from Python): tell the data-parallel layer, it may start the all-reduce;
-//   fused train step: the `opt` stream waits for the main stream, exchanges the range over NVLink (data parallel) and --
-//   unless `defer_opt` -- runs clip + Adamax and re-derives alpha / the bf16 copies for it.
-int range_ready(Ctx& c, int r, bool defer_opt = false) {
+// Range r of the flat gradient buffer has received its last write: on the main stream and -- with side_work -- on the side
+// stream (bias sums, the geometry reduction).
+//   not fused: the side stream is joined into the main stream and the callback (library all-reduce driven from Python) is told;
+//   fused train step: nothing is joined into the main stream -- the consumers wait for both producers by event.  Data parallel:
+//   the `comm` stream exchanges the range over NVLink; then the `opt` stream runs clip + Adamax and re-derives alpha / the
+//   bf16 kernels of the range (unless defer_opt: the caller queues optimize_range later).  Exchange r+1 overlaps optimizer r.
+int range_ready(Ctx& c, int r, bool side_work, bool defer_opt = false) {
   regat_engine* e = c.e;
   const OptRange& R = e->rng[r];
-  if (R.l_last < R.l_first) return REGAT_OK;
   if (!c.fused_opt) {
-    if (e->grad_cb) e->grad_cb(e->grad_cb_user, R.lo, R.hi - R.lo);
+    if (side_work) REGAT_TRY(fork_to(e->side, c.st, e->ev[16 + r]));
+    if (e->grad_cb && R.l_last >= R.l_first) e->grad_cb(e->grad_cb_user, R.lo, R.hi - R.lo);
     return REGAT_OK;
   }
-  REGAT_TRY(fork_to(c.st, e->opt, e->ev[10 + r]));
-  if (e->dp_world > 1)
+  const bool dp = e->dp_world > 1 && R.l_last >= R.l_first;
+  cudaStream_t next = dp ? e->comm : e->opt;
+  REGAT_TRY(fork_to(c.st, next, e->ev[10 + r]));
+  if (side_work) REGAT_TRY(fork_to(e->side, next, e->ev[16 + r]));
+  if (dp) {
     REGAT_TRY(dp_allreduce_f32_impl(e->dp_grad_ptrs, e->dp_mc, e->dp_flag_ptrs, e->dp_rank, e->dp_world, R.lo, R.hi - R.lo, 0,
-                                    e->at<uint32_t>(e->hyp) + 8, e->dp_blocks, e->opt));
+                                    e->at<uint32_t>(e->hyp) + 8, e->dp_blocks, e->comm));
+    REGAT_TRY(fork_to(e->comm, e->opt, e->ev[20 + r]));
+  }
   if (!defer_opt) REGAT_TRY(optimize_range(e, r, e->opt));
   return REGAT_OK;
 }
@@ -688,8 +697,8 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   REGAT_TRY(regat_attn_bwd(dt, B, N, cf.nongt_dim, D, H, dirs, e->atv(e->Qb), e->atv(e->KVb), e->atv(e->dv1),
                            e->at<uint64_t>(e->gate), e->at<float>(e->P), e->atv(e->dQb), e->atv(e->dKVb), e->atv(e->ds), st));
   REGAT_TRY(k_colsum_multi(dt, cb_side, sd));
-  REGAT_TRY(fork_to(sd, st, e->ev[0]));   // join the side stream: BUTD + classifier gradients (the tail of the flat buffer) are final
-  REGAT_TRY(range_ready(c, 0));
+  // BUTD + classifier gradients (the tail of the flat buffer) are final once the side stream has drained
+  REGAT_TRY(range_ready(c, 0, /*side_work=*/true));
   // The bias gradients (column sums -- HBM-bound) and the small question-side products run on the side stream next to the
   // tensor-bound GEMMs of the main stream.  Gradient ranges are announced in the order they become final: attention layers,
   // then self_weights + label FC, then v2out -- the data-parallel layer starts each all-reduce behind the rest of the backward.
@@ -722,10 +731,9 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
     }
     REGAT_TRY(dense_scatter(e, st, D, dirs * D, R, e->atv(e->s), D, e->atv(e->dQb), dirs * D, gradW(e, e->l_q[0]), D, D, qo));
     REGAT_TRY(dense_scatter(e, st, D, 2 * dirs * D, Rm, e->atv(e->strunc), D, e->atv(e->dKVb), 2 * dirs * D, gradW(e, e->l_k[0]), D, D, kvo));
-    REGAT_TRY(fork_to(sd, st, e->ev[7]));
     // both attention layers: exchanged from here on; their optimizer step rewrites the bf16 kernels the two input-gradient
     // products below still read, so it is queued behind them
-    REGAT_TRY(range_ready(c, 1, /*defer_opt=*/true));
+    REGAT_TRY(range_ready(c, 1, /*side_work=*/true, /*defer_opt=*/true));
     EpiArgs ep = epi0();
     ep.accumulate = 1;                                 // ds already holds dout
     REGAT_TRY(dense(e, st, false, true, R, D, dirs * D, e->atv(e->dQb), dirs * D, lowp_at(e, e->gq_off), dirs * D, e->atv(e->ds), D, dt, ep));
@@ -748,8 +756,7 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
       REGAT_TRY(fc_dgrad(e, st, e->l_out[d], 0, Rm, D, dVd, 2 * dirs * D, e->atv(e->dstrunc), D, dt, true));
     }
     REGAT_TRY(k_colsum_multi(dt, cb_qkv, sd));
-    REGAT_TRY(fork_to(sd, st, e->ev[7]));
-    REGAT_TRY(range_ready(c, 1));                      // every product that reads these layers' kernels has been issued
+    REGAT_TRY(range_ready(c, 1, /*side_work=*/true));  // every product that reads these layers' kernels has been issued
   }
   REGAT_TRY(k_addrows(dt, e->atv(e->ds), e->atv(e->dstrunc), B, N, M, D, st));
   // self_weights: s = alpha (v0 Ws[:D] + mask (q Ws[D:])) + b.   ds is final: its column sum and the masked segment sum go to
@@ -771,14 +778,14 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   }
   // every announcement is a full join of the side stream (a data-parallel caller may end a CUDA-graph capture segment there)
   REGAT_TRY(fork_to(sd, st, e->ev[9]));
-  REGAT_TRY(range_ready(c, 2));
+  REGAT_TRY(range_ready(c, 2, /*side_work=*/false));
   // self_weights last, as ONE range: an exchange has a fixed cost of ~40 us (three launches, two cross-GPU flag rounds), so
   // the tail of the step is one such exchange, not two
   REGAT_TRY(fc_wgrad(e, st, e->l_self, 0, R, D, v0, D, e->atv(e->ds), D, false));
   REGAT_TRY(fc_wgrad(e, st, e->l_self, D, B, Q, qatt, Q, e->atv(e->dsq), D, false));
   if (dq_att) REGAT_TRY(fc_dgrad(e, st, e->l_self, D, B, Q, e->atv(e->dsq), D, dq_att, Q, REGAT_F32, false));
   (void)LS;
-  REGAT_TRY(range_ready(c, 3));                        // self_weights (kernel, g, bias) and the label FC
+  REGAT_TRY(range_ready(c, 3, /*side_work=*/false));   // self_weights (kernel, g, bias) and the label FC
   if (c.fused_opt) REGAT_TRY(fork_to(e->opt, st, e->ev[15]));      // the step is complete on the caller's stream
   return REGAT_OK;
 }
@@ -835,6 +842,7 @@ extern "C" int regat_engine_destroy(regat_engine* e) {
     for (int i = 0; i < regat_engine::NEV; ++i) if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     if (e->side) cudaStreamDestroy(e->side);
     if (e->opt) cudaStreamDestroy(e->opt);
+    if (e->comm) cudaStreamDestroy(e->comm);
     delete e;
   }
   return REGAT_OK;
