@@ -665,9 +665,10 @@ def main():
             bx = leg.devb[0]["boxes"]
             wd = _lib.wave_divisors(cfg.pos_emb_dim)
             st = torch.cuda.current_stream().cuda_stream
-            call = lambda: _lib.check(l.regat_geoattn_fwd(
-                _lib.BF16, B, N, cfg.nongt_dim, cfg.rel_dim, cfg.num_heads, cfg.dir_num, cfg.pos_emb_dim, buf("Qb"), buf("KVb"),
-                bx.data_ptr(), None, wd.ctypes.data, eng.params.data_ptr() + 4 * w0.offset,
+            assert l.regat_geoattn_fast_supported(N, cfg.nongt_dim) == 1
+            call = lambda: _lib.check(l.regat_geoattn_fwd_fast(
+                B, N, cfg.nongt_dim, cfg.rel_dim, cfg.num_heads, cfg.dir_num, cfg.pos_emb_dim, buf("Qb"), buf("KVb"),
+                bx.data_ptr(), wd.ctypes.data, eng.params.data_ptr() + 4 * w0.offset,
                 (w1.offset - w0.offset) if w1 else 0, alphas.data_ptr(), eng.params.data_ptr() + 4 * b0.offset,
                 (b1.offset - b0.offset) if b1 else 0, None, buf("s"), buf("v0"), 1 if cfg.residual else 0, buf("v1"),
                 buf("P") if training else None, buf("GB") if training else None, None, st))
@@ -685,9 +686,9 @@ def main():
             D_, H_, dirs_ = cfg.rel_dim, cfg.num_heads, cfg.dir_num
             # read Q (N D), K, V' (M D each) per direction + boxes once; write O (N D) + LSE per direction  (bf16)
             alg = B * (dirs_ * (N * D_ + 2 * M_k * D_ + N * D_) * 2 + 16 * N + dirs_ * 4 * N * H_)
-            saved = B * dirs_ * H_ * N * M_k * 4 * 2 if training else 0
-            attn_probe = {"bound": "hbm", "kernel": "geoattn_fwd_bf16_kernel (fused box geometry + graph attention forward)",
-                          "achieved": alg / (t_ms * 1e-3) / 1e9, "achieved_incl_saved_p_and_bias": (alg + saved) / (t_ms * 1e-3) / 1e9,
+            saved = B * dirs_ * H_ * N * ((M_k + 1) // 2 * 2) * 2 * 2 if training else 0     # packed bf16 P and rz
+            attn_probe = {"bound": "hbm", "kernel": "geoattn_fwd_fast_kernel (fused box geometry + graph attention forward)",
+                          "achieved": alg / (t_ms * 1e-3) / 1e9, "achieved_incl_saved_p_and_rz": (alg + saved) / (t_ms * 1e-3) / 1e9,
                           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": alg / (t_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
                           "launch_ms": t_ms, "algorithmic_bytes_per_launch": alg, "saved_for_backward_bytes": saved}
         except Exception as ex:          # the probe must never take the headline number down with it

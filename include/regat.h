@@ -189,6 +189,28 @@ REGAT_API int regat_geo_bwd_ex(int B, int N, int nongt_dim, int H, int dirs, int
                   float* dwg, int64_t dwg_stride, float* dbg, int64_t dbg_stride, float* dc,
                   int fast_math, regat_stream_t stream);
 
+/* bf16 training fast path of the three calls above (boxes given, M = min(nongt_dim, N) <= 24 keys -- every BASELINE config;
+ * regat_geoattn_fast_supported says whether a shape qualifies).  Same math, sized for bytes and instructions: SFU sin/cos/log/exp,
+ * one-pass TF32 geometry projection, bf16 mma for Q K^T and P V'.  What is kept for the backward pass is packed bf16
+ * [B][dirs*H][N][MPAD], MPAD = M rounded up to even:
+ *   save_p16  the probabilities (the very bf16 pairs that fed the P V' mma);
+ *   save_rz16 rz = 1/z where the pair_pos_fc pre-activation z is above the relu / 1e-6 clamp, else 0 (graph_att_layer.py:79-88).
+ * regat_attn_bwd_fast overwrites save_p16 in place with dz = dL * rz (dL = gradient w.r.t. the logits) and adds sum(dL) to *dc
+ * (the label constant's gradient, optional); regat_geo_bwd_fast reduces dz into dWg / dbg with recomputed embeddings.
+ * q, kv, s, v0, v1, dv1, dq, dkv, dout are bf16 with the layouts documented above. */
+REGAT_API int regat_geoattn_fast_supported(int N, int nongt_dim);
+REGAT_API int regat_geoattn_fwd_fast(int B, int N, int nongt_dim, int D, int H, int dirs, int E, const void* q, const void* kv,
+                           const float* boxes, const float* wave_div_host, const float* wg, int64_t wg_stride,
+                           const float* alpha_g, const float* bg, int64_t bg_stride, const float* label_c, const void* s,
+                           const void* v0, int residual, void* v1, void* save_p16, void* save_rz16, uint64_t* gate,
+                           regat_stream_t stream);
+REGAT_API int regat_attn_bwd_fast(int B, int N, int nongt_dim, int D, int H, int dirs, const void* q, const void* kv,
+                        const void* dv1, const uint64_t* gate, void* p16_inout_dz, const void* rz16, void* dq, void* dkv,
+                        void* dout, float* dc, regat_stream_t stream);
+REGAT_API int regat_geo_bwd_fast(int B, int N, int nongt_dim, int H, int dirs, int E, const float* boxes,
+                       const float* wave_div_host, const void* dz16, float* dwg, int64_t dwg_stride, float* dbg,
+                       int64_t dbg_stride, regat_stream_t stream);
+
 /* ------------------------------------------------------------------ BUTD pooling --------
  * fusion.py:43-54 + :34 with the (linear) v2attention FC re-associated:
  *   logit[b,n] = <v1[b,n,:], weff[b,:]> + cb[b];  att = softmax_n;  pooled[b,:] = sum_n att*v1.

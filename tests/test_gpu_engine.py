@@ -189,7 +189,9 @@ def test_cached_weight_state_follows_the_parameters(dtype, tol):
     fresh = HotPathEngine(cfg, 3, 36, dtype=dtype)
     fresh.load_params(eng.params.clone())
     want = fresh.forward(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"])
-    assert _rel(after.cpu().numpy(), want.cpu().numpy()) < 1e-5      # ||v||^2 summed in a different order only
+    # ||v||^2 is summed in a different order only: alpha differs by an ulp of fp32.  In bf16 mode that ulp flips the rounding of a
+    # few elements of bf16(alpha * v), i.e. a handful of weights move by one bf16 ulp (2^-9 relative)
+    assert _rel(after.cpu().numpy(), want.cpu().numpy()) < (1e-5 if dtype == "fp32" else 5e-3)
     assert _rel(after.cpu().numpy(), ref0) > 10 * _rel(after.cpu().numpy(), want.cpu().numpy())
     # an outside write announced with load_params / params_changed drops the caches
     eng.load_params(flat)

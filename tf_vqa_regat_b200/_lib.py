@@ -49,6 +49,10 @@ SIGNATURES = {
     "regat_attn_bwd": [i32] * 7 + [vp] * 9,
     "regat_geo_bwd": [i32] * 6 + [vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp],
     "regat_geo_bwd_ex": [i32] * 6 + [vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, i32, vp],
+    "regat_geoattn_fast_supported": [i32, i32],
+    "regat_geoattn_fwd_fast": [i32] * 7 + [vp, vp, vp, vp, vp, i64, vp, vp, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp],
+    "regat_attn_bwd_fast": [i32] * 6 + [vp] * 11,
+    "regat_geo_bwd_fast": [i32] * 6 + [vp, vp, vp, vp, i64, vp, i64, vp],
     "regat_butd_pool_fwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp],
     "regat_butd_pool_bwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp],
     "regat_pad_ragged": [i32, i32, i32, i64, vp, vp, vp, vp, vp],

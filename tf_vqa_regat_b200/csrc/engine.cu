@@ -450,6 +450,9 @@ int optimize_range(regat_engine* e, int r, cudaStream_t st) {
   return derive_weights(e, r, st);
 }
 
+// bf16 engine, M <= 24 keys: packed-bf16 fast path of the fused attention kernels (P buffer = probabilities -> dz, GB buffer = rz)
+bool attn_fast(const regat_engine* e, int N) { return e->dtype == REGAT_BF16 && regat_geoattn_fast_supported(N, e->cfg.nongt_dim) != 0; }
+
 int ensure_side(regat_engine* e) {
   if (e->side) return REGAT_OK;
   REGAT_CUDA(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
@@ -552,11 +555,17 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
     float* ag = e->at<float>(e->scal) + 8;
     for (int d = 0; d < dirs; ++d)
       REGAT_CUDA(cudaMemcpyAsync(ag + d, alphap(e, e->l_pos[d]), sizeof(float), cudaMemcpyDeviceToDevice, st));
-    REGAT_TRY(regat_geoattn_fwd(dt, B, N, cf.nongt_dim, D, H, dirs, cf.pos_emb_dim, e->atv(e->Qb), e->atv(e->KVb), c.boxes, nullptr,
-                                e->wave_div, e->params + P0.v_off, wstride, ag, e->params + P0.b_off, bstride,
-                                e->at<float>(e->scal), e->atv(e->s), v0, cf.residual, e->atv(e->v1),
-                                training ? e->at<float>(e->P) : nullptr, training ? e->at<float>(e->GB) : nullptr,
-                                training ? e->at<uint64_t>(e->gate) : nullptr, st));
+    if (attn_fast(e, N))
+      REGAT_TRY(regat_geoattn_fwd_fast(B, N, cf.nongt_dim, D, H, dirs, cf.pos_emb_dim, e->atv(e->Qb), e->atv(e->KVb), c.boxes, e->wave_div,
+                                       e->params + P0.v_off, wstride, ag, e->params + P0.b_off, bstride, e->at<float>(e->scal),
+                                       e->atv(e->s), v0, cf.residual, e->atv(e->v1), training ? e->atv(e->P) : nullptr,
+                                       training ? e->atv(e->GB) : nullptr, training ? e->at<uint64_t>(e->gate) : nullptr, st));
+    else
+      REGAT_TRY(regat_geoattn_fwd(dt, B, N, cf.nongt_dim, D, H, dirs, cf.pos_emb_dim, e->atv(e->Qb), e->atv(e->KVb), c.boxes, nullptr,
+                                  e->wave_div, e->params + P0.v_off, wstride, ag, e->params + P0.b_off, bstride,
+                                  e->at<float>(e->scal), e->atv(e->s), v0, cf.residual, e->atv(e->v1),
+                                  training ? e->at<float>(e->P) : nullptr, training ? e->at<float>(e->GB) : nullptr,
+                                  training ? e->at<uint64_t>(e->gate) : nullptr, st));
   }
   REGAT_TRY(fork_to(sd, st, e->ev[1]));   // join: weff / cb / uqe are ready
   REGAT_TRY(regat_butd_pool_fwd(dt, B, N, D, e->atv(e->v1), e->atv(e->weff), e->at<float>(e->cb), e->at<float>(e->att),
@@ -694,8 +703,12 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
     }
   }
   // attention backward: dQ, dK, dV', dout (-> ds), dL (in place of P); then the geometry reduction
-  REGAT_TRY(regat_attn_bwd(dt, B, N, cf.nongt_dim, D, H, dirs, e->atv(e->Qb), e->atv(e->KVb), e->atv(e->dv1),
-                           e->at<uint64_t>(e->gate), e->at<float>(e->P), e->atv(e->dQb), e->atv(e->dKVb), e->atv(e->ds), st));
+  if (attn_fast(e, N))
+    REGAT_TRY(regat_attn_bwd_fast(B, N, cf.nongt_dim, D, H, dirs, e->atv(e->Qb), e->atv(e->KVb), e->atv(e->dv1), e->at<uint64_t>(e->gate),
+                                  e->atv(e->P), e->atv(e->GB), e->atv(e->dQb), e->atv(e->dKVb), e->atv(e->ds), scal + 1, st));
+  else
+    REGAT_TRY(regat_attn_bwd(dt, B, N, cf.nongt_dim, D, H, dirs, e->atv(e->Qb), e->atv(e->KVb), e->atv(e->dv1),
+                             e->at<uint64_t>(e->gate), e->at<float>(e->P), e->atv(e->dQb), e->atv(e->dKVb), e->atv(e->ds), st));
   REGAT_TRY(k_colsum_multi(dt, cb_side, sd));
   // BUTD + classifier gradients (the tail of the flat buffer) are final once the side stream has drained
   REGAT_TRY(range_ready(c, 0, /*side_work=*/true));
@@ -708,9 +721,13 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
     const Layer& P0 = e->layers[e->l_pos[0]];
     const long long wstride = dirs > 1 ? e->layers[e->l_pos[1]].v_off - P0.v_off : 0;
     const long long bstride = dirs > 1 ? e->layers[e->l_pos[1]].b_off - P0.b_off : 0;
-    REGAT_TRY(regat_geo_bwd_ex(B, N, cf.nongt_dim, H, dirs, cf.pos_emb_dim, c.boxes, nullptr, e->wave_div, e->at<float>(e->P),
-                               e->at<float>(e->GB), e->grads + P0.v_off, wstride, e->grads + P0.b_off, bstride, scal + 1,
-                               dt == REGAT_BF16, sd));
+    if (attn_fast(e, N))
+      REGAT_TRY(regat_geo_bwd_fast(B, N, cf.nongt_dim, H, dirs, cf.pos_emb_dim, c.boxes, e->wave_div, e->atv(e->P), e->grads + P0.v_off,
+                                   wstride, e->grads + P0.b_off, bstride, sd));
+    else
+      REGAT_TRY(regat_geo_bwd_ex(B, N, cf.nongt_dim, H, dirs, cf.pos_emb_dim, c.boxes, nullptr, e->wave_div, e->at<float>(e->P),
+                                 e->at<float>(e->GB), e->grads + P0.v_off, wstride, e->grads + P0.b_off, bstride, scal + 1,
+                                 dt == REGAT_BF16, sd));
     const Layer& LL = e->layers[e->l_label];
     REGAT_TRY(k_label_grad(scal + 1, e->grads, LL.v_off, LL.b_off, sd));
   }

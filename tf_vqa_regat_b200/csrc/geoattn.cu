@@ -585,18 +585,48 @@ __device__ __forceinline__ uint4 ldg128(const bf16* p) {
 // word i (compile-time after unrolling) of a 128-bit register quad, without taking its address
 __device__ __forceinline__ uint32_t word(const uint4& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w)); }
 
-template <int NTS>
-__global__ void __launch_bounds__(256, 2) geoattn_fwd_bf16_kernel(const FwdParams p) {
+// SFU transcendentals without the denormal fix-up code that __expf / __logf carry when the file is not built with -ftz
+__device__ __forceinline__ float ex2_ftz(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_ftz(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_ftz(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// exact for 0 <= x < 2^20 and 1 <= d <= 4096: (x + 0.5)/d stays >= 0.5/d away from every integer, far more than the rounding
+// of the reciprocal and the product
+__device__ __forceinline__ int fdiv_small(int x, float inv_d) { return (int)(((float)x + 0.5f) * inv_d); }
+
+struct FastFwdParams {
+  int B, N, M, D, H, dirs, MP /* fp32 row stride of the bias tile in shared memory (even) */, MPAD /* bf16 row stride of P / rz */;
+  int CR /* query rows per CTA (multiple of 16, or >= N) */, residual;
+  const bf16* q; const bf16* kv; const float* boxes; WaveDiv wd;
+  const float* wg; long long wg_stride; const float* alpha_g; const float* bg; long long bg_stride; const float* label_c;
+  const bf16* s; const bf16* v0; bf16* v1;
+  bf16* save_p; bf16* save_rz; unsigned long long* gate;
+};
+
+// One CTA = one graph (all of its query rows when N <= 48, else a chunk of CR rows).
+//   phase 1  the log-bias of rows x M pairs for all heads and both directions, once, into a shared-memory tile
+//            [dirs*H][rows][MP] fp32.  A warp takes 16 consecutive pairs as one mma m-tile; lane (g, t) evaluates exactly the
+//            sin/cos its A fragments need (pairs g, g+8; wave numbers t, t+4), the 64 -> dirs*H projection is one TF32 pass.
+//            Index scramble (graph_att_layer.py:74,81) without integer division.
+//   phase 2  warp <-> head (h = warp, warp + 8, ...); per (head, 16-row tile, direction): Q K^T on mma.m16n8k16.bf16 (the
+//            128-bit global loads ARE the fragments), softmax in the C fragments, P V'.  For training the probabilities leave as
+//            the SAME packed bf16 pairs that feed the P V' mma, next to rz = 1/z (0 where the relu / 1e-6 clamp cut the
+//            gradient), which the backward kernels consume in the same fragment layout: no fp32 copies of P or of the bias.
+//   epilogue v1 = v0 + relu(s + O_0 + O_1) and the 64-bit relu gate per (row, head).
+template <int NTS, int DIRS>
+__global__ void __launch_bounds__(256, 2) geoattn_fwd_fast_kernel(const FastFwdParams p) {
   constexpr int NKS = (NTS + 1) / 2;             // 16-key k-steps of P V'
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int DH = p.dirs * p.H;
+  const int DH = DIRS * p.H;
   float4* obj = reinterpret_cast<float4*>(smem_raw);                 // [MAX_ROIS]
   float* wgs = reinterpret_cast<float*>(obj + MAX_ROIS);             // [EMB][DH] in B-fragment order
   float* bgs = wgs + EMB * DH;                                       // [DH]
   float* ags = bgs + DH;                                             // [DH]
-  float* tile = ags + DH;                                            // [DH][TS]  (TS = ROWS*MP + 4: conflict-free scatter)
-  const int tid = threadIdx.x, b = blockIdx.y, i0 = blockIdx.x * ROWS;
-  const int N = p.N, M = p.M, MP = p.MP, D = p.D, H = p.H, TS = ROWS * MP + 4;
+  float* tile = ags + DH;                                            // [DH][rows][MP]
+  const int tid = threadIdx.x, b = blockIdx.y, i0 = blockIdx.x * p.CR;
+  const int N = p.N, M = p.M, MP = p.MP, D = p.D, H = p.H;
+  const int rows = min(p.CR, N - i0);                                // query rows of this CTA
+  const int TS = rows * MP;                                          // floats per (dir, head) slice of the tile
   const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
 
   for (int n = tid; n < N; n += 256) obj[n] = box_terms(p.boxes + ((size_t)b * N + n) * 4);
@@ -613,12 +643,13 @@ __global__ void __launch_bounds__(256, 2) geoattn_fwd_bf16_kernel(const FwdParam
   }
   __syncthreads();
 
-  // ---- phase 1: log-bias of the (rows of this tile that exist) x M pairs, all heads and directions
+  // ---- phase 1
   {
-    const int npairs = min(ROWS, N - i0) * M;
+    const int npairs = rows * M;
     const float winv0 = 100.0f / p.wd.d[t], winv1 = 100.0f / p.wd.d[t + 4];
+    const float invM = 1.0f / (float)M, invN = 1.0f / (float)N;
     for (int mt = warp; mt * 16 < npairs; mt += 8) {
-      int il[2], jj[2];
+      int toff[2];
       bool inb[2];
       float mine[2];
 #pragma unroll
@@ -626,9 +657,10 @@ __global__ void __launch_bounds__(256, 2) geoattn_fwd_bf16_kernel(const FwdParam
         const int pi = mt * 16 + g + 8 * u;
         inb[u] = pi < npairs;
         const int pc = min(pi, npairs - 1);
-        il[u] = pc / M; jj[u] = pc - il[u] * M;
-        const int f = (i0 + il[u]) * M + jj[u];              // raw-reshape scramble (graph_att_layer.py:74,81)
-        const int ip = f / N, jp = f - ip * N;
+        const int il = fdiv_small(pc, invM), jj = pc - il * M;
+        toff[u] = il * MP + jj;
+        const int f = i0 * M + pc;                            // = (i0 + il) * M + jj: raw-reshape scramble (graph_att_layer.py:74,81)
+        const int ip = fdiv_small(f, invN), jp = f - ip * N;
         mine[u] = pair_log_term_fast(obj[ip], obj[jp], t);
       }
       float zc[MAX_DH / 8][4];
@@ -663,9 +695,7 @@ __global__ void __launch_bounds__(256, 2) geoattn_fwd_bf16_kernel(const FwdParam
             const int u = e >> 1, dh = 8 * nt + 2 * t + (e & 1);
             if (inb[u]) {
               const float z = fmaf(ags[dh], zc[nt][e], bgs[dh]);
-              const float gb = __logf(fmaxf(z, 1e-6f));                   // graph_att_layer.py:79,86,88
-              if (p.save_gb) p.save_gb[(((size_t)b * DH + dh) * N + i0 + il[u]) * M + jj[u]] = gb;
-              tile[dh * TS + il[u] * MP + jj[u]] = gb;
+              tile[dh * TS + toff[u]] = 0.6931471806f * lg2_ftz(fmaxf(z, 1e-6f));          // log(max(relu(z), 1e-6)), graph_att_layer.py:79,86,88
             }
           }
         }
@@ -674,164 +704,184 @@ __global__ void __launch_bounds__(256, 2) geoattn_fwd_bf16_kernel(const FwdParam
   }
   __syncthreads();
 
-  // ---- phase 2: attention.  warp <-> head; lane (g, t) in mma fragment terms
-  const bf16* Q = static_cast<const bf16*>(p.q);
-  const bf16* KV = static_cast<const bf16*>(p.kv);
-  const int ldq = p.dirs * D, ldkv = 2 * p.dirs * D;
+  // ---- phase 2
+  constexpr float LOG2E = 1.4426950409f;
+  const int ldq = DIRS * D, ldkv = 2 * DIRS * D;
   const float c_label = p.label_c ? __ldg(p.label_c) : 0.f;
-  const int r0 = i0 + g, r1 = i0 + g + 8;
-  const int r0c = min(r0, N - 1), r1c = min(r1, N - 1);
+  const float LOGMIN = -13.815510f;                       // log(1e-6): bias values at the clamp carry no gradient
+  const bf16* qg = p.q + (size_t)b * N * ldq + 8 * t;      // + row * ldq + d * D + h * HD (+ 32)
+  const bf16* kg = p.kv + (size_t)b * M * ldkv + 8 * t;    // + key * ldkv + d * D + h * HD (+ 32)
+  const bf16* vg = p.kv + (size_t)b * M * ldkv + 8 * g;    // + key * ldkv + (dirs + d) * D + h * HD
+  // key rows this lane touches (clamped once): K fragments by (nt, g), V' pieces by (ks, t)
+  int krow[NTS], vrow[NKS][4];
+#pragma unroll
+  for (int nt = 0; nt < NTS; ++nt) krow[nt] = min(nt * 8 + g, M - 1) * ldkv;
+#pragma unroll
+  for (int ks = 0; ks < NKS; ++ks) {
+    const int j = 16 * ks + 2 * t;
+    vrow[ks][0] = min(j, M - 1) * ldkv; vrow[ks][1] = min(j + 1, M - 1) * ldkv;
+    vrow[ks][2] = min(j + 8, M - 1) * ldkv; vrow[ks][3] = min(j + 9, M - 1) * ldkv;
+  }
+  const int ntiles = (rows + 15) >> 4;
 
   for (int h = warp; h < H; h += 8) {
-    float oacc[8][4];
+    for (int tl = 0; tl < ntiles; ++tl) {
+      const int lr0 = tl * 16 + g, lr1 = lr0 + 8;                       // local rows of this lane
+      const bool ok0 = lr0 < rows, ok1 = lr1 < rows;
+      const int r0 = i0 + min(lr0, rows - 1), r1 = i0 + min(lr1, rows - 1);   // clamped global rows (loads)
+      float oacc[8][4];
 #pragma unroll
-    for (int ot = 0; ot < 8; ++ot) { oacc[ot][0] = oacc[ot][1] = oacc[ot][2] = oacc[ot][3] = 0.f; }
+      for (int ot = 0; ot < 8; ++ot) { oacc[ot][0] = oacc[ot][1] = oacc[ot][2] = oacc[ot][3] = 0.f; }
 
-    for (int d = 0; d < p.dirs; ++d) {
-      const int dh = d * H + h;
-      // Q and K of this (dir, head) are requested up front (one memory round trip)
-      uint4 qw[2][2], kw[NTS][2], vw[NKS][4];
-      {
-        const bf16* qp0 = Q + ((size_t)b * N + r0c) * ldq + d * D + h * HD + 8 * t;
-        const bf16* qp1 = Q + ((size_t)b * N + r1c) * ldq + d * D + h * HD + 8 * t;
-        qw[0][0] = ldg128(qp0); qw[0][1] = ldg128(qp0 + 32);
-        qw[1][0] = ldg128(qp1); qw[1][1] = ldg128(qp1 + 32);
-        const bf16* kbase = KV + (size_t)b * M * ldkv + d * D + h * HD + 8 * t;
+#pragma unroll 1
+      for (int d = 0; d < DIRS; ++d) {
+        const int dh = d * H + h, col = d * D + h * HD;
+        uint4 qw[2][2], kw[NTS][2], vw[NKS][4];
+        {
+          const bf16* qp0 = qg + (size_t)r0 * ldq + col;
+          const bf16* qp1 = qg + (size_t)r1 * ldq + col;
+          qw[0][0] = ldg128(qp0); qw[0][1] = ldg128(qp0 + 32);
+          qw[1][0] = ldg128(qp1); qw[1][1] = ldg128(qp1 + 32);
+          const bf16* kb = kg + col;
+#pragma unroll
+          for (int nt = 0; nt < NTS; ++nt) { kw[nt][0] = ldg128(kb + krow[nt]); kw[nt][1] = ldg128(kb + krow[nt] + 32); }
+        }
+        float sacc[NTS][4];
+#pragma unroll
+        for (int nt = 0; nt < NTS; ++nt) { sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f; }
+#pragma unroll
+        for (int sst = 0; sst < 4; ++sst) {
+          const int w0 = 2 * (sst & 1);
+          const uint32_t a[4] = {word(qw[0][sst >> 1], w0), word(qw[1][sst >> 1], w0), word(qw[0][sst >> 1], w0 + 1), word(qw[1][sst >> 1], w0 + 1)};
+#pragma unroll
+          for (int nt = 0; nt < NTS; ++nt) mma_bf16(sacc[nt], a, word(kw[nt][sst >> 1], w0), word(kw[nt][sst >> 1], w0 + 1));
+        }
+        {
+          const bf16* vb = vg + (DIRS + d) * D + h * HD;
+#pragma unroll
+          for (int ks = 0; ks < NKS; ++ks) {
+            vw[ks][0] = ldg128(vb + vrow[ks][0]); vw[ks][1] = ldg128(vb + vrow[ks][1]);
+            vw[ks][2] = ldg128(vb + vrow[ks][2]); vw[ks][3] = ldg128(vb + vrow[ks][3]);
+          }
+        }
+        // logits = S/sqrt(dh) + geometry bias + label const; keys >= M masked; softmax over keys (base-2 exponent)
+        const float* trow0 = tile + dh * TS + min(lr0, rows - 1) * MP;
+        const float* trow1 = tile + dh * TS + min(lr1, rows - 1) * MP;
+        // packed-pair rows of this lane in the saved tensors: [b][dh][row][MPAD] bf16 = 32-bit words [.. * MPAD/2 + t]
+        const size_t w0i = (((size_t)b * DH + dh) * N + r0) * (p.MPAD >> 1) + t, w1i = (((size_t)b * DH + dh) * N + r1) * (p.MPAD >> 1) + t;
+        uint32_t* rzp0 = reinterpret_cast<uint32_t*>(p.save_rz) + w0i;
+        uint32_t* rzp1 = reinterpret_cast<uint32_t*>(p.save_rz) + w1i;
+        float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
         for (int nt = 0; nt < NTS; ++nt) {
-          const bf16* kp = kbase + (size_t)min(nt * 8 + g, M - 1) * ldkv;
-          kw[nt][0] = ldg128(kp); kw[nt][1] = ldg128(kp + 32);
-        }
-      }
-      // S = Q K^T: k-step s takes words (2(s&1), 2(s&1)+1) of load s>>1 from A and B alike
-      float sacc[NTS][4];
-#pragma unroll
-      for (int nt = 0; nt < NTS; ++nt) { sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f; }
-#pragma unroll
-      for (int s = 0; s < 4; ++s) {
-        const int w0 = 2 * (s & 1);
-        const uint32_t a[4] = {word(qw[0][s >> 1], w0), word(qw[1][s >> 1], w0), word(qw[0][s >> 1], w0 + 1), word(qw[1][s >> 1], w0 + 1)};
-#pragma unroll
-        for (int nt = 0; nt < NTS; ++nt) mma_bf16(sacc[nt], a, word(kw[nt][s >> 1], w0), word(kw[nt][s >> 1], w0 + 1));
-      }
-      {
-        const bf16* vbase = KV + (size_t)b * M * ldkv + (p.dirs + d) * D + h * HD + 8 * g;
-#pragma unroll
-        for (int ks = 0; ks < NKS; ++ks) {
-          const int j = 16 * ks + 2 * t;
-          vw[ks][0] = ldg128(vbase + (size_t)min(j, M - 1) * ldkv);
-          vw[ks][1] = ldg128(vbase + (size_t)min(j + 1, M - 1) * ldkv);
-          vw[ks][2] = ldg128(vbase + (size_t)min(j + 8, M - 1) * ldkv);
-          vw[ks][3] = ldg128(vbase + (size_t)min(j + 9, M - 1) * ldkv);
-        }
-      }
-      // logits = S/sqrt(dh) + geometry bias + label const; mask padded key columns; softmax over keys
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-      const float* trow = tile + dh * TS;
-#pragma unroll
-      for (int nt = 0; nt < NTS; ++nt) {
-        const int c0 = nt * 8 + 2 * t;
-        const float2 b0 = *reinterpret_cast<const float2*>(trow + g * MP + min(c0, MP - 2));
-        const float2 b1 = *reinterpret_cast<const float2*>(trow + (g + 8) * MP + min(c0, MP - 2));
-        sacc[nt][0] = c0 < M ? fmaf(sacc[nt][0], 0.125f, b0.x + c_label) : -INFINITY;
-        sacc[nt][1] = c0 + 1 < M ? fmaf(sacc[nt][1], 0.125f, b0.y + c_label) : -INFINITY;
-        sacc[nt][2] = c0 < M ? fmaf(sacc[nt][2], 0.125f, b1.x + c_label) : -INFINITY;
-        sacc[nt][3] = c0 + 1 < M ? fmaf(sacc[nt][3], 0.125f, b1.y + c_label) : -INFINITY;
-        mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
-        mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
-      }
-      mx0 = quad_max(mx0); mx1 = quad_max(mx1);
-      float sm0 = 0.f, sm1 = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < NTS; ++nt) {
-        sacc[nt][0] = __expf(sacc[nt][0] - mx0); sacc[nt][1] = __expf(sacc[nt][1] - mx0);
-        sacc[nt][2] = __expf(sacc[nt][2] - mx1); sacc[nt][3] = __expf(sacc[nt][3] - mx1);
-        sm0 += sacc[nt][0] + sacc[nt][1]; sm1 += sacc[nt][2] + sacc[nt][3];
-      }
-      const float inv0 = __fdividef(1.f, quad_sum(sm0)), inv1 = __fdividef(1.f, quad_sum(sm1));
-#pragma unroll
-      for (int nt = 0; nt < NTS; ++nt) {
-        sacc[nt][0] *= inv0; sacc[nt][1] *= inv0; sacc[nt][2] *= inv1; sacc[nt][3] *= inv1;
-        if (p.save_p) {
           const int c0 = nt * 8 + 2 * t;
-          float* pr0 = p.save_p + (((size_t)b * DH + dh) * N + r0) * M;
-          float* pr1 = p.save_p + (((size_t)b * DH + dh) * N + r1) * M;
-          if ((M & 1) == 0) {       // rows start 8-byte aligned: one 64-bit store per row
-            if (r0 < N && c0 < M) *reinterpret_cast<float2*>(pr0 + c0) = make_float2(sacc[nt][0], sacc[nt][1]);
-            if (r1 < N && c0 < M) *reinterpret_cast<float2*>(pr1 + c0) = make_float2(sacc[nt][2], sacc[nt][3]);
-          } else {
-            if (r0 < N) { if (c0 < M) pr0[c0] = sacc[nt][0]; if (c0 + 1 < M) pr0[c0 + 1] = sacc[nt][1]; }
-            if (r1 < N) { if (c0 < M) pr1[c0] = sacc[nt][2]; if (c0 + 1 < M) pr1[c0 + 1] = sacc[nt][3]; }
+          const bool v0k = c0 < M, v1k = c0 + 1 < M;
+          const int co = v0k ? c0 : 0;                           // column pairs past M re-read pair 0 of the row (values unused)
+          const float2 b0 = *reinterpret_cast<const float2*>(trow0 + co);
+          const float2 b1 = *reinterpret_cast<const float2*>(trow1 + co);
+          if (p.save_rz && v0k) {
+            // rz = d log(max(relu(z), 1e-6)) / dz = 1/z above the clamp, 0 at it (graph_att_layer.py:79-88); bias = log z
+            const float z0 = b0.x > LOGMIN ? ex2_ftz(-LOG2E * b0.x) : 0.f, z1 = (v1k && b0.y > LOGMIN) ? ex2_ftz(-LOG2E * b0.y) : 0.f;
+            const float z2 = b1.x > LOGMIN ? ex2_ftz(-LOG2E * b1.x) : 0.f, z3 = (v1k && b1.y > LOGMIN) ? ex2_ftz(-LOG2E * b1.y) : 0.f;
+            if (ok0) rzp0[4 * nt] = pack2_bf16(z0, z1);
+            if (ok1) rzp1[4 * nt] = pack2_bf16(z2, z3);
           }
+          // logits in base-2 units: (S/8 + bias + c) * log2(e)
+          sacc[nt][0] = v0k ? fmaf(sacc[nt][0], 0.125f * LOG2E, (b0.x + c_label) * LOG2E) : -INFINITY;
+          sacc[nt][1] = v1k ? fmaf(sacc[nt][1], 0.125f * LOG2E, (b0.y + c_label) * LOG2E) : -INFINITY;
+          sacc[nt][2] = v0k ? fmaf(sacc[nt][2], 0.125f * LOG2E, (b1.x + c_label) * LOG2E) : -INFINITY;
+          sacc[nt][3] = v1k ? fmaf(sacc[nt][3], 0.125f * LOG2E, (b1.y + c_label) * LOG2E) : -INFINITY;
+          mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+          mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
         }
-      }
-      // O += P V'.  k-step ks covers keys 16ks..16ks+15: the C fragments of key tiles 2ks, 2ks+1 are the A fragment.
-      // Output n-tile ot, column n stands for head-dim element 8n+ot, so the lane's 8 contiguous V' elements per key
-      // feed n-tile ot from element ot (one PRMT per register) and the lane ends up owning 16 contiguous outputs per row.
+        mx0 = quad_max(mx0); mx1 = quad_max(mx1);
+        float sm0 = 0.f, sm1 = 0.f;
 #pragma unroll
-      for (int ks = 0; ks < NKS; ++ks) {
-        uint32_t a[4];
-        a[0] = pack2_bf16(sacc[2 * ks][0], sacc[2 * ks][1]);
-        a[1] = pack2_bf16(sacc[2 * ks][2], sacc[2 * ks][3]);
-        if (2 * ks + 1 < NTS) {
-          a[2] = pack2_bf16(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1]);
-          a[3] = pack2_bf16(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3]);
-        } else {
-          a[2] = 0u; a[3] = 0u;
+        for (int nt = 0; nt < NTS; ++nt) {
+          sacc[nt][0] = ex2_ftz(sacc[nt][0] - mx0); sacc[nt][1] = ex2_ftz(sacc[nt][1] - mx0);
+          sacc[nt][2] = ex2_ftz(sacc[nt][2] - mx1); sacc[nt][3] = ex2_ftz(sacc[nt][3] - mx1);
+          sm0 += sacc[nt][0] + sacc[nt][1]; sm1 += sacc[nt][2] + sacc[nt][3];
         }
+        const float inv0 = rcp_ftz(quad_sum(sm0)), inv1 = rcp_ftz(quad_sum(sm1));
+        // P as packed bf16 pairs: A fragments of P V' and, for training, the saved probabilities
+        uint32_t pk[NTS][2];
 #pragma unroll
-        for (int ot = 0; ot < 8; ++ot) {
-          const uint32_t sel = (ot & 1) ? 0x7632u : 0x5410u;
-          const uint32_t b0 = __byte_perm(word(vw[ks][0], ot >> 1), word(vw[ks][1], ot >> 1), sel);
-          const uint32_t b1 = __byte_perm(word(vw[ks][2], ot >> 1), word(vw[ks][3], ot >> 1), sel);
-          mma_bf16(oacc[ot], a, b0, b1);
+        for (int nt = 0; nt < NTS; ++nt) {
+          pk[nt][0] = pack2_bf16(sacc[nt][0] * inv0, sacc[nt][1] * inv0);
+          pk[nt][1] = pack2_bf16(sacc[nt][2] * inv1, sacc[nt][3] * inv1);
         }
-      }
-    }  // dirs
-
-    // epilogue: lane owns head-dim elements [16t, 16t+16) of rows r0 and r1
-    const bf16* S = static_cast<const bf16*>(p.s);
-    const bf16* V0 = static_cast<const bf16*>(p.v0);
-    bf16* V1 = static_cast<bf16*>(p.v1);
+        if (p.save_p) {
+          uint32_t* pp0 = reinterpret_cast<uint32_t*>(p.save_p) + w0i;
+          uint32_t* pp1 = reinterpret_cast<uint32_t*>(p.save_p) + w1i;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      const int r = half ? r1 : r0;
-      unsigned long long bits = 0ull;
-      if (r < N) {
-        const size_t off = ((size_t)b * N + r) * D + h * HD + 16 * t;
-        const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
-        uint4 sw[2] = {zero4, zero4}, vv[2] = {zero4, zero4};
-        if (S) { sw[0] = ldg128(S + off); sw[1] = ldg128(S + off + 8); }
-        if (p.residual) { vv[0] = ldg128(V0 + off); vv[1] = ldg128(V0 + off + 8); }
-        uint32_t ow[8];
-#pragma unroll
-        for (int w = 0; w < 8; ++w) {
-          float o2[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int u = 2 * w + e;
-            const float o = oacc[u & 7][(u >> 3) + 2 * half];      // element 16t+u <- tile (u%8), col 2t + u/8
-            if (S) {
-              const uint32_t sword = word(sw[w >> 2], w & 3), vword = word(vv[w >> 2], w & 3);
-              const float x = __uint_as_float(e ? (sword & 0xffff0000u) : (sword << 16)) + o;
-              if (x > 0.f) bits |= 1ull << (16 * t + u);
-              o2[e] = __uint_as_float(e ? (vword & 0xffff0000u) : (vword << 16)) + fmaxf(x, 0.f);
-            } else {
-              o2[e] = o;
+          for (int nt = 0; nt < NTS; ++nt) {
+            if (nt * 8 + 2 * t < M) {
+              if (ok0) pp0[4 * nt] = pk[nt][0];
+              if (ok1) pp1[4 * nt] = pk[nt][1];
             }
           }
-          ow[w] = pack2_bf16(o2[0], o2[1]);
         }
-        *reinterpret_cast<uint4*>(V1 + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-        *reinterpret_cast<uint4*>(V1 + off + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+        // O += P V'.  k-step ks covers keys 16ks..16ks+15; output n-tile ot, column n <-> head-dim element 8n+ot
+#pragma unroll
+        for (int ks = 0; ks < NKS; ++ks) {
+          uint32_t a[4];
+          a[0] = pk[2 * ks][0]; a[1] = pk[2 * ks][1];
+          if (2 * ks + 1 < NTS) { a[2] = pk[2 * ks + 1][0]; a[3] = pk[2 * ks + 1][1]; } else { a[2] = 0u; a[3] = 0u; }
+#pragma unroll
+          for (int ot = 0; ot < 8; ++ot) {
+            const uint32_t sel = (ot & 1) ? 0x7632u : 0x5410u;
+            const uint32_t b0 = __byte_perm(word(vw[ks][0], ot >> 1), word(vw[ks][1], ot >> 1), sel);
+            const uint32_t b1 = __byte_perm(word(vw[ks][2], ot >> 1), word(vw[ks][3], ot >> 1), sel);
+            mma_bf16(oacc[ot], a, b0, b1);
+          }
+        }
+      }  // dirs
+
+      // epilogue: lane owns head-dim elements [16t, 16t+16) of rows r0 and r1
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const bool ok = half ? ok1 : ok0;
+        const int r = half ? r1 : r0;
+        uint32_t m16 = 0u;                                   // relu gate of this lane's 16 elements
+        if (ok) {
+          const size_t off = ((size_t)b * N + r) * D + h * HD + 16 * t;
+          const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+          uint4 sw[2] = {zero4, zero4}, vv[2] = {zero4, zero4};
+          if (p.s) { sw[0] = ldg128(p.s + off); sw[1] = ldg128(p.s + off + 8); }
+          if (p.residual) { vv[0] = ldg128(p.v0 + off); vv[1] = ldg128(p.v0 + off + 8); }
+          uint32_t ow[8];
+#pragma unroll
+          for (int w = 0; w < 8; ++w) {
+            float o2[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int u = 2 * w + e;
+              const float o = oacc[u & 7][(u >> 3) + 2 * half];      // element 16t+u <- tile (u%8), col 2t + u/8
+              if (p.s) {
+                const uint32_t sword = word(sw[w >> 2], w & 3), vword = word(vv[w >> 2], w & 3);
+                const float x = __uint_as_float(e ? (sword & 0xffff0000u) : (sword << 16)) + o;
+                m16 |= (x > 0.f) ? (1u << u) : 0u;
+                o2[e] = __uint_as_float(e ? (vword & 0xffff0000u) : (vword << 16)) + fmaxf(x, 0.f);
+              } else {
+                o2[e] = o;
+              }
+            }
+            ow[w] = pack2_bf16(o2[0], o2[1]);
+          }
+          *reinterpret_cast<uint4*>(p.v1 + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          *reinterpret_cast<uint4*>(p.v1 + off + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+        }
+        if (p.gate) {
+          // 64-bit gate word of (row, head): lane t of the quad owns bits [16t, 16t+16)
+          const uint32_t m1 = __shfl_xor_sync(0xffffffffu, m16, 1);
+          const uint32_t lo16 = (t & 1) ? m1 : m16, hi16 = (t & 1) ? m16 : m1;       // elements of lanes (t&~1) and (t|1)
+          const uint32_t half32 = lo16 | (hi16 << 16);
+          const uint32_t other = __shfl_xor_sync(0xffffffffu, half32, 2);
+          if (t == 0 && ok) reinterpret_cast<uint2*>(p.gate)[((size_t)b * N + r) * H + h] = make_uint2(half32, other);
+        }
       }
-      if (p.gate) {
-        bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
-        bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
-        if (t == 0 && r < N) p.gate[((size_t)b * N + r) * H + h] = bits;
-      }
-    }
-  }
+    }  // row tiles
+  }  // heads
 }
 
 // ==========================================================================================
@@ -840,6 +890,8 @@ struct BwdParams {
   int B, N, M, D, H, dirs, NP;       // NP = N rounded up to 16
   const void* q; const void* kv; const void* dv1; const unsigned long long* gate;
   float* p_dl; void* dq; void* dkv; void* dout;
+  // fast path (attn_bwd_bf16_kernel): probabilities and rz as packed bf16 [B][dirs*H][N][MPAD]; dz = dL * rz replaces P in place
+  bf16* p16; const bf16* rz16; int MPAD; float* dc;
 };
 constexpr int LDX = HD + 8;          // smem row stride of the Q / dO tiles (== 8 mod 32: conflict-free float2 reads)
 
@@ -1152,7 +1204,10 @@ __global__ void __launch_bounds__(128, 4) attn_bwd_bf16_kernel(const BwdParams p
   const bf16* Q = static_cast<const bf16*>(p.q);
   const bf16* KV = static_cast<const bf16*>(p.kv);
   const bf16* dV1 = static_cast<const bf16*>(p.dv1);
-  float* P_g = p.p_dl + ((size_t)b * p.dirs * H + dh) * N * M;
+  uint32_t* P_g = reinterpret_cast<uint32_t*>(p.p16 + ((size_t)b * p.dirs * H + dh) * N * p.MPAD);        // packed pairs
+  const uint32_t* RZ_g = reinterpret_cast<const uint32_t*>(p.rz16 + ((size_t)b * p.dirs * H + dh) * N * p.MPAD);
+  const int MW = p.MPAD >> 1;                 // 32-bit words per row
+  float dlsum = 0.f;                          // sum of dL over this lane's entries: the label constant's gradient
   const bf16* kbase = KV + (size_t)b * M * ldkv + d * D + h * HD;
   const bf16* vbase = KV + (size_t)b * M * ldkv + (p.dirs + d) * D + h * HD;
 
@@ -1190,17 +1245,10 @@ __global__ void __launch_bounds__(128, 4) attn_bwd_bf16_kernel(const BwdParams p
 #pragma unroll
     for (int nt = 0; nt < NTS; ++nt) {
       const int c0 = nt * 8 + 2 * t;
-      if ((M & 1) == 0) {
-        const float2 z2 = make_float2(0.f, 0.f);
-        const float2 p0 = (r0 < N && c0 < M) ? *reinterpret_cast<const float2*>(P_g + (size_t)r0 * M + c0) : z2;
-        const float2 p1 = (r1 < N && c0 < M) ? *reinterpret_cast<const float2*>(P_g + (size_t)r1 * M + c0) : z2;
-        pr[nt][0] = p0.x; pr[nt][1] = p0.y; pr[nt][2] = p1.x; pr[nt][3] = p1.y;
-      } else {
-        pr[nt][0] = (r0 < N && c0 < M) ? P_g[(size_t)r0 * M + c0] : 0.f;
-        pr[nt][1] = (r0 < N && c0 + 1 < M) ? P_g[(size_t)r0 * M + c0 + 1] : 0.f;
-        pr[nt][2] = (r1 < N && c0 < M) ? P_g[(size_t)r1 * M + c0] : 0.f;
-        pr[nt][3] = (r1 < N && c0 + 1 < M) ? P_g[(size_t)r1 * M + c0 + 1] : 0.f;
-      }
+      const bool in0 = r0 < N && c0 < M, in1 = r1 < N && c0 < M;
+      const uint32_t p0 = in0 ? P_g[r0 * MW + 4 * nt + t] : 0u, p1 = in1 ? P_g[r1 * MW + 4 * nt + t] : 0u;
+      pr[nt][0] = __uint_as_float(p0 << 16); pr[nt][1] = __uint_as_float(p0 & 0xffff0000u);
+      pr[nt][2] = __uint_as_float(p1 << 16); pr[nt][3] = __uint_as_float(p1 & 0xffff0000u);
     }
     // relu gate applied to the packed words: element e <-> bit e of the (row, head) gate word
 #pragma unroll
@@ -1234,7 +1282,15 @@ __global__ void __launch_bounds__(128, 4) attn_bwd_bf16_kernel(const BwdParams p
 #pragma unroll
       for (int nt = 0; nt < NTS; ++nt) mma_bf16(sacc[nt], a, word(vw[nt][s >> 1], w0), word(vw[nt][s >> 1], w0 + 1));
     }
-    // K row pieces for dQ = dL K: requested now, arrive during the softmax backward
+    // rz words (consumed when dz = dL * rz is written) and the K row pieces for dQ = dL K: requested now, arrive during the
+    // softmax backward
+    uint32_t zw[NTS][2];
+#pragma unroll
+    for (int nt = 0; nt < NTS; ++nt) {
+      const bool inc = nt * 8 + 2 * t < M;
+      zw[nt][0] = (inc && r0 < N) ? __ldg(RZ_g + r0 * MW + 4 * nt + t) : 0u;
+      zw[nt][1] = (inc && r1 < N) ? __ldg(RZ_g + r1 * MW + 4 * nt + t) : 0u;
+    }
 #pragma unroll
     for (int ks = 0; ks < NKS; ++ks) {
       const int j = 16 * ks + 2 * t;
@@ -1256,13 +1312,12 @@ __global__ void __launch_bounds__(128, 4) attn_bwd_bf16_kernel(const BwdParams p
       float dl[4];
       dl[0] = pr[nt][0] * (sacc[nt][0] - dl0); dl[1] = pr[nt][1] * (sacc[nt][1] - dl0);
       dl[2] = pr[nt][2] * (sacc[nt][2] - dl1); dl[3] = pr[nt][3] * (sacc[nt][3] - dl1);
-      if ((M & 1) == 0) {
-        if (r0 < N && c0 < M) *reinterpret_cast<float2*>(P_g + (size_t)r0 * M + c0) = make_float2(dl[0], dl[1]);
-        if (r1 < N && c0 < M) *reinterpret_cast<float2*>(P_g + (size_t)r1 * M + c0) = make_float2(dl[2], dl[3]);
-      } else {
-        if (r0 < N) { if (c0 < M) P_g[(size_t)r0 * M + c0] = dl[0]; if (c0 + 1 < M) P_g[(size_t)r0 * M + c0 + 1] = dl[1]; }
-        if (r1 < N) { if (c0 < M) P_g[(size_t)r1 * M + c0] = dl[2]; if (c0 + 1 < M) P_g[(size_t)r1 * M + c0 + 1] = dl[3]; }
-      }
+      dlsum += (dl[0] + dl[1]) + (dl[2] + dl[3]);
+      // dz = dL * rz (gradient w.r.t. the pair_pos_fc pre-activation) replaces P in place, same packed layout
+      if (r0 < N && c0 < M)
+        P_g[r0 * MW + 4 * nt + t] = pack2_bf16(dl[0] * __uint_as_float(zw[nt][0] << 16), dl[1] * __uint_as_float(zw[nt][0] & 0xffff0000u));
+      if (r1 < N && c0 < M)
+        P_g[r1 * MW + 4 * nt + t] = pack2_bf16(dl[2] * __uint_as_float(zw[nt][1] << 16), dl[3] * __uint_as_float(zw[nt][1] & 0xffff0000u));
       // transposed bf16 copies for phase B: tile[key][query]
       LT[(c0) * LDT + r0] = __float2bfloat16_rn(dl[0]); LT[(c0 + 1) * LDT + r0] = __float2bfloat16_rn(dl[1]);
       LT[(c0) * LDT + r1] = __float2bfloat16_rn(dl[2]); LT[(c0 + 1) * LDT + r1] = __float2bfloat16_rn(dl[3]);
@@ -1306,6 +1361,10 @@ __global__ void __launch_bounds__(128, 4) attn_bwd_bf16_kernel(const BwdParams p
         *reinterpret_cast<uint4*>(dst + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
       }
     }
+  }
+  if (p.dc) {      // d(label const) = sum dL  (zero in exact arithmetic: softmax shift invariance)
+    dlsum = warp_sum(dlsum);
+    if (lane == 0) atomicAdd(p.dc, dlsum);
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
@@ -1364,6 +1423,7 @@ struct GeoBwdParams {
   const float* boxes; const float* pos_emb; WaveDiv wd; int fast;
   const float* dl; const float* gbias;
   float* dwg; long long dwg_stride; float* dbg; long long dbg_stride; float* dc;
+  const bf16* dz16; int MPAD;      // DZ16 variant: dz = dL / z already formed by attn_bwd_bf16_kernel, packed bf16 [B][dirs*H][N][MPAD]
 };
 // One warp = one mma pipeline: per k-step it takes 8 consecutive (graph, pair) items.  D[feature, dh] += Emb^T[feature, pair] *
 // dz[pair, dh] with the 64 features as 4 m-tiles (one per geometry term c: rows g = sin, g+8 = cos of wave number g) and dh as
@@ -1371,7 +1431,7 @@ struct GeoBwdParams {
 // log-geometry terms of a k-step are computed one per lane and exchanged by shuffle.  3xTF32 keeps fp32 accuracy.
 // FAST (bf16 training mode): SFU sincos / log / exp and one TF32 pass, like the forward fast path; the fp32 parity mode
 // keeps accurate transcendentals and 3xTF32.
-template <int DH, bool FAST>
+template <int DH, bool FAST, bool DZ16 = false>
 __global__ void __launch_bounds__(256, 2) geo_bwd_kernel(const GeoBwdParams p) {
   constexpr int NTD = DH / 8;
   __shared__ float red[EMB * DH];
@@ -1416,23 +1476,43 @@ __global__ void __launch_bounds__(256, 2) geo_bwd_kernel(const GeoBwdParams p) {
     const bool vA = fA < NM, vB = fB < NM;
     const int bA = bq, bB = bq;
     // B fragments: dz = dL / z where z = exp(gbias) >= 1e-6, else 0    (d log(max(relu(z), 1e-6)) / dz)
-    const float* dlb = p.dl + (size_t)bq * DH * NM;
-    const float* gbb = p.gbias + (size_t)bq * DH * NM;
     Opnd<!FAST, 2> bz[NTD];
-    float dlA[NTD], dlB[NTD], gbA[NTD], gbB[NTD];
+    if constexpr (DZ16) {
+      // dz was formed by the attention backward kernel; pair f = i*M + j sits at row i, column j of the [N][MPAD] slice
+      const bf16* dzb = p.dz16 + (size_t)bq * DH * N * p.MPAD;
+      const float invM = 1.0f / (float)p.M;
+      const int iA = fdiv_small(min(fA, NM - 1), invM), iB = fdiv_small(min(fB, NM - 1), invM);
+      const int oA = iA * p.MPAD + (fA - iA * p.M), oB = iB * p.MPAD + (fB - iB * p.M);
+      float dzA[NTD], dzB[NTD];
 #pragma unroll
-    for (int nt = 0; nt < NTD; ++nt) {      // all loads of the k-step first
-      const int off = (8 * nt + g) * NM;
-      dlA[nt] = vA ? __ldg(dlb + off + fA) : 0.f; gbA[nt] = vA ? __ldg(gbb + off + fA) : 0.f;
-      dlB[nt] = vB ? __ldg(dlb + off + fB) : 0.f; gbB[nt] = vB ? __ldg(gbb + off + fB) : 0.f;
-    }
+      for (int nt = 0; nt < NTD; ++nt) {      // all loads of the k-step first
+        const bf16* row = dzb + (size_t)(8 * nt + g) * N * p.MPAD;
+        dzA[nt] = vA ? __bfloat162float(row[oA]) : 0.f;
+        dzB[nt] = vB ? __bfloat162float(row[oB]) : 0.f;
+      }
 #pragma unroll
-    for (int nt = 0; nt < NTD; ++nt) {
-      csum += dlA[nt] + dlB[nt];
-      const float dzA = (vA && gbA[nt] > LOGMIN) ? dlA[nt] * (FAST ? __expf(-gbA[nt]) : expf(-gbA[nt])) : 0.f;
-      const float dzB = (vB && gbB[nt] > LOGMIN) ? dlB[nt] * (FAST ? __expf(-gbB[nt]) : expf(-gbB[nt])) : 0.f;
-      bsum[nt] += dzA + dzB;
-      bz[nt].set(0, dzA); bz[nt].set(1, dzB);
+      for (int nt = 0; nt < NTD; ++nt) {
+        bsum[nt] += dzA[nt] + dzB[nt];
+        bz[nt].set(0, dzA[nt]); bz[nt].set(1, dzB[nt]);
+      }
+    } else {
+      const float* dlb = p.dl + (size_t)bq * DH * NM;
+      const float* gbb = p.gbias + (size_t)bq * DH * NM;
+      float dlA[NTD], dlB[NTD], gbA[NTD], gbB[NTD];
+#pragma unroll
+      for (int nt = 0; nt < NTD; ++nt) {      // all loads of the k-step first
+        const int off = (8 * nt + g) * NM;
+        dlA[nt] = vA ? __ldg(dlb + off + fA) : 0.f; gbA[nt] = vA ? __ldg(gbb + off + fA) : 0.f;
+        dlB[nt] = vB ? __ldg(dlb + off + fB) : 0.f; gbB[nt] = vB ? __ldg(gbb + off + fB) : 0.f;
+      }
+#pragma unroll
+      for (int nt = 0; nt < NTD; ++nt) {
+        csum += dlA[nt] + dlB[nt];
+        const float dzA = (vA && gbA[nt] > LOGMIN) ? dlA[nt] * (FAST ? __expf(-gbA[nt]) : expf(-gbA[nt])) : 0.f;
+        const float dzB = (vB && gbB[nt] > LOGMIN) ? dlB[nt] * (FAST ? __expf(-gbB[nt]) : expf(-gbB[nt])) : 0.f;
+        bsum[nt] += dzA + dzB;
+        bz[nt].set(0, dzA); bz[nt].set(1, dzB);
+      }
     }
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
@@ -1487,7 +1567,7 @@ __global__ void __launch_bounds__(256, 2) geo_bwd_kernel(const GeoBwdParams p) {
     const int d = tid / p.H, h = tid - d * p.H;
     atomicAdd(p.dbg + (size_t)d * p.dbg_stride + h, redb[tid]);
   }
-  if (tid == 0 && p.dc) atomicAdd(p.dc, redc);
+  if (!DZ16 && tid == 0 && p.dc) atomicAdd(p.dc, redc);
 }
 
 // ==========================================================================================
@@ -1531,12 +1611,19 @@ int launch_fwd(const FwdParams& p, cudaStream_t st) {
   return REGAT_OK;
 }
 
-int launch_fwd_bf16(const FwdParams& p, cudaStream_t st) {
+int launch_fwd_fast(const FastFwdParams& p, cudaStream_t st) {
   const int DH = p.dirs * p.H;
-  const size_t smem = sizeof(float4) * MAX_ROIS + sizeof(float) * ((size_t)EMB * DH + 2 * DH + (size_t)DH * (ROWS * p.MP + 4));
-  REGAT_TRY(set_smem(geoattn_fwd_bf16_kernel<3>, smem));
-  dim3 grid(ceil_div(p.N, ROWS), p.B);
-  geoattn_fwd_bf16_kernel<3><<<grid, 256, smem, st>>>(p);
+  const int rows = std::min(p.CR, p.N);
+  const size_t smem = sizeof(float4) * MAX_ROIS + sizeof(float) * ((size_t)EMB * DH + 2 * DH + (size_t)DH * rows * p.MP);
+  REGAT_REQUIRE(smem <= 227 * 1024, REGAT_ERR_UNSUPPORTED, "geoattn_fwd_fast: bias tile needs %zu B of shared memory", smem);
+  dim3 grid(ceil_div(p.N, p.CR), p.B);
+  if (p.dirs == 2) {
+    REGAT_TRY(set_smem(geoattn_fwd_fast_kernel<3, 2>, smem));
+    geoattn_fwd_fast_kernel<3, 2><<<grid, 256, smem, st>>>(p);
+  } else {
+    REGAT_TRY(set_smem(geoattn_fwd_fast_kernel<3, 1>, smem));
+    geoattn_fwd_fast_kernel<3, 1><<<grid, 256, smem, st>>>(p);
+  }
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
@@ -1550,7 +1637,7 @@ int launch_bwd_nts(const BwdParams& p, cudaStream_t st) {
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
-int launch_bwd_bf16(const BwdParams& p, cudaStream_t st) {
+int launch_bwd_fast(const BwdParams& p, cudaStream_t st) {
   constexpr int NTS = 3, NKS = 2;
   const size_t smem = sizeof(bf16) * (2 * (size_t)p.NP * (HD + 8) + 2 * (size_t)16 * NKS * (p.NP + 8));
   REGAT_TRY(set_smem(attn_bwd_bf16_kernel<NTS>, smem));
@@ -1625,8 +1712,6 @@ extern "C" int regat_geoattn_fwd(int dtype, int B, int N, int nongt_dim, int D, 
   p.s = s; p.v0 = v0; p.v1 = v1; p.save_p = save_p; p.save_gb = save_gbias;
   p.gate = reinterpret_cast<unsigned long long*>(gate);
   if (dtype == REGAT_F32) return launch_fwd<float, true>(p, (cudaStream_t)stream);
-  static const int no_fast = [] { const char* e = getenv("REGAT_ATTN_GENERIC"); return e ? atoi(e) : 0; }();
-  if (boxes && p.M <= 24 && !no_fast) return launch_fwd_bf16(p, (cudaStream_t)stream);
   return launch_fwd<bf16, false>(p, (cudaStream_t)stream);
 }
 
@@ -1643,9 +1728,8 @@ extern "C" int regat_attn_bwd(int dtype, int B, int N, int nongt_dim, int D, int
   p.NP = (N + 15) / 16 * 16;
   p.q = q; p.kv = kv; p.dv1 = dv1; p.gate = reinterpret_cast<const unsigned long long*>(gate);
   p.p_dl = p_inout_dl; p.dq = dq; p.dkv = dkv; p.dout = dout;
+  p.p16 = nullptr; p.rz16 = nullptr; p.MPAD = 0; p.dc = nullptr;
   if (dtype == REGAT_F32) return launch_bwd<float, true>(p, (cudaStream_t)stream);
-  static const int no_fast = [] { const char* e = getenv("REGAT_ATTN_GENERIC"); return e ? atoi(e) : 0; }();
-  if (p.M <= 24 && !no_fast) return launch_bwd_bf16(p, (cudaStream_t)stream);
   return launch_bwd<bf16, false>(p, (cudaStream_t)stream);
 }
 
@@ -1671,6 +1755,7 @@ extern "C" int regat_geo_bwd_ex(int B, int N, int nongt_dim, int H, int dirs, in
   p.boxes = boxes; p.pos_emb = pos_emb; p.fast = (fast_math && boxes) ? 1 : 0;
   for (int k = 0; k < 8; ++k) p.wd.d[k] = wave_div_host ? wave_div_host[k] : 1.f;
   p.dl = dl; p.gbias = gbias; p.dwg = dwg; p.dwg_stride = dwg_stride; p.dbg = dbg; p.dbg_stride = dbg_stride; p.dc = dc;
+  p.dz16 = nullptr; p.MPAD = 0;
   const int DH = dirs * H;
   const long long ksteps = ((long long)B * p.N * p.M + 7) / 8;
   const int blocks = (int)std::max<long long>(1, std::min<long long>((ksteps + 7) / 8, (long long)num_sms() * 2));
@@ -1682,6 +1767,86 @@ extern "C" int regat_geo_bwd_ex(int B, int N, int nongt_dim, int H, int dirs, in
   else if (DH == 8) REGAT_GB_CASE(8)
   else REGAT_REQUIRE(false, REGAT_ERR_UNSUPPORTED, "geo_bwd: dir_num*num_heads must be 8, 16, 24 or 32 (got %d)", DH);
 #undef REGAT_GB_CASE
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// bf16 training fast path (boxes given, M = min(nongt_dim, N) <= 24): probabilities and rz = 1/z leave the forward kernel as
+// packed bf16 [B][dirs*H][N][MPAD] (MPAD = M rounded up to even); the attention backward turns P into dz = dL * rz in place;
+// the geometry reduction consumes dz.
+extern "C" int regat_geoattn_fast_supported(int N, int nongt_dim) {
+  static const int no_fast = [] { const char* e = getenv("REGAT_ATTN_GENERIC"); return e ? atoi(e) : 0; }();
+  const int M = nongt_dim < N ? nongt_dim : N;
+  return (!no_fast && M >= 1 && M <= 24 && N <= MAX_ROIS) ? 1 : 0;
+}
+
+extern "C" int regat_geoattn_fwd_fast(int B, int N, int nongt_dim, int D, int H, int dirs, int E, const void* q, const void* kv,
+                                      const float* boxes, const float* wave_div_host, const float* wg, int64_t wg_stride,
+                                      const float* alpha_g, const float* bg, int64_t bg_stride, const float* label_c, const void* s,
+                                      const void* v0, int residual, void* v1, void* save_p16, void* save_rz16, uint64_t* gate,
+                                      regat_stream_t stream) {
+  REGAT_TRY(check_common(B, N, D, H, dirs, E));
+  REGAT_REQUIRE(q && kv && wg && alpha_g && v1 && boxes && wave_div_host, REGAT_ERR_ARG, "geoattn_fwd_fast: null pointer");
+  REGAT_REQUIRE(s || !residual, REGAT_ERR_ARG, "geoattn_fwd_fast: raw-output mode (s == NULL) has no residual");
+  REGAT_REQUIRE(!residual || v0, REGAT_ERR_ARG, "geoattn_fwd_fast: residual needs v0");
+  REGAT_REQUIRE((save_p16 != nullptr) == (save_rz16 != nullptr), REGAT_ERR_ARG, "geoattn_fwd_fast: pass both or neither of save_p16 / save_rz16");
+  REGAT_REQUIRE(aligned16(q) && aligned16(kv) && (!s || aligned16(s)) && aligned16(v1) && (!v0 || aligned16(v0)) &&
+                    (!save_p16 || (aligned16(save_p16) && aligned16(save_rz16))),
+                REGAT_ERR_ALIGN, "geoattn_fwd_fast: tensors must be 16-byte aligned");
+  REGAT_REQUIRE(regat_geoattn_fast_supported(N, nongt_dim), REGAT_ERR_UNSUPPORTED, "geoattn_fwd_fast: needs min(nongt_dim, N) <= 24");
+  FastFwdParams p;
+  p.B = B; p.N = N; p.M = nongt_dim < N ? nongt_dim : N; p.D = D; p.H = H; p.dirs = dirs;
+  p.MP = (p.M + 1) & ~1; p.MPAD = p.MP; p.residual = residual;
+  p.CR = N <= 48 ? (N + 15) / 16 * 16 : 32;
+  p.q = static_cast<const bf16*>(q); p.kv = static_cast<const bf16*>(kv); p.boxes = boxes;
+  for (int k = 0; k < 8; ++k) p.wd.d[k] = wave_div_host[k];
+  p.wg = wg; p.wg_stride = wg_stride; p.alpha_g = alpha_g; p.bg = bg; p.bg_stride = bg_stride; p.label_c = label_c;
+  p.s = static_cast<const bf16*>(s); p.v0 = static_cast<const bf16*>(v0); p.v1 = static_cast<bf16*>(v1);
+  p.save_p = static_cast<bf16*>(save_p16); p.save_rz = static_cast<bf16*>(save_rz16);
+  p.gate = reinterpret_cast<unsigned long long*>(gate);
+  return launch_fwd_fast(p, (cudaStream_t)stream);
+}
+
+extern "C" int regat_attn_bwd_fast(int B, int N, int nongt_dim, int D, int H, int dirs, const void* q, const void* kv, const void* dv1,
+                                   const uint64_t* gate, void* p16_inout_dz, const void* rz16, void* dq, void* dkv, void* dout,
+                                   float* dc, regat_stream_t stream) {
+  REGAT_TRY(check_common(B, N, D, H, dirs, EMB));
+  REGAT_REQUIRE(q && kv && dv1 && gate && p16_inout_dz && rz16 && dq && dkv && dout, REGAT_ERR_ARG, "attn_bwd_fast: null pointer");
+  REGAT_REQUIRE(aligned16(q) && aligned16(kv) && aligned16(dv1) && aligned16(dq) && aligned16(dkv) && aligned16(dout) &&
+                    aligned16(p16_inout_dz) && aligned16(rz16),
+                REGAT_ERR_ALIGN, "attn_bwd_fast: tensors must be 16-byte aligned");
+  REGAT_REQUIRE(regat_geoattn_fast_supported(N, nongt_dim), REGAT_ERR_UNSUPPORTED, "attn_bwd_fast: needs min(nongt_dim, N) <= 24");
+  BwdParams p;
+  p.B = B; p.N = N; p.M = nongt_dim < N ? nongt_dim : N; p.D = D; p.H = H; p.dirs = dirs;
+  p.NP = (N + 15) / 16 * 16;
+  p.q = q; p.kv = kv; p.dv1 = dv1; p.gate = reinterpret_cast<const unsigned long long*>(gate);
+  p.p_dl = nullptr; p.dq = dq; p.dkv = dkv; p.dout = dout;
+  p.p16 = static_cast<bf16*>(p16_inout_dz); p.rz16 = static_cast<const bf16*>(rz16); p.MPAD = (p.M + 1) & ~1; p.dc = dc;
+  return launch_bwd_fast(p, (cudaStream_t)stream);
+}
+
+extern "C" int regat_geo_bwd_fast(int B, int N, int nongt_dim, int H, int dirs, int E, const float* boxes, const float* wave_div_host,
+                                  const void* dz16, float* dwg, int64_t dwg_stride, float* dbg, int64_t dbg_stride,
+                                  regat_stream_t stream) {
+  REGAT_REQUIRE(E == EMB, REGAT_ERR_UNSUPPORTED, "geo_bwd_fast: pos_emb_dim must be 64");
+  REGAT_REQUIRE(dz16 && dwg && boxes && wave_div_host, REGAT_ERR_ARG, "geo_bwd_fast: null pointer");
+  if (B <= 0 || N <= 0) return REGAT_OK;
+  GeoBwdParams p;
+  p.B = B; p.N = N; p.M = nongt_dim < N ? nongt_dim : N; p.H = H; p.dirs = dirs;
+  p.boxes = boxes; p.pos_emb = nullptr; p.fast = 1;
+  for (int k = 0; k < 8; ++k) p.wd.d[k] = wave_div_host[k];
+  p.dl = nullptr; p.gbias = nullptr; p.dwg = dwg; p.dwg_stride = dwg_stride; p.dbg = dbg; p.dbg_stride = dbg_stride; p.dc = nullptr;
+  p.dz16 = static_cast<const bf16*>(dz16); p.MPAD = (p.M + 1) & ~1;
+  const int DH = dirs * H;
+  const long long ksteps = (long long)B * ((p.N * p.M + 7) / 8);
+  const int blocks = (int)std::max<long long>(1, std::min<long long>((ksteps + 7) / 8, (long long)num_sms() * 2));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (DH == 32) geo_bwd_kernel<32, true, true><<<blocks, 256, 0, st>>>(p);
+  else if (DH == 24) geo_bwd_kernel<24, true, true><<<blocks, 256, 0, st>>>(p);
+  else if (DH == 16) geo_bwd_kernel<16, true, true><<<blocks, 256, 0, st>>>(p);
+  else if (DH == 8) geo_bwd_kernel<8, true, true><<<blocks, 256, 0, st>>>(p);
+  else REGAT_REQUIRE(false, REGAT_ERR_UNSUPPORTED, "geo_bwd_fast: dir_num*num_heads must be 8, 16, 24 or 32 (got %d)", DH);
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
