@@ -460,7 +460,7 @@ def dp_check(leg, cfg, rank, world, dev):
         gr, pm, pmean = 0.0, 0.0, 0.0
         zero_dir = lambda n: ("implicit_relation.bias/" in n or n.endswith(".key/bias") or n in ("joint_emb.linear/bias", "joint_emb.v2attention/bias"))
         for e in eng.entries:
-            if zero_dir(e.name) or e.kind == "g":
+            if zero_dir(e.name) or e.kind == "g":   # (kind is "v" | "g" | "b")
                 continue            # g's slot in the dL/dW_eff buffer is unused; zero directions carry rounding noise only
             a, b = g_dp[e.offset:e.offset + e.numel], g_one[e.offset:e.offset + e.numel]
             gr = max(gr, float((a - b).abs().max()) / max(float(b.abs().max()), 1e-30))

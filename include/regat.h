@@ -76,6 +76,11 @@ REGAT_API int regat_last_error(char* buf, size_t n);
 REGAT_API int regat_default_config(regat_config* cfg);
 /* Number of CUDA devices visible (0 on a CPU-only box); never fails. */
 REGAT_API int regat_device_count(void);
+/* For bindings whose tensor provider exposes neither copies nor a stream (TensorFlow eager): kind 1 = host to
+ * device, 2 = device to host (both return after the copy has completed), 3 = device to device (asynchronous on `stream`);
+ * regat_device_synchronize waits for all work on the current device. */
+REGAT_API int regat_memcpy(void* dst, const void* src, int64_t bytes, int kind, regat_stream_t stream);
+REGAT_API int regat_device_synchronize(void);
 
 /* ------------------------------------------------------------------ stage 1 ----------
  * Materialised position embedding, the drop-in for

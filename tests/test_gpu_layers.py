@@ -117,3 +117,48 @@ def test_reference_error_behaviour():
     expect_mask = np.array([[1, 0, 0], [0, 0, 1]], dtype=np.float32)          # row (1,1) sums to exactly 0 -> masked
     np.testing.assert_array_equal(out[..., 8:], expect_mask[..., None] * q.cpu().numpy()[:, None, :])
     np.testing.assert_array_equal(out[..., :8], v.cpu().numpy())
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_layer_model_trains_through_the_engine(dtype):
+    """The training path behind the layer API (train.py:103-113 tapes model(...)): model.compile binds the layers' own variables
+    as the engine's parameter buffer, model.train_step runs tape + clip + Adamax, and afterwards the layer-by-layer forward,
+    the compiled forward and get_weights all show the updated weights."""
+    from tf_vqa_regat_b200.engine import HotPathEngine
+    from tf_vqa_regat_b200.model import build_hot_path, prepare_graph_variables
+    cfg = HotPathConfig(**SMALL)
+    B, N, lr = 4, 36, 2e-3
+    inp = syn.make_inputs(cfg, B, N, seed=1000, adaptive=True)
+    flat = syn.make_params(cfg, seed=7, trained_like=True)
+    dev = {k: torch.tensor(v).cuda() for k, v in inp.items() if k != "n_obj"}
+    model = build_hot_path(cfg)
+    model.load_flat(cfg, flat)
+    model.compile(cfg, B, N, dtype=dtype)
+    np.testing.assert_array_equal(model.to_flat(cfg), flat)                 # rebinding kept the values
+    geo, _, _ = prepare_graph_variables("implicit", dev["boxes"], None, None, N, cfg.nongt_dim, cfg.pos_emb_dim, 11, 15, lazy=True)
+    ref = HotPathEngine(cfg, B, N, dtype=dtype)
+    ref.load_params(flat)
+    before = model(dev["features"], dev["q_att"], dev["q_last"], geo).clone()
+    for s in range(3):
+        l = model.train_step(dev["features"], dev["q_att"], dev["q_last"], geo, dev["target"], lr, s + 1)
+        w = ref.train_step(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"], dev["target"], lr, s + 1)
+        assert abs(float(l[0]) - float(w[0])) < (2e-5 if dtype == "fp32" else 2e-3) * abs(float(w[0]))
+    # one set of weights: the layers see what the engine trained
+    got = model.to_flat(cfg)
+    dd = np.abs(got - ref.params.cpu().numpy())
+    assert dd.max() <= 2 * lr + 1e-6 and dd.mean() < 0.02 * lr
+    assert np.abs(got - flat).max() > 0.5 * lr                                # and they really moved
+    layerwise = model(dev["features"], dev["q_att"], dev["q_last"], geo)     # fp32 layer-by-layer kernels on the trained weights
+    compiled = model.predict(dev["features"], dev["q_att"], dev["q_last"], geo)
+    assert _rel(layerwise.cpu().numpy(), compiled.cpu().numpy()) < (2e-5 if dtype == "fp32" else 1e-2)
+    assert _rel(layerwise.cpu().numpy(), before.cpu().numpy()) > 1e-3
+    # set_weights through the layer API reaches the engine's derived state (alpha, bf16 kernels)
+    model.load_flat(cfg, flat)
+    again = model.predict(dev["features"], dev["q_att"], dev["q_last"], geo)
+    fresh = HotPathEngine(cfg, B, N, dtype=dtype); fresh.load_params(flat)
+    want = fresh.forward(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"])
+    assert torch.equal(again, want)
+    out = model.train_step(dev["features"], dev["q_att"], dev["q_last"], geo, dev["target"], lr, 1, want_dq=True)
+    assert out[1][0].shape == (B, cfg.q_dim) and out[1][1].shape == (B, cfg.q_dim)
+    with pytest.raises(TypeError):
+        model.predict(dev["features"], dev["q_att"], dev["q_last"], torch.zeros(B, 20, N, 64, device="cuda"))

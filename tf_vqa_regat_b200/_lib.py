@@ -41,6 +41,8 @@ SIGNATURES = {
     "regat_last_error": [C.c_char_p, C.c_size_t],
     "regat_default_config": [C.POINTER(Config)],
     "regat_device_count": [],
+    "regat_memcpy": [vp, vp, i64, i32, vp],
+    "regat_device_synchronize": [],
     "regat_position_embedding": [vp, i32, i32, i32, i32, vp, vp, vp],
     "regat_wn_prepare": [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "regat_wn_alpha": [vp, vp, i32, vp, vp, vp, vp],

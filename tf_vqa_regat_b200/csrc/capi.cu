@@ -61,6 +61,22 @@ extern "C" int regat_device_count(void) {
   return n;
 }
 
+// Host <-> device copies and a device-wide synchronisation for bindings whose tensor provider exposes neither (TensorFlow eager):
+// thin wrappers over the CUDA runtime the library links statically, so such a binding needs no other CUDA dependency.
+extern "C" int regat_memcpy(void* dst, const void* src, int64_t bytes, int kind, regat_stream_t stream) {
+  REGAT_REQUIRE(dst && src && bytes >= 0, REGAT_ERR_ARG, "memcpy: null pointer / negative size");
+  REGAT_REQUIRE(kind >= 1 && kind <= 3, REGAT_ERR_ARG, "memcpy: kind must be 1 (host to device), 2 (device to host) or 3 (device to device)");
+  if (bytes == 0) return REGAT_OK;
+  const cudaMemcpyKind k = kind == 1 ? cudaMemcpyHostToDevice : (kind == 2 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice);
+  REGAT_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, k, (cudaStream_t)stream));
+  if (kind != 3) REGAT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));      // host memory is safe to reuse / read on return
+  return REGAT_OK;
+}
+extern "C" int regat_device_synchronize(void) {
+  REGAT_CUDA(cudaDeviceSynchronize());
+  return REGAT_OK;
+}
+
 extern "C" int regat_gemm(int dtype, int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
                           void* C, int ldc, int c_dtype, const regat_epilogue* epi, regat_stream_t stream) {
   REGAT_REQUIRE(A && B && C, REGAT_ERR_ARG, "gemm: null pointer");

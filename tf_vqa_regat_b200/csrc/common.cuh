@@ -106,6 +106,12 @@ int gemm_simt(int in_dtype, int transA, int transB, int M, int N, int K, const v
 int gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
             void* C, int ldc, int c_dtype, const EpiArgs& e, int split_k, cudaStream_t st, int c_block_cols = 0,
             const long long* c_block_off = nullptr);
+struct GemmCall {
+  int transA, transB, M, N, K;
+  const void* A; int lda; const void* B; int ldb; void* C; int ldc; int c_dtype;
+  EpiArgs e;
+};
+int gemm_tc_pair(const GemmCall& c0, const GemmCall& c1, cudaStream_t st);
 bool gemm_tc_supported(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B,
                        int ldb);
 

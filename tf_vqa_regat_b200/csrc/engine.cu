@@ -751,11 +751,15 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
     // both attention layers: exchanged from here on; their optimizer step rewrites the bf16 kernels the two input-gradient
     // products below still read, so it is queued behind them
     REGAT_TRY(range_ready(c, 1, /*side_work=*/true, /*defer_opt=*/true));
-    EpiArgs ep = epi0();
-    ep.accumulate = 1;                                 // ds already holds dout
-    REGAT_TRY(dense(e, st, false, true, R, D, dirs * D, e->atv(e->dQb), dirs * D, lowp_at(e, e->gq_off), dirs * D, e->atv(e->ds), D, dt, ep));
-    REGAT_TRY(dense(e, st, false, true, Rm, D, 2 * dirs * D, e->atv(e->dKVb), 2 * dirs * D, lowp_at(e, e->gkv_off), 2 * dirs * D,
-                    e->atv(e->dstrunc), D, dt, epi0()));
+    {
+      // ds += dQ [W_q0|W_q1]^T and dstrunc = dKV [W_k0|W_k1|Kc_0|Kc_1]^T in ONE launch: 160 long tiles (K = 4 D) and 288 short ones
+      // (K = 2 D) leave no part-filled wave between them
+      ProfScope prof(e, st, R + Rm, D, (int)(((long long)R * dirs * D + (long long)Rm * 2 * dirs * D) / (R + Rm)));
+      GemmCall ckv{0, 1, Rm, D, 2 * dirs * D, e->atv(e->dKVb), 2 * dirs * D, lowp_at(e, e->gkv_off), 2 * dirs * D, e->atv(e->dstrunc), D, dt, epi0()};
+      GemmCall cq{0, 1, R, D, dirs * D, e->atv(e->dQb), dirs * D, lowp_at(e, e->gq_off), dirs * D, e->atv(e->ds), D, dt, epi0()};
+      cq.e.accumulate = 1;                             // ds already holds dout
+      REGAT_TRY(gemm_tc_pair(ckv, cq, st));
+    }
     if (c.fused_opt) {
       REGAT_TRY(fork_to(st, e->opt, e->ev[14]));
       REGAT_TRY(optimize_range(e, 1, e->opt));

@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -180,6 +181,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
          ((uint32_t)(BM >> 4) << 24);
 }
 
+// Optional second product riding in the same launch.  It shares N, ldc, the output type and the (empty) epilogue with the first
+// and differs only in what is listed here; its units follow the first problem's.
+struct TcSecond {
+  int units;                      // tiles_m * tiles_n (no split-K); 0 = absent
+  int M, tiles_m, total_k_blocks, accumulate;
+  void* C;
+};
+
 struct TcParams {
   int M, N, K, ldc, c_f32, k_blocks_per_split, total_k_blocks, atomic_out, tiles_m, tiles_n, splits;
   int c_block_cols;               // > 0: column block j = c / c_block_cols of C lives at C + c_block_off[j] (fp32 outputs only)
@@ -187,23 +196,26 @@ struct TcParams {
   long long c_block_off_or;       // OR of all block offsets (alignment test)
   void* C;
   EpiArgs e;
+  TcSecond s2;
 };
 
 // Generic per-element epilogue for ragged edges and unaligned tensors (4 consecutive columns of one row).
-__device__ __noinline__ void epi_slow(const TcParams& p, int r, int c, float4 x) {
+__device__ __noinline__ void epi_slow(const TcParams& p, void* Cout, int accumulate, int r, int c, float4 x) {
   const float xs[4] = {x.x, x.y, x.z, x.w};
+  EpiArgs e = p.e;
+  e.accumulate = accumulate;
   for (int j = 0; j < 4 && c + j < p.N; ++j) {
     if (p.atomic_out) {
       float y = xs[j];
-      if (p.e.alpha) y *= p.e.alpha[p.e.alpha_cols ? (c + j) / p.e.alpha_cols : 0];
+      if (e.alpha) y *= e.alpha[e.alpha_cols ? (c + j) / e.alpha_cols : 0];
       int cj = c + j;
       long long off = 0;
       if (p.c_block_cols) { const int jb = cj / p.c_block_cols; off = p.c_block_off[jb]; cj -= jb * p.c_block_cols; }
-      atomicAdd(static_cast<float*>(p.C) + off + (size_t)r * p.ldc + cj, y);
+      atomicAdd(static_cast<float*>(Cout) + off + (size_t)r * p.ldc + cj, y);
     } else if (p.c_f32) {
-      epi_store<float>(p.e, r, c + j, xs[j], static_cast<float*>(p.C), p.ldc);
+      epi_store<float>(e, r, c + j, xs[j], static_cast<float*>(Cout), p.ldc);
     } else {
-      epi_store<bf16>(p.e, r, c + j, xs[j], static_cast<bf16*>(p.C), p.ldc);
+      epi_store<bf16>(e, r, c + j, xs[j], static_cast<bf16*>(Cout), p.ldc);
     }
   }
 }
@@ -211,9 +223,11 @@ __device__ __noinline__ void epi_slow(const TcParams& p, int r, int c, float4 x)
 // Persistent: CTA c processes work units c, c+grid, ... where a unit = (m-tile, n-tile, k-split), n fastest so that
 // concurrently running CTAs share A rows in L2.  ACC accumulator stages in TMEM (ACC*BN <= 512 columns) let the epilogue
 // of unit i overlap the MMAs of unit i+1.
-template <int BN, int STAGES, int ACC, int EPIW, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                           const __grid_constant__ CUtensorMap mapB, const __grid_constant__ TcParams p) {
+template <int BN, int STAGES, int ACC, int EPIW, bool A_MN, bool B_MN, bool PAIR>
+__global__ void __launch_bounds__(64 + 32 * EPIW, BN == 128 ? 2 : 0) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                           const __grid_constant__ CUtensorMap mapB, const __grid_constant__ TcParams p,
+                                                           const __grid_constant__ CUtensorMap mapA2,
+                                                           const __grid_constant__ CUtensorMap mapB2) {
   constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = ACC * BN;
   static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
@@ -229,7 +243,9 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = p.tiles_n, splits = p.splits;
-  const int units = p.tiles_m * tiles_n * splits;
+  // units [0, units1) belong to the launch's first problem, [units1, units) to the optional second one (host: longer K first)
+  const int units1 = p.tiles_m * tiles_n * splits;
+  const int units = units1 + (PAIR ? p.s2.units : 0);
 
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -246,6 +262,12 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
 
   // unit -> (m0, n0, kb0, kb1)
   auto decode = [&](int u, int& m0, int& n0, int& kb0, int& kb1) {
+    if (PAIR && u >= units1) {    // second problem: no split-K
+      const int tile = u - units1;
+      const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+      m0 = tm * BM; n0 = tn * BN; kb0 = 0; kb1 = p.s2.total_k_blocks;
+      return;
+    }
     const int tile = u / splits, z = u - tile * splits;
     const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
     m0 = tm * BM; n0 = tn * BN;
@@ -262,6 +284,8 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
       for (int u = blockIdx.x; u < units; u += gridDim.x) {
         int m0, n0, kb0, kb1;
         decode(u, m0, n0, kb0, kb1);
+        const CUtensorMap* ma = (PAIR && u >= units1) ? &mapA2 : &mapA;
+        const CUtensorMap* mb = (PAIR && u >= units1) ? &mapB2 : &mapB;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + s, ph ^ 1);
           if (leader) {
@@ -269,16 +293,16 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
           unsigned char* sa = tiles + s * STAGE_BYTES;
           unsigned char* sb = sa + A_BYTES;
           if (!A_MN) {
-            tma_load_2d(sa, &mapA, full_bar + s, kb * BK, m0);
+            tma_load_2d(sa, ma, full_bar + s, kb * BK, m0);
           } else {
 #pragma unroll
-            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (64 * BK * 2), &mapA, full_bar + s, m0 + c * 64, kb * BK);
+            for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (64 * BK * 2), ma, full_bar + s, m0 + c * 64, kb * BK);
           }
           if (!B_MN) {
-            tma_load_2d(sb, &mapB, full_bar + s, kb * BK, n0);
+            tma_load_2d(sb, mb, full_bar + s, kb * BK, n0);
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (64 * BK * 2), &mapB, full_bar + s, n0 + c * 64, kb * BK);
+            for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (64 * BK * 2), mb, full_bar + s, n0 + c * 64, kb * BK);
           }
           }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
@@ -332,7 +356,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
     const int lr = lane >> 3, lc = lane & 7; // drain phase: lane handles the 16-byte column group lc of rows lr + 4 i
     const size_t esz = p.c_f32 ? 4 : 2;
     // vector path needs 16-byte aligned rows for every tensor touched with vector accesses
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.C) | ((size_t)p.ldc * esz)) & 15) == 0 &&
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.C) | (PAIR ? reinterpret_cast<uintptr_t>(p.s2.C) : 0) | ((size_t)p.ldc * esz)) & 15) == 0 &&
                         (!p.e.bias || (reinterpret_cast<uintptr_t>(p.e.bias) & 15) == 0) &&
                         (!p.e.addend || ((reinterpret_cast<uintptr_t>(p.e.addend) | ((size_t)p.e.addend_ld * 4)) & 15) == 0) &&
                         (!p.e.gate || ((reinterpret_cast<uintptr_t>(p.e.gate) | ((size_t)p.e.gate_ld * esz)) & 15) == 0) &&
@@ -343,15 +367,20 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
     for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
       int m0, n0, kb0, kb1;
       decode(u, m0, n0, kb0, kb1);
+      // the few things in which the launch's second problem differs from the first
+      const bool sec = PAIR && u >= units1;
+      const int uM = sec ? p.s2.M : p.M;
+      void* const uC = sec ? p.s2.C : p.C;
+      const int uAcc = sec ? p.s2.accumulate : p.e.accumulate;
       const int acc_stage = ui % ACC;
       // read-modify-write epilogues (bf16 C): pull the old C / gate tiles into L2 while the MMAs of this unit are still running
-      if (!p.c_f32 && (p.e.accumulate || p.e.gate)) {
+      if (!p.c_f32 && (uAcc || p.e.gate)) {
         const int et = (warp - 2) * 32 + lane;
         constexpr int LPR = BN / 64;                    // 128-byte lines per tile row
         for (int id = et; id < BM * LPR; id += 32 * EPIW) {
           const int row = m0 + id / LPR, col = n0 + (id % LPR) * 64;
-          if (row < p.M && col < p.N) {
-            if (p.e.accumulate) asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const bf16*>(p.C) + (size_t)row * p.ldc + col));
+          if (row < uM && col < p.N) {
+            if (uAcc) asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const bf16*>(uC) + (size_t)row * p.ldc + col));
             if (p.e.gate) asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const bf16*>(p.e.gate) + (size_t)row * p.e.gate_ld + col));
           }
         }
@@ -361,13 +390,13 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
       const uint32_t tmem_acc = tmem_base + (uint32_t)(acc_stage * BN) + ((uint32_t)(q * 32) << 16);
       const int rbase = m0 + q * 32;
       // 32-column blocks this warp really has to move (none if its rows or the unit's K range are empty)
-      const int nblk = (rbase < p.M && kb1 > kb0) ? min(BN / 32, (p.N - n0 + 31) / 32) : 0;
+      const int nblk = (rbase < uM && kb1 > kb0) ? min(BN / 32, (p.N - n0 + 31) / 32) : 0;
       // per-row terms of the 8 rows this lane drains, hoisted out of the column loop
       float rs[8];
       int arow[8], r2[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int r = min(rbase + lr + 4 * i, p.M - 1);
+        const int r = min(rbase + lr + 4 * i, uM - 1);
         rs[i] = (p.e.addend && p.e.row_scale) ? __ldg(p.e.row_scale + r) : 1.f;
         arow[i] = p.e.addend ? (r / p.e.addend_rows) * p.e.addend_ld : 0;
         r2[i] = -1;
@@ -393,18 +422,18 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
         }
         // bf16 outputs: the read-modify-write terms (old C for accumulate, the relu gate) are requested here too -- their
         // DRAM latency then runs under the TMEM wait and the transpose instead of stalling the drain
-        const int rcl = min(rbase + lr, p.M - 1);      // clamped first row of this lane (loads only)
+        const int rcl = min(rbase + lr, uM - 1);      // clamped first row of this lane (loads only)
         uint2 oldc[8], gt[8];
-        const bool pre_acc = vec && !p.c_f32 && p.e.accumulate, pre_gate = vec && !p.c_f32 && p.e.gate;
+        const bool pre_acc = vec && !p.c_f32 && uAcc, pre_gate = vec && !p.c_f32 && p.e.gate;
         if (pre_acc) {
-          const bf16* c0p = static_cast<const bf16*>(p.C) + c;
+          const bf16* c0p = static_cast<const bf16*>(uC) + c;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) oldc[i] = ldg_v2(c0p + (size_t)min(rcl + 4 * i, p.M - 1) * p.ldc);
+          for (int i = 0; i < 8; ++i) oldc[i] = ldg_v2(c0p + (size_t)min(rcl + 4 * i, uM - 1) * p.ldc);
         }
         if (pre_gate) {
           const bf16* g0 = static_cast<const bf16*>(p.e.gate) + c;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) gt[i] = ldg_nc_v2(g0 + (size_t)min(rcl + 4 * i, p.M - 1) * p.e.gate_ld);
+          for (int i = 0; i < 8; ++i) gt[i] = ldg_nc_v2(g0 + (size_t)min(rcl + 4 * i, uM - 1) * p.e.gate_ld);
         }
         tmem_ld32_wait(acc);
         // transpose in: lane = row, 16-byte group g lands at slot g ^ (row & 7)  (conflict-free both ways)
@@ -434,7 +463,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
 #pragma unroll 1
             for (int i = 0; i < 8; ++i) {
               const int rl = lr + 4 * i, r = rbase + rl;
-              if (r < p.M) epi_slow(p, r, c, reinterpret_cast<const float4*>(patch + rl * 32)[lc ^ (rl & 7)]);
+              if (r < uM) epi_slow(p, uC, uAcc, r, c, reinterpret_cast<const float4*>(patch + rl * 32)[lc ^ (rl & 7)]);
             }
           }
         } else {
@@ -467,18 +496,18 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
               x[i].x = fmaxf(x[i].x, 0.f); x[i].y = fmaxf(x[i].y, 0.f); x[i].z = fmaxf(x[i].z, 0.f); x[i].w = fmaxf(x[i].w, 0.f);
             }
           }
-          const int rows_ok = p.M - rbase - lr;        // row i of this lane is valid iff 4 i < rows_ok
+          const int rows_ok = uM - rbase - lr;        // row i of this lane is valid iff 4 i < rows_ok
           if (p.c_f32) {
-            float* dst0 = static_cast<float*>(p.C) + cboff + cl;
+            float* dst0 = static_cast<float*>(uC) + cboff + cl;
             if (p.atomic_out) {
 #pragma unroll
               for (int i = 0; i < 8; ++i)
                 if (4 * i < rows_ok) red_add_v4(dst0 + (size_t)(rbase + lr + 4 * i) * p.ldc, x[i]);
             } else {
-              if (p.e.accumulate) {
+              if (uAcc) {
                 float4 o[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = ldg_v4(dst0 + (size_t)min(rcl + 4 * i, p.M - 1) * p.ldc);
+                for (int i = 0; i < 8; ++i) o[i] = ldg_v4(dst0 + (size_t)min(rcl + 4 * i, uM - 1) * p.ldc);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { x[i].x += o[i].x; x[i].y += o[i].y; x[i].z += o[i].z; x[i].w += o[i].w; }
               }
@@ -486,7 +515,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
                 const float* g0 = static_cast<const float*>(p.e.gate) + c;
                 float4 g[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) g[i] = ldg_nc_v4(g0 + (size_t)min(rcl + 4 * i, p.M - 1) * p.e.gate_ld);
+                for (int i = 0; i < 8; ++i) g[i] = ldg_nc_v4(g0 + (size_t)min(rcl + 4 * i, uM - 1) * p.e.gate_ld);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                   x[i].x = g[i].x > 0.f ? x[i].x : 0.f; x[i].y = g[i].y > 0.f ? x[i].y : 0.f;
@@ -503,8 +532,8 @@ __global__ void __launch_bounds__(64 + 32 * EPIW) gemm_tc_kernel(const __grid_co
               }
             }
           } else {
-            bf16* dst0 = static_cast<bf16*>(p.C) + c;
-            if (p.e.accumulate) {
+            bf16* dst0 = static_cast<bf16*>(uC) + c;
+            if (uAcc) {
 #pragma unroll
               for (int i = 0; i < 8; ++i) { x[i].x += bf_lo(oldc[i].x); x[i].y += bf_hi(oldc[i].x); x[i].z += bf_lo(oldc[i].y); x[i].w += bf_hi(oldc[i].y); }
             }
@@ -591,43 +620,57 @@ int make_map(CUtensorMap* out, const void* base, long long inner, long long oute
 }
 
 template <int BN, int STAGES, int ACC, int EPIW>
-int launch_cfg(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int ctas, cudaStream_t st) {
+int launch_cfg(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, const CUtensorMap& ma2,
+               const CUtensorMap& mb2, int ctas, cudaStream_t st) {
+  const bool pair = p.s2.units > 0;
   constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + EPIW * EPI_PATCH_BYTES + (2 * STAGES + 2 * ACC) * 8 + 16;
+  // the shared-memory attribute is per (function, device): one flag per device, set under a lock
 #define REGAT_TC_CASE(AM, BMN)                                                                              \
+  if (pair) REGAT_TC_CASE2(AM, BMN, true) else REGAT_TC_CASE2(AM, BMN, false)
+#define REGAT_TC_CASE2(AM, BMN, PR)                                                                         \
   {                                                                                                         \
-    auto kern = gemm_tc_kernel<BN, STAGES, ACC, EPIW, AM, BMN>;                                                   \
-    static bool attr_set = false;                                                                           \
-    if (!attr_set) {                                                                                        \
-      REGAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));        \
-      attr_set = true;                                                                                      \
+    auto kern = gemm_tc_kernel<BN, STAGES, ACC, EPIW, AM, BMN, PR>;                                               \
+    static std::mutex mu;                                                                                   \
+    static bool attr_set[64] = {};                                                                          \
+    int dev = 0;                                                                                            \
+    REGAT_CUDA(cudaGetDevice(&dev));                                                                        \
+    {                                                                                                       \
+      std::lock_guard<std::mutex> lk(mu);                                                                   \
+      if (dev < 0 || dev >= 64 || !attr_set[dev]) {                                                         \
+        REGAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;                                                     \
+      }                                                                                                     \
     }                                                                                                       \
-    kern<<<ctas, 64 + 32 * EPIW, smem, st>>>(ma, mb, p);                                                          \
+    kern<<<ctas, 64 + 32 * EPIW, smem, st>>>(ma, mb, p, ma2, mb2);                                                \
   }
   if (!a_mn && b_mn) REGAT_TC_CASE(false, true)
   else if (!a_mn && !b_mn) REGAT_TC_CASE(false, false)
   else if (a_mn && b_mn) REGAT_TC_CASE(true, true)
   else REGAT_TC_CASE(true, false)
 #undef REGAT_TC_CASE
+#undef REGAT_TC_CASE2
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
 
-}  // namespace
+struct Prepared {
+  CUtensorMap ma, mb;
+  TcParams p;
+  bool a_mn, b_mn;
+  int bn;
+};
 
-bool gemm_tc_supported(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb) {
-  (void)transA; (void)transB; (void)M; (void)N; (void)K;
-  return aligned16(A) && aligned16(B) && lda % 8 == 0 && ldb % 8 == 0;
-}
-
-int gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
-            int c_dtype, const EpiArgs& e, int split_k, cudaStream_t st, int c_block_cols, const long long* c_block_off) {
-  if (M <= 0 || N <= 0) return REGAT_OK;
+// tile width, split-K and tensor maps of one problem; zeroes split-K destinations on `st`
+int prepare(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
+            int c_dtype, const EpiArgs& e, int split_k, cudaStream_t st, int c_block_cols, const long long* c_block_off, int force_bn_arg,
+            Prepared& out) {
   REGAT_REQUIRE(K > 0, REGAT_ERR_SHAPE, "gemm: K must be positive");
   REGAT_REQUIRE(gemm_tc_supported(transA, transB, M, N, K, A, lda, B, ldb), REGAT_ERR_ALIGN, "gemm_tc: unaligned operands");
   const bool a_mn = transA != 0;   // A stored [K, M]: M contiguous
   const bool b_mn = transB == 0;   // B stored [K, N]: N contiguous
   // tile width: 256 when there are enough column tiles to keep >= 1 wave busy, else 128
-  static const int force_bn = [] { const char* s = getenv("REGAT_TC_BN"); return s ? atoi(s) : 0; }();
+  static const int force_bn_env = [] { const char* s = getenv("REGAT_TC_BN"); return s ? atoi(s) : 0; }();
+  const int force_bn = force_bn_arg ? force_bn_arg : force_bn_env;
   const int tiles_m = ceil_div(M, BM);
   int bn = (force_bn == 64 || force_bn == 128 || force_bn == 256) ? force_bn : ((N >= 256 && tiles_m * ceil_div(N, 256) >= num_sms()) ? 256 : 128);
   // skinny problems (a batch-sized M, long K): the 128-wide tiling leaves most SMs idle behind a serial K loop that is
@@ -648,11 +691,11 @@ int gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int lda,
   const int kbps = ceil_div(total_kb, splits);
   splits = ceil_div(total_kb, kbps);
 
-  CUtensorMap ma, mb;
-  if (!a_mn) REGAT_TRY(make_map(&ma, A, K, M, lda, BM)); else REGAT_TRY(make_map(&ma, A, M, K, lda, BK));
-  if (!b_mn) REGAT_TRY(make_map(&mb, B, K, N, ldb, bn)); else REGAT_TRY(make_map(&mb, B, N, K, ldb, BK));
+  if (!a_mn) REGAT_TRY(make_map(&out.ma, A, K, M, lda, BM)); else REGAT_TRY(make_map(&out.ma, A, M, K, lda, BK));
+  if (!b_mn) REGAT_TRY(make_map(&out.mb, B, K, N, ldb, bn)); else REGAT_TRY(make_map(&out.mb, B, N, K, ldb, BK));
 
-  TcParams p;
+  TcParams& p = out.p;
+  memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.c_f32 = c_dtype == REGAT_F32; p.k_blocks_per_split = kbps; p.total_k_blocks = total_kb;
   p.atomic_out = splits > 1; p.C = C; p.e = e;
   p.c_block_cols = 0; p.c_block_off_or = 0;
@@ -669,14 +712,65 @@ int gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int lda,
       REGAT_CUDA(cudaMemset2DAsync(static_cast<float*>(C) + p.c_block_off[j], (size_t)ldc * 4, 0, (size_t)bw * 4, (size_t)M, st));
   }
   p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.splits = splits;
-  const int units = tiles_m * tiles_n * splits;
+  out.a_mn = a_mn; out.b_mn = b_mn; out.bn = bn;
+  return REGAT_OK;
+}
+
+int launch_prepared(const Prepared& x, const Prepared* y, cudaStream_t st) {
+  TcParams p = x.p;
+  if (y) {
+    p.s2.units = y->p.tiles_m * y->p.tiles_n; p.s2.M = y->p.M; p.s2.tiles_m = y->p.tiles_m; p.s2.total_k_blocks = y->p.total_k_blocks;
+    p.s2.accumulate = y->p.e.accumulate; p.s2.C = y->p.C;
+  }
+  const int units = p.tiles_m * p.tiles_n * p.splits + p.s2.units;
   // BN=256: 4 stages x 48 KB + 2 x 256 TMEM columns, one CTA per SM.  BN=128: 3 stages x 32 KB + 2 x 128 columns, two per SM.
   // REGAT_SM_RESERVE=n leaves n SMs free of persistent GEMM CTAs so that a concurrent NCCL all-reduce can make progress
   static const int reserve = [] { const char* s = getenv("REGAT_SM_RESERVE"); return s ? std::max(0, atoi(s)) : 0; }();
   const int sms = std::max(1, num_sms() - reserve);
-  if (bn == 256) return launch_cfg<256, 4, 2, 8>(a_mn, b_mn, ma, mb, p, std::min(units, sms), st);
-  if (bn == 64) return launch_cfg<64, 8, 2, 4>(a_mn, b_mn, ma, mb, p, std::min(units, sms), st);
-  return launch_cfg<128, 3, 2, 4>(a_mn, b_mn, ma, mb, p, std::min(units, 2 * sms), st);
+  const CUtensorMap& ma2 = y ? y->ma : x.ma;
+  const CUtensorMap& mb2 = y ? y->mb : x.mb;
+  if (x.bn == 256) return launch_cfg<256, 4, 2, 8>(x.a_mn, x.b_mn, x.ma, x.mb, p, ma2, mb2, std::min(units, sms), st);
+  if (x.bn == 64) return launch_cfg<64, 8, 2, 4>(x.a_mn, x.b_mn, x.ma, x.mb, p, ma2, mb2, std::min(units, sms), st);
+  return launch_cfg<128, 3, 2, 4>(x.a_mn, x.b_mn, x.ma, x.mb, p, ma2, mb2, std::min(units, 2 * sms), st);
+}
+
+}  // namespace
+
+bool gemm_tc_supported(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb) {
+  (void)transA; (void)transB; (void)M; (void)N; (void)K;
+  return aligned16(A) && aligned16(B) && lda % 8 == 0 && ldb % 8 == 0;
+}
+
+int gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
+            int c_dtype, const EpiArgs& e, int split_k, cudaStream_t st, int c_block_cols, const long long* c_block_off) {
+  if (M <= 0 || N <= 0) return REGAT_OK;
+  Prepared x;
+  REGAT_TRY(prepare(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, c_dtype, e, split_k, st, c_block_cols, c_block_off, 0, x));
+  return launch_prepared(x, nullptr, st);
+}
+
+// Two independent products in ONE launch: the persistent CTAs walk the units of c0, then those of c1, so a part-filled last
+// wave of one problem is topped up with tiles of the other.  Pass the problem with the longer K first.  The second problem may
+// differ from the first in M, K, its operands, its output pointer and the accumulate flag only (same N, ldc, output type, no
+// other epilogue term, no split-K); anything else falls back to two launches.
+int gemm_tc_pair(const GemmCall& c0, const GemmCall& c1, cudaStream_t st) {
+  auto single = [&](const GemmCall& c) {
+    return gemm_tc(c.transA, c.transB, c.M, c.N, c.K, c.A, c.lda, c.B, c.ldb, c.C, c.ldc, c.c_dtype, c.e, 1, st);
+  };
+  if (c0.M <= 0 || c0.N <= 0) return single(c1);
+  if (c1.M <= 0 || c1.N <= 0) return single(c0);
+  auto bare = [](EpiArgs e) { e.accumulate = 0; EpiArgs z; memset(&z, 0, sizeof(z)); return memcmp(&e, &z, sizeof(z)) == 0; };
+  static const int no_pair = [] { const char* s = getenv("REGAT_TC_PAIR"); return s ? atoi(s) == 0 : 0; }();
+  bool ok = !no_pair && c0.N == c1.N && c0.ldc == c1.ldc && c0.c_dtype == c1.c_dtype && c0.transA == c1.transA && c0.transB == c1.transB &&
+            bare(c0.e) && bare(c1.e) && c0.N % 8 == 0 && aligned16(c0.C) && aligned16(c1.C) && c0.ldc % 8 == 0;
+  Prepared x, y;
+  if (ok) {
+    REGAT_TRY(prepare(c0.transA, c0.transB, c0.M, c0.N, c0.K, c0.A, c0.lda, c0.B, c0.ldb, c0.C, c0.ldc, c0.c_dtype, c0.e, 1, st, 0, nullptr, 0, x));
+    REGAT_TRY(prepare(c1.transA, c1.transB, c1.M, c1.N, c1.K, c1.A, c1.lda, c1.B, c1.ldb, c1.C, c1.ldc, c1.c_dtype, c1.e, 1, st, 0, nullptr, x.bn, y));
+    ok = x.p.splits == 1 && y.p.splits == 1 && x.bn == y.bn && x.p.tiles_n == y.p.tiles_n;
+  }
+  if (!ok) { REGAT_TRY(single(c0)); return single(c1); }
+  return launch_prepared(x, &y, st);
 }
 
 }  // namespace regat

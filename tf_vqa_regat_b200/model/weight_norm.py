@@ -115,6 +115,21 @@ class WeightNorm(Layer):
         self._stats = self._flat[r64(n) + 64 + r64(cols):]              # [0]=sumsq [32]=alpha [64]=inv_norm
         self.built = True
 
+    def rebind(self, flat, v_off, g_off, b_off):
+        """Moves the variables into `flat` (a 1-D fp32 device buffer with the engine's layout: tensors at 64-element aligned
+        offsets), keeping their values: from now on this layer and the engine that owns `flat` share one set of weights."""
+        v, g, bias = self.v, self.g, self.bias
+        stats = torch.zeros(128, dtype=torch.float32, device=flat.device)
+        self._flat = flat[v_off:]
+        self.v = flat[v_off:v_off + v.numel()].view(v.shape)
+        self.g = flat[g_off:g_off + 1].view(())
+        self.v.copy_(v); self.g.copy_(g)
+        if bias is not None:
+            self.bias = flat[b_off:b_off + bias.numel()]
+            self.bias.copy_(bias)
+        self._g_off = g_off - v_off
+        self._stats = stats
+
     def _own_weights(self):
         if not self.built:
             return []
