@@ -216,6 +216,29 @@ REGAT_API int regat_geo_bwd_fast(int B, int N, int nongt_dim, int H, int dirs, i
                        const float* wave_div_host, const void* dz16, float* dwg, int64_t dwg_stride, float* dbg,
                        int64_t dbg_stride, regat_stream_t stream);
 
+/* ------------------------------------------------------------------ explicit relation ---------------------
+ * ExplicitRelationEncoder (relation_encoder.py:95-143) = the same GraphAttentionNetwork with pos_emb_dim = -1 (no pair_pos_fc,
+ * no geometry) and a labelled adjacency adj [B,N,N,L] (one-hot edge labels; spatial L = 11, semantic L = 15).  Per direction d
+ * (d = 1 uses adj transposed in its two object axes, graph_att_net.py:56) and restricted to the first M = min(nongt_dim, N) keys:
+ *     label_att = bias-FC(adj_d) = sum_l adj_d[..,l] * w_label[l] (+ b_label)          graph_att_net.py:71
+ *     logits    = where(sum_l adj_d > 0, Q K^T / 8, -9e15) + label_att                 graph_att_layer.py:90-102
+ * regat_explicit_pair_bias builds pair_bias [B,dirs,N,M] = label_att where the adjacency is set, -9e15 where it is not (in fp32
+ * -9e15 absorbs both the affinity and the label term, exactly as the reference's where + add does); w_label is the EFFECTIVE
+ * kernel alpha*v of the label FC [L,1].  regat_graphattn_explicit_fwd / _bwd are regat_geoattn_fwd / regat_attn_bwd with that
+ * term in place of the geometry bias (same layouts; P / dL fp32 [B,dirs,H,N,M]); masked pairs pass no gradient to Q and K,
+ * while dL still reaches the label bias: regat_explicit_pair_bias_bwd adds dw_label[l] += sum adj_d * (sum_h dL) and
+ * db_label += sum dL (caller zeroes both).                                                                              */
+REGAT_API int regat_explicit_pair_bias(int B, int N, int nongt_dim, int L, int dirs, const float* adj, const float* w_label,
+                             const float* b_label, float* pair_bias, regat_stream_t stream);
+REGAT_API int regat_explicit_pair_bias_bwd(int B, int N, int nongt_dim, int L, int dirs, int H, const float* adj, const float* dl,
+                                 float* dw_label, float* db_label, regat_stream_t stream);
+REGAT_API int regat_graphattn_explicit_fwd(int dtype, int B, int N, int nongt_dim, int D, int H, int dirs, const void* q,
+                                 const void* kv, const float* pair_bias, const void* s, const void* v0, int residual, void* v1,
+                                 float* save_p, uint64_t* gate, regat_stream_t stream);
+REGAT_API int regat_graphattn_explicit_bwd(int dtype, int B, int N, int nongt_dim, int D, int H, int dirs, const void* q,
+                                 const void* kv, const void* dv1, const uint64_t* gate, const float* pair_bias,
+                                 float* p_inout_dl, void* dq, void* dkv, void* dout, regat_stream_t stream);
+
 /* ------------------------------------------------------------------ BUTD pooling --------
  * fusion.py:43-54 + :34 with the (linear) v2attention FC re-associated:
  *   logit[b,n] = <v1[b,n,:], weff[b,:]> + cb[b];  att = softmax_n;  pooled[b,:] = sum_n att*v1.

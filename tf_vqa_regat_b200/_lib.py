@@ -55,6 +55,10 @@ SIGNATURES = {
     "regat_geoattn_fwd_fast": [i32] * 7 + [vp, vp, vp, vp, vp, i64, vp, vp, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "regat_attn_bwd_fast": [i32] * 6 + [vp] * 11,
     "regat_geo_bwd_fast": [i32] * 6 + [vp, vp, vp, vp, i64, vp, i64, vp],
+    "regat_explicit_pair_bias": [i32] * 5 + [vp, vp, vp, vp, vp],
+    "regat_explicit_pair_bias_bwd": [i32] * 6 + [vp, vp, vp, vp, vp],
+    "regat_graphattn_explicit_fwd": [i32] * 7 + [vp, vp, vp, vp, vp, i32, vp, vp, vp, vp],
+    "regat_graphattn_explicit_bwd": [i32] * 7 + [vp] * 10,
     "regat_butd_pool_fwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp],
     "regat_butd_pool_bwd": [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp],
     "regat_pad_ragged": [i32, i32, i32, i64, vp, vp, vp, vp, vp],

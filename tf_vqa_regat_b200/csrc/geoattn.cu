@@ -24,6 +24,7 @@
 //     separate pair-tiled kernel reduces dW_g/db_g with recomputed embeddings.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -235,6 +236,10 @@ struct FwdParams {
   const float* label_c;
   const void* s; const void* v0; void* v1;
   float* save_p; float* save_gb; unsigned long long* gate;
+  // explicit relation (graph_att_layer.py:90-102): per-pair additive term [B][dirs][N][M] = label bias where the adjacency is set,
+  // -9e15 where it is not (in fp32 that absorbs the affinity and the label bias exactly as where(adj > 0, aff, -9e15) + label does);
+  // replaces the geometry bias (pos_emb_dim = -1: the layer has no pair_pos_fc)
+  const float* pair_bias;
 };
 
 template <typename T, bool S3, int NTS>
@@ -249,6 +254,14 @@ __global__ void __launch_bounds__(256, 2) geoattn_fwd_kernel(const FwdParams p) 
   const int tid = threadIdx.x, b = blockIdx.y, i0 = blockIdx.x * ROWS;
   const int N = p.N, M = p.M, MP = p.MP, D = p.D, H = p.H;
 
+  if (p.pair_bias) {
+    // explicit relation: the additive term is an input, identical for all heads of a direction
+    for (int x = tid; x < DH * ROWS * M; x += 256) {
+      const int dh = x / (ROWS * M), rem = x - dh * (ROWS * M), il = rem / M, j = rem - il * M, d = dh / H;
+      const int i = min(i0 + il, N - 1);
+      tile[(dh * ROWS + il) * MP + j] = __ldg(p.pair_bias + (((size_t)b * p.dirs + d) * N + i) * M + j);
+    }
+  } else {
   // ---- phase 0: per-object terms and the pair_pos_fc weights into shared memory
   for (int n = tid; n < N; n += 256) obj[n] = p.boxes ? box_terms(p.boxes + ((size_t)b * N + n) * 4) : make_float4(1, 1, 0, 0);
   // pair_pos_fc kernels of all directions, stored in mma B-fragment order: wgs[((ks*NTD + nt)*32 + lane)*2 + r] =
@@ -342,6 +355,7 @@ __global__ void __launch_bounds__(256, 2) geoattn_fwd_kernel(const FwdParams p) 
       }
     }
   }
+  }  // geometry bias
   __syncthreads();
 
   // ---- phase 2: attention.  warp <-> head; lane (g = lane/4, t = lane%4) in mma fragment terms.
@@ -892,6 +906,9 @@ struct BwdParams {
   float* p_dl; void* dq; void* dkv; void* dout;
   // fast path (attn_bwd_bf16_kernel): probabilities and rz as packed bf16 [B][dirs*H][N][MPAD]; dz = dL * rz replaces P in place
   bf16* p16; const bf16* rz16; int MPAD; float* dc;
+  // explicit relation: the forward's per-pair term [B][dirs][N][M]; entries <= -1e15 are masked pairs, whose affinity received no
+  // gradient (tf.where in graph_att_layer.py:98) -- dL keeps flowing to the label bias, which is added after the where
+  const float* pair_bias;
 };
 constexpr int LDX = HD + 8;          // smem row stride of the Q / dO tiles (== 8 mod 32: conflict-free float2 reads)
 
@@ -1080,6 +1097,13 @@ __global__ void __launch_bounds__(128) attn_bwd_kernel(const BwdParams p) {
       } else {
         if (r0 < N) { if (c0 < M) P_g[(size_t)r0 * M + c0] = dl[0]; if (c0 + 1 < M) P_g[(size_t)r0 * M + c0 + 1] = dl[1]; }
         if (r1 < N) { if (c0 < M) P_g[(size_t)r1 * M + c0] = dl[2]; if (c0 + 1 < M) P_g[(size_t)r1 * M + c0 + 1] = dl[3]; }
+      }
+      if (p.pair_bias) {      // after the full dL went to global memory (label-bias gradient): masked pairs pass nothing to Q / K
+        const float* pb = p.pair_bias + ((size_t)b * p.dirs + d) * N * M;
+        if (!(r0 < N && c0 < M && __ldg(pb + (size_t)r0 * M + c0) > -1e15f)) dl[0] = 0.f;
+        if (!(r0 < N && c0 + 1 < M && __ldg(pb + (size_t)r0 * M + c0 + 1) > -1e15f)) dl[1] = 0.f;
+        if (!(r1 < N && c0 < M && __ldg(pb + (size_t)r1 * M + c0) > -1e15f)) dl[2] = 0.f;
+        if (!(r1 < N && c0 + 1 < M && __ldg(pb + (size_t)r1 * M + c0 + 1) > -1e15f)) dl[3] = 0.f;
       }
       if (c0 < NTS * 8) {
         *reinterpret_cast<float2*>(Ls + r0 * LDT + c0) = make_float2(dl[0], dl[1]);
@@ -1711,6 +1735,7 @@ extern "C" int regat_geoattn_fwd(int dtype, int B, int N, int nongt_dim, int D, 
   p.wg = wg; p.wg_stride = wg_stride; p.alpha_g = alpha_g; p.bg = bg; p.bg_stride = bg_stride; p.label_c = label_c;
   p.s = s; p.v0 = v0; p.v1 = v1; p.save_p = save_p; p.save_gb = save_gbias;
   p.gate = reinterpret_cast<unsigned long long*>(gate);
+  p.pair_bias = nullptr;
   if (dtype == REGAT_F32) return launch_fwd<float, true>(p, (cudaStream_t)stream);
   return launch_fwd<bf16, false>(p, (cudaStream_t)stream);
 }
@@ -1728,7 +1753,7 @@ extern "C" int regat_attn_bwd(int dtype, int B, int N, int nongt_dim, int D, int
   p.NP = (N + 15) / 16 * 16;
   p.q = q; p.kv = kv; p.dv1 = dv1; p.gate = reinterpret_cast<const unsigned long long*>(gate);
   p.p_dl = p_inout_dl; p.dq = dq; p.dkv = dkv; p.dout = dout;
-  p.p16 = nullptr; p.rz16 = nullptr; p.MPAD = 0; p.dc = nullptr;
+  p.p16 = nullptr; p.rz16 = nullptr; p.MPAD = 0; p.dc = nullptr; p.pair_bias = nullptr;
   if (dtype == REGAT_F32) return launch_bwd<float, true>(p, (cudaStream_t)stream);
   return launch_bwd<bf16, false>(p, (cudaStream_t)stream);
 }
@@ -1823,6 +1848,7 @@ extern "C" int regat_attn_bwd_fast(int B, int N, int nongt_dim, int D, int H, in
   p.q = q; p.kv = kv; p.dv1 = dv1; p.gate = reinterpret_cast<const unsigned long long*>(gate);
   p.p_dl = nullptr; p.dq = dq; p.dkv = dkv; p.dout = dout;
   p.p16 = static_cast<bf16*>(p16_inout_dz); p.rz16 = static_cast<const bf16*>(rz16); p.MPAD = (p.M + 1) & ~1; p.dc = dc;
+  p.pair_bias = nullptr;
   return launch_bwd_fast(p, (cudaStream_t)stream);
 }
 
@@ -1849,4 +1875,113 @@ extern "C" int regat_geo_bwd_fast(int B, int N, int nongt_dim, int H, int dirs, 
   else REGAT_REQUIRE(false, REGAT_ERR_UNSUPPORTED, "geo_bwd_fast: dir_num*num_heads must be 8, 16, 24 or 32 (got %d)", DH);
   REGAT_POST_LAUNCH();
   return REGAT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// explicit relation encoders (relation_encoder.py:95-143, graph_att_net.py:56-71, graph_att_layer.py:90-102)
+namespace regat {
+namespace {
+
+// pair_bias[b][d][i][j] = (sum_l adj_d[b,i,j,l] > 0) ? sum_l adj_d[b,i,j,l] w[l] + bias : -9e15,  adj_1 = adj_0 transposed in (i, j)
+__global__ void __launch_bounds__(256) explicit_pair_bias_kernel(const float* __restrict__ adj, const float* __restrict__ w,
+                                                                 const float* __restrict__ bias, int N, int M, int L, int dirs,
+                                                                 long long total, float* __restrict__ out) {
+  for (long long x = (long long)blockIdx.x * 256 + threadIdx.x; x < total; x += (long long)gridDim.x * 256) {
+    const int j = (int)(x % M), i = (int)((x / M) % N), d = (int)((x / ((long long)M * N)) % dirs);
+    const long long b = x / ((long long)M * N * dirs);
+    const float* a = adj + ((b * N + (d ? j : i)) * N + (d ? i : j)) * L;
+    float cnt = 0.f, lab = bias ? __ldg(bias) : 0.f;
+    for (int l = 0; l < L; ++l) { const float v = __ldg(a + l); cnt += v; lab = fmaf(v, __ldg(w + l), lab); }
+    out[x] = cnt > 0.f ? lab : -9e15f;
+  }
+}
+
+// dlab[b][d][i][j] = sum_h dL[b][d][h][i][j];  dw[l] += sum adj_d[b,i,j,l] dlab;  dbias += sum dlab
+__global__ void __launch_bounds__(256) explicit_pair_bias_bwd_kernel(const float* __restrict__ adj, const float* __restrict__ dl, int N, int M,
+                                                                     int L, int dirs, int H, long long total, float* dw, float* dbias) {
+  extern __shared__ float acc[];        // [L + 1]
+  for (int l = threadIdx.x; l <= L; l += 256) acc[l] = 0.f;
+  __syncthreads();
+  for (long long x = (long long)blockIdx.x * 256 + threadIdx.x; x < total; x += (long long)gridDim.x * 256) {
+    const int j = (int)(x % M), i = (int)((x / M) % N), d = (int)((x / ((long long)M * N)) % dirs);
+    const long long b = x / ((long long)M * N * dirs);
+    float g = 0.f;
+    for (int h = 0; h < H; ++h) g += __ldg(dl + ((((b * dirs + d) * H + h) * N + i) * (long long)M + j));
+    if (g != 0.f) {
+      const float* a = adj + ((b * N + (d ? j : i)) * N + (d ? i : j)) * L;
+      for (int l = 0; l < L; ++l) { const float v = __ldg(a + l); if (v != 0.f) atomicAdd(acc + l, v * g); }
+      atomicAdd(acc + L, g);
+    }
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l < L; l += 256) atomicAdd(dw + l, acc[l]);
+  if (threadIdx.x == 0 && dbias) atomicAdd(dbias, acc[L]);
+}
+
+}  // namespace
+}  // namespace regat
+
+extern "C" int regat_explicit_pair_bias(int B, int N, int nongt_dim, int L, int dirs, const float* adj, const float* w_label,
+                                        const float* b_label, float* pair_bias, regat_stream_t stream) {
+  REGAT_REQUIRE(adj && w_label && pair_bias, REGAT_ERR_ARG, "explicit_pair_bias: null pointer");
+  REGAT_REQUIRE(B >= 0 && N > 0 && L > 0 && dirs >= 1 && dirs <= 2 && nongt_dim > 0, REGAT_ERR_SHAPE, "explicit_pair_bias: bad shape");
+  if (B == 0) return REGAT_OK;
+  const int M = nongt_dim < N ? nongt_dim : N;
+  const long long total = (long long)B * dirs * N * M;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 8);
+  explicit_pair_bias_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(adj, w_label, b_label, N, M, L, dirs, total, pair_bias);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+
+extern "C" int regat_explicit_pair_bias_bwd(int B, int N, int nongt_dim, int L, int dirs, int H, const float* adj, const float* dl,
+                                            float* dw_label, float* db_label, regat_stream_t stream) {
+  REGAT_REQUIRE(adj && dl && dw_label, REGAT_ERR_ARG, "explicit_pair_bias_bwd: null pointer");
+  REGAT_REQUIRE(B >= 0 && N > 0 && L > 0 && L <= 1024 && dirs >= 1 && dirs <= 2 && H > 0, REGAT_ERR_SHAPE, "explicit_pair_bias_bwd: bad shape");
+  if (B == 0) return REGAT_OK;
+  const int M = nongt_dim < N ? nongt_dim : N;
+  const long long total = (long long)B * dirs * N * M;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)num_sms() * 2);
+  explicit_pair_bias_bwd_kernel<<<blocks, 256, (L + 1) * sizeof(float), (cudaStream_t)stream>>>(adj, dl, N, M, L, dirs, H, total, dw_label,
+                                                                                               db_label);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+
+extern "C" int regat_graphattn_explicit_fwd(int dtype, int B, int N, int nongt_dim, int D, int H, int dirs, const void* q, const void* kv,
+                                            const float* pair_bias, const void* s, const void* v0, int residual, void* v1, float* save_p,
+                                            uint64_t* gate, regat_stream_t stream) {
+  REGAT_TRY(check_common(B, N, D, H, dirs, EMB));
+  REGAT_REQUIRE(q && kv && pair_bias && v1, REGAT_ERR_ARG, "graphattn_explicit_fwd: null pointer");
+  REGAT_REQUIRE(s || !residual, REGAT_ERR_ARG, "graphattn_explicit_fwd: raw-output mode (s == NULL) has no residual");
+  REGAT_REQUIRE(!residual || v0, REGAT_ERR_ARG, "graphattn_explicit_fwd: residual needs v0");
+  REGAT_REQUIRE(aligned16(q) && aligned16(kv) && (!s || aligned16(s)) && aligned16(v1) && (!v0 || aligned16(v0)), REGAT_ERR_ALIGN,
+                "graphattn_explicit_fwd: tensors must be 16-byte aligned");
+  REGAT_REQUIRE(dtype == REGAT_F32 || dtype == REGAT_BF16, REGAT_ERR_DTYPE, "graphattn_explicit_fwd: bad dtype %d", dtype);
+  FwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.N = N; p.M = nongt_dim < N ? nongt_dim : N; p.D = D; p.H = H; p.dirs = dirs;
+  p.MP = bias_stride(p.M); p.residual = residual;
+  p.q = q; p.kv = kv; p.pair_bias = pair_bias;
+  p.s = s; p.v0 = v0; p.v1 = v1; p.save_p = save_p; p.gate = reinterpret_cast<unsigned long long*>(gate);
+  if (dtype == REGAT_F32) return launch_fwd<float, true>(p, (cudaStream_t)stream);
+  return launch_fwd<bf16, false>(p, (cudaStream_t)stream);
+}
+
+extern "C" int regat_graphattn_explicit_bwd(int dtype, int B, int N, int nongt_dim, int D, int H, int dirs, const void* q, const void* kv,
+                                            const void* dv1, const uint64_t* gate, const float* pair_bias, float* p_inout_dl, void* dq,
+                                            void* dkv, void* dout, regat_stream_t stream) {
+  REGAT_TRY(check_common(B, N, D, H, dirs, EMB));
+  REGAT_REQUIRE(q && kv && dv1 && gate && pair_bias && p_inout_dl && dq && dkv && dout, REGAT_ERR_ARG, "graphattn_explicit_bwd: null pointer");
+  REGAT_REQUIRE(aligned16(q) && aligned16(kv) && aligned16(dv1) && aligned16(dq) && aligned16(dkv) && aligned16(dout), REGAT_ERR_ALIGN,
+                "graphattn_explicit_bwd: tensors must be 16-byte aligned");
+  REGAT_REQUIRE(dtype == REGAT_F32 || dtype == REGAT_BF16, REGAT_ERR_DTYPE, "graphattn_explicit_bwd: bad dtype %d", dtype);
+  BwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.N = N; p.M = nongt_dim < N ? nongt_dim : N; p.D = D; p.H = H; p.dirs = dirs;
+  p.NP = (N + 15) / 16 * 16;
+  p.q = q; p.kv = kv; p.dv1 = dv1; p.gate = reinterpret_cast<const unsigned long long*>(gate);
+  p.p_dl = p_inout_dl; p.dq = dq; p.dkv = dkv; p.dout = dout; p.pair_bias = pair_bias;
+  if (dtype == REGAT_F32) return launch_bwd<float, true>(p, (cudaStream_t)stream);
+  return launch_bwd<bf16, false>(p, (cudaStream_t)stream);
 }

@@ -8,5 +8,5 @@ from .graph_att_layer import GraphSelfAttentionLayer  # noqa: F401
 from .graph_att_net import GraphAttentionNetwork  # noqa: F401
 from .position_emb import BoxGeometry, prepare_graph_variables  # noqa: F401
 from .rel_graph_net import ReGATHotPath, build_hot_path  # noqa: F401
-from .relation_encoder import ImplicitRelationEncoder, concat_visual_question  # noqa: F401
+from .relation_encoder import ExplicitRelationEncoder, ImplicitRelationEncoder, concat_visual_question  # noqa: F401
 from .weight_norm import WeightNorm  # noqa: F401

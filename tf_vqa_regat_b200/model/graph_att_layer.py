@@ -6,8 +6,10 @@ returns the layer's raw output [B, N, hidden] (graph_att_layer.py:121).  The ari
     because Conv2D(groups=H) reads, for head h, all `hidden` channels of block h (graph_att_layer.py:31-37,110-117);
   * the geometry bias is rebuilt on chip from boxes (BoxGeometry) or read from a materialised pos_emb, with the reference's
     raw-reshape index scramble (graph_att_layer.py:74,81);
-  * adj_mat must be the implicit relation's all-ones adjacency (relation_encoder.py:76): tf.where is then a no-op;
-    label_att must be the constant produced by the label FC on ones (graph_att_net.py:71) -- its first element is used."""
+  * implicit relation: adj_mat must be the all-ones adjacency (relation_encoder.py:76): tf.where is then a no-op; label_att
+    must be the constant produced by the label FC on ones (graph_att_net.py:71) -- its first element is used;
+  * explicit relation (pos_emb None, pos_emb_dim = -1): adj_mat [B,N,M] masks the affinities with -9e15 (:90-98) and
+    label_att [B,N,M] is added after the mask (:100)."""
 
 from .. import _lib
 from . import _rt
@@ -59,9 +61,24 @@ class GraphSelfAttentionLayer(Layer):
     def call(self, roi, adj_mat, pos_emb, label_att):
         roi = _rt.need_cuda(roi, "roi")
         B, N, D = roi.shape
-        if self.pos_emb_dim <= 0 or pos_emb is None:
-            raise NotImplementedError("GraphSelfAttentionLayer without a position embedding (explicit relations) is out of scope")
         M = self.nongt_dim if self.nongt_dim < N else N
+        if self.pos_emb_dim <= 0 or pos_emb is None:
+            # explicit relation, one direction (graph_att_layer.py:90-102): adj_mat [B,N,M] (condensed: > 0 where an edge exists),
+            # label_att [B,N,M]; masked pairs get -9e15 (which absorbs the label term in fp32 exactly as where(...) + label_att does)
+            import torch
+            adj = _rt.need_cuda(adj_mat, "adj_mat")
+            lab = _rt.need_cuda(label_att, "label_att")
+            if tuple(adj.shape) != (B, N, M) or tuple(lab.shape) != (B, N, M):
+                raise ValueError(f"adj_mat and label_att must be [batch, num_rois, nongt] = {(B, N, M)}")
+            pair_bias = torch.where(adj > 0, lab, torch.full_like(lab, -9e15)).contiguous()
+            q = _rt.empty(B * N, D, device=roi.device)
+            kv = _rt.empty(B * M, 2 * D, device=roi.device)
+            self.project(roi, q.data_ptr(), D, kv.data_ptr(), 2 * D, 0, D)
+            out = _rt.empty(B, N, D, device=roi.device)
+            _lib.check(_lib.lib().regat_graphattn_explicit_fwd(_rt.DT, B, N, self.nongt_dim, D, self.num_heads, 1, q.data_ptr(), kv.data_ptr(),
+                                                               pair_bias.data_ptr(), None, None, 0, out.data_ptr(), None, None,
+                                                               _rt.stream()))
+            return out
         q = _rt.empty(B * N, D, device=roi.device)
         kv = _rt.empty(B * M, 2 * D, device=roi.device)
         self.project(roi, q.data_ptr(), D, kv.data_ptr(), 2 * D, 0, D)

@@ -1,7 +1,10 @@
-"""GraphAttentionNetwork -- mirrors model/graph_att_net.py:12-83 (implicit relation: label_num = 1).
+"""GraphAttentionNetwork -- mirrors model/graph_att_net.py:12-83.
 
 call(v_feat, adj_mat, pos_emb) -> relu(self_weights(v_feat) + sum_d neighbor_net[d](...)) with ONE launch of the fused
-geometry-attention kernel covering every direction and head (the sum over directions and the ReLU are its epilogue)."""
+attention kernel covering every direction and head (the sum over directions and the ReLU are its epilogue).
+  implicit relation (pos_emb_dim > 0, label_num = 1): geometry bias rebuilt on chip, all-ones adjacency;
+  explicit relation (pos_emb_dim = -1, label_num = 11 / 15): adj_mat [B,N,N,label_num] masks the affinities with -9e15 and the
+  label FC adds a per-pair bias; the second direction uses the adjacency transposed in its object axes (:56)."""
 import torch
 
 from .. import _lib
@@ -39,7 +42,7 @@ class GraphAttentionNetwork(Layer):
         elif self.pos_emb_dim < 0 and pos_emb is not None:
             raise ValueError("position embedding is NOT None with pos_emb_dim < 0")                        # :47-51
         if self.pos_emb_dim < 0:
-            raise NotImplementedError("explicit-relation graphs (no position embedding) are out of scope")
+            return self._call_explicit(v_feat, adj_mat, residual)
         v_feat = _rt.need_cuda(v_feat, "v_feat")
         B, N, _ = v_feat.shape
         D, dirs, H = self.out_feat_dim, self.dir_num, self.num_heads
@@ -67,3 +70,34 @@ class GraphAttentionNetwork(Layer):
                                                 res.data_ptr() if res is not None else None, int(res is not None), out.data_ptr(),
                                                 None, None, None, _rt.stream()))
         return out                                                                 # relu(dropout(s + sum_d o_d)), :78-81
+
+    def _call_explicit(self, v_feat, adj_mat, residual):
+        """graph_att_net.py:56-81 with a labelled adjacency: per direction, input_adj = adj_d[:, :, :nongt] (:65), its sum over
+        labels is the where-mask (:69, graph_att_layer.py:90-98), the label FC on it the additive bias (:71)."""
+        v_feat = _rt.need_cuda(v_feat, "v_feat")
+        adj = _rt.need_cuda(adj_mat, "adj_mat")
+        B, N, _ = v_feat.shape
+        D, dirs, H, L = self.out_feat_dim, self.dir_num, self.num_heads, self.label_num
+        if tuple(adj.shape) != (B, N, N, L):
+            raise ValueError(f"adj_mat must be [batch, num_rois, num_rois, label_num] = {(B, N, N, L)}; got {tuple(adj.shape)}")
+        M = self.nongt_dim if self.nongt_dim < N else N
+        s = self.self_weights(v_feat)                                              # :58
+        q = _rt.empty(B * N, dirs * D, device=v_feat.device)
+        kv = _rt.empty(B * M, 2 * dirs * D, device=v_feat.device)
+        for d, net in enumerate(self.neighbor_net):
+            net.project(s, q.data_ptr() + 4 * d * D, dirs * D, kv.data_ptr(), 2 * dirs * D, d * D, (dirs + d) * D)
+        lab = self.bias.dense                                                      # WN Dense(label_num -> 1), shared by both directions
+        if not lab.built:
+            lab.build(L, v_feat.device)
+        lab.alpha_ptr()
+        w_eff = (lab.v.view(-1) * lab._stats[32]).contiguous()                     # effective kernel alpha * v  [L]
+        pair_bias = _rt.empty(B, dirs, N, M, device=v_feat.device)
+        l = _lib.lib()
+        _lib.check(l.regat_explicit_pair_bias(B, N, self.nongt_dim, L, dirs, adj.data_ptr(), w_eff.data_ptr(),
+                                              lab.bias.data_ptr() if lab.bias is not None else None, pair_bias.data_ptr(), _rt.stream()))
+        out = _rt.empty(B, N, D, device=v_feat.device)
+        res = _rt.need_cuda(residual, "residual") if residual is not None else None
+        _lib.check(l.regat_graphattn_explicit_fwd(_rt.DT, B, N, self.nongt_dim, D, H, dirs, q.data_ptr(), kv.data_ptr(), pair_bias.data_ptr(),
+                                                  s.data_ptr(), res.data_ptr() if res is not None else None, int(res is not None),
+                                                  out.data_ptr(), None, None, _rt.stream()))
+        return out

@@ -48,3 +48,59 @@ def prepare_graph_variables(relation_Type, bb, sem_adj_matrix, spa_adj_matrix, n
     if lazy:
         return BoxGeometry(_to_device_boxes(bb), nongt_dim, pos_emb_dim), None, None
     return tf_extract_position_embedding_from_boxes(bb, nongt_dim, pos_emb_dim), None, None
+
+
+def build_graph(bbox, spatial, label_num=11):
+    """Spatial relation labels of one image -- position_emb.py:23-90, vectorised (NumPy, host: it is dataset preparation).
+
+    bbox [n,4] absolute (x1,y1,x2,y2); spatial [n,6] normalised, columns 4/5 = box width/height over image width/height.
+    Returns the [n,n] label matrix of the reference: 12 on the diagonal of real boxes, 1 = j inside i, 2 = j covers i,
+    3 = IoU >= 0.5, 4..11 = direction octant of the centre offset when the centres are closer than half the image diagonal,
+    0 = no edge; boxes whose coordinates sum to 0 (padding) have no edges.  (`label_num` is accepted and unused, as there.)"""
+    bbox = np.asarray(bbox, dtype=np.float64)
+    n = bbox.shape[0]
+    x1, y1, x2, y2 = (bbox[:, k] for k in range(4))
+    w, h = x2 - x1 + 1.0, y2 - y1 + 1.0
+    image_h, image_w = h[0] / spatial[0, -1], w[0] / spatial[0, -2]
+    cx, cy = 0.5 * (x1 + x2), 0.5 * (y1 + y2)
+    half_diag = 0.5 * np.sqrt(image_h ** 2 + image_w ** 2)
+    real = bbox.sum(1) != 0
+    I, J = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    pair = real[I] & real[J] & (I < J)                               # the reference fills (i,j) and (j,i) from the i < j visit
+    inside = (x1[I] < x1[J]) & (x2[I] > x2[J]) & (y1[I] < y1[J]) & (y2[I] > y2[J])       # j inside i
+    cover = (x1[J] < x1[I]) & (x2[J] > x2[I]) & (y1[J] < y1[I]) & (y2[J] > y2[I])        # j covers i
+    iw = np.maximum(0.0, np.minimum(x2[I], x2[J]) - np.maximum(x1[I], x1[J]) + 1)
+    ih = np.maximum(0.0, np.minimum(y2[I], y2[J]) - np.maximum(y1[I], y1[J]) + 1)
+    inter = iw * ih
+    iou = inter / (w[I] * h[I] + w[J] * h[J] - inter)
+    yd, xd = cy[I] - cy[J], cx[I] - cx[J]
+    diag = np.sqrt(yd ** 2 + xd ** 2)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        sin_ij, cos_ij = yd / diag, xd / diag
+        q1, q4 = (sin_ij >= 0) & (cos_ij >= 0), (sin_ij < 0) & (cos_ij >= 0)
+        q2 = (sin_ij >= 0) & (cos_ij < 0)
+        asin, acos_c, acos_s = np.arcsin(np.clip(sin_ij, -1, 1)), np.arccos(np.clip(cos_ij, -1, 1)), np.arccos(np.clip(sin_ij, -1, 1))
+        two_pi = 2 * np.pi
+        label_i = np.where(q1, asin, np.where(q4, asin + two_pi, np.where(q2, acos_c, -acos_s + two_pi)))
+        label_j = np.where(q1 | q2, two_pi - label_i, label_i - np.pi)
+        oct_i = np.ceil(label_i / (np.pi / 4)).astype(np.int64) + 3
+        oct_j = np.ceil(label_j / (np.pi / 4)).astype(np.int64) + 3
+    rest = pair & ~inside & ~cover
+    near = rest & (iou < 0.5) & (diag < half_diag)
+    upper = np.where(pair & inside, 1, np.where(pair & cover & ~inside, 2, np.where(rest & (iou >= 0.5), 3, np.where(near, oct_i, 0))))
+    lower = np.where(pair & inside, 2, np.where(pair & cover & ~inside, 1, np.where(rest & (iou >= 0.5), 3, np.where(near, oct_j, 0))))
+    adj = (upper + lower.T).astype(np.float64)
+    adj[np.arange(n)[real], np.arange(n)[real]] = 12
+    return adj
+
+
+def one_hot_adjacency(adj_labels, label_num):
+    """[.., n, n] integer labels (0 = no edge) -> [.., n, n, label_num] one-hot on label - 1, the [B,N,N,label_num] adjacency that
+    ExplicitRelationEncoder.call consumes (relation_encoder.py:124; the reference's own tf_broadcast_adj_matrix is an empty stub,
+    position_emb.py:92-93).  Labels above label_num (the diagonal's 12 when label_num = 11) are dropped, as in the original ReGAT."""
+    a = np.asarray(adj_labels).astype(np.int64)
+    out = np.zeros(a.shape + (label_num,), dtype=np.float32)
+    ok = (a > 0) & (a <= label_num)
+    idx = np.nonzero(ok)
+    out[idx + (a[ok] - 1,)] = 1.0
+    return out

@@ -74,3 +74,42 @@ def unflatten(cfg: HotPathConfig, flat: np.ndarray) -> dict:
     for e in param_layout(cfg)[0]:
         out[e.name] = flat[e.offset:e.offset + e.numel].reshape(e.shape)
     return out
+
+
+# ---- explicit relation encoders: seeded inputs and weights shared by the golden generator, the oracle and the tests
+def make_explicit_inputs(v_dim, q_dim, label_num, B, N, seed):
+    """visual >= 0 with zero rows for padded objects, question, and a one-hot labelled adjacency [B,N,N,L] in which padded objects
+    have no edges at all (rows AND columns empty: their softmax rows are fully masked) and ~40 % of the real pairs are linked."""
+    rng = np.random.default_rng(seed)
+    visual = np.maximum(rng.standard_normal((B, N, v_dim)), 0.0)
+    question = 0.5 * rng.standard_normal((B, q_dim))
+    n_obj = rng.integers(max(2, N // 2), N + 1, size=B)
+    n_obj[0] = N
+    adj = np.zeros((B, N, N, label_num))
+    for b in range(B):
+        visual[b, n_obj[b]:] = 0.0
+        for i in range(n_obj[b]):
+            for j in range(n_obj[b]):
+                if i == j or rng.random() < 0.4:
+                    adj[b, i, j, rng.integers(0, label_num)] = 1.0
+    return visual, question, adj, n_obj
+
+
+def explicit_param_values(shapes, seed):
+    """Trained-like values for a list of variable shapes in Keras order (v, g, [bias] per WeightNorm): v Glorot-uniform, g = ||v|| times
+    U(0.7, 1.4), bias 0.1 N(0,1).  float64; the same call rebuilds the parameters the golden generator assigned."""
+    rng = np.random.default_rng(seed)
+    out, last_norm = [], 1.0
+    for shp in shapes:
+        shp = tuple(int(x) for x in shp)
+        if len(shp) >= 2:
+            fan_in, fan_out = (shp[2], shp[3]) if len(shp) == 4 else (shp[0], shp[1])
+            lim = np.sqrt(6.0 / (fan_in + fan_out))
+            v = rng.uniform(-lim, lim, shp)
+            last_norm = float(np.sqrt((v * v).sum()))
+            out.append(v)
+        elif len(shp) == 0:
+            out.append(np.asarray(last_norm * rng.uniform(0.7, 1.4)))
+        else:
+            out.append(0.1 * rng.standard_normal(shp))
+    return out
