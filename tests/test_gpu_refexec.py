@@ -24,7 +24,7 @@ IDS = ORDER
 
 def test_every_kernel_sized_fixture_is_covered():
     have = {os.path.basename(f)[len("refexec_"):-4] for f in glob.glob(os.path.join(HERE, "golden", "refexec_*.npz"))}
-    assert {n for n in have if not n.startswith(("tiny_", "question_", "collate"))} == set(ORDER)   # question_*: tests/test_refexec_question.py
+    assert {n for n in have if not n.startswith(("tiny_", "question_", "collate", "explicit_"))} == set(ORDER)   # question_*: tests/test_refexec_question.py
 
 
 def _zero_direction(name):

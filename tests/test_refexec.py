@@ -20,7 +20,8 @@ from tf_vqa_regat_b200 import synthetic as syn
 from tf_vqa_regat_b200.config import HotPathConfig, param_layout
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FILES = [f for f in sorted(glob.glob(os.path.join(HERE, "golden", "refexec_*.npz"))) if "refexec_question_" not in f and "refexec_collate" not in f]
+FILES = [f for f in sorted(glob.glob(os.path.join(HERE, "golden", "refexec_*.npz"))) if "refexec_question_" not in f and "refexec_collate" not in f
+         and "refexec_explicit_" not in f]      # explicit relation encoders: tests/test_explicit.py
 IDS = [os.path.basename(f)[len("refexec_"):-4] for f in FILES]
 
 
