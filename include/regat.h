@@ -462,6 +462,20 @@ REGAT_API int regat_q_wn_bwd(const float* G, const float* v, const float* g, con
                    float* dg, regat_stream_t stream);
 REGAT_API int regat_q_clip_adamax(float* w, const float* grad, float* m, float* u, int64_t n, const float* gsumsq, float clip,
                         float lr, int step, float beta1, float beta2, float eps, regat_stream_t stream);
+/* The embedding tables are read through tf.nn.embedding_lookup (language_model.py:33), so their tape gradient is tf.IndexedSlices and
+ * train.py:112-113 treats it as such.  dX [BT, width] is the gradient w.r.t. the (masked) lookup output, the table occupying columns
+ * [col0, col0+E); rows of the padding token (tok == n_token) are skipped (their values are zero).
+ * regat_q_embed_sumsq       out[0] += sum over occurrences of ||dX[r, col0:col0+E]||^2 -- what tf.clip_by_norm normalises by
+ *                           (duplicate tokens NOT summed first); caller zeroes out.
+ * regat_q_embed_clip_adamax Keras Adamax, sparse branch, for one table [n_token+1, E]: grad_dense is the scatter-added table
+ *                           (regat_q_embed_bwd), clipped by the occurrence norm; m <- b1 m + (1-b1) g; u <- b2 u, then every occurrence
+ *                           adds max(u_row, |value|) - u_row of the decayed row (uinc: zeroed scratch of the table's size, left zero);
+ *                           table -= lr_t m / (u + eps) over ALL rows. */
+REGAT_API int regat_q_embed_sumsq(const int32_t* tokens, int64_t BT, int n_token, int E, int width, int col0, const float* dX,
+                        float* out, regat_stream_t stream);
+REGAT_API int regat_q_embed_clip_adamax(const int32_t* tokens, int64_t BT, int n_token, int E, int width, int col0, const float* dX,
+                              float* table, const float* grad_dense, float* m, float* u, float* uinc, const float* gsumsq,
+                              float clip, float lr, int step, float beta1, float beta2, float eps, regat_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -121,3 +121,26 @@ def make_tokens(batch, n_token, seq_len=14, seed=21):
         tok[b, int(rng.integers(3, seq_len + 1)):] = n_token
     tok[0, :] = rng.integers(0, n_token, seq_len)                               # one question of full length
     return tok.astype(np.int64)
+
+
+def sparse_clip_adamax(w, tokens, values, m, u, step, lr, clip, beta1, beta2, eps, n_token):
+    """train.py:112-113 for an embedding table: its tape gradient is tf.IndexedSlices (the variable is read through
+    tf.nn.embedding_lookup, language_model.py:33) -- `values` [B,T,E] are the per-occurrence gradients of the MASKED lookup output
+    (the gradient of the raw lookup output is that times the padding mask, applied here).
+      tf.clip_by_norm(IndexedSlices): values * clip / max(||values||_2, clip), the norm over the un-deduplicated occurrences;
+      Keras Adamax, sparse branch:    m <- beta1 m + (1-beta1) scatter_add(values); u <- beta2 u; every occurrence adds
+                                      max(u[row], |value|) - u[row] of the DECAYED row it gathered; w -= lr_t m / (u + eps), all rows.
+    NumPy float64; returns (w, m, u)."""
+    tok = np.asarray(tokens).reshape(-1)
+    vals = np.asarray(values, dtype=np.float64).reshape(tok.size, -1)
+    vals = vals * (tok != n_token)[:, None]        # the mask multiplies the lookup's output (language_model.py:34-38): padding occurrences carry 0
+    nrm = np.sqrt((vals * vals).sum())
+    vals = vals * (clip / max(nrm, clip))
+    m = beta1 * m
+    np.add.at(m, tok, (1.0 - beta1) * vals)
+    u = beta2 * u
+    us = u[tok]
+    np.add.at(u, tok, np.maximum(us, np.abs(vals)) - us)
+    w = w - (lr / (1.0 - beta1 ** step)) * m / (u + eps)
+    return w, m, u
+

@@ -23,6 +23,9 @@ CASES = {
     "question_tiny": (TINY, 3, 9, True, 40, 10, "c", False, 2),
     "question_small": (SMALL, 4, 36, True, 60, 12, "c", True, 2),
     "question_small_noconcat": (SMALL, 2, 20, False, 60, 12, "", False, 2),
+    # a vocabulary of 6 words: every batch repeats every token many times, so the IndexedSlices semantics of the embedding
+    # gradient (clip by the un-deduplicated norm, per-occurrence Adamax `u` increments) differ visibly from the dense ones
+    "question_tiny_repeats": (TINY, 3, 9, True, 6, 10, "c", True, 3),
 }
 
 
@@ -86,7 +89,11 @@ def run_case(name, mods, save=True):
                loss=loss.numpy())
     names = [n for n, _, t in fshapes if t] + [e.name for e in entries]
     for n, g in zip(names, grads):
-        if n.startswith(("w_emb", "q_emb", "q_att")):
+        if n.startswith("w_emb"):
+            assert type(g).__name__ == "IndexedSlices", "the embedding tables' gradient must come back sparse"
+            out["grad/" + n] = g.numpy()                                                     # densified (duplicates summed)
+            out["grad_occurrence_norm/" + n] = float(np.sqrt((g.values.numpy() ** 2).sum()))  # what tf.clip_by_norm divides by
+        elif n.startswith(("q_emb", "q_att")):
             out["grad/" + n] = g.numpy()
         else:
             out["gradnorm/" + n] = float(np.sqrt((g.numpy() ** 2).sum()))

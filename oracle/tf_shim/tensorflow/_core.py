@@ -237,9 +237,31 @@ def where(condition, x=None, y=None):
     return _w(torch.where(c, _t(x), _t(y)))
 
 
+class IndexedSlices:
+    """tf.IndexedSlices: what GradientTape returns for a variable that was read through tf.nn.embedding_lookup / tf.gather
+    (array_grad.py, _GatherV2Grad / _ResourceGatherGrad): `values[k]` is the gradient of occurrence k of row `indices[k]`,
+    duplicates NOT summed."""
+
+    def __init__(self, values, indices, dense_shape):
+        self.values, self.indices, self.dense_shape = values, indices, tuple(dense_shape)
+
+    def to_dense(self):
+        v = _t(self.values)
+        out = torch.zeros(self.dense_shape, dtype=v.dtype)
+        out.index_add_(0, _t(self.indices).long(), v)
+        return _w(out)
+
+    def numpy(self):
+        return self.to_dense().numpy()
+
+
 def clip_by_norm(t, clip_norm):
     """tf.clip_by_norm (clip_ops.py): t * clip_norm / max(||t||_2, clip_norm), the norm taken
-    over the whole tensor, with the all-zero tensor mapped to itself."""
+    over the whole tensor, with the all-zero tensor mapped to itself.  For IndexedSlices the norm is that of `.values`
+    -- the un-deduplicated occurrences -- and the result is IndexedSlices again (clip_ops.py: `values = t.values if
+    isinstance(t, IndexedSlices) else t` ... `return IndexedSlices(values_clip, t.indices, t.dense_shape)`)."""
+    if isinstance(t, IndexedSlices):
+        return IndexedSlices(clip_by_norm(t.values, clip_norm), t.indices, t.dense_shape)
     t = _t(t)
     l2sum = (t * t).sum()
     pred = l2sum > 0
@@ -266,12 +288,41 @@ class GradientTape:
     def __exit__(self, *exc):
         return False
 
+    _sparse = {}                                   # id(variable) -> [(indices, values)] recorded by embedding_lookup's backward
+
     def gradient(self, target, sources):
         sources = list(sources)
+        GradientTape._sparse = {}
         g = torch.autograd.grad(_t(target), sources, allow_unused=True, retain_graph=self.persistent)
-        out = [None if x is None else _w(x) for x in g]
+        out = []
+        for src, x in zip(sources, g):
+            rec = GradientTape._sparse.get(id(src))
+            if x is None:
+                out.append(None)
+            elif rec:                              # the variable was only read through lookups: TensorFlow hands back IndexedSlices
+                out.append(IndexedSlices(_w(torch.cat([v for _, v in rec], 0)), _w(torch.cat([i for i, _ in rec], 0)), src.shape))
+            else:
+                out.append(_w(x))
         GradientTape.last = (sources, out)
         return out
+
+
+class _Lookup(torch.autograd.Function):
+    """params[ids] whose backward also records the sparse form of the gradient (indices, per-occurrence values)."""
+
+    @staticmethod
+    def forward(ctx, params, ids, key):
+        ctx.ids, ctx.key, ctx.pshape = ids, key, params.shape
+        return params[ids]
+
+    @staticmethod
+    def backward(ctx, g):
+        ids = ctx.ids.reshape(-1)
+        vals = g.reshape(ids.numel(), -1)
+        GradientTape._sparse.setdefault(ctx.key, []).append((ids, vals))
+        dense = torch.zeros(ctx.pshape, dtype=g.dtype)
+        dense.index_add_(0, ids, vals)
+        return dense, None, None
 
 
 # ----------------------------------------------------------------------------- tf.nn / tf.math
@@ -299,6 +350,8 @@ class nn:
 
     @staticmethod
     def embedding_lookup(params, ids):
+        if isinstance(params, Variable):           # gradient w.r.t. the table comes back as IndexedSlices (see GradientTape.gradient)
+            return _w(_Lookup.apply(params, _t(ids).long(), id(params)))
         return _w(_t(params)[_t(ids).long()])
 
 

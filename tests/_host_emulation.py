@@ -152,3 +152,30 @@ class HostOps:
         mm[...] = mi; uu[...] = ui
         ww[...] = ww - (lr / (1 - b1 ** step)) * mi / (ui + eps)
         return 0
+
+    def regat_q_embed_sumsq(self, tokens, BT, n_token, E, width, col0, dX, out, stream):
+        tok = _arr(tokens, BT, np.int32)
+        d = _mat(dX, BT, width, width)[:, col0:col0 + E].astype(np.float64)
+        _arr(out, 1)[0] += float((d[tok != n_token] ** 2).sum())
+        return 0
+
+    def regat_q_embed_clip_adamax(self, tokens, BT, n_token, E, width, col0, dX, table, grad, m, u, uinc, gsumsq, clip, lr, step, b1, b2, eps,
+                                  stream):
+        tok = _arr(tokens, BT, np.int32)
+        n = (n_token + 1) * E
+        scale = clip / max(np.sqrt(float(_arr(gsumsq, 1)[0])), clip)
+        vals = _mat(dX, BT, width, width)[:, col0:col0 + E].astype(np.float64) * scale
+        uu = _arr(u, n).reshape(n_token + 1, E)
+        ud = b2 * uu.astype(np.float64)
+        inc = np.zeros_like(ud)
+        live = tok != n_token
+        np.add.at(inc, tok[live], np.maximum(ud[tok[live]], np.abs(vals[live])) - ud[tok[live]])
+        g = _arr(grad, n).astype(np.float64) * scale
+        mm, ww = _arr(m, n), _arr(table, n)
+        mi = mm + (g - mm) * (1 - b1)
+        ui = (ud + inc).ravel()
+        mm[...] = mi; uu[...] = ui.reshape(uu.shape)
+        ww[...] = ww - (lr / (1 - b1 ** step)) * mi / (ui + eps)
+        _arr(uinc, n)[...] = 0
+        return 0
+

@@ -120,6 +120,36 @@ def test_reduction_weight_norm_and_optimizer_kernels():
         np.testing.assert_allclose(*r[k], rtol=1e-5, atol=1e-7, err_msg=k)
 
 
+def test_embedding_sparse_clip_and_adamax_kernels():
+    """The IndexedSlices path of train.py:112-113 for the embedding tables: occurrence-norm (regat_q_embed_sumsq) and the sparse
+    Adamax (regat_q_embed_clip_adamax) against the host emulation AND the oracle statement pinned to the executed reference."""
+    rng = np.random.default_rng(8)
+    n_token, E, BT, W = 7, 12, 40, 24                       # 7 words over 40 positions: every word repeats; table in columns [12, 24)
+    tok = rng.integers(0, n_token + 1, BT).astype(np.int32)
+    dX = rng.standard_normal((BT, W)).astype(np.float32)
+    r = _both("regat_q_embed_sumsq", dict(t=tok, d=dX, o=np.zeros(1, np.float32)), lambda p: (p["t"], BT, n_token, E, W, 12, p["d"], p["o"]), ["o"])
+    np.testing.assert_allclose(*r["o"], rtol=1e-5)
+    want_ss = float((dX[tok != n_token][:, 12:].astype(np.float64) ** 2).sum())
+    np.testing.assert_allclose(r["o"][0][0], want_ss, rtol=1e-5)
+    n = (n_token + 1) * E
+    table, m, u = rng.standard_normal(n).astype(np.float32), 0.1 * rng.standard_normal(n).astype(np.float32), np.abs(rng.standard_normal(n)).astype(np.float32) * 0.05
+    dense = np.zeros((n_token + 1, E), np.float32)
+    np.add.at(dense, tok[tok != n_token], dX[tok != n_token][:, 12:])
+    ss = np.array([want_ss], np.float32)
+    arrays = dict(t=tok, d=dX, w=table, g=dense.ravel(), m=m, u=u, ui=np.zeros(n, np.float32), ss=ss)
+    r = _both("regat_q_embed_clip_adamax", arrays,
+              lambda p: (p["t"], BT, n_token, E, W, 12, p["d"], p["w"], p["g"], p["m"], p["u"], p["ui"], p["ss"], 0.25, 1e-3, 3, 0.9, 0.999, 1e-8),
+              ["w", "m", "u", "ui"])
+    for k in ("w", "m", "u"):
+        np.testing.assert_allclose(*r[k], rtol=1e-5, atol=1e-7, err_msg=k)
+    assert not r["ui"][0].any()
+    from oracle import language_model as olm
+    w2, m2, u2 = olm.sparse_clip_adamax(table.astype(np.float64).reshape(-1, E), tok, dX[:, 12:], m.astype(np.float64).reshape(-1, E),
+                                         u.astype(np.float64).reshape(-1, E), 3, 1e-3, 0.25, 0.9, 0.999, 1e-8, n_token)
+    np.testing.assert_allclose(r["w"][0].reshape(-1, E), w2, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(r["u"][0].reshape(-1, E), u2, rtol=1e-5, atol=1e-7)
+
+
 @pytest.mark.parametrize("op,B,emb2_tr", [("c", 6, True), ("", 3, False)])
 def test_front_end_matches_oracle(op, B, emb2_tr):
     from tf_vqa_regat_b200.question import QuestionFrontEnd

@@ -26,9 +26,12 @@ def _setup(op, B, emb2_trainable, n_token=40, E=10, H=24, T=14, max_batch=None):
 def _oracle(front, tok, n_token, op, dq_att, dq_last, trainable):
     p = {k: torch.tensor(np.asarray(v, dtype=np.float64), requires_grad=True) for k, v in front.items()}
     q = olm.forward(p, tok, n_token, op)
+    q["w_emb"].retain_grad()
     loss = (q["q_att"] * torch.tensor(dq_att, dtype=torch.float64)).sum() + (q["q_last"] * torch.tensor(dq_last, dtype=torch.float64)).sum()
     loss.backward()
-    return q, {k: (v.grad.numpy() if v.grad is not None else np.zeros(v.shape)) for k, v in p.items()}
+    grads = {k: (v.grad.numpy() if v.grad is not None else np.zeros(v.shape)) for k, v in p.items()}
+    grads["__w_emb_occurrences"] = q["w_emb"].grad.numpy()          # IndexedSlices.values of the tables (before the padding mask)
+    return q, grads
 
 
 def test_layout_matches_the_oracle_order():
@@ -70,7 +73,12 @@ def test_update_is_per_tensor_clip_then_adamax():
         fe.backward(torch.tensor(dqa), torch.tensor(dql))
         fe.update(1e-3, step)
         _, grads = _oracle(p, tok, 40, "c", dqa, dql, None)
+        occ = grads["__w_emb_occurrences"]
         for k in p:
+            if k.startswith("w_emb."):         # tf.IndexedSlices semantics: occurrence-norm clip, sparse Adamax (train.py:112-113)
+                vals = occ[..., :10] if k == "w_emb.emb/emb" else occ[..., 10:]
+                p[k], m[k], u[k] = olm.sparse_clip_adamax(p[k], tok, vals, m[k], u[k], step, 1e-3, 0.25, 0.9, 0.999, 1e-8, 40)
+                continue
             p[k], m[k], u[k] = ot.adamax_step(p[k], ot.clip_by_norm(grads[k], 0.25), m[k], u[k], step, 1e-3)
     got = {k: v.numpy() for k, v in fe.named().items()}
     for k in p:
@@ -114,7 +122,9 @@ def _dp_worker(rank, world, port, out):
     q_att, q_last = fe.forward(torch.tensor(tok[sl], dtype=torch.int32))
     fe.backward(torch.tensor(dqa[sl]), torch.tensor(dql[sl]))
     fe.allreduce_grads()
-    out[rank] = (q_att.numpy().copy(), q_last.numpy().copy(), {k: v.numpy().copy() for k, v in fe.named(fe.grads).items()})
+    grads = {k: v.numpy().copy() for k, v in fe.named(fe.grads).items()}
+    fe.update(1e-3, 1)                      # embedding tables: occurrence-norm clip + sparse Adamax over the GLOBAL batch's tokens
+    out[rank] = (q_att.numpy().copy(), q_last.numpy().copy(), grads, {k: v.numpy().copy() for k, v in fe.named().items()})
     dist.destroy_process_group()
 
 
@@ -142,6 +152,15 @@ def test_two_rank_gloo_front_end_reproduces_the_global_batch():
                 continue
             scale = max(np.abs(grads[name]).max(), 1e-6)
             assert np.abs(g - grads[name]).max() < 5e-5 * scale + 1e-7, (r, name)
+    # one optimizer step: both ranks hold the single-process result (the embedding tables need every rank's token occurrences)
+    occ = grads["__w_emb_occurrences"]
+    for name in ("w_emb.emb/emb", "w_emb.emb_/emb_"):
+        vals = occ[..., :E] if name == "w_emb.emb/emb" else occ[..., E:]
+        z = np.zeros_like(np.asarray(front[name], dtype=np.float64))
+        want, _, _ = olm.sparse_clip_adamax(np.asarray(front[name], dtype=np.float64), tok, vals, z, z.copy(), 1, 1e-3, 0.25, 0.9, 0.999, 1e-8, n_token)
+        for r in range(2):
+            assert np.abs(out[r][3][name] - want).max() < 0.02 * 1e-3, (r, name)
+        assert np.array_equal(out[0][3][name], out[1][3][name])
     # and it matters: a rank that normalised over its own half only would be far off
     p = {k: torch.tensor(np.asarray(v, dtype=np.float64)) for k, v in front.items()}
     local_only = olm.forward(p, tok[:3], n_token, "c")["q_att"].numpy()

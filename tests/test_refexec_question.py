@@ -40,9 +40,12 @@ def _loss_and_grads(cfg, hot, front, shapes, batch, tok, n_token, op):
     pf = {k: torch.tensor(v, dtype=torch.float64, requires_grad=k in trainable) for k, v in front.items()}
     ph = ot.to_torch_params(hot)
     q = olm.forward(pf, tok, n_token, op)
+    q["w_emb"].retain_grad()
     out = ot.forward(ph, cfg, batch["features"], batch["boxes"], q["q_att"], q["q_last"], batch["target"])
     out["loss"].backward()
     grads = {k: v.grad.numpy() for k, v in list(pf.items()) + list(ph.items()) if v.grad is not None}
+    # per-occurrence gradient of the (masked) lookup output: what TensorFlow hands over as IndexedSlices.values for the tables
+    grads["__w_emb_occurrences"] = q["w_emb"].grad.numpy()
     return q, out, grads
 
 
@@ -98,7 +101,14 @@ def test_train_loop_updates_front_end_like_reference_train(path):
         ho = {k: p[k] for k in hot}
         _, out, grads = _loss_and_grads(cfg, ho, fr, shapes, batches[step - 1], tokens[step - 1], n_token, op)
         np.testing.assert_allclose(out["logits"].detach().numpy(), g["train.logits"][step - 1], rtol=1e-8, atol=1e-10)
+        occ = grads["__w_emb_occurrences"]
+        E = p["w_emb.emb/emb"].shape[1]
         for k in trainable:
+            if k.startswith("w_emb."):          # IndexedSlices: clipped by the occurrence norm, sparse Adamax (oracle/language_model.py)
+                vals = occ[..., :E] if k == "w_emb.emb/emb" else occ[..., E:]
+                p[k], m[k], u[k] = olm.sparse_clip_adamax(p[k], tokens[step - 1], vals, m[k], u[k], step, lr, cfg.grad_clip, cfg.beta1, cfg.beta2,
+                                                          cfg.eps, n_token)
+                continue
             gk = ot.clip_by_norm(grads[k], cfg.grad_clip)
             p[k], m[k], u[k] = ot.adamax_step(p[k], gk, m[k], u[k], step, lr, cfg.beta1, cfg.beta2, cfg.eps)
     for n, _, t in shapes:

@@ -111,6 +111,8 @@ SIGNATURES = {
     "regat_q_wn_alpha": [vp, vp, vp, vp],
     "regat_q_wn_bwd": [vp, vp, vp, vp, vp, i64, vp, vp, vp],
     "regat_q_clip_adamax": [vp, vp, vp, vp, i64, vp, f32, f32, i32, f32, f32, f32, vp],
+    "regat_q_embed_sumsq": [vp, i64, i32, i32, i32, i32, vp, vp, vp],
+    "regat_q_embed_clip_adamax": [vp, i64, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, f32, f32, i32, f32, f32, f32, vp],
 }
 
 

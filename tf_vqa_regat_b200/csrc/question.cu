@@ -188,6 +188,55 @@ __global__ void q_clip_adamax_kernel(float* __restrict__ w, const float* __restr
   }
 }
 
+// ---- the embedding tables' gradient is tf.IndexedSlices in the reference (language_model.py:33 reads the variable through
+// tf.nn.embedding_lookup), and train.py:112-113 treats it as such:
+//   tf.clip_by_norm   takes the norm of the PER-OCCURRENCE values (duplicates not summed):   sumsq = sum_r ||dX[r, col0:col0+E]||^2
+//   Adamax (sparse)   m decays everywhere and receives the summed occurrences; u decays everywhere, then every occurrence adds
+//                     max(u_row, |value|) - u_row of the decayed row it gathered; the subtraction covers the whole table.
+// (Rows of the padding token carry zero values: the mask multiplies the lookup's output.)
+__global__ void q_embed_sumsq_kernel(const int* __restrict__ tokens, long long BT, int n_token, int E, int W, int col0,
+                                     const float* __restrict__ dX, float* out) {
+  float ss = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < BT * E; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / E;
+    const int c = (int)(i - r * E);
+    const int tok = tokens[r];
+    if (tok == n_token || tok < 0 || tok > n_token) continue;
+    const float v = dX[r * W + col0 + c];
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0 && ss != 0.f) atomicAdd(out, ss);
+}
+// uinc[tok, c] += max(beta2 * u[tok, c], |scale * dX[r, col0 + c]|) - beta2 * u[tok, c]   per occurrence r
+__global__ void q_embed_uinc_kernel(const int* __restrict__ tokens, long long BT, int n_token, int E, int W, int col0,
+                                    const float* __restrict__ dX, const float* __restrict__ u, const float* gsumsq, float clip, float b2,
+                                    float* uinc) {
+  const float scale = clip / fmaxf(sqrtf(*gsumsq), clip);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < BT * E; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / E;
+    const int c = (int)(i - r * E);
+    const int tok = tokens[r];
+    if (tok == n_token || tok < 0 || tok > n_token) continue;
+    const float ud = b2 * u[(long long)tok * E + c];
+    const float inc = fmaxf(ud, fabsf(scale * dX[r * W + col0 + c])) - ud;
+    if (inc > 0.f) atomicAdd(uinc + (long long)tok * E + c, inc);
+  }
+}
+// dense pass of the sparse Adamax: grad = summed occurrences (scatter-added table), uinc from the kernel above (zeroed on exit)
+__global__ void q_clip_adamax_sparse_kernel(float* __restrict__ w, const float* __restrict__ grad, float* __restrict__ m,
+                                            float* __restrict__ u, float* __restrict__ uinc, long long n, const float* gsumsq, float clip,
+                                            float lr_t, float b1, float b2, float eps) {
+  const float scale = clip / fmaxf(sqrtf(*gsumsq), clip);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float g = grad[i] * scale;
+    const float mi = m[i] + (g - m[i]) * (1.f - b1);
+    const float ui = b2 * u[i] + uinc[i];
+    m[i] = mi; u[i] = ui; uinc[i] = 0.f;
+    w[i] -= (lr_t * mi) / (ui + eps);
+  }
+}
+
 int need_device(const char* what) {
   if (regat_device_count() == 0) { set_error("%s: no CUDA device (there is no CPU fallback)", what); return REGAT_ERR_CUDA; }
   return REGAT_OK;
@@ -324,6 +373,34 @@ extern "C" int regat_q_clip_adamax(float* w, const float* grad, float* m, float*
   REGAT_TRY(need_device("q_clip_adamax"));
   const float lr_t = (float)((double)lr / (1.0 - pow((double)beta1, (double)step)));
   q_clip_adamax_kernel<<<grid1d(n), 256, 0, (cudaStream_t)stream>>>(w, grad, m, u, n, gsumsq, clip, lr_t, beta1, beta2, eps);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+
+extern "C" int regat_q_embed_sumsq(const int32_t* tokens, int64_t BT, int n_token, int E, int width, int col0, const float* dX, float* out,
+                                   regat_stream_t stream) {
+  REGAT_REQUIRE(BT >= 0 && n_token > 0 && E > 0 && col0 >= 0 && col0 + E <= width, REGAT_ERR_SHAPE, "q_embed_sumsq: bad shape");
+  if (BT == 0) return REGAT_OK;
+  REGAT_REQUIRE(tokens && dX && out, REGAT_ERR_ARG, "q_embed_sumsq: null pointer");
+  REGAT_TRY(need_device("q_embed_sumsq"));
+  q_embed_sumsq_kernel<<<grid1d(BT * E), 256, 0, (cudaStream_t)stream>>>(tokens, BT, n_token, E, width, col0, dX, out);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
+}
+extern "C" int regat_q_embed_clip_adamax(const int32_t* tokens, int64_t BT, int n_token, int E, int width, int col0, const float* dX,
+                                         float* table, const float* grad_dense, float* m, float* u, float* uinc, const float* gsumsq,
+                                         float clip, float lr, int step, float beta1, float beta2, float eps, regat_stream_t stream) {
+  REGAT_REQUIRE(BT >= 0 && n_token > 0 && E > 0 && col0 >= 0 && col0 + E <= width && step >= 1, REGAT_ERR_SHAPE, "q_embed_clip_adamax: bad shape");
+  REGAT_REQUIRE(tokens && dX && table && grad_dense && m && u && uinc && gsumsq, REGAT_ERR_ARG, "q_embed_clip_adamax: null pointer");
+  REGAT_TRY(need_device("q_embed_clip_adamax"));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BT > 0) {
+    q_embed_uinc_kernel<<<grid1d(BT * E), 256, 0, st>>>(tokens, BT, n_token, E, width, col0, dX, u, gsumsq, clip, beta2, uinc);
+    REGAT_POST_LAUNCH();
+  }
+  const long long n = (long long)(n_token + 1) * E;
+  const float lr_t = (float)((double)lr / (1.0 - pow((double)beta1, (double)step)));
+  q_clip_adamax_sparse_kernel<<<grid1d(n), 256, 0, st>>>(table, grad_dense, m, u, uinc, n, gsumsq, clip, lr_t, beta1, beta2, eps);
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }

@@ -222,6 +222,15 @@ class QuestionFrontEnd:
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.grads, group=self.group)
+            # the embedding tables' clip norm and Adamax `u` are functions of the per-occurrence values of the WHOLE batch
+            # (IndexedSlices semantics, see update()): every rank needs every rank's tokens and lookup-output gradients
+            B, T = self._saved_B, self.T
+            if getattr(self, "_tok_g", None) is None:
+                self._tok_g = torch.zeros(self.world * self.max_batch * T, dtype=torch.int32, device=self.device)
+                self._DX_g = torch.zeros(self.world * self.max_batch * T * self.Ein, dtype=torch.float32, device=self.device)
+            dist.all_gather_into_tensor(self._tok_g[:self.world * B * T], self._tok.reshape(-1)[:B * T].contiguous(), group=self.group)
+            dist.all_gather_into_tensor(self._DX_g[:self.world * B * T * self.Ein], self._DX[:B * T * self.Ein], group=self.group)
+            self._gathered = True
 
     # ---- train.py:112-113 for the front-end's variables
     def update(self, lr, step=None):
@@ -230,9 +239,29 @@ class QuestionFrontEnd:
         sc = self._scal.data_ptr()
         names = self.trainable()
         self._scal[32:32 + len(names)].zero_()
+        B = self._saved_B
         for k, name in enumerate(names):
             n = [int(np.prod(s)) if s else 1 for nm, s, _ in self.entries if nm == name][0]
             gp, ss = self._p(name, self.grads), sc + 4 * (32 + k)
+            if name.startswith("w_emb."):
+                # the table was read through tf.nn.embedding_lookup: its tape gradient is IndexedSlices, which train.py:112 clips by
+                # the norm of the per-occurrence values and Adamax applies through its sparse branch (duplicate tokens are visible)
+                if B is None:
+                    raise RuntimeError("update() before forward() / backward()")
+                col0 = 0 if name == "w_emb.emb/emb" else self.E
+                if getattr(self, "_UINC", None) is None:
+                    self._UINC = torch.zeros((self.n_token + 1) * self.E, dtype=torch.float32, device=self.device)
+                if self.world > 1 and not getattr(self, "_gathered", False):
+                    raise RuntimeError("data parallel: call allreduce_grads() before update() (the embedding update needs every rank's tokens)")
+                tokp, dxp, BT = ((self._tok_g.data_ptr(), self._DX_g.data_ptr(), self.world * B * self.T) if self.world > 1
+                                 else (self._tok.data_ptr(), self._DX.data_ptr(), B * self.T))
+                _lib.check(L.regat_q_embed_sumsq(tokp, BT, self.n_token, self.E, self.Ein, col0, dxp, ss, st))
+                _lib.check(L.regat_q_embed_clip_adamax(tokp, BT, self.n_token, self.E, self.Ein, col0, dxp,
+                                                       self._p(name), gp, self._p(name, self.adamax_m), self._p(name, self.adamax_u),
+                                                       self._UINC.data_ptr(), ss, self.grad_clip, float(lr), int(self.step_count), self.beta1,
+                                                       self.beta2, self.eps, st))
+                continue
             _lib.check(L.regat_q_dot(gp, gp, n, ss, st))
             _lib.check(L.regat_q_clip_adamax(self._p(name), gp, self._p(name, self.adamax_m), self._p(name, self.adamax_u), n, ss,
                                              self.grad_clip, float(lr), int(self.step_count), self.beta1, self.beta2, self.eps, st))
+        self._gathered = False
