@@ -1,4 +1,6 @@
 """Checkpoint I/O by variable order (tf_vqa_regat_b200/checkpoint.py; reference main.py:145,155)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -94,3 +96,46 @@ def test_whole_model_checkpoint_round_trip(tmp_path):
         ck.load_model_weights(str(p), SMALL, [(n, (s if n != "q_emb.gru/kernel" else (5, 5))) for n, s in shapes])
     with pytest.raises(ValueError):
         ck.load_model_weights(str(p), SMALL, shapes[:-1])      # one front-end variable short: the hot-path count no longer fits
+
+
+def test_foreign_npz_is_ordered_by_integer_index_and_meta_is_validated(tmp_path):
+    """'arr_10' must not sort before 'arr_2'; a `__meta__` record written for another variable list is refused."""
+    import json
+    cfg = HotPathConfig(v_dim=96, q_dim=48, rel_dim=64, num_heads=4, nongt_dim=5, num_answers=37)
+    flat = syn.make_params(cfg, seed=3, trained_like=True)
+    arrays = ck.flat_to_arrays(cfg, flat)
+    assert len(arrays) > 11
+    p = tmp_path / "foreign.npz"
+    np.savez(p, *arrays)                                   # numpy's own keys: arr_0 ... arr_N (lexical order would scramble them)
+    np.testing.assert_array_equal(ck.load_weights(str(p), cfg), flat)
+    np.savez(tmp_path / "gap.npz", **{"0": arrays[0], "2": arrays[1]})
+    with pytest.raises(ValueError, match="without gaps"):
+        ck.load_weights(str(tmp_path / "gap.npz"), cfg)
+    np.savez(tmp_path / "noindex.npz", kernel=arrays[0])
+    with pytest.raises(ValueError, match="no variable index"):
+        ck.load_weights(str(tmp_path / "noindex.npz"), cfg)
+    good = tmp_path / "good.npz"
+    ck.save_weights(str(good), cfg, flat)
+    with np.load(good) as z:
+        payload = {k: z[k] for k in z.files}
+    meta = json.loads(bytes(payload["__meta__"]).decode())
+    meta["variables"][3] = "somebody.else/v"
+    payload["__meta__"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez(tmp_path / "othermodel.npz", **payload)
+    with pytest.raises(ValueError, match="different variable list"):
+        ck.load_weights(str(tmp_path / "othermodel.npz"), cfg)
+
+
+def test_keras_h5_needs_h5py_and_says_so(tmp_path):
+    try:
+        import h5py  # noqa: F401
+        pytest.skip("h5py is installed here")
+    except ImportError:
+        pass
+    with pytest.raises(ImportError, match="convert_keras_h5"):
+        ck.read_keras_h5(str(tmp_path / "x.h5"))
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "convert_keras_h5.py"),
+                        str(tmp_path / "x.h5"), str(tmp_path / "out")], capture_output=True, text=True)
+    assert r.returncode != 0 and "h5py" in (r.stderr + r.stdout)

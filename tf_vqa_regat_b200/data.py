@@ -27,6 +27,21 @@ class AdaptiveFeatureStore:
         self.bb = np.ascontiguousarray(image_bb, dtype=np.float32)
         self.pos_boxes = np.asarray(pos_boxes, dtype=np.int64)
 
+    @classmethod
+    def from_hdf5(cls, path: str, in_memory: bool = True) -> "AdaptiveFeatureStore":
+        """The reference's adaptive feature file (dataset.py:206-230: datasets `image_features` [T,V], `spatial_features` [T,6],
+        `image_bb` [T,4], `pos_boxes` [num_images,2]).  Needs h5py, which is not part of this repository's image (no HDF5 library
+        there: the container format is WAIVED, the layout behind it is what this class implements and tests); in_memory=True reads
+        the arrays whole, as the reference does (`np.array(hf.get(...))`, dataset.py:212-221)."""
+        try:
+            import h5py
+        except ImportError as ex:
+            raise ImportError("AdaptiveFeatureStore.from_hdf5 needs h5py (not installed in this image); pass the four arrays to the "
+                              "constructor instead, e.g. from np.load of a converted file") from ex
+        with h5py.File(path, "r") as hf:
+            get = (lambda k: np.array(hf.get(k))) if in_memory else (lambda k: hf.get(k)[...])
+            return cls(get("image_features"), get("spatial_features"), get("image_bb"), get("pos_boxes"))
+
     def counts(self, image_ids: Sequence[int]) -> np.ndarray:
         pb = self.pos_boxes[np.asarray(image_ids, dtype=np.int64)]
         return (pb[:, 1] - pb[:, 0]).astype(np.int64)
