@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libregat.so")
+LIB_PATH = os.environ.get("REGAT_LIB") or os.path.join(_HERE, "libregat.so")     # REGAT_LIB: same-session A/B of two builds (tools/ab_lib.sh)
 
 F32, BF16 = 0, 1
 

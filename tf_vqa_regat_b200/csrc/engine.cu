@@ -435,6 +435,9 @@ OptHyper opt_hyper(const regat_engine* e) {
 }
 
 // clip + Adamax of one range (r < 0: everything), then the derived state of the tensors just written
+// (Measured and dropped: capping the grids of these launches so that they stream at a fraction of the HBM bandwidth beside the
+// backward pass.  At 296 / 148 / 74 CTAs the step went from 0.98 ms to 1.15 / 1.45 / 2.02 ms: the optimizer has less slack than
+// its traffic needs, it has to run at full width.)
 int optimize_range(regat_engine* e, int r, cudaStream_t st) {
   const bool all = r < 0;
   const TensorList& to = all ? e->tl_opt : e->rng[r].tl_opt;
@@ -468,6 +471,33 @@ int fork_to(cudaStream_t from, cudaStream_t to, cudaEvent_t ev) {
   return REGAT_OK;
 }
 
+// bias / pair_pos_fc / label gradients, the loss and the score are accumulated with atomics: zero those slots (the kernels'
+// gradients are overwritten).  With `tick` the same launch opens the optimizer step (++step, lr_t).  Issued on the side stream at
+// the start of a training forward pass, off the critical path; every consumer is ordered behind it (same stream, or the join
+// before the pooling kernel).
+int zero_accumulators(regat_engine* e, cudaStream_t st, bool tick) {
+  const int dirs = e->cfg.dir_num;
+  TensorList z;
+  memset(&z, 0, sizeof(z));
+  for (size_t l = 0; l < e->layers.size(); ++l) {
+    const Layer& L = e->layers[l];
+    if (L.b_off >= 0) { z.off[z.n] = L.b_off; z.numel[z.n] = L.cols; ++z.n; }
+    z.off[z.n] = L.g_off; z.numel[z.n] = 1; ++z.n;
+  }
+  {
+    const Layer& L = e->layers[e->l_lin];
+    z.off[z.n] = L.v_off; z.numel[z.n] = (long long)L.rows * L.cols; ++z.n;
+  }
+  for (int d = 0; d < dirs; ++d) {
+    const Layer& L = e->layers[e->l_pos[d]];
+    z.off[z.n] = L.v_off; z.numel[z.n] = (long long)L.rows * L.cols; ++z.n;
+  }
+  zero_list_kernel<<<z.n, 128, 0, st>>>(e->grads, z, tick ? e->at<Hyper>(e->hyp) : nullptr, e->cfg.beta1);
+  REGAT_POST_LAUNCH();
+  REGAT_CUDA(cudaMemsetAsync(e->at<float>(e->scal) + 1, 0, 3 * sizeof(float), st));   // dc, loss, score
+  return REGAT_OK;
+}
+
 int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
   regat_engine* e = c.e;
   cudaStream_t st = c.st;
@@ -481,6 +511,10 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
   // activations in the compute dtype: the casts do not depend on the weights, so they run on the side stream while the main
   // stream derives alpha and the bf16 kernels from the parameters (both HBM-bound, neither saturates the memory system alone)
   const void* feat = c.features; const void* qatt = c.q_att; const void* qlast = c.q_last;
+  if (training && e->grads) {
+    REGAT_TRY(fork_to(st, sd, e->ev[2]));
+    REGAT_TRY(zero_accumulators(e, sd, c.fused_opt));
+  }
   if (dt == REGAT_BF16) {
     REGAT_TRY(fork_to(st, sd, e->ev[2]));
     REGAT_TRY(k_cast(REGAT_BF16, c.features, e->atv(e->featT), (long long)R * V, sd));
@@ -624,27 +658,6 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   float* scal = e->at<float>(e->scal);
   e->grads_final = 0;
 
-  // bias / pair_pos_fc / label gradients are accumulated with atomics: zero those slots (kernels' gradients are overwritten)
-  {
-    TensorList z;
-    memset(&z, 0, sizeof(z));
-    for (size_t l = 0; l < e->layers.size(); ++l) {
-      const Layer& L = e->layers[l];
-      if (L.b_off >= 0) { z.off[z.n] = L.b_off; z.numel[z.n] = L.cols; ++z.n; }
-      z.off[z.n] = L.g_off; z.numel[z.n] = 1; ++z.n;
-    }
-    {
-      const Layer& L = e->layers[e->l_lin];
-      z.off[z.n] = L.v_off; z.numel[z.n] = (long long)L.rows * L.cols; ++z.n;
-    }
-    for (int d = 0; d < dirs; ++d) {
-      const Layer& L = e->layers[e->l_pos[d]];
-      z.off[z.n] = L.v_off; z.numel[z.n] = (long long)L.rows * L.cols; ++z.n;
-    }
-    zero_list_kernel<<<z.n, 128, 0, st>>>(e->grads, z, c.fused_opt ? e->at<Hyper>(e->hyp) : nullptr, cf.beta1);
-    REGAT_POST_LAUNCH();
-    REGAT_CUDA(cudaMemsetAsync(scal + 1, 0, 3 * sizeof(float), st));   // dc, loss, score
-  }
   // loss + dlogits                                                     train.py:107-108
   REGAT_TRY(k_bce(B, A, e->at<float>(e->logits), e->a_pad, target, grad_scale, scal + 2, scal + 3, e->atv(e->dlogits), e->a_pad, dt, st));
   // The input-gradient chain (dhid -> djoint -> dpv -> dpooled -> dv1) stays on the main stream; every weight / bias gradient of
