@@ -379,6 +379,11 @@ REGAT_API int regat_engine_refresh_weights(regat_engine* e, regat_stream_t strea
  * event on `stream` and starts an all-reduce of that range on another stream, overlapping the rest of the backward.  */
 typedef void (*regat_grad_ready_fn)(void* user, int64_t offset, int64_t numel);
 REGAT_API int regat_engine_set_grad_callback(regat_engine* e, regat_grad_ready_fn fn, void* user);
+/* Measurement aid (tools/gemm_trace.py): with a device buffer of >= 256 int64 the tcgen05 GEMM launches that follow record
+ * clock64 stamps of CTA 0 -- [0] kernel start, [1] roles done, [2] exit, then per unit u (u < 30) at [8 + 8u + k]:
+ * k=0/1 first/last TMA issue, 2 accumulator stage free, 3 first operands landed, 4 last MMA issued, 5 epilogue ready,
+ * 6 accumulator complete, 7 unit stored.  NULL switches it off (the default).  Not thread-safe; never leave it on. */
+REGAT_API int regat_gemm_trace(void* device_buf);
 /* Measurement aid (bench.py's GEMM-class figure): with on != 0 every dense product of the following EAGER engine calls is
  * bracketed by CUDA timing events; profile_read synchronises the device, returns up to max_records entries -- mnk[3i..3i+2] =
  * (M, N, K), ms[i] -- in launch order and clears the list.  Never enable it while a CUDA graph is being captured. */

@@ -112,6 +112,7 @@ def test_masked_attention_kernels_vs_torch(dtype, tol):
     from tf_vqa_regat_b200 import _lib
     l = _lib.lib()
     st = torch.cuda.current_stream().cuda_stream
+    torch.manual_seed(20260318)      # operands must not depend on what ran before (the bf16 bound is a max-norm over random data)
     B, N, nongt, D, H, dirs, L = 3, 36, 20, 256, 4, 2, 11
     M = min(nongt, N)
     rng = np.random.default_rng(3)

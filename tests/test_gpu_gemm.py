@@ -32,6 +32,10 @@ def _operands(tA, tB, M, N, K, dt, pad=0, seed=0):
 
 
 SHAPES = [(128, 128, 64), (256, 256, 512), (300, 200, 136), (128, 264, 1000), (72, 3129, 1536), (1024, 768, 4608), (384, 3136, 256)]
+# enough 128 x 256 tiles for the 256-wide configuration, which runs on CTA pairs (tcgen05.mma.cta_group::2, 256-row units):
+# a last unit whose second CTA has no rows at all (4736 = 18.5 x 256), ragged M and N with a column half fully out of range
+# (1100 = 4 x 256 + 76), several units per pair with a long K loop (ring wrap-around, both accumulator stages)
+SHAPES_PAIRS = [(4736, 1024, 320), (5000, 1100, 200), (2304, 4096, 1024), (9216, 1024, 2048)]
 
 
 @pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
@@ -45,6 +49,29 @@ def test_bf16_tcgen05_matches_torch(tA, tB, M, N, K):
 
 
 @pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", SHAPES_PAIRS)
+@pytest.mark.parametrize("out_dtype", ["f32", "f32_aligned", "bf16"])
+def test_bf16_cta_pair_matches_torch(tA, tB, M, N, K, out_dtype):
+    # "f32": odd row pitch -> the generic epilogue kind; "f32_aligned" / "bf16": the lean kinds when N is a multiple of 32
+    A, B, ref = _operands(tA, tB, M, N, K, torch.bfloat16, pad=8)
+    if out_dtype.startswith("f32"):
+        out = torch.full((M, N + (3 if out_dtype == "f32" else 8)), float("nan"), device="cuda", dtype=torch.float32)[:, :N]
+        _gemm(_lib.BF16, tA, tB, M, N, K, A, B, out, _lib.F32)
+        tol = 2e-3
+    else:
+        out = torch.full((M, (N + 7) // 8 * 8 + 8), float("nan"), device="cuda", dtype=torch.bfloat16)[:, :N]
+        _gemm(_lib.BF16, tA, tB, M, N, K, A, B, out, _lib.BF16)
+        tol = 1e-2
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < tol, err
+    # a second call on the same operands: the persistent pipeline state (ring phase, accumulator stage) restarts cleanly
+    out2 = torch.zeros_like(out)
+    _gemm(_lib.BF16, tA, tB, M, N, K, A, B, out2, _lib.F32 if out_dtype.startswith("f32") else _lib.BF16)
+    assert torch.equal(out2, out)
+
+
+@pytest.mark.parametrize("tA,tB", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_fp32_simt_matches_torch(tA, tB):
     M, N, K = 200, 301, 777
     A, B, ref = _operands(tA, tB, M, N, K, torch.float32)
@@ -54,14 +81,15 @@ def test_fp32_simt_matches_torch(tA, tB):
     assert ((out.double() - ref).abs().max() / ref.abs().max()).item() < 1e-5
 
 
-@pytest.mark.parametrize("dtype", ["bf16", "fp32"])
-def test_fused_epilogue(dtype):
+@pytest.mark.parametrize("dtype,G,N", [("bf16", 32, 256), ("fp32", 32, 256), ("bf16", 600, 1024)])
+def test_fused_epilogue(dtype, G, N):
+    # G = 600, N = 1024: 43 x 4 tiles of 128 x 256 -> the CTA-pair configuration, every fused term at once
     dt, code = (torch.bfloat16, _lib.BF16) if dtype == "bf16" else (torch.float32, _lib.F32)
-    rows_in, keep, G = 9, 5, 32
-    M, N, K = rows_in * G, 256, 192
+    rows_in, keep = 9, 5
+    M, K = rows_in * G, 192
     A, B, acc = _operands(0, 0, M, N, K, dt, seed=3)
     g = torch.Generator(device="cuda").manual_seed(5)
-    alpha = torch.tensor([0.7, -1.3], device="cuda")
+    alpha = torch.tensor([0.7, -1.3], device="cuda").repeat(N // 256)
     bias = torch.randn(N, device="cuda", generator=g)
     addend = torch.randn(G, N, device="cuda", generator=g)
     row_scale = (torch.rand(M, device="cuda", generator=g) > 0.3).float()

@@ -46,6 +46,7 @@ SIGNATURES = {
     "regat_position_embedding": [vp, i32, i32, i32, i32, vp, vp, vp],
     "regat_wn_prepare": [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "regat_wn_alpha": [vp, vp, i32, vp, vp, vp, vp],
+    "regat_gemm_trace": [vp],
     "regat_gemm": [i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, C.POINTER(Epilogue), vp],
     "regat_geoattn_fwd": [i32] * 8 + [vp, vp, vp, vp, vp, vp, i64, vp, vp, i64, vp, vp, vp, i32, vp, vp, vp, vp, vp],
     "regat_attn_bwd": [i32] * 7 + [vp] * 9,

@@ -77,6 +77,11 @@ extern "C" int regat_device_synchronize(void) {
   return REGAT_OK;
 }
 
+extern "C" int regat_gemm_trace(void* device_buf) {
+  regat::gemm_tc_set_trace(static_cast<long long*>(device_buf));
+  return REGAT_OK;
+}
+
 extern "C" int regat_gemm(int dtype, int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
                           void* C, int ldc, int c_dtype, const regat_epilogue* epi, regat_stream_t stream) {
   REGAT_REQUIRE(A && B && C, REGAT_ERR_ARG, "gemm: null pointer");

@@ -112,6 +112,7 @@ struct GemmCall {
   EpiArgs e;
 };
 int gemm_tc_pair(const GemmCall& c0, const GemmCall& c1, cudaStream_t st);
+void gemm_tc_set_trace(long long* buf);
 bool gemm_tc_supported(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B,
                        int ldb);
 

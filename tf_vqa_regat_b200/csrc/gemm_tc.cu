@@ -12,11 +12,13 @@
 //                  (next 8 K-rows), +2048 B per UMMA_K
 // Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer, warps 2.. = EPIW (4 or 8) epilogue warps
 // (warp w reads TMEM lanes 32*(w%4)..; with 8, the two warps of a lane quarter interleave the 32-column blocks).  Every mbarrier wait is bounded and traps instead of hanging.
-// Epilogue data path: tcgen05.ld hands each thread one accumulator ROW, which is the wrong shape for global memory
-// (a warp store would touch 32 different lines).  Each epilogue warp therefore transposes 32x32 fp32 blocks through a
-// private 4 KB XOR-swizzled shared-memory patch: row-per-lane in, 8 lanes per 128-byte row out, so every global access
-// of the fused epilogue (C, accumulate, gate, addend, second output, split-K reductions) is a run of full 32-byte
-// sectors, and the next block's tcgen05.ld is in flight while the current one drains.
+// Epilogue data path: tcgen05.ld (32x32b.x32) hands each thread 32 consecutive columns of one accumulator ROW -- 64 bytes
+// of a bf16 output, 128 of an fp32 one, i.e. whole 32-byte sectors.  Each thread finishes its piece in registers and
+// stores it with 256-bit accesses; the global-memory terms of the fused epilogue (old C, relu gate, addend) are requested
+// before the TMEM wait, and the next block's tcgen05.ld is in flight while the current one is processed.  (The first
+// version transposed 32x32 blocks through shared memory to get row-contiguous warp stores; measured on the step's shapes it
+// cost ~6 us per 128x256 unit -- latency of four dependent phases per block with two warps per scheduler -- which bounded
+// every K <= 1024 product and left a ~6 us tail on the others.)
 #include <cuda.h>
 
 #include <algorithm>
@@ -33,7 +35,6 @@ namespace {
 
 constexpr int BM = 128, BK = 64, UMMA_K = 16;
 constexpr uint32_t SPIN_LIMIT = 1u << 27;
-constexpr int EPI_PATCH_BYTES = 32 * 32 * 4;   // one 32x32 fp32 transpose patch per epilogue warp
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -67,6 +68,53 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// ---- CTA pair (cta_group::2): two CTAs of a cluster on one TPC share one 256-row MMA; CTA rank 0 issues it
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+// each CTA of the pair loads its own half of the operands; the bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// completion of the pair's MMAs arrives on the barrier at this offset in BOTH CTAs
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
@@ -124,12 +172,9 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 // C / gate / c2 arrive as generic pointers; they are global memory by contract, and saying so keeps the accesses off the
-// generic path (which the compiler must order against the shared-memory patch)
+// generic path
 __device__ __forceinline__ void stg_v4(void* p, float4 v) {
   asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
-}
-__device__ __forceinline__ void stg_v2(void* p, uint2 v) {
-  asm volatile("st.global.v2.b32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y));
 }
 __device__ __forceinline__ float4 ldg_v4(const void* p) {
   float4 v;
@@ -141,24 +186,52 @@ __device__ __forceinline__ float4 ldg_nc_v4(const void* p) {
   asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
-__device__ __forceinline__ uint2 ldg_nc_v2(const void* p) {
-  uint2 v;
-  asm volatile("ld.global.nc.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+__device__ __forceinline__ uint4 ldg_v4u(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
-__device__ __forceinline__ float4 lds_v4(uint32_t saddr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+__device__ __forceinline__ uint4 ldg_nc_v4u(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
-__device__ __forceinline__ uint2 ldg_v2(const void* p) {
-  uint2 v;
-  asm volatile("ld.global.v2.b32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
-  return v;
+__device__ __forceinline__ void stg_v4u(void* p, const uint32_t* w) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]));
+}
+// 256-bit stores (sm_100): one full 32-byte sector per thread and instruction
+__device__ __forceinline__ void stg_v8u(void* p, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
+               "r"(w[5]), "r"(w[6]), "r"(w[7]));
+}
+__device__ __forceinline__ void stg_v8f(void* p, const float* x) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]), "f"(x[4]),
+               "f"(x[5]), "f"(x[6]), "f"(x[7]));
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
+}
+// packed fp32x2 arithmetic (sm_100): (a0, a1) += (b0, b1);  (a0, a1) = (a0, a1) * s + (b0, b1)
+__device__ __forceinline__ void fadd2(uint32_t& a0, uint32_t& a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%2, %3};\n\tadd.rn.f32x2 ra, ra, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+      : "+r"(a0), "+r"(a1)
+      : "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+__device__ __forceinline__ void ffma2(uint32_t& a0, uint32_t& a1, float s, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rs;\n\tmov.b64 ra, {%0, %1};\n\tmov.b64 rb, {%3, %4};\n\tmov.b64 rs, {%2, %2};\n\tfma.rn.f32x2 ra, ra, rs, rb;\n\tmov.b64 {%0, %1}, ra;\n\t}"
+      : "+r"(a0), "+r"(a1)
+      : "r"(__float_as_uint(s)), "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+// relu folded into the conversion
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t w;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(w) : "f"(hi), "f"(lo));
+  return w;
+}
+// 0xffff in each half whose bf16 value is > 0
+__device__ __forceinline__ uint32_t bf16x2_gt0_mask(uint32_t g) {
+  return __hgt2_mask(*reinterpret_cast<const __nv_bfloat162*>(&g), __float2bfloat162_rn(0.f));
 }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
@@ -176,9 +249,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, a_major bit15, b_major bit16,
 // N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn, int m = BM) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(BM >> 4) << 24);
+         ((uint32_t)(m >> 4) << 24);
 }
 
 // Optional second product riding in the same launch.  It shares N, ldc, the output type and the (empty) epilogue with the first
@@ -197,6 +270,8 @@ struct TcParams {
   void* C;
   EpiArgs e;
   TcSecond s2;
+  int dbg;                        // experiments (REGAT_TC_DBG): 1 = no stores, 2 = no TMEM loads -- results are wrong
+  long long* trace;               // measurement aid (regat_gemm_trace): per-unit clock64 stamps of CTA 0's warp roles, or null
 };
 
 // Generic per-element epilogue for ragged edges and unaligned tensors (4 consecutive columns of one row).
@@ -223,25 +298,42 @@ __device__ __noinline__ void epi_slow(const TcParams& p, void* Cout, int accumul
 // Persistent: CTA c processes work units c, c+grid, ... where a unit = (m-tile, n-tile, k-split), n fastest so that
 // concurrently running CTAs share A rows in L2.  ACC accumulator stages in TMEM (ACC*BN <= 512 columns) let the epilogue
 // of unit i overlap the MMAs of unit i+1.
-template <int BN, int STAGES, int ACC, int EPIW, bool A_MN, bool B_MN, bool PAIR>
-__global__ void __launch_bounds__(64 + 32 * EPIW, BN == 128 ? 2 : 0) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
+// CTA2: the launch is made of clusters of two CTAs (one TPC).  A unit is a 256 x BN tile: CTA rank r of the pair loads rows
+// m0 + 128 r of A and columns n0 + (BN/2) r of B into its own shared memory, the leader (rank 0) issues ONE
+// tcgen05.mma.cta_group::2 of 256 x BN x 16 per k-step that reads both CTAs' shared memory, and each CTA drains the 128
+// accumulator rows that live in its own TMEM.  Per SM that halves the B traffic (TMA writes and MMA reads of shared memory),
+// which is what bounds the single-CTA 128 x 256 tile.
+// EPI selects how much of the fused epilogue is compiled in.  The epilogue is a long chain of optional terms; with all of them
+// in one loop body the executed path hops through ~60 KB of code, the loop no longer fits the instruction cache next to the
+// producer / MMA loops, and the epilogue warps run at ~4 cycles per instruction (measured: 4.5 us per 128 x 256 unit, more
+// than the unit's K = 1024 main loop).  The host picks the smallest kind that covers the call (epi_kind()):
+//   0 generic (everything, ragged / unaligned tensors included)      2 bf16 output with read-modify-write terms (old C, gate,
+//   1 bf16 output, optional bias and relu                               addend, second output)
+//   3 fp32 output, optional bias; plain store, split-K red or column-block scatter
+template <int BN, int STAGES, int ACC, int EPIW, bool A_MN, bool B_MN, bool PAIR, bool CTA2, int EPI>
+__global__ void __launch_bounds__(64 + 32 * EPIW, BN == 128 ? 2 : 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                            const __grid_constant__ CUtensorMap mapB, const __grid_constant__ TcParams p,
                                                            const __grid_constant__ CUtensorMap mapA2,
                                                            const __grid_constant__ CUtensorMap mapB2) {
-  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr int BNL = CTA2 ? BN / 2 : BN;         // B columns this CTA loads
+  constexpr int TM = CTA2 ? 2 * BM : BM;          // rows of a unit
+  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BNL * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr uint32_t TMEM_COLS = ACC * BN;
   static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* tiles = smem;            // SWIZZLE_128B tiles need 1024-byte alignment: the dynamic window provides it (checked)
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  float* stage = reinterpret_cast<float*>(tiles + STAGES * STAGE_BYTES);                 // EPIW epilogue warps x 4 KB
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES + EPIW * EPI_PATCH_BYTES);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;       // [ACC]
   uint64_t* tmem_empty = tmem_full + ACC;         // [ACC]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC);
+  float* bias_stage = reinterpret_cast<float*>(tmem_slot + 4);       // EPIW x 128 floats: each epilogue warp's bias columns of a unit
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = CTA2 ? cluster_ctarank() : 0u;            // rank in the CTA pair
+  const int worker = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int workers = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const int tiles_n = p.tiles_n, splits = p.splits;
   // units [0, units1) belong to the launch's first problem, [units1, units) to the optional second one (host: longer K first)
   const int units1 = p.tiles_m * tiles_n * splits;
@@ -251,12 +343,13 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, BN == 128 ? 2 : 0) gemm_tc_ker
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
-    for (int a = 0; a < ACC; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, EPIW); }
+    // CTA pair: the epilogue warps of BOTH CTAs hand an accumulator stage back to the leader
+    for (int a = 0; a < ACC; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, CTA2 ? 2 * EPIW : EPIW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  if (warp == 1) { if (CTA2) tmem_alloc_pair(tmem_slot, TMEM_COLS); else tmem_alloc(tmem_slot, TMEM_COLS); }
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();     // pair: the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -265,33 +358,59 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, BN == 128 ? 2 : 0) gemm_tc_ker
     if (PAIR && u >= units1) {    // second problem: no split-K
       const int tile = u - units1;
       const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
-      m0 = tm * BM; n0 = tn * BN; kb0 = 0; kb1 = p.s2.total_k_blocks;
+      m0 = tm * TM; n0 = tn * BN; kb0 = 0; kb1 = p.s2.total_k_blocks;
       return;
     }
     const int tile = u / splits, z = u - tile * splits;
     const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
-    m0 = tm * BM; n0 = tn * BN;
+    m0 = tm * TM; n0 = tn * BN;
     kb0 = z * p.k_blocks_per_split;
     kb1 = min(p.total_k_blocks, kb0 + p.k_blocks_per_split);
   };
 
+  // measurement aid: CTA 0 stamps clock64 at the phase boundaries of each unit; slot layout trace[8 + 8 * unit + k]
+  long long* const tr = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
+  auto stamp = [&](int ui, int k) { if (tr && ui < 30) tr[8 + 8 * ui + k] = clock64(); };
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
   if (warp == 0) {
     // ===== TMA producer: warp-uniform loop, one elected lane issues =====
     {
       const bool leader = elect_one();
       int s = 0;
       uint32_t ph = 0;
-      for (int u = blockIdx.x; u < units; u += gridDim.x) {
+      int pui = 0;
+      for (int u = worker; u < units; u += workers, ++pui) {
         int m0, n0, kb0, kb1;
         decode(u, m0, n0, kb0, kb1);
         const CUtensorMap* ma = (PAIR && u >= units1) ? &mapA2 : &mapA;
         const CUtensorMap* mb = (PAIR && u >= units1) ? &mapB2 : &mapB;
+        const int ma0 = m0 + (int)crank * BM;          // this CTA's rows of A / columns of B
+        const int nb0 = n0 + (int)crank * BNL;
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty_bar + s, ph ^ 1);
+          mbar_wait(empty_bar + s, ph ^ 1);            // the pair's MMAs have released this CTA's slot
           if (leader) {
-          mbar_expect_tx(full_bar + s, STAGE_BYTES);
+          if (kb == kb0) stamp(pui, 0);
+          if (kb == kb1 - 1) stamp(pui, 1);
           unsigned char* sa = tiles + s * STAGE_BYTES;
           unsigned char* sb = sa + A_BYTES;
+          if (CTA2) {
+            // one barrier per stage, in the leader CTA: it expects the bytes of both CTAs
+            if (crank == 0) mbar_expect_tx(full_bar + s, 2 * STAGE_BYTES);
+            const uint32_t lbar = mapa_u32(smem_u32(full_bar + s), 0);
+            if (!A_MN) {
+              tma_load_2d_pair(sa, ma, lbar, kb * BK, ma0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BM / 64; ++c) tma_load_2d_pair(sa + c * (64 * BK * 2), ma, lbar, ma0 + c * 64, kb * BK);
+            }
+            if (!B_MN) {
+              tma_load_2d_pair(sb, mb, lbar, kb * BK, nb0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BNL / 64; ++c) tma_load_2d_pair(sb + c * (64 * BK * 2), mb, lbar, nb0 + c * 64, kb * BK);
+            }
+          } else {
+          mbar_expect_tx(full_bar + s, STAGE_BYTES);
           if (!A_MN) {
             tma_load_2d(sa, ma, full_bar + s, kb * BK, m0);
           } else {
@@ -305,6 +424,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, BN == 128 ? 2 : 0) gemm_tc_ker
             for (int c = 0; c < BN / 64; ++c) tma_load_2d(sb + c * (64 * BK * 2), mb, full_bar + s, n0 + c * 64, kb * BK);
           }
           }
+          }
           if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -314,7 +434,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, BN == 128 ? 2 : 0) gemm_tc_ker
     // The issue loop is on the critical path of every k-block (4 MMAs of 128 x BN x 16 take only ~128 BN/256 ns), so it is
     // kept to a wait, four descriptor adds and the instructions themselves: descriptors are built once and advanced by
     // adding the byte offset >> 4 to their start-address field (shared memory addresses fit its 14 bits without carry).
-    constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+    constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN, TM);
     constexpr uint32_t KSTEP_A = A_MN ? 2048u : 32u, KSTEP_B = B_MN ? 2048u : 32u;   // bytes per UMMA_K step
     const uint32_t tiles_addr = smem_u32(tiles);
     const uint64_t da0 = A_MN ? make_desc(tiles_addr, 64 * BK * 2, 1024) : make_desc(tiles_addr, 16, 1024);
@@ -322,7 +442,8 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, BN == 128 ? 2 : 0) gemm_tc_ker
     const bool leader = elect_one();
     int s = 0, ui = 0;
     uint32_t ph = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
+    // CTA pair: only the leader CTA issues (its MMAs read both CTAs' shared memory and write both CTAs' TMEM)
+    for (int u = (CTA2 && crank != 0) ? units : worker; u < units; u += workers, ++ui) {
       int m0, n0, kb0, kb1;
       decode(u, m0, n0, kb0, kb1);
       const int a = ui % ACC;
@@ -331,247 +452,326 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, BN == 128 ? 2 : 0) gemm_tc_ker
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
       uint32_t acc_flag = 0u;
+      if (leader) stamp(ui, 2);                    // accumulator stage available
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(full_bar + s, ph);
         tc_fence_after();
         if (leader) {
+          if (kb == kb0) stamp(ui, 3);             // first operands have landed
           const uint64_t da = da0 + (uint64_t)((uint32_t)s * (STAGE_BYTES >> 4));
           const uint64_t db = db0 + (uint64_t)((uint32_t)s * (STAGE_BYTES >> 4));
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_bf16(tmem_d, da + (uint64_t)(k * (KSTEP_A >> 4)), db + (uint64_t)(k * (KSTEP_B >> 4)), idesc, k == 0 ? acc_flag : 1u);
+            if (CTA2) umma_bf16_pair(tmem_d, da + (uint64_t)(k * (KSTEP_A >> 4)), db + (uint64_t)(k * (KSTEP_B >> 4)), idesc, k == 0 ? acc_flag : 1u);
+            else umma_bf16(tmem_d, da + (uint64_t)(k * (KSTEP_A >> 4)), db + (uint64_t)(k * (KSTEP_B >> 4)), idesc, k == 0 ? acc_flag : 1u);
           }
-          umma_commit(empty_bar + s);          // frees the smem slot once these MMAs have read it
+          // frees the smem slot (in both CTAs of a pair) once these MMAs have read it
+          if (CTA2) umma_commit_pair(empty_bar + s); else umma_commit(empty_bar + s);
         }
         acc_flag = 1u;
         if (++s == STAGES) { s = 0; ph ^= 1u; }
       }
-      if (leader) umma_commit(tmem_full + a);  // accumulator of this unit complete
+      if (leader) { if (CTA2) umma_commit_pair(tmem_full + a); else umma_commit(tmem_full + a); }  // accumulator of this unit complete
+      if (leader) stamp(ui, 4);                    // last MMA of the unit issued
       __syncwarp();
     }
+    if (CTA2 && crank == 0 && ui > 0) {
+      // the peer's epilogue warps arrive on this CTA's barriers: see the last hand-back before the barriers go away
+      mbar_wait(tmem_empty + ((ui - 1) % ACC), ((ui - 1) / ACC) & 1);
+    }
   } else {
-    // ===== epilogue: TMEM -> registers -> swizzled smem patch -> fused epilogue -> coalesced global =====
+    // ===== epilogue: TMEM -> registers -> fused epilogue -> global, one accumulator row per thread =====
+    // tcgen05.ld hands each thread 32 consecutive columns of ONE row: 64 bytes of a bf16 output (128 of an fp32 one), i.e.
+    // whole 32-byte sectors.  The thread finishes its row piece in registers and stores it with 256-bit (or 128-bit)
+    // accesses: no shared-memory transpose, no warp synchronisation, and every term of the fused epilogue that lives in
+    // global memory (old C, relu gate, addend) is requested before the TMEM wait.
+    constexpr bool E_GEN = EPI == 0, E_RMW = EPI == 0 || EPI == 2, E_F32 = EPI == 0 || EPI == 3, E_BF16 = EPI != 3;
     const int q = warp & 3;                  // TMEM lane quarter this warp may access
-    float* patch = stage + (warp - 2) * (32 * 32);          // this warp's 32 x 32 fp32 transpose patch
-    const int lr = lane >> 3, lc = lane & 7; // drain phase: lane handles the 16-byte column group lc of rows lr + 4 i
-    const size_t esz = p.c_f32 ? 4 : 2;
-    // vector path needs 16-byte aligned rows for every tensor touched with vector accesses
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.C) | (PAIR ? reinterpret_cast<uintptr_t>(p.s2.C) : 0) | ((size_t)p.ldc * esz)) & 15) == 0 &&
-                        (!p.e.bias || (reinterpret_cast<uintptr_t>(p.e.bias) & 15) == 0) &&
+    const size_t esz = E_GEN ? (p.c_f32 ? 4 : 2) : (E_F32 ? 4 : 2);
+    // vector path: 16-byte aligned rows for every tensor touched with vector accesses (al32: 32-byte, 256-bit accesses)
+    const uintptr_t all_ptrs = reinterpret_cast<uintptr_t>(p.C) | (PAIR ? reinterpret_cast<uintptr_t>(p.s2.C) : 0) | ((size_t)p.ldc * esz) |
+                               (p.e.gate ? (reinterpret_cast<uintptr_t>(p.e.gate) | ((size_t)p.e.gate_ld * esz)) : 0) |
+                               (p.e.c2 ? (reinterpret_cast<uintptr_t>(p.e.c2) | ((size_t)p.e.c2_ld * esz)) : 0) |
+                               ((size_t)p.c_block_off_or * 4);
+    const bool vec_ok = !E_GEN || (all_ptrs & 15) == 0 && (!p.e.bias || (reinterpret_cast<uintptr_t>(p.e.bias) & 15) == 0) &&
                         (!p.e.addend || ((reinterpret_cast<uintptr_t>(p.e.addend) | ((size_t)p.e.addend_ld * 4)) & 15) == 0) &&
-                        (!p.e.gate || ((reinterpret_cast<uintptr_t>(p.e.gate) | ((size_t)p.e.gate_ld * esz)) & 15) == 0) &&
-                        (!p.e.c2 || ((reinterpret_cast<uintptr_t>(p.e.c2) | ((size_t)p.e.c2_ld * esz)) & 15) == 0) &&
-                        (p.e.alpha_cols % 32 == 0) && (p.c_block_off_or & 3) == 0;
-    const float alpha0 = (p.e.alpha && p.e.alpha_cols == 0) ? __ldg(p.e.alpha) : 1.f;
+                        (p.e.alpha_cols % 32 == 0) && (p.c_block_cols % 32 == 0);
+    const bool al32 = (all_ptrs & 31) == 0;
+    const float alpha0 = (E_GEN && p.e.alpha && p.e.alpha_cols == 0) ? __ldg(p.e.alpha) : 1.f;
     int ui = 0;
-    for (int u = blockIdx.x; u < units; u += gridDim.x, ++ui) {
+    for (int u = worker; u < units; u += workers, ++ui) {
       int m0, n0, kb0, kb1;
       decode(u, m0, n0, kb0, kb1);
+      m0 += (int)crank * BM;                  // CTA pair: this CTA's TMEM holds rows 128 r .. of the unit
       // the few things in which the launch's second problem differs from the first
       const bool sec = PAIR && u >= units1;
       const int uM = sec ? p.s2.M : p.M;
       void* const uC = sec ? p.s2.C : p.C;
-      const int uAcc = sec ? p.s2.accumulate : p.e.accumulate;
+      const int uAcc = E_RMW ? (sec ? p.s2.accumulate : p.e.accumulate) : 0;
       const int acc_stage = ui % ACC;
-      // read-modify-write epilogues (bf16 C): pull the old C / gate tiles into L2 while the MMAs of this unit are still running
-      if (!p.c_f32 && (uAcc || p.e.gate)) {
-        const int et = (warp - 2) * 32 + lane;
-        constexpr int LPR = BN / 64;                    // 128-byte lines per tile row
-        for (int id = et; id < BM * LPR; id += 32 * EPIW) {
-          const int row = m0 + id / LPR, col = n0 + (id % LPR) * 64;
-          if (row < uM && col < p.N) {
-            if (uAcc) asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const bf16*>(uC) + (size_t)row * p.ldc + col));
-            if (p.e.gate) asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const bf16*>(p.e.gate) + (size_t)row * p.e.gate_ld + col));
-          }
-        }
-      }
-      mbar_wait(tmem_full + acc_stage, (ui / ACC) & 1);
-      tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc_stage * BN) + ((uint32_t)(q * 32) << 16);
       const int rbase = m0 + q * 32;
+      const int r = rbase + lane;               // this thread's row
+      const bool valid = r < uM && !(p.dbg & 1);
+      const int rc = min(r, uM - 1);            // clamped (loads only)
       // 32-column blocks this warp really has to move (none if its rows or the unit's K range are empty)
       const int nblk = (rbase < uM && kb1 > kb0) ? min(BN / 32, (p.N - n0 + 31) / 32) : 0;
-      // per-row terms of the 8 rows this lane drains, hoisted out of the column loop
-      float rs[8];
-      int arow[8], r2[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = min(rbase + lr + 4 * i, uM - 1);
-        rs[i] = (p.e.addend && p.e.row_scale) ? __ldg(p.e.row_scale + r) : 1.f;
-        arow[i] = p.e.addend ? (r / p.e.addend_rows) * p.e.addend_ld : 0;
-        r2[i] = -1;
-        if (p.e.c2) {
-          const int rr = r % p.e.c2_rows_in;
-          if (rr < p.e.c2_rows_keep) r2[i] = (r / p.e.c2_rows_in) * p.e.c2_rows_keep + rr;
-        }
-      }
-      uint32_t acc[32];
       constexpr int CSTEP = EPIW / 4;                      // warps sharing a lane quarter interleave the column blocks
       const int cfirst = (warp - 2) >> 2;
-      if (cfirst < nblk) tmem_ld32_issue(tmem_acc + (uint32_t)(cfirst * 32), acc);
-#pragma unroll 1
-      for (int cc = cfirst; cc < nblk; cc += CSTEP) {
-        const int c = n0 + cc * 32 + lc * 4;               // first of this lane's 4 columns in the drain phase
-        const bool vec = vec_ok && c + 4 <= p.N;
-        // column terms: issued before the TMEM wait so their latency is hidden
-        float al = alpha0;
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (vec) {
-          if (p.e.alpha && p.e.alpha_cols) al = __ldg(p.e.alpha + c / p.e.alpha_cols);
-          if (p.e.bias) bv = __ldg(reinterpret_cast<const float4*>(p.e.bias + c));
+      // read-modify-write epilogues (bf16 C): pull this thread's pieces of the old C / gate rows into L2 while the MMAs of this
+      // unit are still running
+      if (E_RMW && !p.c_f32 && (uAcc || p.e.gate) && valid) {
+        for (int cc = cfirst; cc < nblk; cc += CSTEP) {
+          const int c = n0 + cc * 32;
+          if (uAcc) asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const bf16*>(uC) + (size_t)r * p.ldc + c));
+          if (p.e.gate) asm volatile("prefetch.global.L2 [%0];" ::"l"(static_cast<const bf16*>(p.e.gate) + (size_t)r * p.e.gate_ld + c));
         }
-        // bf16 outputs: the read-modify-write terms (old C for accumulate, the relu gate) are requested here too -- their
-        // DRAM latency then runs under the TMEM wait and the transpose instead of stalling the drain
-        const int rcl = min(rbase + lr, uM - 1);      // clamped first row of this lane (loads only)
-        uint2 oldc[8], gt[8];
-        const bool pre_acc = vec && !p.c_f32 && uAcc, pre_gate = vec && !p.c_f32 && p.e.gate;
+      }
+      // per-row terms
+      const float rs = (E_RMW && p.e.addend && p.e.row_scale) ? __ldg(p.e.row_scale + rc) : 1.f;
+      const float* arow = (E_RMW && p.e.addend) ? p.e.addend + (size_t)(rc / p.e.addend_rows) * p.e.addend_ld : nullptr;
+      long long r2 = -1;
+      if (E_RMW && p.e.c2) {
+        const int rr = r % p.e.c2_rows_in;
+        if (rr < p.e.c2_rows_keep) r2 = (long long)(r / p.e.c2_rows_in) * p.e.c2_rows_keep + rr;
+      }
+      // this warp's bias columns of the unit (<= 4 blocks of 32) go to its private shared-memory strip while the MMAs still run:
+      // the per-block reads are then broadcast LDS instead of one L2 round trip per block
+      float* const bsm = bias_stage + (warp - 2) * 128;
+      if (p.e.bias && vec_ok) {
+        const int bc = n0 + (cfirst + (lane >> 3) * CSTEP) * 32 + (lane & 7) * 4;
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bc + 4 <= p.N && (lane >> 3) * CSTEP + cfirst < BN / 32) bv = __ldg(reinterpret_cast<const float4*>(p.e.bias + bc));
+        __syncwarp();                            // the previous unit's reads of the strip are done
+        reinterpret_cast<float4*>(bsm)[lane] = bv;
+        __syncwarp();
+      }
+      if (warp == 2 && lane == 0) stamp(ui, 5);    // epilogue ready for this unit
+      mbar_wait(tmem_full + acc_stage, (ui / ACC) & 1);
+      tc_fence_after();
+      if (warp == 2 && lane == 0) stamp(ui, 6);    // accumulator complete
+      const uint32_t tmem_acc = tmem_base + (uint32_t)(acc_stage * BN) + ((uint32_t)(q * 32) << 16);
+      // Row pointers of this thread for the unit (column n0); the block loop only adds its column offset.  The loop is fully
+      // unrolled over the warp's <= 4 blocks with two alternating accumulator register sets, so the next block's tcgen05.ld
+      // lands while the current block is processed and nothing is copied.  The epilogue is bound by instruction issue (two
+      // warps per scheduler, dependent chains), hence packed fp32x2 arithmetic, relu folded into the bf16 conversion and
+      // the relu gate applied to the packed result.
+      unsigned char* const crow = static_cast<unsigned char*>(uC) + ((size_t)rc * p.ldc + n0) * esz;
+      unsigned char* const c2row = r2 >= 0 ? static_cast<unsigned char*>(p.e.c2) + ((size_t)r2 * p.e.c2_ld + n0) * esz : nullptr;
+      const unsigned char* const grow = (E_RMW && p.e.gate) ? static_cast<const unsigned char*>(p.e.gate) + ((size_t)rc * p.e.gate_ld + n0) * esz : nullptr;
+      const float* const arow0 = arow ? arow + n0 : nullptr;
+      const bool f_relu = (E_GEN || EPI == 1) && p.e.relu != 0, f_bias = p.e.bias != nullptr, f_alpha = E_GEN && p.e.alpha != nullptr;
+      const bool f_f32 = E_GEN ? p.c_f32 != 0 : EPI == 3;
+      constexpr int NB = (BN / 32) / CSTEP;                // blocks per warp and unit
+      uint32_t accA[32], accB[32];
+      auto block = [&](uint32_t (&x)[32], uint32_t (&nxt)[32], const int cc, const int slot) {
+        const int c = n0 + cc * 32;                        // first of this thread's 32 columns
+        const int co = cc * 32;                            // ... relative to the row pointers
+        const bool vec = vec_ok && c + 32 <= p.N;
+        // terms from global memory: requested before the TMEM wait so that their latency is hidden
+        // (one 128-byte register buffer: the old C + gate pieces of a bf16 read-modify-write epilogue, or the addend piece)
+        const float al = (vec && f_alpha && p.e.alpha_cols) ? __ldg(p.e.alpha + c / p.e.alpha_cols) : alpha0;
+        const bool pre_acc = E_RMW && vec && !f_f32 && uAcc, pre_gate = E_RMW && vec && !f_f32 && grow;
+        const bool pre_add = E_RMW && vec && arow0 && !pre_acc && !pre_gate, late_add = E_RMW && vec && arow0 && !pre_add;
+        uint4 pre[8];
         if (pre_acc) {
-          const bf16* c0p = static_cast<const bf16*>(uC) + c;
+          const uint4* src = reinterpret_cast<const uint4*>(crow + (size_t)co * 2);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) oldc[i] = ldg_v2(c0p + (size_t)min(rcl + 4 * i, uM - 1) * p.ldc);
+          for (int g = 0; g < 4; ++g) pre[g] = ldg_v4u(src + g);
         }
         if (pre_gate) {
-          const bf16* g0 = static_cast<const bf16*>(p.e.gate) + c;
+          const uint4* src = reinterpret_cast<const uint4*>(grow + (size_t)co * 2);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) gt[i] = ldg_nc_v2(g0 + (size_t)min(rcl + 4 * i, uM - 1) * p.e.gate_ld);
+          for (int g = 0; g < 4; ++g) pre[4 + g] = ldg_nc_v4u(src + g);
         }
-        tmem_ld32_wait(acc);
-        // transpose in: lane = row, 16-byte group g lands at slot g ^ (row & 7)  (conflict-free both ways)
-        {
-          float4* prow = reinterpret_cast<float4*>(patch + lane * 32);
+        if (pre_add) {
 #pragma unroll
-          for (int g = 0; g < 8; ++g)
-            prow[g ^ (lane & 7)] = make_float4(__uint_as_float(acc[4 * g]), __uint_as_float(acc[4 * g + 1]),
-                                               __uint_as_float(acc[4 * g + 2]), __uint_as_float(acc[4 * g + 3]));
+          for (int g = 0; g < 8; ++g) pre[g] = ldg_nc_v4u(arow0 + co + 4 * g);
         }
+        tmem_ld32_wait(x);
         if (cc + CSTEP < nblk) {
-          tmem_ld32_issue(tmem_acc + (uint32_t)((cc + CSTEP) * 32), acc);   // overlaps the drain below
+          if (!(p.dbg & 2)) tmem_ld32_issue(tmem_acc + (uint32_t)((cc + CSTEP) * 32), nxt);   // overlaps the work below
         } else {
           // every TMEM read of this unit has completed: hand the accumulator stage back to the MMA issuer early
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty + acc_stage);
+          if (lane == 0) { if (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty + acc_stage), 0)); else mbar_arrive(tmem_empty + acc_stage); }
         }
-        __syncwarp();
-        // column-block scatter (weight gradients of side-by-side layers): block j of C lives at C + c_block_off[j]
-        long long cboff = 0;
-        int cl = c;
-        if (p.c_block_cols) { const int jb = c / p.c_block_cols; cboff = p.c_block_off[jb]; cl = c - jb * p.c_block_cols; }
-        if (!vec) {
+        if (E_GEN && !vec) {
           // ragged edge / unaligned tensors: generic per-element path (kept out of line: it must not bloat the hot loop)
-          if (c < p.N) {
-#pragma unroll 1
-            for (int i = 0; i < 8; ++i) {
-              const int rl = lr + 4 * i, r = rbase + rl;
-              if (r < uM) epi_slow(p, uC, uAcc, r, c, reinterpret_cast<const float4*>(patch + rl * 32)[lc ^ (rl & 7)]);
-            }
+          if (valid) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)      // unrolled: x[] must stay in registers
+              if (c + 4 * g < p.N)
+                epi_slow(p, uC, uAcc, r, c + 4 * g, make_float4(__uint_as_float(x[4 * g]), __uint_as_float(x[4 * g + 1]),
+                                                              __uint_as_float(x[4 * g + 2]), __uint_as_float(x[4 * g + 3])));
           }
-        } else {
-          // Staged, branch-free drain: every load of a stage is issued before the first use (shared-memory and global
-          // latencies are paid once per stage, not once per row); rows past M are clamped for loads, predicated for stores.
-          float4 x[8];
-          const uint32_t pbase = smem_u32(patch);
+          return;
+        }
+        if (pre_add) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rl = lr + 4 * i;
-            x[i] = lds_v4(pbase + (uint32_t)(rl * 128 + ((lc ^ (rl & 7)) << 4)));
+          for (int g = 0; g < 8; ++g) {
+            x[4 * g] = __float_as_uint(fmaf(rs, __uint_as_float(pre[g].x), __uint_as_float(x[4 * g])));
+            x[4 * g + 1] = __float_as_uint(fmaf(rs, __uint_as_float(pre[g].y), __uint_as_float(x[4 * g + 1])));
+            x[4 * g + 2] = __float_as_uint(fmaf(rs, __uint_as_float(pre[g].z), __uint_as_float(x[4 * g + 2])));
+            x[4 * g + 3] = __float_as_uint(fmaf(rs, __uint_as_float(pre[g].w), __uint_as_float(x[4 * g + 3])));
           }
-          if (p.e.addend) {
-            float4 a[8];
+        } else if (late_add) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) a[i] = ldg_nc_v4(p.e.addend + arow[i] + c);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              x[i].x = fmaf(rs[i], a[i].x, x[i].x); x[i].y = fmaf(rs[i], a[i].y, x[i].y);
-              x[i].z = fmaf(rs[i], a[i].z, x[i].z); x[i].w = fmaf(rs[i], a[i].w, x[i].w);
-            }
+          for (int g = 0; g < 8; ++g) {
+            const float4 a = ldg_nc_v4(arow0 + co + 4 * g);
+            x[4 * g] = __float_as_uint(fmaf(rs, a.x, __uint_as_float(x[4 * g])));
+            x[4 * g + 1] = __float_as_uint(fmaf(rs, a.y, __uint_as_float(x[4 * g + 1])));
+            x[4 * g + 2] = __float_as_uint(fmaf(rs, a.z, __uint_as_float(x[4 * g + 2])));
+            x[4 * g + 3] = __float_as_uint(fmaf(rs, a.w, __uint_as_float(x[4 * g + 3])));
           }
+        }
+        if (f_bias) {
+          const float4* bsrc = reinterpret_cast<const float4*>(bsm + slot * 32);
+          if (f_alpha) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            x[i].x = fmaf(x[i].x, al, bv.x); x[i].y = fmaf(x[i].y, al, bv.y); x[i].z = fmaf(x[i].z, al, bv.z); x[i].w = fmaf(x[i].w, al, bv.w);
-          }
-          if (p.e.relu) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              x[i].x = fmaxf(x[i].x, 0.f); x[i].y = fmaxf(x[i].y, 0.f); x[i].z = fmaxf(x[i].z, 0.f); x[i].w = fmaxf(x[i].w, 0.f);
-            }
-          }
-          const int rows_ok = uM - rbase - lr;        // row i of this lane is valid iff 4 i < rows_ok
-          if (p.c_f32) {
-            float* dst0 = static_cast<float*>(uC) + cboff + cl;
-            if (p.atomic_out) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (4 * i < rows_ok) red_add_v4(dst0 + (size_t)(rbase + lr + 4 * i) * p.ldc, x[i]);
-            } else {
-              if (uAcc) {
-                float4 o[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) o[i] = ldg_v4(dst0 + (size_t)min(rcl + 4 * i, uM - 1) * p.ldc);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { x[i].x += o[i].x; x[i].y += o[i].y; x[i].z += o[i].z; x[i].w += o[i].w; }
-              }
-              if (p.e.gate) {
-                const float* g0 = static_cast<const float*>(p.e.gate) + c;
-                float4 g[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) g[i] = ldg_nc_v4(g0 + (size_t)min(rcl + 4 * i, uM - 1) * p.e.gate_ld);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                  x[i].x = g[i].x > 0.f ? x[i].x : 0.f; x[i].y = g[i].y > 0.f ? x[i].y : 0.f;
-                  x[i].z = g[i].z > 0.f ? x[i].z : 0.f; x[i].w = g[i].w > 0.f ? x[i].w : 0.f;
-                }
-              }
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (4 * i < rows_ok) stg_v4(dst0 + (size_t)(rbase + lr + 4 * i) * p.ldc, x[i]);
-              if (p.e.c2) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  if (4 * i < rows_ok && r2[i] >= 0) stg_v4(static_cast<float*>(p.e.c2) + (size_t)r2[i] * p.e.c2_ld + c, x[i]);
-              }
+            for (int g = 0; g < 8; ++g) {
+              const float4 bv = bsrc[g];                                                    // warp-uniform address: broadcast
+              ffma2(x[4 * g], x[4 * g + 1], al, bv.x, bv.y); ffma2(x[4 * g + 2], x[4 * g + 3], al, bv.z, bv.w);
             }
           } else {
-            bf16* dst0 = static_cast<bf16*>(uC) + c;
-            if (uAcc) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) { x[i].x += bf_lo(oldc[i].x); x[i].y += bf_hi(oldc[i].x); x[i].z += bf_lo(oldc[i].y); x[i].w += bf_hi(oldc[i].y); }
+            for (int g = 0; g < 8; ++g) {
+              const float4 bv = bsrc[g];
+              fadd2(x[4 * g], x[4 * g + 1], bv.x, bv.y); fadd2(x[4 * g + 2], x[4 * g + 3], bv.z, bv.w);
             }
-            if (p.e.gate) {
+          }
+        } else if (f_alpha) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                x[i].x = bf_lo(gt[i].x) > 0.f ? x[i].x : 0.f; x[i].y = bf_hi(gt[i].x) > 0.f ? x[i].y : 0.f;
-                x[i].z = bf_lo(gt[i].y) > 0.f ? x[i].z : 0.f; x[i].w = bf_hi(gt[i].y) > 0.f ? x[i].w : 0.f;
+          for (int j = 0; j < 32; j += 2) ffma2(x[j], x[j + 1], al, 0.f, 0.f);
+        }
+        if (E_F32 && f_f32) {
+          if (f_relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = __float_as_uint(fmaxf(__uint_as_float(x[j]), 0.f));
+          }
+          // column-block scatter (weight gradients of side-by-side layers): block j of C lives at C + c_block_off[j]
+          float* dst = reinterpret_cast<float*>(crow) + co;
+          if (p.c_block_cols) { const int jb = c / p.c_block_cols; dst += p.c_block_off[jb] - (long long)jb * p.c_block_cols; }
+          if (p.atomic_out) {
+            if (valid) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                red_add_v4(dst + 4 * g, make_float4(__uint_as_float(x[4 * g]), __uint_as_float(x[4 * g + 1]), __uint_as_float(x[4 * g + 2]),
+                                                    __uint_as_float(x[4 * g + 3])));
+            }
+          } else {
+            if (E_GEN && uAcc) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 o = ldg_v4(dst + 4 * g);
+                fadd2(x[4 * g], x[4 * g + 1], o.x, o.y); fadd2(x[4 * g + 2], x[4 * g + 3], o.z, o.w);
               }
             }
-            uint2 w[8];
+            if (E_GEN && grow) {
+              const float* g0 = reinterpret_cast<const float*>(grow) + co;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = make_uint2(pack_bf16(x[i].x, x[i].y), pack_bf16(x[i].z, x[i].w));
+              for (int g = 0; g < 8; ++g) {
+                const float4 gv = ldg_nc_v4(g0 + 4 * g);
+                x[4 * g] = gv.x > 0.f ? x[4 * g] : 0u; x[4 * g + 1] = gv.y > 0.f ? x[4 * g + 1] : 0u;
+                x[4 * g + 2] = gv.z > 0.f ? x[4 * g + 2] : 0u; x[4 * g + 3] = gv.w > 0.f ? x[4 * g + 3] : 0u;
+              }
+            }
+            if (valid) {
+              if (al32) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (4 * i < rows_ok) stg_v2(dst0 + (size_t)(rbase + lr + 4 * i) * p.ldc, w[i]);
-            if (p.e.c2) {
+                for (int g = 0; g < 4; ++g) stg_v8u(dst + 8 * g, x + 8 * g);
+              } else {
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (4 * i < rows_ok && r2[i] >= 0) stg_v2(static_cast<bf16*>(p.e.c2) + (size_t)r2[i] * p.e.c2_ld + c, w[i]);
+                for (int g = 0; g < 8; ++g) stg_v4u(dst + 4 * g, x + 4 * g);
+              }
+              if (E_GEN && c2row) {
+                float* d2 = reinterpret_cast<float*>(c2row) + co;
+#pragma unroll
+                for (int g = 0; g < 8; ++g) stg_v4u(d2 + 4 * g, x + 4 * g);
+              }
+            }
+          }
+        } else if (E_BF16) {
+          uint32_t w[16];
+          if (f_relu && !pre_acc) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = pack_bf16_relu(__uint_as_float(x[2 * j]), __uint_as_float(x[2 * j + 1]));
+          } else {
+            if (f_relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = __float_as_uint(fmaxf(__uint_as_float(x[j]), 0.f));
+            }
+            if (pre_acc) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                fadd2(x[8 * g], x[8 * g + 1], bf_lo(pre[g].x), bf_hi(pre[g].x)); fadd2(x[8 * g + 2], x[8 * g + 3], bf_lo(pre[g].y), bf_hi(pre[g].y));
+                fadd2(x[8 * g + 4], x[8 * g + 5], bf_lo(pre[g].z), bf_hi(pre[g].z)); fadd2(x[8 * g + 6], x[8 * g + 7], bf_lo(pre[g].w), bf_hi(pre[g].w));
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) w[j] = pack_bf16(__uint_as_float(x[2 * j]), __uint_as_float(x[2 * j + 1]));
+          }
+          if (pre_gate) {
+            // gate > 0 per bf16 half, applied to the packed result (a rejected element becomes +0)
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              w[4 * g] &= bf16x2_gt0_mask(pre[4 + g].x); w[4 * g + 1] &= bf16x2_gt0_mask(pre[4 + g].y);
+              w[4 * g + 2] &= bf16x2_gt0_mask(pre[4 + g].z); w[4 * g + 3] &= bf16x2_gt0_mask(pre[4 + g].w);
+            }
+          }
+          if (valid) {
+            bf16* dst = reinterpret_cast<bf16*>(crow) + co;
+            if (al32) { stg_v8u(dst, w); stg_v8u(dst + 16, w + 8); }
+            else {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) stg_v4u(dst + 8 * g, w + 4 * g);
+            }
+            if (E_RMW && c2row) {
+              bf16* d2 = reinterpret_cast<bf16*>(c2row) + co;
+              if (al32) { stg_v8u(d2, w); stg_v8u(d2 + 16, w + 8); }
+              else {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) stg_v4u(d2 + 8 * g, w + 4 * g);
+              }
             }
           }
         }
-        __syncwarp();    // the patch is rewritten by the next block
+      };
+      if (cfirst < nblk && !(p.dbg & 2)) tmem_ld32_issue(tmem_acc + (uint32_t)(cfirst * 32), accA);
+      if constexpr (EPI == 1 || EPI == 3) {
+        // lean kinds: all blocks unrolled
+#pragma unroll
+        for (int i = 0; i < NB; i += 2) {
+          const int cc = cfirst + i * CSTEP;
+          if (cc < nblk) block(accA, accB, cc, i);
+          if (cc + CSTEP < nblk) block(accB, accA, cc + CSTEP, i + 1);
+        }
+      } else {
+        // unrolled by two -- one round trip through the two register sets (all four would need > 168 registers, the most a
+        // 10-warp CTA can have)
+#pragma unroll 1
+        for (int i = 0; i < NB; i += 2) {
+          const int cc = cfirst + i * CSTEP;
+          if (cc < nblk) block(accA, accB, cc, i);
+          if (cc + CSTEP < nblk) block(accB, accA, cc + CSTEP, i + 1);
+        }
       }
       if (cfirst >= nblk) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty + acc_stage);
+        if (lane == 0) { if (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(tmem_empty + acc_stage), 0)); else mbar_arrive(tmem_empty + acc_stage); }
       }
+      if (warp == 2 && lane == 0) stamp(ui, 7);    // unit stored
     }  // units
   }
+  if (tr && threadIdx.x == 0) tr[1] = clock64();
   tc_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all(); else __syncthreads();     // pair: neither CTA's shared memory / TMEM goes away under the other
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (CTA2) tmem_dealloc_pair(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (tr && threadIdx.x == 0) tr[2] = clock64();
 }
 
 // ------------------------------------------------------------------ host side
@@ -619,45 +819,96 @@ int make_map(CUtensorMap* out, const void* base, long long inner, long long oute
   return REGAT_OK;
 }
 
-template <int BN, int STAGES, int ACC, int EPIW>
-int launch_cfg(bool a_mn, bool b_mn, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, const CUtensorMap& ma2,
-               const CUtensorMap& mb2, int ctas, cudaStream_t st) {
-  const bool pair = p.s2.units > 0;
-  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BN * BK * 2) + EPIW * EPI_PATCH_BYTES + (2 * STAGES + 2 * ACC) * 8 + 16;
+template <int BN, int STAGES, int ACC, int EPIW, bool CTA2, bool AM, bool BMN, bool PR, int EPI>
+int launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, const CUtensorMap& ma2, const CUtensorMap& mb2, int ctas,
+               cudaStream_t st) {
+  constexpr int BNL = CTA2 ? BN / 2 : BN;
+  constexpr size_t smem = (size_t)STAGES * (BM * BK * 2 + BNL * BK * 2) + (2 * STAGES + 2 * ACC) * 8 + 16 + EPIW * 512;
+  auto kern = gemm_tc_kernel<BN, STAGES, ACC, EPIW, AM, BMN, PR, CTA2, EPI>;
   // the shared-memory attribute is per (function, device): one flag per device, set under a lock
-#define REGAT_TC_CASE(AM, BMN)                                                                              \
-  if (pair) REGAT_TC_CASE2(AM, BMN, true) else REGAT_TC_CASE2(AM, BMN, false)
-#define REGAT_TC_CASE2(AM, BMN, PR)                                                                         \
-  {                                                                                                         \
-    auto kern = gemm_tc_kernel<BN, STAGES, ACC, EPIW, AM, BMN, PR>;                                               \
-    static std::mutex mu;                                                                                   \
-    static bool attr_set[64] = {};                                                                          \
-    int dev = 0;                                                                                            \
-    REGAT_CUDA(cudaGetDevice(&dev));                                                                        \
-    {                                                                                                       \
-      std::lock_guard<std::mutex> lk(mu);                                                                   \
-      if (dev < 0 || dev >= 64 || !attr_set[dev]) {                                                         \
-        REGAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;                                                     \
-      }                                                                                                     \
-    }                                                                                                       \
-    kern<<<ctas, 64 + 32 * EPIW, smem, st>>>(ma, mb, p, ma2, mb2);                                                \
+  static std::mutex mu;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  REGAT_CUDA(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      REGAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
   }
-  if (!a_mn && b_mn) REGAT_TC_CASE(false, true)
-  else if (!a_mn && !b_mn) REGAT_TC_CASE(false, false)
-  else if (a_mn && b_mn) REGAT_TC_CASE(true, true)
-  else REGAT_TC_CASE(true, false)
-#undef REGAT_TC_CASE
-#undef REGAT_TC_CASE2
+  if (CTA2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)ctas, 1, 1); cfg.blockDim = dim3(64 + 32 * EPIW, 1, 1);
+    cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    REGAT_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, p, ma2, mb2));
+  } else {
+    kern<<<ctas, 64 + 32 * EPIW, smem, st>>>(ma, mb, p, ma2, mb2);
+  }
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
+
+// two-problem launches exist for the 256-wide tiles only, and only with the kinds the engine pairs (2) or the generic one
+template <int BN, int STAGES, int ACC, int EPIW, bool CTA2, bool AM, bool BMN>
+int launch_majors(bool pair, int epi, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, const CUtensorMap& ma2,
+                  const CUtensorMap& mb2, int ctas, cudaStream_t st) {
+  if (pair) {
+    if constexpr (BN == 256) {
+      if (epi == 2) return launch_one<BN, STAGES, ACC, EPIW, CTA2, AM, BMN, true, 2>(ma, mb, p, ma2, mb2, ctas, st);
+      return launch_one<BN, STAGES, ACC, EPIW, CTA2, AM, BMN, true, 0>(ma, mb, p, ma2, mb2, ctas, st);
+    } else {
+      REGAT_REQUIRE(false, REGAT_ERR_UNSUPPORTED, "gemm_tc: two-problem launches need 256-wide tiles");
+    }
+  }
+  switch (epi) {
+    case 1: return launch_one<BN, STAGES, ACC, EPIW, CTA2, AM, BMN, false, 1>(ma, mb, p, ma2, mb2, ctas, st);
+    case 2: return launch_one<BN, STAGES, ACC, EPIW, CTA2, AM, BMN, false, 2>(ma, mb, p, ma2, mb2, ctas, st);
+    case 3: return launch_one<BN, STAGES, ACC, EPIW, CTA2, AM, BMN, false, 3>(ma, mb, p, ma2, mb2, ctas, st);
+    default: return launch_one<BN, STAGES, ACC, EPIW, CTA2, AM, BMN, false, 0>(ma, mb, p, ma2, mb2, ctas, st);
+  }
+}
+
+template <int BN, int STAGES, int ACC, int EPIW, bool CTA2 = false>
+int launch_cfg(bool a_mn, bool b_mn, int epi, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, const CUtensorMap& ma2,
+               const CUtensorMap& mb2, int ctas, cudaStream_t st) {
+  const bool pair = p.s2.units > 0;
+  if (!a_mn && b_mn) return launch_majors<BN, STAGES, ACC, EPIW, CTA2, false, true>(pair, epi, ma, mb, p, ma2, mb2, ctas, st);
+  if (!a_mn && !b_mn) return launch_majors<BN, STAGES, ACC, EPIW, CTA2, false, false>(pair, epi, ma, mb, p, ma2, mb2, ctas, st);
+  if (a_mn && b_mn) return launch_majors<BN, STAGES, ACC, EPIW, CTA2, true, true>(pair, epi, ma, mb, p, ma2, mb2, ctas, st);
+  return launch_majors<BN, STAGES, ACC, EPIW, CTA2, true, false>(pair, epi, ma, mb, p, ma2, mb2, ctas, st);
+}
+
+// Smallest epilogue kind that covers a call (see the kernel's EPI parameter); `acc2`: a paired second problem accumulates.
+int epi_kind(const TcParams& p, bool pair, int acc2, const void* C2) {
+  const EpiArgs& e = p.e;
+  static const int force = [] { const char* s = getenv("REGAT_TC_EPI"); return s ? atoi(s) : -1; }();
+  if (force == 0) return 0;
+  const size_t esz = p.c_f32 ? 4 : 2;
+  uintptr_t a = reinterpret_cast<uintptr_t>(p.C) | reinterpret_cast<uintptr_t>(C2) | ((size_t)p.ldc * esz) | ((size_t)p.c_block_off_or * 4);
+  if (e.gate) a |= reinterpret_cast<uintptr_t>(e.gate) | ((size_t)e.gate_ld * esz);
+  if (e.c2) a |= reinterpret_cast<uintptr_t>(e.c2) | ((size_t)e.c2_ld * esz);
+  if (e.bias) a |= reinterpret_cast<uintptr_t>(e.bias);
+  if (e.addend) a |= reinterpret_cast<uintptr_t>(e.addend) | ((size_t)e.addend_ld * 4);
+  if ((a & 15) != 0 || p.N % 32 != 0 || e.alpha || p.c_block_cols % 32 != 0) return 0;
+  const bool rmw = e.addend || e.gate || e.c2 || e.accumulate || acc2;
+  if (p.c_f32) return (rmw || e.relu || pair) ? 0 : 3;
+  return rmw ? 2 : (pair ? 2 : 1);
+}
+
+long long* g_trace = nullptr;   // regat_gemm_trace
 
 struct Prepared {
   CUtensorMap ma, mb;
   TcParams p;
   bool a_mn, b_mn;
   int bn;
+  bool cta2;     // 256-row units on CTA pairs (cta_group::2)
 };
 
 // tile width, split-K and tensor maps of one problem; zeroes split-K destinations on `st`
@@ -671,12 +922,16 @@ int prepare(int transA, int transB, int M, int N, int K, const void* A, int lda,
   // tile width: 256 when there are enough column tiles to keep >= 1 wave busy, else 128
   static const int force_bn_env = [] { const char* s = getenv("REGAT_TC_BN"); return s ? atoi(s) : 0; }();
   const int force_bn = force_bn_arg ? force_bn_arg : force_bn_env;
-  const int tiles_m = ceil_div(M, BM);
+  int tiles_m = ceil_div(M, BM);
   int bn = (force_bn == 64 || force_bn == 128 || force_bn == 256) ? force_bn : ((N >= 256 && tiles_m * ceil_div(N, 256) >= num_sms()) ? 256 : 128);
   // skinny problems (a batch-sized M, long K): the 128-wide tiling leaves most SMs idle behind a serial K loop that is
   // bound by TMA latency at 3 stages -- narrower tiles double the CTAs and the 24 KB stages allow an 8-deep ring
   static const int skinny = [] { const char* s = getenv("REGAT_TC_SKINNY"); return s ? atoi(s) : 1; }();
   if (!force_bn && skinny && bn == 128 && tiles_m <= 2 && tiles_m * ceil_div(N, 128) * 2 <= num_sms() && K >= 512) bn = 64;
+  // 256-wide tiles run on CTA pairs: a unit is 256 x 256, each CTA of the pair loads half of it (REGAT_TC_CTA2=0: single CTAs)
+  static const int cta2_env = [] { const char* s = getenv("REGAT_TC_CTA2"); return s ? atoi(s) : 1; }();
+  const bool cta2 = bn == 256 && cta2_env != 0;
+  if (cta2) tiles_m = ceil_div(M, 2 * BM);
   const int tiles_n = ceil_div(N, bn);
   const int total_kb = ceil_div(K, BK);
   // split-K only for plain fp32 targets (weight gradients: few output tiles, very long K): fill ~2 CTAs per SM
@@ -692,7 +947,7 @@ int prepare(int transA, int transB, int M, int N, int K, const void* A, int lda,
   splits = ceil_div(total_kb, kbps);
 
   if (!a_mn) REGAT_TRY(make_map(&out.ma, A, K, M, lda, BM)); else REGAT_TRY(make_map(&out.ma, A, M, K, lda, BK));
-  if (!b_mn) REGAT_TRY(make_map(&out.mb, B, K, N, ldb, bn)); else REGAT_TRY(make_map(&out.mb, B, N, K, ldb, BK));
+  if (!b_mn) REGAT_TRY(make_map(&out.mb, B, K, N, ldb, cta2 ? bn / 2 : bn)); else REGAT_TRY(make_map(&out.mb, B, N, K, ldb, BK));
 
   TcParams& p = out.p;
   memset(&p, 0, sizeof(p));
@@ -712,7 +967,10 @@ int prepare(int transA, int transB, int M, int N, int K, const void* A, int lda,
       REGAT_CUDA(cudaMemset2DAsync(static_cast<float*>(C) + p.c_block_off[j], (size_t)ldc * 4, 0, (size_t)bw * 4, (size_t)M, st));
   }
   p.tiles_m = tiles_m; p.tiles_n = tiles_n; p.splits = splits;
-  out.a_mn = a_mn; out.b_mn = b_mn; out.bn = bn;
+  p.trace = g_trace;
+  static const int dbg_env = [] { const char* s = getenv("REGAT_TC_DBG"); return s ? atoi(s) : 0; }();
+  p.dbg = dbg_env;
+  out.a_mn = a_mn; out.b_mn = b_mn; out.bn = bn; out.cta2 = cta2;
   return REGAT_OK;
 }
 
@@ -729,12 +987,17 @@ int launch_prepared(const Prepared& x, const Prepared* y, cudaStream_t st) {
   const int sms = std::max(1, num_sms() - reserve);
   const CUtensorMap& ma2 = y ? y->ma : x.ma;
   const CUtensorMap& mb2 = y ? y->mb : x.mb;
-  if (x.bn == 256) return launch_cfg<256, 4, 2, 8>(x.a_mn, x.b_mn, x.ma, x.mb, p, ma2, mb2, std::min(units, sms), st);
-  if (x.bn == 64) return launch_cfg<64, 8, 2, 4>(x.a_mn, x.b_mn, x.ma, x.mb, p, ma2, mb2, std::min(units, sms), st);
-  return launch_cfg<128, 3, 2, 4>(x.a_mn, x.b_mn, x.ma, x.mb, p, ma2, mb2, std::min(units, 2 * sms), st);
+  const int epi = epi_kind(p, y != nullptr, y ? y->p.e.accumulate : 0, y ? y->p.C : nullptr);
+  // CTA pairs: 6 stages x 32 KB per CTA, grid = an even number of CTAs, two per unit in flight
+  if (x.bn == 256 && x.cta2) return launch_cfg<256, 6, 2, 8, true>(x.a_mn, x.b_mn, epi, x.ma, x.mb, p, ma2, mb2, 2 * std::min(units, sms / 2), st);
+  if (x.bn == 256) return launch_cfg<256, 4, 2, 8>(x.a_mn, x.b_mn, epi, x.ma, x.mb, p, ma2, mb2, std::min(units, sms), st);
+  if (x.bn == 64) return launch_cfg<64, 8, 2, 4>(x.a_mn, x.b_mn, epi, x.ma, x.mb, p, ma2, mb2, std::min(units, sms), st);
+  return launch_cfg<128, 3, 2, 4>(x.a_mn, x.b_mn, epi, x.ma, x.mb, p, ma2, mb2, std::min(units, 2 * sms), st);
 }
 
 }  // namespace
+
+void gemm_tc_set_trace(long long* buf) { g_trace = buf; }
 
 bool gemm_tc_supported(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb) {
   (void)transA; (void)transB; (void)M; (void)N; (void)K;
@@ -767,7 +1030,7 @@ int gemm_tc_pair(const GemmCall& c0, const GemmCall& c1, cudaStream_t st) {
   if (ok) {
     REGAT_TRY(prepare(c0.transA, c0.transB, c0.M, c0.N, c0.K, c0.A, c0.lda, c0.B, c0.ldb, c0.C, c0.ldc, c0.c_dtype, c0.e, 1, st, 0, nullptr, 0, x));
     REGAT_TRY(prepare(c1.transA, c1.transB, c1.M, c1.N, c1.K, c1.A, c1.lda, c1.B, c1.ldb, c1.C, c1.ldc, c1.c_dtype, c1.e, 1, st, 0, nullptr, x.bn, y));
-    ok = x.p.splits == 1 && y.p.splits == 1 && x.bn == y.bn && x.p.tiles_n == y.p.tiles_n;
+    ok = x.p.splits == 1 && y.p.splits == 1 && x.bn == 256 && x.bn == y.bn && x.cta2 == y.cta2 && x.p.tiles_n == y.p.tiles_n;
   }
   if (!ok) { REGAT_TRY(single(c0)); return single(c1); }
   return launch_prepared(x, &y, st);
