@@ -380,7 +380,7 @@ REGAT_API int regat_engine_refresh_weights(regat_engine* e, regat_stream_t strea
 typedef void (*regat_grad_ready_fn)(void* user, int64_t offset, int64_t numel);
 REGAT_API int regat_engine_set_grad_callback(regat_engine* e, regat_grad_ready_fn fn, void* user);
 /* Measurement aid (tools/gemm_trace.py): with a device buffer of >= 256 int64 the tcgen05 GEMM launches that follow record
- * clock64 stamps of CTA 0 -- [0] kernel start, [1] roles done, [2] exit, then per unit u (u < 30) at [8 + 8u + k]:
+ * clock64 stamps of CTA 0 -- [0] kernel start, [1] roles done, [2] exit, then per unit u (u < 14) at [8 + 8u + k]:
  * k=0/1 first/last TMA issue, 2 accumulator stage free, 3 first operands landed, 4 last MMA issued, 5 epilogue ready,
  * 6 accumulator complete, 7 unit stored.  NULL switches it off (the default).  Not thread-safe; never leave it on. */
 REGAT_API int regat_gemm_trace(void* device_buf);

@@ -112,6 +112,28 @@ struct GemmCall {
   EpiArgs e;
 };
 int gemm_tc_pair(const GemmCall& c0, const GemmCall& c1, cudaStream_t st);
+// Dependent chain of batch-sized products (+ the loss) as stages of ONE persistent launch (csrc/gemm_tc.cu, gemm_chain_kernel).
+struct ChainEpi {
+  const float* bias = nullptr; int relu = 0;
+  const void* gate = nullptr; int gate_ld = 0;          // bf16: keep where gate > 0
+  const void* mul = nullptr; int mul_ld = 0;            // bf16: C = x * mul
+  void* out2 = nullptr; int out2_ld = 0; const void* mul2 = nullptr; int mul2_ld = 0;   // bf16: out2 = x * mul2
+};
+class ChainBuilder {
+ public:
+  explicit ChainBuilder(unsigned int* counter);          // device counter, zero between launches
+  ~ChainBuilder();
+  ChainBuilder(const ChainBuilder&) = delete;
+  ChainBuilder& operator=(const ChainBuilder&) = delete;
+  int product(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C, int ldc, int c_dtype,
+              const ChainEpi& e);
+  int loss(int B, int A, const float* logits, int ldl, const float* target, float gscale, float* loss, float* score, void* dlog, int ldd);
+  int launch(cudaStream_t st);
+ private:
+  struct Impl;
+  Impl* impl;
+};
+bool chain_fits(int max_units);
 void gemm_tc_set_trace(long long* buf);
 bool gemm_tc_supported(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B,
                        int ldb);

@@ -313,6 +313,8 @@ struct Ctx {
   int B, N, M, R, Rm;
   const float* features; const float* boxes; const float* q_att; const float* q_last;
   bool fused_opt = false;    // train step: exchange + optimizer of each gradient range on the `opt` stream as soon as it is final
+  bool chain = false;        // the batch-sized tail (pv .. logits, loss, dhid .. dpooled) runs as ONE chained launch in backward()
+  float* logits_out = nullptr;   // fwd_bwd caller's logits pointer, served after the chain
 };
 
 EpiArgs epi0() { EpiArgs x; memset(&x, 0, sizeof(x)); return x; }
@@ -605,6 +607,16 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
   REGAT_TRY(regat_butd_pool_fwd(dt, B, N, D, e->atv(e->v1), e->atv(e->weff), e->at<float>(e->cb), e->at<float>(e->att),
                                 e->atv(e->pooled), st));
   if (att_out) REGAT_CUDA(cudaMemcpyAsync(att_out, e->atv(e->att), (size_t)B * N * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // Training with the bf16 tensor-core kernels: the batch-sized products from here to the logits, the loss and their transposes
+  // are the stages of one chained launch issued by backward() (csrc/gemm_tc.cu: gemm_chain_kernel)
+  // (REGAT_CHAIN=1 opts in.  Measured at batch 256: the chain runs in 75 us against ~60 us for the separately launched kernels
+  // inside the step's CUDA graph -- its stages keep only 24-98 CTAs busy and each streams 0.4-1.2 MB through one SM's L2 port,
+  // while separate launches overlap their tails and the side stream's weight gradients; the step is 18 us slower with it.)
+  const char* chain_s = getenv("REGAT_CHAIN");
+  const int chain_env = chain_s ? atoi(chain_s) : 0;
+  c.chain = training && e->grads && dt == REGAT_BF16 && e->use_tc && chain_env != 0 &&
+            chain_fits(ceil_div(B, 128) * ceil_div(A, 64));
+  if (c.chain) { c.logits_out = logits_out; return REGAT_OK; }
   REGAT_TRY(fc_fwd(e, st, e->l_ve, 0, B, D, e->atv(e->pooled), D, e->atv(e->pv), Hd, dt, false));
   REGAT_TRY(k_mul(dt, e->atv(e->pv), Hd, e->at<unsigned char>(e->uqe) + (size_t)Hd * es, 2 * Hd, e->atv(e->joint), Hd, B, Hd, st));
   // classifier                                                          classifier.py:14-25
@@ -658,13 +670,42 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   float* scal = e->at<float>(e->scal);
   e->grads_final = 0;
 
+  cudaStream_t sd = e->side;
+  unsigned char* dqe = e->at<unsigned char>(e->duqe) + (size_t)Hd * es;
+  ColsumBatch cb_side, cb_qkv, cb_ds, cb_v0;   // bias gradients, one multi-problem launch per backward stage (all on the side stream)
+  if (c.chain) {
+    // pv -> joint -> hid -> logits -> loss / dlogits -> dhid -> djoint (dpv, dqe) -> dpooled as seven stages of ONE launch
+    // (fusion.py:37-52, classifier.py:14-25, train.py:107-108 and their transposes); the weight gradients follow on the side stream
+    ChainBuilder ch(e->at<unsigned int>(e->hyp) + 12);
+    const unsigned char* qe = e->at<unsigned char>(e->uqe) + (size_t)Hd * es;
+    ChainEpi ep;
+    ep.bias = biasp(e, e->l_ve); ep.out2 = e->atv(e->joint); ep.out2_ld = Hd; ep.mul2 = qe; ep.mul2_ld = 2 * Hd;
+    REGAT_TRY(ch.product(0, 0, B, Hd, D, e->atv(e->pooled), D, W(e, e->l_ve), ldW(e, e->l_ve), e->atv(e->pv), Hd, dt, ep));
+    ep = ChainEpi(); ep.bias = biasp(e, e->l_c0); ep.relu = 1;
+    REGAT_TRY(ch.product(0, 0, B, 2 * Hd, Hd, e->atv(e->joint), Hd, W(e, e->l_c0), ldW(e, e->l_c0), e->atv(e->hid), 2 * Hd, dt, ep));
+    ep = ChainEpi(); ep.bias = biasp(e, e->l_c3);
+    REGAT_TRY(ch.product(0, 0, B, A, 2 * Hd, e->atv(e->hid), 2 * Hd, W(e, e->l_c3), ldW(e, e->l_c3), e->atv(e->logits), e->a_pad, REGAT_F32, ep));
+    REGAT_TRY(ch.loss(B, A, e->at<float>(e->logits), e->a_pad, target, grad_scale, scal + 2, scal + 3, e->atv(e->dlogits), e->a_pad));
+    ep = ChainEpi(); ep.gate = e->atv(e->hid); ep.gate_ld = 2 * Hd;
+    REGAT_TRY(ch.product(0, 1, B, 2 * Hd, A, e->atv(e->dlogits), e->a_pad, W(e, e->l_c3), ldW(e, e->l_c3), e->atv(e->dhid), 2 * Hd, dt, ep));
+    ep = ChainEpi(); ep.mul = qe; ep.mul_ld = 2 * Hd; ep.out2 = dqe; ep.out2_ld = 2 * Hd; ep.mul2 = e->atv(e->pv); ep.mul2_ld = Hd;
+    REGAT_TRY(ch.product(0, 1, B, Hd, 2 * Hd, e->atv(e->dhid), 2 * Hd, W(e, e->l_c0), ldW(e, e->l_c0), e->atv(e->dpv), Hd, dt, ep));
+    ep = ChainEpi();
+    REGAT_TRY(ch.product(0, 1, B, D, Hd, e->atv(e->dpv), Hd, W(e, e->l_ve), ldW(e, e->l_ve), e->atv(e->dpooled), D, dt, ep));
+    {
+      // one timing record for the whole chain: (M, N, K) = (B, 1, FLOPs / 2B) so that 2 M N K is the chain's FLOP count
+      ProfScope prof(e, st, B, 1, 2 * (D * Hd + Hd * 2 * Hd + 2 * Hd * A));
+      REGAT_TRY(ch.launch(st));
+    }
+    if (c.logits_out)
+      REGAT_CUDA(cudaMemcpy2DAsync(c.logits_out, (size_t)A * sizeof(float), e->atv(e->logits), (size_t)e->a_pad * sizeof(float),
+                                   (size_t)A * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
+    // the classifier / BUTD weight gradients are issued further down, behind the attention backward pass (chain_wgrads)
+  } else {
   // loss + dlogits                                                     train.py:107-108
   REGAT_TRY(k_bce(B, A, e->at<float>(e->logits), e->a_pad, target, grad_scale, scal + 2, scal + 3, e->atv(e->dlogits), e->a_pad, dt, st));
   // The input-gradient chain (dhid -> djoint -> dpv -> dpooled -> dv1) stays on the main stream; every weight / bias gradient of
   // the classifier and of BUTD is off the critical path and goes to the side stream as soon as its operands exist.
-  cudaStream_t sd = e->side;
-  unsigned char* dqe = e->at<unsigned char>(e->duqe) + (size_t)Hd * es;
-  ColsumBatch cb_side, cb_qkv, cb_ds, cb_v0;   // bias gradients, one multi-problem launch per backward stage (all on the side stream)
   REGAT_TRY(fork_to(st, sd, e->ev[2]));                    // dlogits ready
   if (dt == REGAT_BF16 && e->use_tc && (A % 4) != 0) {
     // the [2Hd, A] gradient has unaligned rows (A = 3129): compute it with a padded pitch, then compact into the flat buffer
@@ -686,6 +727,7 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   REGAT_TRY(fork_to(st, sd, e->ev[4]));                    // dpv, dqe ready
   REGAT_TRY(fc_wgrad(e, sd, e->l_ve, 0, B, D, e->atv(e->pooled), D, e->atv(e->dpv), Hd, true, &cb_side));
   REGAT_TRY(fc_dgrad(e, st, e->l_ve, 0, B, D, e->atv(e->dpv), Hd, e->atv(e->dpooled), D, dt, false));
+  }
   // attention pooling
   REGAT_TRY(regat_butd_pool_bwd(dt, B, N, D, e->atv(e->v1), e->atv(e->weff), e->at<float>(e->att), e->atv(e->dpooled),
                                 e->atv(e->dv1), e->atv(e->dweff), e->at<float>(e->dcb), st));
@@ -715,6 +757,14 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
       REGAT_TRY(fc_dgrad(e, sd, e->l_qe, 0, B, Q, dqe, 2 * Hd, dq_last, Q, REGAT_F32, true));
     }
   }
+  if (!c.chain) {
+    // BUTD + classifier gradients (the tail of the flat buffer) are final once the side stream has drained what is queued on it
+    // now; nothing on the main stream writes them any more.  Announced BEFORE the attention backward pass is launched: that
+    // kernel is latency-bound and uses little HBM bandwidth, the best partner the HBM-bound optimizer (and, data parallel, the
+    // exchange) of this largest range can get.
+    REGAT_TRY(k_colsum_multi(dt, cb_side, sd));
+    REGAT_TRY(range_ready(c, 0, /*side_work=*/true));
+  }
   // attention backward: dQ, dK, dV', dout (-> ds), dL (in place of P); then the geometry reduction
   if (attn_fast(e, N))
     REGAT_TRY(regat_attn_bwd_fast(B, N, cf.nongt_dim, D, H, dirs, e->atv(e->Qb), e->atv(e->KVb), e->atv(e->dv1), e->at<uint64_t>(e->gate),
@@ -722,13 +772,30 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   else
     REGAT_TRY(regat_attn_bwd(dt, B, N, cf.nongt_dim, D, H, dirs, e->atv(e->Qb), e->atv(e->KVb), e->atv(e->dv1),
                              e->at<uint64_t>(e->gate), e->at<float>(e->P), e->atv(e->dQb), e->atv(e->dKVb), e->atv(e->ds), st));
-  REGAT_TRY(k_colsum_multi(dt, cb_side, sd));
-  // BUTD + classifier gradients (the tail of the flat buffer) are final once the side stream has drained
-  REGAT_TRY(range_ready(c, 0, /*side_work=*/true));
+  if (c.chain) {
+    // Weight gradients of the chained products: side stream, but only once the attention backward pass has run -- issued
+    // earlier their CTAs take SM slots from that latency-bound kernel (measured: +20 us on the step)
+    REGAT_TRY(fork_to(st, sd, e->ev[6]));                  // dQb, dKVb, dL final (and with them everything the chain produced)
+    if ((A % 4) != 0) {
+      REGAT_TRY(dense(e, sd, true, false, 2 * Hd, A, B, e->atv(e->hid), 2 * Hd, e->atv(e->dlogits), e->a_pad, e->atv(e->dwc3), e->a_pad,
+                      REGAT_F32, epi0()));
+      REGAT_CUDA(cudaMemcpy2DAsync(gradW(e, e->l_c3), (size_t)A * sizeof(float), e->atv(e->dwc3), (size_t)e->a_pad * sizeof(float),
+                                   (size_t)A * sizeof(float), 2 * Hd, cudaMemcpyDeviceToDevice, sd));
+      REGAT_TRY(bias_grad(e, sd, e->atv(e->dlogits), e->a_pad, B, A, gradB(e, e->l_c3), &cb_side));
+    } else {
+      REGAT_TRY(fc_wgrad(e, sd, e->l_c3, 0, B, 2 * Hd, e->atv(e->hid), 2 * Hd, e->atv(e->dlogits), e->a_pad, true, &cb_side));
+    }
+    REGAT_TRY(fc_wgrad(e, sd, e->l_c0, 0, B, Hd, e->atv(e->joint), Hd, e->atv(e->dhid), 2 * Hd, true, &cb_side));
+    REGAT_TRY(fc_wgrad(e, sd, e->l_ve, 0, B, D, e->atv(e->pooled), D, e->atv(e->dpv), Hd, true, &cb_side));
+  }
+  if (c.chain) {
+    REGAT_TRY(k_colsum_multi(dt, cb_side, sd));
+    REGAT_TRY(range_ready(c, 0, /*side_work=*/true));
+  }
   // The bias gradients (column sums -- HBM-bound) and the small question-side products run on the side stream next to the
   // tensor-bound GEMMs of the main stream.  Gradient ranges are announced in the order they become final: attention layers,
   // then self_weights + label FC, then v2out -- the data-parallel layer starts each all-reduce behind the rest of the backward.
-  REGAT_TRY(fork_to(st, sd, e->ev[6]));                    // dQb, dKVb, dL final
+  if (!c.chain) REGAT_TRY(fork_to(st, sd, e->ev[6]));      // dQb, dKVb, dL final
   // the geometry reduction (SFU / issue bound, produces only dW_g, db_g, dc) runs beside the tensor-bound GEMMs
   {
     const Layer& P0 = e->layers[e->l_pos[0]];

@@ -370,16 +370,25 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, BN == 128 ? 2 : 1) gemm_tc_ker
 
   // measurement aid: CTA 0 stamps clock64 at the phase boundaries of each unit; slot layout trace[8 + 8 * unit + k]
   long long* const tr = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
-  auto stamp = [&](int ui, int k) { if (tr && ui < 30) tr[8 + 8 * ui + k] = clock64(); };
+  auto stamp = [&](int ui, int k) { if (tr && ui < 14) tr[8 + 8 * ui + k] = clock64(); };
   if (tr && threadIdx.x == 0) tr[0] = clock64();
+  // Unit of this worker in round `it` (-1: none left).  Two-problem launches mix long-K and short-K units (long first): complete
+  // odd rounds run in reverse worker order, so the workers that drew a second long unit are not the ones that get the extra
+  // unit of the last, partial round (dQ / dKV input gradients: 192 -> 160 k-blocks on the most loaded worker).
+  auto unit_at = [&](int it) -> int {
+    const int base = it * workers;
+    if (base >= units) return -1;
+    if (PAIR && (it & 1) && base + workers <= units) return base + workers - 1 - worker;
+    const int u = base + worker;
+    return u < units ? u : -1;
+  };
   if (warp == 0) {
     // ===== TMA producer: warp-uniform loop, one elected lane issues =====
     {
       const bool leader = elect_one();
       int s = 0;
       uint32_t ph = 0;
-      int pui = 0;
-      for (int u = worker; u < units; u += workers, ++pui) {
+      for (int pui = 0, u; (u = unit_at(pui)) >= 0; ++pui) {
         int m0, n0, kb0, kb1;
         decode(u, m0, n0, kb0, kb1);
         const CUtensorMap* ma = (PAIR && u >= units1) ? &mapA2 : &mapA;
@@ -443,7 +452,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, BN == 128 ? 2 : 1) gemm_tc_ker
     int s = 0, ui = 0;
     uint32_t ph = 0;
     // CTA pair: only the leader CTA issues (its MMAs read both CTAs' shared memory and write both CTAs' TMEM)
-    for (int u = (CTA2 && crank != 0) ? units : worker; u < units; u += workers, ++ui) {
+    for (int u; !(CTA2 && crank != 0) && (u = unit_at(ui)) >= 0; ++ui) {
       int m0, n0, kb0, kb1;
       decode(u, m0, n0, kb0, kb1);
       const int a = ui % ACC;
@@ -498,8 +507,7 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, BN == 128 ? 2 : 1) gemm_tc_ker
                         (p.e.alpha_cols % 32 == 0) && (p.c_block_cols % 32 == 0);
     const bool al32 = (all_ptrs & 31) == 0;
     const float alpha0 = (E_GEN && p.e.alpha && p.e.alpha_cols == 0) ? __ldg(p.e.alpha) : 1.f;
-    int ui = 0;
-    for (int u = worker; u < units; u += workers, ++ui) {
+    for (int ui = 0, u; (u = unit_at(ui)) >= 0; ++ui) {
       int m0, n0, kb0, kb1;
       decode(u, m0, n0, kb0, kb1);
       m0 += (int)crank * BM;                  // CTA pair: this CTA's TMEM holds rows 128 r .. of the unit
@@ -774,6 +782,391 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, BN == 128 ? 2 : 1) gemm_tc_ker
   if (tr && threadIdx.x == 0) tr[2] = clock64();
 }
 
+// ================================================================== dependent chain of batch-sized products in ONE launch
+// The classifier / BUTD tail of the step (fusion.py:37-52, classifier.py:14-25, train.py:107-108 and their transposes) is a
+// chain of seven products whose M is the batch (256 rows): each depends on the previous one, each is < 1 % of the step's
+// FLOPs, and launched one by one each costs a launch, a pipeline fill and a drain (8-22 us a piece, ~120 us together, with
+// 24-98 CTAs on 148 SMs).  Here they are stages of one persistent launch: every CTA keeps its barriers, TMEM and warp roles,
+// runs its tiles of stage i, and a grid-wide arrival counter (release / acquire at gpu scope, then fence.proxy.async before
+// the next stage's TMA reads what other SMs' epilogues stored) separates the stages.  128 x 64 tiles, 8-deep ring, operand
+// major-ness per stage at run time (forward: weights MN-major, input gradients: K-major).  The loss (BCE + score + dlogits)
+// is a stage of its own executed by the epilogue warps.  All CTAs of the launch must be resident together: grid <= SM count.
+constexpr int CH_BN = 64, CH_STAGES = 8, CH_ACC = 2, CH_EPIW = 4, CH_MAXP = 8;
+struct ChainProblem {
+  int kind;                       // 0 product, 1 loss
+  int M, N, total_kb, tiles_n, units, a_mn, b_mn;
+  void* C; int ldc, c_f32;        // C = f(acc) [* mul]
+  const float* bias; int relu;
+  const bf16* gate; int gate_ld;  // keep where gate > 0
+  const bf16* mul; int mul_ld;    // C = x * mul
+  bf16* out2; int out2_ld; const bf16* mul2; int mul2_ld;   // out2 = x * mul2 (bf16)
+  // loss stage (train.py:20-26,107-108): logits [M, ldl] fp32, target [M, A] fp32 -> loss, score, dlog [M, ldd] bf16
+  const float* logits; int ldl; const float* target; int A; float inv_B, gscale; float* loss; float* score; bf16* dlog; int ldd;
+};
+struct ChainParams {
+  CUtensorMap map[2 * CH_MAXP];
+  ChainProblem prob[CH_MAXP];
+  int nprob;
+  unsigned int* counter;          // grid arrival counter (0 between launches)
+  long long* trace;               // measurement aid (regat_gemm_trace): CTA 0's clock64 at kernel start [128], when a stage's wait is passed [152 + stage] and at its end [136 + stage]
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// warp-collective: lane 0 polls (one L2 transaction per warp and round), everybody leaves together; the trailing fence orders the
+// other lanes' later reads behind lane 0's acquire
+__device__ __forceinline__ void chain_wait(const unsigned int* ctr, unsigned int need) {
+  if ((threadIdx.x & 31) == 0) {
+    uint32_t spin = 0;
+#pragma unroll 1
+    while (ld_acquire_gpu(ctr) < need) {
+      if (++spin > SPIN_LIMIT) __trap();
+      __nanosleep(32);
+    }
+  }
+  __syncwarp();
+  __threadfence();
+}
+__device__ __forceinline__ uint4 ldg_cg_v4u(const void* p) {     // L2 only: the data was written by other SMs earlier in this launch
+  uint4 v;
+  asm volatile("ld.global.cg.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+
+__global__ void __launch_bounds__(64 + 32 * CH_EPIW, 1) gemm_chain_kernel(const __grid_constant__ ChainParams cp) {
+  constexpr int BN = CH_BN, STAGES = CH_STAGES, ACC = CH_ACC, EPIW = CH_EPIW;
+  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t TMEM_COLS = ACC * BN;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* tiles = smem;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tiles + STAGES * STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC);
+  float* red = reinterpret_cast<float*>(tmem_slot + 4);       // 16 floats: reductions of the loss stage
+  float* bias_stage = red + 16;                                // EPIW x 64 floats: each epilogue warp's bias columns of a unit
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x;
+  if (threadIdx.x < 2 * cp.nprob && cp.prob[threadIdx.x >> 1].kind == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&cp.map[threadIdx.x]) : "memory");
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar + s, 1); mbar_init(empty_bar + s, 1); }
+    for (int a = 0; a < ACC; ++a) { mbar_init(tmem_full + a, 1); mbar_init(tmem_empty + a, EPIW); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  long long* const tr = (cp.trace && blockIdx.x == 0) ? cp.trace : nullptr;
+  if (tr && threadIdx.x == 0) tr[128] = clock64();
+
+  if (warp == 0) {
+    // ===== TMA producer
+    const bool leader = elect_one();
+    int s = 0;
+    uint32_t ph = 0;
+    for (int pi = 0; pi < cp.nprob; ++pi) {
+      const ChainProblem& P = cp.prob[pi];
+      if (P.kind != 0) continue;
+      if (pi > 0) {
+        // every CTA's epilogue of the stages before has stored (and released) its results; what follows reads them through TMA
+        chain_wait(cp.counter, (unsigned)G * (unsigned)pi);
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
+      const CUtensorMap* ma = &cp.map[2 * pi];
+      const CUtensorMap* mb = &cp.map[2 * pi + 1];
+      for (int u = blockIdx.x; u < P.units; u += G) {
+        const int tm = u / P.tiles_n, tn = u - tm * P.tiles_n;
+        const int m0 = tm * BM, n0 = tn * BN;
+        for (int kb = 0; kb < P.total_kb; ++kb) {
+          mbar_wait(empty_bar + s, ph ^ 1);
+          if (leader) {
+            mbar_expect_tx(full_bar + s, STAGE_BYTES);
+            unsigned char* sa = tiles + s * STAGE_BYTES;
+            unsigned char* sb = sa + A_BYTES;
+            if (!P.a_mn) {
+              tma_load_2d(sa, ma, full_bar + s, kb * BK, m0);
+            } else {
+#pragma unroll
+              for (int c = 0; c < BM / 64; ++c) tma_load_2d(sa + c * (64 * BK * 2), ma, full_bar + s, m0 + c * 64, kb * BK);
+            }
+            if (!P.b_mn) tma_load_2d(sb, mb, full_bar + s, kb * BK, n0);
+            else tma_load_2d(sb, mb, full_bar + s, n0, kb * BK);
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer
+    const uint32_t tiles_addr = smem_u32(tiles);
+    const bool leader = elect_one();
+    int s = 0, ui = 0;
+    uint32_t ph = 0;
+    for (int pi = 0; pi < cp.nprob; ++pi) {
+      const ChainProblem& P = cp.prob[pi];
+      if (P.kind != 0) continue;
+      const uint32_t idesc = make_idesc(BN, P.a_mn != 0, P.b_mn != 0, BM);
+      const uint32_t kstep_a = P.a_mn ? (2048u >> 4) : (32u >> 4), kstep_b = P.b_mn ? (2048u >> 4) : (32u >> 4);
+      const uint64_t da0 = P.a_mn ? make_desc(tiles_addr, 64 * BK * 2, 1024) : make_desc(tiles_addr, 16, 1024);
+      const uint64_t db0 = P.b_mn ? make_desc(tiles_addr + A_BYTES, 64 * BK * 2, 1024) : make_desc(tiles_addr + A_BYTES, 16, 1024);
+      for (int u = blockIdx.x; u < P.units; u += G, ++ui) {
+        const int a = ui % ACC;
+        mbar_wait(tmem_empty + a, ((ui / ACC) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
+        uint32_t acc_flag = 0u;
+        for (int kb = 0; kb < P.total_kb; ++kb) {
+          mbar_wait(full_bar + s, ph);
+          tc_fence_after();
+          if (leader) {
+            const uint64_t da = da0 + (uint64_t)((uint32_t)s * (STAGE_BYTES >> 4));
+            const uint64_t db = db0 + (uint64_t)((uint32_t)s * (STAGE_BYTES >> 4));
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k)
+              umma_bf16(tmem_d, da + (uint64_t)(k * kstep_a), db + (uint64_t)(k * kstep_b), idesc, k == 0 ? acc_flag : 1u);
+            umma_commit(empty_bar + s);
+          }
+          acc_flag = 1u;
+          if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+        if (leader) umma_commit(tmem_full + a);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== epilogue warps: products' epilogues, the loss stage, and the grid arrival of every stage
+    const int q = warp & 3;
+    const int et = (warp - 2) * 32 + lane;           // 0..127
+    int ui = 0;
+    for (int pi = 0; pi < cp.nprob; ++pi) {
+      const ChainProblem& P = cp.prob[pi];
+      if (pi > 0) chain_wait(cp.counter, (unsigned)G * (unsigned)pi);     // operands of this stage's epilogue / loss are visible
+      if (tr && et == 0) tr[152 + pi] = clock64();
+      if (P.kind == 0) {
+        for (int u = blockIdx.x; u < P.units; u += G, ++ui) {
+          const int tm = u / P.tiles_n, tn = u - tm * P.tiles_n;
+          const int m0 = tm * BM, n0 = tn * BN;
+          const int a = ui % ACC;
+          const int r = m0 + q * 32 + lane;
+          const bool valid = r < P.M;
+          const int rc = min(r, P.M - 1);
+          // Everything the epilogue reads from global memory is requested BEFORE the accumulator wait (bias: this warp's 64
+          // columns into its shared-memory strip; gate / mul / mul2: this thread's 2 x 64-byte row pieces into registers), so
+          // the only latency left after the last MMA is the TMEM read.
+          float* const bsm = bias_stage + (warp - 2) * 64;
+          if (P.bias) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane < 16) {
+              const int bc = n0 + 4 * lane;
+              if (bc + 4 <= P.N) bv = __ldg(reinterpret_cast<const float4*>(P.bias + bc));
+              else {
+                if (bc < P.N) bv.x = __ldg(P.bias + bc);
+                if (bc + 1 < P.N) bv.y = __ldg(P.bias + bc + 1);
+                if (bc + 2 < P.N) bv.z = __ldg(P.bias + bc + 2);
+              }
+            }
+            __syncwarp();
+            if (lane < 16) reinterpret_cast<float4*>(bsm)[lane] = bv;
+            __syncwarp();
+          }
+          uint4 pg[2][4], pm[2][4], pm2[2][4];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int c = n0 + half * 32;
+            if (c + 32 > P.N) continue;       // gate / mul terms exist for full blocks only (host-checked: N % 32 == 0)
+            if (P.gate) {
+              const uint4* g4 = reinterpret_cast<const uint4*>(P.gate + (size_t)rc * P.gate_ld + c);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) pg[half][g] = ldg_cg_v4u(g4 + g);
+            }
+            if (P.mul) {
+              const uint4* m4 = reinterpret_cast<const uint4*>(P.mul + (size_t)rc * P.mul_ld + c);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) pm[half][g] = ldg_cg_v4u(m4 + g);
+            }
+            if (P.out2) {
+              const uint4* m4 = reinterpret_cast<const uint4*>(P.mul2 + (size_t)rc * P.mul2_ld + c);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) pm2[half][g] = ldg_cg_v4u(m4 + g);
+            }
+          }
+          mbar_wait(tmem_full + a, (ui / ACC) & 1);
+          tc_fence_after();
+          const uint32_t tmem_acc = tmem_base + (uint32_t)(a * BN) + ((uint32_t)(q * 32) << 16);
+          uint32_t acc0[32], acc1[32];
+          tmem_ld32_issue(tmem_acc, acc0);
+          tmem_ld32_issue(tmem_acc + 32u, acc1);
+          tmem_ld32_wait(acc0);
+          tmem_ld32_wait(acc1);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty + a);       // the accumulator stage is free again
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t (&x)[32] = half ? acc1 : acc0;
+            const int c = n0 + half * 32;
+            if (c >= P.N) continue;
+            const bool full = c + 32 <= P.N;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(x[j]);
+            if (P.bias) {
+              const float4* bsrc = reinterpret_cast<const float4*>(bsm + half * 32);
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float4 bv = bsrc[g];
+                v[4 * g] += bv.x; v[4 * g + 1] += bv.y; v[4 * g + 2] += bv.z; v[4 * g + 3] += bv.w;
+              }
+            }
+            if (P.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (P.gate && full) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint32_t ws[4] = {pg[half][g].x, pg[half][g].y, pg[half][g].z, pg[half][g].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  if (!(bf_lo(ws[k]) > 0.f)) v[8 * g + 2 * k] = 0.f;
+                  if (!(bf_hi(ws[k]) > 0.f)) v[8 * g + 2 * k + 1] = 0.f;
+                }
+              }
+            }
+            if (P.out2 && full) {      // out2 = x * mul2
+              uint32_t w2[16];
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint32_t ws[4] = {pm2[half][g].x, pm2[half][g].y, pm2[half][g].z, pm2[half][g].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) w2[4 * g + k] = pack_bf16(v[8 * g + 2 * k] * bf_lo(ws[k]), v[8 * g + 2 * k + 1] * bf_hi(ws[k]));
+              }
+              if (valid) {
+                bf16* d2 = P.out2 + (size_t)r * P.out2_ld + c;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) stg_v4u(d2 + 8 * g, w2 + 4 * g);
+              }
+            }
+            if (P.mul && full) {       // C = x * mul
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint32_t ws[4] = {pm[half][g].x, pm[half][g].y, pm[half][g].z, pm[half][g].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { v[8 * g + 2 * k] *= bf_lo(ws[k]); v[8 * g + 2 * k + 1] *= bf_hi(ws[k]); }
+              }
+            }
+            if (valid) {
+              if (P.c_f32) {
+                float* dst = static_cast<float*>(P.C) + (size_t)r * P.ldc + c;
+                if (full) {
+#pragma unroll
+                  for (int g = 0; g < 8; ++g) stg_v4u(dst + 4 * g, reinterpret_cast<const uint32_t*>(v) + 4 * g);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j)
+                    if (c + j < P.N) dst[j] = v[j];
+                }
+              } else {
+                bf16* dst = static_cast<bf16*>(P.C) + (size_t)r * P.ldc + c;
+                uint32_t w[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) w[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) stg_v4u(dst + 8 * g, w + 4 * g);
+              }
+            }
+          }
+        }
+      } else {
+        // ----- loss stage: one row per CTA and round, 128 threads per row
+        for (int b = blockIdx.x; b < P.M; b += G) {
+          const float* xrow = P.logits + (size_t)b * P.ldl;
+          const float* zrow = P.target + (size_t)b * P.A;
+          float ls = 0.f, bv = -INFINITY;
+          int bi = 0x7fffffff;
+          // batches of 8 elements per thread: all sixteen loads of a batch are in flight before the first use (with 4 warps per
+          // row there is no other latency hiding)
+          constexpr int LB = 8;
+          for (int a0 = et; a0 < P.ldd; a0 += LB * 32 * EPIW) {
+            float xs[LB], zs[LB];
+#pragma unroll
+            for (int i = 0; i < LB; ++i) {
+              const int a = a0 + i * 32 * EPIW;
+              const bool in = a < P.A;
+              xs[i] = in ? __ldcg(xrow + a) : 0.f;
+              zs[i] = in ? __ldg(zrow + a) : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < LB; ++i) {
+              const int a = a0 + i * 32 * EPIW;
+              if (a >= P.ldd) break;
+              float g = 0.f;
+              if (a < P.A) {
+                const float xv = xs[i], zv = zs[i];
+                // tf.nn.sigmoid_cross_entropy_with_logits: max(x, 0) - x z + log1p(exp(-|x|)), one SFU exponential per element:
+                // t = exp(-|x|); log1p(t) by its series where 1 + t would round t away; sigmoid(x) = 1/(1+t) or t/(1+t)
+                const float t = __expf(-fabsf(xv));
+                const float l1p = t < 1e-3f ? t * (1.f - t * (0.5f - t * (1.f / 3.f))) : __logf(1.f + t);
+                ls += fmaxf(xv, 0.f) - xv * zv + l1p;
+                const float sg = __fdividef(xv >= 0.f ? 1.f : t, 1.f + t);
+                g = (sg - zv) * P.inv_B * P.gscale;
+                if (xv > bv) { bv = xv; bi = a; }
+              }
+              P.dlog[(size_t)b * P.ldd + a] = __float2bfloat16_rn(g);
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {        // argmax with first-index tie-break (np.argmax), and the loss sum
+            const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            ls += __shfl_xor_sync(0xffffffffu, ls, o);
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");      // previous row's reads of `red` are done
+          if (lane == 0) { red[warp - 2] = ls; red[4 + warp - 2] = bv; reinterpret_cast<int*>(red)[8 + warp - 2] = bi; }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (et == 0) {
+            float tot = 0.f, best = red[4];
+            int besti = reinterpret_cast<int*>(red)[8];
+            for (int w = 0; w < EPIW; ++w) {
+              tot += red[w];
+              const float ov = red[4 + w];
+              const int oi = reinterpret_cast<int*>(red)[8 + w];
+              if (ov > best || (ov == best && oi < besti)) { best = ov; besti = oi; }
+            }
+            atomicAdd(P.loss, tot * P.inv_B);
+            if (P.score) atomicAdd(P.score, __ldg(zrow + besti));
+          }
+        }
+      }
+      // ----- stage done on this CTA: publish
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) {
+        if (tr) tr[136 + pi] = clock64();
+        const unsigned int old = atomicAdd(cp.counter, 1u);
+        if (pi == cp.nprob - 1 && old == (unsigned)G * (unsigned)cp.nprob - 1u) {
+          // last arrival of the launch: every CTA has passed every wait -- leave the counter at 0 for the next launch
+          atomicExch(cp.counter, 0u);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -1034,6 +1427,75 @@ int gemm_tc_pair(const GemmCall& c0, const GemmCall& c1, cudaStream_t st) {
   }
   if (!ok) { REGAT_TRY(single(c0)); return single(c1); }
   return launch_prepared(x, &y, st);
+}
+
+
+// ---- chain launches (see gemm_chain_kernel)
+struct ChainBuilder::Impl { ChainParams cp; int max_units; bool ok; };
+ChainBuilder::ChainBuilder(unsigned int* counter) : impl(new Impl) {
+  memset(&impl->cp, 0, sizeof(impl->cp));
+  impl->cp.counter = counter; impl->max_units = 0; impl->ok = true;
+}
+ChainBuilder::~ChainBuilder() { delete impl; }
+int ChainBuilder::product(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
+                          int c_dtype, const ChainEpi& e) {
+  ChainParams& cp = impl->cp;
+  REGAT_REQUIRE(cp.nprob < CH_MAXP, REGAT_ERR_UNSUPPORTED, "chain: too many stages");
+  REGAT_REQUIRE(gemm_tc_supported(transA, transB, M, N, K, A, lda, B, ldb), REGAT_ERR_ALIGN, "chain: unaligned operands");
+  const int es = c_dtype == REGAT_F32 ? 4 : 2;
+  REGAT_REQUIRE(aligned16(C) && (ldc * es) % 16 == 0, REGAT_ERR_ALIGN, "chain: unaligned output");
+  REGAT_REQUIRE(c_dtype == REGAT_F32 || N % 32 == 0, REGAT_ERR_UNSUPPORTED, "chain: bf16 outputs need N %% 32 == 0");
+  REGAT_REQUIRE((!e.gate && !e.mul && !e.out2) || N % 32 == 0, REGAT_ERR_UNSUPPORTED, "chain: gate / mul terms need N %% 32 == 0");
+  REGAT_REQUIRE((!e.gate || (aligned16(e.gate) && e.gate_ld % 8 == 0)) && (!e.mul || (aligned16(e.mul) && e.mul_ld % 8 == 0)) &&
+                    (!e.out2 || (aligned16(e.out2) && e.out2_ld % 8 == 0 && e.mul2 && aligned16(e.mul2) && e.mul2_ld % 8 == 0)),
+                REGAT_ERR_ALIGN, "chain: unaligned epilogue tensors");
+  const int pi = cp.nprob++;
+  ChainProblem& P = cp.prob[pi];
+  memset(&P, 0, sizeof(P));
+  const bool a_mn = transA != 0, b_mn = transB == 0;
+  if (!a_mn) REGAT_TRY(make_map(&cp.map[2 * pi], A, K, M, lda, BM)); else REGAT_TRY(make_map(&cp.map[2 * pi], A, M, K, lda, BK));
+  if (!b_mn) REGAT_TRY(make_map(&cp.map[2 * pi + 1], B, K, N, ldb, CH_BN)); else REGAT_TRY(make_map(&cp.map[2 * pi + 1], B, N, K, ldb, BK));
+  P.kind = 0; P.M = M; P.N = N; P.total_kb = ceil_div(K, BK); P.tiles_n = ceil_div(N, CH_BN); P.units = ceil_div(M, BM) * P.tiles_n;
+  P.a_mn = a_mn; P.b_mn = b_mn; P.C = C; P.ldc = ldc; P.c_f32 = c_dtype == REGAT_F32;
+  P.bias = e.bias; P.relu = e.relu; P.gate = static_cast<const bf16*>(e.gate); P.gate_ld = e.gate_ld;
+  P.mul = static_cast<const bf16*>(e.mul); P.mul_ld = e.mul_ld; P.out2 = static_cast<bf16*>(e.out2); P.out2_ld = e.out2_ld;
+  P.mul2 = static_cast<const bf16*>(e.mul2); P.mul2_ld = e.mul2_ld;
+  impl->max_units = std::max(impl->max_units, P.units);
+  return REGAT_OK;
+}
+int ChainBuilder::loss(int B, int A, const float* logits, int ldl, const float* target, float gscale, float* loss, float* score, void* dlog,
+                       int ldd) {
+  ChainParams& cp = impl->cp;
+  REGAT_REQUIRE(cp.nprob < CH_MAXP, REGAT_ERR_UNSUPPORTED, "chain: too many stages");
+  ChainProblem& P = cp.prob[cp.nprob++];
+  memset(&P, 0, sizeof(P));
+  P.kind = 1; P.M = B; P.logits = logits; P.ldl = ldl; P.target = target; P.A = A; P.inv_B = 1.f / (float)B; P.gscale = gscale;
+  P.loss = loss; P.score = score; P.dlog = static_cast<bf16*>(dlog); P.ldd = ldd;
+  impl->max_units = std::max(impl->max_units, std::min(B, num_sms()));   // one row per CTA and round: worth every SM
+  return REGAT_OK;
+}
+bool chain_fits(int max_units) { return max_units <= 2 * num_sms(); }
+int ChainBuilder::launch(cudaStream_t st) {
+  ChainParams& cp = impl->cp;
+  if (cp.nprob == 0) return REGAT_OK;
+  constexpr size_t smem = (size_t)CH_STAGES * (BM * BK * 2 + CH_BN * BK * 2) + (2 * CH_STAGES + 2 * CH_ACC) * 8 + 16 + 64 + CH_EPIW * 256;
+  static std::mutex mu;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  REGAT_CUDA(cudaGetDevice(&dev));
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+      REGAT_CUDA(cudaFuncSetAttribute(gemm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+  }
+  cp.trace = g_trace;
+  // every CTA waits for every other one between stages: the grid must be resident as a whole (one CTA per SM)
+  const int grid = std::max(1, std::min(impl->max_units, num_sms()));
+  gemm_chain_kernel<<<grid, 64 + 32 * CH_EPIW, smem, st>>>(cp);
+  REGAT_POST_LAUNCH();
+  return REGAT_OK;
 }
 
 }  // namespace regat

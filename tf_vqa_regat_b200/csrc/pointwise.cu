@@ -580,10 +580,26 @@ __global__ void __launch_bounds__(256) opt_reduce_kernel(const float* __restrict
   const float* g = grads + tl.off[l];
   const float* v = params + tl.off[l];
   float dot = 0.f, gg = 0.f;
-  for (long long i = base + threadIdx.x; i < end; i += 256) {
-    const float gv = g[i];
-    dot = fmaf(gv, v[i], dot);
-    gg = fmaf(gv, gv, gg);
+  if (end - base == WN_CHUNK) {
+    // full chunk: 2 x 4 x 16-byte loads per thread in flight before the first use.  These passes run beside the backward pass's
+    // persistent GEMM CTAs, which leave room for about one such block per SM: the bandwidth has to come from loads in flight
+    // per thread, not from resident blocks.
+    const float4* g4 = reinterpret_cast<const float4*>(g + base);
+    const float4* v4 = reinterpret_cast<const float4*>(v + base);
+    float4 gs[4], vs[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { gs[j] = g4[threadIdx.x + 256 * j]; vs[j] = v4[threadIdx.x + 256 * j]; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      dot = fmaf(gs[j].x, vs[j].x, dot); dot = fmaf(gs[j].y, vs[j].y, dot); dot = fmaf(gs[j].z, vs[j].z, dot); dot = fmaf(gs[j].w, vs[j].w, dot);
+      gg = fmaf(gs[j].x, gs[j].x, gg); gg = fmaf(gs[j].y, gs[j].y, gg); gg = fmaf(gs[j].z, gs[j].z, gg); gg = fmaf(gs[j].w, gs[j].w, gg);
+    }
+  } else {
+    for (long long i = base + threadIdx.x; i < end; i += 256) {
+      const float gv = g[i];
+      dot = fmaf(gv, v[i], dot);
+      gg = fmaf(gv, gv, gg);
+    }
   }
   dot = block_sum_256(dot, red);
   gg = block_sum_256(gg, red);
@@ -650,15 +666,40 @@ __global__ void __launch_bounds__(256) opt_update_kernel(float* __restrict__ par
   const float cs = hp.clip / fmaxf(nrm, hp.clip);           // tf.clip_by_norm
   const float lr_t = hp.lr_t_dev ? __ldg(hp.lr_t_dev) : hp.lr_t;
   float ss = 0.f;
-  for (long long i = base + threadIdx.x; i < end; i += 256) {
-    const float w = params[off + i];
-    const float g = cs * a * (grads[off + i] - proj * w);
-    const float m = hp.beta1 * am[off + i] + (1.f - hp.beta1) * g;
-    const float u = fmaxf(hp.beta2 * au[off + i], fabsf(g));
-    am[off + i] = m; au[off + i] = u;
+  auto step1 = [&](float w, float gr, float& m, float& u) -> float {
+    const float g = cs * a * (gr - proj * w);
+    m = hp.beta1 * m + (1.f - hp.beta1) * g;
+    u = fmaxf(hp.beta2 * u, fabsf(g));
     const float wn = w - lr_t * m / (u + hp.eps);
-    params[off + i] = wn;
     ss = fmaf(wn, wn, ss);
+    return wn;
+  };
+  if (end - base == WN_CHUNK) {
+    // full chunk: all sixteen 16-byte loads of a thread are in flight before the first use (see opt_reduce_kernel)
+    float4* w4 = reinterpret_cast<float4*>(params + off + base);
+    const float4* g4 = reinterpret_cast<const float4*>(grads + off + base);
+    float4* m4 = reinterpret_cast<float4*>(am + off + base);
+    float4* u4 = reinterpret_cast<float4*>(au + off + base);
+    float4 ws[4], gs[4], ms[4], us[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = threadIdx.x + 256 * j;
+      ws[j] = w4[i]; gs[j] = g4[i]; ms[j] = m4[i]; us[j] = u4[i];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = threadIdx.x + 256 * j;
+      ws[j].x = step1(ws[j].x, gs[j].x, ms[j].x, us[j].x); ws[j].y = step1(ws[j].y, gs[j].y, ms[j].y, us[j].y);
+      ws[j].z = step1(ws[j].z, gs[j].z, ms[j].z, us[j].z); ws[j].w = step1(ws[j].w, gs[j].w, ms[j].w, us[j].w);
+      m4[i] = ms[j]; u4[i] = us[j]; w4[i] = ws[j];
+    }
+  } else {
+    for (long long i = base + threadIdx.x; i < end; i += 256) {
+      float m = am[off + i], u = au[off + i];
+      const float wn = step1(params[off + i], grads[off + i], m, u);
+      am[off + i] = m; au[off + i] = u;
+      params[off + i] = wn;
+    }
   }
   // ||v_new||^2 per chunk, laid out like wn_prepare_kernel's partials: the next forward pass skips that read of the parameters
   if (vpartials && tl.kind[l] == 0) {

@@ -34,7 +34,7 @@ t0 = t[0]
 us = lambda x: (x - t0) / ghz / 1e3 if x else float("nan")
 print(f"{M}x{N}x{K} tA={tA} tB={tB} CTA2={os.environ.get('REGAT_TC_CTA2', '1')}: roles done {us(t[1]):.2f} us, exit {us(t[2]):.2f} us (clock64 / {ghz} GHz, from kernel start)")
 print("unit  tma_first tma_last | acc_free operands mma_issued | epi_ready acc_done stored   (us)")
-for u in range(30):
+for u in range(14):
     r = t[8 + 8 * u: 16 + 8 * u]
     if not any(r):
         break
