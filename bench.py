@@ -613,12 +613,24 @@ def main():
         for i in range(6):
             call(i)
         torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # 30 launches on rotating operands (6 x 57 MB > L2), replayed from a CUDA graph like the step itself, CUDA events around
+        # the replay on the stream it runs on: average launch duration without the host's per-call ctypes overhead
         reps = 30
-        e0.record()
-        for i in range(reps):
-            call(i)
-        e1.record(); torch.cuda.synchronize()
+        pst = torch.cuda.Stream()
+        pg = torch.cuda.CUDAGraph()
+        call_on = lambda i, s_: _lib.check(l.regat_gemm(code, 0, 0, M_, N_, K_, As[i % nrot].data_ptr(), K_, Wt.data_ptr(), N_,
+                                                        Cs[i % nrot].data_ptr(), N_, code, C.byref(epi), s_))
+        pst.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(pst):
+            with torch.cuda.graph(pg, stream=pst):
+                for i in range(reps):
+                    call_on(i, torch.cuda.current_stream().cuda_stream)
+            pg.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pg.replay()
+            e1.record(); torch.cuda.synchronize()
         t_ms = e0.elapsed_time(e1) / reps
         tflops = 2.0 * M_ * N_ * K_ / (t_ms * 1e-3) / 1e12
         peak = peaks["bf16_tflops"] if args.dtype == "bf16" else None

@@ -151,8 +151,15 @@ def test_masked_attention_kernels_vs_torch(dtype, tol):
     dq, dkv, dout = torch.empty_like(qd), torch.empty_like(kvd), torch.empty_like(sd)
     _lib.check(l.regat_graphattn_explicit_bwd(code, B, N, nongt, D, H, dirs, qd.data_ptr(), kvd.data_ptr(), cast(probe).data_ptr(), gate.data_ptr(),
                                               pb.data_ptr(), P.data_ptr(), dq.data_ptr(), dkv.data_ptr(), dout.data_ptr(), st))
-    gtol = tol if dtype == "fp32" else 8e-2       # bf16 storage of dQ / dK / dV' on top of single-pass TF32 products
-    assert rel(dq, gq) < gtol and rel(dkv, gkv) < gtol and rel(dout, gs) < gtol, (rel(dq, gq), rel(dkv, gkv), rel(dout, gs))
+    if dtype == "fp32":
+        assert rel(dq, gq) < tol and rel(dkv, gkv) < tol and rel(dout, gs) < tol, (rel(dq, gq), rel(dkv, gkv), rel(dout, gs))
+    else:
+        # bf16: a relu pre-activation within rounding distance of 0 lands on the other side in bf16 and its element of the gated
+        # gradient appears or disappears whole, so single elements are bounded loosely (0.3 of the largest entry) and the tensors
+        # in the 2-norm (bf16 storage of dQ / dK / dV' on top of single-pass TF32 products: measured 1e-2)
+        fro = lambda a, b: float((a.float() - b).norm() / b.norm())
+        errs = (fro(dq, gq), fro(dkv, gkv), fro(dout, gs), rel(dq, gq), rel(dkv, gkv), rel(dout, gs))
+        assert max(errs[:3]) < 4e-2 and max(errs[3:]) < 0.3, errs
     dw, db = torch.zeros(L, device="cuda"), torch.zeros(1, device="cuda")
     _lib.check(l.regat_explicit_pair_bias_bwd(B, N, nongt, L, dirs, H, adj_t.data_ptr(), P.data_ptr(), dw.data_ptr(), db.data_ptr(), st))
     torch.cuda.synchronize()

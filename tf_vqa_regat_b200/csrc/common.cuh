@@ -105,7 +105,7 @@ int gemm_simt(int in_dtype, int transA, int transB, int M, int N, int K, const v
               const void* B, int ldb, void* C, int ldc, int c_dtype, const EpiArgs& e, cudaStream_t st);
 int gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb,
             void* C, int ldc, int c_dtype, const EpiArgs& e, int split_k, cudaStream_t st, int c_block_cols = 0,
-            const long long* c_block_off = nullptr);
+            const long long* c_block_off = nullptr, int max_ctas = 0);
 struct GemmCall {
   int transA, transB, M, N, K;
   const void* A; int lda; const void* B; int ldb; void* C; int ldc; int c_dtype;

@@ -337,8 +337,12 @@ int dense(regat_engine* e, cudaStream_t st, bool tA, bool tB, int M, int N, int 
           int ldb, void* C, int ldc, int c_dtype, const EpiArgs& ep, int split_k = 1) {
   ProfScope prof(e, st, M, N, K);
   if (e->dtype == REGAT_F32) return gemm_simt(REGAT_F32, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, REGAT_F32, ep, st);
-  if (e->use_tc && gemm_tc_supported(tA, tB, M, N, K, A, lda, Bm, ldb))
-    return gemm_tc(tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, c_dtype, ep, split_k, st);
+  if (e->use_tc && gemm_tc_supported(tA, tB, M, N, K, A, lda, Bm, ldb)) {
+    // products on the side stream are off the dependency chain: they may not take every SM from the main stream's kernels
+    // (a persistent launch holds its SMs' shared memory until it ends).  REGAT_SIDE_CAP = CTAs they may use, 0 = no limit.
+    static const int side_cap = [] { const char* s = getenv("REGAT_SIDE_CAP"); return s ? atoi(s) : 0; }();
+    return gemm_tc(tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, c_dtype, ep, split_k, st, 0, nullptr, st == e->side ? side_cap : 0);
+  }
   return gemm_simt(REGAT_BF16, tA, tB, M, N, K, A, lda, Bm, ldb, C, ldc, c_dtype, ep, st);
 }
 // weight gradients of side-by-side layers: one product whose column blocks land in the layers' own gradient slots
@@ -622,7 +626,16 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
   // classifier                                                          classifier.py:14-25
   REGAT_TRY(fc_fwd(e, st, e->l_c0, 0, B, Hd, e->atv(e->joint), Hd, e->atv(e->hid), 2 * Hd, dt, true));
   // logits live in a buffer whose row pitch is padded to 16 bytes (3129 -> 3136) so the epilogue can use vector stores
-  REGAT_TRY(fc_fwd(e, st, e->l_c3, 0, B, 2 * Hd, e->atv(e->hid), 2 * Hd, e->atv(e->logits), e->a_pad, REGAT_F32, false));
+  if (dt == REGAT_BF16 && e->use_tc && e->layers[e->l_c3].lowp_ld >= e->a_pad) {
+    // all a_pad columns: the pad columns of the bf16 kernel copy and the floats behind the bias are zero (never written), so the
+    // extra logits are 0 and the product has whole 32-column blocks -- the lean fp32 epilogue instead of the ragged generic one
+    EpiArgs ep = epi0();
+    ep.bias = biasp(e, e->l_c3);
+    REGAT_TRY(dense(e, st, false, false, B, e->a_pad, 2 * Hd, e->atv(e->hid), 2 * Hd, W(e, e->l_c3), ldW(e, e->l_c3), e->atv(e->logits),
+                    e->a_pad, REGAT_F32, ep));
+  } else {
+    REGAT_TRY(fc_fwd(e, st, e->l_c3, 0, B, 2 * Hd, e->atv(e->hid), 2 * Hd, e->atv(e->logits), e->a_pad, REGAT_F32, false));
+  }
   if (logits_out)
     REGAT_CUDA(cudaMemcpy2DAsync(logits_out, (size_t)A * sizeof(float), e->atv(e->logits), (size_t)e->a_pad * sizeof(float),
                                  (size_t)A * sizeof(float), B, cudaMemcpyDeviceToDevice, st));
@@ -709,11 +722,12 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
   REGAT_TRY(fork_to(st, sd, e->ev[2]));                    // dlogits ready
   if (dt == REGAT_BF16 && e->use_tc && (A % 4) != 0) {
     // the [2Hd, A] gradient has unaligned rows (A = 3129): compute it with a padded pitch, then compact into the flat buffer
-    REGAT_TRY(dense(e, sd, true, false, 2 * Hd, A, B, e->atv(e->hid), 2 * Hd, e->atv(e->dlogits), e->a_pad, e->atv(e->dwc3), e->a_pad,
+    // (all a_pad columns: dlogits' pad columns are zero)
+    REGAT_TRY(dense(e, sd, true, false, 2 * Hd, e->a_pad, B, e->atv(e->hid), 2 * Hd, e->atv(e->dlogits), e->a_pad, e->atv(e->dwc3), e->a_pad,
                     REGAT_F32, epi0()));
     REGAT_CUDA(cudaMemcpy2DAsync(gradW(e, e->l_c3), (size_t)A * sizeof(float), e->atv(e->dwc3), (size_t)e->a_pad * sizeof(float),
                                  (size_t)A * sizeof(float), 2 * Hd, cudaMemcpyDeviceToDevice, sd));
-    REGAT_TRY(bias_grad(e, sd, e->atv(e->dlogits), e->a_pad, B, A, gradB(e, e->l_c3), &cb_side));
+    REGAT_TRY(bias_grad(e, sd, e->atv(e->dlogits), e->a_pad, B, e->a_pad, gradB(e, e->l_c3), &cb_side));   // pad columns: zeros into the slot's alignment padding
   } else {
     REGAT_TRY(fc_wgrad(e, sd, e->l_c3, 0, B, 2 * Hd, e->atv(e->hid), 2 * Hd, e->atv(e->dlogits), e->a_pad, true, &cb_side));
   }
@@ -781,7 +795,7 @@ int backward(Ctx& c, const float* target, float grad_scale, float* dq_att, float
                       REGAT_F32, epi0()));
       REGAT_CUDA(cudaMemcpy2DAsync(gradW(e, e->l_c3), (size_t)A * sizeof(float), e->atv(e->dwc3), (size_t)e->a_pad * sizeof(float),
                                    (size_t)A * sizeof(float), 2 * Hd, cudaMemcpyDeviceToDevice, sd));
-      REGAT_TRY(bias_grad(e, sd, e->atv(e->dlogits), e->a_pad, B, A, gradB(e, e->l_c3), &cb_side));
+      REGAT_TRY(bias_grad(e, sd, e->atv(e->dlogits), e->a_pad, B, e->a_pad, gradB(e, e->l_c3), &cb_side));   // pad columns: zeros into the slot's alignment padding
     } else {
       REGAT_TRY(fc_wgrad(e, sd, e->l_c3, 0, B, 2 * Hd, e->atv(e->hid), 2 * Hd, e->atv(e->dlogits), e->a_pad, true, &cb_side));
     }

@@ -1367,7 +1367,7 @@ int prepare(int transA, int transB, int M, int N, int K, const void* A, int lda,
   return REGAT_OK;
 }
 
-int launch_prepared(const Prepared& x, const Prepared* y, cudaStream_t st) {
+int launch_prepared(const Prepared& x, const Prepared* y, cudaStream_t st, int max_ctas = 0) {
   TcParams p = x.p;
   if (y) {
     p.s2.units = y->p.tiles_m * y->p.tiles_n; p.s2.M = y->p.M; p.s2.tiles_m = y->p.tiles_m; p.s2.total_k_blocks = y->p.total_k_blocks;
@@ -1377,7 +1377,8 @@ int launch_prepared(const Prepared& x, const Prepared* y, cudaStream_t st) {
   // BN=256: 4 stages x 48 KB + 2 x 256 TMEM columns, one CTA per SM.  BN=128: 3 stages x 32 KB + 2 x 128 columns, two per SM.
   // REGAT_SM_RESERVE=n leaves n SMs free of persistent GEMM CTAs so that a concurrent NCCL all-reduce can make progress
   static const int reserve = [] { const char* s = getenv("REGAT_SM_RESERVE"); return s ? std::max(0, atoi(s)) : 0; }();
-  const int sms = std::max(1, num_sms() - reserve);
+  // max_ctas > 0: a launch that must not take every SM (side-stream products beside the main stream's dependency chain)
+  const int sms = std::max(2, std::min(num_sms() - reserve, max_ctas > 0 ? max_ctas : num_sms()));
   const CUtensorMap& ma2 = y ? y->ma : x.ma;
   const CUtensorMap& mb2 = y ? y->mb : x.mb;
   const int epi = epi_kind(p, y != nullptr, y ? y->p.e.accumulate : 0, y ? y->p.C : nullptr);
@@ -1398,11 +1399,11 @@ bool gemm_tc_supported(int transA, int transB, int M, int N, int K, const void* 
 }
 
 int gemm_tc(int transA, int transB, int M, int N, int K, const void* A, int lda, const void* B, int ldb, void* C, int ldc,
-            int c_dtype, const EpiArgs& e, int split_k, cudaStream_t st, int c_block_cols, const long long* c_block_off) {
+            int c_dtype, const EpiArgs& e, int split_k, cudaStream_t st, int c_block_cols, const long long* c_block_off, int max_ctas) {
   if (M <= 0 || N <= 0) return REGAT_OK;
   Prepared x;
   REGAT_TRY(prepare(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, c_dtype, e, split_k, st, c_block_cols, c_block_off, 0, x));
-  return launch_prepared(x, nullptr, st);
+  return launch_prepared(x, nullptr, st, max_ctas);
 }
 
 // Two independent products in ONE launch: the persistent CTAs walk the units of c0, then those of c1, so a part-filled last
