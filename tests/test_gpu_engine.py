@@ -197,3 +197,26 @@ def test_cached_weight_state_follows_the_parameters(dtype, tol):
     eng.load_params(flat)
     again = eng.forward(dev["features"], dev["boxes"], dev["q_att"], dev["q_last"])
     assert _rel(again.cpu().numpy(), a.cpu().numpy()) < 1e-6
+
+
+@pytest.mark.parametrize("kw,B,N", [(SMALL, 5, 36), (dict(SMALL, q_dim=128, rel_dim=512, num_heads=8, num_answers=3129), 130, 20)])
+def test_chained_launch_matches_separate_launches(kw, B, N, monkeypatch):
+    """REGAT_CHAIN=1 (opt-in): pv -> hid -> logits -> loss -> dhid -> djoint -> dpooled as stages of one persistent launch
+    (gemm_chain_kernel) against the separately launched kernels: same loss, logits and gradients up to bf16 rounding of the
+    intermediates (the chain multiplies by the question embedding before rounding pv)."""
+    cfg, inp, flat, eng, dev, named64, args64 = _setup(kw, B, N, False, True, "bf16")
+    args = (dev["features"], dev["boxes"], dev["q_att"], dev["q_last"], dev["target"])
+    monkeypatch.delenv("REGAT_CHAIN", raising=False)
+    ref = eng.fwd_bwd(*args, want_logits=True, want_dq=True)
+    ref = {k: v.clone() for k, v in ref.items()}
+    g_ref = eng.grads.clone()
+    monkeypatch.setenv("REGAT_CHAIN", "1")
+    for _ in range(2):                       # twice: the stage counter must be back at zero after a launch
+        out = eng.fwd_bwd(*args, want_logits=True, want_dq=True)
+        torch.cuda.synchronize()
+        assert abs(float(out["loss"]) - float(ref["loss"])) <= 2e-3 * abs(float(ref["loss"]))
+        assert float(out["score"]) == pytest.approx(float(ref["score"]), abs=1e-3 * B + 1e-6)
+        assert _rel(out["logits"].cpu(), ref["logits"].cpu()) < 1e-2
+        assert float((eng.grads - g_ref).norm() / g_ref.norm()) < 2e-2
+        for k in ("dq_att", "dq_last"):
+            assert float((out[k] - ref[k]).norm() / ref[k].norm()) < 3e-2

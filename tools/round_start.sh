@@ -17,6 +17,9 @@ tail -c 600 $out/${tag}_bench_1gpu.json
 # launch list: cold-cache, serialised -- shares only (B200_PROFILING.md)
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/${tag}_ncu_list.log 2>&1; echo "ncu list rc=$?"
-# one full capture of the kernels that bound the step
-ncu --set full --clock-control none --import-source on -k "regex:gemm_tc_kernel|geoattn_fwd_bf16_kernel|attn_bwd_bf16_kernel" \
-    -c 12 -o $out/${tag}_full python bench.py --steps 1 --warmup 3 --no-cpu-baseline > $out/${tag}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+# full captures of the kernels that bound the step: the three attention kernels, and the first 8 tcgen05 products (qs, uqe, weff,
+# v2out, s, Q, KV, pv) of the first step
+ncu --set full --clock-control none --import-source on -k "regex:geoattn_fwd_fast_kernel|attn_bwd_bf16_kernel|geo_bwd_kernel" \
+    -c 3 -o $out/${tag}_attn python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra-legs > $out/${tag}_ncu_attn.log 2>&1; echo "ncu attn rc=$?"
+ncu --set full --clock-control none --import-source on -k "regex:gemm_tc_kernel" \
+    -c 8 -o $out/${tag}_gemm python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-extra-legs > $out/${tag}_ncu_gemm.log 2>&1; echo "ncu gemm rc=$?"
