@@ -451,6 +451,9 @@ int optimize_range(regat_engine* e, int r, cudaStream_t st) {
   const int cbase = all ? 0 : e->rng[r].cbase, tbase = all ? 0 : e->rng[r].tbase;
   if (to.n == 0) return REGAT_OK;
   float* stats = e->at<float>(e->stats) + 2 * tbase;
+  // (Measured and dropped: one launch with grid-wide barriers for the small ranges at the tail of the step -- statistics, update,
+  // alpha and bf16 copies bit-identical to the four kernels -- made the step 5 us SLOWER: its blocks cannot become resident beside
+  // the weight-gradient GEMMs that are still running, while the four small grids slip into the gaps.)
   REGAT_TRY(k_opt_reduce(e->params, e->grads, to, chunks, e->at<float>(e->partials) + 2 * cbase, stats, st,
                          e->at<unsigned int>(e->counters) + tbase));
   // the update leaves ||v_new||^2 per chunk in `vpart` (engine-wide chunk numbering)
@@ -462,11 +465,20 @@ int optimize_range(regat_engine* e, int r, cudaStream_t st) {
 // bf16 engine, M <= 24 keys: packed-bf16 fast path of the fused attention kernels (P buffer = probabilities -> dz, GB buffer = rz)
 bool attn_fast(const regat_engine* e, int N) { return e->dtype == REGAT_BF16 && regat_geoattn_fast_supported(N, e->cfg.nongt_dim) != 0; }
 
-int ensure_side(regat_engine* e) {
+// The side stream (bias sums, geometry reduction, off-chain products) runs at the lowest priority; the optimizer and exchange
+// streams take the priority of the caller's stream.  A caller that runs the step on a high-priority stream (bench.py,
+// GraphedTrainStep) thereby ranks the dependency chain and the optimizer above the side work when SM slots free up
+// (REGAT_OPT_PRIO=low: optimizer at the lowest priority too).
+int ensure_side(regat_engine* e, cudaStream_t caller) {
   if (e->side) return REGAT_OK;
-  REGAT_CUDA(cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking));
-  REGAT_CUDA(cudaStreamCreateWithFlags(&e->opt, cudaStreamNonBlocking));
-  REGAT_CUDA(cudaStreamCreateWithFlags(&e->comm, cudaStreamNonBlocking));
+  int lo = 0, hi = 0, pr = 0;
+  REGAT_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  if (caller == nullptr || cudaStreamGetPriority(caller, &pr) != cudaSuccess) { pr = lo; (void)cudaGetLastError(); }
+  const char* op = getenv("REGAT_OPT_PRIO");
+  const int opt_pr = (op && strcmp(op, "low") == 0) ? lo : pr;
+  REGAT_CUDA(cudaStreamCreateWithPriority(&e->side, cudaStreamNonBlocking, lo));
+  REGAT_CUDA(cudaStreamCreateWithPriority(&e->opt, cudaStreamNonBlocking, opt_pr));
+  REGAT_CUDA(cudaStreamCreateWithPriority(&e->comm, cudaStreamNonBlocking, opt_pr));
   for (int i = 0; i < regat_engine::NEV; ++i) REGAT_CUDA(cudaEventCreateWithFlags(&e->ev[i], cudaEventDisableTiming));
   return REGAT_OK;
 }
@@ -511,7 +523,7 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
   const int dt = e->dtype, B = c.B, N = c.N, M = c.M, R = c.R, Rm = c.Rm;
   const int V = cf.v_dim, Q = cf.q_dim, D = cf.rel_dim, H = cf.num_heads, A = cf.num_answers, Hd = cf.q_dim, dirs = cf.dir_num;
 
-  REGAT_TRY(ensure_side(e));
+  REGAT_TRY(ensure_side(e, st));
   cudaStream_t sd = e->side;
   const size_t es = dtype_size(dt);
   // activations in the compute dtype: the casts do not depend on the weights, so they run on the side stream while the main

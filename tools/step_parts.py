@@ -14,14 +14,18 @@ eng.load_params(synthetic.make_params(cfg, seed=7, trained_like=True))
 inp = synthetic.make_inputs(cfg, B, N, seed=3)
 dev = {k: torch.as_tensor(v).cuda() for k, v in inp.items()}
 args = (dev["features"], dev["boxes"], dev["q_att"], dev["q_last"], dev["target"])
-eng.set_lr(1e-3)
-for _ in range(2):
-    eng.train_step_dev(*args)
+# -1: the step's stream outranks the engine's side stream (the engine's optimizer / exchange streams take the caller's priority)
+ST = torch.cuda.Stream(priority=int(os.environ.get("PRIO", "0")))
+ST.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(ST):
+    eng.set_lr(1e-3)
+    for _ in range(2):
+        eng.train_step_dev(*args)
 torch.cuda.synchronize()
 
 
 def timed(fn, reps=30):
-    st = torch.cuda.Stream()
+    st = ST
     g = torch.cuda.CUDAGraph()
     with torch.cuda.stream(st):
         fn(); torch.cuda.synchronize()
