@@ -418,7 +418,8 @@ int derive_weights(regat_engine* e, int r, cudaStream_t st) {
   REGAT_TRY(k_wn_alpha(e->params, tv, e->at<float>(e->sumsq) + l0, e->at<float>(e->alpha) + l0, e->at<float>(e->invn) + l0, st,
                        e->at<float>(e->vpart) + vbase, (e->dtype == REGAT_BF16 && tg.n) ? &tg : nullptr, e->at<float>(e->gbias),
                        label_local, LL.v_off, LL.b_off, label_local >= 0 ? e->at<float>(e->scal) : nullptr));
-  if (e->dtype == REGAT_BF16) REGAT_TRY(k_wn_scaled_copy(e->params, tv, chunks, e->at<float>(e->alpha), e->atv(e->lowp), st));
+  static const int dbg_nocopy = [] { const char* s = getenv("REGAT_OPT_DEBUG"); return (s && strstr(s, "nocopy")) ? 1 : 0; }();
+  if (e->dtype == REGAT_BF16 && !(dbg_nocopy && !all)) REGAT_TRY(k_wn_scaled_copy(e->params, tv, chunks, e->at<float>(e->alpha), e->atv(e->lowp), st));
   return REGAT_OK;
 }
 
@@ -454,6 +455,8 @@ int optimize_range(regat_engine* e, int r, cudaStream_t st) {
   // (Measured and dropped: one launch with grid-wide barriers for the small ranges at the tail of the step -- statistics, update,
   // alpha and bf16 copies bit-identical to the four kernels -- made the step 5 us SLOWER: its blocks cannot become resident beside
   // the weight-gradient GEMMs that are still running, while the four small grids slip into the gaps.)
+  static const int dbg_noreduce = [] { const char* s = getenv("REGAT_OPT_DEBUG"); return (s && strstr(s, "noreduce")) ? 1 : 0; }();
+  if (!(dbg_noreduce && !all))
   REGAT_TRY(k_opt_reduce(e->params, e->grads, to, chunks, e->at<float>(e->partials) + 2 * cbase, stats, st,
                          e->at<unsigned int>(e->counters) + tbase));
   // the update leaves ||v_new||^2 per chunk in `vpart` (engine-wide chunk numbering)
