@@ -3,6 +3,8 @@
 // 128-bit accesses, grid sized in multiples of the SM count, warp-shuffle reductions.
 #include <algorithm>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -389,6 +391,137 @@ __global__ void __launch_bounds__(256) butd_pool_bwd_kernel(const T* __restrict_
       st8<T>(dv1 + ((size_t)b * N + n) * D + c, o);
     }
     st8<T>(dweff + (size_t)b * D + c, acc);
+  }
+}
+
+// bf16, one graph's v1 rows fit in shared memory (N D bf16 <= 200 KB): the tile is staged ONCE with cp.async -- every 16-byte piece
+// of it in flight at the same time -- and both passes over it (logits, weighted sum) read shared memory.  The kernels above walk
+// the rows from global memory twice with one dependent round trip per row and warp (13.6 / 16.1 us for 19 MB; these: one round trip).
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__global__ void __launch_bounds__(256) butd_pool_fwd_staged_kernel(const bf16* __restrict__ v1, const bf16* __restrict__ weff,
+                                                                   const float* __restrict__ cb, float* __restrict__ att,
+                                                                   bf16* __restrict__ pooled, int N, int D) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  bf16* vs = reinterpret_cast<bf16*>(smraw);                       // [N][D]
+  float* sm = reinterpret_cast<float*>(smraw + (size_t)N * D * 2);  // [N] logits / att
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bf16* vb = v1 + (size_t)b * N * D;
+  const bf16* wb = weff + (size_t)b * D;
+  for (int i = threadIdx.x; i < N * D / 8; i += 256) cp_async16(vs + (size_t)i * 8, vb + (size_t)i * 8);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  for (int n = warp; n < N; n += 8) {
+    float s = 0.f;
+    for (int c = lane * 8; c < D; c += 256) {
+      float x[8], w[8];
+      ld8<bf16>(vs + (size_t)n * D + c, x);
+      ld8<bf16>(wb + c, w);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s = fmaf(x[u], w[u], s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) sm[n] = s + cb[b];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int n = lane; n < N; n += 32) mx = fmaxf(mx, sm[n]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int n = lane; n < N; n += 32) { const float e = expf(sm[n] - mx); sm[n] = e; sum += e; }
+    sum = warp_sum(sum);
+    const float inv = 1.f / sum;
+    for (int n = lane; n < N; n += 32) { const float a = sm[n] * inv; sm[n] = a; att[(size_t)b * N + n] = a; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x * 8; c < D; c += 256 * 8) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int n = 0; n < N; ++n) {
+      float x[8];
+      ld8<bf16>(vs + (size_t)n * D + c, x);
+      const float a = sm[n];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] = fmaf(a, x[u], acc[u]);
+    }
+    st8<bf16>(pooled + (size_t)b * D + c, acc);
+  }
+}
+__global__ void __launch_bounds__(256) butd_pool_bwd_staged_kernel(const bf16* __restrict__ v1, const bf16* __restrict__ weff,
+                                                                   const float* __restrict__ att, const bf16* __restrict__ dpooled,
+                                                                   bf16* __restrict__ dv1, bf16* __restrict__ dweff,
+                                                                   float* __restrict__ dcb, int N, int D) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  bf16* vs = reinterpret_cast<bf16*>(smraw);
+  float* a_s = reinterpret_cast<float*>(smraw + (size_t)N * D * 2);
+  float* dl_s = a_s + N;
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bf16* vb = v1 + (size_t)b * N * D;
+  const bf16* dp = dpooled + (size_t)b * D;
+  for (int i = threadIdx.x; i < N * D / 8; i += 256) cp_async16(vs + (size_t)i * 8, vb + (size_t)i * 8);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int n = threadIdx.x; n < N; n += 256) a_s[n] = att[(size_t)b * N + n];
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  // da[n] = <dpooled, v1[n]>
+  for (int n = warp; n < N; n += 8) {
+    float s = 0.f;
+    for (int c = lane * 8; c < D; c += 256) {
+      float x[8], g[8];
+      ld8<bf16>(vs + (size_t)n * D + c, x);
+      ld8<bf16>(dp + c, g);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s = fmaf(x[u], g[u], s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) dl_s[n] = s;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    float dot = 0.f;
+    for (int n = lane; n < N; n += 32) dot = fmaf(a_s[n], dl_s[n], dot);
+    dot = warp_sum(dot);
+    float tot = 0.f;
+    for (int n = lane; n < N; n += 32) { const float d = a_s[n] * (dl_s[n] - dot); dl_s[n] = d; tot += d; }
+    tot = warp_sum(tot);
+    if (lane == 0) dcb[b] = tot;
+  }
+  __syncthreads();
+  // column group cg = 8 columns; the block's 256 threads cover D / 8 column groups x (256 / (D/8)) row phases
+  const int groups = D / 8;
+  const int phases = max(1, 256 / groups);
+  const int cgi = threadIdx.x % groups, ph = threadIdx.x / groups;
+  if (ph < phases) {
+    const int c = cgi * 8;
+    float g[8], w[8], acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    ld8<bf16>(dp + c, g);
+    ld8<bf16>(weff + (size_t)b * D + c, w);
+    for (int n = ph; n < N; n += phases) {
+      float x[8], o[8];
+      ld8<bf16>(vs + (size_t)n * D + c, x);
+      const float a = a_s[n], d = dl_s[n];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { o[u] = fmaf(a, g[u], d * w[u]); acc[u] = fmaf(d, x[u], acc[u]); }
+      st8<bf16>(dv1 + ((size_t)b * N + n) * D + c, o);
+    }
+    if (phases == 1) {
+      st8<bf16>(dweff + (size_t)b * D + c, acc);
+    } else {
+      // combine the row phases of a column group through shared memory (the staged tile is no longer needed)
+      __syncthreads();
+      float* part = reinterpret_cast<float*>(smraw);      // [phases][D]
+#pragma unroll
+      for (int u = 0; u < 8; ++u) part[(size_t)ph * D + c + u] = acc[u];
+      __syncthreads();
+      if (ph == 0) {
+        for (int q = 1; q < phases; ++q)
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc[u] += part[(size_t)q * D + c + u];
+        st8<bf16>(dweff + (size_t)b * D + c, acc);
+      }
+    }
   }
 }
 
@@ -963,6 +1096,20 @@ int k_label_grad(const float* dc, float* grads, long long v_off, long long b_off
   return REGAT_OK;
 }
 
+// the staged pooling kernels need more than the default 48 KB of dynamic shared memory: raised once per device to the 200 KB cap
+int set_pool_smem(bool fwd, size_t /*bytes*/) {
+  static std::mutex mu;
+  static bool done[2][64] = {};
+  int dev = 0;
+  REGAT_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(mu);
+  if (dev >= 0 && dev < 64 && done[fwd][dev]) return REGAT_OK;
+  if (fwd) REGAT_CUDA(cudaFuncSetAttribute(butd_pool_fwd_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  else REGAT_CUDA(cudaFuncSetAttribute(butd_pool_bwd_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  if (dev >= 0 && dev < 64) done[fwd][dev] = true;
+  return REGAT_OK;
+}
+
 }  // namespace regat
 
 using namespace regat;
@@ -974,6 +1121,17 @@ extern "C" int regat_butd_pool_fwd(int dtype, int B, int N, int D, const void* v
   REGAT_REQUIRE(aligned16(v1) && aligned16(weff) && aligned16(pooled), REGAT_ERR_ALIGN, "butd_pool_fwd: unaligned tensor");
   if (B <= 0 || N <= 0) return REGAT_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const size_t staged = (size_t)N * D * 2 + (size_t)N * 4 + 16;
+    static const int staged_on = [] { const char* s = getenv("REGAT_POOL_STAGED"); return s ? atoi(s) : 1; }();
+    if (staged_on && dtype == REGAT_BF16 && staged <= 200 * 1024 && aligned16(v1)) {
+      REGAT_TRY(set_pool_smem(true, staged));
+      butd_pool_fwd_staged_kernel<<<B, 256, staged, st>>>(static_cast<const bf16*>(v1), static_cast<const bf16*>(weff), cb, att,
+                                                           static_cast<bf16*>(pooled), N, D);
+      REGAT_POST_LAUNCH();
+      return REGAT_OK;
+    }
+  }
   DISPATCH_T(dtype, (butd_pool_fwd_kernel<T><<<B, 256, N * sizeof(float), st>>>(static_cast<const T*>(v1), static_cast<const T*>(weff), cb, att,
                                                                                static_cast<T*>(pooled), N, D)));
   REGAT_POST_LAUNCH();
@@ -985,6 +1143,20 @@ extern "C" int regat_butd_pool_bwd(int dtype, int B, int N, int D, const void* v
   REGAT_REQUIRE(D % 8 == 0, REGAT_ERR_SHAPE, "butd_pool_bwd: D must be a multiple of 8");
   if (B <= 0 || N <= 0) return REGAT_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const int groups = D / 8, phases = std::max(1, 256 / groups);
+    const size_t staged = std::max((size_t)N * D * 2, (size_t)phases * D * 4) + (size_t)2 * N * 4 + 16;
+    static const int staged_on = [] { const char* s = getenv("REGAT_POOL_STAGED"); return s ? atoi(s) : 1; }();
+    if (staged_on && dtype == REGAT_BF16 && staged <= 200 * 1024 && aligned16(v1) && aligned16(dv1) && aligned16(dpooled) && aligned16(weff) &&
+        aligned16(dweff) && groups <= 256 && (256 % groups == 0 || groups == 256)) {
+      REGAT_TRY(set_pool_smem(false, staged));
+      butd_pool_bwd_staged_kernel<<<B, 256, staged, st>>>(static_cast<const bf16*>(v1), static_cast<const bf16*>(weff), att,
+                                                           static_cast<const bf16*>(dpooled), static_cast<bf16*>(dv1),
+                                                           static_cast<bf16*>(dweff), dcb, N, D);
+      REGAT_POST_LAUNCH();
+      return REGAT_OK;
+    }
+  }
   DISPATCH_T(dtype, (butd_pool_bwd_kernel<T><<<B, 256, 2 * N * sizeof(float), st>>>(
                         static_cast<const T*>(v1), static_cast<const T*>(weff), att, static_cast<const T*>(dpooled),
                         static_cast<T*>(dv1), static_cast<T*>(dweff), dcb, N, D)));
