@@ -121,6 +121,19 @@ def test_split_k_weight_gradient_shape():
     assert ((out - ref).abs().max() / ref.abs().max()).item() < 2e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 2048, 9216), (1024, 4096, 5120), (1024, 1024, 9216), (2048, 1024, 4608)])
+def test_long_k_weight_gradient_on_cta_pairs(M, N, K):
+    """Weight-gradient shapes (both operands MN-major, plain fp32 output, K >= 2048, few output tiles): 256 x 256 units on CTA pairs
+    with the split-K factor that fills one round of pairs (1, 2 or 4 here) -- vector red into a destination the call zeroes itself."""
+    A, B, ref = _operands(1, 0, M, N, K, torch.bfloat16, seed=11)
+    out = torch.full((M, N), 3.0, device="cuda", dtype=torch.float32)      # must be overwritten, not accumulated into
+    _gemm(_lib.BF16, 1, 0, M, N, K, A, B, out, _lib.F32)
+    assert ((out - ref).abs().max() / ref.abs().max()).item() < 2e-3
+    out2 = torch.full((M, N), -1.0, device="cuda", dtype=torch.float32)
+    _gemm(_lib.BF16, 1, 0, M, N, K, A, B, out2, _lib.F32)
+    assert ((out2 - out).abs().max() / ref.abs().max()).item() < 1e-5        # atomics: order noise only
+
+
 def test_gemm_argument_errors():
     a = torch.zeros(8, 8, device="cuda")
     l = _lib.lib()
