@@ -5,6 +5,8 @@
 
 #include <mutex>
 
+#include <cstring>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -48,6 +50,12 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {   // block
   return s;   // valid in warp 0
 }
 
+// Programmatic dependent launch between the optimizer's small kernels of one range: the dependent grid is scheduled while the
+// upstream one still runs and blocks in pdl_wait() until that grid has completed and flushed (griddepcontrol.wait); without the
+// launch attribute both calls are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- weight norm (weight_norm.py:35-41)
 constexpr int WN_CHUNK = 4096;   // elements per block
 __global__ void __launch_bounds__(256) wn_prepare_kernel(const float* __restrict__ params, TensorList tl, float* sumsq,
@@ -89,6 +97,7 @@ __global__ void __launch_bounds__(256) wn_prepare_kernel(const float* __restrict
 // layers sharing an input can sit side by side in one wide matrix (Q_0|Q_1, K_0|K_1|V'_0|V'_1, q2attention|question_embed).
 __global__ void __launch_bounds__(256) wn_scaled_copy_kernel(const float* __restrict__ params, TensorList tl, int chunks,
                                                              const float* __restrict__ alpha, bf16* __restrict__ lowp) {
+  pdl_wait();
   // persistent: a few fat blocks per SM walk the 16 KB chunks (4634 two-iteration blocks spent their time being scheduled)
   int l = 0;
   for (int chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
@@ -142,6 +151,8 @@ struct AlphaExtras {          // small per-forward chores folded into the one-bl
 };
 __global__ void wn_alpha_kernel(const float* __restrict__ params, TensorList tl, float* __restrict__ sumsq,
                                 const float* __restrict__ partials, float* alpha, float* inv_norm, AlphaExtras ex) {
+  pdl_wait();
+  pdl_trigger();
   // one warp per tensor; with `partials` the per-chunk sums are added in a fixed order (bitwise reproducible, so data-parallel
   // replicas that hold identical parameters compute identical alpha)
   const int l = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -704,6 +715,7 @@ __global__ void __launch_bounds__(256) opt_reduce_kernel(const float* __restrict
                                                          TensorList tl, float* stats /* per-chunk partials [chunks][2] */,
                                                          float* __restrict__ tstats /* per-tensor [n][2] */,
                                                          unsigned int* __restrict__ counters) {
+  pdl_trigger();                 // the update kernel may be scheduled behind this grid right away (it waits for our results)
   __shared__ float red[8];
   __shared__ bool last;
   int l = 0;
@@ -777,6 +789,8 @@ __global__ void __launch_bounds__(256) opt_update_kernel(float* __restrict__ par
                                                          const float* __restrict__ stats, const float* __restrict__ alpha,
                                                          const float* __restrict__ inv_norm, OptHyper hp,
                                                          float* __restrict__ vpartials) {
+  pdl_wait();                    // statistics of opt_reduce_kernel (programmatic dependent launch: we may have started early)
+  pdl_trigger();
   __shared__ float red[8];
   int l = 0;
   while (l + 1 < tl.n && (int)blockIdx.x >= tl.chunk_start[l + 1]) ++l;
@@ -913,6 +927,20 @@ inline int grid_for(long long n, int per_block = 256) {
 }  // namespace
 
 // ---------------------------------------------------------------- host launchers (declared in kernels.h)
+// launch with the programmatic-stream-serialization attribute (REGAT_OPT_PDL=0: plain launches)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, cudaStream_t st, Args... args) {
+  static const int on = [] { const char* s = getenv("REGAT_OPT_PDL"); return s ? atoi(s) : 1; }();
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid, 1, 1); cfg.blockDim = dim3((unsigned)block, 1, 1); cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 int build_tensor_list(TensorList& tl) {
   int c = 0;
   for (int l = 0; l < tl.n; ++l) {
@@ -929,7 +957,7 @@ int k_wn_prepare(const float* params, const TensorList& tl, int chunks, float* s
   return REGAT_OK;
 }
 int k_wn_scaled_copy(const float* params, const TensorList& tl, int chunks, const float* alpha, void* lowp, cudaStream_t st) {
-  wn_scaled_copy_kernel<<<std::min(chunks, num_sms() * 8), 256, 0, st>>>(params, tl, chunks, alpha, static_cast<bf16*>(lowp));
+  REGAT_CUDA(launch_pdl(wn_scaled_copy_kernel, std::min(chunks, num_sms() * 8), 256, st, params, tl, chunks, alpha, static_cast<bf16*>(lowp)));
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
@@ -949,7 +977,7 @@ int k_wn_alpha(const float* params, const TensorList& tl, float* sumsq, float* a
     ex.gather_n = gather->n;
     for (int k = 0; k < gather->n; ++k) { ex.g_src[k] = gather->off[k]; ex.g_dst[k] = gather->off_lowp[k]; ex.g_numel[k] = gather->numel[k]; }
   }
-  wn_alpha_kernel<<<1, 1024, 0, st>>>(params, tl, sumsq, partials, alpha, inv_norm, ex);
+  REGAT_CUDA(launch_pdl(wn_alpha_kernel, 1, 1024, st, params, tl, sumsq, partials, alpha, inv_norm, ex));
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
@@ -1070,7 +1098,7 @@ int k_opt_reduce(const float* params, const float* grads, const TensorList& tl, 
 }
 int k_opt_update(float* params, const float* grads, float* m, float* u, const TensorList& tl, int chunks, const float* stats,
                  const float* alpha, const float* inv_norm, const OptHyper& hp, cudaStream_t st, float* vpartials) {
-  opt_update_kernel<<<chunks, 256, 0, st>>>(params, grads, m, u, tl, stats, alpha, inv_norm, hp, vpartials);
+  REGAT_CUDA(launch_pdl(opt_update_kernel, chunks, 256, st, params, grads, m, u, tl, stats, alpha, inv_norm, hp, vpartials));
   REGAT_POST_LAUNCH();
   return REGAT_OK;
 }
