@@ -478,7 +478,8 @@ int ensure_side(regat_engine* e, cudaStream_t caller) {
   REGAT_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
   if (caller == nullptr || cudaStreamGetPriority(caller, &pr) != cudaSuccess) { pr = lo; (void)cudaGetLastError(); }
   const char* op = getenv("REGAT_OPT_PRIO");
-  const int opt_pr = (op && strcmp(op, "low") == 0) ? lo : pr;
+  int opt_pr = (op && strcmp(op, "low") == 0) ? lo : pr;
+  if (op && strcmp(op, "high") == 0) opt_pr = hi;      // numerically smallest = highest
   REGAT_CUDA(cudaStreamCreateWithPriority(&e->side, cudaStreamNonBlocking, lo));
   REGAT_CUDA(cudaStreamCreateWithPriority(&e->opt, cudaStreamNonBlocking, opt_pr));
   REGAT_CUDA(cudaStreamCreateWithPriority(&e->comm, cudaStreamNonBlocking, opt_pr));

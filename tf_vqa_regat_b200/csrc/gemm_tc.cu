@@ -330,6 +330,9 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, BN == 128 ? 2 : 1) gemm_tc_ker
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + ACC);
   float* bias_stage = reinterpret_cast<float*>(tmem_slot + 4);       // EPIW x 128 floats: each epilogue warp's bias columns of a unit
 
+  // programmatic dependent launch: let the next kernel of the stream be scheduled as soon as resources free up (it blocks in its
+  // own griddepcontrol.wait until this grid has completed)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t crank = CTA2 ? cluster_ctarank() : 0u;            // rank in the CTA pair
   const int worker = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -352,6 +355,9 @@ __global__ void __launch_bounds__(64 + 32 * EPIW, BN == 128 ? 2 : 1) gemm_tc_ker
   if (CTA2) cluster_sync_all(); else __syncthreads();     // pair: the peer's barriers exist before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above (barriers, TMEM, tensor-map prefetch) touched nothing the previous kernel of the stream produces; from here
+  // on it does (no-op unless launched with the programmatic attribute)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // unit -> (m0, n0, kb0, kb1)
   auto decode = [&](int u, int& m0, int& n0, int& kb0, int& kb1) {
@@ -1230,18 +1236,26 @@ int launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, 
       if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
   }
-  if (CTA2) {
+  {
+    static const int pdl = [] { const char* s = getenv("REGAT_TC_PDL"); return s ? atoi(s) : 1; }();
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)ctas, 1, 1); cfg.blockDim = dim3(64 + 32 * EPIW, 1, 1);
     cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if (CTA2) {
+      at[na].id = cudaLaunchAttributeClusterDimension;
+      at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (pdl) {
+      at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = at; cfg.numAttrs = na;
     REGAT_CUDA(cudaLaunchKernelEx(&cfg, kern, ma, mb, p, ma2, mb2));
-  } else {
-    kern<<<ctas, 64 + 32 * EPIW, smem, st>>>(ma, mb, p, ma2, mb2);
   }
   REGAT_POST_LAUNCH();
   return REGAT_OK;
