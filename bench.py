@@ -219,6 +219,10 @@ class Leg:
             self.trainer.broadcast_params(0)
             if not self.trainer.fused and rank == 0:
                 print("[bench] fused in-place exchange unavailable on this system: eager steps with the callback-free exchange", flush=True)
+        if self.trainer is None and world > 1:
+            # the data-parallel legs before this one switched programmatic dependent launch off for the process (it delays the
+            # exchange kernels); a leg without an exchange gets it back
+            self.eng.lib.regat_engine_set_dp(self.eng._h, None, 0, None, 0, 1, 0)
         self.logits = torch.empty(B, cfg.num_answers, device=dev) if self.eval_only else None
         self.graphs, self.launches, self.graphed = {}, 0, False
         if not self.eval_only:

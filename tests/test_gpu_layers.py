@@ -146,7 +146,9 @@ def test_layer_model_trains_through_the_engine(dtype):
     # one set of weights: the layers see what the engine trained
     got = model.to_flat(cfg)
     dd = np.abs(got - ref.params.cpu().numpy())
-    assert dd.max() <= 2 * lr + 1e-6 and dd.mean() < 0.02 * lr
+    # two engines, same arithmetic, but atomics order noise decides the sign of a gradient that is ~0 and Adamax moves such an element by
+    # +-lr per step: single elements may differ by up to 2 lr per step, the mean stays far below
+    assert dd.max() <= 2 * lr * 3 + 1e-6 and dd.mean() < 0.02 * lr
     assert np.abs(got - flat).max() > 0.5 * lr                                # and they really moved
     layerwise = model(dev["features"], dev["q_att"], dev["q_last"], geo)     # fp32 layer-by-layer kernels on the trained weights
     compiled = model.predict(dev["features"], dev["q_att"], dev["q_last"], geo)

@@ -23,6 +23,7 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return REGAT_ERR_CUDA;
 }
 int& launch_counter() { return g_launches; }
+int& pdl_enabled() { static int on = 1; return on; }
 
 int num_sms() {
   static int cached = 0;

@@ -48,6 +48,9 @@ inline int64_t round_up64(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 inline size_t dtype_size(int dt) { return dt == REGAT_BF16 ? 2 : 4; }
 
 int num_sms();  // cached multiprocessor count of the current device
+// Programmatic dependent launch for the library's kernel chains (tcgen05 products, optimizer kernels).  On by default; the engine
+// switches it off for data-parallel steps (measured on 8 GPUs: early-resident dependents delay the exchange kernels, +40 us).
+int& pdl_enabled();
 
 // ---- device-side scalar conversions ----
 __device__ __forceinline__ float to_f(float x) { return x; }

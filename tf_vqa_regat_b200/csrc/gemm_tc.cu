@@ -1249,7 +1249,7 @@ int launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, 
       at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
       ++na;
     }
-    if (pdl) {
+    if (pdl && pdl_enabled()) {
       at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       at[na].val.programmaticStreamSerializationAllowed = 1;
       ++na;

@@ -937,7 +937,7 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, cudaStream_t
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = on ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = (on && pdl_enabled()) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
