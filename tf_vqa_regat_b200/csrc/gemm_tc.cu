@@ -173,9 +173,6 @@ __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
 }
 // C / gate / c2 arrive as generic pointers; they are global memory by contract, and saying so keeps the accesses off the
 // generic path
-__device__ __forceinline__ void stg_v4(void* p, float4 v) {
-  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w));
-}
 __device__ __forceinline__ float4 ldg_v4(const void* p) {
   float4 v;
   asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
@@ -203,10 +200,6 @@ __device__ __forceinline__ void stg_v4u(void* p, const uint32_t* w) {
 __device__ __forceinline__ void stg_v8u(void* p, const uint32_t* w) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
                "r"(w[5]), "r"(w[6]), "r"(w[7]));
-}
-__device__ __forceinline__ void stg_v8f(void* p, const float* x) {
-  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]), "f"(x[4]),
-               "f"(x[5]), "f"(x[6]), "f"(x[7]));
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
