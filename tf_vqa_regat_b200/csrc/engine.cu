@@ -533,17 +533,20 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
   // activations in the compute dtype: the casts do not depend on the weights, so they run on the side stream while the main
   // stream derives alpha and the bf16 kernels from the parameters (both HBM-bound, neither saturates the memory system alone)
   const void* feat = c.features; const void* qatt = c.q_att; const void* qlast = c.q_last;
-  if (training && e->grads) {
-    REGAT_TRY(fork_to(st, sd, e->ev[2]));
-    REGAT_TRY(zero_accumulators(e, sd, c.fused_opt));
-  }
   if (dt == REGAT_BF16) {
+    // the feature cast is the first thing on the step's critical path (v2out waits for it): it goes first on the side stream and
+    // the main stream waits for it alone; the question casts and the accumulator zeroing, which only later side-stream work and
+    // the backward pass need, queue behind it
     REGAT_TRY(fork_to(st, sd, e->ev[2]));
     REGAT_TRY(k_cast(REGAT_BF16, c.features, e->atv(e->featT), (long long)R * V, sd));
+    REGAT_CUDA(cudaEventRecord(e->ev[3], sd));                       // bf16 features ready
     REGAT_TRY(k_cast(REGAT_BF16, c.q_last, e->atv(e->qlastT), (long long)B * Q, sd));
     REGAT_TRY(k_cast(REGAT_BF16, c.q_att, e->atv(e->qattT), (long long)B * Q, sd));
     feat = e->atv(e->featT); qatt = e->atv(e->qattT); qlast = e->atv(e->qlastT);
-    REGAT_CUDA(cudaEventRecord(e->ev[3], sd));                       // casts done
+  }
+  if (training && e->grads) {
+    REGAT_TRY(fork_to(st, sd, e->ev[2]));
+    REGAT_TRY(zero_accumulators(e, sd, c.fused_opt));
   }
   REGAT_TRY(prepare_weights(e, st));
   // ---- side stream: the question branches depend only on q_last / q_att and the weights (fusion.py:37,47-52)
