@@ -552,6 +552,10 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
   // ---- side stream: the question branches depend only on q_last / q_att and the weights (fusion.py:37,47-52)
   REGAT_TRY(fork_to(st, sd, e->ev[0]));
   if (dt == REGAT_BF16) REGAT_CUDA(cudaStreamWaitEvent(st, e->ev[3], 0));      // main stream: the bf16 features are ready
+  // alpha of the pair_pos_fc layers must be contiguous per direction for the attention kernels: gathered here, off the main
+  // stream's chain of encoder products (the main stream joins at ev[4], before the s product)
+  for (int d = 0; d < dirs; ++d)
+    REGAT_CUDA(cudaMemcpyAsync(e->at<float>(e->scal) + 8 + d, alphap(e, e->l_pos[d]), sizeof(float), cudaMemcpyDeviceToDevice, sd));
   {  // qs = q_att Ws[D:]  (the question half of self_weights' input, relation_encoder.py:31-35); consumed by the s GEMM below
     EpiArgs ep = epi0();
     REGAT_TRY(dense(e, sd, false, false, B, D, Q, qatt, Q, W(e, e->l_self, D), ldW(e, e->l_self), e->atv(e->qs), D, REGAT_F32, ep));
@@ -610,10 +614,7 @@ int forward(Ctx& c, bool training, float* logits_out, float* att_out) {
     const Layer& P0 = e->layers[e->l_pos[0]];
     const long long wstride = dirs > 1 ? e->layers[e->l_pos[1]].v_off - P0.v_off : 0;
     const long long bstride = dirs > 1 ? e->layers[e->l_pos[1]].b_off - P0.b_off : 0;
-    // alpha of the pair_pos_fc layers must be contiguous per direction: gather them
-    float* ag = e->at<float>(e->scal) + 8;
-    for (int d = 0; d < dirs; ++d)
-      REGAT_CUDA(cudaMemcpyAsync(ag + d, alphap(e, e->l_pos[d]), sizeof(float), cudaMemcpyDeviceToDevice, st));
+    const float* ag = e->at<float>(e->scal) + 8;                     // gathered on the side stream above
     if (attn_fast(e, N))
       REGAT_TRY(regat_geoattn_fwd_fast(B, N, cf.nongt_dim, D, H, dirs, cf.pos_emb_dim, e->atv(e->Qb), e->atv(e->KVb), c.boxes, e->wave_div,
                                        e->params + P0.v_off, wstride, ag, e->params + P0.b_off, bstride, e->at<float>(e->scal),
