@@ -57,23 +57,25 @@ def _att_layer(p, pre, roi, adj, pos_emb, label_att, cfg):
     return out.reshape(B, N, D)
 
 
-def encoder(p, cfg, features, pos_emb, q_att):
-    # relation_encoder.py:65-93 + graph_att_net.py:40-83
+def encoder(p, cfg, features, pos_emb, q_att, num_steps=1):
+    # relation_encoder.py:65-93 + graph_att_net.py:40-83; num_steps > 1 repeats :82-91 on the running `visual`, same variables
     B, N, _ = features.shape
     adj = torch.ones(B, N, N, 1, dtype=features.dtype)
-    v0 = _fc(features, p, "v_relation.v2out", relu=True) if cfg.v_dim != cfg.rel_dim else features
-    mask = (v0.sum(-1) != 0).to(v0.dtype).unsqueeze(-1)
-    x = torch.cat([v0, q_att.unsqueeze(1).expand(B, N, -1) * mask], dim=-1)
+    visual = _fc(features, p, "v_relation.v2out", relu=True) if cfg.v_dim != cfg.rel_dim else features
     pre = "v_relation.implicit_relation"
-    s = _fc(x, p, pre + ".self_weights")
-    out = s
     adjs = [adj, adj.permute(0, 2, 1, 3)]
-    for d in range(cfg.dir_num):
-        a = adjs[d][:, :, :cfg.nongt_dim, :]
-        lab = _fc(a, p, pre + ".bias").squeeze(-1)
-        out = out + _att_layer(p, f"{pre}.neighbor_net.{d}", s, a.sum(-1), pos_emb, lab, cfg)
-    imp = torch.relu(out)
-    return (v0 + imp) if cfg.residual else imp
+    for _ in range(num_steps):
+        mask = (visual.sum(-1) != 0).to(visual.dtype).unsqueeze(-1)
+        x = torch.cat([visual, q_att.unsqueeze(1).expand(B, N, -1) * mask], dim=-1)
+        s = _fc(x, p, pre + ".self_weights")
+        out = s
+        for d in range(cfg.dir_num):
+            a = adjs[d][:, :, :cfg.nongt_dim, :]
+            lab = _fc(a, p, pre + ".bias").squeeze(-1)
+            out = out + _att_layer(p, f"{pre}.neighbor_net.{d}", s, a.sum(-1), pos_emb, lab, cfg)
+        imp = torch.relu(out)
+        visual = (visual + imp) if cfg.residual else imp
+    return visual
 
 
 def head(p, v1, q_last):
