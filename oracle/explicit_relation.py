@@ -34,28 +34,30 @@ def pair_bias(p, prefix, adj, nongt, dirs):
 
 def forward(p, cfg, visual, adj, question):
     """p: name -> tensor with the golden files' variable names; cfg: dict(v_dim, q_dim, out_dim, dir_num, label_num, nongt_dim,
-    num_heads, residual, label_bias).  Returns the encoder output [B, N, out_dim]."""
+    num_heads, residual, label_bias[, num_steps = 1]).  Returns the encoder output [B, N, out_dim]."""
     D, H, dirs = cfg["out_dim"], cfg["num_heads"], cfg["dir_num"]
     dh = D // H
     v = torch.relu(_fc(p, "v2out", visual)) if cfg["v_dim"] != cfg["out_dim"] else visual
     B, N, _ = v.shape
     M = min(cfg["nongt_dim"], N)
-    mask = (v.sum(-1) != 0).to(v.dtype)
-    x = torch.cat([v, mask[..., None] * question[:, None, :]], -1)
     pre = "explicit_relation"
-    s = _fc(p, pre + ".self_weights", x)
     pb = pair_bias(p, pre, adj, M, dirs)
-    total = s
-    for d in range(dirs):
-        ln = f"{pre}.neighbor_net.{d}"
-        q = _fc(p, ln + ".query", s).view(B, N, H, dh).transpose(1, 2)
-        k = _fc(p, ln + ".key", s[:, :M]).view(B, M, H, dh).transpose(1, 2)
-        kc = _wn(p, ln + ".linear_out_").reshape(D, D)               # Conv2D kernel [1,1,D,D]: head h owns output block h
-        vp = (s[:, :M] @ kc + p[ln + ".linear_out_/bias"]).view(B, M, H, dh).transpose(1, 2)
-        aff = q @ k.transpose(-1, -2) / dh ** 0.5
-        live = pb[:, d][:, None] > -1e15
-        logits = torch.where(live, aff + pb[:, d][:, None], pb[:, d][:, None].expand_as(aff))       # -9e15 absorbs aff and label in fp32/fp64 alike
-        att = torch.softmax(logits, -1)
-        total = total + (att @ vp).transpose(1, 2).reshape(B, N, D)
-    out = torch.relu(total)
-    return v + out if cfg["residual"] else out
+    for _ in range(cfg.get("num_steps", 1)):                         # relation_encoder.py:134-141: same variables every step
+        mask = (v.sum(-1) != 0).to(v.dtype)
+        x = torch.cat([v, mask[..., None] * question[:, None, :]], -1)
+        s = _fc(p, pre + ".self_weights", x)
+        total = s
+        for d in range(dirs):
+            ln = f"{pre}.neighbor_net.{d}"
+            q = _fc(p, ln + ".query", s).view(B, N, H, dh).transpose(1, 2)
+            k = _fc(p, ln + ".key", s[:, :M]).view(B, M, H, dh).transpose(1, 2)
+            kc = _wn(p, ln + ".linear_out_").reshape(D, D)           # Conv2D kernel [1,1,D,D]: head h owns output block h
+            vp = (s[:, :M] @ kc + p[ln + ".linear_out_/bias"]).view(B, M, H, dh).transpose(1, 2)
+            aff = q @ k.transpose(-1, -2) / dh ** 0.5
+            live = pb[:, d][:, None] > -1e15
+            logits = torch.where(live, aff + pb[:, d][:, None], pb[:, d][:, None].expand_as(aff))   # -9e15 absorbs aff and label in fp32/fp64 alike
+            att = torch.softmax(logits, -1)
+            total = total + (att @ vp).transpose(1, 2).reshape(B, N, D)
+        out = torch.relu(total)
+        v = v + out if cfg["residual"] else out
+    return v

@@ -26,6 +26,9 @@ CASES = {
     "spatial_small": (64, 32, 256, 2, 11, 20, 4, 3, 36, True, True),
     "semantic_dir1_nores": (512, 64, 512, 1, 15, 20, 8, 2, 24, False, False),           # v_dim == out_dim: no v2out; one direction
     "spatial_clamped_n12": (64, 32, 256, 2, 11, 20, 4, 2, 12, True, True),               # N < nongt_dim
+    # trailing element = num_steps (relation_encoder.py:134-141: the q-mask, the network and the residual add repeat on `visual`)
+    "spatial_small_steps2": (64, 32, 256, 2, 11, 20, 4, 2, 36, True, True, 2),
+    "semantic_nores_steps3": (64, 32, 256, 2, 15, 20, 4, 2, 24, False, True, 3),
 }
 
 
@@ -40,9 +43,11 @@ def main():
     from model import position_emb as ref_pe
     from oracle.make_golden_ref import _norm_name
 
-    for name, (v_dim, q_dim, out_dim, dirs, L, nongt, heads, B, N, residual, label_bias) in CASES.items():
+    for name, case in CASES.items():
+        v_dim, q_dim, out_dim, dirs, L, nongt, heads, B, N, residual, label_bias = case[:11]
+        steps = case[11] if len(case) > 11 else 1
         ref_enc.residual_connection = residual            # the one-name shim described in the module docstring
-        enc = ref_enc.ExplicitRelationEncoder(v_dim, q_dim, out_dim, dirs, L, nongt_dim=nongt, num_heads=heads, num_steps=1,
+        enc = ref_enc.ExplicitRelationEncoder(v_dim, q_dim, out_dim, dirs, L, nongt_dim=nongt, num_heads=heads, num_steps=steps,
                                               label_bias=label_bias)
         from tf_vqa_regat_b200.synthetic import explicit_param_values, make_explicit_inputs
         from tensorflow._core import Variable
@@ -63,7 +68,7 @@ def main():
             loss = tf.reduce_sum(out * tf.constant(probe, dtype=tf.float64))
         grads = tape.gradient(loss, list(enc.trainable_variables) + [tv, tq])
         rec = dict(cfg=str(dict(v_dim=v_dim, q_dim=q_dim, out_dim=out_dim, dir_num=dirs, label_num=L, nongt_dim=nongt, num_heads=heads,
-                                residual=residual, label_bias=label_bias)),
+                                residual=residual, label_bias=label_bias, **({'num_steps': steps} if steps > 1 else {}))),
                    B=B, N=N, seed=seed, input_check=np.array([visual.sum(), question.sum(), adj.sum()]),
                    param_check=np.array([float(np.sum(w.numpy())) for _, w in nw]), output=out.numpy().astype(np.float32),
                    names=np.array([_norm_name(p) for p, _ in nw]), shapes=np.array([str(s_) for s_ in shapes]))

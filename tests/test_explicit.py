@@ -29,7 +29,9 @@ def _case(path):
 
 
 def test_fixtures_exist():
-    assert len(FILES) >= 3 and any(os.path.getsize(f) for f in FILES)
+    assert len(FILES) >= 5 and any(os.path.getsize(f) for f in FILES)
+    steps = sorted(ast.literal_eval(str(np.load(f)["cfg"])).get("num_steps", 1) for f in FILES)
+    assert steps[-2:] == [2, 3]                       # the encoder's num_steps argument is covered beyond the default
 
 
 @pytest.mark.parametrize("path", FILES, ids=IDS)
@@ -69,7 +71,8 @@ def test_layer_mirror_matches_reference_execution(path):
     from tf_vqa_regat_b200.model import ExplicitRelationEncoder
     g, cfg, B, N, visual, question, adj, names, params = _case(path)
     enc = ExplicitRelationEncoder(cfg["v_dim"], cfg["q_dim"], cfg["out_dim"], cfg["dir_num"], cfg["label_num"], nongt_dim=cfg["nongt_dim"],
-                                  num_heads=cfg["num_heads"], num_steps=1, residual_connection=cfg["residual"], label_bias=cfg["label_bias"])
+                                  num_heads=cfg["num_heads"], num_steps=cfg.get("num_steps", 1), residual_connection=cfg["residual"],
+                                  label_bias=cfg["label_bias"])       # *_steps2 / *_steps3 fixtures: relation_encoder.py:134-141
     f32 = lambda a: torch.tensor(np.asarray(a, dtype=np.float32)).cuda()
     enc(f32(visual), f32(adj), f32(question))                        # creates the variables
     got_names = [n for n, _ in enc.weights]
