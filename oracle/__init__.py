@@ -27,4 +27,11 @@ Pinning status:
     tests/golden/refexec_collate.npz: the reference's own dataset.py (tensorize /
     split_entries / trim_collate) executed on an in-memory store
     (oracle/make_golden_ref_collate.py; Keras' pad_sequences restated in the stand-in).
+  * explicit relation encoders (relation_encoder.py:95-143, position_emb.py:23-90) --
+    oracle/explicit_relation.py, pinned by tests/golden/refexec_explicit_*.npz and explicit_build_graph.npz
+    (oracle/make_golden_ref_explicit.py), two cases at num_steps 2 and 3.
+  * ImplicitRelationEncoder(num_steps > 1) (relation_encoder.py:82-91) -- regat_torch.encoder(num_steps=k),
+    pinned by tests/golden/encsteps_*.npz (oracle/make_golden_ref_steps.py).
+  * learning-rate schedule / tokenizer -- tests/golden/refexec_lr_schedule.json, refexec_tokens.json
+    (oracle/make_golden_ref_schedule.py, oracle/make_golden_ref_tokens.py).
 """
